@@ -1,0 +1,151 @@
+/* C-ABI of the B200-native MRCPP operator-application path (libmrcpp_b200.so).
+ *
+ * Plain pointers and sizes only. Every entry point names the reference interface it replaces
+ * (file:line relative to the MRCPP source tree). Error convention follows the reference: hard
+ * failures print and abort() (src/utils/Printer.h:165-169); calls that can fail softly return a
+ * non-zero status. All coefficient arrays are FP64; all index arrays int32.
+ *
+ * Node layout (identical to the reference, src/utils/math_utils.cpp:223-235, MWNode.h): one node =
+ * 8 blocks of (k+1)^3 doubles; block t bit d = wavelet (compressed form) along dimension d; inside a
+ * block the x index is fastest.
+ *
+ * Node order in every array interface: slot order of the flat tree = roots in box order (x fastest),
+ * then the 8 children of each split node contiguously, in creation order (the reference's
+ * NodeAllocator serial index order, src/trees/NodeAllocator.cpp:115-216).
+ */
+#ifndef MRCPP_B200_H
+#define MRCPP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrx_mra mrx_mra;   /* MultiResolutionAnalysis<3>  (src/trees/MultiResolutionAnalysis.h:49) */
+typedef struct mrx_tree mrx_tree; /* FunctionTree<3,double>      (src/trees/FunctionTree.h)               */
+typedef struct mrx_oper mrx_oper; /* ConvolutionOperator<3> / DerivativeOperator<3> packed for HBM       */
+
+enum { MRX_TOP_DOWN = 0, MRX_BOTTOM_UP = 1 }; /* api/constants.h TopDown/BottomUp */
+
+/* counters of one apply; mirrors OperatorStatistics (src/operators/OperatorStatistics.cpp:83-106) */
+typedef struct mrx_apply_stats {
+    long long g_nodes;     /* totGCount: calcNode invocations over all refinement iterations          */
+    long long f_applied;   /* totFCount: (g,f,ft,gt,term) tuples that passed screening; x 6(k+1)^4 flop */
+    long long gen_nodes;   /* generated input nodes materialised on the device                          */
+    int iterations;        /* refinement iterations of TreeBuilder::build                               */
+    int n_nodes_out;       /* nodes of the output tree                                                  */
+    double ms_upload;      /* host->device copies of the input tree + tables                            */
+    double ms_build;       /* TreeBuilder::build loop (device kernels + host split logic)               */
+    double ms_kernel;      /* device time inside the contraction kernels only (CUDA events)             */
+    double ms_post;        /* TopDown(+=) and BottomUp transforms + norms                               */
+    double ms_download;    /* device->host copy of the result                                           */
+    long long kernel_launches; /* CUDA kernels launched by this call                                    */
+} mrx_apply_stats;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+/* Loads the filter tables (share/mwfilters subset packed by tools/pack_tables.py; replaces
+ * details::find_filters, src/utils/details.cpp:53-69) and selects the CUDA device. device < 0 keeps the
+ * library host-only (construction helpers work; every hot-path call aborts: there is no CPU fallback). */
+int mrx_init(const char *table_path, int device);
+int mrx_device_count(void);
+const char *mrx_version(void);
+
+/* ---- MRA -------------------------------------------------------------------------------------- */
+/* BoundingBox<3>(scale, corner, boxes) + InterpolatingBasis(order) + MultiResolutionAnalysis<3>(world,
+ * basis, max_depth): src/trees/MultiResolutionAnalysis.cpp:69-77, examples/poisson.cpp:24-31 */
+mrx_mra *mrx_mra_create(int order, int root_scale, const int corner[3], const int nboxes[3], int max_depth);
+void mrx_mra_destroy(mrx_mra *mra);
+
+/* ---- function trees --------------------------------------------------------------------------- */
+mrx_tree *mrx_tree_create(const mrx_mra *mra);                  /* FunctionTree<3>(MRA): empty roots        */
+void mrx_tree_destroy(mrx_tree *tree);
+int mrx_tree_n_nodes(const mrx_tree *tree);                     /* MWTree::getNNodes                        */
+int mrx_tree_n_end_nodes(const mrx_tree *tree);                 /* MWTree::getNEndNodes                     */
+double mrx_tree_square_norm(const mrx_tree *tree);              /* MWTree::getSquareNorm                    */
+void mrx_tree_clear(mrx_tree *tree);                            /* FunctionTree::clear: back to empty roots */
+
+/* Import a tree built by the reference (or anybody): arrays in slot order. child0[i] = slot of child 0
+ * or -1. Replaces nothing in the reference; it is what a binding on the MRCPP side calls with the
+ * contents of its NodeAllocator chunks (src/trees/NodeAllocator.cpp:362-415 reassemble()). */
+mrx_tree *mrx_tree_from_arrays(const mrx_mra *mra, int n_nodes, const int *scale, const int *transl /*[n][3]*/,
+                               const int *parent, const int *child0, const double *coefs /*[n][8*(k+1)^3]*/);
+/* Export: any pointer may be NULL. norms = component norms [n][8] (MWNode::getComponentNorm). Makes the
+ * host copy current first (device->host copy if the device copy is newer). */
+int mrx_tree_to_arrays(mrx_tree *tree, int *scale, int *transl, int *parent, int *child0, double *coefs, double *norms);
+/* copy_grid (src/treebuilders/grid.cpp:150-166): give `out` the node structure of `inp`, no coefs */
+int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp);
+
+/* Host-side input generator: build_grid + project of a Gaussian expansion
+ * (src/treebuilders/grid.cpp:78-123, project.cpp:85-104, ProjectionCalculator.cpp:34-51). The per-node
+ * quadrature runs on the host; with finalize != 0 the closing mwTransform(BottomUp) + calcSquareNorm
+ * (project.cpp:96-97) run on the device. finalize == 0 stops before them (no device needed): the
+ * caller owes the tree an mrx_mw_transform(BOTTOM_UP) + mrx_calc_square_norm. */
+int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
+                          const double *pos /*[n][3]*/, const int *power /*[n][3] or NULL*/, int build_grid, int finalize);
+
+/* ---- operators -------------------------------------------------------------------------------- */
+/* PoissonOperator(MRA, prec): src/operators/PoissonOperator.cpp:40-55 */
+mrx_oper *mrx_poisson_create(const mrx_mra *mra, double prec);
+/* HelmholtzOperator(MRA, mu, prec): src/operators/HelmholtzOperator.cpp:44-59 */
+mrx_oper *mrx_helmholtz_create(const mrx_mra *mra, double mu, double prec);
+/* ConvolutionOperator<3>(MRA, GaussExp<1> kernel, prec): src/operators/ConvolutionOperator.cpp:50-62 */
+mrx_oper *mrx_convolution_create(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec);
+/* ABGVOperator<3>(MRA, a, b): src/operators/ABGVOperator.cpp:46-74 */
+mrx_oper *mrx_abgv_create(const mrx_mra *mra, double a, double b);
+/* Import operator trees built by the reference: per term the [depth][transl] node cache of
+ * OperatorTree::setupOperNodeCache (src/trees/OperatorTree.cpp:200-238). max_transl[t][d] for d <
+ * n_depth[t]; mats/norms hold, term after term, depth after depth, transl = -max..max, the node's four
+ * (k+1)^2 blocks (column-major, element [i + (k+1) m]) and four component norms. */
+mrx_oper *mrx_oper_from_arrays(const mrx_mra *mra, int n_terms, const int *n_depth, const int *max_transl /* ragged, concatenated */,
+                               const double *mats, const double *norms, int oper_root, int derivative_order,
+                               double build_prec);
+void mrx_oper_destroy(mrx_oper *oper);
+int mrx_oper_n_terms(const mrx_oper *oper);                      /* MWOperator::size                        */
+/* MWOperator::calcBandWidths(prec) + getMaxBandWidth(depth): src/operators/MWOperator.cpp:63-108.
+ * widths: [n_terms][max_depth+1][5] (T,C,B,A,max), may be NULL; returns number of depths. */
+int mrx_oper_band_widths(mrx_oper *oper, double prec, int *band_max, int band_max_len);
+/* packed table introspection (tests): pointer to the 4 blocks / 4 norms of node (term, depth, transl) */
+int mrx_oper_node(const mrx_oper *oper, int term, int depth, int transl, double *mats /*4*(k+1)^2*/, double *norms /*4*/);
+int mrx_oper_depth(const mrx_oper *oper, int term);
+int mrx_oper_max_transl(const mrx_oper *oper, int term, int depth);
+/* PoissonKernel / HelmholtzKernel expansions (tests: size()==26 / 33 KATs) */
+int mrx_poisson_kernel(double epsilon, double r_min, double r_max, double *coef, double *expo, int cap);
+int mrx_helmholtz_kernel(double mu, double epsilon, double r_min, double r_max, double *coef, double *expo, int cap);
+
+/* ---- the hot path (device) -------------------------------------------------------------------- */
+/* mrcpp::apply(prec, out, oper, inp, maxIter, absPrec): src/treebuilders/apply.cpp:68-93.
+ * `out` enters with its starting grid (normally empty roots) and no coefficients. The result stays
+ * resident in HBM; mrx_tree_to_arrays / mrx_tree_sync_host bring it back. */
+int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec, mrx_apply_stats *stats);
+/* mrcpp::apply(out, DerivativeOperator, inp, dir): src/treebuilders/apply.cpp:379-412 */
+int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, mrx_apply_stats *stats);
+/* MWTree::mwTransform(type, overwrite): src/trees/MWTree.cpp:143-216 (+ norms of touched nodes) */
+int mrx_mw_transform(mrx_tree *tree, int type, int overwrite);
+/* MWTree::calcSquareNorm: src/trees/MWTree.cpp:109-118 */
+double mrx_calc_square_norm(mrx_tree *tree);
+/* mrcpp::dot(bra, ket): src/treebuilders/multiply.cpp:286-318 */
+double mrx_dot(mrx_tree *bra, mrx_tree *ket);
+/* FunctionTree::rescale(c): src/trees/FunctionTree.cpp (coefficient-wise scaling) */
+int mrx_tree_rescale(mrx_tree *tree, double c);
+
+/* residency control for measurement: host->device / device->host copies of a tree's coefficients */
+int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */
+int mrx_tree_sync_host(mrx_tree *tree);   /* download if the device copy is newer                    */
+int mrx_tree_drop_device(mrx_tree *tree); /* free the HBM copy (next use uploads again)              */
+long long mrx_tree_bytes(const mrx_tree *tree);
+
+/* Host-object handles for the test oracle (oracle/ restates the reference on the same host data
+ * model): mrx::Tree<3>* and mrx::Operator*. Not used by the product path. */
+void *mrx_tree_host_handle(mrx_tree *tree);
+void *mrx_oper_host_handle(mrx_oper *oper);
+/* tell the library that the host copy was modified through the handle (device copy becomes stale) */
+void mrx_tree_host_modified(mrx_tree *tree);
+
+/* micro-benchmarks used by bench.py for the roofline denominators (FP64 tensor pipe, HBM copy) */
+double mrx_bench_dmma_tflops(int iters);
+double mrx_bench_dfma_tflops(int iters);
+double mrx_bench_hbm_gbs(long long bytes, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,279 @@
+"""mrcpp_b200 — B200-native operator application for adaptive multiwavelet function trees.
+
+Python host mirror of the part of the MRCPP C++ API that sits on the hot path (names and argument
+meaning follow the reference: api/MRCPP/MWFunctions, MWOperators). Everything here is a thin wrapper
+over the C-ABI in include/mrcpp_b200.h; the numerics run in hand-written sm_100a kernels.
+
+    mra  = MultiResolutionAnalysis(order=7, root_scale=-4, corner=(-1,-1,-1), boxes=(2,2,2), max_depth=25)
+    f    = FunctionTree(mra); project(prec, f, GaussFunc(beta, alpha, pos))
+    P    = PoissonOperator(mra, prec)
+    g    = FunctionTree(mra); apply(prec, g, P, f)
+    e    = dot(g, f)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ApplyStats
+
+TopDown = 0   # api/constants.h
+BottomUp = 1
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class MultiResolutionAnalysis:
+    """BoundingBox<3> + InterpolatingBasis + max depth (src/trees/MultiResolutionAnalysis.h:49)."""
+
+    def __init__(self, order, root_scale=0, corner=(0, 0, 0), boxes=(1, 1, 1), max_depth=30):
+        _lib.init()
+        self.order, self.root_scale, self.corner, self.boxes, self.max_depth = order, root_scale, tuple(corner), tuple(boxes), max_depth
+        c = np.asarray(corner, dtype=np.int32)
+        b = np.asarray(boxes, dtype=np.int32)
+        self._h = _lib.load().mrx_mra_create(order, root_scale, _ip(c), _ip(b), max_depth)
+
+    @property
+    def kp1(self):
+        return self.order + 1
+
+    def lower_bounds(self):
+        return tuple(2.0 ** (-self.root_scale) * c for c in self.corner)
+
+    def upper_bounds(self):
+        return tuple(2.0 ** (-self.root_scale) * (c + b) for c, b in zip(self.corner, self.boxes))
+
+    def __del__(self):
+        try:
+            _lib.load().mrx_mra_destroy(self._h)
+        except Exception:
+            pass
+
+
+class GaussFunc:
+    """coef * prod (x-pos)^pow * exp(-beta |x-pos|^2) (src/functions/GaussFunc.h)."""
+
+    def __init__(self, beta, alpha=1.0, pos=(0.0, 0.0, 0.0), power=(0, 0, 0)):
+        self.beta, self.coef, self.pos, self.power = float(beta), float(alpha), tuple(pos), tuple(power)
+
+    def calc_coulomb_energy(self, other):
+        """GaussFunc::calcCoulombEnergy (src/functions/GaussFunc.cpp:210-237) for s-type Gaussians."""
+        import math
+        p, q = self.beta, other.beta
+        alpha = p * q / (p + q)
+        R2 = sum((a - b) ** 2 for a, b in zip(self.pos, other.pos))
+        x = alpha * R2
+        boys = 1.0 if x < 1e-14 else 0.5 * math.sqrt(math.pi / x) * math.erf(math.sqrt(x))
+        return math.sqrt(4.0 * alpha / math.pi) * boys * self.coef * other.coef * (math.pi / p) ** 1.5 * (math.pi / q) ** 1.5
+
+    def evalf(self, r):
+        r = np.asarray(r, dtype=float)
+        q = r - np.asarray(self.pos)
+        poly = np.prod(q ** np.asarray(self.power), axis=-1)
+        return self.coef * poly * np.exp(-self.beta * np.sum(q * q, axis=-1))
+
+
+class GaussExp(list):
+    """Sum of GaussFunc (src/functions/GaussExp.h)."""
+
+    def evalf(self, r):
+        return sum(g.evalf(r) for g in self)
+
+
+class FunctionTree:
+    """FunctionTree<3,double> with an HBM-resident node store (src/trees/FunctionTree.h)."""
+
+    def __init__(self, mra, _handle=None):
+        self.mra = mra
+        self._h = _handle if _handle is not None else _lib.load().mrx_tree_create(mra._h)
+
+    def __del__(self):
+        try:
+            _lib.load().mrx_tree_destroy(self._h)
+        except Exception:
+            pass
+
+    # -- reference-named accessors
+    def getNNodes(self):
+        return _lib.load().mrx_tree_n_nodes(self._h)
+
+    def getNEndNodes(self):
+        return _lib.load().mrx_tree_n_end_nodes(self._h)
+
+    def getSquareNorm(self):
+        return _lib.load().mrx_tree_square_norm(self._h)
+
+    def clear(self):
+        _lib.load().mrx_tree_clear(self._h)
+
+    def mwTransform(self, kind, overwrite=True):
+        _lib.load().mrx_mw_transform(self._h, kind, 1 if overwrite else 0)
+
+    def calcSquareNorm(self):
+        return _lib.load().mrx_calc_square_norm(self._h)
+
+    def rescale(self, c):
+        _lib.load().mrx_tree_rescale(self._h, float(c))
+
+    # -- array interface
+    @classmethod
+    def from_arrays(cls, mra, scale, transl, parent, child0, coefs):
+        scale = np.ascontiguousarray(scale, dtype=np.int32)
+        transl = np.ascontiguousarray(transl, dtype=np.int32)
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        child0 = np.ascontiguousarray(child0, dtype=np.int32)
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+        h = _lib.load().mrx_tree_from_arrays(mra._h, len(scale), _ip(scale), _ip(transl), _ip(parent), _ip(child0), _dp(coefs))
+        return cls(mra, _handle=h)
+
+    def to_arrays(self, coefs=True):
+        n = self.getNNodes()
+        K = self.mra.kp1
+        out = {
+            "scale": np.zeros(n, dtype=np.int32),
+            "transl": np.zeros((n, 3), dtype=np.int32),
+            "parent": np.zeros(n, dtype=np.int32),
+            "child0": np.zeros(n, dtype=np.int32),
+            "norms": np.zeros((n, 8), dtype=np.float64),
+        }
+        cp = None
+        if coefs:
+            out["coefs"] = np.zeros((n, 8 * K ** 3), dtype=np.float64)
+            cp = _dp(out["coefs"])
+        _lib.load().mrx_tree_to_arrays(self._h, _ip(out["scale"]), _ip(out["transl"]), _ip(out["parent"]), _ip(out["child0"]),
+                                       cp, _dp(out["norms"]))
+        return out
+
+    def sync_device(self):
+        _lib.load().mrx_tree_sync_device(self._h)
+
+    def sync_host(self):
+        _lib.load().mrx_tree_sync_host(self._h)
+
+    def drop_device(self):
+        _lib.load().mrx_tree_drop_device(self._h)
+
+    def nbytes(self):
+        return _lib.load().mrx_tree_bytes(self._h)
+
+
+class _Operator:
+    def __init__(self, mra, handle):
+        self.mra = mra
+        self._h = handle
+
+    def __del__(self):
+        try:
+            _lib.load().mrx_oper_destroy(self._h)
+        except Exception:
+            pass
+
+    def size(self):
+        return _lib.load().mrx_oper_n_terms(self._h)
+
+    def band_widths(self, prec):
+        """getMaxBandWidth(depth) for every depth after calcBandWidths(prec) (MWOperator.cpp:63-108)."""
+        buf = np.zeros(64, dtype=np.int32)
+        n = _lib.load().mrx_oper_band_widths(self._h, float(prec), _ip(buf), 64)
+        return buf[:n].copy()
+
+    def node(self, term, depth, transl):
+        K = self.mra.kp1
+        mats = np.zeros((4, K * K))
+        norms = np.zeros(4)
+        rc = _lib.load().mrx_oper_node(self._h, term, depth, transl, _dp(mats), _dp(norms))
+        if rc != 0:
+            raise IndexError((term, depth, transl))
+        return mats, norms
+
+
+class PoissonOperator(_Operator):
+    """src/operators/PoissonOperator.cpp:40-55"""
+
+    def __init__(self, mra, prec):
+        _lib.init()
+        super().__init__(mra, _lib.load().mrx_poisson_create(mra._h, float(prec)))
+
+
+class HelmholtzOperator(_Operator):
+    """src/operators/HelmholtzOperator.cpp:44-59"""
+
+    def __init__(self, mra, mu, prec):
+        _lib.init()
+        super().__init__(mra, _lib.load().mrx_helmholtz_create(mra._h, float(mu), float(prec)))
+
+
+class ConvolutionOperator(_Operator):
+    """ConvolutionOperator<3>(mra, GaussExp<1>, prec): src/operators/ConvolutionOperator.cpp:50-62"""
+
+    def __init__(self, mra, coefs, expos, prec):
+        _lib.init()
+        c = np.ascontiguousarray(coefs, dtype=np.float64)
+        e = np.ascontiguousarray(expos, dtype=np.float64)
+        super().__init__(mra, _lib.load().mrx_convolution_create(mra._h, len(c), _dp(c), _dp(e), float(prec)))
+
+
+class ABGVOperator(_Operator):
+    """src/operators/ABGVOperator.cpp:46-74"""
+
+    def __init__(self, mra, a, b):
+        _lib.init()
+        super().__init__(mra, _lib.load().mrx_abgv_create(mra._h, float(a), float(b)))
+
+
+def poisson_kernel(epsilon, r_min, r_max):
+    c = np.zeros(1000)
+    e = np.zeros(1000)
+    n = _lib.load().mrx_poisson_kernel(epsilon, r_min, r_max, _dp(c), _dp(e), 1000)
+    return c[:n].copy(), e[:n].copy()
+
+
+def helmholtz_kernel(mu, epsilon, r_min, r_max):
+    c = np.zeros(1000)
+    e = np.zeros(1000)
+    n = _lib.load().mrx_helmholtz_kernel(mu, epsilon, r_min, r_max, _dp(c), _dp(e), 1000)
+    return c[:n].copy(), e[:n].copy()
+
+
+def _gauss_arrays(func):
+    funcs = list(func) if isinstance(func, (list, tuple)) else [func]
+    coef = np.array([g.coef for g in funcs], dtype=np.float64)
+    alpha = np.array([g.beta for g in funcs], dtype=np.float64)
+    pos = np.ascontiguousarray([g.pos for g in funcs], dtype=np.float64)
+    power = np.ascontiguousarray([g.power for g in funcs], dtype=np.int32)
+    return len(funcs), coef, alpha, pos, power
+
+
+def project(prec, out, func, build_grid=True, finalize=True):
+    """build_grid + project of a Gaussian (expansion): src/treebuilders/project.cpp:85-104, grid.cpp:78-123."""
+    n, coef, alpha, pos, power = _gauss_arrays(func)
+    _lib.load().mrx_project_gaussians(out._h, float(prec), n, _dp(coef), _dp(alpha), _dp(pos), _ip(power),
+                                      1 if build_grid else 0, 1 if finalize else 0)
+
+
+def copy_grid(out, inp):
+    """src/treebuilders/grid.cpp:150-166"""
+    _lib.load().mrx_tree_copy_grid(out._h, inp._h)
+
+
+def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None):
+    """mrcpp::apply. ConvolutionOperator form: apply(prec, out, oper, inp, maxIter, absPrec)
+    (src/treebuilders/apply.cpp:68-93); derivative form: apply(None, out, D, inp, dir=d) (:379-412).
+    Returns the work counters (OperatorStatistics)."""
+    st = ApplyStats()
+    if dir is not None:
+        _lib.load().mrx_apply_derivative(out._h, oper._h, inp._h, int(dir), C.byref(st))
+    else:
+        _lib.load().mrx_apply(float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, C.byref(st))
+    return st
+
+
+def dot(bra, ket):
+    """src/treebuilders/multiply.cpp:286-318"""
+    return _lib.load().mrx_dot(bra._h, ket._h)

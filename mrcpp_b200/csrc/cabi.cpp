@@ -1,0 +1,335 @@
+// C-ABI entry points (include/mrcpp_b200.h). Host-side object management lives here; every hot-path
+// call forwards to the CUDA engine and aborts when no device was selected (no CPU fallback).
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "engine.hpp"
+
+using namespace mrx;
+
+namespace {
+bool g_device_on = false;
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+long long g_launches = 0;
+} // namespace
+
+namespace mrx {
+bool device_enabled() { return g_device_on; }
+void require_device(const char *what) {
+    if (!g_device_on) MRX_ABORT(std::string(what) + ": no CUDA device selected (mrx_init device<0); there is no CPU fallback");
+}
+cudaStream_t stream() { return g_stream; }
+long long &launch_counter() { return g_launches; }
+} // namespace mrx
+
+extern "C" {
+
+const char *mrx_version(void) { return "mrcpp_b200 0.1 (sm_100a)"; }
+
+int mrx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mrx_init(const char *table_path, int device) {
+    if (table_path && table_path[0]) set_table_path(table_path);
+    if (device >= 0) {
+        int n = mrx_device_count();
+        if (device >= n) {
+            std::fprintf(stderr, "mrx_init: CUDA device %d requested but %d visible\n", device, n);
+            return 1;
+        }
+        if (cudaSetDevice(device) != cudaSuccess) return 2;
+        if (!g_stream) {
+            if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return 3;
+        }
+        g_device = device;
+        g_device_on = true;
+    }
+    return 0;
+}
+
+mrx_mra *mrx_mra_create(int order, int root_scale, const int corner[3], const int nboxes[3], int max_depth) {
+    auto *m = new mrx_mra;
+    m->m.order = order;
+    m->m.rootScale = root_scale;
+    for (int d = 0; d < 3; d++) {
+        m->m.corner[d] = corner[d];
+        m->m.nboxes[d] = nboxes[d];
+    }
+    m->m.maxDepth = max_depth;
+    if (order < 1 || order > MaxOrder) MRX_ABORT("Invalid scaling order");
+    if (m->m.maxDepth > MaxDepth) MRX_ABORT("Beyond MaxDepth");
+    if (m->m.maxScale() > MaxScale) MRX_ABORT("Beyond MaxScale");
+    return m;
+}
+void mrx_mra_destroy(mrx_mra *mra) { delete mra; }
+
+mrx_tree *mrx_tree_create(const mrx_mra *mra) { return new mrx_tree(mra->m); }
+void mrx_tree_destroy(mrx_tree *tree) { delete tree; }
+int mrx_tree_n_nodes(const mrx_tree *tree) { return tree->host.nReal; }
+int mrx_tree_n_end_nodes(const mrx_tree *tree) {
+    std::vector<int> e;
+    tree->host.endNodeTable(e);
+    return (int)e.size();
+}
+double mrx_tree_square_norm(const mrx_tree *tree) { return tree->host.squareNorm; }
+void mrx_tree_clear(mrx_tree *tree) {
+    tree->host.deleteGenerated();
+    tree->host.clearToRoots();
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    tree->dev.nNodes = 0;
+    tree->dev.nGen = 0;
+}
+long long mrx_tree_bytes(const mrx_tree *tree) { return (long long)tree->host.nReal * tree->host.ncoef * 8; }
+
+mrx_tree *mrx_tree_from_arrays(const mrx_mra *mra, int n_nodes, const int *scale, const int *transl, const int *parent,
+                               const int *child0, const double *coefs) {
+    auto *t = new mrx_tree(mra->m);
+    Tree<3> &h = t->host;
+    if (n_nodes < h.nRoots) MRX_ABORT("tree_from_arrays: fewer nodes than root boxes");
+    // replay the splits in slot order of the children
+    std::vector<std::pair<int, int>> splits;
+    for (int n = 0; n < n_nodes; n++)
+        if (child0[n] >= 0) splits.push_back({child0[n], n});
+    std::sort(splits.begin(), splits.end());
+    for (auto &s : splits) {
+        if (s.second >= h.size()) MRX_ABORT("tree_from_arrays: parent slot after its children");
+        int c0 = h.createChildren(s.second, false);
+        if (c0 != s.first) MRX_ABORT("tree_from_arrays: children must be contiguous in creation order");
+    }
+    if (h.size() != n_nodes) MRX_ABORT("tree_from_arrays: node count mismatch");
+    for (int n = 0; n < n_nodes; n++) {
+        if (h.nodes[n].scale != scale[n]) MRX_ABORT("tree_from_arrays: scale mismatch");
+        for (int d = 0; d < 3; d++)
+            if (h.nodes[n].l[d] != transl[3 * n + d]) MRX_ABORT("tree_from_arrays: translation mismatch");
+        if (parent && h.nodes[n].parent != parent[n]) MRX_ABORT("tree_from_arrays: parent mismatch");
+        if (coefs) {
+            std::memcpy(h.coef(n), coefs + (size_t)n * h.ncoef, sizeof(double) * h.ncoef);
+            h.nodes[n].flags |= FlagHasCoefs;
+            h.calcNorms(n);
+        }
+    }
+    if (coefs) h.calcSquareNorm();
+    return t;
+}
+
+int mrx_tree_to_arrays(mrx_tree *tree, int *scale, int *transl, int *parent, int *child0, double *coefs, double *norms) {
+    Tree<3> &h = tree->host;
+    if (coefs && !tree->hostCoefsValid) mrx_tree_sync_host(tree);
+    for (int n = 0; n < h.nReal; n++) {
+        if (scale) scale[n] = h.nodes[n].scale;
+        if (transl)
+            for (int d = 0; d < 3; d++) transl[3 * n + d] = h.nodes[n].l[d];
+        if (parent) parent[n] = h.nodes[n].parent;
+        if (child0) child0[n] = (h.nodes[n].child0 >= 0 && h.nodes[n].child0 < h.nReal) ? h.nodes[n].child0 : -1;
+        if (coefs) std::memcpy(coefs + (size_t)n * h.ncoef, h.coef(n), sizeof(double) * h.ncoef);
+        if (norms)
+            for (int t = 0; t < 8; t++) norms[(size_t)n * 8 + t] = h.cnorm[(size_t)n * 8 + t];
+    }
+    return 0;
+}
+
+int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp) {
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    out->host.copyGridFrom(inp->host);
+    out->hostCoefsValid = true;
+    out->devValid = false;
+    out->dev.nNodes = 0;
+    return 0;
+}
+
+int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
+                          const double *pos, const int *power, int do_build_grid, int finalize) {
+    if (finalize) require_device("mrx_project_gaussians (final BottomUp transform)");
+    GaussExp<3> gexp(n_gauss);
+    for (int i = 0; i < n_gauss; i++) {
+        gexp[i].coef = coef[i];
+        gexp[i].alpha = alpha[i];
+        for (int d = 0; d < 3; d++) {
+            gexp[i].pos[d] = pos[3 * i + d];
+            gexp[i].power[d] = power ? power[3 * i + d] : 0;
+        }
+    }
+    Tree<3> &h = tree->host;
+    if (do_build_grid) build_grid<3>(h, gexp, -1);
+    auto f = [&gexp](const double *r) {
+        double s = 0.0;
+        for (const auto &g : gexp) s += g.evalf(r);
+        return s;
+    };
+    project<3>(prec, h, f, -1, false, /*finalize=*/false);
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    // project.cpp:96-97: out.mwTransform(BottomUp); out.calcSquareNorm() -- on the device
+    if (finalize) {
+        mrx_mw_transform(tree, MRX_BOTTOM_UP, 1);
+        mrx_calc_square_norm(tree);
+    }
+    return 0;
+}
+
+// ---- operators
+mrx_oper *mrx_poisson_create(const mrx_mra *mra, double prec) {
+    auto *o = new mrx_oper;
+    o->op = build_poisson_operator(mra->m, prec);
+    return o;
+}
+mrx_oper *mrx_helmholtz_create(const mrx_mra *mra, double mu, double prec) {
+    auto *o = new mrx_oper;
+    o->op = build_helmholtz_operator(mra->m, mu, prec);
+    return o;
+}
+mrx_oper *mrx_convolution_create(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec) {
+    GaussExp<1> kernel(n_terms);
+    for (int i = 0; i < n_terms; i++) {
+        kernel[i].coef = coef[i];
+        kernel[i].alpha = expo[i];
+    }
+    auto *o = new mrx_oper;
+    o->op = build_convolution_operator(mra->m, kernel, prec / 10.0, prec);
+    return o;
+}
+mrx_oper *mrx_abgv_create(const mrx_mra *mra, double a, double b) {
+    auto *o = new mrx_oper;
+    o->op = build_abgv_operator(mra->m, a, b);
+    return o;
+}
+mrx_oper *mrx_oper_from_arrays(const mrx_mra *mra, int n_terms, const int *n_depth, const int *max_transl, const double *mats,
+                               const double *norms, int oper_root, int derivative_order, double build_prec) {
+    auto *o = new mrx_oper;
+    Operator &op = o->op;
+    op.k = mra->m.order;
+    op.K = op.k + 1;
+    op.operRoot = oper_root;
+    op.derivative = derivative_order > 0;
+    op.order = derivative_order;
+    op.buildPrec = build_prec;
+    op.terms.resize(n_terms);
+    size_t mt_pos = 0, node_pos = 0;
+    const size_t stride = (size_t)4 * op.K * op.K;
+    for (int t = 0; t < n_terms; t++) {
+        OperTerm &term = op.terms[t];
+        term.nDepth = n_depth[t];
+        term.matStride = stride;
+        term.maxTransl.assign(max_transl + mt_pos, max_transl + mt_pos + n_depth[t]);
+        mt_pos += n_depth[t];
+        term.offset.resize(n_depth[t]);
+        size_t total = 0;
+        for (int d = 0; d < n_depth[t]; d++) {
+            term.offset[d] = total;
+            total += 2 * (size_t)term.maxTransl[d] + 1;
+        }
+        term.mats.assign(mats + node_pos * stride, mats + (node_pos + total) * stride);
+        term.norms.assign(norms + node_pos * 4, norms + (node_pos + total) * 4);
+        node_pos += total;
+    }
+    return o;
+}
+void mrx_oper_destroy(mrx_oper *oper) { delete oper; }
+int mrx_oper_n_terms(const mrx_oper *oper) { return oper->op.size(); }
+int mrx_oper_band_widths(mrx_oper *oper, double prec, int *band_max, int band_max_len) {
+    oper->op.calcBandWidths(prec);
+    int n = (int)oper->op.bandMax.size();
+    if (band_max)
+        for (int i = 0; i < n && i < band_max_len; i++) band_max[i] = oper->op.bandMax[i];
+    oper->op.clearBandWidths();
+    return n;
+}
+int mrx_oper_depth(const mrx_oper *oper, int term) { return oper->op.terms[term].nDepth; }
+int mrx_oper_max_transl(const mrx_oper *oper, int term, int depth) { return oper->op.terms[term].maxTransl[depth]; }
+int mrx_oper_node(const mrx_oper *oper, int term, int depth, int transl, double *mats, double *norms) {
+    const OperTerm &t = oper->op.terms[term];
+    if (depth < 0 || depth >= t.nDepth || std::abs(transl) > t.maxTransl[depth]) return 1;
+    if (mats) std::memcpy(mats, t.node(depth, transl), sizeof(double) * t.matStride);
+    if (norms) std::memcpy(norms, t.nodeNorms(depth, transl), sizeof(double) * 4);
+    return 0;
+}
+int mrx_poisson_kernel(double epsilon, double r_min, double r_max, double *coef, double *expo, int cap) {
+    GaussExp<1> k = poisson_kernel(epsilon, r_min, r_max);
+    for (int i = 0; i < (int)k.size() && i < cap; i++) {
+        if (coef) coef[i] = k[i].coef;
+        if (expo) expo[i] = k[i].alpha;
+    }
+    return (int)k.size();
+}
+int mrx_helmholtz_kernel(double mu, double epsilon, double r_min, double r_max, double *coef, double *expo, int cap) {
+    GaussExp<1> k = helmholtz_kernel(mu, epsilon, r_min, r_max);
+    for (int i = 0; i < (int)k.size() && i < cap; i++) {
+        if (coef) coef[i] = k[i].coef;
+        if (expo) expo[i] = k[i].alpha;
+    }
+    return (int)k.size();
+}
+
+// ---- hot path
+int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec, mrx_apply_stats *stats) {
+    require_device("mrx_apply");
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (oper->op.derivative) MRX_ABORT("mrx_apply: derivative operator passed to the convolution apply");
+    device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats);
+    return 0;
+}
+int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, mrx_apply_stats *stats) {
+    require_device("mrx_apply_derivative");
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (dir < 0 || dir >= 3) MRX_ABORT("Invalid apply dir");
+    if (!oper->op.derivative) MRX_ABORT("mrx_apply_derivative: not a derivative operator");
+    device_apply_derivative(*out, *oper, *inp, dir, stats);
+    return 0;
+}
+int mrx_mw_transform(mrx_tree *tree, int type, int overwrite) {
+    require_device("mrx_mw_transform");
+    if (type == MRX_BOTTOM_UP && !overwrite) MRX_ABORT("BottomUp without overwrite is not implemented (MWTree.cpp:148)");
+    if (type != MRX_BOTTOM_UP && type != MRX_TOP_DOWN) MRX_ABORT("Invalid wavelet transform");
+    device_mw_transform(*tree, type, overwrite != 0);
+    return 0;
+}
+double mrx_calc_square_norm(mrx_tree *tree) {
+    require_device("mrx_calc_square_norm");
+    device_calc_norms_all(*tree);
+    tree->host.calcSquareNorm();
+    return tree->host.squareNorm;
+}
+double mrx_dot(mrx_tree *bra, mrx_tree *ket) {
+    require_device("mrx_dot");
+    if (!(bra->host.mra == ket->host.mra)) MRX_ABORT("Incompatible MRA");
+    return device_dot(*bra, *ket);
+}
+int mrx_tree_rescale(mrx_tree *tree, double c) {
+    require_device("mrx_tree_rescale");
+    device_rescale(*tree, c);
+    return 0;
+}
+int mrx_tree_sync_device(mrx_tree *tree) {
+    require_device("mrx_tree_sync_device");
+    if (!tree->devValid) tree_upload(*tree);
+    return 0;
+}
+int mrx_tree_sync_host(mrx_tree *tree) {
+    if (tree->hostCoefsValid) return 0;
+    require_device("mrx_tree_sync_host");
+    tree_download(*tree);
+    return 0;
+}
+int mrx_tree_drop_device(mrx_tree *tree) {
+    if (!tree->hostCoefsValid) mrx_tree_sync_host(tree);
+    tree_drop_device(*tree);
+    return 0;
+}
+
+void *mrx_tree_host_handle(mrx_tree *tree) { return &tree->host; }
+void *mrx_oper_host_handle(mrx_oper *oper) { return &oper->op; }
+void mrx_tree_host_modified(mrx_tree *tree) {
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    tree->dev.nNodes = 0;
+}
+}

@@ -1,0 +1,230 @@
+// HBM-resident node store: upload/download, whole-tree two-scale transforms (level-synchronous),
+// component norms, dot product, rescale, operator-table packing.
+//
+// Reference functions replaced here (file:line relative to the MRCPP tree):
+//   MWTree::mwTransformDown / mwTransformUp          src/trees/MWTree.cpp:166-216
+//   MWNode::giveChildrenCoefs / reCompress<3>        src/trees/MWNode.cpp:312-335, FunctionNode.cpp:391-410
+//   tree_utils::mw_transform / mw_transform_back     src/utils/tree_utils.cpp:113-301
+//   math_utils::apply_filter                         src/utils/math_utils.cpp:175-194
+//   MWNode::calcNorms / calcComponentNorm            src/trees/MWNode.cpp:609-616, :643-655
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "../engine.hpp"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mrx {
+
+// ---- filter tables per order, device resident: [op][idx][K*K] row-major F(i,j)
+const double *device_filters(int k) {
+    static std::map<int, double *> cache;
+    auto it = cache.find(k);
+    if (it != cache.end()) return it->second;
+    const FilterSet &fs = filter_set(k);
+    int K = k + 1;
+    std::vector<double> h((size_t)8 * K * K);
+    for (int op = 0; op < 2; op++)
+        for (int i = 0; i < 4; i++) std::memcpy(h.data() + (size_t)(op * 4 + i) * K * K, fs.sub[op][i].data(), sizeof(double) * K * K);
+    double *d = nullptr;
+    MRX_CUDA(cudaMalloc(&d, h.size() * sizeof(double)));
+    MRX_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cache[k] = d;
+    return d;
+}
+
+void tree_upload(mrx_tree &t) {
+    require_device("tree_upload");
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    int n = h.nReal;
+    t.dev.coefs.reserve((size_t)n * h.ncoef, false, st);
+    t.dev.norms.reserve((size_t)n * 8, false, st);
+    // host chunks are 64 nodes each
+    for (int s = 0; s < n; s += 64) {
+        int cnt = std::min(64, n - s);
+        MRX_CUDA(cudaMemcpyAsync(t.dev.coefs.p + (size_t)s * h.ncoef, h.coef(s), sizeof(double) * (size_t)cnt * h.ncoef,
+                                 cudaMemcpyHostToDevice, st));
+    }
+    MRX_CUDA(cudaMemcpyAsync(t.dev.norms.p, h.cnorm.data(), sizeof(double) * (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    t.dev.nNodes = n;
+    t.dev.nGen = 0;
+    t.devValid = true;
+}
+
+void tree_download(mrx_tree &t) {
+    require_device("tree_download");
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    int n = h.nReal;
+    if (!t.devValid || t.dev.nNodes < n) MRX_ABORT("tree_download: device copy is not current");
+    h.ensureCoefStorage();
+    for (int s = 0; s < n; s += 64) {
+        int cnt = std::min(64, n - s);
+        MRX_CUDA(cudaMemcpyAsync(h.coef(s), t.dev.coefs.p + (size_t)s * h.ncoef, sizeof(double) * (size_t)cnt * h.ncoef,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    MRX_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) h.nodes[i].flags |= FlagHasCoefs;
+    t.hostCoefsValid = true;
+}
+
+void tree_drop_device(mrx_tree &t) {
+    t.dev.coefs.release();
+    t.dev.norms.release();
+    t.dev.genCoefs.release();
+    t.dev.genNorms.release();
+    t.dev.nNodes = 0;
+    t.dev.nGen = 0;
+    t.devValid = false;
+}
+
+// norms of every real node on the device -> host cnorm / sqn (MWNode::calcNorms)
+void device_calc_norms_all(mrx_tree &t) {
+    require_device("device_calc_norms_all");
+    if (!t.devValid) tree_upload(t);
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    int n = h.nReal;
+    launch_norms(t.dev.coefs.p, t.dev.norms.p, nullptr, n, h.Kd, st);
+    MRX_CUDA(cudaMemcpyAsync(h.cnorm.data(), t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) {
+        double sq = 0.0;
+        for (int c = 0; c < 8; c++) sq += h.cnorm[(size_t)i * 8 + c] * h.cnorm[(size_t)i * 8 + c];
+        h.sqn[i] = sq;
+    }
+}
+
+void device_mw_transform(mrx_tree &t, int type, bool overwrite) {
+    require_device("device_mw_transform");
+    if (!t.devValid) tree_upload(t);
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    // level lists of branch nodes, in the reference's per-depth node-table order
+    std::vector<std::vector<int>> table;
+    h.nodeTableByDepth(table);
+    std::vector<int> flat;
+    std::vector<int> levelOff(table.size() + 1, 0);
+    for (size_t d = 0; d < table.size(); d++) {
+        for (int n : table[d])
+            if (h.isBranch(n) && !h.isGen(h.nodes[n].child0)) {
+                flat.push_back(n);
+                flat.push_back(h.nodes[n].child0);
+            }
+        levelOff[d + 1] = (int)flat.size() / 2;
+    }
+    if (flat.empty()) {
+        device_calc_norms_all(t);
+        return;
+    }
+    DevBuf<int> pairs;
+    pairs.reserve(flat.size(), false, st);
+    MRX_CUDA(cudaMemcpyAsync(pairs.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
+    const double *filt = device_filters(h.k);
+    if (type == MRX_TOP_DOWN) {
+        for (size_t d = 0; d < table.size(); d++) {
+            int cnt = levelOff[d + 1] - levelOff[d];
+            if (cnt > 0)
+                launch_transform(true, overwrite, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
+        }
+    } else {
+        for (int d = (int)table.size() - 1; d >= 0; d--) {
+            int cnt = levelOff[d + 1] - levelOff[d];
+            if (cnt > 0)
+                launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
+        }
+    }
+    MRX_CUDA(cudaStreamSynchronize(st));
+    t.devValid = true;
+    t.hostCoefsValid = false;
+    device_calc_norms_all(t);
+}
+
+double device_dot(mrx_tree &bra, mrx_tree &ket) {
+    if (!bra.devValid) tree_upload(bra);
+    if (!ket.devValid) tree_upload(ket);
+    const Tree<3> &a = bra.host, &b = ket.host;
+    cudaStream_t st = stream();
+    // pairs of nodes present in both trees (multiply.cpp:286-318 walks the same intersection)
+    std::vector<int> pairs;
+    std::vector<std::pair<int, int>> stack;
+    for (int r = a.nRoots - 1; r >= 0; r--) stack.push_back({r, r});
+    while (!stack.empty()) {
+        auto pr = stack.back();
+        stack.pop_back();
+        pairs.push_back(pr.first);
+        pairs.push_back(pr.second);
+        bool aB = a.isBranch(pr.first) && !a.isGen(a.nodes[pr.first].child0);
+        bool bB = b.isBranch(pr.second) && !b.isGen(b.nodes[pr.second].child0);
+        if (aB && bB)
+            for (int c = 7; c >= 0; c--) stack.push_back({a.nodes[pr.first].child0 + c, b.nodes[pr.second].child0 + c});
+    }
+    int np = (int)pairs.size() / 2;
+    DevBuf<int> dpairs;
+    DevBuf<double> dres;
+    dpairs.reserve(pairs.size(), false, st);
+    dres.reserve(np, false, st);
+    MRX_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(int) * pairs.size(), cudaMemcpyHostToDevice, st));
+    launch_dot(bra.dev.coefs.p, ket.dev.coefs.p, dpairs.p, dres.p, np, a.nRoots, a.Kd, st);
+    std::vector<double> res(np);
+    MRX_CUDA(cudaMemcpyAsync(res.data(), dres.p, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    double s = 0.0;
+    for (double v : res) s += v;
+    return s;
+}
+
+void device_rescale(mrx_tree &t, double c) {
+    if (!t.devValid) tree_upload(t);
+    cudaStream_t st = stream();
+    launch_scale(t.dev.coefs.p, (size_t)t.host.nReal * t.host.ncoef, c, st);
+    MRX_CUDA(cudaStreamSynchronize(st));
+    t.hostCoefsValid = false;
+    device_calc_norms_all(t);
+    t.host.calcSquareNorm();
+}
+
+// pack the [term][depth][transl] operator tables once into HBM
+void oper_upload(mrx_oper &o) {
+    require_device("oper_upload");
+    if (o.dev.tablesValid) return;
+    cudaStream_t st = stream();
+    Operator &op = o.op;
+    int M = op.size(), DM = 0;
+    for (auto &t : op.terms) DM = std::max(DM, t.nDepth);
+    size_t totalNodes = 0;
+    o.dev.termNodeBase.assign(M, 0);
+    for (int i = 0; i < M; i++) {
+        o.dev.termNodeBase[i] = totalNodes;
+        totalNodes += op.terms[i].norms.size() / 4;
+    }
+    const size_t stride = (size_t)4 * op.K * op.K;
+    std::vector<double> mats(totalNodes * stride), norms(totalNodes * 4);
+    std::vector<int> nodeOff((size_t)M * DM, -1), maxT((size_t)M * DM, 0);
+    for (int i = 0; i < M; i++) {
+        const OperTerm &t = op.terms[i];
+        std::memcpy(mats.data() + o.dev.termNodeBase[i] * stride, t.mats.data(), sizeof(double) * t.mats.size());
+        std::memcpy(norms.data() + o.dev.termNodeBase[i] * 4, t.norms.data(), sizeof(double) * t.norms.size());
+        for (int d = 0; d < t.nDepth; d++) {
+            nodeOff[(size_t)i * DM + d] = (int)(o.dev.termNodeBase[i] + t.offset[d]);
+            maxT[(size_t)i * DM + d] = t.maxTransl[d];
+        }
+    }
+    o.dev.mats.reserve(mats.size(), false, st);
+    o.dev.norms.reserve(norms.size(), false, st);
+    o.dev.nodeOff.reserve(nodeOff.size(), false, st);
+    o.dev.maxTransl.reserve(maxT.size(), false, st);
+    MRX_CUDA(cudaMemcpyAsync(o.dev.mats.p, mats.data(), sizeof(double) * mats.size(), cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaMemcpyAsync(o.dev.norms.p, norms.data(), sizeof(double) * norms.size(), cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaMemcpyAsync(o.dev.nodeOff.p, nodeOff.data(), sizeof(int) * nodeOff.size(), cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaMemcpyAsync(o.dev.maxTransl.p, maxT.data(), sizeof(int) * maxT.size(), cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    o.dev.M = M;
+    o.dev.DM = DM;
+    o.dev.tablesValid = true;
+}
+
+} // namespace mrx

@@ -1,0 +1,221 @@
+// Tree-maintenance kernels: two-scale filter passes (generic order), generated children, norms, dot.
+//
+// One CTA per parent node. A node is 8 blocks of K^3 doubles; each of the three passes applies the
+// 2K x 2K two-scale filter along one dimension (math_utils::apply_filter, math_utils.cpp:175-194:
+// out(K^2 x K) (+)= in(K x K^2)^T F), contracting the fastest index and making it the slowest, so
+// after three passes the layout is restored. Blocks are staged in shared memory with one pad word
+// per K elements so that the strided reads of a pass are bank-conflict free.
+//
+// Algorithmic traffic per node: read 8 K^3 + write 8 K^3 doubles = 128 K^3 bytes.
+#include "../engine.hpp"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mrx {
+
+namespace {
+
+constexpr int kTransformThreads = 256;
+
+// MODE 0: TopDown (parent -> children scaling, = or +=); 1: BottomUp (children scaling -> parent);
+// MODE 2: generated children of an input-tree node (scaling only, separate pool) + their norms.
+template <int MODE>
+__global__ void __launch_bounds__(kTransformThreads)
+transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoefs, double *__restrict__ genCoefs,
+                 double *__restrict__ genNorms, int nReal, const int *__restrict__ pairs, int K, int padOn,
+                 const double *__restrict__ filters, int overwrite) {
+    extern __shared__ double sm[];
+    const int K2 = K * K, Kd = K2 * K, ncoef = 8 * Kd;
+    const int KdP = padOn ? (Kd + K2) : Kd;
+    const int rowS = padOn ? (K + 1) : K;
+    double *A = sm;
+    double *B = sm + 8 * KdP;
+    double *F = B + 8 * KdP;
+    const int parent = pairs[2 * blockIdx.x];
+    const int child0 = pairs[2 * blockIdx.x + 1];
+    const int tid = threadIdx.x;
+
+    const int op = (MODE == 1) ? 0 : 1; // Compression : Reconstruction
+    for (int i = tid; i < 4 * K2; i += kTransformThreads) F[i] = filters[(size_t)op * 4 * K2 + i];
+
+    for (int o = tid; o < 8 * Kd; o += kTransformThreads) {
+        int t = o / Kd, rem = o - t * Kd;
+        double v;
+        if (MODE == 0) {
+            v = coefs[(size_t)parent * ncoef + o];
+        } else if (MODE == 1) {
+            v = coefs[(size_t)(child0 + t) * ncoef + rem];
+        } else {
+            if (parent < nReal) v = realCoefs[(size_t)parent * ncoef + o];
+            else v = (t == 0) ? genCoefs[(size_t)(parent - nReal) * Kd + rem] : 0.0;
+        }
+        A[t * KdP + (padOn ? rem + rem / K : rem)] = v;
+    }
+    __syncthreads();
+
+    double *in = A, *out = B;
+    for (int pass = 0; pass < 3; pass++) {
+        for (int o = tid; o < 8 * Kd; o += kTransformThreads) {
+            int gt = o / Kd, rem = o - gt * Kd;
+            int j = rem / K2, m = rem - j * K2;
+            int gbit = (gt >> pass) & 1;
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                int ft = (gt & ~(1 << pass)) | (b << pass);
+                const double *inb = in + ft * KdP + m * rowS;
+                const double *Fm = F + (2 * gbit + b) * K2 + j;
+                for (int t = 0; t < K; t++) acc = fma(inb[t], Fm[t * K], acc);
+            }
+            if (pass < 2) {
+                out[gt * KdP + (padOn ? rem + rem / K : rem)] = acc;
+            } else if (MODE == 0) {
+                double *dst = coefs + (size_t)(child0 + gt) * ncoef + rem;
+                if (overwrite) *dst = acc;
+                else *dst += acc;
+            } else if (MODE == 1) {
+                coefs[(size_t)parent * ncoef + o] = acc;
+            } else {
+                genCoefs[(size_t)(child0 - nReal + gt) * Kd + rem] = acc;
+                out[gt * KdP + (padOn ? rem + rem / K : rem)] = acc;
+            }
+        }
+        __syncthreads();
+        double *tmp = in;
+        in = out;
+        out = tmp;
+    }
+    if (MODE == 0 && overwrite) {
+        // giveChildrenCoefs(overwrite=true) zeroes the children first (MWNode.cpp:317-319)
+        for (int o = tid; o < 8 * 7 * Kd; o += kTransformThreads) {
+            int c = o / (7 * Kd), rem = o - c * 7 * Kd;
+            coefs[(size_t)(child0 + c) * ncoef + Kd + rem] = 0.0;
+        }
+    }
+    if (MODE == 2) {
+        // norms of the 8 generated scaling blocks: warp w reduces child w (`in` holds the last pass)
+        int w = tid >> 5, lane = tid & 31;
+        double s = 0.0;
+        for (int e = lane; e < Kd; e += 32) {
+            double v = in[w * KdP + (padOn ? e + e / K : e)];
+            s = fma(v, v, s);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) genNorms[child0 - nReal + w] = sqrt(s);
+    }
+}
+
+__global__ void __launch_bounds__(256) norms_kernel(const double *__restrict__ coefs, double *__restrict__ norms,
+                                                    const int *__restrict__ slots, int Kd) {
+    int node = slots ? slots[blockIdx.x] : blockIdx.x;
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double *b = coefs + ((size_t)node * 8 + w) * Kd;
+    double s = 0.0;
+    for (int e = lane; e < Kd; e += 32) {
+        double v = b[e];
+        s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) norms[(size_t)node * 8 + w] = sqrt(s);
+}
+
+__global__ void __launch_bounds__(256) dot_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                                  const int *__restrict__ pairs, double *__restrict__ res, int nRoots, int Kd) {
+    __shared__ double part[8];
+    int na = pairs[2 * blockIdx.x], nb = pairs[2 * blockIdx.x + 1];
+    const double *pa = a + (size_t)na * 8 * Kd, *pb = b + (size_t)nb * 8 * Kd;
+    int start = (na < nRoots) ? 0 : Kd; // scaling part only at the roots
+    double s = 0.0;
+    for (int e = start + threadIdx.x; e < 8 * Kd; e += 256) s = fma(pa[e], pb[e], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += part[i];
+        res[blockIdx.x] = t;
+    }
+}
+
+__global__ void scale_kernel(double *x, size_t n, double c) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) x[i] *= c;
+}
+
+size_t transform_smem(int K, int &padOn) {
+    int K2 = K * K, Kd = K2 * K;
+    padOn = 1;
+    size_t bytes = ((size_t)16 * (Kd + K2) + 4 * K2) * sizeof(double);
+    if (bytes > 227 * 1024) {
+        padOn = 0;
+        bytes = ((size_t)16 * Kd + 4 * K2) * sizeof(double);
+    }
+    if (bytes > 227 * 1024) MRX_ABORT("transform kernel: order too large for shared memory staging");
+    return bytes;
+}
+
+template <int MODE> void set_smem_attr(size_t bytes) {
+    static size_t configured = 0;
+    if (bytes > configured) {
+        MRX_CUDA(cudaFuncSetAttribute(transform_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+}
+
+} // namespace
+
+void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t st) {
+    if (n <= 0) return;
+    norms_kernel<<<n, 256, 0, st>>>(coefs, norms, slots, Kd);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
+                      cudaStream_t st) {
+    if (cnt <= 0) return;
+    int padOn;
+    size_t bytes = transform_smem(K, padOn);
+    if (down) {
+        set_smem_attr<0>(bytes);
+        transform_kernel<0><<<cnt, kTransformThreads, bytes, st>>>(coefs, nullptr, nullptr, nullptr, 0, pairs, K, padOn, filters,
+                                                                  overwrite ? 1 : 0);
+    } else {
+        set_smem_attr<1>(bytes);
+        transform_kernel<1><<<cnt, kTransformThreads, bytes, st>>>(coefs, nullptr, nullptr, nullptr, 0, pairs, K, padOn, filters, 1);
+    }
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_gen_children(const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *items, int cnt,
+                         int K, const double *filters, cudaStream_t st) {
+    if (cnt <= 0) return;
+    int padOn;
+    size_t bytes = transform_smem(K, padOn);
+    set_smem_attr<2>(bytes);
+    transform_kernel<2><<<cnt, kTransformThreads, bytes, st>>>(nullptr, realCoefs, genCoefs, genNorms, nReal, items, K, padOn,
+                                                              filters, 1);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_dot(const double *a, const double *b, const int *pairs, double *res, int np, int nRoots, int Kd, cudaStream_t st) {
+    if (np <= 0) return;
+    dot_kernel<<<np, 256, 0, st>>>(a, b, pairs, res, nRoots, Kd);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_scale(double *x, size_t n, double c, cudaStream_t st) {
+    if (n == 0) return;
+    scale_kernel<<<1184, 256, 0, st>>>(x, n, c);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+} // namespace mrx

@@ -1,0 +1,27 @@
+// Launchers of the tree-maintenance kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+namespace mrx {
+
+const double *device_filters(int k);
+
+/// component norms: norms[node*8 + c] = ||block c|| for node = slots ? slots[i] : i, i < n
+void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t st);
+
+/// one level of the two-scale transform. pairs = (parent slot, child0 slot) x cnt.
+/// down: children.scaling (=|+=) reconstruct(parent 8 blocks); up: parent 8 blocks = compress(children.scaling)
+void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
+                      cudaStream_t st);
+
+/// generated children of input-tree nodes (FunctionNode::genChildren + giveChildrenCoefs):
+/// items = (parent slot, child0 slot) in the unified slot space (slot >= nReal -> generated pool)
+void launch_gen_children(const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *items, int cnt,
+                         int K, const double *filters, cudaStream_t st);
+
+void launch_dot(const double *a, const double *b, const int *pairs, double *res, int np, int nRoots, int Kd, cudaStream_t st);
+void launch_scale(double *x, size_t n, double c, cudaStream_t st);
+
+} // namespace mrx

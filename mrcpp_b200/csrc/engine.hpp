@@ -1,0 +1,104 @@
+// Internal glue between the C-ABI (cabi.cpp), the host data model (host/) and the CUDA engine (cuda/).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/mrcpp_b200.h"
+#include "host/mrx_host.hpp"
+
+struct mrx_mra {
+    mrx::MRA<3> m;
+};
+
+namespace mrx {
+
+/// Growable device buffer. Growth is geometric and preserves contents (device-to-device copy).
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n, bool keep, cudaStream_t st) {
+        if (n <= cap) return;
+        size_t ncap = n > cap + cap / 2 ? n : cap + cap / 2;
+        T *np = nullptr;
+        if (cudaMalloc(&np, ncap * sizeof(T)) != cudaSuccess) MRX_ABORT("cudaMalloc failed (out of device memory?)");
+        if (keep && p && cap) cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (p) {
+            cudaStreamSynchronize(st);
+            cudaFree(p);
+        }
+        p = np;
+        cap = ncap;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+/// HBM-resident node store of one function tree: SoA blocks in slot order.
+struct DeviceTree {
+    DevBuf<double> coefs;    // [nNodes][8][K^3]
+    DevBuf<double> norms;    // [nNodes][8] component norms
+    DevBuf<double> genCoefs; // [nGen][K^3]   generated (scaling-only) nodes, slot = nReal + i
+    DevBuf<double> genNorms; // [nGen]
+    int nNodes = 0;          // real nodes with valid device storage
+    int nGen = 0;
+};
+
+struct DeviceOper {
+    DevBuf<double> mats;   // all terms, all nodes: 4*K*K each
+    DevBuf<double> norms;  // 4 per node
+    DevBuf<int> nodeOff;   // [M][DM] global node index of transl = -maxTransl, -1 if depth absent
+    DevBuf<int> maxTransl; // [M][DM]
+    DevBuf<int> bw;        // [M][DM][5]   (per apply: depends on prec)
+    DevBuf<int> bsf;       // [M][DM][64]  band size factors (per apply)
+    int M = 0, DM = 0;
+    bool tablesValid = false;
+    std::vector<size_t> termNodeBase; // host: first global node index of each term
+};
+
+} // namespace mrx
+
+struct mrx_tree {
+    mrx::Tree<3> host;
+    mrx::DeviceTree dev;
+    bool hostCoefsValid = true; // host coefficient chunks hold the current values
+    bool devValid = false;      // device copy holds the current values
+    explicit mrx_tree(const mrx::MRA<3> &m)
+            : host(m) {}
+};
+
+struct mrx_oper {
+    mrx::Operator op;
+    mrx::DeviceOper dev;
+};
+
+namespace mrx {
+
+bool device_enabled();
+void require_device(const char *what); // aborts: there is no CPU fallback for the hot path
+cudaStream_t stream();
+long long &launch_counter();
+
+// device_tree.cu
+void tree_upload(mrx_tree &t);
+void tree_download(mrx_tree &t);
+void tree_drop_device(mrx_tree &t);
+void device_mw_transform(mrx_tree &t, int type, bool overwrite); // whole-tree transform + norms
+void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
+double device_dot(mrx_tree &bra, mrx_tree &ket);
+void device_rescale(mrx_tree &t, double c);
+void oper_upload(mrx_oper &o);
+
+// apply.cu
+void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
+                  mrx_apply_stats *stats);
+void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int dir, mrx_apply_stats *stats);
+
+} // namespace mrx

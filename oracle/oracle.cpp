@@ -1,0 +1,677 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product.
+//
+// CPU (C++17 + OpenMP) restatement of the reference's hot path for 3-D real function trees:
+//   mrcpp::apply (ConvolutionOperator)      src/treebuilders/apply.cpp:68-93
+//   TreeBuilder::build                      src/treebuilders/TreeBuilder.cpp:38-86
+//   ConvolutionCalculator                   src/treebuilders/ConvolutionCalculator.cpp:105-382
+//   MWTree::mwTransformUp/Down              src/trees/MWTree.cpp:166-216
+//   tree_utils::mw_transform[_back]         src/utils/tree_utils.cpp:113-301
+//   mrcpp::apply (DerivativeOperator)       src/treebuilders/apply.cpp:379-412
+//   DerivativeCalculator                    src/treebuilders/DerivativeCalculator.cpp:115-275
+// Same loop structure, same thresholds, same summation order for the norms that feed thresholds.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library; the product (mrcpp_b200/) never does.
+//
+// PARITY PINNING: the reference cannot be built in this image (Eigen 3.4.0 and Catch2 are
+// un-vendored dependencies, no network), so this oracle is pinned by the reference's own
+// known-answer tests instead (tests/test_oracle_kats.py): Poisson/Helmholtz kernel sizes and point
+// values, filter orthonormality, Coulomb self-energy of a Gaussian, band-width monotonicity,
+// derivative L2 error, projected-Gaussian integral/norm. At the 1e-12 coefficient level parity with
+// the real reference is UNPINNED (Eigen's summation order is unspecified anyway).
+//
+// It uses the product's host data model (mrcpp_b200/csrc/host: flat trees, tables, operator tables)
+// for inputs; the operator application and tree transforms below are written independently of the
+// CUDA implementation.
+#include "../mrcpp_b200/csrc/host/mrx_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <omp.h>
+
+using namespace mrx;
+
+namespace orc {
+
+struct ApplyStats {
+    long long gNodes = 0;    // OperatorStatistics::totGCount (calcNode invocations)
+    long long fApplied = 0;  // totFCount: tuples passing the screening (x 6 kp1^4 flops each)
+    long long genUsed = 0;   // generated f-nodes created
+    int iters = 0;
+    int nNodesOut = 0;
+    double t_band = 0, t_calc = 0, t_post = 0, t_total = 0;
+};
+
+static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// out(kp1_dm1 x kp1) (=|+=) in(kp1 x kp1_dm1)^T * F ; F(i,j) row-major  (math_utils.cpp:175-194)
+static inline void apply_filter(double *out, const double *in, const double *F, int K, int Kdm1, bool acc) {
+    for (int j = 0; j < K; j++)
+        for (int m = 0; m < Kdm1; m++) {
+            double s = 0.0;
+            const double *col = in + (size_t)K * m;
+            for (int i = 0; i < K; i++) s += col[i] * F[i * K + j];
+            if (acc) out[m + (size_t)Kdm1 * j] += s;
+            else out[m + (size_t)Kdm1 * j] = s;
+        }
+}
+
+// tree_utils::mw_transform, D = 3 (tree_utils.cpp:113-216)
+static void mw_transform3(const FilterSet &fs, int K, const double *coeff_in, double *coeff_out, bool readOnlyScaling,
+                          int stride, bool b_overwrite) {
+    const int Kd = K * K * K, Kdm1 = K * K, tDim = 8;
+    std::vector<double> tmp1((size_t)Kd * tDim), tmp2((size_t)Kd * tDim);
+    int ftlim = tDim, ftlim2 = tDim, ftlim3 = tDim;
+    if (readOnlyScaling) {
+        ftlim = 1;
+        ftlim2 = 2;
+        ftlim3 = 4;
+    }
+    int i = 0, mask = 1;
+    for (int gt = 0; gt < tDim; gt++) {
+        double *out = tmp1.data() + (size_t)gt * Kd;
+        bool acc = false;
+        for (int ft = 0; ft < ftlim; ft++)
+            if ((gt | mask) == (ft | mask)) {
+                int fi = 2 * ((gt >> i) & 1) + ((ft >> i) & 1);
+                apply_filter(out, coeff_in + (size_t)ft * Kd, fs.sub[Reconstruction][fi].data(), K, Kdm1, acc);
+                acc = true;
+            }
+    }
+    i = 1, mask = 2;
+    for (int gt = 0; gt < tDim; gt++) {
+        double *out = tmp2.data() + (size_t)gt * Kd;
+        bool acc = false;
+        for (int ft = 0; ft < ftlim2; ft++)
+            if ((gt | mask) == (ft | mask)) {
+                int fi = 2 * ((gt >> i) & 1) + ((ft >> i) & 1);
+                apply_filter(out, tmp1.data() + (size_t)ft * Kd, fs.sub[Reconstruction][fi].data(), K, Kdm1, acc);
+                acc = true;
+            }
+    }
+    i = 2, mask = 4;
+    for (int gt = 0; gt < tDim; gt++) {
+        double *out = coeff_out + (size_t)gt * stride; // straight into the children
+        bool acc = !b_overwrite;
+        for (int ft = 0; ft < ftlim3; ft++)
+            if ((gt | mask) == (ft | mask)) {
+                int fi = 2 * ((gt >> i) & 1) + ((ft >> i) & 1);
+                apply_filter(out, tmp2.data() + (size_t)ft * Kd, fs.sub[Reconstruction][fi].data(), K, Kdm1, acc);
+                acc = true;
+            }
+    }
+}
+
+// tree_utils::mw_transform_back, D = 3 (tree_utils.cpp:229-301)
+static void mw_transform_back3(const FilterSet &fs, int K, const double *coeff_in, double *coeff_out, int stride) {
+    const int Kd = K * K * K, Kdm1 = K * K, tDim = 8;
+    std::vector<double> tmp((size_t)Kd * tDim);
+    int i = 0, mask = 1;
+    for (int gt = 0; gt < tDim; gt++) {
+        double *out = coeff_out + (size_t)gt * Kd;
+        bool acc = false;
+        for (int ft = 0; ft < tDim; ft++)
+            if ((gt | mask) == (ft | mask)) {
+                int fi = 2 * ((gt >> i) & 1) + ((ft >> i) & 1);
+                apply_filter(out, coeff_in + (size_t)ft * stride, fs.sub[Compression][fi].data(), K, Kdm1, acc);
+                acc = true;
+            }
+    }
+    i = 1, mask = 2;
+    for (int gt = 0; gt < tDim; gt++) {
+        double *out = tmp.data() + (size_t)gt * Kd;
+        bool acc = false;
+        for (int ft = 0; ft < tDim; ft++)
+            if ((gt | mask) == (ft | mask)) {
+                int fi = 2 * ((gt >> i) & 1) + ((ft >> i) & 1);
+                apply_filter(out, coeff_out + (size_t)ft * Kd, fs.sub[Compression][fi].data(), K, Kdm1, acc);
+                acc = true;
+            }
+    }
+    i = 2, mask = 4;
+    for (int gt = 0; gt < tDim; gt++) {
+        double *out = coeff_out + (size_t)gt * Kd;
+        bool acc = false;
+        for (int ft = 0; ft < tDim; ft++)
+            if ((gt | mask) == (ft | mask)) {
+                int fi = 2 * ((gt >> i) & 1) + ((ft >> i) & 1);
+                apply_filter(out, tmp.data() + (size_t)ft * Kd, fs.sub[Compression][fi].data(), K, Kdm1, acc);
+                acc = true;
+            }
+    }
+}
+
+// MWNode::calcNorms / calcComponentNorm (MWNode.cpp:609-616, :643-655)
+static void calc_norms(Tree<3> &t, int n) {
+    const double *c = t.coef(n);
+    double sq = 0.0;
+    for (int i = 0; i < 8; i++) {
+        double norm_i = 0.0;
+        if (!(t.isGen(n) && i != 0)) {
+            double s = 0.0;
+            const double *v = c + (size_t)i * t.Kd;
+            for (int j = 0; j < t.Kd; j++) s += v[j] * v[j];
+            norm_i = std::sqrt(s);
+        }
+        t.cnorm[(size_t)n * 8 + i] = norm_i;
+        sq += norm_i * norm_i;
+    }
+    t.sqn[n] = sq;
+}
+
+// MWNode::giveChildrenCoefs (MWNode.cpp:312-335)
+static void give_children_coefs(Tree<3> &t, const FilterSet &fs, int n, bool overwrite) {
+    int c0 = t.nodes[n].child0;
+    if (overwrite)
+        for (int c = 0; c < 8; c++) std::memset(t.coef(c0 + c), 0, sizeof(double) * t.ncoef);
+    // children are contiguous slots but live in chunked storage: go through a dense scratch
+    std::vector<double> out((size_t)8 * t.Kd);
+    for (int c = 0; c < 8; c++) std::memcpy(out.data() + (size_t)c * t.Kd, t.coef(c0 + c), sizeof(double) * t.Kd);
+    mw_transform3(fs, t.K, t.coef(n), out.data(), t.isGen(n), t.Kd, overwrite);
+    for (int c = 0; c < 8; c++) {
+        std::memcpy(t.coef(c0 + c), out.data() + (size_t)c * t.Kd, sizeof(double) * t.Kd);
+        t.nodes[c0 + c].flags |= FlagHasCoefs;
+        calc_norms(t, c0 + c);
+    }
+}
+
+// MWTree::getNode with generation (MWTree.cpp:340-352, MWNode.cpp:1097-1120, :410-418)
+static int get_node_gen(Tree<3> &t, const FilterSet &fs, int scale, const std::array<int, 3> &l, long long *genCount) {
+    int n = t.rootIndex(scale, l);
+    if (n < 0) MRX_ABORT("oracle getNode outside world");
+    while (t.nodes[n].scale < scale) {
+        if (t.nodes[n].child0 < 0) {
+            t.createChildren(n, true);
+            give_children_coefs(t, fs, n, true);
+            if (genCount) *genCount += 8;
+        }
+        int shift = scale - t.nodes[n].scale - 1;
+        int c = 0;
+        for (int d = 0; d < 3; d++) c |= ((l[d] >> shift) & 1) << d;
+        n = t.nodes[n].child0 + c;
+    }
+    return n;
+}
+
+void mw_transform_down(Tree<3> &t, bool overwrite) {
+    // MWTree::mwTransformDown (MWTree.cpp:194-216)
+    const FilterSet &fs = filter_set(t.k);
+    std::vector<std::vector<int>> table;
+    t.nodeTableByDepth(table);
+    for (size_t n = 0; n < table.size(); n++) {
+        int nn = (int)table[n].size();
+#pragma omp parallel for schedule(guided)
+        for (int i = 0; i < nn; i++) {
+            int node = table[n][i];
+            if (t.isBranch(node) && !t.isGen(t.nodes[node].child0)) give_children_coefs(t, fs, node, overwrite);
+        }
+    }
+}
+
+void mw_transform_up(Tree<3> &t) {
+    // MWTree::mwTransformUp (MWTree.cpp:166-181) + FunctionNode<3>::reCompress (FunctionNode.cpp:391-410)
+    const FilterSet &fs = filter_set(t.k);
+    std::vector<std::vector<int>> table;
+    t.nodeTableByDepth(table);
+    for (int n = (int)table.size() - 2; n >= 0; n--) {
+        int nn = (int)table[n].size();
+#pragma omp parallel for schedule(guided)
+        for (int i = 0; i < nn; i++) {
+            int node = table[n][i];
+            if (t.isBranch(node) && !t.isGen(t.nodes[node].child0)) {
+                int c0 = t.nodes[node].child0;
+                std::vector<double> in((size_t)8 * t.Kd);
+                for (int c = 0; c < 8; c++) std::memcpy(in.data() + (size_t)c * t.Kd, t.coef(c0 + c), sizeof(double) * t.Kd);
+                mw_transform_back3(fs, t.K, in.data(), t.coef(node), t.Kd);
+                t.nodes[node].flags |= FlagHasCoefs;
+                calc_norms(t, node);
+            }
+        }
+    }
+}
+
+void calc_square_norm(Tree<3> &t) {
+    std::vector<int> ends;
+    t.endNodeTable(ends);
+    double s = 0.0;
+    for (int n : ends) s += t.sqn[n];
+    t.squareNorm = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvolutionCalculator
+struct ConvCalc {
+    double prec;
+    Operator *oper;
+    Tree<3> *fTree;
+    const FilterSet *fs;
+    std::vector<std::vector<int>> bandSizes; // [term][depth*65 + gt*8+ft]
+    static constexpr int maxDepth = MaxDepth;
+
+    // initBandSizes / calcBandSizeFactor (ConvolutionCalculator.cpp:105-139), incl. the quirk that a
+    // negative width does not stop the assignment at the end of the loop body
+    void initBandSizes() {
+        bandSizes.resize(oper->size());
+        for (int i = 0; i < oper->size(); i++) {
+            const OperTerm &ot = oper->terms[i];
+            auto &bs = bandSizes[i];
+            bs.assign((size_t)maxDepth * 65, 0);
+            for (int depth = 0; depth < maxDepth; depth++) {
+                int mx = 0;
+                for (int gt = 0; gt < 8; gt++)
+                    for (int ft = 0; ft < 8; ft++) {
+                        int kk = gt * 8 + ft;
+                        int totNodes = 1;
+                        for (int d = 0; d < 3; d++) {
+                            int oIdx = 2 * ((gt >> d) & 1) + ((ft >> d) & 1);
+                            int width = ot.width(depth, oIdx);
+                            if (width < 0) {
+                                bs[depth * 65 + kk] = 0;
+                                continue;
+                            }
+                            totNodes *= 2 * width + 1;
+                        }
+                        bs[depth * 65 + kk] = totNodes * 64;
+                        mx = std::max(mx, bs[depth * 65 + kk]);
+                    }
+                bs[depth * 65 + 64] = mx;
+            }
+        }
+    }
+
+    // makeOperBand / fillOperBand (ConvolutionCalculator.cpp:142-222), non-periodic
+    void band(const Tree<3> &gTree, int g, std::vector<std::array<int, 3>> &idx_band) const {
+        idx_band.clear();
+        int scale = gTree.nodes[g].scale;
+        int o_depth = scale - oper->operRoot;
+        int width = oper->getMaxBandWidth(o_depth);
+        if (width < 0) return;
+        int s[3], nbox[3];
+        for (int i = 0; i < 3; i++) {
+            int sI = gTree.nodes[g].l[i] - width, eI = gTree.nodes[g].l[i] + width;
+            int nboxes = fTree->mra.nboxes[i] * (1 << o_depth);
+            int c_i = fTree->mra.corner[i] * (1 << o_depth);
+            if (sI < c_i) sI = c_i;
+            if (eI > c_i + nboxes - 1) eI = c_i + nboxes - 1;
+            s[i] = sI;
+            nbox[i] = eI - sI + 1;
+        }
+        for (int z = 0; z < nbox[2]; z++)
+            for (int y = 0; y < nbox[1]; y++)
+                for (int x = 0; x < nbox[0]; x++) idx_band.push_back({s[0] + x, s[1] + y, s[2] + z});
+    }
+
+    // tensorApplyOperComp (ConvolutionCalculator.cpp:333-382): three (kp1^2 x kp1)(kp1 x kp1) products,
+    // each contracting the fastest index and making it the slowest; the last accumulates into g.
+    static void tensorApply(int K, const double *f, const double *const oData[3], double *scr, double *gOut) {
+        const int K2 = K * K, Kd = K2 * K;
+        const double *aux[4] = {f, scr + Kd, scr, gOut};
+        for (int i = 0; i < 3; i++) {
+            const double *fi = aux[i];
+            double *gi = const_cast<double *>(aux[i + 1]);
+            const double *op = oData[i];
+            if (op != nullptr) {
+                for (int c = 0; c < K; c++) {
+                    double *gc = gi + (size_t)K2 * c;
+                    const double *oc = op + (size_t)K * c;
+                    if (i != 2)
+                        for (int r = 0; r < K2; r++) gc[r] = 0.0;
+                    for (int r = 0; r < K2; r++) {
+                        const double *fr = fi + (size_t)K * r;
+                        double s = 0.0;
+                        for (int t = 0; t < K; t++) s += fr[t] * oc[t];
+                        gc[r] += s;
+                    }
+                }
+            } else {
+                // identity in direction i: pure transpose (derivative operators)
+                for (int c = 0; c < K; c++)
+                    for (int r = 0; r < K2; r++) {
+                        if (i == 2) gi[r + (size_t)K2 * c] += fi[c + (size_t)K * r];
+                        else gi[r + (size_t)K2 * c] = fi[c + (size_t)K * r];
+                    }
+            }
+        }
+    }
+
+    // calcNode (ConvolutionCalculator.cpp:224-274) with applyOperComp (:277-288) and applyOperator (:297-329)
+    long long calcNode(Tree<3> &gTree, int g, const std::vector<int> &fBand, const std::vector<std::array<int, 3>> &idx_band,
+                       double *scr) const {
+        long long applied = 0;
+        const int K = gTree.K, K2 = K * K, Kd = gTree.Kd;
+        std::memset(gTree.coef(g), 0, sizeof(double) * gTree.ncoef); // zeroCoefs
+        double *gData = gTree.coef(g);
+        int o_depth = gTree.nodes[g].scale - oper->operRoot;
+        const auto &gl = gTree.nodes[g].l;
+
+        double gThrs = gTree.squareNorm;
+        if (gThrs > 0.0) {
+            auto nTerms = static_cast<double>(oper->size());
+            double precFac = 1.0;
+            gThrs = prec * precFac * std::sqrt(gThrs / nTerms);
+        }
+        const int M = oper->size();
+        for (size_t n = 0; n < fBand.size(); n++) {
+            int fN = fBand[n];
+            const auto &fl = idx_band[n];
+            int maxDeltaL = 0;
+            for (int d = 0; d < 3; d++) maxDeltaL = std::max(maxDeltaL, std::abs(fl[d] - gl[d]));
+            const double *fData = fTree->coef(fN);
+            for (int ft = 0; ft < 8; ft++) {
+                double fNorm = fTree->cnorm[(size_t)fN * 8 + ft];
+                if (fNorm < MachineZero) continue;
+                for (int gt = 0; gt < 8; gt++) {
+                    if (!(o_depth == 0 or gt != 0 or ft != 0)) continue;
+                    // applyOperComp
+                    for (int i = 0; i < M; i++) {
+                        const OperTerm &ot = oper->terms[i];
+                        if (maxDeltaL > ot.maxWidth(o_depth)) continue;
+                        double fThreshold = bandSizes[i][o_depth * 65 + gt * 8 + ft] * fNorm;
+                        // applyOperator
+                        double oNorm = 1.0;
+                        const double *oData[3];
+                        bool outside = false;
+                        for (int d = 0; d < 3; d++) {
+                            int oTransl = fl[d] - gl[d];
+                            int a = (gt >> d) & 1, b = (ft >> d) & 1;
+                            int idx = (a << 1) + b;
+                            if (std::abs(oTransl) > ot.width(o_depth, idx)) {
+                                outside = true;
+                                break;
+                            }
+                            oNorm *= ot.nodeNorms(o_depth, oTransl)[idx];
+                            oData[d] = ot.node(o_depth, oTransl) + (size_t)idx * K2;
+                        }
+                        if (outside) continue;
+                        double upperBound = oNorm * fThreshold;
+                        if (upperBound > gThrs) {
+                            applied++;
+                            tensorApply(K, fData + (size_t)ft * Kd, oData, scr, gData + (size_t)gt * Kd);
+                        }
+                    }
+                }
+            }
+        }
+        calc_norms(gTree, g);
+        return applied;
+    }
+};
+
+// mrcpp::apply (apply.cpp:68-93) = calcBandWidths + TreeBuilder::build + TopDown(+=) + BottomUp + norm
+void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter, bool absPrec, ApplyStats *stats) {
+    if (!(out.mra == inp.mra)) MRX_ABORT("Incompatible MRA");
+    double t0 = now();
+    ApplyStats st;
+    oper.calcBandWidths(prec);
+    int maxScale = out.mra.maxScale();
+    ConvCalc calc;
+    calc.prec = prec;
+    calc.oper = &oper;
+    calc.fTree = &inp;
+    calc.fs = &filter_set(inp.k);
+    calc.initBandSizes();
+
+    // TreeBuilder::build (TreeBuilder.cpp:38-86); initial work vector = all nodes of `out` (:400-405)
+    std::vector<int> workVec;
+    out.nodeTable(workVec);
+    double sNorm = 0.0, wNorm = 0.0;
+    int iter = 0;
+    const int nThreads = omp_get_max_threads();
+    std::vector<std::vector<double>> scratch(nThreads, std::vector<double>((size_t)2 * out.Kd));
+    while (!workVec.empty()) {
+        int nNodes = (int)workVec.size();
+        // band pre-pass: the reference generates missing f-nodes lazily under locks inside calcNode
+        // (makeOperBand -> fTree->getNode); here the same nodes are generated up front, serially.
+        double tb = now();
+        std::vector<std::vector<int>> bands(nNodes);
+        std::vector<std::vector<std::array<int, 3>>> idxs(nNodes);
+        for (int i = 0; i < nNodes; i++) {
+            calc.band(out, workVec[i], idxs[i]);
+            bands[i].resize(idxs[i].size());
+            for (size_t j = 0; j < idxs[i].size(); j++)
+                bands[i][j] = get_node_gen(inp, *calc.fs, out.nodes[workVec[i]].scale, idxs[i][j], &st.genUsed);
+        }
+        st.t_band += now() - tb;
+        double tc = now();
+        long long applied = 0;
+#pragma omp parallel for schedule(guided) reduction(+ : applied)
+        for (int i = 0; i < nNodes; i++)
+            applied += calc.calcNode(out, workVec[i], bands[i], idxs[i], scratch[omp_get_thread_num()].data());
+        st.t_calc += now() - tc;
+        st.fApplied += applied;
+        st.gNodes += nNodes;
+
+        if (iter == 0) {
+            sNorm = 0.0;
+            for (int n : workVec) sNorm += out.scalingNorm(n);
+        }
+        for (int n : workVec) wNorm += out.waveletNorm(n);
+        if (sNorm < 0.0 or wNorm < 0.0) out.squareNorm = -1.0;
+        else out.squareNorm = sNorm + wNorm;
+
+        std::vector<int> newVec;
+        if (iter >= maxIter and maxIter >= 0) workVec.clear();
+        for (int n : workVec) {
+            // TreeAdaptor::splitNodeVector (TreeAdaptor.h:41-54) + WaveletAdaptor::splitNode
+            if (out.isBranch(n)) continue;
+            if (out.nodes[n].scale + 2 > maxScale) continue;
+            if (split_check(out, n, prec, 1.0, absPrec)) {
+                int c0 = out.createChildren(n, false);
+                for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
+            }
+        }
+        workVec.swap(newVec);
+        iter++;
+    }
+    st.iters = iter;
+    double tp = now();
+    oper.clearBandWidths();
+    mw_transform_down(out, false); // add coarse scale contributions
+    mw_transform_up(out);
+    calc_square_norm(out);
+    inp.deleteGenerated();
+    st.t_post = now() - tp;
+    st.nNodesOut = out.size();
+    st.t_total = now() - t0;
+    if (stats) *stats = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// derivative apply (apply.cpp:379-412)
+void apply_derivative(Tree<3> &out, Operator &oper, Tree<3> &inp, int dir, ApplyStats *stats) {
+    if (!(out.mra == inp.mra)) MRX_ABORT("Incompatible MRA");
+    if (dir < 0 or dir >= 3) MRX_ABORT("Invalid apply dir");
+    ApplyStats st;
+    double t0 = now();
+    const FilterSet &fs = filter_set(inp.k);
+    int maxScale = out.mra.maxScale();
+    oper.calcBandWidths(1.0);
+    int bw[3] = {0, 0, 0};
+    bw[dir] = oper.getMaxBandWidth();
+
+    // grid: CopyAdaptor(inp, maxScale, bw) + DefaultCalculator (CopyAdaptor.cpp:56-72)
+    {
+        std::vector<int> workVec;
+        out.endNodeTable(workVec);
+        while (!workVec.empty()) {
+            std::vector<int> newVec;
+            for (int n : workVec) {
+                if (out.isBranch(n)) continue;
+                if (out.nodes[n].scale + 2 > maxScale) continue;
+                // CopyAdaptor::splitNode (CopyAdaptor.cpp:56-72): any child index, shifted within the
+                // band along each dimension, that exists in the input tree
+                bool split = false;
+                const auto idx0 = out.nodes[n];
+                for (int c = 0; c < 8 && !split; c++)
+                    for (int d = 0; d < 3 && !split; d++)
+                        for (int b = -bw[d]; b <= bw[d] && !split; b++) {
+                            std::array<int, 3> l;
+                            for (int dd = 0; dd < 3; dd++) l[dd] = 2 * idx0.l[dd] + ((c >> dd) & 1);
+                            l[d] += b;
+                            if (inp.findNode(idx0.scale + 1, l) >= 0) split = true;
+                        }
+                if (split) {
+                    int c0 = out.createChildren(n, false);
+                    for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
+                }
+            }
+            workVec.swap(newVec);
+        }
+    }
+
+    // DerivativeCalculator on end nodes only, maxIter = 0 (DerivativeCalculator.cpp:115-154, :277-279)
+    std::vector<int> workVec;
+    out.endNodeTable(workVec);
+    int nNodes = (int)workVec.size();
+    const int K = out.K, K2 = K * K, Kd = out.Kd;
+    const OperTerm &ot = oper.terms[0];
+    int width = oper.getMaxBandWidth();
+    // band pre-pass (makeOperBand, :157-178)
+    std::vector<std::vector<int>> bands(nNodes);
+    std::vector<std::vector<std::array<int, 3>>> idxs(nNodes);
+    for (int i = 0; i < nNodes; i++) {
+        const auto &nd = out.nodes[workVec[i]];
+        for (int w = -width; w <= width; w++) {
+            std::array<int, 3> l = nd.l;
+            l[dir] += w;
+            if (inp.rootIndex(nd.scale, l) >= 0) {
+                idxs[i].push_back(l);
+                bands[i].push_back(get_node_gen(inp, fs, nd.scale, l, &st.genUsed));
+            }
+        }
+    }
+    const int nThreads = omp_get_max_threads();
+    std::vector<std::vector<double>> scratch(nThreads, std::vector<double>((size_t)2 * Kd));
+    long long applied = 0;
+#pragma omp parallel for schedule(guided) reduction(+ : applied)
+    for (int i = 0; i < nNodes; i++) {
+        int g = workVec[i];
+        double *scr = scratch[omp_get_thread_num()].data();
+        std::memset(out.coef(g), 0, sizeof(double) * out.ncoef);
+        double *gData = out.coef(g);
+        int depth = out.depth(g);
+        const auto &gl = out.nodes[g].l;
+        for (size_t n = 0; n < bands[i].size(); n++) {
+            int fN = bands[i][n];
+            const auto &fl = idxs[i][n];
+            const double *fData = inp.coef(fN);
+            for (int ft = 0; ft < 8; ft++) {
+                double fNorm = inp.cnorm[(size_t)fN * 8 + ft];
+                if (fNorm < MachineZero) continue;
+                for (int gt = 0; gt < 8; gt++) {
+                    // applyOperator (DerivativeCalculator.cpp:211-249)
+                    const double *oData[3];
+                    bool skip = false;
+                    for (int d = 0; d < 3; d++) {
+                        int oTransl = fl[d] - gl[d];
+                        int a = (gt >> d) & 1, b = (ft >> d) & 1;
+                        int idx = (a << 1) + b;
+                        int w = ot.width(depth, idx);
+                        if (std::abs(oTransl) > w) {
+                            skip = true;
+                            break;
+                        }
+                        if (dir == d) {
+                            oData[d] = ot.node(depth, oTransl) + (size_t)idx * K2;
+                        } else {
+                            if (oTransl == 0 and (idx == 0 or idx == 3)) oData[d] = nullptr;
+                            else {
+                                skip = true;
+                                break;
+                            }
+                        }
+                    }
+                    if (skip) continue;
+                    applied++;
+                    ConvCalc::tensorApply(K, fData + (size_t)ft * Kd, oData, scr, gData + (size_t)gt * Kd);
+                }
+            }
+        }
+        // divide by scalingFactor^order: scaling factor is 1 here
+        out.nodes[g].flags |= FlagHasCoefs;
+        calc_norms(out, g);
+    }
+    st.gNodes = nNodes;
+    st.fApplied = applied;
+    oper.clearBandWidths();
+    mw_transform_up(out);
+    calc_square_norm(out);
+    inp.deleteGenerated();
+    st.nNodesOut = out.size();
+    st.t_total = now() - t0;
+    if (stats) *stats = st;
+}
+
+// <bra|ket> from compressed coefficients: scaling blocks of the roots + wavelet blocks of every node
+// present in both trees (mathematically equal to mrcpp::dot, multiply.cpp:286-318).
+double dot(const Tree<3> &bra, const Tree<3> &ket) {
+    if (!(bra.mra == ket.mra)) MRX_ABORT("Incompatible MRA");
+    double result = 0.0;
+    const int Kd = bra.Kd;
+    // walk both trees together
+    std::vector<std::pair<int, int>> stack;
+    for (int r = 0; r < bra.nRoots; r++) {
+        const double *a = bra.coef(r), *b = ket.coef(r);
+        for (int i = 0; i < Kd; i++) result += a[i] * b[i];
+        stack.push_back({r, r});
+    }
+    while (!stack.empty()) {
+        auto [na, nb] = stack.back();
+        stack.pop_back();
+        const double *a = bra.coef(na), *b = ket.coef(nb);
+        bool aBranch = bra.isBranch(na) && !bra.isGen(bra.nodes[na].child0);
+        bool bBranch = ket.isBranch(nb) && !ket.isGen(ket.nodes[nb].child0);
+        // wavelet coefficients of an end node are kept by the reference's projection too
+        double s = 0.0;
+        for (int i = Kd; i < 8 * Kd; i++) s += a[i] * b[i];
+        result += s;
+        if (aBranch && bBranch)
+            for (int c = 0; c < 8; c++) stack.push_back({bra.nodes[na].child0 + c, ket.nodes[nb].child0 + c});
+    }
+    return result;
+}
+
+} // namespace orc
+
+// ------------------------------------------------------------------------------------------------
+// C entry points (ctypes). Handles are the product's host objects: mrx::Tree<3>* and mrx::Operator*.
+extern "C" {
+void orc_set_table_path(const char *p) { mrx::set_table_path(p); }
+int orc_num_threads() { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+
+struct orc_stats {
+    long long gNodes, fApplied, genUsed;
+    int iters, nNodesOut;
+    double t_band, t_calc, t_post, t_total;
+};
+static void copy_stats(const orc::ApplyStats &s, orc_stats *o) {
+    if (!o) return;
+    o->gNodes = s.gNodes;
+    o->fApplied = s.fApplied;
+    o->genUsed = s.genUsed;
+    o->iters = s.iters;
+    o->nNodesOut = s.nNodesOut;
+    o->t_band = s.t_band;
+    o->t_calc = s.t_calc;
+    o->t_post = s.t_post;
+    o->t_total = s.t_total;
+}
+void orc_apply(double prec, void *out, void *oper, void *inp, int maxIter, int absPrec, orc_stats *stats) {
+    orc::ApplyStats st;
+    orc::apply(prec, *static_cast<Tree<3> *>(out), *static_cast<Operator *>(oper), *static_cast<Tree<3> *>(inp), maxIter,
+               absPrec != 0, &st);
+    copy_stats(st, stats);
+}
+void orc_apply_derivative(void *out, void *oper, void *inp, int dir, orc_stats *stats) {
+    orc::ApplyStats st;
+    orc::apply_derivative(*static_cast<Tree<3> *>(out), *static_cast<Operator *>(oper), *static_cast<Tree<3> *>(inp), dir, &st);
+    copy_stats(st, stats);
+}
+void orc_mw_transform_down(void *tree, int overwrite) { orc::mw_transform_down(*static_cast<Tree<3> *>(tree), overwrite != 0); }
+void orc_mw_transform_up(void *tree) { orc::mw_transform_up(*static_cast<Tree<3> *>(tree)); }
+void orc_calc_square_norm(void *tree) { orc::calc_square_norm(*static_cast<Tree<3> *>(tree)); }
+double orc_dot(void *bra, void *ket) { return orc::dot(*static_cast<Tree<3> *>(bra), *static_cast<Tree<3> *>(ket)); }
+}

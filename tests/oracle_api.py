@@ -1,0 +1,104 @@
+"""ctypes wrapper of the CPU oracle (oracle/oracle.cpp). TEST INFRASTRUCTURE: imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+
+from mrcpp_b200 import _lib as _plib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+
+
+class OrcStats(C.Structure):
+    _fields_ = [("gNodes", C.c_longlong), ("fApplied", C.c_longlong), ("genUsed", C.c_longlong), ("iters", C.c_int),
+                ("nNodesOut", C.c_int), ("t_band", C.c_double), ("t_calc", C.c_double), ("t_post", C.c_double),
+                ("t_total", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_o = None
+
+
+def lib():
+    global _o
+    if _o is None:
+        if not os.path.exists(ORACLE_LIB):
+            raise ImportError(f"{ORACLE_LIB} missing: run `make -C oracle`")
+        o = C.CDLL(ORACLE_LIB)
+        o.orc_set_table_path.argtypes = [C.c_char_p]
+        o.orc_num_threads.restype = C.c_int
+        o.orc_set_num_threads.argtypes = [C.c_int]
+        o.orc_apply.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcStats)]
+        o.orc_apply_derivative.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcStats)]
+        o.orc_mw_transform_down.argtypes = [C.c_void_p, C.c_int]
+        o.orc_mw_transform_up.argtypes = [C.c_void_p]
+        o.orc_calc_square_norm.argtypes = [C.c_void_p]
+        o.orc_dot.argtypes = [C.c_void_p, C.c_void_p]
+        o.orc_dot.restype = C.c_double
+        o.orc_set_table_path(_plib.TABLES.encode())
+        _o = o
+    return _o
+
+
+def _th(tree):
+    return _plib.load().mrx_tree_host_handle(tree._h)
+
+
+def _oh(oper):
+    return _plib.load().mrx_oper_host_handle(oper._h)
+
+
+def _modified(tree):
+    _plib.load().mrx_tree_host_modified(tree._h)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def apply(prec, out, oper, inp, maxIter=-1, absPrec=False):
+    st = OrcStats()
+    inp.sync_host()
+    lib().orc_apply(prec, _th(out), _oh(oper), _th(inp), maxIter, 1 if absPrec else 0, C.byref(st))
+    _modified(out)
+    return st
+
+
+def apply_derivative(out, oper, inp, dir):
+    st = OrcStats()
+    inp.sync_host()
+    lib().orc_apply_derivative(_th(out), _oh(oper), _th(inp), dir, C.byref(st))
+    _modified(out)
+    return st
+
+
+def mw_transform_up(tree):
+    tree.sync_host()
+    lib().orc_mw_transform_up(_th(tree))
+    _modified(tree)
+
+
+def mw_transform_down(tree, overwrite=True):
+    tree.sync_host()
+    lib().orc_mw_transform_down(_th(tree), 1 if overwrite else 0)
+    _modified(tree)
+
+
+def calc_square_norm(tree):
+    lib().orc_calc_square_norm(_th(tree))
+
+
+def dot(bra, ket):
+    bra.sync_host()
+    ket.sync_host()
+    return lib().orc_dot(_th(bra), _th(ket))
+
+
+def project(prec, out, func, build_grid=True):
+    """product host projection (quadrature + in-node compression) closed by the ORACLE's BottomUp"""
+    import mrcpp_b200 as mw
+    mw.project(prec, out, func, build_grid=build_grid, finalize=False)
+    mw_transform_up(out)
+    calc_square_norm(out)
