@@ -224,6 +224,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         P.K = K;
         P.gThrs = gThrs;
         P.counters = scr.counters.p;
+        P.derivDir = -1;
 
         MRX_CUDA(cudaEventRecord(ev0, st));
         launch_apply(P, nG, st);
