@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py — Poisson-apply throughput on B200 (BASELINE.json metric).
+
+A "step" is one mrcpp::apply of the 3-D Poisson operator (k=7, prec 1e-7: the north_star target) onto a
+synthetic multi-centre Gaussian density (seed 42, centres uniform in [-8,8]^3, beta log-uniform in
+[10,1000], as config C5 of SURVEY.md §8d) with a fresh output tree each step.
+
+  value  output nodes/s (calcNode invocations over all refinement iterations / device time), inputs
+         resident in HBM when the timed region starts.
+  e2e    same metric through the C-ABI with HOST buffers: the input tree is uploaded and the result
+         tree downloaded inside the timed region.
+  roofline  dominant kernel = the contraction kernel (apply_dmma8_kernel): algorithmic flops =
+         surviving tuples x 6 (k+1)^4, divided by the kernel's CUDA-event time; peak = FP64 tensor
+         (DMMA) rate measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline  the CPU oracle (OpenMP restatement of the reference) on a bounded sample.
+
+N > 1 (torchrun): one process per GPU; each rank applies the replicated operator to its own density
+(independent objects, no data-path collective) -> weak scaling; time = max over ranks.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def density(mw, n, seed):
+    rng = np.random.default_rng(seed)
+    g = mw.GaussExp()
+    for _ in range(n):
+        beta = 10.0 ** rng.uniform(1, 3)
+        g.append(mw.GaussFunc(beta, (beta / math.pi) ** 1.5 / n, tuple(rng.uniform(-8, 8, 3))))
+    return g
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path. The real MRCPP cannot be built in this
+    image (Eigen 3.4.0 is an un-vendored dependency), so this arm times the oracle port (oracle/oracle.cpp: OpenMP
+    restatement, same loop structure and thresholds) on all host threads, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mrcpp_b200 as mw
+    from mrcpp_b200 import _lib, build
+    build.build_oracle()
+    _lib.load().mrx_init(_lib.TABLES.encode(), -1)
+    _lib._device = -1
+    import oracle_api as orc
+    k, prec = args.order, args.prec
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    P = mw.PoissonOperator(mra, prec)
+    func = density(mw, args.cpu_centers, 42)
+    ft = mw.FunctionTree(mra)
+    orc.project(prec, ft, func)
+    times, nodes, tuples = [], 0, 0
+    for it in range(args.warmup + args.steps):
+        gt = mw.FunctionTree(mra)
+        t0 = time.perf_counter()
+        st = orc.apply(prec, gt, P, ft)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            nodes += st.gNodes
+            tuples += st.fApplied
+    total = sum(times)
+    value = nodes / total
+    K = k + 1
+    line = {
+        "impl": "reference", "metric": "poisson_apply_output_nodes_per_s", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.cpu_centers, sample=True),
+        "fp64_tflops": tuples * 6 * K ** 4 / total / 1e12,
+        "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": f"{args.cpu_centers}-centre subset of the workload density, full adaptive apply"},
+        "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, centers, sample=False):
+    return {"workload": f"poisson_apply_k{args.order}_prec{args.prec:g}_gauss{centers}" + ("_cpu_sample" if sample else ""),
+            "order": args.order, "prec": args.prec, "centers": centers, "world": "[-16,16]^3 root scale -4, max depth 25",
+            "operator": "PoissonOperator(prec)", "mode": "adaptive (maxIter=-1)",
+            "l2_policy": "fresh output tree each step; input tree + operator tables exceed nothing: working set per step "
+                         "is re-generated (generated input nodes, output coefficients) and an L2 flush buffer (256 MB) is written between steps",
+            "parallelism": "independent densities per GPU (seed 42+rank), operator replicated"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--order", type=int, default=7)
+    ap.add_argument("--prec", type=float, default=1e-7)
+    ap.add_argument("--centers", type=int, default=100)
+    ap.add_argument("--cpu-centers", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import ctypes as C
+    import mrcpp_b200 as mw
+    from mrcpp_b200 import _lib
+    from mrcpp_b200 import build
+    if rank == 0 and not os.path.exists(_lib.LIB_PATH):
+        build.build_lib()
+    if world > 1:
+        dist.barrier()
+    _lib.init(local_rank)
+    L = _lib.load()
+
+    k, prec, K = args.order, args.prec, args.order + 1
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    t0 = time.perf_counter()
+    P = mw.PoissonOperator(mra, prec)
+    t_oper = time.perf_counter() - t0
+    func = density(mw, args.centers, 42 + rank)
+    ft = mw.FunctionTree(mra)
+    t0 = time.perf_counter()
+    mw.project(prec, ft, func)
+    t_proj = time.perf_counter() - t0
+    ft.sync_device()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(e2e):
+        flush.fill_(1)  # L2 flush between timed iterations (untimed: the timer runs on the library stream)
+        torch.cuda.synchronize()
+        if e2e:
+            ft.drop_device()  # input starts in (pinned) host memory
+        out = mw.FunctionTree(mra)
+        L.mrx_timer_start()
+        st = mw.apply(prec, out, P, ft)
+        if e2e:
+            out.sync_host()  # result back in host memory
+        ms = L.mrx_timer_stop_ms()
+        nbytes_out = out.nbytes()
+        del out
+        return st, ms, nbytes_out
+
+    # ---- resident-input arm
+    for _ in range(args.warmup):
+        one_step(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    tot_ms = 0.0
+    nodes = tuples = launches = 0
+    kern_ms = 0.0
+    phases = {"ms_build": 0.0, "ms_post": 0.0, "ms_upload": 0.0}
+    last = None
+    for _ in range(args.steps):
+        st, ms, _ = one_step(False)
+        tot_ms += ms
+        nodes += st.g_nodes
+        tuples += st.f_applied
+        launches += st.kernel_launches
+        kern_ms += st.ms_kernel
+        for kk in phases:
+            phases[kk] += getattr(st, kk)
+        last = st
+    barrier()
+    clocks = sampler.stop()
+
+    # ---- end-to-end arm (host buffers in, host buffers out)
+    one_step(True)
+    barrier()
+    e2e_ms = 0.0
+    e2e_nodes = 0
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        st, ms, nb_out = one_step(True)
+        e2e_ms += ms
+        e2e_nodes += st.g_nodes
+        h2d = ft.nbytes()
+        d2h = nb_out
+    barrier()
+
+    if world > 1:
+        t = torch.tensor([tot_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([nodes, tuples, launches, e2e_nodes], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        nodes, tuples, launches, e2e_nodes = (int(x) for x in c.tolist())
+        km = torch.tensor([kern_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        kern_ms_max = float(km[0])
+    else:
+        kern_ms_max = kern_ms
+
+    if rank == 0:
+        peak_dmma = L.mrx_bench_dmma_tflops(20000)
+        peak_dfma = L.mrx_bench_dfma_tflops(20000)
+        flops = tuples * 6.0 * K ** 4
+        achieved = (last.f_applied * 6.0 * K ** 4 * args.steps) / (kern_ms * 1e-3) / 1e12  # rank-0 kernel
+        line = {
+            "metric": "poisson_apply_output_nodes_per_s", "value": nodes / (tot_ms * 1e-3), "unit": "nodes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.centers),
+            "fp64_tflops": flops / (tot_ms * 1e-3) / 1e12,
+            "fp64_tflops_frac_of_dmma_peak": flops / (tot_ms * 1e-3) / 1e12 / (peak_dmma * world),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
+                         "traffic": None, "kernel": "apply_dmma8_kernel" if k == 7 else "apply_generic_kernel",
+                         "peak_source": "FP64 DMMA m8n8k4 micro-benchmark measured in this run (no FP64 figure in "
+                                        "MEASURED_PEAKS.json); DFMA peak %.1f TFLOP/s" % peak_dfma,
+                         "kernel_share_of_step": kern_ms / tot_ms},
+            "clocks": clocks,
+            "e2e": {"value": e2e_nodes / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "detail": {"output_nodes_per_step": last.g_nodes, "final_tree_nodes": last.n_nodes_out, "iterations": last.iterations,
+                       "tuples_per_step": last.f_applied, "generated_input_nodes": last.gen_nodes, "input_tree_nodes": ft.getNNodes(),
+                       "separation_rank": P.size(), "ms_kernel_per_step": kern_ms / args.steps,
+                       "ms_build_per_step": phases["ms_build"] / args.steps, "ms_post_per_step": phases["ms_post"] / args.steps,
+                       "setup_s": {"operator": t_oper, "projection": t_proj}},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, mw, mra, P)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, mw, mra, P):
+    """oracle (kind: port) on a bounded sample: same operator, cpu_centers-centre density, all host threads"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mrcpp_b200 import build
+    build.build_oracle()
+    import oracle_api as orc
+    func = density(mw, args.cpu_centers, 42)
+    ft = mw.FunctionTree(mra)
+    orc.project(args.prec, ft, func)
+    gt = mw.FunctionTree(mra)
+    t0 = time.perf_counter()
+    st = orc.apply(args.prec, gt, P, ft)
+    dt = time.perf_counter() - t0
+    K = args.order + 1
+    return {"value": st.gNodes / dt, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{args.cpu_centers}-centre subset of the workload density, one full adaptive apply ({dt:.1f} s)",
+            "fp64_tflops": st.fApplied * 6 * K ** 4 / dt / 1e12, "output_nodes": st.gNodes}
+
+
+if __name__ == "__main__":
+    main()

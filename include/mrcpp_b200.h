@@ -140,6 +140,10 @@ void *mrx_oper_host_handle(mrx_oper *oper);
 /* tell the library that the host copy was modified through the handle (device copy becomes stale) */
 void mrx_tree_host_modified(mrx_tree *tree);
 
+/* device-side stopwatch on the library's stream (CUDA events): start, run calls, stop -> elapsed ms */
+void mrx_timer_start(void);
+double mrx_timer_stop_ms(void);
+
 /* micro-benchmarks used by bench.py for the roofline denominators (FP64 tensor pipe, HBM copy) */
 double mrx_bench_dmma_tflops(int iters);
 double mrx_bench_dfma_tflops(int iters);

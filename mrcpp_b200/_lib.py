@@ -79,6 +79,8 @@ SIGNATURES = {
     "mrx_tree_host_handle": (_P, [_P]),
     "mrx_oper_host_handle": (_P, [_P]),
     "mrx_tree_host_modified": (None, [_P]),
+    "mrx_timer_start": (None, []),
+    "mrx_timer_stop_ms": (_D, []),
     "mrx_bench_dmma_tflops": (_D, [_I]),
     "mrx_bench_dfma_tflops": (_D, [_I]),
     "mrx_bench_hbm_gbs": (_D, [C.c_longlong, _I]),

@@ -51,6 +51,13 @@ int mrx_init(const char *table_path, int device) {
         }
         g_device = device;
         g_device_on = true;
+        // pinned coefficient chunks from now on
+        chunk_alloc = [](size_t bytes) -> void * {
+            void *p = nullptr;
+            if (cudaMallocHost(&p, bytes) != cudaSuccess) MRX_ABORT("cudaMallocHost failed");
+            return p;
+        };
+        chunk_free = [](void *p) { cudaFreeHost(p); };
     }
     return 0;
 }
@@ -325,6 +332,23 @@ int mrx_tree_drop_device(mrx_tree *tree) {
     return 0;
 }
 
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+void mrx_timer_start(void) {
+    require_device("mrx_timer_start");
+    if (!g_ev0) {
+        cudaEventCreate(&g_ev0);
+        cudaEventCreate(&g_ev1);
+    }
+    cudaEventRecord(g_ev0, g_stream);
+}
+double mrx_timer_stop_ms(void) {
+    require_device("mrx_timer_stop_ms");
+    cudaEventRecord(g_ev1, g_stream);
+    cudaEventSynchronize(g_ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+    return ms;
+}
 void *mrx_tree_host_handle(mrx_tree *tree) { return &tree->host; }
 void *mrx_oper_host_handle(mrx_oper *oper) { return &oper->op; }
 void mrx_tree_host_modified(mrx_tree *tree) {

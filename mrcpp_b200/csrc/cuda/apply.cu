@@ -61,39 +61,100 @@ void band_size_factors(const Operator &op, int DM, std::vector<int> &bsf, std::v
 
 struct Scratch {
     DevBuf<GDesc> gdesc;
-    DevBuf<int> nbr;
+    DevBuf<NbrEntry> nbr;
     DevBuf<int> genItems;
     DevBuf<int> gslots;
     DevBuf<unsigned long long> counters;
+    DevBuf<DepthInfo> depthInfo;
+    DevBuf<int> candOff;
+    DevBuf<int> candTerm;
+    DevBuf<unsigned long long> candMask;
+};
+
+/// Host copy of the per-depth band tables (see DepthInfo). Built lazily for the depths that occur.
+struct BandTables {
+    std::vector<DepthInfo> info;                // [DM]
+    std::vector<char> built;                    // [DM]
+    std::vector<int> candOff;                   // concatenated prefix arrays
+    std::vector<int> candTerm;
+    std::vector<unsigned long long> candMask;
+    std::vector<std::vector<std::array<int, 4>>> needed; // per depth: (dx,dy,dz,code) of offsets with candidates
+    bool dirty = false;
+
+    // integer part of the screening: per-term max width (applyOperComp :283), per-dimension band test per
+    // component (applyOperator :311-318, OperatorTree::isOutsideBand), T block only at depth 0 (calcNode :261).
+    // derivative operators: DerivativeCalculator::applyOperator (:211-249).
+    void build(const Operator &op, int depth, int derivDir) {
+        const int M = op.size();
+        const int W = op.getMaxBandWidth(depth);
+        info[depth].W = W;
+        info[depth].cubeOff = (int)candOff.size();
+        built[depth] = 1;
+        dirty = true;
+        if (W < 0) {
+            candOff.push_back((int)candTerm.size());
+            return;
+        }
+        const int cube = 2 * W + 1;
+        // per term, per distance a: bitmask over the 64 (gt,ft) combos whose component along a dimension is in band
+        // combo bit b = gt*8+ft; component along d: c_d = 2*gt_d + ft_d
+        std::vector<unsigned long long> dimMask((size_t)M * 3 * (W + 1), 0ull);
+        for (int t = 0; t < M; t++) {
+            const OperTerm &ot = op.terms[t];
+            for (int d = 0; d < 3; d++)
+                for (int a = 0; a <= W; a++) {
+                    unsigned long long m = 0ull;
+                    for (int b = 0; b < 64; b++) {
+                        int gt = b >> 3, ft = b & 7;
+                        int c = 2 * ((gt >> d) & 1) + ((ft >> d) & 1);
+                        bool ok = a <= ot.width(depth, c);
+                        if (derivDir >= 0 && d != derivDir) ok = ok && (a == 0) && (c == 0 || c == 3);
+                        if (ok) m |= 1ull << b;
+                    }
+                    dimMask[((size_t)t * 3 + d) * (W + 1) + a] = m;
+                }
+        }
+        const unsigned long long tExcl = (derivDir < 0 && depth != 0) ? ~1ull : ~0ull; // drop (gt=0,ft=0)
+        needed[depth].clear();
+        for (int z = -W; z <= W; z++)
+            for (int y = -W; y <= W; y++)
+                for (int x = -W; x <= W; x++) {
+                    const int code = ((z + W) * cube + (y + W)) * cube + (x + W);
+                    candOff.push_back((int)candTerm.size());
+                    const int ax = std::abs(x), ay = std::abs(y), az = std::abs(z);
+                    const int maxD = std::max(ax, std::max(ay, az));
+                    const size_t before = candTerm.size();
+                    for (int t = 0; t < M; t++) {
+                        if (derivDir < 0 && maxD > op.terms[t].maxWidth(depth)) continue;
+                        unsigned long long m = dimMask[((size_t)t * 3 + 0) * (W + 1) + ax] &
+                                               dimMask[((size_t)t * 3 + 1) * (W + 1) + ay] &
+                                               dimMask[((size_t)t * 3 + 2) * (W + 1) + az] & tExcl;
+                        if (m) {
+                            candTerm.push_back(t);
+                            candMask.push_back(m);
+                        }
+                    }
+                    if (candTerm.size() != before) needed[depth].push_back({x, y, z, code});
+                }
+        candOff.push_back((int)candTerm.size());
+    }
 };
 
 } // namespace
 
-void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats) {
-    require_device("device_apply");
+static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
+                      std::vector<int> workVec, mrx_apply_stats &S) {
     cudaStream_t st = stream();
-    mrx_apply_stats S{};
-    long long launches0 = launch_counter();
-    double t0 = now_ms();
-
-    // ---- residency: input tree + operator tables in HBM
-    if (!inp.devValid) tree_upload(inp);
-    oper_upload(oper);
     Operator &op = oper.op;
-    op.calcBandWidths(prec);
     const int M = op.size(), DM = oper.dev.DM;
+    const bool deriv = derivDir >= 0;
     {
         std::vector<int> bsf, bw;
         band_size_factors(op, DM, bsf, bw);
         oper.dev.bsf.reserve(bsf.size(), false, st);
-        oper.dev.bw.reserve(bw.size(), false, st);
         MRX_CUDA(cudaMemcpyAsync(oper.dev.bsf.p, bsf.data(), sizeof(int) * bsf.size(), cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(oper.dev.bw.p, bw.data(), sizeof(int) * bw.size(), cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaStreamSynchronize(st));
     }
-    S.ms_upload = now_ms() - t0;
-
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -106,25 +167,26 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     Scratch scr;
     scr.counters.reserve(4, false, st);
     MRX_CUDA(cudaMemsetAsync(scr.counters.p, 0, 4 * sizeof(unsigned long long), st));
+    BandTables bt;
+    bt.info.assign(DM, DepthInfo{-1, 0});
+    bt.built.assign(DM, 0);
+    bt.needed.resize(DM);
 
     cudaEvent_t ev0, ev1;
     MRX_CUDA(cudaEventCreate(&ev0));
     MRX_CUDA(cudaEventCreate(&ev1));
     float kernel_ms = 0.f;
 
-    double tb = now_ms();
-    std::vector<int> workVec;
-    g.nodeTable(workVec); // getInitialWorkVector: ALL nodes of `out` (ConvolutionCalculator.cpp:400-405)
     double sNorm = 0.0, wNorm = 0.0;
     int iter = 0;
     const int fRealN = f.nReal;
     std::vector<GDesc> gdesc;
-    std::vector<int> nbr;
+    std::vector<NbrEntry> nbr;
     std::vector<int> newParents;
-    std::vector<double> normsHost;
     while (!workVec.empty()) {
         const int nG = (int)workVec.size();
-        // ---- band enumeration (makeOperBand/fillOperBand, :142-222, non-periodic) on the topology
+        // ---- band enumeration (makeOperBand/fillOperBand, :142-222, non-periodic) on the topology,
+        //      restricted to offsets that at least one (term, gt, ft) can reach
         gdesc.resize(nG);
         nbr.clear();
         newParents.clear();
@@ -134,26 +196,40 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
             d.slot = workVec[i];
             d.depth = nd.scale - op.operRoot;
             d.nbrOff = (int)nbr.size();
+            d.nbrCnt = 0;
+            if (d.depth < 0 || d.depth >= DM) continue; // deeper than every operator tree: empty band (:146-151)
+            if (!bt.built[d.depth]) bt.build(op, d.depth, derivDir);
+            if (bt.info[d.depth].W < 0) continue;
+            int lo[3], hi[3];
             for (int x = 0; x < 3; x++) {
-                d.l[x] = nd.l[x];
-                d.s[x] = 0;
-                d.nb[x] = 0;
-            }
-            int width = op.getMaxBandWidth(d.depth);
-            if (width < 0) continue;
-            for (int x = 0; x < 3; x++) {
-                int sI = nd.l[x] - width, eI = nd.l[x] + width;
                 int nboxes = f.mra.nboxes[x] * (1 << d.depth);
-                int c_i = f.mra.corner[x] * (1 << d.depth);
-                if (sI < c_i) sI = c_i;
-                if (eI > c_i + nboxes - 1) eI = c_i + nboxes - 1;
-                d.s[x] = sI;
-                d.nb[x] = eI - sI + 1;
+                lo[x] = f.mra.corner[x] * (1 << d.depth);
+                hi[x] = lo[x] + nboxes - 1;
             }
-            for (int z = 0; z < d.nb[2]; z++)
-                for (int y = 0; y < d.nb[1]; y++)
-                    for (int x = 0; x < d.nb[0]; x++)
-                        nbr.push_back(f.getNodeTopo(nd.scale, {d.s[0] + x, d.s[1] + y, d.s[2] + z}, &newParents));
+            for (const auto &o : bt.needed[d.depth]) {
+                std::array<int, 3> l = {nd.l[0] + o[0], nd.l[1] + o[1], nd.l[2] + o[2]};
+                if (l[0] < lo[0] || l[0] > hi[0] || l[1] < lo[1] || l[1] > hi[1] || l[2] < lo[2] || l[2] > hi[2]) continue;
+                NbrEntry e;
+                e.fslot = f.getNodeTopo(nd.scale, l, &newParents);
+                e.code = o[3];
+                nbr.push_back(e);
+            }
+            d.nbrCnt = (int)nbr.size() - d.nbrOff;
+        }
+        if (bt.dirty) {
+            scr.depthInfo.reserve(DM, false, st);
+            scr.candOff.reserve(bt.candOff.size(), false, st);
+            scr.candTerm.reserve(std::max<size_t>(bt.candTerm.size(), 1), false, st);
+            scr.candMask.reserve(std::max<size_t>(bt.candMask.size(), 1), false, st);
+            MRX_CUDA(cudaMemcpyAsync(scr.depthInfo.p, bt.info.data(), sizeof(DepthInfo) * DM, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(scr.candOff.p, bt.candOff.data(), sizeof(int) * bt.candOff.size(), cudaMemcpyHostToDevice, st));
+            if (!bt.candTerm.empty()) {
+                MRX_CUDA(cudaMemcpyAsync(scr.candTerm.p, bt.candTerm.data(), sizeof(int) * bt.candTerm.size(),
+                                         cudaMemcpyHostToDevice, st));
+                MRX_CUDA(cudaMemcpyAsync(scr.candMask.p, bt.candMask.data(), sizeof(unsigned long long) * bt.candMask.size(),
+                                         cudaMemcpyHostToDevice, st));
+            }
+            bt.dirty = false;
         }
         // ---- generated input nodes: parents in creation order; a parent created this iteration must be
         //      filled before its own children -> waves
@@ -164,7 +240,6 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
             std::vector<int> items;
             size_t pos = 0;
             while (pos < newParents.size()) {
-                // wave = maximal run whose parents do not depend on children created inside the run
                 size_t end = pos;
                 int firstChildOfWave = f.nodes[newParents[pos]].child0;
                 while (end < newParents.size() && newParents[end] < firstChildOfWave) end++;
@@ -193,7 +268,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         scr.gslots.reserve(nG, false, st);
         MRX_CUDA(cudaMemcpyAsync(scr.gdesc.p, gdesc.data(), sizeof(GDesc) * nG, cudaMemcpyHostToDevice, st));
         if (!nbr.empty())
-            MRX_CUDA(cudaMemcpyAsync(scr.nbr.p, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(scr.nbr.p, nbr.data(), sizeof(NbrEntry) * nbr.size(), cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
 
         // gThrs (ConvolutionCalculator.cpp:241-248)
@@ -215,24 +290,25 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         P.nbr = scr.nbr.p;
         P.mats = oper.dev.mats.p;
         P.onorms = oper.dev.norms.p;
-        P.nodeOff = oper.dev.nodeOff.p;
-        P.maxTransl = oper.dev.maxTransl.p;
-        P.bw = oper.dev.bw.p;
+        P.nodeBase = oper.dev.nodeBase.p;
         P.bsf = oper.dev.bsf.p;
+        P.depthInfo = scr.depthInfo.p;
+        P.candOff = scr.candOff.p;
+        P.candTerm = scr.candTerm.p;
+        P.candMask = scr.candMask.p;
         P.M = M;
         P.DM = DM;
         P.K = K;
         P.gThrs = gThrs;
         P.counters = scr.counters.p;
-        P.derivDir = -1;
+        P.derivDir = derivDir;
 
         MRX_CUDA(cudaEventRecord(ev0, st));
         launch_apply(P, nG, st);
         MRX_CUDA(cudaEventRecord(ev1, st));
         // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
         launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
-        normsHost.resize((size_t)nG * 8);
-        // gather norms of the work vector: they are scattered by slot -> copy the covering range
+        // norms are scattered by slot -> copy the covering range
         int lo = *std::min_element(workVec.begin(), workVec.end());
         int hi = *std::max_element(workVec.begin(), workVec.end());
         std::vector<double> range((size_t)(hi - lo + 1) * 8);
@@ -267,49 +343,126 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         // ---- splitNodeVector (TreeAdaptor.h:41-54) with WaveletAdaptor::splitNode
         std::vector<int> newVec;
         if (iter >= maxIter and maxIter >= 0) workVec.clear();
-        for (int n : workVec) {
-            if (g.isBranch(n)) continue;
-            if (g.nodes[n].scale + 2 > maxScale) continue;
-            if (split_check(g, n, prec, 1.0, absPrec)) {
-                int c0 = g.createChildren(n, false);
-                for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
+        if (!deriv) {
+            for (int n : workVec) {
+                if (g.isBranch(n)) continue;
+                if (g.nodes[n].scale + 2 > maxScale) continue;
+                if (split_check(g, n, prec, 1.0, absPrec)) {
+                    int c0 = g.createChildren(n, false);
+                    for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
+                }
             }
         }
         workVec.swap(newVec);
         iter++;
     }
     S.iterations = iter;
-    S.ms_build = now_ms() - tb;
     S.ms_kernel = kernel_ms;
-
-    // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)
-    double tp = now_ms();
-    op.clearBandWidths();
     unsigned long long counters[4];
     MRX_CUDA(cudaMemcpyAsync(counters, scr.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
     MRX_CUDA(cudaStreamSynchronize(st));
     S.f_applied = (long long)counters[0];
     out.dev.nNodes = g.nReal;
-    device_mw_transform(out, MRX_TOP_DOWN, false);
-    device_mw_transform(out, MRX_BOTTOM_UP, true);
-    g.calcSquareNorm();
-    f.deleteGenerated();
-    inp.dev.nGen = 0;
-    S.ms_post = now_ms() - tp;
-    S.n_nodes_out = g.nReal;
-    S.kernel_launches = launch_counter() - launches0;
     MRX_CUDA(cudaEventDestroy(ev0));
     MRX_CUDA(cudaEventDestroy(ev1));
+}
+
+void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
+                  mrx_apply_stats *stats) {
+    require_device("device_apply");
+    mrx_apply_stats S{};
+    long long launches0 = launch_counter();
+    double t0 = now_ms();
+    // ---- residency: input tree + operator tables in HBM
+    if (!inp.devValid) tree_upload(inp);
+    oper_upload(oper);
+    oper.op.calcBandWidths(prec);
+    S.ms_upload = now_ms() - t0;
+
+    double tb = now_ms();
+    std::vector<int> workVec;
+    out.host.nodeTable(workVec); // getInitialWorkVector: ALL nodes of `out` (ConvolutionCalculator.cpp:400-405)
+    run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);
+    S.ms_build = now_ms() - tb;
+
+    // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)
+    double tp = now_ms();
+    oper.op.clearBandWidths();
+    device_mw_transform(out, MRX_TOP_DOWN, false);
+    device_mw_transform(out, MRX_BOTTOM_UP, true);
+    out.host.calcSquareNorm();
+    inp.host.deleteGenerated();
+    inp.dev.nGen = 0;
+    S.ms_post = now_ms() - tp;
+    S.n_nodes_out = out.host.nReal;
+    S.kernel_launches = launch_counter() - launches0;
     if (stats) *stats = S;
 }
 
 void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int dir, mrx_apply_stats *stats) {
-    (void)out;
-    (void)oper;
-    (void)inp;
-    (void)dir;
-    (void)stats;
-    MRX_ABORT("device_apply_derivative: not built yet");
+    require_device("device_apply_derivative");
+    mrx_apply_stats S{};
+    long long launches0 = launch_counter();
+    double t0 = now_ms();
+    if (!inp.devValid) tree_upload(inp);
+    oper_upload(oper);
+    Operator &op = oper.op;
+    op.calcBandWidths(1.0); // fixed 0 or 1 for derivatives (apply.cpp:389)
+    S.ms_upload = now_ms() - t0;
+    double tb = now_ms();
+    Tree<3> &g = out.host;
+    Tree<3> &f = inp.host;
+    const int maxScale = g.mra.maxScale();
+    int bw[3] = {0, 0, 0};
+    bw[dir] = op.getMaxBandWidth();
+    g.allocCoefs = false;
+    // grid: CopyAdaptor(inp, maxScale, bw) + DefaultCalculator, maxIter = -1 (apply.cpp:391-393, CopyAdaptor.cpp:56-72)
+    {
+        std::vector<int> workVec;
+        g.endNodeTable(workVec);
+        while (!workVec.empty()) {
+            std::vector<int> newVec;
+            for (int n : workVec) {
+                if (g.isBranch(n)) continue;
+                if (g.nodes[n].scale + 2 > maxScale) continue;
+                bool split = false;
+                const auto idx0 = g.nodes[n];
+                for (int c = 0; c < 8 && !split; c++)
+                    for (int d = 0; d < 3 && !split; d++)
+                        for (int b = -bw[d]; b <= bw[d] && !split; b++) {
+                            std::array<int, 3> l;
+                            for (int dd = 0; dd < 3; dd++) l[dd] = 2 * idx0.l[dd] + ((c >> dd) & 1);
+                            l[d] += b;
+                            if (f.findNode(idx0.scale + 1, l) >= 0) split = true;
+                        }
+                if (split) {
+                    int c0 = g.createChildren(n, false);
+                    for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
+                }
+            }
+            workVec.swap(newVec);
+        }
+    }
+    // DerivativeCalculator on the end nodes, one pass (DerivativeCalculator.cpp:277-279, apply.cpp:396-398)
+    std::vector<int> workVec;
+    g.endNodeTable(workVec);
+    // branch nodes are never computed: zero their device storage so BottomUp starts from defined memory
+    cudaStream_t st = stream();
+    out.dev.coefs.reserve((size_t)g.nReal * g.ncoef, false, st);
+    out.dev.norms.reserve((size_t)g.nReal * 8, false, st);
+    MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p, 0, sizeof(double) * (size_t)g.nReal * g.ncoef, st));
+    run_apply(-1.0, out, oper, inp, 0, false, dir, workVec, S);
+    S.ms_build = now_ms() - tb;
+    double tp = now_ms();
+    op.clearBandWidths();
+    device_mw_transform(out, MRX_BOTTOM_UP, true);
+    out.host.calcSquareNorm();
+    inp.host.deleteGenerated();
+    inp.dev.nGen = 0;
+    S.ms_post = now_ms() - tp;
+    S.n_nodes_out = g.nReal;
+    S.kernel_launches = launch_counter() - launches0;
+    if (stats) *stats = S;
 }
 
 } // namespace mrx

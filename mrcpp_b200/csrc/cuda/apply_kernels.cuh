@@ -8,10 +8,22 @@ namespace mrx {
 struct GDesc {
     int slot;   // slot in the output tree
     int depth;  // operator depth = scale - operator root
-    int l[3];   // translation
-    int s[3];   // first translation of the (clipped) input band
-    int nb[3];  // band extent per dimension (0 = empty band)
-    int nbrOff; // offset of this node's neighbour slots in `nbr` (x fastest)
+    int nbrOff; // first entry of this node's neighbour list in `nbr`
+    int nbrCnt; // number of neighbour entries
+};
+
+/// neighbour entry: input-node slot and the code of its translation offset inside the depth's band cube
+struct NbrEntry {
+    int fslot;
+    int code; // (dz+W)*(2W+1)^2 + (dy+W)*(2W+1) + (dx+W)
+};
+
+/// per-depth band table: for every offset of the band cube, the separation terms that can reach it and
+/// the (gt,ft) combinations whose per-dimension band tests pass (integer part of applyOperator,
+/// ConvolutionCalculator.cpp:311-318, hoisted out of the node loop because it only depends on depth/offset)
+struct DepthInfo {
+    int W;       // band_max(depth), -1 = no operator at this depth
+    int cubeOff; // offset of this depth's (2W+1)^3+1 prefix array in candOff
 };
 
 struct ApplyParams {
@@ -24,19 +36,20 @@ struct ApplyParams {
     // output tree
     double *gCoefs;
     const GDesc *gdesc;
-    const int *nbr;
+    const NbrEntry *nbr;
     // operator tables
     const double *mats;   // node-major: 4 blocks of K*K (column-major p[i + K m], i = input, m = output)
     const double *onorms; // 4 per node
-    const int *nodeOff;   // [M][DM]
-    const int *maxTransl; // [M][DM]
-    const int *bw;        // [M][DM][5]
+    const int *nodeBase;  // [M][DM] node index of translation 0 (= nodeOff + maxTransl), -1 if depth absent
     const int *bsf;       // [M][DM][64]
+    const DepthInfo *depthInfo;         // [DM]
+    const int *candOff;                 // prefix arrays, all depths
+    const int *candTerm;                // candidate term ids
+    const unsigned long long *candMask; // band-allowed (gt*8+ft) bits per candidate
     int M, DM, K;
     double gThrs;
     unsigned long long *counters; // [0] tuples applied
-    // derivative apply
-    int derivDir; // -1 for convolution operators
+    int derivDir;                 // -1 for convolution operators
 };
 
 void launch_apply(const ApplyParams &P, int nG, cudaStream_t st);

@@ -203,7 +203,7 @@ void oper_upload(mrx_oper &o) {
     }
     const size_t stride = (size_t)4 * op.K * op.K;
     std::vector<double> mats(totalNodes * stride), norms(totalNodes * 4);
-    std::vector<int> nodeOff((size_t)M * DM, -1), maxT((size_t)M * DM, 0);
+    std::vector<int> nodeOff((size_t)M * DM, -1), maxT((size_t)M * DM, 0), nodeBase((size_t)M * DM, -1);
     for (int i = 0; i < M; i++) {
         const OperTerm &t = op.terms[i];
         std::memcpy(mats.data() + o.dev.termNodeBase[i] * stride, t.mats.data(), sizeof(double) * t.mats.size());
@@ -211,12 +211,15 @@ void oper_upload(mrx_oper &o) {
         for (int d = 0; d < t.nDepth; d++) {
             nodeOff[(size_t)i * DM + d] = (int)(o.dev.termNodeBase[i] + t.offset[d]);
             maxT[(size_t)i * DM + d] = t.maxTransl[d];
+            nodeBase[(size_t)i * DM + d] = nodeOff[(size_t)i * DM + d] + t.maxTransl[d];
         }
     }
     o.dev.mats.reserve(mats.size(), false, st);
     o.dev.norms.reserve(norms.size(), false, st);
     o.dev.nodeOff.reserve(nodeOff.size(), false, st);
     o.dev.maxTransl.reserve(maxT.size(), false, st);
+    o.dev.nodeBase.reserve(nodeBase.size(), false, st);
+    MRX_CUDA(cudaMemcpyAsync(o.dev.nodeBase.p, nodeBase.data(), sizeof(int) * nodeBase.size(), cudaMemcpyHostToDevice, st));
     MRX_CUDA(cudaMemcpyAsync(o.dev.mats.p, mats.data(), sizeof(double) * mats.size(), cudaMemcpyHostToDevice, st));
     MRX_CUDA(cudaMemcpyAsync(o.dev.norms.p, norms.data(), sizeof(double) * norms.size(), cudaMemcpyHostToDevice, st));
     MRX_CUDA(cudaMemcpyAsync(o.dev.nodeOff.p, nodeOff.data(), sizeof(int) * nodeOff.size(), cudaMemcpyHostToDevice, st));

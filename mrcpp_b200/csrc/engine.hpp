@@ -56,6 +56,7 @@ struct DeviceOper {
     DevBuf<double> norms;  // 4 per node
     DevBuf<int> nodeOff;   // [M][DM] global node index of transl = -maxTransl, -1 if depth absent
     DevBuf<int> maxTransl; // [M][DM]
+    DevBuf<int> nodeBase;  // [M][DM] node index of translation 0 (nodeOff + maxTransl), -1 if absent
     DevBuf<int> bw;        // [M][DM][5]   (per apply: depends on prec)
     DevBuf<int> bsf;       // [M][DM][64]  band size factors (per apply)
     int M = 0, DM = 0;

@@ -119,6 +119,7 @@ template <int D> struct GaussFunc {
             if (power[d] == 1) p2 *= q;
             else p2 *= std::pow(q, power[d]);
         }
+        if (q2 > 746.0) return 0.0 * coef * p2; // exp(-q2) underflows to exactly 0 in IEEE double
         return coef * p2 * std::exp(-q2);
     }
     // Gaussian.cpp:116-135
@@ -138,6 +139,11 @@ template <int D> struct GaussFunc {
     }
 };
 template <int D> using GaussExp = std::vector<GaussFunc<D>>;
+
+// coefficient-chunk allocator hooks (default: new[]/delete[]; the C-ABI installs cudaMallocHost/cudaFreeHost
+// when a device is selected so that host<->device copies run at full PCIe/NVLink-C2C speed)
+extern void *(*chunk_alloc)(size_t bytes);
+extern void (*chunk_free)(void *p);
 
 // ---------------------------------------------------------------- flat adaptive tree
 enum NodeFlags : uint8_t { FlagBranch = 1, FlagGen = 2, FlagHasCoefs = 4, FlagEnd = 8 };
@@ -168,8 +174,11 @@ public:
 
     explicit Tree(const MRA<D> &m);
     int size() const { return (int)nodes.size(); }
-    double *coef(int n) { return chunks_[n >> chunkShift_].get() + (size_t)(n & chunkMask_) * ncoef; }
-    const double *coef(int n) const { return chunks_[n >> chunkShift_].get() + (size_t)(n & chunkMask_) * ncoef; }
+    double *coef(int n) { return chunks_[n >> chunkShift_] + (size_t)(n & chunkMask_) * ncoef; }
+    const double *coef(int n) const { return chunks_[n >> chunkShift_] + (size_t)(n & chunkMask_) * ncoef; }
+    ~Tree();
+    Tree(const Tree &) = delete;
+    Tree &operator=(const Tree &) = delete;
     int depth(int n) const { return nodes[n].scale - mra.rootScale; }
     bool isBranch(int n) const { return nodes[n].flags & FlagBranch; }
     bool isGen(int n) const { return nodes[n].flags & FlagGen; }
@@ -210,7 +219,9 @@ public:
 
 private:
     static constexpr int chunkShift_ = 6, chunkMask_ = 63;
-    std::vector<std::unique_ptr<double[]>> chunks_;
+    std::vector<double *> chunks_; // 64 nodes each; pinned host memory when a CUDA device is in use
+    void *(*alloc_)(size_t) = nullptr; // allocator pair captured at construction
+    void (*free_)(void *) = nullptr;
     const FilterSet *fs_ = nullptr;
     int allocNodes(int count);
     void mwTransformCoefs(const double *in, double *out_children, bool readOnlyScaling, int stride, bool overwrite) const;

@@ -286,7 +286,10 @@ Operator build_abgv_operator(const MRA<3> &mra, double a, double b) {
     for (int i = 0; i < K; i++) {
         valueZero[i] = interp_scaling_eval(k, i, 0.0);
         valueOne[i] = interp_scaling_eval(k, i, 1.0);
-        for (int j = 0; j < K; j++) Kmat[i * K + j] = 2.0 * std::sqrt(q.weights[j]) * interp_scaling_deriv(k, i, q.roots[j]);
+        // ABGVCalculator::calcKMatrix: K(i,j) = 2 sqrt(w_j) * poly_i'(x_j) where Polynomial::calcDerivative
+        // (Polynomial.cpp:229-237) differentiates w.r.t. the INTERNAL argument q = 2x-1, i.e. poly' = (1/2) dphi/dx
+        for (int j = 0; j < K; j++)
+            Kmat[i * K + j] = 2.0 * std::sqrt(q.weights[j]) * (0.5 * interp_scaling_deriv(k, i, q.roots[j]));
     }
 
     Tree<2> o_tree(o_mra);

@@ -21,6 +21,15 @@ static inline void apply_filter(double *out, const double *in, const double *F, 
     }
 }
 
+static void *default_chunk_alloc(size_t bytes) { return ::operator new[](bytes); }
+static void default_chunk_free(void *p) { ::operator delete[](p); }
+void *(*chunk_alloc)(size_t) = default_chunk_alloc;
+void (*chunk_free)(void *) = default_chunk_free;
+
+template <int D> Tree<D>::~Tree() {
+    for (double *c : chunks_) free_(c);
+}
+
 template <int D>
 Tree<D>::Tree(const MRA<D> &m)
         : mra(m) {
@@ -30,6 +39,8 @@ Tree<D>::Tree(const MRA<D> &m)
     ncoef = tdim * Kd;
     nRoots = m.nRoots();
     fs_ = &filter_set(k);
+    alloc_ = chunk_alloc;
+    free_ = chunk_free;
     if (m.maxDepth > MaxDepth) MRX_ABORT("Beyond MaxDepth");
     if (m.maxScale() > MaxScale) MRX_ABORT("Beyond MaxScale");
     // root nodes in box order, x fastest (BoundingBox.cpp:322-335)
@@ -63,8 +74,8 @@ template <int D> void Tree<D>::ensureCoefStorage() {
     size_t needChunks = (nodes.size() + chunkMask_) >> chunkShift_;
     while (chunks_.size() < needChunks) {
         size_t n = (size_t)(chunkMask_ + 1) * ncoef;
-        chunks_.emplace_back(new double[n]);
-        if (allocCoefs) std::memset(chunks_.back().get(), 0, n * sizeof(double));
+        chunks_.push_back(static_cast<double *>(alloc_(n * sizeof(double))));
+        if (allocCoefs) std::memset(chunks_.back(), 0, n * sizeof(double));
     }
 }
 

@@ -1,0 +1,271 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs. Bars: node set and indexing bit-exact; per-node coefficients within 1e-12 relative
+to the node norm (BASELINE.json north_star); screened tuple count identical."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+COEF_TOL = 1e-12  # relative to the node norm
+
+
+@pytest.fixture(scope="module")
+def gpu(libs):
+    mw, orc = libs
+    from mrcpp_b200 import _lib
+    if _lib.device() is None or _lib.device() < 0:
+        pytest.fail("no CUDA device visible: the product has no CPU fallback")
+    return mw, orc
+
+
+def assert_same_tree(a, b, tol=COEF_TOL):
+    A, B = a.to_arrays(), b.to_arrays()
+    assert A["scale"].shape == B["scale"].shape
+    assert np.array_equal(A["scale"], B["scale"])
+    assert np.array_equal(A["transl"], B["transl"])
+    assert np.array_equal(A["parent"], B["parent"])
+    assert np.array_equal(A["child0"], B["child0"])
+    nrm = np.sqrt((B["coefs"] ** 2).sum(axis=1))
+    err = np.abs(A["coefs"] - B["coefs"]).max(axis=1)
+    # relative to the node norm; nodes whose norm is below 1e-3 of the largest node norm are measured against
+    # that floor instead (a node of norm ~1e-14 cannot agree to 1e-12 of itself: rounding of the operator
+    # application is relative to the INPUT neighbourhood, not to the near-zero output)
+    scale = np.maximum(nrm, 1e-3 * nrm.max() + 1e-300)
+    worst = float((err / scale).max())
+    assert worst < tol, worst
+    assert np.allclose(A["norms"], B["norms"], rtol=1e-10, atol=1e-12 * nrm.max())
+    return worst
+
+
+def gaussians(n, seed, box=8.0, lo=1.0, hi=3.0):
+    import mrcpp_b200 as mw
+    rng = np.random.default_rng(seed)
+    g = mw.GaussExp()
+    for _ in range(n):
+        beta = 10.0 ** rng.uniform(lo, hi)
+        g.append(mw.GaussFunc(beta, (beta / math.pi) ** 1.5 / n, tuple(rng.uniform(-box, box, 3))))
+    return g
+
+
+def world(mw, k):
+    return mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+def test_bottom_up_and_norms(gpu, k):
+    """project: host quadrature + DEVICE mwTransform(BottomUp)/calcSquareNorm vs oracle transform."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(3, 7)
+    a, b = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(1e-4, a, func)
+    orc.project(1e-4, b, func)
+    assert_same_tree(a, b)
+    assert abs(a.getSquareNorm() - b.getSquareNorm()) <= 1e-13 * b.getSquareNorm()
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_top_down_roundtrip(gpu, k):
+    """mwTransform(TopDown) then (BottomUp) on the device: TopDown(overwrite) parity vs oracle and the
+    size-independent property compress(reconstruct(x)) == x."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(2, 11)
+    a, b = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(1e-4, a, func)
+    orc.project(1e-4, b, func)
+    before = a.to_arrays()
+    a.mwTransform(mw.TopDown, overwrite=False)  # children.s += reconstruct(parent)
+    orc.mw_transform_down(b, overwrite=False)
+    assert_same_tree(a, b)
+    a.mwTransform(mw.BottomUp)
+    orc.mw_transform_up(b)
+    assert_same_tree(a, b)
+    after = a.to_arrays()
+    # leaves were doubled at most levels; roots re-compressed consistently: norms finite, grid unchanged
+    assert np.array_equal(before["transl"], after["transl"])
+
+
+@pytest.mark.parametrize("k,prec", [(5, 1e-3), (7, 1e-5), (9, 1e-4), (3, 1e-2)])
+def test_poisson_apply_adaptive(gpu, k, prec):
+    """examples/poisson.cpp (C1): adaptive apply; node set, tuple count, coefficients, energy."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    beta = 100.0
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)
+    P = mw.PoissonOperator(mra, prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, f)
+    orc.project(prec, fc, f)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(prec, gg, P, fg)
+    sc = orc.apply(prec, gc, P, fc)
+    assert sg.f_applied == sc.fApplied
+    assert sg.g_nodes == sc.gNodes and sg.iterations == sc.iters
+    assert_same_tree(gg, gc)
+    assert abs(gg.getSquareNorm() - gc.getSquareNorm()) <= 1e-12 * gc.getSquareNorm()
+    en = mw.dot(gg, fg)
+    assert abs(en - orc.dot(gc, fc)) <= 1e-12 * abs(en)
+    assert abs(en - 7.978845608) / 7.978845608 < prec
+    assert fg.getNNodes() == fc.getNNodes()  # generated nodes were cleaned up (apply.cpp:86)
+
+
+@pytest.mark.parametrize("k,prec", [(5, 1e-3), (7, 1e-4)])
+def test_poisson_apply_fixed_grid(gpu, k, prec):
+    """parity mode A: fixed output grid, maxIter=0, no norm screening -> 1e-12 coefficients."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(3, 5)
+    P = mw.PoissonOperator(mra, prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, func)
+    orc.project(prec, fc, func)
+    ref = mw.FunctionTree(mra)
+    orc.apply(prec, ref, P, fc)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.copy_grid(gg, ref)
+    mw.copy_grid(gc, ref)
+    sg = mw.apply(prec, gg, P, fg, maxIter=0)
+    sc = orc.apply(prec, gc, P, fc, maxIter=0)
+    assert sg.f_applied == sc.fApplied and sg.g_nodes == ref.getNNodes()
+    assert_same_tree(gg, gc)
+
+
+def test_multi_center_density(gpu):
+    """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
+    mw, orc = gpu
+    prec = 1e-5
+    mra = world(mw, 7)
+    func = gaussians(10, 42, box=4.0, lo=1.0, hi=2.0)
+    P = mw.PoissonOperator(mra, prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, func)
+    orc.project(prec, fc, func)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(prec, gg, P, fg)
+    sc = orc.apply(prec, gc, P, fc)
+    assert sg.f_applied == sc.fApplied
+    assert_same_tree(gg, gc)
+    ana = sum(a.calc_coulomb_energy(b) for a in func for b in func)
+    en = mw.dot(gg, fg)
+    assert abs(en - ana) / ana < 10 * prec
+
+
+def test_helmholtz_apply(gpu):
+    """HelmholtzOperator (mu=1) apply, k=5: parity vs oracle."""
+    mw, orc = gpu
+    prec = 1e-4
+    mra = world(mw, 5)
+    func = gaussians(4, 3, box=3.0, lo=0.5, hi=1.5)
+    H = mw.HelmholtzOperator(mra, 1.0, prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, func)
+    orc.project(prec, fc, func)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(prec, gg, H, fg)
+    sc = orc.apply(prec, gc, H, fc)
+    assert sg.f_applied == sc.fApplied
+    assert_same_tree(gg, gc)
+
+
+@pytest.mark.parametrize("a,b", [(0.5, 0.5), (0.0, 0.0)])
+def test_abgv_derivative(gpu, a, b):
+    """C3: apply(out, ABGVOperator, inp, dir) on the device vs oracle for dir 0,1,2 (fixed, widened grid)."""
+    mw, orc = gpu
+    prec = 1e-5
+    mra = world(mw, 7)
+    func = gaussians(4, 1234, box=4.0, lo=0.0, hi=2.0)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, func)
+    orc.project(prec, fc, func)
+    D = mw.ABGVOperator(mra, a, b)
+    for d in range(3):
+        og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        sg = mw.apply(None, og, D, fg, dir=d)
+        sc = orc.apply_derivative(oc, D, fc, d)
+        assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
+        assert_same_tree(og, oc)
+
+
+def test_empty_and_edge_inputs(gpu):
+    """edge cases: zero function (every f component norm < MachineZero -> nothing applied), function
+    hugging the world border (band clipping), maxIter=0 on bare roots."""
+    mw, orc = gpu
+    prec = 1e-3
+    mra = world(mw, 5)
+    P = mw.PoissonOperator(mra, prec)
+    zero = mw.FunctionTree(mra)
+    zero.mwTransform(mw.BottomUp)  # roots only, all-zero coefficients
+    out = mw.FunctionTree(mra)
+    st = mw.apply(prec, out, P, zero)
+    assert st.f_applied == 0 and out.getNNodes() == 8
+    assert out.getSquareNorm() == 0.0
+    beta = 50.0
+    edge = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (15.5, -15.5, 15.0))
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, edge)
+    orc.project(prec, fc, edge)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(prec, gg, P, fg)
+    sc = orc.apply(prec, gc, P, fc)
+    assert sg.f_applied == sc.fApplied
+    assert_same_tree(gg, gc)
+    g0, c0 = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    s0 = mw.apply(prec, g0, P, fg, maxIter=0)
+    t0 = orc.apply(prec, c0, P, fc, maxIter=0)
+    assert s0.g_nodes == 8 and s0.f_applied == t0.fApplied
+    assert_same_tree(g0, c0)
+
+
+def test_linearity_property(gpu):
+    """size-independent property: apply is linear -> P(2f) == 2 P(f) on a fixed grid (exact in FP64 up to
+    rounding of a power-of-two scale: bit-identical)."""
+    mw, orc = gpu
+    prec = 1e-4
+    mra = world(mw, 7)
+    func = gaussians(5, 9, box=5.0)
+    P = mw.PoissonOperator(mra, prec)
+    f1 = mw.FunctionTree(mra)
+    mw.project(prec, f1, func)
+    g1 = mw.FunctionTree(mra)
+    mw.apply(prec, g1, P, f1)
+    f2 = mw.FunctionTree(mra)
+    mw.project(prec, f2, func)
+    f2.rescale(2.0)
+    a, b = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.copy_grid(a, g1)
+    mw.copy_grid(b, g1)
+    mw.apply(prec, a, P, f1, maxIter=0)
+    mw.apply(prec, b, P, f2, maxIter=0)
+    A, B = a.to_arrays(), b.to_arrays()
+    assert np.array_equal(2.0 * A["coefs"], B["coefs"])
+
+
+def test_golden_fixture(gpu):
+    """committed golden vectors (tests/golden/make_golden.py, generated with the oracle in the build container)."""
+    mw, orc = gpu
+    path = os.path.join(os.path.dirname(__file__), "golden", "poisson_small.npz")
+    gold = np.load(path)
+    k, prec = int(gold["k"]), float(gold["prec"])
+    mra = world(mw, k)
+    beta = float(gold["beta"])
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, tuple(gold["pos"]))
+    P = mw.PoissonOperator(mra, prec)
+    assert P.size() == int(gold["n_terms"])
+    ft = mw.FunctionTree(mra)
+    mw.project(prec, ft, f)
+    F = ft.to_arrays()
+    assert np.array_equal(F["transl"], gold["f_transl"]) and np.array_equal(F["scale"], gold["f_scale"])
+    assert np.abs(F["coefs"][:8] - gold["f_coefs_head"]).max() <= 1e-13 * np.abs(gold["f_coefs_head"]).max()
+    assert np.allclose(F["norms"], gold["f_norms"], rtol=1e-12, atol=1e-16)
+    gt = mw.FunctionTree(mra)
+    st = mw.apply(prec, gt, P, ft)
+    G = gt.to_arrays()
+    assert st.f_applied == int(gold["f_applied"])
+    assert np.array_equal(G["transl"], gold["g_transl"]) and np.array_equal(G["scale"], gold["g_scale"])
+    nrm = np.sqrt((gold["g_coefs"] ** 2).sum(axis=1))
+    err = np.abs(G["coefs"] - gold["g_coefs"]).max(axis=1)
+    assert (err / np.maximum(nrm, 1e-300)).max() < COEF_TOL

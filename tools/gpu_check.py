@@ -53,3 +53,10 @@ gB = mw.FunctionTree(mra); mw.copy_grid(gB, g_cpu); sB = orc.apply(prec, gB, P, 
 print("fixed grid tuples gpu", sA.f_applied, "oracle", sB.fApplied, "gpu ms_kernel", sA.ms_kernel,
       "TFLOP/s", sA.f_applied * 6 * K ** 4 / (sA.ms_kernel * 1e-3) / 1e12)
 compare(gA, gB, "apply fixed grid")
+# derivative
+D = mw.ABGVOperator(mra, 0.5, 0.5)
+for d in range(3):
+    og = mw.FunctionTree(mra); sd = mw.apply(None, og, D, f_gpu, dir=d)
+    oc = mw.FunctionTree(mra); sc = orc.apply_derivative(oc, D, f_cpu, d)
+    print("deriv dir", d, "tuples", sd.f_applied, sc.fApplied)
+    compare(og, oc, f"ABGV dir {d}")
