@@ -2,7 +2,10 @@
 // call forwards to the CUDA engine and aborts when no device was selected (no CPU fallback).
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "engine.hpp"
 
@@ -13,6 +16,9 @@ bool g_device_on = false;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
 long long g_launches = 0;
+std::mutex g_pin_mutex;
+std::map<size_t, std::vector<void *>> g_pin_free;
+std::map<void *, size_t> g_pin_size;
 } // namespace
 
 namespace mrx {
@@ -52,12 +58,35 @@ int mrx_init(const char *table_path, int device) {
         g_device = device;
         g_device_on = true;
         // pinned coefficient chunks from now on
+        // pinned coefficient chunks, recycled through a free list (cudaMallocHost is slow)
         chunk_alloc = [](size_t bytes) -> void * {
+            {
+                std::lock_guard<std::mutex> lock(g_pin_mutex);
+                auto &fl = g_pin_free[bytes];
+                if (!fl.empty()) {
+                    void *p = fl.back();
+                    fl.pop_back();
+                    return p;
+                }
+            }
             void *p = nullptr;
             if (cudaMallocHost(&p, bytes) != cudaSuccess) MRX_ABORT("cudaMallocHost failed");
+            std::lock_guard<std::mutex> lock(g_pin_mutex);
+            g_pin_size[p] = bytes;
             return p;
         };
-        chunk_free = [](void *p) { cudaFreeHost(p); };
+        chunk_free = [](void *p) {
+            std::lock_guard<std::mutex> lock(g_pin_mutex);
+            g_pin_free[g_pin_size[p]].push_back(p);
+        };
+        // device pool: keep freed memory cached
+        {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        }
     }
     return 0;
 }

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <map>
+#include <memory>
 
 #include "../engine.hpp"
 #include "apply_kernels.cuh"
@@ -65,26 +67,32 @@ struct Scratch {
     DevBuf<int> genItems;
     DevBuf<int> gslots;
     DevBuf<unsigned long long> counters;
-    DevBuf<DepthInfo> depthInfo;
-    DevBuf<int> candOff;
-    DevBuf<int> candTerm;
-    DevBuf<unsigned long long> candMask;
+    DevBuf<GDesc> units;
+    DevBuf<int> reduceItems;
+    DevBuf<double> partials;
 };
 
 /// Host copy of the per-depth band tables (see DepthInfo). Built lazily for the depths that occur.
 struct BandTables {
+    double prec = 0.0; // cache key: band widths depend on the apply precision
+    int derivDir = -2;
+    DevBuf<DepthInfo> d_info;
+    DevBuf<int> d_candOff;
+    DevBuf<int> d_candTerm;
+    DevBuf<unsigned long long> d_candMask;
     std::vector<DepthInfo> info;                // [DM]
     std::vector<char> built;                    // [DM]
     std::vector<int> candOff;                   // concatenated prefix arrays
     std::vector<int> candTerm;
     std::vector<unsigned long long> candMask;
     std::vector<std::vector<std::array<int, 4>>> needed; // per depth: (dx,dy,dz,code) of offsets with candidates
+    std::vector<std::vector<double>> maxO;               // per depth, per needed offset: max_{term,combo} |O|^3 * bandSizeFactor
     bool dirty = false;
 
     // integer part of the screening: per-term max width (applyOperComp :283), per-dimension band test per
     // component (applyOperator :311-318, OperatorTree::isOutsideBand), T block only at depth 0 (calcNode :261).
     // derivative operators: DerivativeCalculator::applyOperator (:211-249).
-    void build(const Operator &op, int depth, int derivDir) {
+    void build(const Operator &op, int depth, int derivDir, const std::vector<int> &bsf, int DM) {
         const int M = op.size();
         const int W = op.getMaxBandWidth(depth);
         info[depth].W = W;
@@ -116,6 +124,7 @@ struct BandTables {
         }
         const unsigned long long tExcl = (derivDir < 0 && depth != 0) ? ~1ull : ~0ull; // drop (gt=0,ft=0)
         needed[depth].clear();
+        maxO[depth].clear();
         for (int z = -W; z <= W; z++)
             for (int y = -W; y <= W; y++)
                 for (int x = -W; x <= W; x++) {
@@ -124,6 +133,7 @@ struct BandTables {
                     const int ax = std::abs(x), ay = std::abs(y), az = std::abs(z);
                     const int maxD = std::max(ax, std::max(ay, az));
                     const size_t before = candTerm.size();
+                    double mo = 0.0;
                     for (int t = 0; t < M; t++) {
                         if (derivDir < 0 && maxD > op.terms[t].maxWidth(depth)) continue;
                         unsigned long long m = dimMask[((size_t)t * 3 + 0) * (W + 1) + ax] &
@@ -132,9 +142,29 @@ struct BandTables {
                         if (m) {
                             candTerm.push_back(t);
                             candMask.push_back(m);
+                            if (derivDir < 0) {
+                                // upper bound of oNorm * bandSizeFactor over the allowed combos (same product order as the kernel)
+                                const OperTerm &ot = op.terms[t];
+                                const double *n0 = ot.nodeNorms(depth, x), *n1 = ot.nodeNorms(depth, y), *n2 = ot.nodeNorms(depth, z);
+                                const int *bs = bsf.data() + ((size_t)t * DM + depth) * 64;
+                                unsigned long long mm = m;
+                                while (mm) {
+                                    int b = __builtin_ctzll(mm);
+                                    mm &= mm - 1;
+                                    int gt = b >> 3, ft = b & 7;
+                                    double o = 1.0;
+                                    o *= n0[2 * (gt & 1) + (ft & 1)];
+                                    o *= n1[2 * ((gt >> 1) & 1) + ((ft >> 1) & 1)];
+                                    o *= n2[2 * ((gt >> 2) & 1) + ((ft >> 2) & 1)];
+                                    mo = std::max(mo, o * bs[b]);
+                                }
+                            }
                         }
                     }
-                    if (candTerm.size() != before) needed[depth].push_back({x, y, z, code});
+                    if (candTerm.size() != before) {
+                        needed[depth].push_back({x, y, z, code});
+                        maxO[depth].push_back(mo);
+                    }
                 }
         candOff.push_back((int)candTerm.size());
     }
@@ -148,13 +178,11 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     Operator &op = oper.op;
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
-    {
-        std::vector<int> bsf, bw;
-        band_size_factors(op, DM, bsf, bw);
-        oper.dev.bsf.reserve(bsf.size(), false, st);
-        MRX_CUDA(cudaMemcpyAsync(oper.dev.bsf.p, bsf.data(), sizeof(int) * bsf.size(), cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaStreamSynchronize(st));
-    }
+    std::vector<int> bsf, bwTab;
+    band_size_factors(op, DM, bsf, bwTab);
+    oper.dev.bsf.reserve(bsf.size(), false, st);
+    MRX_CUDA(cudaMemcpyAsync(oper.dev.bsf.p, bsf.data(), sizeof(int) * bsf.size(), cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -167,10 +195,19 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     Scratch scr;
     scr.counters.reserve(4, false, st);
     MRX_CUDA(cudaMemsetAsync(scr.counters.p, 0, 4 * sizeof(unsigned long long), st));
-    BandTables bt;
-    bt.info.assign(DM, DepthInfo{-1, 0});
-    bt.built.assign(DM, 0);
-    bt.needed.resize(DM);
+    // per-depth band tables are cached on the operator: they depend only on (operator, prec, direction)
+    std::shared_ptr<BandTables> btp = std::static_pointer_cast<BandTables>(oper.bandCache);
+    if (!btp || btp->prec != prec || btp->derivDir != derivDir || (int)btp->info.size() != DM) {
+        btp = std::make_shared<BandTables>();
+        btp->prec = prec;
+        btp->derivDir = derivDir;
+        btp->info.assign(DM, DepthInfo{-1, 0});
+        btp->built.assign(DM, 0);
+        btp->needed.resize(DM);
+        btp->maxO.resize(DM);
+        oper.bandCache = btp;
+    }
+    BandTables &bt = *btp;
 
     cudaEvent_t ev0, ev1;
     MRX_CUDA(cudaEventCreate(&ev0));
@@ -183,50 +220,199 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     std::vector<GDesc> gdesc;
     std::vector<NbrEntry> nbr;
     std::vector<int> newParents;
+    std::vector<double> genBound; // per generated node: norm of its real leaf ancestor (upper bound of its own norm)
+    std::vector<double> fNodeNorm(fRealN);
+    double fMaxNorm = 0.0;
+    for (int n = 0; n < fRealN; n++) {
+        fNodeNorm[n] = std::sqrt(f.sqn[n]);
+        fMaxNorm = std::max(fMaxNorm, fNodeNorm[n]);
+    }
+    double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
+    const bool profile = getenv("MRX_PROFILE") != nullptr;
     while (!workVec.empty()) {
         const int nG = (int)workVec.size();
+        double tq = now_ms();
         // ---- band enumeration (makeOperBand/fillOperBand, :142-222, non-periodic) on the topology,
         //      restricted to offsets that at least one (term, gt, ft) can reach
         gdesc.resize(nG);
         nbr.clear();
         newParents.clear();
+        double gThrsIter = g.squareNorm;
+        if (gThrsIter > 0.0) gThrsIter = prec * 1.0 * std::sqrt(gThrsIter / static_cast<double>(M));
+        const bool screenOn = !deriv && gThrsIter >= 0.0;
+        // global cut: offsets whose largest operator-norm product cannot lift even the largest input node over gThrs
+        // are dropped for every node of this iteration (per depth, computed on first use)
+        std::vector<std::vector<int>> live(DM); // indices into bt.needed[depth]
+        std::vector<char> liveBuilt(DM, 0);
+        auto live_list = [&](int depth) -> const std::vector<int> & {
+            if (!liveBuilt[depth]) {
+                liveBuilt[depth] = 1;
+                const auto &mo = bt.maxO[depth];
+                live[depth].reserve(mo.size());
+                for (size_t oi = 0; oi < mo.size(); oi++)
+                    if (!screenOn || mo[oi] * fMaxNorm * (1.0 + 1e-9) > gThrsIter) live[depth].push_back((int)oi);
+            }
+            return live[depth];
+        };
+        for (int i = 0; i < nG; i++) {
+            const int dep = g.nodes[workVec[i]].scale - op.operRoot;
+            if (dep >= 0 && dep < DM) {
+                if (!bt.built[dep]) bt.build(op, dep, derivDir, bsf, DM);
+                live_list(dep);
+            }
+        }
+        tp_tables += now_ms() - tq;
+        tq = now_ms();
+        // phase 1 (parallel over output nodes): enumerate the band on the topology, prune, record the deepest
+        // existing input node per surviving offset
+        struct Hit {
+            int node;
+            int code;
+            std::array<int, 3> l;
+        };
+        std::vector<std::vector<Hit>> hits(nG);
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int i = 0; i < nG; i++) {
+            const auto &nd = g.nodes[workVec[i]];
+            const int dep = nd.scale - op.operRoot;
+            if (dep < 0 || dep >= DM) continue; // deeper than every operator tree: empty band (:146-151)
+            if (bt.info[dep].W < 0) continue;
+            int lo[3], hi[3];
+            for (int x = 0; x < 3; x++) {
+                int nboxes = f.mra.nboxes[x] * (1 << dep);
+                lo[x] = f.mra.corner[x] * (1 << dep);
+                hi[x] = lo[x] + nboxes - 1;
+            }
+            const auto &need = bt.needed[dep];
+            const auto &mo = bt.maxO[dep];
+            auto &out_hits = hits[i];
+            int cur = -1; // deepest existing input node found for the previous offset (locality: x runs fastest)
+            for (int oi : live[dep]) {
+                const auto &o = need[oi];
+                std::array<int, 3> l = {nd.l[0] + o[0], nd.l[1] + o[1], nd.l[2] + o[2]};
+                if (l[0] < lo[0] || l[0] > hi[0] || l[1] < lo[1] || l[1] > hi[1] || l[2] < lo[2] || l[2] > hi[2]) continue;
+                // walk up from the previous hit until an ancestor of l, then down through existing nodes
+                while (cur >= 0) {
+                    const auto &cn = f.nodes[cur];
+                    int sh = nd.scale - cn.scale;
+                    if (sh >= 0 && (l[0] >> sh) == cn.l[0] && (l[1] >> sh) == cn.l[1] && (l[2] >> sh) == cn.l[2]) break;
+                    cur = cn.parent;
+                }
+                if (cur < 0) cur = f.rootIndex(nd.scale, l);
+                while (f.nodes[cur].scale < nd.scale && f.nodes[cur].child0 >= 0) {
+                    int shift = nd.scale - f.nodes[cur].scale - 1;
+                    int c = ((l[0] >> shift) & 1) | (((l[1] >> shift) & 1) << 1) | (((l[2] >> shift) & 1) << 2);
+                    cur = f.nodes[cur].child0 + c;
+                }
+                if (screenOn) {
+                    // no (term, gt, ft) can pass the norm screening if even the largest operator-norm product times
+                    // an upper bound of |f| stays below gThrs. |f_ft| <= |node| for an existing real node, and a
+                    // generated node is an orthogonal projection of its real leaf ancestor: |gen| <= |leaf|.
+                    double fb = (cur < fRealN) ? fNodeNorm[cur] : genBound[cur - fRealN];
+                    if (mo[oi] * fb * (1.0 + 1e-9) <= gThrsIter) continue;
+                }
+                out_hits.push_back({cur, o[3], l});
+            }
+        }
+        tp_enum += now_ms() - tq;
+        tq = now_ms();
+        // phase 2 (serial, work-vector order): create the missing generated nodes, emit neighbour entries
         for (int i = 0; i < nG; i++) {
             const auto &nd = g.nodes[workVec[i]];
             GDesc &d = gdesc[i];
             d.slot = workVec[i];
             d.depth = nd.scale - op.operRoot;
             d.nbrOff = (int)nbr.size();
-            d.nbrCnt = 0;
-            if (d.depth < 0 || d.depth >= DM) continue; // deeper than every operator tree: empty band (:146-151)
-            if (!bt.built[d.depth]) bt.build(op, d.depth, derivDir);
-            if (bt.info[d.depth].W < 0) continue;
-            int lo[3], hi[3];
-            for (int x = 0; x < 3; x++) {
-                int nboxes = f.mra.nboxes[x] * (1 << d.depth);
-                lo[x] = f.mra.corner[x] * (1 << d.depth);
-                hi[x] = lo[x] + nboxes - 1;
-            }
-            for (const auto &o : bt.needed[d.depth]) {
-                std::array<int, 3> l = {nd.l[0] + o[0], nd.l[1] + o[1], nd.l[2] + o[2]};
-                if (l[0] < lo[0] || l[0] > hi[0] || l[1] < lo[1] || l[1] > hi[1] || l[2] < lo[2] || l[2] > hi[2]) continue;
+            for (const Hit &h : hits[i]) {
+                int node = h.node;
+                if (f.nodes[node].scale < nd.scale) {
+                    double fb = (node < fRealN) ? fNodeNorm[node] : genBound[node - fRealN];
+                    node = f.getNodeTopo(nd.scale, h.l, &newParents); // continues below existing nodes
+                    genBound.resize(f.size() - fRealN, fb);
+                }
                 NbrEntry e;
-                e.fslot = f.getNodeTopo(nd.scale, l, &newParents);
-                e.code = o[3];
+                e.fslot = node;
+                e.code = h.code;
                 nbr.push_back(e);
             }
             d.nbrCnt = (int)nbr.size() - d.nbrOff;
+            d.partial = -1;
         }
+        // ---- work units: nodes with much work are split into chunks of their neighbour list (one CTA each, partial
+        //      sums reduced in chunk order afterwards); units are launched in order of decreasing cost (LPT)
+        std::vector<GDesc> units;
+        std::vector<long long> unitCost;
+        std::vector<int> reduceItems; // (slot, firstPartial, nPartials)
+        int nPartials = 0;
+        {
+            std::vector<long long> cost(nG, 0);
+            long long total = 0;
+            for (int i = 0; i < nG; i++) {
+                const GDesc &d = gdesc[i];
+                if (d.nbrCnt == 0) continue;
+                const int *coff = bt.candOff.data() + bt.info[d.depth].cubeOff;
+                long long c = 0;
+                for (int q = 0; q < d.nbrCnt; q++) {
+                    int code = nbr[d.nbrOff + q].code;
+                    c += coff[code + 1] - coff[code];
+                }
+                cost[i] = c;
+                total += c;
+            }
+            const long long target = std::max<long long>(total / (148 * 4), 512);
+            for (int i = 0; i < nG; i++) {
+                const GDesc &d = gdesc[i];
+                int nChunks = (int)std::min<long long>((cost[i] + target - 1) / target, std::max(d.nbrCnt, 1));
+                if (nChunks <= 1) {
+                    units.push_back(d);
+                    unitCost.push_back(cost[i]);
+                    continue;
+                }
+                const int *coff = bt.candOff.data() + bt.info[d.depth].cubeOff;
+                reduceItems.push_back(d.slot);
+                reduceItems.push_back(nPartials);
+                int made = 0, q0 = 0;
+                long long acc = 0, done = 0;
+                for (int q = 0; q < d.nbrCnt; q++) {
+                    int code = nbr[d.nbrOff + q].code;
+                    acc += coff[code + 1] - coff[code];
+                    // close the chunk when its share of the remaining cost is reached
+                    long long want = (cost[i] - done + (nChunks - made) - 1) / (nChunks - made);
+                    if ((acc >= want && made < nChunks - 1) || q == d.nbrCnt - 1) {
+                        GDesc u = d;
+                        u.nbrOff = d.nbrOff + q0;
+                        u.nbrCnt = q - q0 + 1;
+                        u.partial = nPartials++;
+                        units.push_back(u);
+                        unitCost.push_back(acc);
+                        done += acc;
+                        acc = 0;
+                        q0 = q + 1;
+                        made++;
+                    }
+                }
+                reduceItems.push_back(made);
+            }
+            std::vector<int> order(units.size());
+            for (size_t u = 0; u < order.size(); u++) order[u] = (int)u;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return unitCost[a] > unitCost[b]; });
+            std::vector<GDesc> sorted(units.size());
+            for (size_t u = 0; u < order.size(); u++) sorted[u] = units[order[u]];
+            units.swap(sorted);
+        }
+        tp_phase2 += now_ms() - tq;
+        tq = now_ms();
         if (bt.dirty) {
-            scr.depthInfo.reserve(DM, false, st);
-            scr.candOff.reserve(bt.candOff.size(), false, st);
-            scr.candTerm.reserve(std::max<size_t>(bt.candTerm.size(), 1), false, st);
-            scr.candMask.reserve(std::max<size_t>(bt.candMask.size(), 1), false, st);
-            MRX_CUDA(cudaMemcpyAsync(scr.depthInfo.p, bt.info.data(), sizeof(DepthInfo) * DM, cudaMemcpyHostToDevice, st));
-            MRX_CUDA(cudaMemcpyAsync(scr.candOff.p, bt.candOff.data(), sizeof(int) * bt.candOff.size(), cudaMemcpyHostToDevice, st));
+            bt.d_info.reserve(DM, false, st);
+            bt.d_candOff.reserve(bt.candOff.size(), false, st);
+            bt.d_candTerm.reserve(std::max<size_t>(bt.candTerm.size(), 1), false, st);
+            bt.d_candMask.reserve(std::max<size_t>(bt.candMask.size(), 1), false, st);
+            MRX_CUDA(cudaMemcpyAsync(bt.d_info.p, bt.info.data(), sizeof(DepthInfo) * DM, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(bt.d_candOff.p, bt.candOff.data(), sizeof(int) * bt.candOff.size(), cudaMemcpyHostToDevice, st));
             if (!bt.candTerm.empty()) {
-                MRX_CUDA(cudaMemcpyAsync(scr.candTerm.p, bt.candTerm.data(), sizeof(int) * bt.candTerm.size(),
+                MRX_CUDA(cudaMemcpyAsync(bt.d_candTerm.p, bt.candTerm.data(), sizeof(int) * bt.candTerm.size(),
                                          cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaMemcpyAsync(scr.candMask.p, bt.candMask.data(), sizeof(unsigned long long) * bt.candMask.size(),
+                MRX_CUDA(cudaMemcpyAsync(bt.d_candMask.p, bt.candMask.data(), sizeof(unsigned long long) * bt.candMask.size(),
                                          cudaMemcpyHostToDevice, st));
             }
             bt.dirty = false;
@@ -258,11 +444,20 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             inp.dev.nGen = nGenTotal;
             S.gen_nodes += 8 * (long long)newParents.size();
         }
+        tp_gen += now_ms() - tq;
+        tq = now_ms();
         // ---- device storage for the output nodes of this iteration
         out.dev.coefs.reserve((size_t)g.nReal * ncoef, true, st);
         out.dev.norms.reserve((size_t)g.nReal * 8, true, st);
         out.dev.nNodes = g.nReal;
 
+        scr.units.reserve(std::max<size_t>(units.size(), 1), false, st);
+        MRX_CUDA(cudaMemcpyAsync(scr.units.p, units.data(), sizeof(GDesc) * units.size(), cudaMemcpyHostToDevice, st));
+        if (nPartials > 0) {
+            scr.partials.reserve((size_t)nPartials * ncoef, false, st);
+            scr.reduceItems.reserve(reduceItems.size(), false, st);
+            MRX_CUDA(cudaMemcpyAsync(scr.reduceItems.p, reduceItems.data(), sizeof(int) * reduceItems.size(), cudaMemcpyHostToDevice, st));
+        }
         scr.gdesc.reserve(nG, false, st);
         scr.nbr.reserve(std::max<size_t>(nbr.size(), 1), false, st);
         scr.gslots.reserve(nG, false, st);
@@ -286,16 +481,17 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         P.fGenNorms = inp.dev.genNorms.p;
         P.nRealF = fRealN;
         P.gCoefs = out.dev.coefs.p;
-        P.gdesc = scr.gdesc.p;
+        P.gdesc = scr.units.p;
+        P.partials = scr.partials.p;
         P.nbr = scr.nbr.p;
         P.mats = oper.dev.mats.p;
         P.onorms = oper.dev.norms.p;
         P.nodeBase = oper.dev.nodeBase.p;
         P.bsf = oper.dev.bsf.p;
-        P.depthInfo = scr.depthInfo.p;
-        P.candOff = scr.candOff.p;
-        P.candTerm = scr.candTerm.p;
-        P.candMask = scr.candMask.p;
+        P.depthInfo = bt.d_info.p;
+        P.candOff = bt.d_candOff.p;
+        P.candTerm = bt.d_candTerm.p;
+        P.candMask = bt.d_candMask.p;
         P.M = M;
         P.DM = DM;
         P.K = K;
@@ -303,8 +499,11 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         P.counters = scr.counters.p;
         P.derivDir = derivDir;
 
+        tp_upload += now_ms() - tq;
+        tq = now_ms();
         MRX_CUDA(cudaEventRecord(ev0, st));
-        launch_apply(P, nG, st);
+        launch_apply(P, (int)units.size(), st);
+        if (nPartials > 0) launch_reduce_partials(out.dev.coefs.p, scr.partials.p, scr.reduceItems.p, (int)reduceItems.size() / 3, ncoef, st);
         MRX_CUDA(cudaEventRecord(ev1, st));
         // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
         launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
@@ -315,9 +514,12 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         MRX_CUDA(cudaMemcpyAsync(range.data(), out.dev.norms.p + (size_t)lo * 8, sizeof(double) * range.size(),
                                  cudaMemcpyDeviceToHost, st));
         MRX_CUDA(cudaStreamSynchronize(st));
+        tp_wait += now_ms() - tq;
+        tq = now_ms();
         float ms = 0.f;
         MRX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         kernel_ms += ms;
+        if (profile) std::fprintf(stderr, "[mrx] iter %d nG %d nbr %zu kernel %.3f ms\n", iter, nG, nbr.size(), ms);
         for (int i = 0; i < nG; i++) {
             int n = workVec[i];
             double sq = 0.0;
@@ -355,7 +557,11 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         }
         workVec.swap(newVec);
         iter++;
+        tp_host += now_ms() - tq;
     }
+    if (profile)
+        std::fprintf(stderr, "[mrx] host phases ms: tables %.2f enum %.2f phase2 %.2f gen %.2f upload %.2f wait %.2f split %.2f\n", tp_tables,
+                     tp_enum, tp_phase2, tp_gen, tp_upload, tp_wait, tp_host);
     S.iterations = iter;
     S.ms_kernel = kernel_ms;
     unsigned long long counters[4];

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_generic_kernel(ApplyParam
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool deriv = P.derivDir >= 0;
 
-    double *gNode = P.gCoefs + (size_t)g.slot * 8 * Kd;
+    double *gNode = (g.partial < 0) ? P.gCoefs + (size_t)g.slot * 8 * Kd : P.partials + (size_t)g.partial * 8 * Kd;
     for (int i = tid; i < 8 * Kd; i += kApplyThreads) gNode[i] = 0.0; // gNode.zeroCoefs()
     __syncthreads();
     if (g.nbrCnt == 0) return;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dmma8_kernel(ApplyPara
     const int sig = (r >> 1) + 4 * (r & 1); // sigma(r)
     double *T = tiles + warp * kTileDoubles;
     const int gt = warp;
-    double *gblk = P.gCoefs + ((size_t)g.slot * 8 + gt) * Kd;
+    double *gblk = ((g.partial < 0) ? P.gCoefs + (size_t)g.slot * 8 * Kd : P.partials + (size_t)g.partial * 8 * Kd) + (size_t)gt * Kd;
 
     double acc[8][2];
 #pragma unroll

@@ -10,6 +10,7 @@ struct GDesc {
     int depth;  // operator depth = scale - operator root
     int nbrOff; // first entry of this node's neighbour list in `nbr`
     int nbrCnt; // number of neighbour entries
+    int partial; // -1: this CTA owns the whole node and writes g directly; >= 0: slot in the partial-sum buffer
 };
 
 /// neighbour entry: input-node slot and the code of its translation offset inside the depth's band cube
@@ -35,6 +36,7 @@ struct ApplyParams {
     int nRealF;
     // output tree
     double *gCoefs;
+    double *partials; // [nPartials][8][K^3]: per-chunk partial sums of nodes split across CTAs
     const GDesc *gdesc;
     const NbrEntry *nbr;
     // operator tables

@@ -140,6 +140,16 @@ __global__ void __launch_bounds__(256) dot_kernel(const double *__restrict__ a, 
     }
 }
 
+__global__ void __launch_bounds__(256) reduce_partials_kernel(double *__restrict__ coefs, const double *__restrict__ partials,
+                                                              const int *__restrict__ items, int ncoef) {
+    const int slot = items[3 * blockIdx.x], first = items[3 * blockIdx.x + 1], n = items[3 * blockIdx.x + 2];
+    for (int e = threadIdx.x; e < ncoef; e += 256) {
+        double s = 0.0;
+        for (int c = 0; c < n; c++) s += partials[(size_t)(first + c) * ncoef + e]; // chunk order = neighbour order
+        coefs[(size_t)slot * ncoef + e] = s;
+    }
+}
+
 __global__ void scale_kernel(double *x, size_t n, double c) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -200,6 +210,13 @@ void launch_gen_children(const double *realCoefs, double *genCoefs, double *genN
     set_smem_attr<2>(bytes);
     transform_kernel<2><<<cnt, kTransformThreads, bytes, st>>>(nullptr, realCoefs, genCoefs, genNorms, nReal, items, K, padOn,
                                                               filters, 1);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_reduce_partials(double *coefs, const double *partials, const int *items, int cnt, int ncoef, cudaStream_t st) {
+    if (cnt <= 0) return;
+    reduce_partials_kernel<<<cnt, 256, 0, st>>>(coefs, partials, items, ncoef);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

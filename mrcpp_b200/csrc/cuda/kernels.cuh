@@ -21,6 +21,10 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
 void launch_gen_children(const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *items, int cnt,
                          int K, const double *filters, cudaStream_t st);
 
+/// fixed-order sum of the per-chunk partial results of nodes that were split across CTAs:
+/// items = (slot, firstPartial, nPartials) x cnt
+void launch_reduce_partials(double *coefs, const double *partials, const int *items, int cnt, int ncoef, cudaStream_t st);
+
 void launch_dot(const double *a, const double *b, const int *pairs, double *res, int np, int nRoots, int Kd, cudaStream_t st);
 void launch_scale(double *x, size_t n, double c, cudaStream_t st);
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <memory>
 #include <vector>
 
 #include "../../include/mrcpp_b200.h"
@@ -17,24 +18,25 @@ namespace mrx {
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    /// stream-ordered allocation from the device memory pool (release threshold = never, set in mrx_init), so
+    /// growing and freeing buffers costs microseconds after the first apply
     void reserve(size_t n, bool keep, cudaStream_t st) {
         if (n <= cap) return;
-        size_t ncap = n > cap + cap / 2 ? n : cap + cap / 2;
+        size_t ncap = n > 2 * cap ? n : 2 * cap;
         T *np = nullptr;
-        if (cudaMalloc(&np, ncap * sizeof(T)) != cudaSuccess) MRX_ABORT("cudaMalloc failed (out of device memory?)");
+        if (cudaMallocAsync(&np, ncap * sizeof(T), st) != cudaSuccess) MRX_ABORT("cudaMallocAsync failed (out of device memory?)");
         if (keep && p && cap) cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-        if (p) {
-            cudaStreamSynchronize(st);
-            cudaFree(p);
-        }
+        if (p) cudaFreeAsync(p, st);
         p = np;
         cap = ncap;
+        stream_ = st;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, stream_);
         p = nullptr;
         cap = 0;
     }
+    cudaStream_t stream_ = nullptr;
     ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
@@ -78,6 +80,7 @@ struct mrx_tree {
 struct mrx_oper {
     mrx::Operator op;
     mrx::DeviceOper dev;
+    std::shared_ptr<void> bandCache; // per-depth band tables of the last (prec, direction) used (apply.cu)
 };
 
 namespace mrx {

@@ -192,7 +192,7 @@ public:
     void deleteGenerated();                                      // MWNode.cpp:736-744
     /// topology-only variant of getNode for device-resident trees: missing nodes are created as
     /// generated nodes WITHOUT host coefficients; parents that got children are appended to newParents
-    int getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents);
+    int getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents, bool withCoefStorage = false);
     void clearToRoots();          // FunctionTree::clear
     void copyGridFrom(const Tree<D> &other); // copy_grid (grid.cpp:150-166)
     bool allocCoefs = true;       // false: new nodes get no host coefficient storage (device-resident)

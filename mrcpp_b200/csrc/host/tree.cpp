@@ -79,13 +79,14 @@ template <int D> void Tree<D>::ensureCoefStorage() {
     }
 }
 
-template <int D> int Tree<D>::getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents) {
+template <int D>
+int Tree<D>::getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents, bool withCoefStorage) {
     int n = rootIndex(scale, l);
     if (n < 0) return -1;
     while (nodes[n].scale < scale) {
         if (nodes[n].child0 < 0) {
             bool saved = allocCoefs;
-            allocCoefs = false;
+            allocCoefs = withCoefStorage;
             createChildren(n, true);
             allocCoefs = saved;
             if (newParents) newParents->push_back(n);

@@ -195,6 +195,21 @@ static int get_node_gen(Tree<3> &t, const FilterSet &fs, int scale, const std::a
     return n;
 }
 
+// Coefficients of freshly created generated nodes. The reference fills them lazily under per-node locks from
+// inside the parallel node loop; here the parents (in creation order) are processed in dependency waves, each
+// wave in parallel.
+static void fill_generated(Tree<3> &t, const FilterSet &fs, const std::vector<int> &newParents) {
+    size_t pos = 0;
+    while (pos < newParents.size()) {
+        size_t end = pos;
+        int firstChild = t.nodes[newParents[pos]].child0;
+        while (end < newParents.size() && newParents[end] < firstChild) end++;
+#pragma omp parallel for schedule(static)
+        for (long q = (long)pos; q < (long)end; q++) give_children_coefs(t, fs, newParents[q], true);
+        pos = end;
+    }
+}
+
 void mw_transform_down(Tree<3> &t, bool overwrite) {
     // MWTree::mwTransformDown (MWTree.cpp:194-216)
     const FilterSet &fs = filter_set(t.k);
@@ -305,7 +320,41 @@ struct ConvCalc {
 
     // tensorApplyOperComp (ConvolutionCalculator.cpp:333-382): three (kp1^2 x kp1)(kp1 x kp1) products,
     // each contracting the fastest index and making it the slowest; the last accumulates into g.
-    static void tensorApply(int K, const double *f, const double *const oData[3], double *scr, double *gOut) {
+    // g(r,c) (+)= sum_t f(t,r) op(t,c). The input is first transposed to FT[t][r] so that the inner loop is a
+    // contiguous axpy over r that the compiler vectorises (the reference leaves this to Eigen's GEMM kernels).
+    template <int K> static void tensorApplyK(const double *f, const double *const oData[3], double *scr, double *gOut) {
+        constexpr int K2 = K * K, Kd = K2 * K;
+        const double *aux[4] = {f, scr + Kd, scr, gOut};
+        alignas(64) double FT[Kd];
+        for (int i = 0; i < 3; i++) {
+            const double *fi = aux[i];
+            double *gi = const_cast<double *>(aux[i + 1]);
+            const double *op = oData[i];
+            for (int r = 0; r < K2; r++)
+                for (int t = 0; t < K; t++) FT[t * K2 + r] = fi[t + K * r];
+            if (op != nullptr) {
+                for (int c = 0; c < K; c++) {
+                    double *gc = gi + (size_t)K2 * c;
+                    if (i != 2)
+                        for (int r = 0; r < K2; r++) gc[r] = 0.0;
+                    for (int t = 0; t < K; t++) {
+                        const double o = op[t + K * c];
+                        const double *ft = FT + t * K2;
+                        for (int r = 0; r < K2; r++) gc[r] += ft[r] * o;
+                    }
+                }
+            } else {
+                // identity in direction i: pure transpose (derivative operators)
+                for (int c = 0; c < K; c++)
+                    for (int r = 0; r < K2; r++) {
+                        if (i == 2) gi[r + (size_t)K2 * c] += FT[c * K2 + r];
+                        else gi[r + (size_t)K2 * c] = FT[c * K2 + r];
+                    }
+            }
+        }
+    }
+
+    static void tensorApplyGeneric(int K, const double *f, const double *const oData[3], double *scr, double *gOut) {
         const int K2 = K * K, Kd = K2 * K;
         const double *aux[4] = {f, scr + Kd, scr, gOut};
         for (int i = 0; i < 3; i++) {
@@ -326,13 +375,22 @@ struct ConvCalc {
                     }
                 }
             } else {
-                // identity in direction i: pure transpose (derivative operators)
                 for (int c = 0; c < K; c++)
                     for (int r = 0; r < K2; r++) {
                         if (i == 2) gi[r + (size_t)K2 * c] += fi[c + (size_t)K * r];
                         else gi[r + (size_t)K2 * c] = fi[c + (size_t)K * r];
                     }
             }
+        }
+    }
+
+    static void tensorApply(int K, const double *f, const double *const oData[3], double *scr, double *gOut) {
+        switch (K) {
+            case 6: tensorApplyK<6>(f, oData, scr, gOut); break;
+            case 8: tensorApplyK<8>(f, oData, scr, gOut); break;
+            case 10: tensorApplyK<10>(f, oData, scr, gOut); break;
+            case 12: tensorApplyK<12>(f, oData, scr, gOut); break;
+            default: tensorApplyGeneric(K, f, oData, scr, gOut);
         }
     }
 
@@ -427,12 +485,15 @@ void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter,
         double tb = now();
         std::vector<std::vector<int>> bands(nNodes);
         std::vector<std::vector<std::array<int, 3>>> idxs(nNodes);
+        std::vector<int> newParents;
         for (int i = 0; i < nNodes; i++) {
             calc.band(out, workVec[i], idxs[i]);
             bands[i].resize(idxs[i].size());
             for (size_t j = 0; j < idxs[i].size(); j++)
-                bands[i][j] = get_node_gen(inp, *calc.fs, out.nodes[workVec[i]].scale, idxs[i][j], &st.genUsed);
+                bands[i][j] = inp.getNodeTopo(out.nodes[workVec[i]].scale, idxs[i][j], &newParents, true);
         }
+        fill_generated(inp, *calc.fs, newParents);
+        st.genUsed += 8 * (long long)newParents.size();
         st.t_band += now() - tb;
         double tc = now();
         long long applied = 0;
@@ -531,17 +592,20 @@ void apply_derivative(Tree<3> &out, Operator &oper, Tree<3> &inp, int dir, Apply
     // band pre-pass (makeOperBand, :157-178)
     std::vector<std::vector<int>> bands(nNodes);
     std::vector<std::vector<std::array<int, 3>>> idxs(nNodes);
+    std::vector<int> newParents;
     for (int i = 0; i < nNodes; i++) {
-        const auto &nd = out.nodes[workVec[i]];
+        const auto nd = out.nodes[workVec[i]];
         for (int w = -width; w <= width; w++) {
             std::array<int, 3> l = nd.l;
             l[dir] += w;
             if (inp.rootIndex(nd.scale, l) >= 0) {
                 idxs[i].push_back(l);
-                bands[i].push_back(get_node_gen(inp, fs, nd.scale, l, &st.genUsed));
+                bands[i].push_back(inp.getNodeTopo(nd.scale, l, &newParents, true));
             }
         }
     }
+    fill_generated(inp, fs, newParents);
+    st.genUsed += 8 * (long long)newParents.size();
     const int nThreads = omp_get_max_threads();
     std::vector<std::vector<double>> scratch(nThreads, std::vector<double>((size_t)2 * Kd));
     long long applied = 0;
