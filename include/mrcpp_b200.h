@@ -35,7 +35,8 @@ typedef struct mrx_apply_stats {
     int n_nodes_out;       /* nodes of the output tree                                                  */
     double ms_upload;      /* host->device copies of the input tree + tables                            */
     double ms_build;       /* TreeBuilder::build loop (device kernels + host split logic)               */
-    double ms_kernel;      /* device time inside the contraction kernels only (CUDA events)             */
+    double ms_kernel;      /* device time of the apply kernels of all iterations (CUDA events)          */
+    double ms_contract;    /* device time of the contraction kernel alone (the FP64 tensor-pipe kernel) */
     double ms_post;        /* TopDown(+=) and BottomUp transforms + norms                               */
     double ms_download;    /* device->host copy of the result                                           */
     long long kernel_launches; /* CUDA kernels launched by this call                                    */

@@ -21,6 +21,7 @@ class ApplyStats(C.Structure):
         ("ms_upload", C.c_double),
         ("ms_build", C.c_double),
         ("ms_kernel", C.c_double),
+        ("ms_contract", C.c_double),
         ("ms_post", C.c_double),
         ("ms_download", C.c_double),
         ("kernel_launches", C.c_longlong),

@@ -70,6 +70,17 @@ struct Scratch {
     DevBuf<GDesc> units;
     DevBuf<int> reduceItems;
     DevBuf<double> partials;
+    // work-list pipeline (apply_pipeline.cu)
+    DevBuf<unsigned long long> masks;
+    DevBuf<unsigned short> cnt64;
+    DevBuf<int> segOff;
+    DevBuf<int> blockCnt;
+    DevBuf<unsigned> blockTupOff;
+    DevBuf<int> blockUnitOff;
+    DevBuf<PipeHeader> header;
+    DevBuf<TupleRec> tuples;
+    DevBuf<UnitDesc> units2;
+    DevBuf<int> queue;
 };
 
 /// Host copy of the per-depth band tables (see DepthInfo). Built lazily for the depths that occur.
@@ -178,6 +189,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     Operator &op = oper.op;
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
+    const char *legacy = getenv("MRX_LEGACY");
+    const bool usePipe = (out.host.K == 8) && !deriv && !(legacy && legacy[0] == '1');
     std::vector<int> bsf, bwTab;
     band_size_factors(op, DM, bsf, bwTab);
     oper.dev.bsf.reserve(bsf.size(), false, st);
@@ -209,10 +222,13 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     }
     BandTables &bt = *btp;
 
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0, ev1, ev2, ev3;
     MRX_CUDA(cudaEventCreate(&ev0));
     MRX_CUDA(cudaEventCreate(&ev1));
-    float kernel_ms = 0.f;
+    MRX_CUDA(cudaEventCreate(&ev2));
+    MRX_CUDA(cudaEventCreate(&ev3));
+    float kernel_ms = 0.f, contract_ms = 0.f;
+    long long tuplesTotal = 0, iterTuples = 0;
 
     double sNorm = 0.0, wNorm = 0.0;
     int iter = 0;
@@ -317,12 +333,14 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         tp_enum += now_ms() - tq;
         tq = now_ms();
         // phase 2 (serial, work-vector order): create the missing generated nodes, emit neighbour entries
+        long long nCand = 0;
         for (int i = 0; i < nG; i++) {
             const auto &nd = g.nodes[workVec[i]];
             GDesc &d = gdesc[i];
             d.slot = workVec[i];
             d.depth = nd.scale - op.operRoot;
             d.nbrOff = (int)nbr.size();
+            const int *coffG = (d.depth >= 0 && d.depth < DM && bt.built[d.depth]) ? bt.candOff.data() + bt.info[d.depth].cubeOff : nullptr;
             for (const Hit &h : hits[i]) {
                 int node = h.node;
                 if (f.nodes[node].scale < nd.scale) {
@@ -333,6 +351,9 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
                 NbrEntry e;
                 e.fslot = node;
                 e.code = h.code;
+                e.g = i;
+                e.candBase = (int)nCand;
+                nCand += coffG[h.code + 1] - coffG[h.code];
                 nbr.push_back(e);
             }
             d.nbrCnt = (int)nbr.size() - d.nbrOff;
@@ -344,7 +365,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         std::vector<long long> unitCost;
         std::vector<int> reduceItems; // (slot, firstPartial, nPartials)
         int nPartials = 0;
-        {
+        if (nCand >= (1ll << 31)) MRX_ABORT("apply: candidate space of one iteration exceeds 2^31");
+        if (!usePipe) {
             std::vector<long long> cost(nG, 0);
             long long total = 0;
             for (int i = 0; i < nG; i++) {
@@ -502,11 +524,54 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         tp_upload += now_ms() - tq;
         tq = now_ms();
         MRX_CUDA(cudaEventRecord(ev0, st));
-        launch_apply(P, (int)units.size(), st);
-        if (nPartials > 0) launch_reduce_partials(out.dev.coefs.p, scr.partials.p, scr.reduceItems.p, (int)reduceItems.size() / 3, ncoef, st);
-        MRX_CUDA(cudaEventRecord(ev1, st));
-        // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-        launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
+        if (usePipe) {
+            const int nNbr = (int)nbr.size();
+            P.gdesc = scr.gdesc.p; // node-level descriptors: balancing happens on the device
+            scr.masks.reserve(std::max<long long>(nCand, 1), false, st);
+            scr.cnt64.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
+            scr.segOff.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
+            scr.blockCnt.reserve((size_t)nG * 8, false, st);
+            scr.blockTupOff.reserve((size_t)nG * 8 + 1, false, st);
+            scr.blockUnitOff.reserve((size_t)nG * 8 + 1, false, st);
+            scr.header.reserve(1, false, st);
+            scr.queue.reserve(1, false, st);
+            PipeBuffers B{};
+            B.masks = scr.masks.p;
+            B.cnt64 = scr.cnt64.p;
+            B.segOff = scr.segOff.p;
+            B.blockCnt = scr.blockCnt.p;
+            B.blockTupOff = scr.blockTupOff.p;
+            B.blockUnitOff = scr.blockUnitOff.p;
+            B.header = scr.header.p;
+            B.queue = scr.queue.p;
+            launch_pipe_screen(P, B, nNbr, st);
+            launch_pipe_scan(P, B, nG, pipe_contract_warps(), st);
+            PipeHeader hdr;
+            MRX_CUDA(cudaMemcpyAsync(&hdr, scr.header.p, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+            MRX_CUDA(cudaStreamSynchronize(st));
+            if (hdr.totalTuples >= (1ull << 32)) MRX_ABORT("apply: tuple list of one iteration exceeds 2^32 records");
+            scr.tuples.reserve(std::max<size_t>((size_t)hdr.totalTuples, 1), false, st);
+            scr.units2.reserve(std::max<size_t>((size_t)hdr.nUnits, 1), false, st);
+            scr.partials.reserve(std::max<size_t>((size_t)hdr.nUnits * Kd, 1), false, st);
+            B.tuples = scr.tuples.p;
+            B.units = scr.units2.p;
+            B.partials = scr.partials.p;
+            launch_pipe_fill(P, B, nNbr, nG, st);
+            MRX_CUDA(cudaEventRecord(ev2, st));
+            launch_pipe_contract(P, B, hdr.nUnits, st);
+            MRX_CUDA(cudaEventRecord(ev3, st));
+            // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
+            launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, nG, st);
+            MRX_CUDA(cudaEventRecord(ev1, st));
+            iterTuples = (long long)hdr.totalTuples;
+            tuplesTotal += iterTuples;
+        } else {
+            launch_apply(P, (int)units.size(), st);
+            if (nPartials > 0) launch_reduce_partials(out.dev.coefs.p, scr.partials.p, scr.reduceItems.p, (int)reduceItems.size() / 3, ncoef, st);
+            MRX_CUDA(cudaEventRecord(ev1, st));
+            // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
+            launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
+        }
         // norms are scattered by slot -> copy the covering range
         int lo = *std::min_element(workVec.begin(), workVec.end());
         int hi = *std::max_element(workVec.begin(), workVec.end());
@@ -516,10 +581,16 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         MRX_CUDA(cudaStreamSynchronize(st));
         tp_wait += now_ms() - tq;
         tq = now_ms();
-        float ms = 0.f;
+        float ms = 0.f, msc = 0.f;
         MRX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         kernel_ms += ms;
-        if (profile) std::fprintf(stderr, "[mrx] iter %d nG %d nbr %zu kernel %.3f ms\n", iter, nG, nbr.size(), ms);
+        if (usePipe) {
+            MRX_CUDA(cudaEventElapsedTime(&msc, ev2, ev3));
+            contract_ms += msc;
+        }
+        if (profile)
+            std::fprintf(stderr, "[mrx] iter %d nG %d nbr %zu cand %lld tuples %lld kernels %.3f ms (contract %.3f ms, %.2f TF/s)\n", iter, nG,
+                         nbr.size(), nCand, iterTuples, ms, msc, msc > 0 ? iterTuples * 24576.0 / (msc * 1e-3) / 1e12 : 0.0);
         for (int i = 0; i < nG; i++) {
             int n = workVec[i];
             double sq = 0.0;
@@ -564,13 +635,16 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
                      tp_enum, tp_phase2, tp_gen, tp_upload, tp_wait, tp_host);
     S.iterations = iter;
     S.ms_kernel = kernel_ms;
+    S.ms_contract = usePipe ? contract_ms : kernel_ms;
     unsigned long long counters[4];
     MRX_CUDA(cudaMemcpyAsync(counters, scr.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
     MRX_CUDA(cudaStreamSynchronize(st));
-    S.f_applied = (long long)counters[0];
+    S.f_applied = usePipe ? tuplesTotal : (long long)counters[0];
     out.dev.nNodes = g.nReal;
     MRX_CUDA(cudaEventDestroy(ev0));
     MRX_CUDA(cudaEventDestroy(ev1));
+    MRX_CUDA(cudaEventDestroy(ev2));
+    MRX_CUDA(cudaEventDestroy(ev3));
 }
 
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,

@@ -16,7 +16,9 @@ struct GDesc {
 /// neighbour entry: input-node slot and the code of its translation offset inside the depth's band cube
 struct NbrEntry {
     int fslot;
-    int code; // (dz+W)*(2W+1)^2 + (dy+W)*(2W+1) + (dx+W)
+    int code;     // (dz+W)*(2W+1)^2 + (dy+W)*(2W+1) + (dx+W)
+    int g;        // index of the output node in this iteration's work vector
+    int candBase; // first candidate (neighbour, term) index of this entry in the iteration's candidate space
 };
 
 /// per-depth band table: for every offset of the band cube, the separation terms that can reach it and
@@ -55,5 +57,41 @@ struct ApplyParams {
 };
 
 void launch_apply(const ApplyParams &P, int nG, cudaStream_t st);
+
+// ---- work-list pipeline (apply_pipeline.cu): screen -> scan -> fill -> contract -> reduce -------------------
+/// one surviving (g, f, ft, gt, term) tuple: indices of the source block and of the three 1-D operator blocks
+struct TupleRec {
+    int fblk; // < 8*nRealF: real block fslot*8+ft; otherwise generated scaling block (fblk - 8*nRealF)
+    int o0, o1, o2; // operator block index (node*4 + component) per dimension
+};
+/// contraction work unit: `cnt` consecutive tuples of one output block (g, gt)
+struct UnitDesc {
+    unsigned t0; // first tuple in the iteration's tuple list
+    int cnt;
+};
+struct PipeHeader {
+    unsigned long long totalTuples;
+    int nUnits;
+    int U; // tuples per unit
+};
+struct PipeBuffers {
+    unsigned long long *masks; // [nCand] surviving (gt,ft) bits per candidate
+    unsigned short *cnt64;     // [nNbr][64] tuples per (neighbour, gt, ft)
+    int *segOff;               // [nNbr][64] offset of the (neighbour, gt, ft) segment inside its block's tuple run
+    int *blockCnt;             // [nG*8]
+    unsigned *blockTupOff;     // [nG*8+1]
+    int *blockUnitOff;         // [nG*8+1]
+    PipeHeader *header;
+    TupleRec *tuples;
+    UnitDesc *units;
+    double *partials; // [nUnits][K^3]
+    int *queue;       // dynamic unit counter of the contraction kernel
+};
+int pipe_contract_warps(); // persistent warps of the contraction kernel on this device
+void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cudaStream_t st);
+void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st);
+void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st);
+void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st);
+void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, int nG, cudaStream_t st);
 
 } // namespace mrx

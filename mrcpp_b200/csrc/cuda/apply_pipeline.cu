@@ -1,0 +1,477 @@
+// Work-list pipeline of the operator application for k = 7 (K = 8): the inner loops of
+// ConvolutionCalculator::calcNode / applyOperComp / applyOperator / tensorApplyOperComp
+// (src/treebuilders/ConvolutionCalculator.cpp:224-382) split into five kernels so that the FP64
+// tensor pipe never waits for screening, barriers or an unbalanced output node:
+//
+//   screen   warp per (output node, input node) pair: every candidate term is screened with the reference's
+//            predicate ((1.0*|O_x|)*|O_y|)*|O_z| * (bandSizeFactor*|f_ft|) > gThrs in the reference's FP64
+//            operation order (:283-288, :320-328); result = 64-bit (gt,ft) mask per candidate + tuple counts per
+//            (pair, gt, ft).
+//   scan     exclusive scans: (pair, ft) segments inside each output block (g, gt), blocks inside the
+//            iteration's tuple list, and the split of every block into units of U tuples.
+//   fill     warp per pair: surviving tuples are written as 16-byte records (source block, three operator
+//            blocks), sorted per output block by (input node, ft, term) -- the reference's accumulation
+//            order (calcNode :252-267 loops input node, ft, gt, term) -- so that a source block is
+//            fetched once for all of its terms.
+//   contract persistent warps pull units from a queue; per tuple 48 DMMA.8x8x4 (three 1-D contractions,
+//            6 K^4 = 24 576 flop), accumulators in registers, one partial block per unit.
+//   reduce   warp per output block: partial blocks summed in unit order (fixed order: results are run-to-run
+//            identical), written to the node store together with the component norm (calcNorms, :270-272).
+//
+// Fragment algebra of the contraction (lane = 4 r + q): see apply_kernels.cu (same chaining: the D fragment
+// of stage 1 is the B fragment of stage 2 under the index permutation sigma; stage 3 contracts the
+// tile index after one trip through a padded warp-private shared-memory tile).
+#include "../engine.hpp"
+#include "apply_kernels.cuh"
+#include "common.cuh"
+
+namespace mrx {
+
+namespace {
+
+constexpr double kMachineZero = 1.0e-14;
+constexpr int kTileSi = 18;  // i2 stride (doubles): 144 B == 16 B mod 128 B
+constexpr int kTileSm = 152; // m1 stride (doubles): 1216 B == 64 B mod 128 B
+constexpr int kTileDoubles = 8 * kTileSm;
+constexpr int kContractWarps = 4;     // per CTA
+constexpr int kContractCtasPerSm = 3; // 12 warps / SM, <= 168 registers per thread
+
+__device__ __forceinline__ void decode_delta(int code, int W, int d[3]) {
+    const int cube = 2 * W + 1;
+    d[0] = code % cube - W;
+    d[1] = (code / cube) % cube - W;
+    d[2] = code / (cube * cube) - W;
+}
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------------------------------------ screen
+__global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuffers B, int nNbr) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= nNbr) return;
+    const NbrEntry nb = P.nbr[w];
+    const GDesc g = P.gdesc[nb.g];
+    const DepthInfo di = P.depthInfo[g.depth];
+    const int *coff = P.candOff + di.cubeOff;
+    const int e0 = coff[nb.code];
+    const int nc = coff[nb.code + 1] - e0;
+    // f component norms; generated nodes carry scaling only (MWNode.cpp:644)
+    double fn[8];
+    if (nb.fslot < P.nRealF) {
+#pragma unroll
+        for (int ft = 0; ft < 8; ft++) fn[ft] = P.fNorms[(size_t)nb.fslot * 8 + ft];
+    } else {
+        fn[0] = P.fGenNorms[nb.fslot - P.nRealF];
+#pragma unroll
+        for (int ft = 1; ft < 8; ft++) fn[ft] = 0.0;
+    }
+    unsigned long long fmask = 0ull; // (gt,ft) bits whose f component is not negligible (:254-255)
+#pragma unroll
+    for (int ft = 0; ft < 8; ft++)
+        if (!(fn[ft] < kMachineZero)) fmask |= 0x0101010101010101ull << ft;
+    int d[3];
+    decode_delta(nb.code, di.W, d);
+    int cnt0 = 0, cnt1 = 0; // lane l counts bits l and l + 32
+    for (int base = 0; base < nc; base += 32) {
+        const int c = base + lane;
+        unsigned long long pass = 0ull;
+        if (c < nc) {
+            const int term = P.candTerm[e0 + c];
+            unsigned long long todo = P.candMask[e0 + c] & fmask;
+            if (todo) {
+                const int nbase = P.nodeBase[(size_t)term * P.DM + g.depth];
+                const double4 v0 = *reinterpret_cast<const double4 *>(P.onorms + (size_t)(nbase + d[0]) * 4);
+                const double4 v1 = *reinterpret_cast<const double4 *>(P.onorms + (size_t)(nbase + d[1]) * 4);
+                const double4 v2 = *reinterpret_cast<const double4 *>(P.onorms + (size_t)(nbase + d[2]) * 4);
+                const double n0[4] = {v0.x, v0.y, v0.z, v0.w};
+                const double n1[4] = {v1.x, v1.y, v1.z, v1.w};
+                const double n2[4] = {v2.x, v2.y, v2.z, v2.w};
+                const int *bs = P.bsf + ((size_t)term * P.DM + g.depth) * 64;
+#pragma unroll
+                for (int gt = 0; gt < 8; gt++) {
+#pragma unroll
+                    for (int ft = 0; ft < 8; ft++) {
+                        const int b = gt * 8 + ft;
+                        if ((todo >> b) & 1ull) {
+                            double oNorm = 1.0;
+                            oNorm *= n0[2 * (gt & 1) + (ft & 1)];
+                            oNorm *= n1[2 * ((gt >> 1) & 1) + ((ft >> 1) & 1)];
+                            oNorm *= n2[2 * ((gt >> 2) & 1) + ((ft >> 2) & 1)];
+                            const double fThreshold = bs[b] * fn[ft];
+                            const double upperBound = oNorm * fThreshold;
+                            if (upperBound > P.gThrs) pass |= 1ull << b;
+                        }
+                    }
+                }
+            }
+            B.masks[(size_t)nb.candBase + c] = pass;
+        }
+        unsigned long long uni = warp_or64(pass);
+        while (uni) {
+            const int b = __ffsll((long long)uni) - 1;
+            uni &= uni - 1;
+            const int n = __popc(__ballot_sync(0xffffffffu, (pass >> b) & 1ull));
+            if (lane == (b & 31)) {
+                if (b < 32) cnt0 += n;
+                else cnt1 += n;
+            }
+        }
+    }
+    B.cnt64[(size_t)w * 64 + lane] = (unsigned short)cnt0;
+    B.cnt64[(size_t)w * 64 + 32 + lane] = (unsigned short)cnt1;
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+// warp per output block (g, gt): offsets of the (input node, ft) segments, input node major
+__global__ void __launch_bounds__(256) pipe_segscan_kernel(ApplyParams P, PipeBuffers B, int nBlocks) {
+    const int lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blk >= nBlocks) return;
+    const GDesc g = P.gdesc[blk >> 3];
+    const int gt = blk & 7;
+    int run = 0;
+    for (int n0 = 0; n0 < g.nbrCnt; n0 += 4) {
+        const int n = n0 + (lane >> 3), ft = lane & 7;
+        const size_t idx = (size_t)(g.nbrOff + n) * 64 + gt * 8 + ft;
+        const int v = (n < g.nbrCnt) ? (int)B.cnt64[idx] : 0;
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (n < g.nbrCnt) B.segOff[idx] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) B.blockCnt[blk] = run;
+}
+
+// one CTA: tuple offsets of the blocks, unit size, unit offsets of the blocks
+__device__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long *sm, unsigned long long &total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long s = sm[lane];
+        unsigned long long si = s;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, si, off);
+            if (lane >= off) si += t;
+        }
+        sm[lane] = si - s;
+        if (lane == 31) sm[32] = si;
+    }
+    __syncthreads();
+    const unsigned long long res = sm[warp] + incl - v;
+    total = sm[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(1024) pipe_blockscan_kernel(PipeBuffers B, int nBlocks, int unitHint) {
+    __shared__ unsigned long long sm[33];
+    const int tid = threadIdx.x;
+    const int per = (nBlocks + 1023) / 1024;
+    const int b0 = min(tid * per, nBlocks), b1 = min(b0 + per, nBlocks);
+    unsigned long long local = 0;
+    for (int b = b0; b < b1; b++) local += (unsigned long long)B.blockCnt[b];
+    unsigned long long total;
+    unsigned long long off = block_excl_scan(local, sm, total);
+    for (int b = b0; b < b1; b++) {
+        B.blockTupOff[b] = (unsigned)off;
+        off += (unsigned long long)B.blockCnt[b];
+    }
+    // unit size: enough units to balance the persistent warps, bounded overhead per unit
+    long long U = (long long)(total / (unsigned long long)(unitHint * 8));
+    U = (U + 7) & ~7ll;
+    if (U < 32) U = 32;
+    if (U > 256) U = 256;
+    local = 0;
+    for (int b = b0; b < b1; b++) local += (unsigned long long)((B.blockCnt[b] + U - 1) / U);
+    unsigned long long totalUnits;
+    off = block_excl_scan(local, sm, totalUnits);
+    for (int b = b0; b < b1; b++) {
+        B.blockUnitOff[b] = (int)off;
+        off += (unsigned long long)((B.blockCnt[b] + U - 1) / U);
+    }
+    if (tid == 0) {
+        B.blockTupOff[nBlocks] = (unsigned)total;
+        B.blockUnitOff[nBlocks] = (int)totalUnits;
+        B.header->totalTuples = total;
+        B.header->nUnits = (int)totalUnits;
+        B.header->U = (int)U;
+    }
+}
+
+__global__ void __launch_bounds__(256) pipe_units_kernel(PipeBuffers B, int nBlocks) {
+    const int lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blk >= nBlocks) return;
+    const int U = B.header->U;
+    const int cnt = B.blockCnt[blk];
+    const unsigned t0 = B.blockTupOff[blk];
+    const int u0 = B.blockUnitOff[blk];
+    const int nu = (cnt + U - 1) / U;
+    for (int u = lane; u < nu; u += 32) {
+        UnitDesc d;
+        d.t0 = t0 + (unsigned)u * U;
+        d.cnt = min(U, cnt - u * U);
+        B.units[u0 + u] = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fill
+__global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffers B, int nNbr) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= nNbr) return;
+    const NbrEntry nb = P.nbr[w];
+    const GDesc g = P.gdesc[nb.g];
+    const DepthInfo di = P.depthInfo[g.depth];
+    const int *coff = P.candOff + di.cubeOff;
+    const int e0 = coff[nb.code];
+    const int nc = coff[nb.code + 1] - e0;
+    int d[3];
+    decode_delta(nb.code, di.W, d);
+    // lane l keeps the running write position of bits l and l + 32
+    unsigned pos0 = B.blockTupOff[nb.g * 8 + (lane >> 3)] + (unsigned)B.segOff[(size_t)w * 64 + lane];
+    unsigned pos1 = B.blockTupOff[nb.g * 8 + 4 + (lane >> 3)] + (unsigned)B.segOff[(size_t)w * 64 + 32 + lane];
+    const int fbase = (nb.fslot < P.nRealF) ? nb.fslot * 8 : P.nRealF * 8 + (nb.fslot - P.nRealF);
+    const bool gen = nb.fslot >= P.nRealF;
+    for (int base = 0; base < nc; base += 32) {
+        const int c = base + lane;
+        unsigned long long pass = 0ull;
+        int oi0 = 0, oi1 = 0, oi2 = 0;
+        if (c < nc) {
+            pass = B.masks[(size_t)nb.candBase + c];
+            if (pass) {
+                const int nbase = P.nodeBase[(size_t)P.candTerm[e0 + c] * P.DM + g.depth];
+                oi0 = (nbase + d[0]) * 4;
+                oi1 = (nbase + d[1]) * 4;
+                oi2 = (nbase + d[2]) * 4;
+            }
+        }
+        unsigned long long uni = warp_or64(pass);
+        while (uni) {
+            const int b = __ffsll((long long)uni) - 1;
+            uni &= uni - 1;
+            const bool mine = (pass >> b) & 1ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            const unsigned start = __shfl_sync(0xffffffffu, (b < 32) ? pos0 : pos1, b & 31);
+            if (mine) {
+                const int gt = b >> 3, ft = b & 7;
+                TupleRec r;
+                r.fblk = gen ? fbase : fbase + ft;
+                r.o0 = oi0 + 2 * (gt & 1) + (ft & 1);
+                r.o1 = oi1 + 2 * ((gt >> 1) & 1) + ((ft >> 1) & 1);
+                r.o2 = oi2 + 2 * ((gt >> 2) & 1) + ((ft >> 2) & 1);
+                *reinterpret_cast<int4 *>(B.tuples + start + __popc(bal & ((1u << lane) - 1u))) =
+                    make_int4(r.fblk, r.o0, r.o1, r.o2);
+            }
+            if (lane == (b & 31)) {
+                if (b < 32) pos0 += __popc(bal);
+                else pos1 += __popc(bal);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ contract
+struct OpFrag {
+    double a00, a01, a10, a11, b20, b21;
+};
+
+__device__ __forceinline__ OpFrag load_frags(const double *__restrict__ mats, const int4 rec, int fo) {
+    OpFrag f;
+    const double *o0 = mats + (size_t)rec.y * 64 + fo;
+    const double *o1 = mats + (size_t)rec.z * 64 + fo;
+    const double *o2 = mats + (size_t)rec.w * 64 + fo;
+    f.a00 = __ldg(o0);
+    f.a01 = __ldg(o0 + 4);
+    f.a10 = __ldg(o1);
+    f.a11 = __ldg(o1 + 4);
+    f.b20 = __ldg(o2);
+    f.b21 = __ldg(o2 + 4);
+    return f;
+}
+
+__global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_contract_kernel(ApplyParams P, PipeBuffers B, int nUnits) {
+    extern __shared__ __align__(16) double tiles[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, q = lane & 3;
+    const int sig = (r >> 1) + 4 * (r & 1); // sigma(r)
+    double *T = tiles + warp * kTileDoubles;
+    const int fo = q + 8 * r;         // operator fragment offset: element (q + 4s) + 8 r
+    const int bo = q + 8 * sig;       // source fragment offset: f[i0 = q + 4s, i1 = sigma(r), i2 = j]
+    const int nReal8 = P.nRealF * 8;
+    const int4 *recs = reinterpret_cast<const int4 *>(B.tuples);
+
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(B.queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nUnits) break;
+        const UnitDesc ud = B.units[u];
+        double acc[8][2];
+#pragma unroll
+        for (int t = 0; t < 8; t++) acc[t][0] = acc[t][1] = 0.0;
+        double bf[8][2];
+        int curF = -1;
+        int4 nrec = __ldg(recs + ud.t0);
+        OpFrag nf = load_frags(P.mats, nrec, fo);
+        for (int t = 0; t < ud.cnt; t++) {
+            const int4 rec = nrec;
+            const OpFrag of = nf;
+            if (t + 1 < ud.cnt) {
+                nrec = __ldg(recs + ud.t0 + t + 1);
+                nf = load_frags(P.mats, nrec, fo);
+            }
+            if (rec.x != curF) {
+                curF = rec.x;
+                const double *fblk = (curF < nReal8) ? P.fReal + (size_t)curF * 512 : P.fGen + (size_t)(curF - nReal8) * 512;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    bf[j][0] = __ldg(fblk + bo + 64 * j);
+                    bf[j][1] = __ldg(fblk + bo + 4 + 64 * j);
+                }
+            }
+            // stage 1: X1[m0=r][i1=q+4e][i2=j]; stage 2: X2[m1=r][m0=2q+e][i2=j]; then T[m1][i2][m0]
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double d10 = 0.0, d11 = 0.0;
+                dmma884(d10, d11, of.a00, bf[j][0]);
+                dmma884(d10, d11, of.a01, bf[j][1]);
+                double d20 = 0.0, d21 = 0.0;
+                dmma884(d20, d21, of.a10, d10);
+                dmma884(d20, d21, of.a11, d11);
+                *reinterpret_cast<double2 *>(T + 2 * q + kTileSi * j + kTileSm * r) = make_double2(d20, d21);
+            }
+            __syncwarp();
+            // stage 3: g[m0=t][m1=r][m2=2q+e] += sum_i2 X2 * O2[i2][m2]
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const double2 x0 = *reinterpret_cast<const double2 *>(T + 2 * v + kTileSi * q + kTileSm * r);
+                const double2 x1 = *reinterpret_cast<const double2 *>(T + 2 * v + kTileSi * (q + 4) + kTileSm * r);
+                dmma884(acc[2 * v][0], acc[2 * v][1], x0.x, of.b20);
+                dmma884(acc[2 * v][0], acc[2 * v][1], x1.x, of.b21);
+                dmma884(acc[2 * v + 1][0], acc[2 * v + 1][1], x0.y, of.b20);
+                dmma884(acc[2 * v + 1][0], acc[2 * v + 1][1], x1.y, of.b21);
+            }
+            __syncwarp();
+        }
+        // partial block of this unit: element m0 + 8 m1 + 64 m2
+        double *pb = B.partials + (size_t)u * 512 + 8 * r + 64 * (2 * q);
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            *reinterpret_cast<double2 *>(pb + 2 * v) = make_double2(acc[2 * v][0], acc[2 * v + 1][0]);
+            *reinterpret_cast<double2 *>(pb + 64 + 2 * v) = make_double2(acc[2 * v][1], acc[2 * v + 1][1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reduce
+__global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const int *__restrict__ gslots, double *__restrict__ gCoefs,
+                                                          double *__restrict__ gNorms, int nBlocks) {
+    const int lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blk >= nBlocks) return;
+    const int u0 = B.blockUnitOff[blk], u1 = B.blockUnitOff[blk + 1];
+    double2 s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = make_double2(0.0, 0.0);
+    for (int u = u0; u < u1; u++) { // unit order = tuple order: fixed summation order
+        const double2 *p = reinterpret_cast<const double2 *>(B.partials + (size_t)u * 512);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double2 v = p[i * 32 + lane];
+            s[i].x += v.x;
+            s[i].y += v.y;
+        }
+    }
+    const int slot = gslots[blk >> 3], gt = blk & 7;
+    double2 *o = reinterpret_cast<double2 *>(gCoefs + ((size_t)slot * 8 + gt) * 512);
+    double n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        o[i * 32 + lane] = s[i];
+        n2 = fma(s[i].x, s[i].x, n2);
+        n2 = fma(s[i].y, s[i].y, n2);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+    if (lane == 0) gNorms[(size_t)slot * 8 + gt] = sqrt(n2);
+}
+
+} // namespace
+
+void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cudaStream_t st) {
+    if (nNbr <= 0) return;
+    pipe_screen_kernel<<<(nNbr + 7) / 8, 256, 0, st>>>(P, B, nNbr);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st) {
+    const int nBlocks = nG * 8;
+    pipe_segscan_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(P, B, nBlocks);
+    pipe_blockscan_kernel<<<1, 1024, 0, st>>>(B, nBlocks, unitHint);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter() += 2;
+}
+
+void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st) {
+    const int nBlocks = nG * 8;
+    pipe_units_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, nBlocks);
+    launch_counter()++;
+    if (nNbr > 0) {
+        pipe_fill_kernel<<<(nNbr + 7) / 8, 256, 0, st>>>(P, B, nNbr);
+        launch_counter()++;
+    }
+    MRX_CUDA(cudaGetLastError());
+}
+
+int pipe_contract_grid() {
+    static int grid = 0;
+    if (!grid) {
+        int dev = 0, sms = 0;
+        MRX_CUDA(cudaGetDevice(&dev));
+        MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kContractWarps * kTileDoubles * sizeof(double))));
+        grid = sms * kContractCtasPerSm;
+    }
+    return grid;
+}
+
+int pipe_contract_warps() { return pipe_contract_grid() * kContractWarps; }
+
+void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
+    if (nUnits <= 0) return;
+    const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
+    MRX_CUDA(cudaMemsetAsync(B.queue, 0, sizeof(int), st));
+    pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, int nG, cudaStream_t st) {
+    const int nBlocks = nG * 8;
+    if (nBlocks <= 0) return;
+    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, nBlocks);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+} // namespace mrx
