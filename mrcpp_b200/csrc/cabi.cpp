@@ -21,7 +21,67 @@ std::map<size_t, std::vector<void *>> g_pin_free;
 std::map<void *, size_t> g_pin_size;
 } // namespace
 
+namespace {
+// caching device allocator: size classes = powers of two up to 1 GiB, multiples of 1 GiB above
+// (leaked on purpose: handles may be destroyed by the host language after static destructors ran)
+std::mutex &g_dev_mutex = *new std::mutex;
+std::map<size_t, std::vector<void *>> &g_dev_free = *new std::map<size_t, std::vector<void *>>;
+std::map<void *, size_t> &g_dev_size = *new std::map<void *, size_t>;
+size_t g_dev_cached = 0;
+size_t dev_size_class(size_t bytes) {
+    if (bytes < 512) return 512;
+    const size_t GiB = (size_t)1 << 30;
+    if (bytes > GiB) return (bytes + GiB - 1) / GiB * GiB;
+    size_t c = 512;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+} // namespace
+
 namespace mrx {
+void *dev_alloc(size_t bytes) {
+    const size_t cls = dev_size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        auto &fl = g_dev_free[cls];
+        if (!fl.empty()) {
+            void *p = fl.back();
+            fl.pop_back();
+            g_dev_cached -= cls;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, cls) != cudaSuccess) {
+        // give the cached blocks back to the driver and retry once
+        {
+            std::lock_guard<std::mutex> lock(g_dev_mutex);
+            cudaDeviceSynchronize();
+            for (auto &kv : g_dev_free) {
+                for (void *q : kv.second) {
+                    cudaFree(q);
+                    g_dev_size.erase(q);
+                }
+                kv.second.clear();
+            }
+            g_dev_cached = 0;
+        }
+        cudaGetLastError();
+        if (cudaMalloc(&p, cls) != cudaSuccess) MRX_ABORT("cudaMalloc failed (out of device memory)");
+    }
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    g_dev_size[p] = cls;
+    return p;
+}
+void dev_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    auto it = g_dev_size.find(p);
+    if (it == g_dev_size.end()) return;
+    g_dev_free[it->second].push_back(p);
+    g_dev_cached += it->second;
+}
+size_t dev_cached_bytes() { return g_dev_cached; }
 bool device_enabled() { return g_device_on; }
 void require_device(const char *what) {
     if (!g_device_on) MRX_ABORT(std::string(what) + ": no CUDA device selected (mrx_init device<0); there is no CPU fallback");

@@ -36,6 +36,19 @@ double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// MRX_PROFILE: report host-side calls that take longer than 3 ms (allocator growth, stalled copies)
+struct SlowCall {
+    const char *what;
+    double t0;
+    bool on;
+    SlowCall(const char *w, bool enabled) : what(w), t0(enabled ? now_ms() : 0.0), on(enabled) {}
+    ~SlowCall() {
+        if (!on) return;
+        double dt = now_ms() - t0;
+        if (dt > 3.0) std::fprintf(stderr, "[mrx] slow host call: %s %.2f ms\n", what, dt);
+    }
+};
+
 // ConvolutionCalculator::initBandSizes / calcBandSizeFactor (ConvolutionCalculator.cpp:105-139), including the
 // quirk that a negative width does not prevent the final assignment (the `continue` only skips the product).
 void band_size_factors(const Operator &op, int DM, std::vector<int> &bsf, std::vector<int> &bw) {
@@ -186,6 +199,7 @@ struct BandTables {
 static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
                       std::vector<int> workVec, mrx_apply_stats &S) {
     cudaStream_t st = stream();
+    const double tEnter = now_ms();
     Operator &op = oper.op;
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
@@ -245,6 +259,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     }
     double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
     const bool profile = getenv("MRX_PROFILE") != nullptr;
+    const double tLoop = now_ms();
     while (!workVec.empty()) {
         const int nG = (int)workVec.size();
         double tq = now_ms();
@@ -469,9 +484,13 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         tp_gen += now_ms() - tq;
         tq = now_ms();
         // ---- device storage for the output nodes of this iteration
-        out.dev.coefs.reserve((size_t)g.nReal * ncoef, true, st);
-        out.dev.norms.reserve((size_t)g.nReal * 8, true, st);
+        {
+            SlowCall sc("reserve output coefficients", profile);
+            out.dev.coefs.reserve((size_t)g.nReal * ncoef, true, st);
+            out.dev.norms.reserve((size_t)g.nReal * 8, true, st);
+        }
         out.dev.nNodes = g.nReal;
+        SlowCall *scUp = new SlowCall("descriptor uploads", profile);
 
         scr.units.reserve(std::max<size_t>(units.size(), 1), false, st);
         MRX_CUDA(cudaMemcpyAsync(scr.units.p, units.data(), sizeof(GDesc) * units.size(), cudaMemcpyHostToDevice, st));
@@ -521,12 +540,14 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         P.counters = scr.counters.p;
         P.derivDir = derivDir;
 
+        delete scUp;
         tp_upload += now_ms() - tq;
         tq = now_ms();
         MRX_CUDA(cudaEventRecord(ev0, st));
         if (usePipe) {
             const int nNbr = (int)nbr.size();
             P.gdesc = scr.gdesc.p; // node-level descriptors: balancing happens on the device
+            SlowCall scM("reserve masks/counts", profile);
             scr.masks.reserve(std::max<long long>(nCand, 1), false, st);
             scr.cnt64.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
             scr.segOff.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
@@ -544,11 +565,17 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             B.blockUnitOff = scr.blockUnitOff.p;
             B.header = scr.header.p;
             B.queue = scr.queue.p;
+            scM.~SlowCall();
+            scM.on = false;
             launch_pipe_screen(P, B, nNbr, st);
             launch_pipe_scan(P, B, nG, pipe_contract_warps(), st);
             PipeHeader hdr;
-            MRX_CUDA(cudaMemcpyAsync(&hdr, scr.header.p, sizeof(hdr), cudaMemcpyDeviceToHost, st));
-            MRX_CUDA(cudaStreamSynchronize(st));
+            {
+                SlowCall sc("header sync", profile);
+                MRX_CUDA(cudaMemcpyAsync(&hdr, scr.header.p, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+                MRX_CUDA(cudaStreamSynchronize(st));
+            }
+            SlowCall scT("reserve tuples/units/partials", profile);
             if (hdr.totalTuples >= (1ull << 32)) MRX_ABORT("apply: tuple list of one iteration exceeds 2^32 records");
             scr.tuples.reserve(std::max<size_t>((size_t)hdr.totalTuples, 1), false, st);
             scr.units2.reserve(std::max<size_t>((size_t)hdr.nUnits, 1), false, st);
@@ -556,6 +583,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             B.tuples = scr.tuples.p;
             B.units = scr.units2.p;
             B.partials = scr.partials.p;
+            scT.~SlowCall();
+            scT.on = false;
             launch_pipe_fill(P, B, nNbr, nG, st);
             MRX_CUDA(cudaEventRecord(ev2, st));
             launch_pipe_contract(P, B, hdr.nUnits, st);
@@ -630,6 +659,9 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         iter++;
         tp_host += now_ms() - tq;
     }
+    const double tLoopEnd = now_ms();
+    if (profile)
+        std::fprintf(stderr, "[mrx] run_apply ms: pre-loop %.2f loop %.2f\n", tLoop - tEnter, tLoopEnd - tLoop);
     if (profile)
         std::fprintf(stderr, "[mrx] host phases ms: tables %.2f enum %.2f phase2 %.2f gen %.2f upload %.2f wait %.2f split %.2f\n", tp_tables,
                      tp_enum, tp_phase2, tp_gen, tp_upload, tp_wait, tp_host);
@@ -645,6 +677,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     MRX_CUDA(cudaEventDestroy(ev1));
     MRX_CUDA(cudaEventDestroy(ev2));
     MRX_CUDA(cudaEventDestroy(ev3));
+    if (profile) std::fprintf(stderr, "[mrx] run_apply ms: post-loop %.2f\n", now_ms() - tLoopEnd);
 }
 
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
@@ -676,6 +709,9 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     S.ms_post = now_ms() - tp;
     S.n_nodes_out = out.host.nReal;
     S.kernel_launches = launch_counter() - launches0;
+    if (getenv("MRX_PROFILE"))
+        std::fprintf(stderr, "[mrx] device_apply ms: upload %.2f build %.2f post %.2f total %.2f\n", S.ms_upload, S.ms_build, S.ms_post,
+                     now_ms() - t0);
     if (stats) *stats = S;
 }
 

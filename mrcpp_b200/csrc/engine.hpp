@@ -14,29 +14,33 @@ struct mrx_mra {
 
 namespace mrx {
 
+/// Caching device allocator (cabi.cpp): blocks are rounded up to size classes and never returned to the driver
+/// while the library is loaded, so after the first apply every buffer (output coefficients that grow per
+/// refinement iteration, tuple lists, partial sums) is served in microseconds. All work runs on the one
+/// library stream, so reuse of a freed block is stream-ordered by construction. (cudaMallocAsync pools were
+/// measured to stall 10-150 ms per growth step on the B200 boxes.)
+void *dev_alloc(size_t bytes);
+void dev_free(void *p);
+size_t dev_cached_bytes();
+
 /// Growable device buffer. Growth is geometric and preserves contents (device-to-device copy).
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
-    /// stream-ordered allocation from the device memory pool (release threshold = never, set in mrx_init), so
-    /// growing and freeing buffers costs microseconds after the first apply
     void reserve(size_t n, bool keep, cudaStream_t st) {
         if (n <= cap) return;
         size_t ncap = n > 2 * cap ? n : 2 * cap;
-        T *np = nullptr;
-        if (cudaMallocAsync(&np, ncap * sizeof(T), st) != cudaSuccess) MRX_ABORT("cudaMallocAsync failed (out of device memory?)");
+        T *np = static_cast<T *>(dev_alloc(ncap * sizeof(T)));
         if (keep && p && cap) cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-        if (p) cudaFreeAsync(p, st);
+        if (p) dev_free(p);
         p = np;
         cap = ncap;
-        stream_ = st;
     }
     void release() {
-        if (p) cudaFreeAsync(p, stream_);
+        if (p) dev_free(p);
         p = nullptr;
         cap = 0;
     }
-    cudaStream_t stream_ = nullptr;
     ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
