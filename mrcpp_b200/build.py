@@ -21,6 +21,7 @@ SOURCES = [
     "cuda/apply.cu",
     "cuda/apply_kernels.cu",
     "cuda/apply_pipeline.cu",
+    "cuda/apply_enum.cu",
     "cuda/microbench.cu",
 ]
 HEADERS = ["engine.hpp", "host/mrx_host.hpp", "cuda/common.cuh", "cuda/kernels.cuh", "cuda/apply_kernels.cuh",

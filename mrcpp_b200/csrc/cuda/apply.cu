@@ -94,6 +94,27 @@ struct Scratch {
     DevBuf<TupleRec> tuples;
     DevBuf<UnitDesc> units2;
     DevBuf<int> queue;
+    // device enumeration (apply_enum.cu)
+    DevBuf<int4> gNodes;
+    DevBuf<int> pending;
+    DevBuf<int> newParents;
+    DevBuf<EnumCounters> ecnt;
+};
+
+/// input-tree topology on the device for the band enumeration: real nodes + generated nodes in one slot space
+struct DevTopo {
+    DevBuf<int> child0, depth, flag;
+    DevBuf<double> bound;
+    void reserve(size_t n, cudaStream_t st) {
+        if (n <= child0.cap) return;
+        const size_t old = child0.cap;
+        child0.reserve(n, true, st);
+        depth.reserve(n, true, st);
+        bound.reserve(n, true, st);
+        flag.reserve(n, true, st);
+        // new tail of the flag array must read 0
+        MRX_CUDA(cudaMemsetAsync(flag.p + old, 0, sizeof(int) * (flag.cap - old), st));
+    }
 };
 
 /// Host copy of the per-depth band tables (see DepthInfo). Built lazily for the depths that occur.
@@ -111,6 +132,11 @@ struct BandTables {
     std::vector<unsigned long long> candMask;
     std::vector<std::vector<std::array<int, 4>>> needed; // per depth: (dx,dy,dz,code) of offsets with candidates
     std::vector<std::vector<double>> maxO;               // per depth, per needed offset: max_{term,combo} |O|^3 * bandSizeFactor
+    // the same offsets flattened for the device enumeration (apply_enum.cu)
+    std::vector<OffEntry> offs;
+    std::vector<int> offStart, offCount; // [DM]
+    DevBuf<OffEntry> d_offs;
+    DevBuf<int> d_offStart, d_offCount;
     bool dirty = false;
 
     // integer part of the screening: per-term max width (applyOperComp :283), per-dimension band test per
@@ -191,6 +217,12 @@ struct BandTables {
                     }
                 }
         candOff.push_back((int)candTerm.size());
+        offStart[depth] = (int)offs.size();
+        offCount[depth] = (int)needed[depth].size();
+        for (size_t q = 0; q < needed[depth].size(); q++) {
+            const auto &o = needed[depth][q];
+            offs.push_back(OffEntry{o[0], o[1], o[2], o[3], maxO[depth][q]});
+        }
     }
 };
 
@@ -232,6 +264,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         btp->built.assign(DM, 0);
         btp->needed.resize(DM);
         btp->maxO.resize(DM);
+        btp->offStart.assign(DM, 0);
+        btp->offCount.assign(DM, 0);
         oper.bandCache = btp;
     }
     BandTables &bt = *btp;
@@ -256,6 +290,21 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     for (int n = 0; n < fRealN; n++) {
         fNodeNorm[n] = std::sqrt(f.sqn[n]);
         fMaxNorm = std::max(fMaxNorm, fNodeNorm[n]);
+    }
+    DevTopo topo;
+    int fTotal = fRealN; // real + generated input nodes known to the device
+    if (usePipe) {
+        std::vector<int> hChild0(fRealN), hDepth(fRealN);
+        for (int n = 0; n < fRealN; n++) {
+            hChild0[n] = f.nodes[n].child0;
+            hDepth[n] = f.nodes[n].scale - f.mra.rootScale;
+        }
+        topo.reserve((size_t)fRealN + 4096, st);
+        MRX_CUDA(cudaMemcpyAsync(topo.child0.p, hChild0.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(topo.depth.p, hDepth.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(topo.bound.p, fNodeNorm.data(), sizeof(double) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemsetAsync(topo.flag.p, 0, sizeof(int) * topo.flag.cap, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
     }
     double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
     const bool profile = getenv("MRX_PROFILE") != nullptr;
@@ -301,9 +350,10 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             int code;
             std::array<int, 3> l;
         };
-        std::vector<std::vector<Hit>> hits(nG);
+        const int nGH = usePipe ? 0 : nG; // the pipeline enumerates on the device (apply_enum.cu)
+        std::vector<std::vector<Hit>> hits(nGH);
 #pragma omp parallel for schedule(dynamic, 16)
-        for (int i = 0; i < nG; i++) {
+        for (int i = 0; i < nGH; i++) {
             const auto &nd = g.nodes[workVec[i]];
             const int dep = nd.scale - op.operRoot;
             if (dep < 0 || dep >= DM) continue; // deeper than every operator tree: empty band (:146-151)
@@ -349,7 +399,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         tq = now_ms();
         // phase 2 (serial, work-vector order): create the missing generated nodes, emit neighbour entries
         long long nCand = 0;
-        for (int i = 0; i < nG; i++) {
+        int nNbr = 0;
+        for (int i = 0; i < nGH; i++) {
             const auto &nd = g.nodes[workVec[i]];
             GDesc &d = gdesc[i];
             d.slot = workVec[i];
@@ -452,7 +503,96 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
                 MRX_CUDA(cudaMemcpyAsync(bt.d_candMask.p, bt.candMask.data(), sizeof(unsigned long long) * bt.candMask.size(),
                                          cudaMemcpyHostToDevice, st));
             }
+            if (usePipe) {
+                bt.d_offs.reserve(std::max<size_t>(bt.offs.size(), 1), false, st);
+                bt.d_offStart.reserve(DM, false, st);
+                bt.d_offCount.reserve(DM, false, st);
+                if (!bt.offs.empty())
+                    MRX_CUDA(cudaMemcpyAsync(bt.d_offs.p, bt.offs.data(), sizeof(OffEntry) * bt.offs.size(), cudaMemcpyHostToDevice, st));
+                MRX_CUDA(cudaMemcpyAsync(bt.d_offStart.p, bt.offStart.data(), sizeof(int) * DM, cudaMemcpyHostToDevice, st));
+                MRX_CUDA(cudaMemcpyAsync(bt.d_offCount.p, bt.offCount.data(), sizeof(int) * DM, cudaMemcpyHostToDevice, st));
+                MRX_CUDA(cudaStreamSynchronize(st)); // host vectors may be reallocated by the next build()
+            }
             bt.dirty = false;
+        }
+        if (usePipe) {
+            // ---- device enumeration of the operator band + generated input nodes (apply_enum.cu)
+            std::vector<int4> gN(nG);
+            long long nbrCap = 0;
+            for (int i = 0; i < nG; i++) {
+                const auto &nd = g.nodes[workVec[i]];
+                const int dep = nd.scale - op.operRoot;
+                gN[i] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
+                if (dep >= 0 && dep < DM && bt.built[dep]) nbrCap += bt.offCount[dep];
+            }
+            if (nbrCap >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
+            scr.gNodes.reserve(nG, false, st);
+            scr.gslots.reserve(nG, false, st);
+            scr.gdesc.reserve(nG, false, st);
+            scr.nbr.reserve(std::max<long long>(nbrCap, 1), false, st);
+            scr.pending.reserve(std::max<long long>(nbrCap, 1), false, st);
+            scr.ecnt.reserve(1, false, st);
+            MRX_CUDA(cudaMemcpyAsync(scr.gNodes.p, gN.data(), sizeof(int4) * nG, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemsetAsync(scr.ecnt.p, 0, sizeof(EnumCounters), st));
+            EnumParams E{};
+            E.gNodes = scr.gNodes.p;
+            E.gSlots = scr.gslots.p;
+            E.nG = nG;
+            E.depthShift = op.operRoot - f.mra.rootScale;
+            E.offStart = bt.d_offStart.p;
+            E.offCount = bt.d_offCount.p;
+            E.offs = bt.d_offs.p;
+            E.depthInfo = bt.d_info.p;
+            E.candOff = bt.d_candOff.p;
+            E.DM = DM;
+            E.fChild0 = topo.child0.p;
+            E.fDepth = topo.depth.p;
+            E.fBound = topo.bound.p;
+            E.fFlag = topo.flag.p;
+            for (int x = 0; x < 3; x++) {
+                E.corner[x] = f.mra.corner[x];
+                E.nboxes[x] = f.mra.nboxes[x];
+            }
+            E.gThrs = gThrsIter;
+            E.fMaxNorm = fMaxNorm;
+            E.screenOn = screenOn ? 1 : 0;
+            E.gdesc = scr.gdesc.p;
+            E.nbr = scr.nbr.p;
+            E.pending = scr.pending.p;
+            E.cnt = scr.ecnt.p;
+            launch_enum(E, st);
+            EnumCounters ec;
+            MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
+            MRX_CUDA(cudaStreamSynchronize(st));
+            nNbr = ec.nNbr;
+            nCand = (long long)ec.nCand;
+            // generated input nodes, one round per missing level
+            const int nPending = ec.nPending;
+            while (nPending > 0) {
+                scr.newParents.reserve(nPending, false, st);
+                scr.genItems.reserve((size_t)2 * nPending, false, st);
+                E.newParents = scr.newParents.p;
+                E.genItems = scr.genItems.p;
+                MRX_CUDA(cudaMemsetAsync(&scr.ecnt.p->nUnresolved, 0, 2 * sizeof(int), st)); // nUnresolved, nNewParents
+                launch_enum_resolve(E, nPending, st);
+                MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
+                MRX_CUDA(cudaStreamSynchronize(st));
+                if (ec.nUnresolved == 0) break;
+                const int nNew = ec.nNewParents;
+                topo.reserve((size_t)fTotal + 8 * (size_t)nNew, st);
+                E.fChild0 = topo.child0.p;
+                E.fDepth = topo.depth.p;
+                E.fBound = topo.bound.p;
+                E.fFlag = topo.flag.p;
+                inp.dev.genCoefs.reserve((size_t)(fTotal - fRealN + 8 * nNew) * Kd, true, st);
+                inp.dev.genNorms.reserve((size_t)(fTotal - fRealN + 8 * nNew), true, st);
+                launch_enum_create(E, nNew, fTotal, st);
+                launch_gen_children(inp.dev.coefs.p, inp.dev.genCoefs.p, inp.dev.genNorms.p, fRealN, scr.genItems.p, nNew, K, filt, st);
+                fTotal += 8 * nNew;
+                S.gen_nodes += 8 * (long long)nNew;
+                inp.dev.nGen = fTotal - fRealN;
+            }
         }
         // ---- generated input nodes: parents in creation order; a parent created this iteration must be
         //      filled before its own children -> waves
@@ -499,13 +639,16 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scr.reduceItems.reserve(reduceItems.size(), false, st);
             MRX_CUDA(cudaMemcpyAsync(scr.reduceItems.p, reduceItems.data(), sizeof(int) * reduceItems.size(), cudaMemcpyHostToDevice, st));
         }
-        scr.gdesc.reserve(nG, false, st);
-        scr.nbr.reserve(std::max<size_t>(nbr.size(), 1), false, st);
-        scr.gslots.reserve(nG, false, st);
-        MRX_CUDA(cudaMemcpyAsync(scr.gdesc.p, gdesc.data(), sizeof(GDesc) * nG, cudaMemcpyHostToDevice, st));
-        if (!nbr.empty())
-            MRX_CUDA(cudaMemcpyAsync(scr.nbr.p, nbr.data(), sizeof(NbrEntry) * nbr.size(), cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+        if (!usePipe) {
+            scr.gdesc.reserve(nG, false, st);
+            scr.nbr.reserve(std::max<size_t>(nbr.size(), 1), false, st);
+            scr.gslots.reserve(nG, false, st);
+            MRX_CUDA(cudaMemcpyAsync(scr.gdesc.p, gdesc.data(), sizeof(GDesc) * nG, cudaMemcpyHostToDevice, st));
+            if (!nbr.empty())
+                MRX_CUDA(cudaMemcpyAsync(scr.nbr.p, nbr.data(), sizeof(NbrEntry) * nbr.size(), cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+            nNbr = (int)nbr.size();
+        }
 
         // gThrs (ConvolutionCalculator.cpp:241-248)
         double gThrs = g.squareNorm;
@@ -545,7 +688,6 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         tq = now_ms();
         MRX_CUDA(cudaEventRecord(ev0, st));
         if (usePipe) {
-            const int nNbr = (int)nbr.size();
             P.gdesc = scr.gdesc.p; // node-level descriptors: balancing happens on the device
             SlowCall scM("reserve masks/counts", profile);
             scr.masks.reserve(std::max<long long>(nCand, 1), false, st);
@@ -618,8 +760,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             contract_ms += msc;
         }
         if (profile)
-            std::fprintf(stderr, "[mrx] iter %d nG %d nbr %zu cand %lld tuples %lld kernels %.3f ms (contract %.3f ms, %.2f TF/s)\n", iter, nG,
-                         nbr.size(), nCand, iterTuples, ms, msc, msc > 0 ? iterTuples * 24576.0 / (msc * 1e-3) / 1e12 : 0.0);
+            std::fprintf(stderr, "[mrx] iter %d nG %d nbr %d cand %lld tuples %lld kernels %.3f ms (contract %.3f ms, %.2f TF/s)\n", iter, nG,
+                         nNbr, nCand, iterTuples, ms, msc, msc > 0 ? iterTuples * 24576.0 / (msc * 1e-3) / 1e12 : 0.0);
         for (int i = 0; i < nG; i++) {
             int n = workVec[i];
             double sq = 0.0;

@@ -58,6 +58,51 @@ struct ApplyParams {
 
 void launch_apply(const ApplyParams &P, int nG, cudaStream_t st);
 
+// ---- band enumeration on the device (apply_enum.cu) ----------------------------------------------------
+/// one reachable offset of a depth's band cube
+struct OffEntry {
+    int dx, dy, dz;
+    int code;    // offset code inside the band cube
+    double maxO; // max over (term, gt, ft) of |O|^3 * bandSizeFactor: upper bound used for the early-out
+};
+struct EnumCounters {
+    int nNbr;
+    unsigned nCand;
+    int nPending;
+    int nUnresolved;
+    int nNewParents;
+    int pad;
+};
+struct EnumParams {
+    const int4 *gNodes; // [nG] (operator depth, lx, ly, lz) of the work-vector nodes
+    const int *gSlots;  // [nG]
+    int nG;
+    int depthShift; // function-tree depth = operator depth + depthShift
+    const int *offStart, *offCount; // [DM] into offs
+    const OffEntry *offs;
+    const DepthInfo *depthInfo;
+    const int *candOff;
+    int DM;
+    // input-tree topology (real + generated nodes, unified slot space)
+    int *fChild0;
+    int *fDepth;
+    double *fBound; // upper bound of the node norm
+    int *fFlag;
+    int corner[3], nboxes[3];
+    double gThrs, fMaxNorm;
+    int screenOn;
+    // outputs
+    GDesc *gdesc;
+    NbrEntry *nbr;
+    int *pending;
+    int *newParents;
+    int *genItems;
+    EnumCounters *cnt;
+};
+void launch_enum(const EnumParams &E, cudaStream_t st);
+void launch_enum_resolve(const EnumParams &E, int nPending, cudaStream_t st);
+void launch_enum_create(const EnumParams &E, int nNew, int firstSlot, cudaStream_t st);
+
 // ---- work-list pipeline (apply_pipeline.cu): screen -> scan -> fill -> contract -> reduce -------------------
 /// one surviving (g, f, ft, gt, term) tuple: indices of the source block and of the three 1-D operator blocks
 struct TupleRec {
