@@ -23,6 +23,7 @@ extern "C" {
 typedef struct mrx_mra mrx_mra;   /* MultiResolutionAnalysis<3>  (src/trees/MultiResolutionAnalysis.h:49) */
 typedef struct mrx_tree mrx_tree; /* FunctionTree<3,double>      (src/trees/FunctionTree.h)               */
 typedef struct mrx_oper mrx_oper; /* ConvolutionOperator<3> / DerivativeOperator<3> packed for HBM       */
+typedef struct mrx_comm mrx_comm; /* one rank of a multi-GPU job (NCCL communicator over NVLink)          */
 
 enum { MRX_TOP_DOWN = 0, MRX_BOTTOM_UP = 1 }; /* api/constants.h TopDown/BottomUp */
 
@@ -117,6 +118,24 @@ int mrx_helmholtz_kernel(double mu, double epsilon, double r_min, double r_max, 
  * `out` enters with its starting grid (normally empty roots) and no coefficients. The result stays
  * resident in HBM; mrx_tree_to_arrays / mrx_tree_sync_host bring it back. */
 int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec, mrx_apply_stats *stats);
+/* ---- multi-GPU: one process per GPU ----------------------------------------------
+ * The reference distributes whole trees over MPI ranks (src/utils/parallel.cpp) and runs each apply inside
+ * one rank with OpenMP (TreeCalculator.h:39-50). Here ONE apply is sharded: every refinement iteration's
+ * work vector is cut into contiguous ranges, one per rank (mrx_shard_partition); input tree and operator
+ * are replicated; component norms (for TreeBuilder's norm bookkeeping and the split decisions, which every
+ * rank then takes identically) and the output coefficient blocks are all-gathered over NCCL, so every
+ * rank ends with the complete output tree, bit-identical across ranks. Rank 0 creates the id, the host
+ * framework broadcasts its 128 bytes (torch.distributed / MPI_Bcast), every rank calls mrx_comm_create. */
+int mrx_comm_unique_id(char *id128);
+mrx_comm *mrx_comm_create(int rank, int world, const char *id128);
+void mrx_comm_destroy(mrx_comm *comm);
+int mrx_comm_rank(const mrx_comm *comm);
+int mrx_comm_size(const mrx_comm *comm);
+void mrx_shard_partition(const long long *cost, int n, int world, int *begin /*[world+1]*/);
+/* mrcpp::apply sharded over the ranks of `comm` (comm == NULL: same as mrx_apply). Collective: every rank
+ * calls it with identical arguments. stats->f_applied / gen_nodes are summed over ranks. */
+int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
+                      const mrx_comm *comm, mrx_apply_stats *stats);
 /* mrcpp::apply(out, DerivativeOperator, inp, dir): src/treebuilders/apply.cpp:379-412 */
 int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, mrx_apply_stats *stats);
 /* MWTree::mwTransform(type, overwrite): src/trees/MWTree.cpp:143-216 (+ norms of touched nodes) */

@@ -262,13 +262,44 @@ def copy_grid(out, inp):
     _lib.load().mrx_tree_copy_grid(out._h, inp._h)
 
 
-def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None):
+class Comm:
+    """One rank of a multi-GPU job: NCCL communicator created inside the library. `bcast` ships the 128-byte
+    NCCL id from rank 0 to every rank (e.g. a torch.distributed / mpi4py broadcast of a bytes object)."""
+
+    def __init__(self, rank, world, bcast):
+        L = _lib.load()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            L.mrx_comm_unique_id(buf)
+        ident = bcast(bytes(buf.raw))
+        self._h = L.mrx_comm_create(int(rank), int(world), C.create_string_buffer(ident, 128))
+        self.rank, self.world = rank, world
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.load().mrx_comm_destroy(self._h)
+            self._h = None
+
+
+def shard_partition(cost, world):
+    """contiguous split of one iteration's work vector over `world` ranks (mrx_shard_partition)"""
+    import numpy as np
+    cost = np.ascontiguousarray(cost, dtype=np.int64)
+    begin = (C.c_int * (world + 1))()
+    _lib.load().mrx_shard_partition(cost.ctypes.data_as(C.POINTER(C.c_longlong)), len(cost), world, begin)
+    return list(begin)
+
+
+def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None, comm=None):
     """mrcpp::apply. ConvolutionOperator form: apply(prec, out, oper, inp, maxIter, absPrec)
     (src/treebuilders/apply.cpp:68-93); derivative form: apply(None, out, D, inp, dir=d) (:379-412).
-    Returns the work counters (OperatorStatistics)."""
+    comm: shard the apply over the ranks of a Comm (collective call). Returns the work counters
+    (OperatorStatistics)."""
     st = ApplyStats()
     if dir is not None:
         _lib.load().mrx_apply_derivative(out._h, oper._h, inp._h, int(dir), C.byref(st))
+    elif comm is not None:
+        _lib.load().mrx_apply_sharded(float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, comm._h, C.byref(st))
     else:
         _lib.load().mrx_apply(float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, C.byref(st))
     return st

@@ -68,6 +68,13 @@ SIGNATURES = {
     "mrx_poisson_kernel": (_I, [_D, _D, _D, _PD, _PD, _I]),
     "mrx_helmholtz_kernel": (_I, [_D, _D, _D, _D, _PD, _PD, _I]),
     "mrx_apply": (_I, [_D, _P, _P, _P, _I, _I, C.POINTER(ApplyStats)]),
+    "mrx_apply_sharded": (_I, [_D, _P, _P, _P, _I, _I, _P, C.POINTER(ApplyStats)]),
+    "mrx_comm_unique_id": (_I, [C.c_char_p]),
+    "mrx_comm_create": (_P, [_I, _I, C.c_char_p]),
+    "mrx_comm_destroy": (None, [_P]),
+    "mrx_comm_rank": (_I, [_P]),
+    "mrx_comm_size": (_I, [_P]),
+    "mrx_shard_partition": (None, [C.POINTER(C.c_longlong), _I, _I, _PI]),
     "mrx_apply_derivative": (_I, [_P, _P, _P, _I, C.POINTER(ApplyStats)]),
     "mrx_mw_transform": (_I, [_P, _I, _I]),
     "mrx_calc_square_norm": (_D, [_P]),

@@ -22,6 +22,7 @@ SOURCES = [
     "cuda/apply_kernels.cu",
     "cuda/apply_pipeline.cu",
     "cuda/apply_enum.cu",
+    "cuda/comm.cu",
     "cuda/microbench.cu",
 ]
 HEADERS = ["engine.hpp", "host/mrx_host.hpp", "cuda/common.cuh", "cuda/kernels.cuh", "cuda/apply_kernels.cuh",
@@ -66,7 +67,7 @@ def build_lib(force=False, verbose=False):
         with open(os.path.join(objdir, s.replace("/", "_") + ".log"), "w") as f:
             f.write(out)
     if force or procs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-lgomp", "-cudart", "static"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-cudart", "static"]
         subprocess.check_call(cmd)
     return LIB
 

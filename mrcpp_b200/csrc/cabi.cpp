@@ -373,6 +373,14 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
     device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats);
     return 0;
 }
+int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec, const mrx_comm *comm,
+                      mrx_apply_stats *stats) {
+    require_device("mrx_apply_sharded");
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (oper->op.derivative) MRX_ABORT("mrx_apply_sharded: derivative operator passed to the convolution apply");
+    device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats, comm);
+    return 0;
+}
 int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, mrx_apply_stats *stats) {
     require_device("mrx_apply_derivative");
     if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");

@@ -99,6 +99,9 @@ struct Scratch {
     DevBuf<int> pending;
     DevBuf<int> newParents;
     DevBuf<EnumCounters> ecnt;
+    DevBuf<double> normsW; // component norms of the iteration's nodes in work-vector order
+    DevBuf<int> gslotsAll; // sharded apply: slots of the whole work vector
+    DevBuf<double> stage;  // sharded apply: output blocks in work-vector order for the exchange
 };
 
 /// input-tree topology on the device for the band enumeration: real nodes + generated nodes in one slot space
@@ -229,7 +232,7 @@ struct BandTables {
 } // namespace
 
 static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
-                      std::vector<int> workVec, mrx_apply_stats &S) {
+                      std::vector<int> workVec, mrx_apply_stats &S, const mrx_comm *comm = nullptr) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
@@ -237,6 +240,10 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     const bool deriv = derivDir >= 0;
     const char *legacy = getenv("MRX_LEGACY");
     const bool usePipe = (out.host.K == 8) && !deriv && !(legacy && legacy[0] == '1');
+    const int world = comm_world(comm), rank = comm_rank(comm);
+    const char *uEnv = getenv("MRX_UNIT_TUPLES");
+    const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
+    if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the k = 7 convolution pipeline only");
     std::vector<int> bsf, bwTab;
     band_size_factors(op, DM, bsf, bwTab);
     oper.dev.bsf.reserve(bsf.size(), false, st);
@@ -351,6 +358,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             std::array<int, 3> l;
         };
         const int nGH = usePipe ? 0 : nG; // the pipeline enumerates on the device (apply_enum.cu)
+        int wb = 0, we = nG, nL = nG;     // range of the work vector this rank computes
+        std::vector<int> shardBegin;
         std::vector<std::vector<Hit>> hits(nGH);
 #pragma omp parallel for schedule(dynamic, 16)
         for (int i = 0; i < nGH; i++) {
@@ -517,28 +526,46 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         }
         if (usePipe) {
             // ---- device enumeration of the operator band + generated input nodes (apply_enum.cu)
-            std::vector<int4> gN(nG);
+            // sharded apply: this rank owns the contiguous range [wb, we) of the work vector
+            if (world > 1) {
+                std::vector<long long> cost(nG);
+                for (int i = 0; i < nG; i++) {
+                    const int dep = g.nodes[workVec[i]].scale - op.operRoot;
+                    cost[i] = 1 + ((dep >= 0 && dep < DM && bt.built[dep]) ? bt.offCount[dep] : 0);
+                }
+                shardBegin.assign(world + 1, 0);
+                mrx_shard_partition(cost.data(), nG, world, shardBegin.data());
+                wb = shardBegin[rank];
+                we = shardBegin[rank + 1];
+            } else {
+                wb = 0;
+                we = nG;
+            }
+            nL = we - wb;
+            std::vector<int4> gN(std::max(nL, 1));
             long long nbrCap = 0;
-            for (int i = 0; i < nG; i++) {
+            for (int i = wb; i < we; i++) {
                 const auto &nd = g.nodes[workVec[i]];
                 const int dep = nd.scale - op.operRoot;
-                gN[i] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
+                gN[i - wb] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
                 if (dep >= 0 && dep < DM && bt.built[dep]) nbrCap += bt.offCount[dep];
             }
             if (nbrCap >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
-            scr.gNodes.reserve(nG, false, st);
-            scr.gslots.reserve(nG, false, st);
-            scr.gdesc.reserve(nG, false, st);
+            scr.gNodes.reserve(std::max(nL, 1), false, st);
+            scr.gslots.reserve(std::max(nL, 1), false, st);
+            scr.gdesc.reserve(std::max(nL, 1), false, st);
             scr.nbr.reserve(std::max<long long>(nbrCap, 1), false, st);
             scr.pending.reserve(std::max<long long>(nbrCap, 1), false, st);
             scr.ecnt.reserve(1, false, st);
-            MRX_CUDA(cudaMemcpyAsync(scr.gNodes.p, gN.data(), sizeof(int4) * nG, cudaMemcpyHostToDevice, st));
-            MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+            if (nL > 0) {
+                MRX_CUDA(cudaMemcpyAsync(scr.gNodes.p, gN.data(), sizeof(int4) * nL, cudaMemcpyHostToDevice, st));
+                MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data() + wb, sizeof(int) * nL, cudaMemcpyHostToDevice, st));
+            }
             MRX_CUDA(cudaMemsetAsync(scr.ecnt.p, 0, sizeof(EnumCounters), st));
             EnumParams E{};
             E.gNodes = scr.gNodes.p;
             E.gSlots = scr.gslots.p;
-            E.nG = nG;
+            E.nG = nL;
             E.depthShift = op.operRoot - f.mra.rootScale;
             E.offStart = bt.d_offStart.p;
             E.offCount = bt.d_offCount.p;
@@ -693,9 +720,10 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scr.masks.reserve(std::max<long long>(nCand, 1), false, st);
             scr.cnt64.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
             scr.segOff.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
-            scr.blockCnt.reserve((size_t)nG * 8, false, st);
-            scr.blockTupOff.reserve((size_t)nG * 8 + 1, false, st);
-            scr.blockUnitOff.reserve((size_t)nG * 8 + 1, false, st);
+            scr.blockCnt.reserve((size_t)nL * 8 + 8, false, st);
+            scr.blockTupOff.reserve((size_t)nL * 8 + 9, false, st);
+            scr.blockUnitOff.reserve((size_t)nL * 8 + 9, false, st);
+            scr.normsW.reserve((size_t)nG * 8, false, st);
             scr.header.reserve(1, false, st);
             scr.queue.reserve(1, false, st);
             PipeBuffers B{};
@@ -710,7 +738,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scM.~SlowCall();
             scM.on = false;
             launch_pipe_screen(P, B, nNbr, st);
-            launch_pipe_scan(P, B, nG, pipe_contract_warps(), st);
+            launch_pipe_scan(P, B, nL, unitTuples, st);
             PipeHeader hdr;
             {
                 SlowCall sc("header sync", profile);
@@ -727,13 +755,34 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             B.partials = scr.partials.p;
             scT.~SlowCall();
             scT.on = false;
-            launch_pipe_fill(P, B, nNbr, nG, st);
+            launch_pipe_fill(P, B, nNbr, nL, st);
             MRX_CUDA(cudaEventRecord(ev2, st));
             launch_pipe_contract(P, B, hdr.nUnits, st);
             MRX_CUDA(cudaEventRecord(ev3, st));
             // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-            launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, nG, st);
+            launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, scr.normsW.p + (size_t)wb * 8, nL, st);
             MRX_CUDA(cudaEventRecord(ev1, st));
+            if (world > 1) {
+                // ---- exchange over NVLink: norms of every node (drives the identical split decision on all ranks)
+                //      and the output coefficient blocks (every rank ends with the complete tree)
+                std::vector<size_t> off(world), cnt(world);
+                for (int r = 0; r < world; r++) {
+                    off[r] = (size_t)shardBegin[r] * 8 * sizeof(double);
+                    cnt[r] = (size_t)(shardBegin[r + 1] - shardBegin[r]) * 8 * sizeof(double);
+                }
+                comm_allgatherv(comm, scr.normsW.p, off.data(), cnt.data(), st);
+                scr.gslotsAll.reserve(nG, false, st);
+                scr.stage.reserve((size_t)nG * ncoef, false, st);
+                MRX_CUDA(cudaMemcpyAsync(scr.gslotsAll.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+                launch_pack_nodes(out.dev.coefs.p, scr.stage.p, scr.gslotsAll.p, wb, nL, ncoef, true, st);
+                for (int r = 0; r < world; r++) {
+                    off[r] *= (size_t)Kd;
+                    cnt[r] *= (size_t)Kd;
+                }
+                comm_allgatherv(comm, scr.stage.p, off.data(), cnt.data(), st);
+                launch_pack_nodes(out.dev.coefs.p, scr.stage.p, scr.gslotsAll.p, 0, wb, ncoef, false, st);
+                launch_pack_nodes(out.dev.coefs.p, scr.stage.p, scr.gslotsAll.p, we, nG - we, ncoef, false, st);
+            }
             iterTuples = (long long)hdr.totalTuples;
             tuplesTotal += iterTuples;
         } else {
@@ -743,12 +792,19 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
             launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
         }
-        // norms are scattered by slot -> copy the covering range
-        int lo = *std::min_element(workVec.begin(), workVec.end());
-        int hi = *std::max_element(workVec.begin(), workVec.end());
-        std::vector<double> range((size_t)(hi - lo + 1) * 8);
-        MRX_CUDA(cudaMemcpyAsync(range.data(), out.dev.norms.p + (size_t)lo * 8, sizeof(double) * range.size(),
-                                 cudaMemcpyDeviceToHost, st));
+        // norms back to the host: work-vector order (pipeline) or the covering slot range (legacy kernels)
+        int lo = 0;
+        std::vector<double> range;
+        if (usePipe) {
+            range.resize((size_t)nG * 8);
+            MRX_CUDA(cudaMemcpyAsync(range.data(), scr.normsW.p, sizeof(double) * range.size(), cudaMemcpyDeviceToHost, st));
+        } else {
+            lo = *std::min_element(workVec.begin(), workVec.end());
+            int hi = *std::max_element(workVec.begin(), workVec.end());
+            range.resize((size_t)(hi - lo + 1) * 8);
+            MRX_CUDA(cudaMemcpyAsync(range.data(), out.dev.norms.p + (size_t)lo * 8, sizeof(double) * range.size(),
+                                     cudaMemcpyDeviceToHost, st));
+        }
         MRX_CUDA(cudaStreamSynchronize(st));
         tp_wait += now_ms() - tq;
         tq = now_ms();
@@ -766,7 +822,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             int n = workVec[i];
             double sq = 0.0;
             for (int c = 0; c < 8; c++) {
-                double v = range[(size_t)(n - lo) * 8 + c];
+                double v = usePipe ? range[(size_t)i * 8 + c] : range[(size_t)(n - lo) * 8 + c];
                 g.cnorm[(size_t)n * 8 + c] = v;
                 sq += v * v;
             }
@@ -814,6 +870,16 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     MRX_CUDA(cudaMemcpyAsync(counters, scr.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
     MRX_CUDA(cudaStreamSynchronize(st));
     S.f_applied = usePipe ? tuplesTotal : (long long)counters[0];
+    if (world > 1) {
+        double h[2] = {(double)S.f_applied, (double)S.gen_nodes};
+        scr.normsW.reserve(2, false, st);
+        MRX_CUDA(cudaMemcpyAsync(scr.normsW.p, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        comm_allreduce_sum(comm, scr.normsW.p, 2, st);
+        MRX_CUDA(cudaMemcpyAsync(h, scr.normsW.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        S.f_applied = (long long)(h[0] + 0.5);
+        S.gen_nodes = (long long)(h[1] + 0.5);
+    }
     out.dev.nNodes = g.nReal;
     MRX_CUDA(cudaEventDestroy(ev0));
     MRX_CUDA(cudaEventDestroy(ev1));
@@ -823,7 +889,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
 }
 
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats) {
+                  mrx_apply_stats *stats, const mrx_comm *comm) {
     require_device("device_apply");
     mrx_apply_stats S{};
     long long launches0 = launch_counter();
@@ -837,7 +903,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     double tb = now_ms();
     std::vector<int> workVec;
     out.host.nodeTable(workVec); // getInitialWorkVector: ALL nodes of `out` (ConvolutionCalculator.cpp:400-405)
-    run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);
+    run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, comm);
     S.ms_build = now_ms() - tb;
 
     // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)

@@ -137,6 +137,10 @@ void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cu
 void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st);
 void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st);
 void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st);
-void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, int nG, cudaStream_t st);
+/// gslots / gNormsW point at the first node of the (rank-local) range
+void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
+                        cudaStream_t st);
+/// copy `count` nodes (work-vector indices first..) between the node store and a work-vector-ordered staging buffer
+void launch_pack_nodes(double *coefs, double *stage, const int *gslots, int first, int count, int ncoef, bool toStage, cudaStream_t st);
 
 } // namespace mrx

@@ -193,11 +193,9 @@ __global__ void __launch_bounds__(1024) pipe_blockscan_kernel(PipeBuffers B, int
         B.blockTupOff[b] = (unsigned)off;
         off += (unsigned long long)B.blockCnt[b];
     }
-    // unit size: enough units to balance the persistent warps, bounded overhead per unit
-    long long U = (long long)(total / (unsigned long long)(unitHint * 8));
-    U = (U + 7) & ~7ll;
-    if (U < 32) U = 32;
-    if (U > 256) U = 256;
+    // unit size: fixed, so that the summation order of a block does not depend on how much other work the launch
+    // holds (results are bit-identical for any number of ranks sharing the work vector)
+    const long long U = unitHint;
     local = 0;
     for (int b = b0; b < b1; b++) local += (unsigned long long)((B.blockCnt[b] + U - 1) / U);
     unsigned long long totalUnits;
@@ -383,7 +381,7 @@ __global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_
 
 // ------------------------------------------------------------------------------------------------ reduce
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const int *__restrict__ gslots, double *__restrict__ gCoefs,
-                                                          double *__restrict__ gNorms, int nBlocks) {
+                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks) {
     const int lane = threadIdx.x & 31;
     const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blk >= nBlocks) return;
@@ -411,7 +409,20 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const i
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-    if (lane == 0) gNorms[(size_t)slot * 8 + gt] = sqrt(n2);
+    if (lane == 0) {
+        const double nrm = sqrt(n2);
+        gNorms[(size_t)slot * 8 + gt] = nrm;
+        gNormsW[blk] = nrm; // work-vector order: what the host's norm bookkeeping and the rank exchange read
+    }
+}
+
+// sharded apply: output blocks of a rank's range packed in work-vector order for the exchange, and back
+__global__ void __launch_bounds__(256) pack_nodes_kernel(const double *__restrict__ coefs, double *__restrict__ stage,
+                                                         const int *__restrict__ gslots, int first, int ncoef, int toStage) {
+    const int i = first + blockIdx.x;
+    const double2 *src = reinterpret_cast<const double2 *>(toStage ? coefs + (size_t)gslots[i] * ncoef : stage + (size_t)i * ncoef);
+    double2 *dst = reinterpret_cast<double2 *>(toStage ? stage + (size_t)i * ncoef : const_cast<double *>(coefs) + (size_t)gslots[i] * ncoef);
+    for (int e = threadIdx.x; e < ncoef / 2; e += 256) dst[e] = src[e];
 }
 
 } // namespace
@@ -425,7 +436,7 @@ void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cu
 
 void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st) {
     const int nBlocks = nG * 8;
-    pipe_segscan_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(P, B, nBlocks);
+    if (nBlocks > 0) pipe_segscan_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(P, B, nBlocks);
     pipe_blockscan_kernel<<<1, 1024, 0, st>>>(B, nBlocks, unitHint);
     MRX_CUDA(cudaGetLastError());
     launch_counter() += 2;
@@ -433,7 +444,7 @@ void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int un
 
 void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st) {
     const int nBlocks = nG * 8;
-    pipe_units_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, nBlocks);
+    if (nBlocks > 0) pipe_units_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, nBlocks);
     launch_counter()++;
     if (nNbr > 0) {
         pipe_fill_kernel<<<(nNbr + 7) / 8, 256, 0, st>>>(P, B, nNbr);
@@ -466,10 +477,18 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
     launch_counter()++;
 }
 
-void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, int nG, cudaStream_t st) {
+void launch_pack_nodes(double *coefs, double *stage, const int *gslots, int first, int count, int ncoef, bool toStage, cudaStream_t st) {
+    if (count <= 0) return;
+    pack_nodes_kernel<<<count, 256, 0, st>>>(coefs, stage, gslots, first, ncoef, toStage ? 1 : 0);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
+                        cudaStream_t st) {
     const int nBlocks = nG * 8;
     if (nBlocks <= 0) return;
-    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, nBlocks);
+    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, nBlocks);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

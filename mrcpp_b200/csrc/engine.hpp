@@ -104,9 +104,15 @@ double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
 void oper_upload(mrx_oper &o);
 
+// comm.cu
+int comm_rank(const mrx_comm *c);
+int comm_world(const mrx_comm *c);
+void comm_allgatherv(const mrx_comm *c, void *base, const size_t *off, const size_t *count, cudaStream_t st);
+void comm_allreduce_sum(const mrx_comm *c, double *buf, size_t n, cudaStream_t st);
+
 // apply.cu
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats);
+                  mrx_apply_stats *stats, const mrx_comm *comm = nullptr);
 void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int dir, mrx_apply_stats *stats);
 
 } // namespace mrx
