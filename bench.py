@@ -14,9 +14,15 @@ synthetic multi-centre Gaussian density (seed 42, centres uniform in [-8,8]^3, b
          (DMMA) rate measured in this run (MEASURED_PEAKS.json has no FP64 entry).
   cpu_baseline  the CPU oracle (OpenMP restatement of the reference) on a bounded sample.
 
-N > 1 (torchrun): one process per GPU; each rank applies the replicated operator to its own density
-(independent objects, no data-path collective) -> weak scaling; time = max over ranks.
+N > 1 (torchrun): one process per GPU; ONE apply is sharded over the ranks: every refinement iteration's
+output-node list is cut into contiguous ranges (one per rank), input tree and operator are replicated,
+component norms and output coefficient blocks are all-gathered over NCCL/NVLink inside the library
+(mrx_apply_sharded). Same workload for every N -> strong scaling; time = max over ranks.
 """
+import os as _os
+if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
+    # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores
+    _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
 import argparse
 import json
 import math
@@ -136,7 +142,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "poisson_apply_output_nodes_per_s", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.cpu_centers, sample=True),
         "fp64_tflops": tuples * 6 * K ** 4 / total / 1e12,
         "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
@@ -152,7 +158,8 @@ def workload_config(args, centers, sample=False):
             "operator": "PoissonOperator(prec)", "mode": "adaptive (maxIter=-1)",
             "l2_policy": "fresh output tree each step; input tree + operator tables exceed nothing: working set per step "
                          "is re-generated (generated input nodes, output coefficients) and an L2 flush buffer (256 MB) is written between steps",
-            "parallelism": "independent densities per GPU (seed 42+rank), operator replicated"}
+            "parallelism": "output-node list of every refinement iteration sharded over the ranks (contiguous ranges), input tree + "
+                           "operator replicated, NCCL all-gather of component norms and output coefficient blocks"}
 
 
 def main():
@@ -203,7 +210,14 @@ def main():
     t0 = time.perf_counter()
     P = mw.PoissonOperator(mra, prec)
     t_oper = time.perf_counter() - t0
-    func = density(mw, args.centers, 42 + rank)
+    func = density(mw, args.centers, 42)  # same density on every rank: the apply is sharded, not the data
+    comm = None
+    if world > 1:
+        def _bcast(b):
+            obj = [b]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        comm = mw.Comm(rank, world, _bcast)
     ft = mw.FunctionTree(mra)
     t0 = time.perf_counter()
     mw.project(prec, ft, func)
@@ -224,7 +238,7 @@ def main():
             ft.drop_device()  # input starts in (pinned) host memory
         out = mw.FunctionTree(mra)
         L.mrx_timer_start()
-        st = mw.apply(prec, out, P, ft)
+        st = mw.apply(prec, out, P, ft, comm=comm)
         if e2e:
             out.sync_host()  # result back in host memory
         ms = L.mrx_timer_stop_ms()
@@ -276,9 +290,11 @@ def main():
         t = torch.tensor([tot_ms, e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_ms, e2e_ms = float(t[0]), float(t[1])
-        c = torch.tensor([nodes, tuples, launches, e2e_nodes], dtype=torch.float64, device="cuda")
+        # output nodes and surviving tuples are whole-job counts already (every rank holds the full topology; the library
+        # sums the tuple counters over ranks); launches and copied bytes add up over ranks
+        c = torch.tensor([launches, h2d, d2h], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        nodes, tuples, launches, e2e_nodes = (int(x) for x in c.tolist())
+        launches, h2d, d2h = (int(x) for x in c.tolist())
         km = torch.tensor([kern_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(km, op=dist.ReduceOp.MAX)
         kern_ms_max = float(km[0])
@@ -289,11 +305,12 @@ def main():
         peak_dmma = L.mrx_bench_dmma_tflops(20000)
         peak_dfma = L.mrx_bench_dfma_tflops(20000)
         flops = tuples * 6.0 * K ** 4
-        achieved = (last.f_applied * 6.0 * K ** 4 * args.steps) / (contract_ms * 1e-3) / 1e12  # rank-0 contraction kernel
+        # rank 0's contraction kernel and the tuples rank 0 contracted
+        achieved = (last.f_applied_rank * 6.0 * K ** 4 * args.steps) / (contract_ms * 1e-3) / 1e12
         line = {
             "metric": "poisson_apply_output_nodes_per_s", "value": nodes / (tot_ms * 1e-3), "unit": "nodes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.centers),
             "fp64_tflops": flops / (tot_ms * 1e-3) / 1e12,
             "fp64_tflops_frac_of_dmma_peak": flops / (tot_ms * 1e-3) / 1e12 / (peak_dmma * world),

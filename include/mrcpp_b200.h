@@ -41,6 +41,7 @@ typedef struct mrx_apply_stats {
     double ms_post;        /* TopDown(+=) and BottomUp transforms + norms                               */
     double ms_download;    /* device->host copy of the result                                           */
     long long kernel_launches; /* CUDA kernels launched by this call                                    */
+    long long f_applied_rank;  /* sharded apply: tuples contracted by THIS rank (f_applied = sum over ranks) */
 } mrx_apply_stats;
 
 /* ---- library / device ------------------------------------------------------------------------ */

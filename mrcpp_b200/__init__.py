@@ -267,6 +267,13 @@ class Comm:
     NCCL id from rank 0 to every rank (e.g. a torch.distributed / mpi4py broadcast of a bytes object)."""
 
     def __init__(self, rank, world, bcast):
+        # the library binds to the NCCL copy already mapped into the process; make sure that is the host framework's
+        # (torch-bundled) one and not an older system copy that torch itself could not live with afterwards
+        try:
+            import torch  # noqa: F401
+            import torch.distributed  # noqa: F401
+        except ImportError:
+            pass
         L = _lib.load()
         buf = C.create_string_buffer(128)
         if rank == 0:

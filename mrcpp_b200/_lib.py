@@ -25,6 +25,7 @@ class ApplyStats(C.Structure):
         ("ms_post", C.c_double),
         ("ms_download", C.c_double),
         ("kernel_launches", C.c_longlong),
+        ("f_applied_rank", C.c_longlong),
     ]
 
     def as_dict(self):

@@ -870,6 +870,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     MRX_CUDA(cudaMemcpyAsync(counters, scr.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
     MRX_CUDA(cudaStreamSynchronize(st));
     S.f_applied = usePipe ? tuplesTotal : (long long)counters[0];
+    S.f_applied_rank = S.f_applied;
     if (world > 1) {
         double h[2] = {(double)S.f_applied, (double)S.gen_nodes};
         scr.normsW.reserve(2, false, st);

@@ -39,10 +39,17 @@ NcclApi &api() {
     static NcclApi a;
     static std::once_flag once;
     std::call_once(once, [] {
+        // 1. the copy the host framework already mapped (two NCCL versions in one process do not mix: the
+        //    second consumer would bind to the first copy by SONAME), 2. $MRX_NCCL_LIB, 3. the system library
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!a.lib) {
+            const char *env = getenv("MRX_NCCL_LIB");
+            if (env && env[0]) a.lib = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+        }
         const char *names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char *n : names) {
-            a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
             if (a.lib) break;
+            a.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         }
         if (!a.lib) MRX_ABORT(std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
         auto sym = [&](const char *s) {

@@ -1,0 +1,79 @@
+"""Host logic of the sharded multi-GPU apply, on CPU: the contiguous work-vector partition
+(mrx_shard_partition) and the exchange protocol built on it, run with world_size 2 over gloo.
+The device part of the same path is covered by tests/test_gpu_sharded.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_partition_properties(libs):
+    mw, _ = libs
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 7, 64, 1000):
+        for world in (1, 2, 3, 8):
+            cost = rng.integers(1, 2000, size=n)
+            b = mw.shard_partition(cost, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n
+            assert all(b[r] <= b[r + 1] for r in range(world))  # contiguous, order preserving, covers everything
+            if n >= 8 * world:
+                loads = [int(cost[b[r]:b[r + 1]].sum()) for r in range(world)]
+                assert max(loads) <= cost.sum() / world + cost.max()  # balanced to within one item
+    # degenerate costs (nodes without any band) still spread by count
+    b = mw.shard_partition(np.ones(10, dtype=np.int64), 2)
+    assert b == [0, 5, 10]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, seed, q):
+    import torch
+    import torch.distributed as dist
+    import mrcpp_b200 as mw
+    from mrcpp_b200 import _lib
+    _lib.init(-1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    cost = rng.integers(1, 500, size=n)            # identical on every rank (replicated topology)
+    truth = np.sqrt(np.arange(n * 8, dtype=np.float64) + 1.0).reshape(n, 8)  # stands for the component norms
+    begin = mw.shard_partition(cost, world)
+    # every rank "computes" only its range, in a work-vector-ordered buffer, then ranges are exchanged root by root
+    normsW = torch.zeros(n, 8, dtype=torch.float64)
+    normsW[begin[rank]:begin[rank + 1]] = torch.from_numpy(truth[begin[rank]:begin[rank + 1]])
+    for r in range(world):
+        seg = normsW[begin[r]:begin[r + 1]]
+        if seg.numel():
+            dist.broadcast(seg, src=r)
+    ok = bool(np.array_equal(normsW.numpy(), truth))
+    # the split decision is a pure function of the exchanged norms -> identical on all ranks
+    split = (normsW[:, 1:].pow(2).sum(1).sqrt() > 20.0).numpy()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, split.tobytes())
+    same = all(g == gathered[0] for g in gathered)
+    q.put((rank, ok, same, begin))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_protocol_gloo_world2(libs):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 257, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and same for _, ok, same, _ in res)
+    assert res[0][3] == res[1][3]
