@@ -910,7 +910,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)
     double tp = now_ms();
     oper.op.clearBandWidths();
-    device_mw_transform(out, MRX_TOP_DOWN, false);
+    device_mw_transform(out, MRX_TOP_DOWN, false, /*norms=*/false); // the BottomUp pass below recomputes every norm
     device_mw_transform(out, MRX_BOTTOM_UP, true);
     out.host.calcSquareNorm();
     inp.host.deleteGenerated();

@@ -98,49 +98,57 @@ void device_calc_norms_all(mrx_tree &t) {
     }
 }
 
-void device_mw_transform(mrx_tree &t, int type, bool overwrite) {
+void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms) {
     require_device("device_mw_transform");
     if (!t.devValid) tree_upload(t);
     Tree<3> &h = t.host;
     cudaStream_t st = stream();
-    // level lists of branch nodes, in the reference's per-depth node-table order
-    std::vector<std::vector<int>> table;
-    h.nodeTableByDepth(table);
-    std::vector<int> flat;
-    std::vector<int> levelOff(table.size() + 1, 0);
-    for (size_t d = 0; d < table.size(); d++) {
-        for (int n : table[d])
-            if (h.isBranch(n) && !h.isGen(h.nodes[n].child0)) {
-                flat.push_back(n);
-                flat.push_back(h.nodes[n].child0);
-            }
-        levelOff[d + 1] = (int)flat.size() / 2;
+    // level lists of branch nodes (counting sort by depth over the slot order; parents of one level are independent,
+    // so their order inside a level is irrelevant)
+    const int n = h.nReal;
+    std::vector<int> levelOff(2, 0);
+    for (int i = 0; i < n; i++) {
+        const auto &nd = h.nodes[i];
+        if (nd.child0 < 0 || nd.child0 >= n) continue; // leaf, or children are generated nodes
+        const int d = nd.scale - h.mra.rootScale;
+        if (d + 2 > (int)levelOff.size()) levelOff.resize(d + 2, 0);
+        levelOff[d + 1]++;
     }
-    if (flat.empty()) {
-        device_calc_norms_all(t);
+    const int nLevels = (int)levelOff.size() - 1;
+    for (int d = 0; d < nLevels; d++) levelOff[d + 1] += levelOff[d];
+    const int nPairs = levelOff[nLevels];
+    if (nPairs == 0) {
+        if (norms) device_calc_norms_all(t);
         return;
+    }
+    std::vector<int> flat((size_t)2 * nPairs), fill(levelOff.begin(), levelOff.end() - 1);
+    for (int i = 0; i < n; i++) {
+        const auto &nd = h.nodes[i];
+        if (nd.child0 < 0 || nd.child0 >= n) continue;
+        const int pos = fill[nd.scale - h.mra.rootScale]++;
+        flat[2 * (size_t)pos] = i;
+        flat[2 * (size_t)pos + 1] = nd.child0;
     }
     DevBuf<int> pairs;
     pairs.reserve(flat.size(), false, st);
     MRX_CUDA(cudaMemcpyAsync(pairs.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
     const double *filt = device_filters(h.k);
     if (type == MRX_TOP_DOWN) {
-        for (size_t d = 0; d < table.size(); d++) {
+        for (int d = 0; d < nLevels; d++) {
             int cnt = levelOff[d + 1] - levelOff[d];
             if (cnt > 0)
                 launch_transform(true, overwrite, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
         }
     } else {
-        for (int d = (int)table.size() - 1; d >= 0; d--) {
+        for (int d = nLevels - 1; d >= 0; d--) {
             int cnt = levelOff[d + 1] - levelOff[d];
             if (cnt > 0)
                 launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
         }
     }
-    MRX_CUDA(cudaStreamSynchronize(st));
     t.devValid = true;
     t.hostCoefsValid = false;
-    device_calc_norms_all(t);
+    if (norms) device_calc_norms_all(t); // synchronises
 }
 
 double device_dot(mrx_tree &bra, mrx_tree &ket) {

@@ -106,6 +106,134 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k = 7 (K = 8): two-scale transform on the FP64 tensor cores. One CTA (4 warps) per parent node.
+// The three filter passes are the same algebra as the three contractions of the operator application
+// (apply_pipeline.cu): pass p contracts dimension p with the 2K x 2K filter, i.e. for output block gt
+//   out_gt = sum_{b} F[2 gbit + b]^T . in_{ft(b)}        (math_utils::apply_filter, math_utils.cpp:175-194)
+// Warp w = (g0, f2) runs passes 0 and 1 register-to-register (D fragment -> B fragment under sigma) for
+// its four input blocks (f0, f1), writes P1(g0, g1, f2) into a padded shared tile, and after one barrier
+// warp w = (g0, g1) contracts z for g2 = 0, 1 out of the tiles. 768 DMMA.8x8x4 per node = 96 K^4 flop.
+constexpr int kT8Si = 18, kT8Sm = 152, kT8Doubles = 8 * kT8Sm; // same padded tile as the apply kernel
+
+template <int MODE> // 0: TopDown (parent 8 blocks -> children scaling, = or +=); 1: BottomUp (children scaling -> parent)
+__global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ coefs, const int *__restrict__ pairs,
+                                                         const double *__restrict__ filters, int overwrite) {
+    extern __shared__ __align__(16) double tiles8[]; // 8 blocks x kT8Doubles
+    constexpr int Kd = 512, ncoef = 8 * Kd;
+    const int parent = pairs[2 * blockIdx.x];
+    const int child0 = pairs[2 * blockIdx.x + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, q = lane & 3;
+    const int sig = (r >> 1) + 4 * (r & 1);
+    const int bo = q + 8 * sig;
+    // filter fragments: F[op][2 gbit + b][t * 8 + j] -> element t = q + 4 s, j = r (A operand of passes 0/1, B operand of pass 2)
+    const double *F = filters + (size_t)((MODE == 1) ? 0 : 1) * 4 * 64;
+    double fa[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        fa[i][0] = F[i * 64 + q * 8 + r];
+        fa[i][1] = F[i * 64 + (q + 4) * 8 + r];
+    }
+    auto in_block = [&](int ft) -> const double * {
+        return (MODE == 0) ? coefs + (size_t)parent * ncoef + (size_t)ft * Kd : coefs + (size_t)(child0 + ft) * ncoef;
+    };
+    {
+        const int g0 = warp & 1, f2 = warp >> 1;
+        // filter pair of pass 0 for this warp's g0 (selected once: keeps the fragment table in registers)
+        double fg[2][2];
+#pragma unroll
+        for (int f0 = 0; f0 < 2; f0++) {
+            fg[f0][0] = g0 ? fa[2 + f0][0] : fa[f0][0];
+            fg[f0][1] = g0 ? fa[2 + f0][1] : fa[f0][1];
+        }
+        double p0[2][8][2];
+#pragma unroll
+        for (int f1 = 0; f1 < 2; f1++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) p0[f1][j][0] = p0[f1][j][1] = 0.0;
+#pragma unroll
+            for (int f0 = 0; f0 < 2; f0++) {
+                const double *blk = in_block(f0 | (f1 << 1) | (f2 << 2));
+                double bf[8][2];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    bf[j][0] = blk[bo + 64 * j];
+                    bf[j][1] = blk[bo + 4 + 64 * j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    dmma884(p0[f1][j][0], p0[f1][j][1], fg[f0][0], bf[j][0]);
+                    dmma884(p0[f1][j][0], p0[f1][j][1], fg[f0][1], bf[j][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g1 = 0; g1 < 2; g1++) {
+            double *T = tiles8 + (g0 | (g1 << 1) | (f2 << 2)) * kT8Doubles;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int f1 = 0; f1 < 2; f1++) {
+                    dmma884(d0, d1, fa[2 * g1 + f1][0], p0[f1][j][0]);
+                    dmma884(d0, d1, fa[2 * g1 + f1][1], p0[f1][j][1]);
+                }
+                *reinterpret_cast<double2 *>(T + 2 * q + kT8Si * j + kT8Sm * r) = make_double2(d0, d1);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int g01 = warp; // (g0, g1)
+#pragma unroll
+        for (int g2 = 0; g2 < 2; g2++) {
+            double acc[8][2];
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+            for (int f2 = 0; f2 < 2; f2++) {
+                const double *T = tiles8 + (g01 | (f2 << 2)) * kT8Doubles;
+                const double b0 = fa[2 * g2 + f2][0], b1 = fa[2 * g2 + f2][1];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const double2 x0 = *reinterpret_cast<const double2 *>(T + 2 * v + kT8Si * q + kT8Sm * r);
+                    const double2 x1 = *reinterpret_cast<const double2 *>(T + 2 * v + kT8Si * (q + 4) + kT8Sm * r);
+                    dmma884(acc[2 * v][0], acc[2 * v][1], x0.x, b0);
+                    dmma884(acc[2 * v][0], acc[2 * v][1], x1.x, b1);
+                    dmma884(acc[2 * v + 1][0], acc[2 * v + 1][1], x0.y, b0);
+                    dmma884(acc[2 * v + 1][0], acc[2 * v + 1][1], x1.y, b1);
+                }
+            }
+            const int gt = g01 | (g2 << 2);
+            double *dst = ((MODE == 0) ? coefs + (size_t)(child0 + gt) * ncoef : coefs + (size_t)parent * ncoef + (size_t)gt * Kd) +
+                          8 * r + 64 * (2 * q);
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                double2 lo = make_double2(acc[2 * v][0], acc[2 * v + 1][0]);
+                double2 hi = make_double2(acc[2 * v][1], acc[2 * v + 1][1]);
+                if (MODE == 0 && !overwrite) {
+                    const double2 a = *reinterpret_cast<const double2 *>(dst + 2 * v);
+                    const double2 b = *reinterpret_cast<const double2 *>(dst + 64 + 2 * v);
+                    lo.x += a.x;
+                    lo.y += a.y;
+                    hi.x += b.x;
+                    hi.y += b.y;
+                }
+                *reinterpret_cast<double2 *>(dst + 2 * v) = lo;
+                *reinterpret_cast<double2 *>(dst + 64 + 2 * v) = hi;
+            }
+        }
+    }
+    if (MODE == 0 && overwrite) {
+        // giveChildrenCoefs(overwrite=true) zeroes the children first (MWNode.cpp:317-319)
+        for (int o = threadIdx.x; o < 8 * 7 * Kd / 2; o += 128) {
+            const int c = o / (7 * Kd / 2), rem = o - c * (7 * Kd / 2);
+            reinterpret_cast<double2 *>(coefs + (size_t)(child0 + c) * ncoef + Kd)[rem] = make_double2(0.0, 0.0);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) norms_kernel(const double *__restrict__ coefs, double *__restrict__ norms,
                                                     const int *__restrict__ slots, int Kd) {
     int node = slots ? slots[blockIdx.x] : blockIdx.x;
@@ -188,6 +316,20 @@ void launch_norms(const double *coefs, double *norms, const int *slots, int n, i
 void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
                       cudaStream_t st) {
     if (cnt <= 0) return;
+    if (K == 8) {
+        constexpr size_t bytes8 = (size_t)8 * kT8Doubles * sizeof(double);
+        static bool conf = false;
+        if (!conf) {
+            MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
+            MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
+            conf = true;
+        }
+        if (down) transform8_kernel<0><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, overwrite ? 1 : 0);
+        else transform8_kernel<1><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, 1);
+        MRX_CUDA(cudaGetLastError());
+        launch_counter()++;
+        return;
+    }
     int padOn;
     size_t bytes = transform_smem(K, padOn);
     if (down) {

@@ -98,7 +98,7 @@ long long &launch_counter();
 void tree_upload(mrx_tree &t);
 void tree_download(mrx_tree &t);
 void tree_drop_device(mrx_tree &t);
-void device_mw_transform(mrx_tree &t, int type, bool overwrite); // whole-tree transform + norms
+void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = true); // whole-tree transform (+ norms of every node)
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
 double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
