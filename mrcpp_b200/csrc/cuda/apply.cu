@@ -239,11 +239,11 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
     const char *legacy = getenv("MRX_LEGACY");
-    const bool usePipe = (out.host.K == 8) && !deriv && !(legacy && legacy[0] == '1');
+    const bool usePipe = pipe_supports_order(out.host.K) && !deriv && !(legacy && legacy[0] == '1');
     const int world = comm_world(comm), rank = comm_rank(comm);
     const char *uEnv = getenv("MRX_UNIT_TUPLES");
     const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
-    if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the k = 7 convolution pipeline only");
+    if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11 convolution operators) only");
     std::vector<int> bsf, bwTab;
     band_size_factors(op, DM, bsf, bwTab);
     oper.dev.bsf.reserve(bsf.size(), false, st);
@@ -817,7 +817,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         }
         if (profile)
             std::fprintf(stderr, "[mrx] iter %d nG %d nbr %d cand %lld tuples %lld kernels %.3f ms (contract %.3f ms, %.2f TF/s)\n", iter, nG,
-                         nNbr, nCand, iterTuples, ms, msc, msc > 0 ? iterTuples * 24576.0 / (msc * 1e-3) / 1e12 : 0.0);
+                         nNbr, nCand, iterTuples, ms, msc, msc > 0 ? iterTuples * 6.0 * K * K * K * K / (msc * 1e-3) / 1e12 : 0.0);
         for (int i = 0; i < nG; i++) {
             int n = workVec[i];
             double sq = 0.0;

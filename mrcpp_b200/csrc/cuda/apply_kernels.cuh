@@ -132,6 +132,7 @@ struct PipeBuffers {
     double *partials; // [nUnits][K^3]
     int *queue;       // dynamic unit counter of the contraction kernel
 };
+bool pipe_supports_order(int K); // orders with a work-list contraction kernel (K = k + 1)
 int pipe_contract_warps(); // persistent warps of the contraction kernel on this device
 void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cudaStream_t st);
 void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st);

@@ -379,33 +379,124 @@ __global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ contract, other orders
+// Even K != 8 (k = 3, 5, 9, 11): FP64 FMA path on the same work lists. DMMA tiles are 8 x 8 x 4, so K = 10 / 12 would
+// waste 50 % / 25 % of the (shared) FP64 unit on padding, while the DFMA rate of sm_100a equals the DMMA rate
+// (profiles/r01_dmma_dfma_probe.txt); a register-tiled FMA contraction is the faster choice there.
+// One warp per unit. A stage computes out[r + K^2 c] = sum_t in[K r + t] * op[t + K c] (tensorApplyOperComp,
+// ConvolutionCalculator.cpp:363-379: g = f^T O): lane owns rows r = lane + 32 i, keeps two rows (2 K inputs) in
+// registers and streams the operator block through uniform (broadcast) loads, so one 16-byte operator load feeds
+// four FMAs. Stages 1 and 2 write warp-private shared scratch; stage 3 accumulates into registers that stay live
+// for the whole unit.
+template <int K, int R, bool ACC>
+__device__ __forceinline__ void fma_stage(const double *__restrict__ in, const double *__restrict__ op, double *__restrict__ out, int lane) {
+    constexpr int K2 = K * K;
+#pragma unroll
+    for (int i0 = 0; i0 < R; i0 += 2) {
+        const int r0 = lane + 32 * i0, r1 = r0 + 32;
+        const bool v0 = r0 < K2, v1 = (i0 + 1 < R) && (r1 < K2);
+        double x0[K], x1[K];
+#pragma unroll
+        for (int t = 0; t < K; t += 2) {
+            const double2 a = v0 ? *reinterpret_cast<const double2 *>(in + K * r0 + t) : make_double2(0.0, 0.0);
+            const double2 b = v1 ? *reinterpret_cast<const double2 *>(in + K * r1 + t) : make_double2(0.0, 0.0);
+            x0[t] = a.x;
+            x0[t + 1] = a.y;
+            x1[t] = b.x;
+            x1[t + 1] = b.y;
+        }
+#pragma unroll 2
+        for (int c = 0; c < K; c++) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < K; t += 2) {
+                const double2 w = __ldg(reinterpret_cast<const double2 *>(op + K * c + t));
+                a0 = fma(x0[t], w.x, a0);
+                a1 = fma(x1[t], w.x, a1);
+                a0 = fma(x0[t + 1], w.y, a0);
+                a1 = fma(x1[t + 1], w.y, a1);
+            }
+            if (ACC) {
+                if (v0) out[r0 + K2 * c] += a0;
+                if (v1) out[r1 + K2 * c] += a1;
+            } else {
+                if (v0) out[r0 + K2 * c] = a0;
+                if (v1) out[r1 + K2 * c] = a1;
+            }
+        }
+    }
+}
+
+template <int K> __global__ void __launch_bounds__(256, 1) pipe_contract_fma_kernel(ApplyParams P, PipeBuffers B, int nUnits, int nWarps) {
+    extern __shared__ __align__(16) double scratch[];
+    constexpr int K2 = K * K, Kd = K2 * K, R = (K2 + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= nWarps) return;
+    double *S1 = scratch + (size_t)warp * 3 * Kd;
+    double *S2 = S1 + Kd;
+    double *S3 = S2 + Kd; // accumulators of the unit's output block (lane-private rows: no synchronisation needed)
+    const long long nReal8 = (long long)P.nRealF * 8;
+    const int4 *recs = reinterpret_cast<const int4 *>(B.tuples);
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(B.queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nUnits) break;
+        const UnitDesc ud = B.units[u];
+        for (int e = lane; e < Kd; e += 32) S3[e] = 0.0;
+        __syncwarp();
+        for (int t = 0; t < ud.cnt; t++) {
+            const int4 rec = __ldg(recs + ud.t0 + t);
+            const double *fblk = (rec.x < nReal8) ? P.fReal + (size_t)rec.x * Kd : P.fGen + (size_t)(rec.x - nReal8) * Kd;
+            fma_stage<K, R, false>(fblk, P.mats + (size_t)rec.y * K2, S1, lane);
+            __syncwarp();
+            fma_stage<K, R, false>(S1, P.mats + (size_t)rec.z * K2, S2, lane);
+            __syncwarp();
+            fma_stage<K, R, true>(S2, P.mats + (size_t)rec.w * K2, S3, lane);
+            __syncwarp();
+        }
+        double *pb = B.partials + (size_t)u * Kd;
+        for (int e = lane; e < Kd; e += 32) pb[e] = S3[e];
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ reduce
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const int *__restrict__ gslots, double *__restrict__ gCoefs,
-                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks) {
+                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks, int Kd) {
     const int lane = threadIdx.x & 31;
     const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blk >= nBlocks) return;
     const int u0 = B.blockUnitOff[blk], u1 = B.blockUnitOff[blk + 1];
-    double2 s[8];
+    const int slot = gslots[blk >> 3], gt = blk & 7;
+    double2 *o = reinterpret_cast<double2 *>(gCoefs + ((size_t)slot * 8 + gt) * Kd);
+    double n2 = 0.0;
+    // K is even on this path, so a block is a whole number of 16-byte pairs; 8 pairs per lane and trip
+    for (int base = 0; base < Kd / 2; base += 256) {
+        double2 s[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = make_double2(0.0, 0.0);
-    for (int u = u0; u < u1; u++) { // unit order = tuple order: fixed summation order
-        const double2 *p = reinterpret_cast<const double2 *>(B.partials + (size_t)u * 512);
+        for (int i = 0; i < 8; i++) s[i] = make_double2(0.0, 0.0);
+        for (int u = u0; u < u1; u++) { // unit order = tuple order: fixed summation order
+            const double2 *p = reinterpret_cast<const double2 *>(B.partials + (size_t)u * Kd);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int e = base + i * 32 + lane;
+                if (e < Kd / 2) {
+                    const double2 v = p[e];
+                    s[i].x += v.x;
+                    s[i].y += v.y;
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const double2 v = p[i * 32 + lane];
-            s[i].x += v.x;
-            s[i].y += v.y;
+            const int e = base + i * 32 + lane;
+            if (e < Kd / 2) {
+                o[e] = s[i];
+                n2 = fma(s[i].x, s[i].x, n2);
+                n2 = fma(s[i].y, s[i].y, n2);
+            }
         }
-    }
-    const int slot = gslots[blk >> 3], gt = blk & 7;
-    double2 *o = reinterpret_cast<double2 *>(gCoefs + ((size_t)slot * 8 + gt) * 512);
-    double n2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        o[i * 32 + lane] = s[i];
-        n2 = fma(s[i].x, s[i].x, n2);
-        n2 = fma(s[i].y, s[i].y, n2);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
@@ -468,11 +559,42 @@ int pipe_contract_grid() {
 
 int pipe_contract_warps() { return pipe_contract_grid() * kContractWarps; }
 
+template <int K> void launch_contract_fma(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
+    constexpr int Kd = K * K * K;
+    static int sms = 0, nWarps = 0;
+    static size_t bytes = 0;
+    if (!sms) {
+        int dev = 0;
+        MRX_CUDA(cudaGetDevice(&dev));
+        MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        nWarps = 8;
+        while (nWarps > 1 && (size_t)nWarps * 3 * Kd * sizeof(double) > 220 * 1024) nWarps--;
+        bytes = (size_t)nWarps * 3 * Kd * sizeof(double);
+        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_fma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    const int grid = std::min(sms, (nUnits + nWarps - 1) / nWarps);
+    pipe_contract_fma_kernel<K><<<grid, 256, bytes, st>>>(P, B, nUnits, nWarps);
+}
+
+bool pipe_supports_order(int K) { return K == 4 || K == 6 || K == 8 || K == 10 || K == 12; }
+
 void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
     if (nUnits <= 0) return;
-    const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
     MRX_CUDA(cudaMemsetAsync(B.queue, 0, sizeof(int), st));
-    pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
+    if (P.K == 8) {
+        const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
+        pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
+    } else if (P.K == 4) {
+        launch_contract_fma<4>(P, B, nUnits, st);
+    } else if (P.K == 6) {
+        launch_contract_fma<6>(P, B, nUnits, st);
+    } else if (P.K == 10) {
+        launch_contract_fma<10>(P, B, nUnits, st);
+    } else if (P.K == 12) {
+        launch_contract_fma<12>(P, B, nUnits, st);
+    } else {
+        MRX_ABORT("pipeline contraction: unsupported order");
+    }
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }
@@ -488,7 +610,7 @@ void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *g
                         cudaStream_t st) {
     const int nBlocks = nG * 8;
     if (nBlocks <= 0) return;
-    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, nBlocks);
+    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, nBlocks, P.K * P.K * P.K);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }
