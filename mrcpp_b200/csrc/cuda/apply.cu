@@ -239,7 +239,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
     const char *legacy = getenv("MRX_LEGACY");
-    const bool usePipe = pipe_supports_order(out.host.K) && !deriv && !(legacy && legacy[0] == '1');
+    const bool usePipe = pipe_supports_order(out.host.K) && !(legacy && legacy[0] == '1');
     const int world = comm_world(comm), rank = comm_rank(comm);
     const char *uEnv = getenv("MRX_UNIT_TUPLES");
     const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
@@ -709,6 +709,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         P.gThrs = gThrs;
         P.counters = scr.counters.p;
         P.derivDir = derivDir;
+        P.identIdx = oper.dev.identIdx;
 
         delete scUp;
         tp_upload += now_ms() - tq;

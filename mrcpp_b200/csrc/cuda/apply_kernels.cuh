@@ -54,6 +54,7 @@ struct ApplyParams {
     double gThrs;
     unsigned long long *counters; // [0] tuples applied
     int derivDir;                 // -1 for convolution operators
+    int identIdx;                 // operator block index of the K x K identity (derivative apply: dimensions != derivDir)
 };
 
 void launch_apply(const ApplyParams &P, int nG, cudaStream_t st);

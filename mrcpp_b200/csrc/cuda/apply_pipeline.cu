@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
         if (c < nc) {
             const int term = P.candTerm[e0 + c];
             unsigned long long todo = P.candMask[e0 + c] & fmask;
-            if (todo) {
+            if (P.derivDir >= 0) {
+                pass = todo; // derivative apply has no norm screening (DerivativeCalculator.cpp:211-249)
+            } else if (todo) {
                 const int nbase = P.nodeBase[(size_t)term * P.DM + g.depth];
                 const double4 v0 = *reinterpret_cast<const double4 *>(P.onorms + (size_t)(nbase + d[0]) * 4);
                 const double4 v1 = *reinterpret_cast<const double4 *>(P.onorms + (size_t)(nbase + d[1]) * 4);
@@ -275,6 +277,13 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
                 r.o0 = oi0 + 2 * (gt & 1) + (ft & 1);
                 r.o1 = oi1 + 2 * ((gt >> 1) & 1) + ((ft >> 1) & 1);
                 r.o2 = oi2 + 2 * ((gt >> 2) & 1) + ((ft >> 2) & 1);
+                if (P.derivDir >= 0) {
+                    // DerivativeCalculator::tensorApplyOperComp (:253-275): only dimension derivDir carries an operator
+                    // block, the others are pure index rotations = contraction with the identity (exact in FP64)
+                    if (P.derivDir != 0) r.o0 = P.identIdx;
+                    if (P.derivDir != 1) r.o1 = P.identIdx;
+                    if (P.derivDir != 2) r.o2 = P.identIdx;
+                }
                 *reinterpret_cast<int4 *>(B.tuples + start + __popc(bal & ((1u << lane) - 1u))) =
                     make_int4(r.fblk, r.o0, r.o1, r.o2);
             }

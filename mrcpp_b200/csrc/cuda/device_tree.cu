@@ -210,7 +210,10 @@ void oper_upload(mrx_oper &o) {
         totalNodes += op.terms[i].norms.size() / 4;
     }
     const size_t stride = (size_t)4 * op.K * op.K;
-    std::vector<double> mats(totalNodes * stride), norms(totalNodes * 4);
+    // one extra node at the end: block 0 = K x K identity (used by the derivative apply for the passive dimensions)
+    std::vector<double> mats((totalNodes + 1) * stride, 0.0), norms((totalNodes + 1) * 4, 0.0);
+    for (int i = 0; i < op.K; i++) mats[totalNodes * stride + (size_t)i * op.K + i] = 1.0;
+    o.dev.identIdx = (int)(totalNodes * 4);
     std::vector<int> nodeOff((size_t)M * DM, -1), maxT((size_t)M * DM, 0), nodeBase((size_t)M * DM, -1);
     for (int i = 0; i < M; i++) {
         const OperTerm &t = op.terms[i];

@@ -66,6 +66,7 @@ struct DeviceOper {
     DevBuf<int> bw;        // [M][DM][5]   (per apply: depends on prec)
     DevBuf<int> bsf;       // [M][DM][64]  band size factors (per apply)
     int M = 0, DM = 0;
+    int identIdx = 0; // operator block index of the identity block appended to `mats`
     bool tablesValid = false;
     std::vector<size_t> termNodeBase; // host: first global node index of each term
 };

@@ -171,6 +171,32 @@ def test_helmholtz_apply(gpu):
     assert_same_tree(gg, gc)
 
 
+def test_helmholtz_orbital_k9(gpu):
+    """C4 shape: HelmholtzOperator mu=1 at k=9 on a benzene-like 12-centre orbital (6 centres at radius
+    2.64, 6 at 4.69 bohr, z=0), two independent trees (the 50-tree batch shards by tree)."""
+    mw, orc = gpu
+    prec = 1e-4
+    mra = world(mw, 9)
+    H = mw.HelmholtzOperator(mra, 1.0, prec)
+    for j in range(2):
+        rng = np.random.default_rng(2024 + j)
+        func = mw.GaussExp()
+        for ring, (rad, beta) in enumerate(((2.64, 1.5), (4.69, 0.8))):
+            for a in range(6):
+                ang = math.pi / 3 * a
+                func.append(mw.GaussFunc(beta, float(rng.normal()), (rad * math.cos(ang), rad * math.sin(ang), 0.0)))
+        fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        mw.project(prec, fg, func)
+        orc.project(prec, fc, func)
+        gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        sg = mw.apply(prec, gg, H, fg)
+        sc = orc.apply(prec, gc, H, fc)
+        assert sg.f_applied == sc.fApplied
+        assert_same_tree(gg, gc)
+        gg.rescale(-1.0 / (2.0 * math.pi))  # scf.cpp:108 pattern
+        assert abs(gg.getSquareNorm() - gc.getSquareNorm() / (2.0 * math.pi) ** 2) <= 1e-12 * gg.getSquareNorm()
+
+
 @pytest.mark.parametrize("a,b", [(0.5, 0.5), (0.0, 0.0)])
 def test_abgv_derivative(gpu, a, b):
     """C3: apply(out, ABGVOperator, inp, dir) on the device vs oracle for dir 0,1,2 (fixed, widened grid)."""
