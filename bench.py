@@ -329,12 +329,48 @@ def main():
                        "ms_build_per_step": phases["ms_build"] / args.steps, "ms_post_per_step": phases["ms_post"] / args.steps,
                        "setup_s": {"operator": t_oper, "projection": t_proj}},
         }
+        line["roofline"]["traffic"] = ncu_traffic()
+        line["transforms"] = transforms_roofline(L, ft, K)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, mw, mra, P)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the contraction kernel from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/ncu_summary.py): bytes of the largest captured launch, or None"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def transforms_roofline(L, ft, K):
+    """C2: filter kernels of mwTransform(TopDown) / (BottomUp) over the bench input tree, CUDA events around the
+    level launches only. Algorithmic traffic 128 K^3 B and 96 K^4 flop per parent node: at k=7 that is 6 flop/B, the ridge
+    of the FP64 roofline (37 TFLOP/s / 6.5 TB/s = 5.7 flop/B), so both bounds are quoted."""
+    import ctypes as C
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+    nb = C.c_int(0)
+    for kind, name in ((0, "top_down"), (1, "bottom_up")):
+        L.mrx_bench_mw_transform(ft._h, kind, 2, C.byref(nb))
+        ms = L.mrx_bench_mw_transform(ft._h, kind, 20, C.byref(nb))
+        gbs = nb.value * 128.0 * K ** 3 / (ms * 1e-3) / 1e9
+        out[name] = {"ms_per_pass": ms, "parent_nodes": nb.value, "nodes_per_s": nb.value / (ms * 1e-3), "achieved_gbs": gbs,
+                     "frac_of_hbm_peak": gbs / hbm, "fp64_tflops": nb.value * 96.0 * K ** 4 / (ms * 1e-3) / 1e12}
+    return out
 
 
 def cpu_baseline(args, mw, mra, P):

@@ -93,6 +93,7 @@ SIGNATURES = {
     "mrx_bench_dmma_tflops": (_D, [_I]),
     "mrx_bench_dfma_tflops": (_D, [_I]),
     "mrx_bench_hbm_gbs": (_D, [C.c_longlong, _I]),
+    "mrx_bench_mw_transform": (_D, [_P, _I, _I, _PI]),
 }
 
 _lib = None

@@ -373,6 +373,12 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
     device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats);
     return 0;
 }
+double mrx_bench_mw_transform(mrx_tree *tree, int type, int reps, int *branch_nodes) {
+    require_device("mrx_bench_mw_transform");
+    double ms = 0.0;
+    device_mw_transform(*tree, type, true, true, reps > 0 ? reps : 1, &ms, branch_nodes);
+    return ms;
+}
 int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec, const mrx_comm *comm,
                       mrx_apply_stats *stats) {
     require_device("mrx_apply_sharded");

@@ -27,6 +27,15 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// read-only global load that keeps its program order relative to the (volatile) DMMA statements: used where a batch of
+// loads must be issued BEFORE the math that consumes the first of them (the compiler otherwise sinks plain loads
+// next to their use to save registers, serialising the memory round trips)
+__device__ __forceinline__ double ldg_ordered(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) ----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

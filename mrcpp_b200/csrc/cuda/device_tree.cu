@@ -98,7 +98,7 @@ void device_calc_norms_all(mrx_tree &t) {
     }
 }
 
-void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms) {
+void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms, int timedReps, double *timedMs, int *branchNodes) {
     require_device("device_mw_transform");
     if (!t.devValid) tree_upload(t);
     Tree<3> &h = t.host;
@@ -133,18 +133,36 @@ void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms) {
     pairs.reserve(flat.size(), false, st);
     MRX_CUDA(cudaMemcpyAsync(pairs.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
     const double *filt = device_filters(h.k);
-    if (type == MRX_TOP_DOWN) {
-        for (int d = 0; d < nLevels; d++) {
-            int cnt = levelOff[d + 1] - levelOff[d];
-            if (cnt > 0)
-                launch_transform(true, overwrite, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timedReps > 0) {
+        MRX_CUDA(cudaEventCreate(&e0));
+        MRX_CUDA(cudaEventCreate(&e1));
+        MRX_CUDA(cudaEventRecord(e0, st));
+    }
+    for (int rep = 0; rep < std::max(timedReps, 1); rep++) {
+        if (type == MRX_TOP_DOWN) {
+            for (int d = 0; d < nLevels; d++) {
+                int cnt = levelOff[d + 1] - levelOff[d];
+                if (cnt > 0)
+                    launch_transform(true, overwrite, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
+            }
+        } else {
+            for (int d = nLevels - 1; d >= 0; d--) {
+                int cnt = levelOff[d + 1] - levelOff[d];
+                if (cnt > 0)
+                    launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
+            }
         }
-    } else {
-        for (int d = nLevels - 1; d >= 0; d--) {
-            int cnt = levelOff[d + 1] - levelOff[d];
-            if (cnt > 0)
-                launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st);
-        }
+    }
+    if (timedReps > 0) {
+        MRX_CUDA(cudaEventRecord(e1, st));
+        MRX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MRX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        MRX_CUDA(cudaEventDestroy(e0));
+        MRX_CUDA(cudaEventDestroy(e1));
+        if (timedMs) *timedMs = ms / timedReps;
+        if (branchNodes) *branchNodes = nPairs;
     }
     t.devValid = true;
     t.hostCoefsValid = false;

@@ -119,7 +119,7 @@ constexpr int kT8Si = 18, kT8Sm = 152, kT8Doubles = 8 * kT8Sm; // same padded ti
 template <int MODE> // 0: TopDown (parent 8 blocks -> children scaling, = or +=); 1: BottomUp (children scaling -> parent)
 __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ coefs, const int *__restrict__ pairs,
                                                          const double *__restrict__ filters, int overwrite) {
-    extern __shared__ __align__(16) double tiles8[]; // 8 blocks x kT8Doubles
+    extern __shared__ __align__(128) double tiles8[]; // 8 padded tiles (kT8Doubles each) + the TMA-staged node (8 x 512)
     constexpr int Kd = 512, ncoef = 8 * Kd;
     const int parent = pairs[2 * blockIdx.x];
     const int child0 = pairs[2 * blockIdx.x + 1];
@@ -135,9 +135,26 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
         fa[i][0] = F[i * 64 + q * 8 + r];
         fa[i][1] = F[i * 64 + (q + 4) * 8 + r];
     }
-    auto in_block = [&](int ft) -> const double * {
-        return (MODE == 0) ? coefs + (size_t)parent * ncoef + (size_t)ft * Kd : coefs + (size_t)(child0 + ft) * ncoef;
-    };
+    // ---- the node's 8 source blocks (32 KB) are staged by the TMA engine: one bulk copy for a parent node (contiguous),
+    //      eight 4 KB copies for the scaling blocks of the children; all bytes in flight at once
+    double *inbuf = tiles8 + 8 * kT8Doubles;
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(ncoef * sizeof(double)));
+        if (MODE == 0) {
+            bulk_g2s(inbuf, coefs + (size_t)parent * ncoef, (uint32_t)(ncoef * sizeof(double)), &bar);
+        } else {
+#pragma unroll
+            for (int ft = 0; ft < 8; ft++)
+                bulk_g2s(inbuf + ft * Kd, coefs + (size_t)(child0 + ft) * ncoef, (uint32_t)(Kd * sizeof(double)), &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
     {
         const int g0 = warp & 1, f2 = warp >> 1;
         // filter pair of pass 0 for this warp's g0 (selected once: keeps the fragment table in registers)
@@ -147,6 +164,17 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
             fg[f0][0] = g0 ? fa[2 + f0][0] : fa[f0][0];
             fg[f0][1] = g0 ? fa[2 + f0][1] : fa[f0][1];
         }
+        // source fragments out of the TMA-staged node: f[i0 = q + 4 s, i1 = sigma(r), i2 = j]
+        double bf[4][8][2];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const double *blk = inbuf + ((b & 1) | ((b >> 1) << 1) | (f2 << 2)) * Kd;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                bf[b][j][0] = blk[bo + 64 * j];
+                bf[b][j][1] = blk[bo + 4 + 64 * j];
+            }
+        }
         double p0[2][8][2];
 #pragma unroll
         for (int f1 = 0; f1 < 2; f1++) {
@@ -154,17 +182,10 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
             for (int j = 0; j < 8; j++) p0[f1][j][0] = p0[f1][j][1] = 0.0;
 #pragma unroll
             for (int f0 = 0; f0 < 2; f0++) {
-                const double *blk = in_block(f0 | (f1 << 1) | (f2 << 2));
-                double bf[8][2];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    bf[j][0] = blk[bo + 64 * j];
-                    bf[j][1] = blk[bo + 4 + 64 * j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    dmma884(p0[f1][j][0], p0[f1][j][1], fg[f0][0], bf[j][0]);
-                    dmma884(p0[f1][j][0], p0[f1][j][1], fg[f0][1], bf[j][1]);
+                    dmma884(p0[f1][j][0], p0[f1][j][1], fg[f0][0], bf[f0 | (f1 << 1)][j][0]);
+                    dmma884(p0[f1][j][0], p0[f1][j][1], fg[f0][1], bf[f0 | (f1 << 1)][j][1]);
                 }
             }
         }
@@ -317,7 +338,7 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
                       cudaStream_t st) {
     if (cnt <= 0) return;
     if (K == 8) {
-        constexpr size_t bytes8 = (size_t)8 * kT8Doubles * sizeof(double);
+        constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
         static bool conf = false;
         if (!conf) {
             MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));

@@ -99,7 +99,10 @@ long long &launch_counter();
 void tree_upload(mrx_tree &t);
 void tree_download(mrx_tree &t);
 void tree_drop_device(mrx_tree &t);
-void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = true); // whole-tree transform (+ norms of every node)
+/// whole-tree transform (+ norms of every node). timedReps > 0: the level kernels are run timedReps times between two
+/// CUDA events (measurement of the filter kernels alone; TopDown with overwrite and BottomUp are idempotent)
+void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = true, int timedReps = 0, double *timedMs = nullptr,
+                         int *branchNodes = nullptr);
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
 double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
