@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_
 template <int K, int R, bool ACC>
 __device__ __forceinline__ void fma_stage(const double *__restrict__ in, const double *__restrict__ op, double *__restrict__ out, int lane) {
     constexpr int K2 = K * K;
-#pragma unroll
-    for (int i0 = 0; i0 < R; i0 += 2) {
+#pragma unroll 1
+    for (int i0 = 0; i0 < R; i0 += 2) { // not unrolled: the operator block is re-streamed per row pair instead of pinned in registers
         const int r0 = lane + 32 * i0, r1 = r0 + 32;
         const bool v0 = r0 < K2, v1 = (i0 + 1 < R) && (r1 < K2);
         double x0[K], x1[K];
@@ -414,23 +414,29 @@ __device__ __forceinline__ void fma_stage(const double *__restrict__ in, const d
             x1[t] = b.x;
             x1[t + 1] = b.y;
         }
-#pragma unroll 2
-        for (int c = 0; c < K; c++) {
-            double a0 = 0.0, a1 = 0.0;
+        // K independent accumulator pairs: the operator block streams through uniform 16-byte loads, each feeding 4 FMAs
+        double a0[K], a1[K];
 #pragma unroll
-            for (int t = 0; t < K; t += 2) {
+        for (int c = 0; c < K; c++) a0[c] = a1[c] = 0.0;
+#pragma unroll
+        for (int t = 0; t < K; t += 2) {
+#pragma unroll
+            for (int c = 0; c < K; c++) {
                 const double2 w = __ldg(reinterpret_cast<const double2 *>(op + K * c + t));
-                a0 = fma(x0[t], w.x, a0);
-                a1 = fma(x1[t], w.x, a1);
-                a0 = fma(x0[t + 1], w.y, a0);
-                a1 = fma(x1[t + 1], w.y, a1);
+                a0[c] = fma(x0[t], w.x, a0[c]);
+                a1[c] = fma(x1[t], w.x, a1[c]);
+                a0[c] = fma(x0[t + 1], w.y, a0[c]);
+                a1[c] = fma(x1[t + 1], w.y, a1[c]);
             }
+        }
+#pragma unroll
+        for (int c = 0; c < K; c++) {
             if (ACC) {
-                if (v0) out[r0 + K2 * c] += a0;
-                if (v1) out[r1 + K2 * c] += a1;
+                if (v0) out[r0 + K2 * c] += a0[c];
+                if (v1) out[r1 + K2 * c] += a1[c];
             } else {
-                if (v0) out[r0 + K2 * c] = a0;
-                if (v1) out[r1 + K2 * c] = a1;
+                if (v0) out[r0 + K2 * c] = a0[c];
+                if (v1) out[r1 + K2 * c] = a1[c];
             }
         }
     }
