@@ -298,3 +298,28 @@ def test_golden_fixture(gpu):
     nrm = np.sqrt((gold["g_coefs"] ** 2).sum(axis=1))
     err = np.abs(G["coefs"] - gold["g_coefs"]).max(axis=1)
     assert (err / np.maximum(nrm, 1e-300)).max() < COEF_TOL
+
+
+def test_full_size_coulomb_energy(gpu):
+    """BASELINE.json's full-size workload (k=7, prec 1e-7, 100-centre density of bench.py) through a size-independent
+    property: <f|P f> must equal the analytic pairwise Coulomb energy of the Gaussian expansion
+    (GaussFunc::calcCoulombEnergy, src/functions/GaussFunc.cpp:210-237), and a second apply must reproduce the first
+    bit for bit (fixed summation order)."""
+    mw, orc = gpu
+    prec = 1e-7
+    mra = world(mw, 7)
+    func = gaussians(100, 42, box=8.0, lo=1.0, hi=3.0)
+    P = mw.PoissonOperator(mra, prec)
+    f = mw.FunctionTree(mra)
+    mw.project(prec, f, func)
+    g1, g2 = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    s1 = mw.apply(prec, g1, P, f)
+    s2 = mw.apply(prec, g2, P, f)
+    assert s1.f_applied == s2.f_applied and s1.g_nodes == s2.g_nodes
+    assert g1.getSquareNorm() == g2.getSquareNorm()
+    A, B = g1.to_arrays(), g2.to_arrays()
+    assert np.array_equal(A["transl"], B["transl"]) and np.array_equal(A["coefs"], B["coefs"])
+    ana = sum(a.calc_coulomb_energy(b) for a in func for b in func)
+    en = mw.dot(g1, f)
+    assert abs(en - ana) / ana < 10 * prec
+    assert f.getNNodes() > 40000 and s1.f_applied > 2e7  # really the full-size case
