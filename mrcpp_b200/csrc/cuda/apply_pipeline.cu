@@ -476,6 +476,107 @@ template <int K> __global__ void __launch_bounds__(256, 1) pipe_contract_fma_ker
     }
 }
 
+// ------------------------------------------------------------------------------------------------ contract, other orders (DMMA, padded)
+// The same three contractions on the FP64 tensor cores for K != 8. A stage is the GEMM D[c][col] = sum_t A[c][t] B[t][col]
+// with A = O^T (K x K, rows padded to 8 MT, inner dimension to 4 KS with zeros) and B the K x K^2 view of the source
+// (K^2 columns in NT tiles of 8). Useful fraction of the issued DMMA work: K = 12: 75 %, K = 10: 50 %, K = 6: 50 %.
+// Unlike the FMA variant above the operator costs MT x KS registers per stage instead of K^2 / 2 uniform loads.
+// Stage outputs live in warp-private shared memory as out[col + CP c] (CP = K^2 padded to 8 mod 16 doubles: the 16-byte
+// stores of a quarter warp then hit 8 distinct bank groups); the next stage reads them back as B fragments
+// (t = col % K, row = col / K + K c). The third stage accumulates in registers for the whole unit.
+template <int K> struct PadDims {
+    static constexpr int K2 = K * K, Kd = K2 * K;
+    static constexpr int MT = (K + 7) / 8, KS = (K + 3) / 4, NT = (K2 + 7) / 8;
+    static constexpr int CP = ((K2 + 7) / 16) * 16 + 8; // >= K2, == 8 (mod 16)
+};
+
+template <int K, bool DENSE, bool ACC>
+__device__ __forceinline__ void dmma_stage(const double *__restrict__ in, const double *__restrict__ op, double *__restrict__ out,
+                                           double (&acc)[PadDims<K>::NT][PadDims<K>::MT][2], int rr, int q) {
+    using D = PadDims<K>;
+    // operator fragments: A[c = rr + 8 mt][t = q + 4 s] = op[t + K c]
+    double a[D::MT][D::KS];
+#pragma unroll
+    for (int mt = 0; mt < D::MT; mt++)
+#pragma unroll
+        for (int s = 0; s < D::KS; s++) {
+            const int c = rr + 8 * mt, t = q + 4 * s;
+            a[mt][s] = (c < K && t < K) ? __ldg(op + t + K * c) : 0.0;
+        }
+#pragma unroll
+    for (int n0 = 0; n0 < D::NT; n0++) {
+        const int r = 8 * n0 + rr; // source row = column of the GEMM
+        const int rowAddr = DENSE ? K * r : K * (r % K) + D::CP * (r / K);
+        double b[D::KS];
+#pragma unroll
+        for (int s = 0; s < D::KS; s++) {
+            const int t = q + 4 * s;
+            b[s] = (r < D::K2 && t < K) ? in[rowAddr + t] : 0.0;
+        }
+#pragma unroll
+        for (int mt = 0; mt < D::MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+            if (ACC) {
+                d0 = acc[n0][mt][0];
+                d1 = acc[n0][mt][1];
+            }
+#pragma unroll
+            for (int s = 0; s < D::KS; s++) dmma884(d0, d1, a[mt][s], b[s]);
+            if (ACC) {
+                acc[n0][mt][0] = d0;
+                acc[n0][mt][1] = d1;
+            } else {
+                const int c = rr + 8 * mt, col = 8 * n0 + 2 * q;
+                if (c < K && col < D::K2) *reinterpret_cast<double2 *>(out + col + D::CP * c) = make_double2(d0, d1);
+            }
+        }
+    }
+}
+
+template <int K> __global__ void __launch_bounds__(256, 1) pipe_contract_pad_kernel(ApplyParams P, PipeBuffers B, int nUnits, int nWarps) {
+    using D = PadDims<K>;
+    extern __shared__ __align__(16) double scratch[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= nWarps) return;
+    const int rr = lane >> 2, q = lane & 3;
+    double *S1 = scratch + (size_t)warp * 2 * K * D::CP;
+    double *S2 = S1 + K * D::CP;
+    const long long nReal8 = (long long)P.nRealF * 8;
+    const int4 *recs = reinterpret_cast<const int4 *>(B.tuples);
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(B.queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nUnits) break;
+        const UnitDesc ud = B.units[u];
+        double acc[D::NT][D::MT][2];
+#pragma unroll
+        for (int n0 = 0; n0 < D::NT; n0++)
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) acc[n0][mt][0] = acc[n0][mt][1] = 0.0;
+        for (int t = 0; t < ud.cnt; t++) {
+            const int4 rec = __ldg(recs + ud.t0 + t);
+            const double *fblk = (rec.x < nReal8) ? P.fReal + (size_t)rec.x * D::Kd : P.fGen + (size_t)(rec.x - nReal8) * D::Kd;
+            dmma_stage<K, true, false>(fblk, P.mats + (size_t)rec.y * D::K2, S1, acc, rr, q);
+            __syncwarp();
+            dmma_stage<K, false, false>(S1, P.mats + (size_t)rec.z * D::K2, S2, acc, rr, q);
+            __syncwarp();
+            dmma_stage<K, false, true>(S2, P.mats + (size_t)rec.w * D::K2, nullptr, acc, rr, q);
+            __syncwarp();
+        }
+        // partial block of this unit, dense: element col + K^2 c (col = m0 + K m1, c = m2)
+        double *pb = B.partials + (size_t)u * D::Kd;
+#pragma unroll
+        for (int n0 = 0; n0 < D::NT; n0++)
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) {
+                const int c = rr + 8 * mt, col = 8 * n0 + 2 * q;
+                if (c < K && col < D::K2)
+                    *reinterpret_cast<double2 *>(pb + col + D::K2 * c) = make_double2(acc[n0][mt][0], acc[n0][mt][1]);
+            }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ reduce
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const int *__restrict__ gslots, double *__restrict__ gCoefs,
                                                           double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks, int Kd) {
@@ -591,22 +692,44 @@ template <int K> void launch_contract_fma(const ApplyParams &P, const PipeBuffer
     pipe_contract_fma_kernel<K><<<grid, 256, bytes, st>>>(P, B, nUnits, nWarps);
 }
 
+template <int K> void launch_contract_pad(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
+    using D = PadDims<K>;
+    static int sms = 0, nWarps = 0;
+    static size_t bytes = 0;
+    if (!sms) {
+        int dev = 0;
+        MRX_CUDA(cudaGetDevice(&dev));
+        MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        nWarps = 8;
+        const size_t perWarp = (size_t)2 * K * D::CP * sizeof(double);
+        while (nWarps > 1 && (size_t)nWarps * perWarp > 220 * 1024) nWarps--;
+        bytes = (size_t)nWarps * perWarp;
+        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_pad_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    const int grid = std::min(sms, (nUnits + nWarps - 1) / nWarps);
+    pipe_contract_pad_kernel<K><<<grid, 256, bytes, st>>>(P, B, nUnits, nWarps);
+}
+
 bool pipe_supports_order(int K) { return K == 4 || K == 6 || K == 8 || K == 10 || K == 12; }
 
 void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
     if (nUnits <= 0) return;
     MRX_CUDA(cudaMemsetAsync(B.queue, 0, sizeof(int), st));
+    static const bool useFma = getenv("MRX_FMA") != nullptr; // development switch: FMA instead of padded-DMMA contraction
     if (P.K == 8) {
         const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
         pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
     } else if (P.K == 4) {
         launch_contract_fma<4>(P, B, nUnits, st);
     } else if (P.K == 6) {
-        launch_contract_fma<6>(P, B, nUnits, st);
+        if (useFma) launch_contract_fma<6>(P, B, nUnits, st);
+        else launch_contract_pad<6>(P, B, nUnits, st);
     } else if (P.K == 10) {
-        launch_contract_fma<10>(P, B, nUnits, st);
+        if (useFma) launch_contract_fma<10>(P, B, nUnits, st);
+        else launch_contract_pad<10>(P, B, nUnits, st);
     } else if (P.K == 12) {
-        launch_contract_fma<12>(P, B, nUnits, st);
+        if (useFma) launch_contract_fma<12>(P, B, nUnits, st);
+        else launch_contract_pad<12>(P, B, nUnits, st);
     } else {
         MRX_ABORT("pipeline contraction: unsupported order");
     }
