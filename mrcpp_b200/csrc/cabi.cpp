@@ -256,12 +256,7 @@ int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double
     }
     Tree<3> &h = tree->host;
     if (do_build_grid) build_grid<3>(h, gexp, -1);
-    auto f = [&gexp](const double *r) {
-        double s = 0.0;
-        for (const auto &g : gexp) s += g.evalf(r);
-        return s;
-    };
-    project<3>(prec, h, f, -1, false, /*finalize=*/false);
+    project_gaussians<3>(prec, h, gexp, -1, false, /*finalize=*/false);
     tree->hostCoefsValid = true;
     tree->devValid = false;
     // project.cpp:96-97: out.mwTransform(BottomUp); out.calcSquareNorm() -- on the device

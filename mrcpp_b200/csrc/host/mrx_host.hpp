@@ -247,6 +247,11 @@ template <int D>
 void project(double prec, Tree<D> &out, const std::function<double(const double *)> &f, int maxIter = -1,
              bool absPrec = false, bool finalize = true);
 
+/// same as project() for f = sum of Gaussians, with exact node-level screening of terms that are identically zero
+template <int D>
+void project_gaussians(double prec, Tree<D> &out, const GaussExp<D> &gexp, int maxIter = -1, bool absPrec = false,
+                       bool finalize = true);
+
 // ---------------------------------------------------------------- operators
 /// One separated term: the 2-D non-standard-form operator tree flattened to its [depth][transl] cache
 /// (OperatorTree::setupOperNodeCache, OperatorTree.cpp:200-238).

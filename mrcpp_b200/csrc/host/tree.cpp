@@ -580,6 +580,58 @@ void project(double prec, Tree<D> &out, const std::function<double(const double 
     }
 }
 
+/// project() of a Gaussian expansion with exact node-level screening: a term whose exponent exceeds 746 everywhere
+/// in the node's box evaluates to exactly 0 at every quadrature point (GaussFunc::evalf), so leaving it out of the sum
+/// changes nothing -- except the time: far, narrow Gaussians dominate the unscreened cost.
+template <int D>
+void project_gaussians(double prec, Tree<D> &out, const GaussExp<D> &gexp, int maxIter, bool absPrec, bool finalize) {
+    const Quadrature &q = quadrature(out.K);
+    auto calc = [&](Tree<D> &t, int n) {
+        const int K = t.K, Kd = t.Kd;
+        const double len = std::pow(2.0, -t.nodes[n].scale);
+        std::vector<int> active;
+        active.reserve(gexp.size());
+        for (int g = 0; g < (int)gexp.size(); g++) {
+            double minq2 = 0.0;
+            for (int d = 0; d < D; d++) {
+                const double lb = len * t.nodes[n].l[d], ub = len * (t.nodes[n].l[d] + 1);
+                const double p = gexp[g].pos[d];
+                const double dist = (p < lb) ? lb - p : (p > ub ? p - ub : 0.0);
+                minq2 += gexp[g].alpha * dist * dist;
+            }
+            if (!(minq2 > 747.0)) active.push_back(g); // 747 > 746: conservative against rounding of the box test
+        }
+        double sFac = std::pow(2.0, -(t.nodes[n].scale + 1));
+        double *c = t.coef(n);
+        double r[D];
+        for (int tt = 0; tt < Tree<D>::tdim; tt++) {
+            for (int idx = 0; idx < Kd; idx++) {
+                int rem = idx;
+                for (int d = 0; d < D; d++) {
+                    int j = rem % K;
+                    rem /= K;
+                    int b = (tt >> d) & 1;
+                    r[d] = sFac * (q.roots[j] + 2.0 * static_cast<double>(t.nodes[n].l[d]) + (b ? 1.0 : 0.0));
+                }
+                double s = 0.0;
+                for (int g : active) s += gexp[g].evalf(r);
+                c[(size_t)tt * Kd + idx] = s;
+            }
+        }
+        t.cvTransformBackward(n);
+        t.mwTransformNode(n, Compression);
+        t.nodes[n].flags |= FlagHasCoefs;
+        t.calcNorms(n);
+    };
+    auto split = [&](const Tree<D> &t, int n) { return split_check(t, n, prec, 1.0, absPrec); };
+    build_tree<D>(out, calc, split, maxIter, false, true);
+    if (finalize) {
+        out.mwTransformUpSerial();
+        out.calcSquareNorm();
+    }
+}
+template void project_gaussians<3>(double, Tree<3> &, const GaussExp<3> &, int, bool, bool);
+
 template class Tree<1>;
 template class Tree<2>;
 template class Tree<3>;
