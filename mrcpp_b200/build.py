@@ -68,14 +68,15 @@ def build_lib(force=False, verbose=False):
             f.write(out)
     if force or procs or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-cudart", "static"]
-        subprocess.check_call(cmd)
+        subprocess.check_call(cmd, stdout=sys.stderr)
     return LIB
 
 
 def build_oracle(force=False):
+    # make's chatter goes to stderr: bench.py must print exactly one JSON line on stdout
     if force:
-        subprocess.call(["make", "-C", ORACLE_DIR, "clean"])
-    subprocess.check_call(["make", "-C", ORACLE_DIR])
+        subprocess.call(["make", "-s", "-C", ORACLE_DIR, "clean"], stdout=sys.stderr)
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR], stdout=sys.stderr)
     return ORACLE_LIB
 
 
