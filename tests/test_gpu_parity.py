@@ -134,6 +134,24 @@ def test_poisson_apply_fixed_grid(gpu, k, prec):
     assert_same_tree(gg, gc)
 
 
+@pytest.mark.parametrize("k,prec,max_iter,abs_prec", [(7, 1e-4, 2, False), (7, 1e-4, -1, True), (5, 1e-3, 1, True), (4, 1e-3, -1, False)])
+def test_apply_variants(gpu, k, prec, max_iter, abs_prec):
+    """maxIter-limited refinement (TreeBuilder.cpp:73), absolute precision (tree_utils.cpp:55-57) and an even order
+    (k = 4 -> K = 5 runs the generic one-CTA-per-node kernel with host-side band enumeration)."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(3, 21, box=4.0, lo=1.0, hi=2.0)
+    P = mw.PoissonOperator(mra, prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, func)
+    orc.project(prec, fc, func)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(prec, gg, P, fg, maxIter=max_iter, absPrec=abs_prec)
+    sc = orc.apply(prec, gc, P, fc, maxIter=max_iter, absPrec=abs_prec)
+    assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes and sg.iterations == sc.iters
+    assert_same_tree(gg, gc)
+
+
 def test_multi_center_density(gpu):
     """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
     mw, orc = gpu
