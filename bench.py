@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "poisson_apply_output_nodes_per_s", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.cpu_centers, sample=True),
+        "config": workload_config(args, args.centers),  # the GPU arm's workload; each step here is the bounded sample below
         "fp64_tflops": tuples * 6 * K ** 4 / total / 1e12,
         "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
                          "sample": f"{args.cpu_centers}-centre subset of the workload density, full adaptive apply"},
