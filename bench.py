@@ -220,7 +220,7 @@ def main():
         comm = mw.Comm(rank, world, _bcast)
     ft = mw.FunctionTree(mra)
     t0 = time.perf_counter()
-    mw.project(prec, ft, func)
+    mw.project(prec, ft, func, device=True)  # quadrature, transforms and norms on the GPU; the host keeps the topology
     t_proj = time.perf_counter() - t0
     ft.sync_device()
 

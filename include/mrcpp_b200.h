@@ -85,6 +85,15 @@ int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp);
 int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
                           const double *pos /*[n][3]*/, const int *power /*[n][3] or NULL*/, int build_grid, int finalize);
 
+/* The same build_grid + project with the per-node quadrature on the device:
+ * ProjectionCalculator::calcNode (src/treebuilders/ProjectionCalculator.cpp:34-51: function values at the expanded child
+ * quadrature points, MWNode::cvTransform(Backward), MWNode::mwTransform(Compression), MWNode::calcNorms) runs as CUDA kernels
+ * for every work vector of TreeBuilder::build (TreeBuilder.cpp:38-86); the host keeps the topology and takes the split
+ * decisions (WaveletAdaptor.h:51-54). The tree is born resident in HBM and has no host coefficient storage until it is
+ * downloaded (mrx_tree_to_arrays / mrx_tree_sync_host). */
+int mrx_project_gaussians_device(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
+                                 const double *pos /*[n][3]*/, const int *power /*[n][3] or NULL*/, int build_grid);
+
 /* ---- operators -------------------------------------------------------------------------------- */
 /* PoissonOperator(MRA, prec): src/operators/PoissonOperator.cpp:40-55 */
 mrx_oper *mrx_poisson_create(const mrx_mra *mra, double prec);

@@ -250,9 +250,14 @@ def _gauss_arrays(func):
     return len(funcs), coef, alpha, pos, power
 
 
-def project(prec, out, func, build_grid=True, finalize=True):
-    """build_grid + project of a Gaussian (expansion): src/treebuilders/project.cpp:85-104, grid.cpp:78-123."""
+def project(prec, out, func, build_grid=True, finalize=True, device=False):
+    """build_grid + project of a Gaussian (expansion): src/treebuilders/project.cpp:85-104, grid.cpp:78-123.
+    device=True: the per-node quadrature, cv/mw transforms and norms run on the GPU (mrx_project_gaussians_device)."""
     n, coef, alpha, pos, power = _gauss_arrays(func)
+    if device:
+        _lib.load().mrx_project_gaussians_device(out._h, float(prec), n, _dp(coef), _dp(alpha), _dp(pos), _ip(power),
+                                                 1 if build_grid else 0)
+        return
     _lib.load().mrx_project_gaussians(out._h, float(prec), n, _dp(coef), _dp(alpha), _dp(pos), _ip(power),
                                       1 if build_grid else 0, 1 if finalize else 0)
 

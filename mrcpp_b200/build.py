@@ -18,6 +18,7 @@ SOURCES = [
     "host/operators.cpp",
     "cuda/device_tree.cu",
     "cuda/kernels.cu",
+    "cuda/project.cu",
     "cuda/apply.cu",
     "cuda/apply_kernels.cu",
     "cuda/apply_pipeline.cu",

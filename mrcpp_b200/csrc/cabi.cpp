@@ -267,6 +267,25 @@ int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double
     return 0;
 }
 
+int mrx_project_gaussians_device(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
+                                 const double *pos, const int *power, int do_build_grid) {
+    require_device("mrx_project_gaussians_device");
+    GaussExp<3> gexp(n_gauss);
+    for (int i = 0; i < n_gauss; i++) {
+        gexp[i].coef = coef[i];
+        gexp[i].alpha = alpha[i];
+        for (int d = 0; d < 3; d++) {
+            gexp[i].pos[d] = pos[3 * i + d];
+            gexp[i].power[d] = power ? power[3 * i + d] : 0;
+        }
+    }
+    Tree<3> &h = tree->host;
+    h.allocCoefs = false; // device-resident from the first node on
+    if (do_build_grid) build_grid<3>(h, gexp, -1);
+    device_project_gaussians(*tree, prec, gexp, -1, false);
+    return 0;
+}
+
 // ---- operators
 mrx_oper *mrx_poisson_create(const mrx_mra *mra, double prec) {
     auto *o = new mrx_oper;

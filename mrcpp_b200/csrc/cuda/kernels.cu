@@ -18,7 +18,9 @@ namespace {
 constexpr int kTransformThreads = 256;
 
 // MODE 0: TopDown (parent -> children scaling, = or +=); 1: BottomUp (children scaling -> parent);
-// MODE 2: generated children of an input-tree node (scaling only, separate pool) + their norms.
+// MODE 2: generated children of an input-tree node (scaling only, separate pool) + their norms;
+// MODE 3: in-node compression (MWNode::mwTransform(Compression), MWNode.cpp:557-594): the node's own 8 blocks hold the
+//         scaling blocks of its children (projection, ProjectionCalculator.cpp:34-51) and are replaced by (s, d).
 template <int MODE>
 __global__ void __launch_bounds__(kTransformThreads)
 transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoefs, double *__restrict__ genCoefs,
@@ -35,13 +37,13 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
     const int child0 = pairs[2 * blockIdx.x + 1];
     const int tid = threadIdx.x;
 
-    const int op = (MODE == 1) ? 0 : 1; // Compression : Reconstruction
+    const int op = (MODE == 1 || MODE == 3) ? 0 : 1; // Compression : Reconstruction
     for (int i = tid; i < 4 * K2; i += kTransformThreads) F[i] = filters[(size_t)op * 4 * K2 + i];
 
     for (int o = tid; o < 8 * Kd; o += kTransformThreads) {
         int t = o / Kd, rem = o - t * Kd;
         double v;
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 3) {
             v = coefs[(size_t)parent * ncoef + o];
         } else if (MODE == 1) {
             v = coefs[(size_t)(child0 + t) * ncoef + rem];
@@ -73,7 +75,7 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
                 double *dst = coefs + (size_t)(child0 + gt) * ncoef + rem;
                 if (overwrite) *dst = acc;
                 else *dst += acc;
-            } else if (MODE == 1) {
+            } else if (MODE == 1 || MODE == 3) {
                 coefs[(size_t)parent * ncoef + o] = acc;
             } else {
                 genCoefs[(size_t)(child0 - nReal + gt) * Kd + rem] = acc;
@@ -116,7 +118,7 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
 // warp w = (g0, g1) contracts z for g2 = 0, 1 out of the tiles. 768 DMMA.8x8x4 per node = 96 K^4 flop.
 constexpr int kT8Si = 18, kT8Sm = 152, kT8Doubles = 8 * kT8Sm; // same padded tile as the apply kernel
 
-template <int MODE> // 0: TopDown (parent 8 blocks -> children scaling, = or +=); 1: BottomUp (children scaling -> parent)
+template <int MODE> // 0: TopDown (parent 8 blocks -> children scaling, = or +=); 1: BottomUp (children scaling -> parent); 3: in-node compression
 __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ coefs, const int *__restrict__ pairs,
                                                          const double *__restrict__ filters, int overwrite) {
     extern __shared__ __align__(128) double tiles8[]; // 8 padded tiles (kT8Doubles each) + the TMA-staged node (8 x 512)
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
     const int sig = (r >> 1) + 4 * (r & 1);
     const int bo = q + 8 * sig;
     // filter fragments: F[op][2 gbit + b][t * 8 + j] -> element t = q + 4 s, j = r (A operand of passes 0/1, B operand of pass 2)
-    const double *F = filters + (size_t)((MODE == 1) ? 0 : 1) * 4 * 64;
+    const double *F = filters + (size_t)((MODE == 1 || MODE == 3) ? 0 : 1) * 4 * 64;
     double fa[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, (uint32_t)(ncoef * sizeof(double)));
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 3) {
             bulk_g2s(inbuf, coefs + (size_t)parent * ncoef, (uint32_t)(ncoef * sizeof(double)), &bar);
         } else {
 #pragma unroll
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
 }
 
 __global__ void __launch_bounds__(256) norms_kernel(const double *__restrict__ coefs, double *__restrict__ norms,
-                                                    const int *__restrict__ slots, int Kd) {
+                                                    const int *__restrict__ slots, int Kd, double *__restrict__ normsW) {
     int node = slots ? slots[blockIdx.x] : blockIdx.x;
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double *b = coefs + ((size_t)node * 8 + w) * Kd;
@@ -267,7 +269,10 @@ __global__ void __launch_bounds__(256) norms_kernel(const double *__restrict__ c
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) norms[(size_t)node * 8 + w] = sqrt(s);
+    if (lane == 0) {
+        norms[(size_t)node * 8 + w] = sqrt(s);
+        if (normsW) normsW[(size_t)blockIdx.x * 8 + w] = sqrt(s); // work-vector order for the host bookkeeping
+    }
 }
 
 __global__ void __launch_bounds__(256) dot_kernel(const double *__restrict__ a, const double *__restrict__ b,
@@ -327,9 +332,9 @@ template <int MODE> void set_smem_attr(size_t bytes) {
 
 } // namespace
 
-void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t st) {
+void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t st, double *normsW) {
     if (n <= 0) return;
-    norms_kernel<<<n, 256, 0, st>>>(coefs, norms, slots, Kd);
+    norms_kernel<<<n, 256, 0, st>>>(coefs, norms, slots, Kd, normsW);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }
@@ -360,6 +365,26 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
     } else {
         set_smem_attr<1>(bytes);
         transform_kernel<1><<<cnt, kTransformThreads, bytes, st>>>(coefs, nullptr, nullptr, nullptr, 0, pairs, K, padOn, filters, 1);
+    }
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st) {
+    if (cnt <= 0) return;
+    if (K == 8) {
+        constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
+        static bool conf = false;
+        if (!conf) {
+            MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
+            conf = true;
+        }
+        transform8_kernel<3><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, 1);
+    } else {
+        int padOn;
+        size_t bytes = transform_smem(K, padOn);
+        set_smem_attr<3>(bytes);
+        transform_kernel<3><<<cnt, kTransformThreads, bytes, st>>>(coefs, nullptr, nullptr, nullptr, 0, pairs, K, padOn, filters, 1);
     }
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;

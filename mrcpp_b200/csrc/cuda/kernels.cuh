@@ -8,13 +8,27 @@ namespace mrx {
 
 const double *device_filters(int k);
 
-/// component norms: norms[node*8 + c] = ||block c|| for node = slots ? slots[i] : i, i < n
-void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t st);
+/// component norms: norms[node*8 + c] = ||block c|| for node = slots ? slots[i] : i, i < n; normsW (optional): the same
+/// values in list order, normsW[i*8 + c]
+void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t st, double *normsW = nullptr);
 
 /// one level of the two-scale transform. pairs = (parent slot, child0 slot) x cnt.
 /// down: children.scaling (=|+=) reconstruct(parent 8 blocks); up: parent 8 blocks = compress(children.scaling)
 void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
                       cudaStream_t st);
+
+/// in-node compression MWNode::mwTransform(Compression) of the nodes pairs[2 i] (pairs[2 i + 1] unused)
+void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st);
+
+/// ProjectionCalculator::calcNode for a Gaussian expansion (project.cu): function values at the expanded child quadrature
+/// points of every work node, scaled to scaling coefficients (cvTransform Backward); nodeInfo = (scale, lx, ly, lz)
+struct GaussTable {
+    const double *coef, *alpha, *pos; // [n], [n], [n][3]
+    const int *power;                 // [n][3]
+    int n;
+};
+void launch_project_eval(double *coefs, const int *slots, const int4 *nodeInfo, int cnt, int K, const GaussTable &g, const double *roots,
+                         const double *sqrtw, cudaStream_t st);
 
 /// generated children of input-tree nodes (FunctionNode::genChildren + giveChildrenCoefs):
 /// items = (parent slot, child0 slot) in the unified slot space (slot >= nReal -> generated pool)

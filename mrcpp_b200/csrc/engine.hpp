@@ -108,6 +108,9 @@ double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
 void oper_upload(mrx_oper &o);
 
+// project.cu
+void device_project_gaussians(mrx_tree &t, double prec, const GaussExp<3> &gexp, int maxIter, bool absPrec);
+
 // comm.cu
 int comm_rank(const mrx_comm *c);
 int comm_world(const mrx_comm *c);

@@ -533,7 +533,65 @@ template <int D> static void default_calc(Tree<D> &t, int n) {
     t.sqn[n] = -1.0;
 }
 
+/// build_grid for one Gaussian on a tree without coefficients, without touching the nodes the Gaussian cannot split:
+/// the first work vector of TreeBuilder::build is the end-node table (DFS, Hilbert order); AnalyticAdaptor::splitNode is
+/// false for a node outside the 5-sigma box or at/after the visible scale, and then false for all its descendants as well,
+/// so a DFS pruned by those two tests visits the splitting end nodes in the same relative order. Same node set, same
+/// creation order as the generic loop, O(nodes near the Gaussian) instead of O(all end nodes) per term.
+template <int D> static void build_grid_pruned(Tree<D> &t, const GaussFunc<D> &f) {
+    const int maxScale = t.mra.maxScale();
+    std::vector<int> workVec;
+    std::vector<std::pair<int, int>> stack;
+    auto reachable = [&](int n) {
+        if (f.isVisibleAtScale(t.nodes[n].scale, t.K)) return false;
+        double lb[D], ub[D];
+        t.lowerBounds(n, lb);
+        t.upperBounds(n, ub);
+        return !f.isZeroOnInterval(lb, ub);
+    };
+    for (int r = 0; r < t.nRoots; r++) {
+        if (!reachable(r)) continue;
+        stack.push_back({r, 0});
+        while (!stack.empty()) {
+            auto &top = stack.back();
+            const int n = top.first;
+            if (!t.isBranch(n)) {
+                workVec.push_back(n); // end node that AnalyticAdaptor would split
+                stack.pop_back();
+                continue;
+            }
+            if (top.second < Tree<D>::tdim) {
+                const int h = top.second++;
+                const int c = t.nodes[n].child0 + hilbert_z_index(D, t.nodes[n].hpath, h);
+                if (reachable(c)) stack.push_back({c, 0});
+            } else {
+                stack.pop_back();
+            }
+        }
+    }
+    while (!workVec.empty()) {
+        std::vector<int> newVec;
+        for (int n : workVec) {
+            if (t.isBranch(n)) continue;
+            if (t.nodes[n].scale + 2 > maxScale) continue;
+            if (analytic_split(t, n, f)) {
+                const int c0 = t.createChildren(n, false);
+                for (int c = 0; c < Tree<D>::tdim; c++) newVec.push_back(c0 + c);
+            }
+        }
+        workVec.swap(newVec);
+    }
+    t.squareNorm = -1.0;
+}
+
 template <int D> void build_grid(Tree<D> &out, const GaussFunc<D> &f, int maxIter) {
+    bool fresh = maxIter < 0 && !getenv("MRX_GRID_GENERIC"); // debug switch: force the generic TreeBuilder loop
+    for (int r = 0; r < out.nRoots && fresh; r++)
+        if (out.nodes[r].flags & FlagHasCoefs) fresh = false;
+    if (fresh) {
+        build_grid_pruned(out, f);
+        return;
+    }
     build_tree<D>(
         out, [](Tree<D> &t, int n) { default_calc(t, n); },
         [&f](const Tree<D> &t, int n) { return analytic_split(t, n, f); }, maxIter, false, false);

@@ -67,6 +67,28 @@ def test_bottom_up_and_norms(gpu, k):
     assert abs(a.getSquareNorm() - b.getSquareNorm()) <= 1e-13 * b.getSquareNorm()
 
 
+@pytest.mark.parametrize("k,n,prec", [(5, 3, 1e-4), (7, 6, 1e-5), (9, 2, 1e-4)])
+def test_device_projection(gpu, k, n, prec):
+    """project with the quadrature, cvTransform, in-node compression and norms on the DEVICE vs the oracle
+    projection: same node set; coefficients within 1e-12 of the node norm (device exp() and glibc exp() differ by <= 1 ulp);
+    the projected density integrates to ~1 through its Coulomb/self-overlap invariants (norm equal to the oracle's)."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(n, 23)
+    a, b = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, a, func, device=True)
+    orc.project(prec, b, func)
+    assert_same_tree(a, b)
+    assert abs(a.getSquareNorm() - b.getSquareNorm()) <= 1e-13 * b.getSquareNorm()
+    # the device-born tree feeds the apply like any other
+    P = mw.PoissonOperator(mra, prec)
+    ga, gb = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sa = mw.apply(prec, ga, P, a)
+    sb = orc.apply(prec, gb, P, b)
+    assert sa.f_applied == sb.fApplied
+    assert_same_tree(ga, gb)
+
+
 @pytest.mark.parametrize("k", [5, 7])
 def test_top_down_roundtrip(gpu, k):
     """mwTransform(TopDown) then (BottomUp) on the device: TopDown(overwrite) parity vs oracle and the
