@@ -131,17 +131,23 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
 /* ---- multi-GPU: one process per GPU ----------------------------------------------
  * The reference distributes whole trees over MPI ranks (src/utils/parallel.cpp) and runs each apply inside
  * one rank with OpenMP (TreeCalculator.h:39-50). Here ONE apply is sharded: every refinement iteration's
- * work vector is cut into contiguous ranges, one per rank (mrx_shard_partition); input tree and operator
- * are replicated; component norms (for TreeBuilder's norm bookkeeping and the split decisions, which every
- * rank then takes identically) and the output coefficient blocks are all-gathered over NCCL, so every
- * rank ends with the complete output tree, bit-identical across ranks. Rank 0 creates the id, the host
- * framework broadcasts its 128 bytes (torch.distributed / MPI_Bcast), every rank calls mrx_comm_create. */
+ * work vector is dealt out cyclically (mrx_shard_cyclic); input tree and operator are replicated. Component
+ * norms (TreeBuilder's norm bookkeeping and the split decisions, which every rank then takes identically) are
+ * all-gathered with NCCL; output coefficient blocks are pushed into the peers' HBM over NVLink by the copy
+ * engines (CUDA IPC mapping of a staging buffer; ncclAllGather if IPC is unavailable) while the next iteration
+ * runs, so every rank ends with the complete output tree, bit-identical across ranks and to the single-GPU
+ * result. Rank 0 creates the id, the host framework broadcasts its 128 bytes (torch.distributed / MPI_Bcast),
+ * every rank calls mrx_comm_create. */
 int mrx_comm_unique_id(char *id128);
 mrx_comm *mrx_comm_create(int rank, int world, const char *id128);
 void mrx_comm_destroy(mrx_comm *comm);
 int mrx_comm_rank(const mrx_comm *comm);
 int mrx_comm_size(const mrx_comm *comm);
 void mrx_shard_partition(const long long *cost, int n, int world, int *begin /*[world+1]*/);
+/* the distribution mrx_apply_sharded uses: item i of an iteration's work vector is computed by rank i % world; exchange
+ * buffers are rank-major with equal, padded segments: item i = row (i % world) * rows + i / world, rows = ceil(n / world) */
+void mrx_shard_cyclic(int n, int world, int rank, int *count, int *rows);
+int mrx_shard_cyclic_row(int i, int n, int world);
 /* mrcpp::apply sharded over the ranks of `comm` (comm == NULL: same as mrx_apply). Collective: every rank
  * calls it with identical arguments. stats->f_applied / gen_nodes are summed over ranks. */
 int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,

@@ -302,6 +302,19 @@ def shard_partition(cost, world):
     return list(begin)
 
 
+def shard_cyclic(n, world, rank):
+    """(count, rows): items of an n-item work vector computed by `rank` under the cyclic distribution of the sharded apply,
+    and the padded items per rank of the rank-major exchange buffers (mrx_shard_cyclic)"""
+    cnt, rows = C.c_int(0), C.c_int(0)
+    _lib.load().mrx_shard_cyclic(int(n), int(world), int(rank), C.byref(cnt), C.byref(rows))
+    return cnt.value, rows.value
+
+
+def shard_cyclic_row(i, n, world):
+    """row of work-vector item i in the rank-major exchange buffers (mrx_shard_cyclic_row)"""
+    return _lib.load().mrx_shard_cyclic_row(int(i), int(n), int(world))
+
+
 def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None, comm=None):
     """mrcpp::apply. ConvolutionOperator form: apply(prec, out, oper, inp, maxIter, absPrec)
     (src/treebuilders/apply.cpp:68-93); derivative form: apply(None, out, D, inp, dir=d) (:379-412).

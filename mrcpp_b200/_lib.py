@@ -77,6 +77,8 @@ SIGNATURES = {
     "mrx_comm_rank": (_I, [_P]),
     "mrx_comm_size": (_I, [_P]),
     "mrx_shard_partition": (None, [C.POINTER(C.c_longlong), _I, _I, _PI]),
+    "mrx_shard_cyclic": (None, [_I, _I, _I, _PI, _PI]),
+    "mrx_shard_cyclic_row": (_I, [_I, _I, _I]),
     "mrx_apply_derivative": (_I, [_P, _P, _P, _I, C.POINTER(ApplyStats)]),
     "mrx_mw_transform": (_I, [_P, _I, _I]),
     "mrx_calc_square_norm": (_D, [_P]),

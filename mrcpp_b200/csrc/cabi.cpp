@@ -183,6 +183,7 @@ void mrx_tree_clear(mrx_tree *tree) {
     tree->devValid = false;
     tree->dev.nNodes = 0;
     tree->dev.nGen = 0;
+    tree->dev.topoNodes = -1;
 }
 long long mrx_tree_bytes(const mrx_tree *tree) { return (long long)tree->host.nReal * tree->host.ncoef * 8; }
 
@@ -239,6 +240,7 @@ int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp) {
     out->hostCoefsValid = true;
     out->devValid = false;
     out->dev.nNodes = 0;
+    out->dev.topoNodes = -1;
     return 0;
 }
 
@@ -259,6 +261,7 @@ int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double
     project_gaussians<3>(prec, h, gexp, -1, false, /*finalize=*/false);
     tree->hostCoefsValid = true;
     tree->devValid = false;
+    tree->dev.topoNodes = -1;
     // project.cpp:96-97: out.mwTransform(BottomUp); out.calcSquareNorm() -- on the device
     if (finalize) {
         mrx_mw_transform(tree, MRX_BOTTOM_UP, 1);
@@ -472,5 +475,6 @@ void mrx_tree_host_modified(mrx_tree *tree) {
     tree->hostCoefsValid = true;
     tree->devValid = false;
     tree->dev.nNodes = 0;
+    tree->dev.topoNodes = -1;
 }
 }

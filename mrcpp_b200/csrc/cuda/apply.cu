@@ -99,9 +99,10 @@ struct Scratch {
     DevBuf<int> pending;
     DevBuf<int> newParents;
     DevBuf<EnumCounters> ecnt;
+    DevBuf<int> chunkOff, pNode;
+    DevBuf<unsigned long long> chunkPacked, chunkScan, tileTotal, tileBase;
     DevBuf<double> normsW; // component norms of the iteration's nodes in work-vector order
-    DevBuf<int> gslotsAll; // sharded apply: slots of the whole work vector
-    DevBuf<double> stage;  // sharded apply: output blocks in work-vector order for the exchange
+    DevBuf<int> gslotsAll[kCommStageBufs]; // sharded apply: slots of the whole work vector, one per staging buffer in flight
 };
 
 /// input-tree topology on the device for the band enumeration: real nodes + generated nodes in one slot space
@@ -141,6 +142,7 @@ struct BandTables {
     DevBuf<OffEntry> d_offs;
     DevBuf<int> d_offStart, d_offCount;
     bool dirty = false;
+    std::vector<int> bsf; // [M][DM][64] band size factors (ConvolutionCalculator::initBandSizes), mirrored in oper.dev.bsf
 
     // integer part of the screening: per-term max width (applyOperComp :283), per-dimension band test per
     // component (applyOperator :311-318, OperatorTree::isOutsideBand), T block only at depth 0 (calcNode :261).
@@ -232,7 +234,7 @@ struct BandTables {
 } // namespace
 
 static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
-                      std::vector<int> workVec, mrx_apply_stats &S, const mrx_comm *comm = nullptr) {
+                      std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm = nullptr) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
@@ -244,11 +246,6 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     const char *uEnv = getenv("MRX_UNIT_TUPLES");
     const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
     if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11 convolution operators) only");
-    std::vector<int> bsf, bwTab;
-    band_size_factors(op, DM, bsf, bwTab);
-    oper.dev.bsf.reserve(bsf.size(), false, st);
-    MRX_CUDA(cudaMemcpyAsync(oper.dev.bsf.p, bsf.data(), sizeof(int) * bsf.size(), cudaMemcpyHostToDevice, st));
-    MRX_CUDA(cudaStreamSynchronize(st));
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -276,6 +273,25 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         oper.bandCache = btp;
     }
     BandTables &bt = *btp;
+    // band size factors depend on the band widths, i.e. on (operator, prec): computed and uploaded once per cache entry
+    if (bt.bsf.empty()) {
+        std::vector<int> bwTab;
+        band_size_factors(op, DM, bt.bsf, bwTab);
+        oper.dev.bsf.reserve(bt.bsf.size(), false, st);
+        MRX_CUDA(cudaMemcpyAsync(oper.dev.bsf.p, bt.bsf.data(), sizeof(int) * bt.bsf.size(), cudaMemcpyHostToDevice, st));
+        // the same factors in separated form: bsf[gt*8+ft] = 64 * prod_d nodes1d[2 gt_d + ft_d] (calcBandSizeFactor :125-139)
+        std::vector<int> sep((size_t)M * DM * 4, 1);
+        for (int i = 0; i < M; i++)
+            for (int depth = 0; depth < DM; depth++)
+                for (int c = 0; c < 4; c++) {
+                    const int w = bwTab[((size_t)i * DM + depth) * 5 + c];
+                    sep[((size_t)i * DM + depth) * 4 + c] = (w < 0) ? 1 : 2 * w + 1;
+                }
+        oper.dev.bw.reserve(sep.size(), false, st);
+        MRX_CUDA(cudaMemcpyAsync(oper.dev.bw.p, sep.data(), sizeof(int) * sep.size(), cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+    }
+    const std::vector<int> &bsf = bt.bsf;
 
     cudaEvent_t ev0, ev1, ev2, ev3;
     MRX_CUDA(cudaEventCreate(&ev0));
@@ -292,28 +308,62 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     std::vector<NbrEntry> nbr;
     std::vector<int> newParents;
     std::vector<double> genBound; // per generated node: norm of its real leaf ancestor (upper bound of its own norm)
-    std::vector<double> fNodeNorm(fRealN);
-    double fMaxNorm = 0.0;
-    for (int n = 0; n < fRealN; n++) {
-        fNodeNorm[n] = std::sqrt(f.sqn[n]);
-        fMaxNorm = std::max(fMaxNorm, fNodeNorm[n]);
-    }
     DevTopo topo;
     int fTotal = fRealN; // real + generated input nodes known to the device
-    if (usePipe) {
+    // pristine topology (child pointers, depths, node norms) of the input tree: cached on the tree, copied device to device
+    // per apply (generated nodes hang new children below real leaves while an apply runs)
+    DeviceTree &fd = inp.dev;
+    if (fd.topoNodes != fRealN) {
         std::vector<int> hChild0(fRealN), hDepth(fRealN);
+        std::vector<double> fNodeNorm(fRealN);
+        double mx = 0.0;
         for (int n = 0; n < fRealN; n++) {
-            hChild0[n] = f.nodes[n].child0;
+            fNodeNorm[n] = std::sqrt(f.sqn[n]);
+            mx = std::max(mx, fNodeNorm[n]);
+            hChild0[n] = (f.nodes[n].child0 >= 0 && f.nodes[n].child0 < fRealN) ? f.nodes[n].child0 : -1;
             hDepth[n] = f.nodes[n].scale - f.mra.rootScale;
         }
-        topo.reserve((size_t)fRealN + 4096, st);
-        MRX_CUDA(cudaMemcpyAsync(topo.child0.p, hChild0.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(topo.depth.p, hDepth.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(topo.bound.p, fNodeNorm.data(), sizeof(double) * fRealN, cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemsetAsync(topo.flag.p, 0, sizeof(int) * topo.flag.cap, st));
+        fd.topoChild0.reserve(fRealN, false, st);
+        fd.topoDepth.reserve(fRealN, false, st);
+        fd.topoBound.reserve(fRealN, false, st);
+        MRX_CUDA(cudaMemcpyAsync(fd.topoChild0.p, hChild0.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(fd.topoDepth.p, hDepth.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(fd.topoBound.p, fNodeNorm.data(), sizeof(double) * fRealN, cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaStreamSynchronize(st));
+        fd.topoNodes = fRealN;
+        fd.topoMaxNorm = mx;
     }
+    const double fMaxNorm = fd.topoMaxNorm;
+    std::vector<double> fNodeNorm; // host enumeration of the legacy (odd K) path only
+    if (!usePipe) {
+        fNodeNorm.resize(fRealN);
+        for (int n = 0; n < fRealN; n++) fNodeNorm[n] = std::sqrt(f.sqn[n]);
+    }
+    if (usePipe) {
+        topo.reserve((size_t)fRealN + 4096, st);
+        MRX_CUDA(cudaMemcpyAsync(topo.child0.p, fd.topoChild0.p, sizeof(int) * fRealN, cudaMemcpyDeviceToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(topo.depth.p, fd.topoDepth.p, sizeof(int) * fRealN, cudaMemcpyDeviceToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(topo.bound.p, fd.topoBound.p, sizeof(double) * fRealN, cudaMemcpyDeviceToDevice, st));
+        MRX_CUDA(cudaMemsetAsync(topo.flag.p, 0, sizeof(int) * topo.flag.cap, st));
+    }
+    // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store
+    struct {
+        bool active = false;
+        int buf = 0, nG = 0, rows = 0;
+    } pend;
+    auto flush_pending = [&]() {
+        if (!pend.active) return;
+        // own push done -> tiny all-reduce: behind it every peer's push is done as well -> unpack
+        MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
+        scr.counters.reserve(4, false, st);
+        comm_allreduce_sum(comm, reinterpret_cast<double *>(scr.counters.p + 2), 1, st);
+        launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)), scr.gslotsAll[pend.buf].p, pend.nG,
+                            world, pend.rows, out.host.ncoef, st);
+        pend.active = false;
+    };
     double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
+    double tg_prep = 0, tg_enum = 0, tg_resolve = 0;
+    int nResolveRounds = 0;
     const bool profile = getenv("MRX_PROFILE") != nullptr;
     const double tLoop = now_ms();
     while (!workVec.empty()) {
@@ -358,8 +408,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             std::array<int, 3> l;
         };
         const int nGH = usePipe ? 0 : nG; // the pipeline enumerates on the device (apply_enum.cu)
-        int wb = 0, we = nG, nL = nG;     // range of the work vector this rank computes
-        std::vector<int> shardBegin;
+        int nL = nG, rowsPerRank = nG;    // items of the work vector this rank computes / padded items per rank
+        std::vector<int> localSlots;
         std::vector<std::vector<Hit>> hits(nGH);
 #pragma omp parallel for schedule(dynamic, 16)
         for (int i = 0; i < nGH; i++) {
@@ -526,30 +576,30 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         }
         if (usePipe) {
             // ---- device enumeration of the operator band + generated input nodes (apply_enum.cu)
-            // sharded apply: this rank owns the contiguous range [wb, we) of the work vector
-            if (world > 1) {
-                std::vector<long long> cost(nG);
-                for (int i = 0; i < nG; i++) {
-                    const int dep = g.nodes[workVec[i]].scale - op.operRoot;
-                    cost[i] = 1 + ((dep >= 0 && dep < DM && bt.built[dep]) ? bt.offCount[dep] : 0);
-                }
-                shardBegin.assign(world + 1, 0);
-                mrx_shard_partition(cost.data(), nG, world, shardBegin.data());
-                wb = shardBegin[rank];
-                we = shardBegin[rank + 1];
-            } else {
-                wb = 0;
-                we = nG;
-            }
-            nL = we - wb;
+            // sharded apply: cyclic distribution of the work vector, rank r computes the items i = r, r + world, ...
+            // (siblings and spatial neighbours cost about the same, so the cyclic cut balances the tuple counts)
+            rowsPerRank = (nG + world - 1) / world;
+            nL = (nG + world - 1 - rank) / world;
             std::vector<int4> gN(std::max(nL, 1));
-            long long nbrCap = 0;
-            for (int i = wb; i < we; i++) {
+            localSlots.resize(std::max(nL, 1));
+            std::vector<int> chunkOff(nL + 1, 0);
+            long long nbrCap = 0, nChunksLL = 0;
+            for (int j = 0; j < nL; j++) {
+                const int i = rank + j * world;
                 const auto &nd = g.nodes[workVec[i]];
                 const int dep = nd.scale - op.operRoot;
-                gN[i - wb] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
-                if (dep >= 0 && dep < DM && bt.built[dep]) nbrCap += bt.offCount[dep];
+                gN[j] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
+                localSlots[j] = workVec[i];
+                chunkOff[j] = (int)nChunksLL;
+                // deeper than every operator tree, or no band at that depth: empty band (:146-151)
+                if (dep >= 0 && dep < DM && bt.built[dep] && bt.info[dep].W >= 0) {
+                    nbrCap += bt.offCount[dep];
+                    nChunksLL += (bt.offCount[dep] + 31) / 32;
+                }
             }
+            chunkOff[nL] = (int)nChunksLL;
+            if (nChunksLL * 32 >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
+            const int nChunks = (int)nChunksLL;
             if (nbrCap >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
             scr.gNodes.reserve(std::max(nL, 1), false, st);
             scr.gslots.reserve(std::max(nL, 1), false, st);
@@ -557,15 +607,29 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scr.nbr.reserve(std::max<long long>(nbrCap, 1), false, st);
             scr.pending.reserve(std::max<long long>(nbrCap, 1), false, st);
             scr.ecnt.reserve(1, false, st);
+            scr.chunkOff.reserve(nL + 1, false, st);
+            scr.pNode.reserve(std::max<size_t>((size_t)nChunks * 32, 1), false, st);
+            scr.chunkPacked.reserve(std::max(nChunks, 1), false, st);
+            scr.chunkScan.reserve(std::max(nChunks, 1), false, st);
+            scr.tileTotal.reserve(nChunks / 2048 + 2, false, st);
+            scr.tileBase.reserve(nChunks / 2048 + 3, false, st);
+            MRX_CUDA(cudaMemcpyAsync(scr.chunkOff.p, chunkOff.data(), sizeof(int) * (nL + 1), cudaMemcpyHostToDevice, st));
             if (nL > 0) {
                 MRX_CUDA(cudaMemcpyAsync(scr.gNodes.p, gN.data(), sizeof(int4) * nL, cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data() + wb, sizeof(int) * nL, cudaMemcpyHostToDevice, st));
+                MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, localSlots.data(), sizeof(int) * nL, cudaMemcpyHostToDevice, st));
             }
             MRX_CUDA(cudaMemsetAsync(scr.ecnt.p, 0, sizeof(EnumCounters), st));
             EnumParams E{};
             E.gNodes = scr.gNodes.p;
             E.gSlots = scr.gslots.p;
             E.nG = nL;
+            E.chunkOff = scr.chunkOff.p;
+            E.nChunks = nChunks;
+            E.pNode = scr.pNode.p;
+            E.chunkPacked = scr.chunkPacked.p;
+            E.chunkScan = scr.chunkScan.p;
+            E.tileTotal = scr.tileTotal.p;
+            E.tileBase = scr.tileBase.p;
             E.depthShift = op.operRoot - f.mra.rootScale;
             E.offStart = bt.d_offStart.p;
             E.offCount = bt.d_offCount.p;
@@ -588,10 +652,14 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             E.nbr = scr.nbr.p;
             E.pending = scr.pending.p;
             E.cnt = scr.ecnt.p;
+            tg_prep += now_ms() - tq;
+            const double tE = now_ms();
             launch_enum(E, st);
             EnumCounters ec;
             MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
             MRX_CUDA(cudaStreamSynchronize(st));
+            tg_enum += now_ms() - tE;
+            const double tR = now_ms();
             nNbr = ec.nNbr;
             nCand = (long long)ec.nCand;
             // generated input nodes, one round per missing level
@@ -602,6 +670,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
                 E.newParents = scr.newParents.p;
                 E.genItems = scr.genItems.p;
                 MRX_CUDA(cudaMemsetAsync(&scr.ecnt.p->nUnresolved, 0, 2 * sizeof(int), st)); // nUnresolved, nNewParents
+                nResolveRounds++;
                 launch_enum_resolve(E, nPending, st);
                 MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
                 MRX_CUDA(cudaStreamSynchronize(st));
@@ -620,6 +689,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
                 S.gen_nodes += 8 * (long long)nNew;
                 inp.dev.nGen = fTotal - fRealN;
             }
+            tg_resolve += now_ms() - tR;
         }
         // ---- generated input nodes: parents in creation order; a parent created this iteration must be
         //      filled before its own children -> waves
@@ -699,6 +769,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         P.onorms = oper.dev.norms.p;
         P.nodeBase = oper.dev.nodeBase.p;
         P.bsf = oper.dev.bsf.p;
+        P.bsfSep = reinterpret_cast<const int4 *>(oper.dev.bw.p);
         P.depthInfo = bt.d_info.p;
         P.candOff = bt.d_candOff.p;
         P.candTerm = bt.d_candTerm.p;
@@ -724,7 +795,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scr.blockCnt.reserve((size_t)nL * 8 + 8, false, st);
             scr.blockTupOff.reserve((size_t)nL * 8 + 9, false, st);
             scr.blockUnitOff.reserve((size_t)nL * 8 + 9, false, st);
-            scr.normsW.reserve((size_t)nG * 8, false, st);
+            scr.normsW.reserve((size_t)world * rowsPerRank * 8 + 8, false, st);
             scr.header.reserve(1, false, st);
             scr.queue.reserve(1, false, st);
             PipeBuffers B{};
@@ -761,28 +832,49 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             launch_pipe_contract(P, B, hdr.nUnits, st);
             MRX_CUDA(cudaEventRecord(ev3, st));
             // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-            launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, scr.normsW.p + (size_t)wb * 8, nL, st);
-            MRX_CUDA(cudaEventRecord(ev1, st));
-            if (world > 1) {
-                // ---- exchange over NVLink: norms of every node (drives the identical split decision on all ranks)
-                //      and the output coefficient blocks (every rank ends with the complete tree)
-                std::vector<size_t> off(world), cnt(world);
-                for (int r = 0; r < world; r++) {
-                    off[r] = (size_t)shardBegin[r] * 8 * sizeof(double);
-                    cnt[r] = (size_t)(shardBegin[r + 1] - shardBegin[r]) * 8 * sizeof(double);
+            double *normsMine = scr.normsW.p + (size_t)rank * rowsPerRank * 8;
+            if (world == 1) {
+                launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
+                MRX_CUDA(cudaEventRecord(ev1, st));
+            } else {
+                // ---- exchange over NVLink. Output blocks: the reduce kernel writes this rank's rows of a rank-major staging
+                //      buffer; copy engines push them into every peer's HBM (CUDA IPC mapping) on a second stream while
+                //      the next iteration already runs, and the whole iteration is unpacked into the node store one
+                //      iteration later. Norms (8 doubles per node, the input of the split decision that every rank takes
+                //      identically) go through one in-place ncclAllGather, which is also the only cross-rank
+                //      synchronisation: a rank enters it only after its previous push has completed, so whoever leaves it
+                //      knows that the previous iteration's rows of all peers have landed.
+                const int b = iter % kCommStageBufs;
+                const size_t rowBytes = (size_t)ncoef * sizeof(double);
+                const size_t segBytes = (size_t)rowsPerRank * rowBytes;
+                if ((size_t)world * segBytes > comm_stage_bytes(comm)) {
+                    flush_pending();
+                    comm_stage_reserve(comm, (size_t)world * segBytes, st);
                 }
-                comm_allgatherv(comm, scr.normsW.p, off.data(), cnt.data(), st);
-                scr.gslotsAll.reserve(nG, false, st);
-                scr.stage.reserve((size_t)nG * ncoef, false, st);
-                MRX_CUDA(cudaMemcpyAsync(scr.gslotsAll.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
-                launch_pack_nodes(out.dev.coefs.p, scr.stage.p, scr.gslotsAll.p, wb, nL, ncoef, true, st);
-                for (int r = 0; r < world; r++) {
-                    off[r] *= (size_t)Kd;
-                    cnt[r] *= (size_t)Kd;
+                const bool push = comm_peer_push_enabled(comm);
+                double *stageB = reinterpret_cast<double *>(comm_stage(comm, b));
+                launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st,
+                                   reinterpret_cast<double *>(comm_stage(comm, b) + (size_t)rank * segBytes));
+                MRX_CUDA(cudaEventRecord(ev1, st));
+                scr.gslotsAll[b].reserve(nG, false, st);
+                MRX_CUDA(cudaMemcpyAsync(scr.gslotsAll[b].p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+                if (push) {
+                    MRX_CUDA(cudaEventRecord(comm_ev_reduced(comm, b), st));
+                    comm_push(comm, b, (size_t)rank * segBytes, (size_t)nL * rowBytes);
+                    if (pend.active) MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
+                    comm_allgather(comm, scr.normsW.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
+                    if (pend.active)
+                        launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)),
+                                            scr.gslotsAll[pend.buf].p, pend.nG, world, pend.rows, ncoef, st);
+                    pend.active = true;
+                    pend.buf = b;
+                    pend.nG = nG;
+                    pend.rows = rowsPerRank;
+                } else {
+                    comm_allgather(comm, scr.normsW.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
+                    comm_allgather(comm, stageB, segBytes, st);
+                    launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, st);
                 }
-                comm_allgatherv(comm, scr.stage.p, off.data(), cnt.data(), st);
-                launch_pack_nodes(out.dev.coefs.p, scr.stage.p, scr.gslotsAll.p, 0, wb, ncoef, false, st);
-                launch_pack_nodes(out.dev.coefs.p, scr.stage.p, scr.gslotsAll.p, we, nG - we, ncoef, false, st);
             }
             iterTuples = (long long)hdr.totalTuples;
             tuplesTotal += iterTuples;
@@ -797,7 +889,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         int lo = 0;
         std::vector<double> range;
         if (usePipe) {
-            range.resize((size_t)nG * 8);
+            range.resize((size_t)world * rowsPerRank * 8);
             MRX_CUDA(cudaMemcpyAsync(range.data(), scr.normsW.p, sizeof(double) * range.size(), cudaMemcpyDeviceToHost, st));
         } else {
             lo = *std::min_element(workVec.begin(), workVec.end());
@@ -823,7 +915,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             int n = workVec[i];
             double sq = 0.0;
             for (int c = 0; c < 8; c++) {
-                double v = usePipe ? range[(size_t)i * 8 + c] : range[(size_t)(n - lo) * 8 + c];
+                // pipeline: rank-major layout of the cyclic distribution (world == 1: plain work-vector order)
+                double v = usePipe ? range[((size_t)(i % world) * rowsPerRank + i / world) * 8 + c] : range[(size_t)(n - lo) * 8 + c];
                 g.cnorm[(size_t)n * 8 + c] = v;
                 sq += v * v;
             }
@@ -845,10 +938,26 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         std::vector<int> newVec;
         if (iter >= maxIter and maxIter >= 0) workVec.clear();
         if (!deriv) {
+            // tree_utils::split_check (tree_utils.cpp:47-65) with the wavelet threshold of a scale computed once per
+            // iteration (same expression, same operation order: the decision is bit-identical)
+            std::vector<double> wThrs(maxScale - g.mra.rootScale + 2, -1.0);
+            const bool precOn = prec > 0.0;
+            double t_norm = 1.0;
+            if (g.squareNorm > 0.0 and not absPrec) t_norm = std::sqrt(g.squareNorm);
+            newVec.reserve(workVec.size());
             for (int n : workVec) {
                 if (g.isBranch(n)) continue;
-                if (g.nodes[n].scale + 2 > maxScale) continue;
-                if (split_check(g, n, prec, 1.0, absPrec)) {
+                const int scale = g.nodes[n].scale;
+                if (scale + 2 > maxScale) continue;
+                if (!precOn) continue;
+                double &thr = wThrs[scale - g.mra.rootScale];
+                if (thr < 0.0) {
+                    const double expo = 0.5 * 1.0 * (scale + 1);
+                    const double scale_fac = std::pow(2.0, -expo);
+                    thr = std::max(2.0 * MachinePrec, prec * t_norm * scale_fac);
+                }
+                const double w_norm = std::sqrt(g.waveletNorm(n));
+                if (w_norm > thr) {
                     int c0 = g.createChildren(n, false);
                     for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
                 }
@@ -858,9 +967,12 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         iter++;
         tp_host += now_ms() - tq;
     }
+    if (world > 1) flush_pending();
     const double tLoopEnd = now_ms();
     if (profile)
         std::fprintf(stderr, "[mrx] run_apply ms: pre-loop %.2f loop %.2f\n", tLoop - tEnter, tLoopEnd - tLoop);
+    if (profile)
+        std::fprintf(stderr, "[mrx] gen phase ms: prep %.2f enum+sync %.2f resolve %.2f (%d rounds)\n", tg_prep, tg_enum, tg_resolve, nResolveRounds);
     if (profile)
         std::fprintf(stderr, "[mrx] host phases ms: tables %.2f enum %.2f phase2 %.2f gen %.2f upload %.2f wait %.2f split %.2f\n", tp_tables,
                      tp_enum, tp_phase2, tp_gen, tp_upload, tp_wait, tp_host);
@@ -905,7 +1017,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     double tb = now_ms();
     std::vector<int> workVec;
     out.host.nodeTable(workVec); // getInitialWorkVector: ALL nodes of `out` (ConvolutionCalculator.cpp:400-405)
-    run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, comm);
+    run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
     S.ms_build = now_ms() - tb;
 
     // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)

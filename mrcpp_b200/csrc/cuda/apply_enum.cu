@@ -5,13 +5,14 @@
 //
 // The reference walks, for every output node, the cube of (2 band_max + 1)^3 translations, fetching (and
 // generating, under locks) the input node at the output node's scale for each. Here:
-//   enum     warp per output node; lanes over the offsets of its depth that at least one (term, gt, ft) can
-//            reach (band tables). Each lane clips to the world, descends the input tree's child pointers
-//            to the deepest existing node on the way to (scale, l), and drops offsets whose largest
-//            operator-norm product times an upper bound of |f| cannot pass the norm screening (the screening
-//            itself is re-done exactly in pipe_screen; this is only a conservative early-out). Survivors
-//            are written in offset order as neighbour entries; entries whose node is still coarser than
-//            the target scale are queued as pending.
+//   probe    lane per (output node, offset of its depth that at least one (term, gt, ft) can reach (band tables)):
+//            clips to the world, descends the input tree's child pointers to the deepest existing node on
+//            the way to (scale, l), and drops offsets whose largest operator-norm product times an upper
+//            bound of |f| cannot pass the norm screening (the screening itself is re-done exactly in
+//            pipe_screen; this is only a conservative early-out).
+//   scan     offsets of the survivors in the neighbour list (node order, offset order) and of their candidates
+//   emit     survivors are written as neighbour entries; entries whose node is still coarser than the
+//            target scale are queued as pending.
 //   resolve  thread per pending entry: continue the descent; a childless node on the way is flagged (once).
 //   create   thread per flagged node: 8 generated children get slots, depth and norm bound; the (parent,
 //            child0) item list feeds transform_kernel<2> which fills their scaling coefficients.
@@ -35,94 +36,191 @@ __device__ __forceinline__ int descend(const int *__restrict__ child0, int node,
     return node;
 }
 
-__global__ void __launch_bounds__(256) enum_kernel(EnumParams E) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= E.nG) return;
-    const int4 gn = E.gNodes[i];
-    const int dep = gn.x;
-    GDesc d;
-    d.slot = E.gSlots[i];
-    d.depth = dep;
-    d.nbrOff = 0;
-    d.nbrCnt = 0;
-    d.partial = -1;
-    if (dep < 0 || dep >= E.DM || E.depthInfo[dep].W < 0) { // deeper than every operator tree: empty band (:146-151)
-        if (lane == 0) E.gdesc[i] = d;
-        return;
+// warp -> (output node j, chunk c of 32 offsets): chunkOff is the prefix of ceil(offCount / 32) over the nodes
+__device__ __forceinline__ int find_node(const int *__restrict__ chunkOff, int nG, int w) {
+    int lo = 0, hi = nG; // invariant: chunkOff[lo] <= w < chunkOff[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunkOff[mid] <= w) lo = mid;
+        else hi = mid;
     }
-    const int o0 = E.offStart[dep], o1 = o0 + E.offCount[dep];
-    const int td = dep + E.depthShift; // depth in the function tree
-    int lo[3], hi[3];
-#pragma unroll
-    for (int x = 0; x < 3; x++) {
-        lo[x] = E.corner[x] * (1 << td);
-        hi[x] = lo[x] + E.nboxes[x] * (1 << td) - 1;
-    }
-    const int *coff = E.candOff + E.depthInfo[dep].cubeOff;
-    const double slack = 1.0 + 1e-9;
+    return lo;
+}
 
-    int nbrBase = 0;
-    unsigned candBase = 0;
-    int total = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        int run = 0;
-        unsigned candRun = 0;
-        for (int base = o0; base < o1; base += 32) {
-            const int oi = base + lane;
-            bool hit = false;
-            int node = 0, nd = 0, code = 0, nc = 0;
-            if (oi < o1) {
-                const OffEntry oe = E.offs[oi];
-                const int lx = gn.y + oe.dx, ly = gn.z + oe.dy, lz = gn.w + oe.dz;
-                const bool inb = lx >= lo[0] && lx <= hi[0] && ly >= lo[1] && ly <= hi[1] && lz >= lo[2] && lz <= hi[2];
-                if (inb && (!E.screenOn || oe.maxO * E.fMaxNorm * slack > E.gThrs)) {
-                    node = ((lx >> td) - E.corner[0]) + E.nboxes[0] * (((ly >> td) - E.corner[1]) + E.nboxes[1] * ((lz >> td) - E.corner[2]));
-                    node = descend(E.fChild0, node, nd, td, lx, ly, lz);
-                    // |f_ft| <= |node| for a real node; a generated node is an orthogonal projection of its real leaf
-                    // ancestor, so the ancestor's norm bounds it
-                    if (!E.screenOn || !(oe.maxO * E.fBound[node] * slack <= E.gThrs)) {
-                        hit = true;
-                        code = oe.code;
-                        nc = coff[code + 1] - coff[code];
-                    }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            // exclusive scan of the candidate counts of the hit lanes
-            int incl = hit ? nc : 0;
+constexpr int kPendingBit = 1 << 30;
+
+// probe: one lane per (output node, reachable offset). Every pointer chase of the iteration is in flight at once (the
+// earlier warp-per-node loop serialised ~offCount / 32 dependent descents per node and was pure latency).
+__global__ void __launch_bounds__(256) enum_probe_kernel(EnumParams E) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= E.nChunks) return;
+    const int j = find_node(E.chunkOff, E.nG, w);
+    const int4 gn = E.gNodes[j];
+    const int dep = gn.x;
+    const int o0 = E.offStart[dep], o1 = o0 + E.offCount[dep];
+    const int oi = o0 + 32 * (w - E.chunkOff[j]) + lane;
+    const int td = dep + E.depthShift; // depth in the function tree
+    bool hit = false;
+    int node = 0, nd = 0, nc = 0;
+    if (oi < o1) {
+        const OffEntry oe = E.offs[oi];
+        const int lx = gn.y + oe.dx, ly = gn.z + oe.dy, lz = gn.w + oe.dz;
+        int lo[3], hi[3];
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += t;
-            }
-            if (pass == 1 && hit) {
-                const int pos = nbrBase + run + __popc(bal & ((1u << lane) - 1u));
-                NbrEntry e;
-                e.fslot = node;
-                e.code = code;
-                e.g = i;
-                e.candBase = (int)(candBase + candRun + (unsigned)(incl - nc));
-                E.nbr[pos] = e;
-                if (nd < td) E.pending[atomicAdd(&E.cnt->nPending, 1)] = pos;
-            }
-            run += __popc(bal);
-            candRun += (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+        for (int x = 0; x < 3; x++) {
+            lo[x] = E.corner[x] * (1 << td);
+            hi[x] = lo[x] + E.nboxes[x] * (1 << td) - 1;
         }
-        if (pass == 0) {
-            total = run;
-            if (lane == 0) {
-                nbrBase = atomicAdd(&E.cnt->nNbr, run);
-                candBase = atomicAdd(&E.cnt->nCand, candRun);
+        const double slack = 1.0 + 1e-9;
+        const bool inb = lx >= lo[0] && lx <= hi[0] && ly >= lo[1] && ly <= hi[1] && lz >= lo[2] && lz <= hi[2];
+        if (inb && (!E.screenOn || oe.maxO * E.fMaxNorm * slack > E.gThrs)) {
+            node = ((lx >> td) - E.corner[0]) + E.nboxes[0] * (((ly >> td) - E.corner[1]) + E.nboxes[1] * ((lz >> td) - E.corner[2]));
+            node = descend(E.fChild0, node, nd, td, lx, ly, lz);
+            // |f_ft| <= |node| for a real node; a generated node is an orthogonal projection of its real leaf
+            // ancestor, so the ancestor's norm bounds it
+            if (!E.screenOn || !(oe.maxO * E.fBound[node] * slack <= E.gThrs)) {
+                hit = true;
+                const int *coff = E.candOff + E.depthInfo[dep].cubeOff;
+                nc = coff[oe.code + 1] - coff[oe.code];
             }
-            nbrBase = __shfl_sync(0xffffffffu, nbrBase, 0);
-            candBase = __shfl_sync(0xffffffffu, candBase, 0);
-            if (total == 0) break;
         }
     }
-    d.nbrOff = nbrBase;
-    d.nbrCnt = total;
-    if (lane == 0) E.gdesc[i] = d;
+    E.pNode[(size_t)w * 32 + lane] = hit ? (node | (nd < td ? kPendingBit : 0)) : -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    int sum = nc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    // low 32 bits: neighbours, high 32 bits: candidates (both < 2^31 per iteration, checked by the host)
+    if (lane == 0) E.chunkPacked[w] = (unsigned long long)__popc(bal) | ((unsigned long long)(unsigned)sum << 32);
+}
+
+// exclusive scans of the per-chunk neighbour and candidate counts (chunk order = node order, offset order: the neighbour
+// list is deterministic). Two levels: CTAs of kScanTile chunks scan locally (coalesced), one CTA scans the tile totals.
+constexpr int kScanTile = 2048; // 256 threads x 8 chunks
+
+__device__ __forceinline__ unsigned long long cta_excl_scan(unsigned long long v, unsigned long long *sm, unsigned long long &total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long s = (lane < nw) ? sm[lane] : 0ull;
+        unsigned long long si = s;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, si, off);
+            if (lane >= off) si += t;
+        }
+        sm[lane] = si - s;
+        if (lane == 31) sm[32] = si;
+    }
+    __syncthreads();
+    const unsigned long long res = sm[warp] + incl - v;
+    total = sm[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(256) enum_scan_tiles_kernel(EnumParams E) {
+    __shared__ unsigned long long sm[33];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * 8;
+    unsigned long long v[8], local = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[i] = (base + i < E.nChunks) ? E.chunkPacked[base + i] : 0ull;
+        local += v[i];
+    }
+    unsigned long long total;
+    unsigned long long run = cta_excl_scan(local, sm, total);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (base + i < E.nChunks) E.chunkScan[base + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == 0) E.tileTotal[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) enum_scan_top_kernel(EnumParams E, int nTiles) {
+    __shared__ unsigned long long sm[33];
+    const int tid = threadIdx.x;
+    const int per = (nTiles + 1023) / 1024;
+    const int b0 = min(tid * per, nTiles), b1 = min(b0 + per, nTiles);
+    unsigned long long local = 0;
+    for (int b = b0; b < b1; b++) local += E.tileTotal[b];
+    unsigned long long total;
+    unsigned long long run = cta_excl_scan(local, sm, total);
+    for (int b = b0; b < b1; b++) {
+        const unsigned long long t = E.tileTotal[b];
+        E.tileBase[b] = run;
+        run += t;
+    }
+    if (tid == 0) {
+        E.tileBase[nTiles] = total;
+        E.cnt->nNbr = (int)(unsigned)total;
+        E.cnt->nCand = (unsigned)(total >> 32);
+    }
+}
+
+__device__ __forceinline__ unsigned long long chunk_offset(const EnumParams &E, int c) {
+    return (c < E.nChunks) ? E.chunkScan[c] + E.tileBase[c / kScanTile] : E.tileBase[(E.nChunks + kScanTile - 1) / kScanTile];
+}
+
+// thread per output node: its slice of the neighbour list
+__global__ void __launch_bounds__(256) enum_desc_kernel(EnumParams E) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= E.nG) return;
+    GDesc d;
+    d.slot = E.gSlots[j];
+    d.depth = E.gNodes[j].x;
+    const int a = (int)(unsigned)chunk_offset(E, E.chunkOff[j]);
+    const int b = (int)(unsigned)chunk_offset(E, E.chunkOff[j + 1]);
+    d.nbrOff = a;
+    d.nbrCnt = b - a;
+    d.partial = -1;
+    E.gdesc[j] = d;
+}
+
+__global__ void __launch_bounds__(256) enum_emit_kernel(EnumParams E) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= E.nChunks) return;
+    const unsigned long long mine = E.chunkPacked[w];
+    if ((unsigned)mine == 0u) return;
+    const unsigned long long base = chunk_offset(E, w);
+    const int j = find_node(E.chunkOff, E.nG, w);
+    const int dep = E.gNodes[j].x;
+    const int oi = E.offStart[dep] + 32 * (w - E.chunkOff[j]) + lane;
+    const int pn = E.pNode[(size_t)w * 32 + lane];
+    const bool hit = pn >= 0;
+    int code = 0, nc = 0;
+    if (hit) {
+        code = E.offs[oi].code;
+        const int *coff = E.candOff + E.depthInfo[dep].cubeOff;
+        nc = coff[code + 1] - coff[code];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    int incl = nc;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (hit) {
+        const int pos = (int)(unsigned)base + __popc(bal & ((1u << lane) - 1u));
+        NbrEntry e;
+        e.fslot = pn & ~kPendingBit;
+        e.code = code;
+        e.g = j;
+        e.candBase = (int)((unsigned)(base >> 32) + (unsigned)(incl - nc));
+        E.nbr[pos] = e;
+        if (pn & kPendingBit) E.pending[atomicAdd(&E.cnt->nPending, 1)] = pos;
+    }
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(EnumParams E, int nPending) {
@@ -169,9 +267,20 @@ __global__ void __launch_bounds__(256) create_kernel(EnumParams E, int nNew, int
 
 void launch_enum(const EnumParams &E, cudaStream_t st) {
     if (E.nG <= 0) return;
-    enum_kernel<<<(E.nG + 7) / 8, 256, 0, st>>>(E);
+    const int nTiles = (E.nChunks + kScanTile - 1) / kScanTile;
+    if (E.nChunks > 0) {
+        enum_probe_kernel<<<(E.nChunks + 7) / 8, 256, 0, st>>>(E);
+        enum_scan_tiles_kernel<<<nTiles, 256, 0, st>>>(E);
+        launch_counter() += 2;
+    }
+    enum_scan_top_kernel<<<1, 1024, 0, st>>>(E, nTiles);
+    enum_desc_kernel<<<(E.nG + 255) / 256, 256, 0, st>>>(E);
+    launch_counter() += 2;
+    if (E.nChunks > 0) {
+        enum_emit_kernel<<<(E.nChunks + 7) / 8, 256, 0, st>>>(E);
+        launch_counter()++;
+    }
     MRX_CUDA(cudaGetLastError());
-    launch_counter()++;
 }
 
 void launch_enum_resolve(const EnumParams &E, int nPending, cudaStream_t st) {

@@ -46,6 +46,7 @@ struct ApplyParams {
     const double *onorms; // 4 per node
     const int *nodeBase;  // [M][DM] node index of translation 0 (= nodeOff + maxTransl), -1 if depth absent
     const int *bsf;       // [M][DM][64]
+    const int4 *bsfSep;   // [M][DM]: 1-D node counts (2 width + 1, or 1) of the components T, C, B, A: bsf = 64 * product over d
     const DepthInfo *depthInfo;         // [DM]
     const int *candOff;                 // prefix arrays, all depths
     const int *candTerm;                // candidate term ids
@@ -78,6 +79,14 @@ struct EnumParams {
     const int4 *gNodes; // [nG] (operator depth, lx, ly, lz) of the work-vector nodes
     const int *gSlots;  // [nG]
     int nG;
+    // lane-per-offset probing: node j owns the chunks (32 offsets each) chunkOff[j] .. chunkOff[j+1]
+    const int *chunkOff; // [nG+1]
+    int nChunks;
+    int *pNode;            // [nChunks*32] probe result: node (| pending bit) or -1
+    unsigned long long *chunkPacked; // [nChunks] surviving offsets (low 32 bits) and their candidates (high 32 bits)
+    unsigned long long *chunkScan;   // [nChunks] exclusive scan inside the chunk's scan tile
+    unsigned long long *tileTotal;   // [nTiles]
+    unsigned long long *tileBase;    // [nTiles+1] exclusive scan of the tile totals
     int depthShift; // function-tree depth = operator depth + depthShift
     const int *offStart, *offCount; // [DM] into offs
     const OffEntry *offs;
@@ -139,10 +148,12 @@ void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cu
 void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st);
 void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st);
 void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st);
-/// gslots / gNormsW point at the first node of the (rank-local) range
+/// gslots / gNormsW: the rank's nodes in local order. stageRows != nullptr: output blocks go to the rank's rows of the
+/// exchange staging buffer (row j = local node j) instead of the node store
 void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
-                        cudaStream_t st);
-/// copy `count` nodes (work-vector indices first..) between the node store and a work-vector-ordered staging buffer
-void launch_pack_nodes(double *coefs, double *stage, const int *gslots, int first, int count, int ncoef, bool toStage, cudaStream_t st);
+                        cudaStream_t st, double *stageRows = nullptr);
+/// sharded apply: rank-major staging buffer (row r * rowsPerRank + j = work-vector item j * world + r) -> node store
+void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
+                         cudaStream_t st);
 
 } // namespace mrx

@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
                 const double n0[4] = {v0.x, v0.y, v0.z, v0.w};
                 const double n1[4] = {v1.x, v1.y, v1.z, v1.w};
                 const double n2[4] = {v2.x, v2.y, v2.z, v2.w};
-                const int *bs = P.bsf + ((size_t)term * P.DM + g.depth) * 64;
+                // band size factor of (gt, ft): 64 * prod_d (nodes of component c_d along d), one 16-byte load per candidate
+                // instead of 64 scattered table reads
+                const int4 s4 = P.bsfSep[(size_t)term * P.DM + g.depth];
+                const int sep[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                 for (int gt = 0; gt < 8; gt++) {
 #pragma unroll
@@ -104,7 +107,9 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
                             oNorm *= n0[2 * (gt & 1) + (ft & 1)];
                             oNorm *= n1[2 * ((gt >> 1) & 1) + ((ft >> 1) & 1)];
                             oNorm *= n2[2 * ((gt >> 2) & 1) + ((ft >> 2) & 1)];
-                            const double fThreshold = bs[b] * fn[ft];
+                            const int bsI = sep[2 * (gt & 1) + (ft & 1)] * sep[2 * ((gt >> 1) & 1) + ((ft >> 1) & 1)] *
+                                            sep[2 * ((gt >> 2) & 1) + ((ft >> 2) & 1)] * 64;
+                            const double fThreshold = bsI * fn[ft];
                             const double upperBound = oNorm * fThreshold;
                             if (upperBound > P.gThrs) pass |= 1ull << b;
                         }
@@ -578,14 +583,17 @@ template <int K> __global__ void __launch_bounds__(256, 1) pipe_contract_pad_ker
 }
 
 // ------------------------------------------------------------------------------------------------ reduce
+// stageRows != nullptr (sharded apply): the block goes to row (blk >> 3) of the rank's segment of the exchange staging buffer
+// instead of the node store; the whole iteration is unpacked into the node store after the peers' rows have arrived
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const int *__restrict__ gslots, double *__restrict__ gCoefs,
-                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks, int Kd) {
+                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks, int Kd,
+                                                          double *__restrict__ stageRows) {
     const int lane = threadIdx.x & 31;
     const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blk >= nBlocks) return;
     const int u0 = B.blockUnitOff[blk], u1 = B.blockUnitOff[blk + 1];
     const int slot = gslots[blk >> 3], gt = blk & 7;
-    double2 *o = reinterpret_cast<double2 *>(gCoefs + ((size_t)slot * 8 + gt) * Kd);
+    double2 *o = reinterpret_cast<double2 *>(stageRows ? stageRows + (size_t)blk * Kd : gCoefs + ((size_t)slot * 8 + gt) * Kd);
     double n2 = 0.0;
     // K is even on this path, so a block is a whole number of 16-byte pairs; 8 pairs per lane and trip
     for (int base = 0; base < Kd / 2; base += 256) {
@@ -623,12 +631,16 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const i
     }
 }
 
-// sharded apply: output blocks of a rank's range packed in work-vector order for the exchange, and back
-__global__ void __launch_bounds__(256) pack_nodes_kernel(const double *__restrict__ coefs, double *__restrict__ stage,
-                                                         const int *__restrict__ gslots, int first, int ncoef, int toStage) {
-    const int i = first + blockIdx.x;
-    const double2 *src = reinterpret_cast<const double2 *>(toStage ? coefs + (size_t)gslots[i] * ncoef : stage + (size_t)i * ncoef);
-    double2 *dst = reinterpret_cast<double2 *>(toStage ? stage + (size_t)i * ncoef : const_cast<double *>(coefs) + (size_t)gslots[i] * ncoef);
+// sharded apply: one iteration's output nodes from the rank-major staging buffer (row r * rowsPerRank + j holds work-vector
+// item i = j * world + r, the cyclic distribution of the work vector) into the node store
+__global__ void __launch_bounds__(256) unpack_nodes_kernel(double *__restrict__ coefs, const double *__restrict__ stage,
+                                                           const int *__restrict__ gslotsAll, int nG, int world, int rowsPerRank,
+                                                           int ncoef) {
+    const int r = blockIdx.x / rowsPerRank, j = blockIdx.x - r * rowsPerRank;
+    const int i = j * world + r;
+    if (i >= nG) return;
+    const double2 *src = reinterpret_cast<const double2 *>(stage + (size_t)blockIdx.x * ncoef);
+    double2 *dst = reinterpret_cast<double2 *>(coefs + (size_t)gslotsAll[i] * ncoef);
     for (int e = threadIdx.x; e < ncoef / 2; e += 256) dst[e] = src[e];
 }
 
@@ -737,18 +749,19 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
     launch_counter()++;
 }
 
-void launch_pack_nodes(double *coefs, double *stage, const int *gslots, int first, int count, int ncoef, bool toStage, cudaStream_t st) {
-    if (count <= 0) return;
-    pack_nodes_kernel<<<count, 256, 0, st>>>(coefs, stage, gslots, first, ncoef, toStage ? 1 : 0);
+void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
+                         cudaStream_t st) {
+    if (nG <= 0) return;
+    unpack_nodes_kernel<<<world * rowsPerRank, 256, 0, st>>>(coefs, stage, gslotsAll, nG, world, rowsPerRank, ncoef);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }
 
 void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
-                        cudaStream_t st) {
+                        cudaStream_t st, double *stageRows) {
     const int nBlocks = nG * 8;
     if (nBlocks <= 0) return;
-    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, nBlocks, P.K * P.K * P.K);
+    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, nBlocks, P.K * P.K * P.K, stageRows);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

@@ -4,8 +4,10 @@
 // else the system one), so the library has no link-time dependency and single-GPU users never touch it.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../engine.hpp"
 #include "common.cuh"
@@ -30,6 +32,7 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -62,6 +65,7 @@ NcclApi &api() {
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
         a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
         a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
         a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
         a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
@@ -80,6 +84,18 @@ void check(int rc, const char *what) {
 struct mrx_comm {
     int rank = 0, world = 1;
     mrx::ncclComm_t comm = nullptr;
+    // ---- peer-memory exchange of output coefficient blocks (NVLink / NVSwitch, copy engines) ----
+    // One cudaMalloc per rank holds kStageBufs staging buffers; its IPC handle is opened by every peer, so a rank PUSHES the
+    // blocks it computed straight into the peers' HBM with DMA copies that use no SM and overlap the next refinement
+    // iteration's kernels. peerBase[r] = base address of rank r's allocation in this process (own rank: local pointer).
+    static constexpr int kStageBufs = 3;
+    char *stageBase = nullptr;
+    size_t stageBytes = 0; // per buffer
+    std::vector<char *> peerBase;
+    bool ipcTried = false, ipcOk = false;
+    cudaStream_t pushStream = nullptr;
+    cudaEvent_t evReduced[kStageBufs] = {nullptr, nullptr, nullptr}, evPushed[kStageBufs] = {nullptr, nullptr, nullptr};
+    char *ipcScratch = nullptr; // device buffer for the handle all-gather
 };
 
 namespace mrx {
@@ -98,6 +114,107 @@ void comm_allgatherv(const mrx_comm *c, void *base, const size_t *off, const siz
     }
     check(a.GroupEnd(), "ncclGroupEnd");
 }
+
+/// in-place all-gather of equal segments: rank r's `bytes` live at base + r * bytes
+void comm_allgather(const mrx_comm *c, void *base, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return;
+    check(api().AllGather(static_cast<char *>(base) + (size_t)c->rank * bytes, base, bytes, kNcclInt8, c->comm, st), "ncclAllGather");
+}
+
+bool comm_peer_push_enabled(const mrx_comm *c) { return c && c->ipcOk; }
+char *comm_stage(const mrx_comm *c, int buf) { return c->stageBase + (size_t)buf * c->stageBytes; }
+size_t comm_stage_bytes(const mrx_comm *c) { return c->stageBytes; }
+
+/// Collective (every rank calls it with the same `bytes`, which all ranks derive from the replicated topology): make the
+/// staging buffers at least `bytes` each and map every peer's allocation. The caller guarantees that no push is in flight
+/// (run_apply flushes the lagging exchange first). Falls back to the NCCL all-gather path if CUDA IPC is unavailable.
+void comm_stage_reserve(mrx_comm *c, size_t bytes, cudaStream_t st) {
+    if (bytes <= c->stageBytes) return;
+    NcclApi &a = api();
+    const int W = c->world;
+    MRX_CUDA(cudaStreamSynchronize(st));
+    if (c->pushStream) MRX_CUDA(cudaStreamSynchronize(c->pushStream));
+    // nobody may still be writing into the buffers that are about to be unmapped
+    if (!c->ipcScratch) MRX_CUDA(cudaMalloc(&c->ipcScratch, (size_t)W * sizeof(cudaIpcMemHandle_t) + 64));
+    MRX_CUDA(cudaMemsetAsync(c->ipcScratch, 0, sizeof(double), st));
+    check(a.AllReduce(c->ipcScratch, c->ipcScratch, 1, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce(barrier)");
+    MRX_CUDA(cudaStreamSynchronize(st));
+    if (c->stageBase) {
+        for (int r = 0; r < W; r++)
+            if (r != c->rank && c->peerBase[r]) cudaIpcCloseMemHandle(c->peerBase[r]);
+        MRX_CUDA(cudaFree(c->stageBase));
+        c->stageBase = nullptr;
+    }
+    // second barrier: every rank has unmapped the old peers before anybody frees/reallocates (cudaFree of memory still
+    // mapped elsewhere is legal but the new allocation must not alias a stale mapping)
+    check(a.AllReduce(c->ipcScratch, c->ipcScratch, 1, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce(barrier)");
+    MRX_CUDA(cudaStreamSynchronize(st));
+    size_t nb = std::max(bytes + bytes / 2, (size_t)64 << 20);
+    nb = (nb + 4095) / 4096 * 4096;
+    MRX_CUDA(cudaMalloc(&c->stageBase, nb * mrx_comm::kStageBufs));
+    c->stageBytes = nb;
+    c->peerBase.assign(W, nullptr);
+    c->peerBase[c->rank] = c->stageBase;
+    if (!c->pushStream) {
+        MRX_CUDA(cudaStreamCreateWithFlags(&c->pushStream, cudaStreamNonBlocking));
+        for (int b = 0; b < mrx_comm::kStageBufs; b++) {
+            MRX_CUDA(cudaEventCreateWithFlags(&c->evReduced[b], cudaEventDisableTiming));
+            MRX_CUDA(cudaEventCreateWithFlags(&c->evPushed[b], cudaEventDisableTiming));
+        }
+    }
+    const bool forceOff = getenv("MRX_NO_IPC") != nullptr;
+    int ok = forceOff ? 0 : 1;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, c->stageBase) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    // handles of all ranks (64 bytes each) through an in-place all-gather on device memory
+    std::vector<cudaIpcMemHandle_t> all(W);
+    MRX_CUDA(cudaMemcpyAsync(c->ipcScratch + (size_t)c->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    check(a.AllGather(c->ipcScratch + (size_t)c->rank * sizeof(mine), c->ipcScratch, sizeof(mine), kNcclInt8, c->comm, st), "ncclAllGather(ipc)");
+    MRX_CUDA(cudaMemcpyAsync(all.data(), c->ipcScratch, sizeof(mine) * W, cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < W && ok; r++) {
+        if (r == c->rank) continue;
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        c->peerBase[r] = static_cast<char *>(p);
+    }
+    // the exchange mode must be the same everywhere: min over ranks
+    double flag = ok ? 1.0 : 0.0;
+    double *dflag = reinterpret_cast<double *>(c->ipcScratch + (size_t)W * sizeof(mine));
+    dflag = reinterpret_cast<double *>(((uintptr_t)dflag + 7) & ~(uintptr_t)7);
+    MRX_CUDA(cudaMemcpyAsync(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+    check(a.AllReduce(dflag, dflag, 1, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce(ipc ok)");
+    MRX_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    c->ipcOk = (flag > W - 0.5);
+    if (!c->ipcOk && !c->ipcTried && c->rank == 0 && !forceOff)
+        std::fprintf(stderr, "[mrx] CUDA IPC peer mapping unavailable: coefficient exchange falls back to ncclAllGather\n");
+    c->ipcTried = true;
+}
+
+/// push `bytes` at offset `off` of staging buffer `buf` into the same place of every peer's buffer (copy engines, push stream);
+/// starts after evReduced[buf] (recorded by the caller on its compute stream), completion = evPushed[buf]
+void comm_push(mrx_comm *c, int buf, size_t off, size_t bytes) {
+    MRX_CUDA(cudaStreamWaitEvent(c->pushStream, c->evReduced[buf], 0));
+    if (bytes > 0) {
+        const char *src = c->stageBase + (size_t)buf * c->stageBytes + off;
+        for (int d = 1; d < c->world; d++) {
+            const int r = (c->rank + d) % c->world; // staggered: at any moment the ranks target distinct peers
+            MRX_CUDA(cudaMemcpyAsync(c->peerBase[r] + (size_t)buf * c->stageBytes + off, src, bytes, cudaMemcpyDeviceToDevice, c->pushStream));
+        }
+    }
+    MRX_CUDA(cudaEventRecord(c->evPushed[buf], c->pushStream));
+}
+cudaEvent_t comm_ev_reduced(const mrx_comm *c, int buf) { return c->evReduced[buf]; }
+cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf) { return c->evPushed[buf]; }
 
 void comm_allreduce_sum(const mrx_comm *c, double *buf, size_t n, cudaStream_t st) {
     check(api().AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce");
@@ -127,12 +244,34 @@ mrx_comm *mrx_comm_create(int rank, int world, const char *id128) {
 
 void mrx_comm_destroy(mrx_comm *c) {
     if (!c) return;
+    if (c->stageBase) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < c->world; r++)
+            if (r != c->rank && r < (int)c->peerBase.size() && c->peerBase[r]) cudaIpcCloseMemHandle(c->peerBase[r]);
+        cudaFree(c->stageBase);
+    }
+    if (c->ipcScratch) cudaFree(c->ipcScratch);
+    if (c->pushStream) cudaStreamDestroy(c->pushStream);
+    for (int b = 0; b < mrx_comm::kStageBufs; b++) {
+        if (c->evReduced[b]) cudaEventDestroy(c->evReduced[b]);
+        if (c->evPushed[b]) cudaEventDestroy(c->evPushed[b]);
+    }
     if (c->comm) mrx::api().CommDestroy(c->comm);
     delete c;
 }
 
 int mrx_comm_rank(const mrx_comm *c) { return mrx::comm_rank(c); }
 int mrx_comm_size(const mrx_comm *c) { return mrx::comm_world(c); }
+
+/* cyclic distribution of one refinement iteration's work vector (n items) over `world` ranks, the layout the sharded
+ * apply uses: rank r computes the items i = r, r + world, ...; *count = how many those are, *rows = items per rank after
+ * padding to equal segments ((n + world - 1) / world). Item i lives in row (i % world) * rows + i / world of the rank-major
+ * exchange buffers (norms and coefficient blocks). Pure host logic, shared with the CPU tests. */
+void mrx_shard_cyclic(int n, int world, int rank, int *count, int *rows) {
+    if (rows) *rows = (n + world - 1) / world;
+    if (count) *count = (n + world - 1 - rank) / world;
+}
+int mrx_shard_cyclic_row(int i, int n, int world) { return (i % world) * ((n + world - 1) / world) + i / world; }
 
 /* contiguous, order-preserving partition of n weighted items into `world` ranges: begin[r]..begin[r+1]
  * (the split of one refinement iteration's work vector; pure host logic, also used by the CPU tests) */

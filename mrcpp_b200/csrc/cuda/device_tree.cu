@@ -51,6 +51,7 @@ void tree_upload(mrx_tree &t) {
     MRX_CUDA(cudaStreamSynchronize(st));
     t.dev.nNodes = n;
     t.dev.nGen = 0;
+    t.dev.topoNodes = -1;
     t.devValid = true;
 }
 
@@ -76,6 +77,10 @@ void tree_drop_device(mrx_tree &t) {
     t.dev.norms.release();
     t.dev.genCoefs.release();
     t.dev.genNorms.release();
+    t.dev.topoChild0.release();
+    t.dev.topoDepth.release();
+    t.dev.topoBound.release();
+    t.dev.topoNodes = -1;
     t.dev.nNodes = 0;
     t.dev.nGen = 0;
     t.devValid = false;
@@ -88,6 +93,7 @@ void device_calc_norms_all(mrx_tree &t) {
     Tree<3> &h = t.host;
     cudaStream_t st = stream();
     int n = h.nReal;
+    t.dev.topoNodes = -1; // node norms change: the cached band-walk topology of this tree is stale
     launch_norms(t.dev.coefs.p, t.dev.norms.p, nullptr, n, h.Kd, st);
     MRX_CUDA(cudaMemcpyAsync(h.cnorm.data(), t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     MRX_CUDA(cudaStreamSynchronize(st));

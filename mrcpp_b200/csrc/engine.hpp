@@ -55,6 +55,12 @@ struct DeviceTree {
     DevBuf<double> genNorms; // [nGen]
     int nNodes = 0;          // real nodes with valid device storage
     int nGen = 0;
+    // band-walk topology of the tree as an apply INPUT (apply.cu): child0 / depth / node norm per real node; valid while
+    // topoNodes == nReal, reset to -1 by everything that changes norms or structure (invalidate_topo)
+    DevBuf<int> topoChild0, topoDepth;
+    DevBuf<double> topoBound;
+    int topoNodes = -1;
+    double topoMaxNorm = 0.0;
 };
 
 struct DeviceOper {
@@ -63,7 +69,7 @@ struct DeviceOper {
     DevBuf<int> nodeOff;   // [M][DM] global node index of transl = -maxTransl, -1 if depth absent
     DevBuf<int> maxTransl; // [M][DM]
     DevBuf<int> nodeBase;  // [M][DM] node index of translation 0 (nodeOff + maxTransl), -1 if absent
-    DevBuf<int> bw;        // [M][DM][5]   (per apply: depends on prec)
+    DevBuf<int> bw;        // [M][DM][4]   1-D node counts 2 width + 1 per component (per apply: depends on prec)
     DevBuf<int> bsf;       // [M][DM][64]  band size factors (per apply)
     int M = 0, DM = 0;
     int identIdx = 0; // operator block index of the identity block appended to `mats`
@@ -116,6 +122,15 @@ int comm_rank(const mrx_comm *c);
 int comm_world(const mrx_comm *c);
 void comm_allgatherv(const mrx_comm *c, void *base, const size_t *off, const size_t *count, cudaStream_t st);
 void comm_allreduce_sum(const mrx_comm *c, double *buf, size_t n, cudaStream_t st);
+void comm_allgather(const mrx_comm *c, void *base, size_t bytes, cudaStream_t st); // in place, equal segments
+constexpr int kCommStageBufs = 3;
+void comm_stage_reserve(mrx_comm *c, size_t bytes, cudaStream_t st); // collective
+bool comm_peer_push_enabled(const mrx_comm *c);
+char *comm_stage(const mrx_comm *c, int buf);
+size_t comm_stage_bytes(const mrx_comm *c);
+void comm_push(mrx_comm *c, int buf, size_t off, size_t bytes);
+cudaEvent_t comm_ev_reduced(const mrx_comm *c, int buf);
+cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf);
 
 // apply.cu
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,

@@ -1,5 +1,6 @@
-"""Host logic of the sharded multi-GPU apply, on CPU: the contiguous work-vector partition
-(mrx_shard_partition) and the exchange protocol built on it, run with world_size 2 over gloo.
+"""Host logic of the sharded multi-GPU apply, on CPU: the cyclic distribution of a work vector (mrx_shard_cyclic, the layout
+mrx_apply_sharded uses), the contiguous weighted partition (mrx_shard_partition) and the exchange protocol built on the
+cyclic layout (rank-major padded segments, one all-gather, identical split decisions), run with world_size 2 over gloo.
 The device part of the same path is covered by tests/test_gpu_sharded.py."""
 import os
 import socket
@@ -25,6 +26,24 @@ def test_partition_properties(libs):
     assert b == [0, 5, 10]
 
 
+def test_cyclic_distribution_properties(libs):
+    mw, _ = libs
+    for n in (0, 1, 2, 7, 8, 9, 64, 1001):
+        for world in (1, 2, 3, 4, 8):
+            counts = [mw.shard_cyclic(n, world, r) for r in range(world)]
+            rows = counts[0][1]
+            assert all(c[1] == rows for c in counts) and rows == (n + world - 1) // world
+            assert sum(c[0] for c in counts) == n                       # every item has exactly one owner
+            assert max(c[0] for c in counts) - min(c[0] for c in counts) <= 1  # balanced to within one item
+            seen = set()
+            for i in range(n):
+                row = mw.shard_cyclic_row(i, n, world)
+                r, j = divmod(row, rows)
+                assert r == i % world and j == i // world and j < counts[r][0]
+                seen.add(row)
+            assert len(seen) == n                                       # rows are distinct: the unpack is a permutation
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -44,13 +63,15 @@ def _worker(rank, world, port, n, seed, q):
     cost = rng.integers(1, 500, size=n)            # identical on every rank (replicated topology)
     truth = np.sqrt(np.arange(n * 8, dtype=np.float64) + 1.0).reshape(n, 8)  # stands for the component norms
     begin = mw.shard_partition(cost, world)
-    # every rank "computes" only its range, in a work-vector-ordered buffer, then ranges are exchanged root by root
-    normsW = torch.zeros(n, 8, dtype=torch.float64)
-    normsW[begin[rank]:begin[rank + 1]] = torch.from_numpy(truth[begin[rank]:begin[rank + 1]])
-    for r in range(world):
-        seg = normsW[begin[r]:begin[r + 1]]
-        if seg.numel():
-            dist.broadcast(seg, src=r)
+    # every rank "computes" only its items (i % world == rank) into its segment of a rank-major, padded buffer; ONE
+    # all-gather of equal segments completes it; the host reads item i at row (i % world) * rows + i / world
+    cnt, rows = mw.shard_cyclic(n, world, rank)
+    mine = torch.zeros(rows, 8, dtype=torch.float64)
+    mine[:cnt] = torch.from_numpy(truth[rank::world])
+    segs = [torch.zeros(rows, 8, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(segs, mine)
+    full = torch.cat(segs)
+    normsW = torch.stack([full[mw.shard_cyclic_row(i, n, world)] for i in range(n)])
     ok = bool(np.array_equal(normsW.numpy(), truth))
     # the split decision is a pure function of the exchanged norms -> identical on all ranks
     split = (normsW[:, 1:].pow(2).sum(1).sqrt() > 20.0).numpy()
