@@ -23,6 +23,7 @@ import os as _os
 if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
     # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores
     _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
+_os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout; bench prints exactly one JSON line
 import argparse
 import json
 import math

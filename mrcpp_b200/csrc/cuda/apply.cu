@@ -101,7 +101,7 @@ struct Scratch {
     DevBuf<EnumCounters> ecnt;
     DevBuf<int> chunkOff, pNode;
     DevBuf<unsigned long long> chunkPacked, chunkScan, tileTotal, tileBase;
-    DevBuf<double> normsW; // component norms of the iteration's nodes in work-vector order
+    DevBuf<double> normsW[kCommStageBufs]; // component norms of the iteration's nodes, rank-major (one per staging buffer in flight)
     DevBuf<int> gslotsAll[kCommStageBufs]; // sharded apply: slots of the whole work vector, one per staging buffer in flight
 };
 
@@ -358,7 +358,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         scr.counters.reserve(4, false, st);
         comm_allreduce_sum(comm, reinterpret_cast<double *>(scr.counters.p + 2), 1, st);
         launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)), scr.gslotsAll[pend.buf].p, pend.nG,
-                            world, pend.rows, out.host.ncoef, st);
+                            world, pend.rows, out.host.ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, st);
         pend.active = false;
     };
     double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
@@ -795,7 +795,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scr.blockCnt.reserve((size_t)nL * 8 + 8, false, st);
             scr.blockTupOff.reserve((size_t)nL * 8 + 9, false, st);
             scr.blockUnitOff.reserve((size_t)nL * 8 + 9, false, st);
-            scr.normsW.reserve((size_t)world * rowsPerRank * 8 + 8, false, st);
+            DevBuf<double> &normsBuf = scr.normsW[world > 1 ? iter % kCommStageBufs : 0];
+            normsBuf.reserve((size_t)world * rowsPerRank * 8 + 8, false, st);
             scr.header.reserve(1, false, st);
             scr.queue.reserve(1, false, st);
             PipeBuffers B{};
@@ -832,7 +833,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             launch_pipe_contract(P, B, hdr.nUnits, st);
             MRX_CUDA(cudaEventRecord(ev3, st));
             // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-            double *normsMine = scr.normsW.p + (size_t)rank * rowsPerRank * 8;
+            double *normsMine = normsBuf.p + (size_t)rank * rowsPerRank * 8;
             if (world == 1) {
                 launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
                 MRX_CUDA(cudaEventRecord(ev1, st));
@@ -862,18 +863,20 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
                     MRX_CUDA(cudaEventRecord(comm_ev_reduced(comm, b), st));
                     comm_push(comm, b, (size_t)rank * segBytes, (size_t)nL * rowBytes);
                     if (pend.active) MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
-                    comm_allgather(comm, scr.normsW.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
+                    comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
                     if (pend.active)
                         launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)),
-                                            scr.gslotsAll[pend.buf].p, pend.nG, world, pend.rows, ncoef, st);
+                                            scr.gslotsAll[pend.buf].p, pend.nG, world, pend.rows, ncoef, scr.normsW[pend.buf].p,
+                                            out.dev.norms.p, st);
                     pend.active = true;
                     pend.buf = b;
                     pend.nG = nG;
                     pend.rows = rowsPerRank;
                 } else {
-                    comm_allgather(comm, scr.normsW.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
+                    comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
                     comm_allgather(comm, stageB, segBytes, st);
-                    launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, st);
+                    launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, normsBuf.p,
+                                        out.dev.norms.p, st);
                 }
             }
             iterTuples = (long long)hdr.totalTuples;
@@ -890,7 +893,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         std::vector<double> range;
         if (usePipe) {
             range.resize((size_t)world * rowsPerRank * 8);
-            MRX_CUDA(cudaMemcpyAsync(range.data(), scr.normsW.p, sizeof(double) * range.size(), cudaMemcpyDeviceToHost, st));
+            MRX_CUDA(cudaMemcpyAsync(range.data(), scr.normsW[world > 1 ? iter % kCommStageBufs : 0].p, sizeof(double) * range.size(),
+                                     cudaMemcpyDeviceToHost, st));
         } else {
             lo = *std::min_element(workVec.begin(), workVec.end());
             int hi = *std::max_element(workVec.begin(), workVec.end());
@@ -986,10 +990,10 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     S.f_applied_rank = S.f_applied;
     if (world > 1) {
         double h[2] = {(double)S.f_applied, (double)S.gen_nodes};
-        scr.normsW.reserve(2, false, st);
-        MRX_CUDA(cudaMemcpyAsync(scr.normsW.p, h, sizeof(h), cudaMemcpyHostToDevice, st));
-        comm_allreduce_sum(comm, scr.normsW.p, 2, st);
-        MRX_CUDA(cudaMemcpyAsync(h, scr.normsW.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        double *dsum = reinterpret_cast<double *>(scr.counters.p + 2);
+        MRX_CUDA(cudaMemcpyAsync(dsum, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        comm_allreduce_sum(comm, dsum, 2, st);
+        MRX_CUDA(cudaMemcpyAsync(h, dsum, sizeof(h), cudaMemcpyDeviceToHost, st));
         MRX_CUDA(cudaStreamSynchronize(st));
         S.f_applied = (long long)(h[0] + 0.5);
         S.gen_nodes = (long long)(h[1] + 0.5);
@@ -1023,12 +1027,12 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)
     double tp = now_ms();
     oper.op.clearBandWidths();
-    device_mw_transform(out, MRX_TOP_DOWN, false, /*norms=*/false); // the BottomUp pass below recomputes every norm
-    device_mw_transform(out, MRX_BOTTOM_UP, true);
-    out.host.calcSquareNorm();
+    const bool prof = getenv("MRX_PROFILE") != nullptr;
+    device_apply_post(out);
     inp.host.deleteGenerated();
     inp.dev.nGen = 0;
     S.ms_post = now_ms() - tp;
+    (void)prof;
     S.n_nodes_out = out.host.nReal;
     S.kernel_launches = launch_counter() - launches0;
     if (getenv("MRX_PROFILE"))

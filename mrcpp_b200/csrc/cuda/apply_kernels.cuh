@@ -152,8 +152,9 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
 /// exchange staging buffer (row j = local node j) instead of the node store
 void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
                         cudaStream_t st, double *stageRows = nullptr);
-/// sharded apply: rank-major staging buffer (row r * rowsPerRank + j = work-vector item j * world + r) -> node store
+/// sharded apply: rank-major staging buffer (row r * rowsPerRank + j = work-vector item j * world + r) -> node store,
+/// coefficient blocks and (normRows, same layout, 8 per row) component norms
 void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
-                         cudaStream_t st);
+                         const double *normRows, double *gNorms, cudaStream_t st);
 
 } // namespace mrx

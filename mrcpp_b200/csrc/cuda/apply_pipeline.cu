@@ -635,13 +635,16 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const i
 // item i = j * world + r, the cyclic distribution of the work vector) into the node store
 __global__ void __launch_bounds__(256) unpack_nodes_kernel(double *__restrict__ coefs, const double *__restrict__ stage,
                                                            const int *__restrict__ gslotsAll, int nG, int world, int rowsPerRank,
-                                                           int ncoef) {
+                                                           int ncoef, const double *__restrict__ normRows, double *__restrict__ gNorms) {
     const int r = blockIdx.x / rowsPerRank, j = blockIdx.x - r * rowsPerRank;
     const int i = j * world + r;
     if (i >= nG) return;
+    const int slot = gslotsAll[i];
     const double2 *src = reinterpret_cast<const double2 *>(stage + (size_t)blockIdx.x * ncoef);
-    double2 *dst = reinterpret_cast<double2 *>(coefs + (size_t)gslotsAll[i] * ncoef);
+    double2 *dst = reinterpret_cast<double2 *>(coefs + (size_t)slot * ncoef);
     for (int e = threadIdx.x; e < ncoef / 2; e += 256) dst[e] = src[e];
+    // component norms of the node (all-gathered in the same rank-major layout) into the node store
+    if (threadIdx.x < 8) gNorms[(size_t)slot * 8 + threadIdx.x] = normRows[(size_t)blockIdx.x * 8 + threadIdx.x];
 }
 
 } // namespace
@@ -750,9 +753,9 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
 }
 
 void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
-                         cudaStream_t st) {
+                         const double *normRows, double *gNorms, cudaStream_t st) {
     if (nG <= 0) return;
-    unpack_nodes_kernel<<<world * rowsPerRank, 256, 0, st>>>(coefs, stage, gslotsAll, nG, world, rowsPerRank, ncoef);
+    unpack_nodes_kernel<<<world * rowsPerRank, 256, 0, st>>>(coefs, stage, gslotsAll, nG, world, rowsPerRank, ncoef, normRows, gNorms);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

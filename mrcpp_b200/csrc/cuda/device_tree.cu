@@ -104,15 +104,11 @@ void device_calc_norms_all(mrx_tree &t) {
     }
 }
 
-void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms, int timedReps, double *timedMs, int *branchNodes) {
-    require_device("device_mw_transform");
-    if (!t.devValid) tree_upload(t);
-    Tree<3> &h = t.host;
-    cudaStream_t st = stream();
-    // level lists of branch nodes (counting sort by depth over the slot order; parents of one level are independent,
-    // so their order inside a level is irrelevant)
+// level lists of branch nodes (counting sort by depth over the slot order; parents of one level are independent, so
+// their order inside a level is irrelevant): flat = (parent, child0) pairs, level d = [levelOff[d], levelOff[d+1])
+static int build_level_pairs(const Tree<3> &h, std::vector<int> &levelOff, std::vector<int> &flat) {
     const int n = h.nReal;
-    std::vector<int> levelOff(2, 0);
+    levelOff.assign(2, 0);
     for (int i = 0; i < n; i++) {
         const auto &nd = h.nodes[i];
         if (nd.child0 < 0 || nd.child0 >= n) continue; // leaf, or children are generated nodes
@@ -123,17 +119,77 @@ void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms, int 
     const int nLevels = (int)levelOff.size() - 1;
     for (int d = 0; d < nLevels; d++) levelOff[d + 1] += levelOff[d];
     const int nPairs = levelOff[nLevels];
-    if (nPairs == 0) {
-        if (norms) device_calc_norms_all(t);
-        return;
-    }
-    std::vector<int> flat((size_t)2 * nPairs), fill(levelOff.begin(), levelOff.end() - 1);
+    flat.resize((size_t)2 * nPairs);
+    std::vector<int> fill(levelOff.begin(), levelOff.end() - 1);
     for (int i = 0; i < n; i++) {
         const auto &nd = h.nodes[i];
         if (nd.child0 < 0 || nd.child0 >= n) continue;
         const int pos = fill[nd.scale - h.mra.rootScale]++;
         flat[2 * (size_t)pos] = i;
         flat[2 * (size_t)pos + 1] = nd.child0;
+    }
+    return nPairs;
+}
+
+/// closing passes of mrcpp::apply (apply.cpp:82-84): mwTransform(TopDown, overwrite = false), mwTransform(BottomUp),
+/// calcSquareNorm. One level list for both passes; where the transform kernels compute the norms of what they write
+/// (scaling norm of every child on the way down, all eight norms of every parent on the way up) no separate pass over the
+/// tree is needed: wavelet norms of the leaves are those of the apply itself. The tree norm is the sum of the end-node
+/// square norms in slot order (the reference sums the same terms in end-node-table order).
+void device_apply_post(mrx_tree &t) {
+    require_device("device_apply_post");
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    const int n = h.nReal;
+    std::vector<int> levelOff, flat;
+    const int nPairs = build_level_pairs(h, levelOff, flat);
+    const int nLevels = (int)levelOff.size() - 1;
+    const bool fused = transform_fuses_norms(h.K);
+    t.dev.topoNodes = -1;
+    if (nPairs > 0) {
+        DevBuf<int> pairs;
+        pairs.reserve(flat.size(), false, st);
+        MRX_CUDA(cudaMemcpyAsync(pairs.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
+        const double *filt = device_filters(h.k);
+        double *nrm = fused ? t.dev.norms.p : nullptr;
+        for (int d = 0; d < nLevels; d++) {
+            const int cnt = levelOff[d + 1] - levelOff[d];
+            if (cnt > 0) launch_transform(true, false, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st, nrm);
+        }
+        for (int d = nLevels - 1; d >= 0; d--) {
+            const int cnt = levelOff[d + 1] - levelOff[d];
+            if (cnt > 0) launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st, nrm);
+        }
+        if (!fused) launch_norms(t.dev.coefs.p, t.dev.norms.p, nullptr, n, h.Kd, st);
+        MRX_CUDA(cudaMemcpyAsync(h.cnorm.data(), t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st)); // also keeps `pairs` alive until the launches have consumed it
+    } else {
+        MRX_CUDA(cudaMemcpyAsync(h.cnorm.data(), t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+    }
+    t.devValid = true;
+    t.hostCoefsValid = false;
+    double tot = 0.0;
+    for (int i = 0; i < n; i++) {
+        double sq = 0.0;
+        for (int c = 0; c < 8; c++) sq += h.cnorm[(size_t)i * 8 + c] * h.cnorm[(size_t)i * 8 + c];
+        h.sqn[i] = sq;
+        if (h.nodes[i].flags & FlagEnd) tot += sq;
+    }
+    h.squareNorm = tot;
+}
+
+void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms, int timedReps, double *timedMs, int *branchNodes) {
+    require_device("device_mw_transform");
+    if (!t.devValid) tree_upload(t);
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    std::vector<int> levelOff, flat;
+    const int nPairs = build_level_pairs(h, levelOff, flat);
+    const int nLevels = (int)levelOff.size() - 1;
+    if (nPairs == 0) {
+        if (norms) device_calc_norms_all(t);
+        return;
     }
     DevBuf<int> pairs;
     pairs.reserve(flat.size(), false, st);

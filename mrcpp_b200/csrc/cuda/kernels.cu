@@ -120,7 +120,7 @@ constexpr int kT8Si = 18, kT8Sm = 152, kT8Doubles = 8 * kT8Sm; // same padded ti
 
 template <int MODE> // 0: TopDown (parent 8 blocks -> children scaling, = or +=); 1: BottomUp (children scaling -> parent); 3: in-node compression
 __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ coefs, const int *__restrict__ pairs,
-                                                         const double *__restrict__ filters, int overwrite) {
+                                                         const double *__restrict__ filters, int overwrite, double *__restrict__ norms) {
     extern __shared__ __align__(128) double tiles8[]; // 8 padded tiles (kT8Doubles each) + the TMA-staged node (8 x 512)
     constexpr int Kd = 512, ncoef = 8 * Kd;
     const int parent = pairs[2 * blockIdx.x];
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
                 }
             }
             const int gt = g01 | (g2 << 2);
+            double n2 = 0.0;
             double *dst = ((MODE == 0) ? coefs + (size_t)(child0 + gt) * ncoef : coefs + (size_t)parent * ncoef + (size_t)gt * Kd) +
                           8 * r + 64 * (2 * q);
 #pragma unroll
@@ -245,6 +246,17 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
                 }
                 *reinterpret_cast<double2 *>(dst + 2 * v) = lo;
                 *reinterpret_cast<double2 *>(dst + 64 + 2 * v) = hi;
+                n2 = fma(lo.x, lo.x, n2);
+                n2 = fma(lo.y, lo.y, n2);
+                n2 = fma(hi.x, hi.x, n2);
+                n2 = fma(hi.y, hi.y, n2);
+            }
+            // component norm of the block just written (MWNode::calcNorms): scaling block of child gt (TopDown) or block gt of
+            // the parent (BottomUp / in-node compression); fixed shuffle tree -> deterministic
+            if (norms) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+                if (lane == 0) norms[(MODE == 0) ? (size_t)(child0 + gt) * 8 : (size_t)parent * 8 + gt] = sqrt(n2);
             }
         }
     }
@@ -339,8 +351,10 @@ void launch_norms(const double *coefs, double *norms, const int *slots, int n, i
     launch_counter()++;
 }
 
+bool transform_fuses_norms(int K) { return K == 8; }
+
 void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
-                      cudaStream_t st) {
+                      cudaStream_t st, double *norms) {
     if (cnt <= 0) return;
     if (K == 8) {
         constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
@@ -350,8 +364,8 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
             MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
             conf = true;
         }
-        if (down) transform8_kernel<0><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, overwrite ? 1 : 0);
-        else transform8_kernel<1><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, 1);
+        if (down) transform8_kernel<0><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, overwrite ? 1 : 0, norms);
+        else transform8_kernel<1><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, 1, norms);
         MRX_CUDA(cudaGetLastError());
         launch_counter()++;
         return;
@@ -370,7 +384,7 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
     launch_counter()++;
 }
 
-void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st) {
+void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st, double *norms) {
     if (cnt <= 0) return;
     if (K == 8) {
         constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
@@ -379,7 +393,7 @@ void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, cons
             MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
             conf = true;
         }
-        transform8_kernel<3><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, 1);
+        transform8_kernel<3><<<cnt, 128, bytes8, st>>>(coefs, pairs, filters, 1, norms);
     } else {
         int padOn;
         size_t bytes = transform_smem(K, padOn);

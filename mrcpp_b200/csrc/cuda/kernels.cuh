@@ -14,11 +14,15 @@ void launch_norms(const double *coefs, double *norms, const int *slots, int n, i
 
 /// one level of the two-scale transform. pairs = (parent slot, child0 slot) x cnt.
 /// down: children.scaling (=|+=) reconstruct(parent 8 blocks); up: parent 8 blocks = compress(children.scaling)
+/// norms (optional, honoured when transform_fuses_norms(K)): component norms of the blocks written, in the node-store
+/// layout norms[node*8 + c]: scaling norm of every child (down) / all 8 norms of every parent (up)
 void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
-                      cudaStream_t st);
+                      cudaStream_t st, double *norms = nullptr);
+bool transform_fuses_norms(int K);
 
 /// in-node compression MWNode::mwTransform(Compression) of the nodes pairs[2 i] (pairs[2 i + 1] unused)
-void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st);
+void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st,
+                           double *norms = nullptr);
 
 /// ProjectionCalculator::calcNode for a Gaussian expansion (project.cu): function values at the expanded child quadrature
 /// points of every work node, scaled to scaling coefficients (cvTransform Backward); nodeInfo = (scale, lx, ly, lz)
