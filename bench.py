@@ -2,8 +2,9 @@
 """bench.py — Poisson-apply throughput on B200 (BASELINE.json metric).
 
 A "step" is one mrcpp::apply of the 3-D Poisson operator (k=7, prec 1e-7: the north_star target) onto a
-synthetic multi-centre Gaussian density (seed 42, centres uniform in [-8,8]^3, beta log-uniform in
-[10,1000], as config C5 of SURVEY.md §8d) with a fresh output tree each step.
+synthetic 1000-centre Gaussian density (seed 42, centres uniform in [-8,8]^3, beta log-uniform in
+[10,1000], the generator of config C5 of SURVEY.md §8d; 343 K input nodes = 11.2 GB, projected on the device)
+with a fresh output tree each step.
 
   value  output nodes/s (calcNode invocations over all refinement iterations / device time), inputs
          resident in HBM when the timed region starts.
@@ -171,7 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--order", type=int, default=7)
     ap.add_argument("--prec", type=float, default=1e-7)
-    ap.add_argument("--centers", type=int, default=100)
+    ap.add_argument("--centers", type=int, default=1000)
     ap.add_argument("--cpu-centers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -23,6 +23,7 @@ SOURCES = [
     "cuda/apply_kernels.cu",
     "cuda/apply_pipeline.cu",
     "cuda/apply_enum.cu",
+    "cuda/apply_split.cu",
     "cuda/comm.cu",
     "cuda/microbench.cu",
 ]

@@ -102,7 +102,13 @@ struct Scratch {
     DevBuf<int> chunkOff, pNode;
     DevBuf<unsigned long long> chunkPacked, chunkScan, tileTotal, tileBase;
     DevBuf<double> normsW[kCommStageBufs]; // component norms of the iteration's nodes, rank-major (one per staging buffer in flight)
-    DevBuf<int> gslotsAll[kCommStageBufs]; // sharded apply: slots of the whole work vector, one per staging buffer in flight
+    DevBuf<int> gslotsAll[kCommStageBufs]; // slots of the whole work vector (sharded apply: one per staging buffer in flight)
+    // device-side refinement (apply_split.cu)
+    DevBuf<int4> gAll[2];            // (depth, l) of the whole work vector, current / next
+    DevBuf<unsigned char> isBranch, flags;
+    bool hasBranchFlags = false;
+    DevBuf<double> scaleFac, state;
+    DevBuf<SplitResult> splitRes;
 };
 
 /// input-tree topology on the device for the band enumeration: real nodes + generated nodes in one slot space
@@ -233,31 +239,10 @@ struct BandTables {
 
 } // namespace
 
-static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
-                      std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm = nullptr) {
-    cudaStream_t st = stream();
-    const double tEnter = now_ms();
+/// band tables of (operator, prec, direction), cached on the operator; band size factors uploaded once per cache entry
+static BandTables &get_band_tables(mrx_oper &oper, double prec, int derivDir, cudaStream_t st) {
     Operator &op = oper.op;
     const int M = op.size(), DM = oper.dev.DM;
-    const bool deriv = derivDir >= 0;
-    const char *legacy = getenv("MRX_LEGACY");
-    const bool usePipe = pipe_supports_order(out.host.K) && !(legacy && legacy[0] == '1');
-    const int world = comm_world(comm), rank = comm_rank(comm);
-    const char *uEnv = getenv("MRX_UNIT_TUPLES");
-    const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
-    if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11 convolution operators) only");
-    Tree<3> &g = out.host;
-    Tree<3> &f = inp.host;
-    const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
-    const int maxScale = g.mra.maxScale();
-    g.allocCoefs = false; // the output lives in HBM until somebody asks for it
-    out.hostCoefsValid = false;
-    out.devValid = true;
-    const double *filt = device_filters(g.k);
-
-    Scratch scr;
-    scr.counters.reserve(4, false, st);
-    MRX_CUDA(cudaMemsetAsync(scr.counters.p, 0, 4 * sizeof(unsigned long long), st));
     // per-depth band tables are cached on the operator: they depend only on (operator, prec, direction)
     std::shared_ptr<BandTables> btp = std::static_pointer_cast<BandTables>(oper.bandCache);
     if (!btp || btp->prec != prec || btp->derivDir != derivDir || (int)btp->info.size() != DM) {
@@ -291,25 +276,42 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         MRX_CUDA(cudaMemcpyAsync(oper.dev.bw.p, sep.data(), sizeof(int) * sep.size(), cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaStreamSynchronize(st));
     }
-    const std::vector<int> &bsf = bt.bsf;
+    return bt;
+}
 
-    cudaEvent_t ev0, ev1, ev2, ev3;
-    MRX_CUDA(cudaEventCreate(&ev0));
-    MRX_CUDA(cudaEventCreate(&ev1));
-    MRX_CUDA(cudaEventCreate(&ev2));
-    MRX_CUDA(cudaEventCreate(&ev3));
-    float kernel_ms = 0.f, contract_ms = 0.f;
-    long long tuplesTotal = 0, iterTuples = 0;
+/// (re)upload the band tables after new depths were built
+static void upload_band_tables(BandTables &bt, int DM, bool usePipe, cudaStream_t st) {
+    if (bt.dirty) {
+        bt.d_info.reserve(DM, false, st);
+        bt.d_candOff.reserve(bt.candOff.size(), false, st);
+        bt.d_candTerm.reserve(std::max<size_t>(bt.candTerm.size(), 1), false, st);
+        bt.d_candMask.reserve(std::max<size_t>(bt.candMask.size(), 1), false, st);
+        MRX_CUDA(cudaMemcpyAsync(bt.d_info.p, bt.info.data(), sizeof(DepthInfo) * DM, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(bt.d_candOff.p, bt.candOff.data(), sizeof(int) * bt.candOff.size(), cudaMemcpyHostToDevice, st));
+        if (!bt.candTerm.empty()) {
+            MRX_CUDA(cudaMemcpyAsync(bt.d_candTerm.p, bt.candTerm.data(), sizeof(int) * bt.candTerm.size(),
+                                     cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(bt.d_candMask.p, bt.candMask.data(), sizeof(unsigned long long) * bt.candMask.size(),
+                                     cudaMemcpyHostToDevice, st));
+        }
+        if (usePipe) {
+            bt.d_offs.reserve(std::max<size_t>(bt.offs.size(), 1), false, st);
+            bt.d_offStart.reserve(DM, false, st);
+            bt.d_offCount.reserve(DM, false, st);
+            if (!bt.offs.empty())
+                MRX_CUDA(cudaMemcpyAsync(bt.d_offs.p, bt.offs.data(), sizeof(OffEntry) * bt.offs.size(), cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(bt.d_offStart.p, bt.offStart.data(), sizeof(int) * DM, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(bt.d_offCount.p, bt.offCount.data(), sizeof(int) * DM, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaStreamSynchronize(st)); // host vectors may be reallocated by the next build()
+        }
+        bt.dirty = false;
+    }
+}
 
-    double sNorm = 0.0, wNorm = 0.0;
-    int iter = 0;
+/// pristine band-walk topology of an input tree (cached on the tree)
+static void ensure_input_topology(mrx_tree &inp, cudaStream_t st) {
+    Tree<3> &f = inp.host;
     const int fRealN = f.nReal;
-    std::vector<GDesc> gdesc;
-    std::vector<NbrEntry> nbr;
-    std::vector<int> newParents;
-    std::vector<double> genBound; // per generated node: norm of its real leaf ancestor (upper bound of its own norm)
-    DevTopo topo;
-    int fTotal = fRealN; // real + generated input nodes known to the device
     // pristine topology (child pointers, depths, node norms) of the input tree: cached on the tree, copied device to device
     // per apply (generated nodes hang new children below real leaves while an apply runs)
     DeviceTree &fd = inp.dev;
@@ -333,6 +335,55 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         fd.topoNodes = fRealN;
         fd.topoMaxNorm = mx;
     }
+}
+
+static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
+                      std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm = nullptr) {
+    cudaStream_t st = stream();
+    const double tEnter = now_ms();
+    Operator &op = oper.op;
+    const int M = op.size(), DM = oper.dev.DM;
+    const bool deriv = derivDir >= 0;
+    const char *legacy = getenv("MRX_LEGACY");
+    const bool usePipe = pipe_supports_order(out.host.K) && !(legacy && legacy[0] == '1');
+    const int world = comm_world(comm), rank = comm_rank(comm);
+    const char *uEnv = getenv("MRX_UNIT_TUPLES");
+    const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
+    if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11 convolution operators) only");
+    Tree<3> &g = out.host;
+    Tree<3> &f = inp.host;
+    const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
+    const int maxScale = g.mra.maxScale();
+    g.allocCoefs = false; // the output lives in HBM until somebody asks for it
+    out.hostCoefsValid = false;
+    out.devValid = true;
+    const double *filt = device_filters(g.k);
+
+    Scratch scr;
+    scr.counters.reserve(4, false, st);
+    MRX_CUDA(cudaMemsetAsync(scr.counters.p, 0, 4 * sizeof(unsigned long long), st));
+    BandTables &bt = get_band_tables(oper, prec, derivDir, st);
+    const std::vector<int> &bsf = bt.bsf;
+
+    cudaEvent_t ev0, ev1, ev2, ev3;
+    MRX_CUDA(cudaEventCreate(&ev0));
+    MRX_CUDA(cudaEventCreate(&ev1));
+    MRX_CUDA(cudaEventCreate(&ev2));
+    MRX_CUDA(cudaEventCreate(&ev3));
+    float kernel_ms = 0.f, contract_ms = 0.f;
+    long long tuplesTotal = 0, iterTuples = 0;
+
+    double sNorm = 0.0, wNorm = 0.0;
+    int iter = 0;
+    const int fRealN = f.nReal;
+    std::vector<GDesc> gdesc;
+    std::vector<NbrEntry> nbr;
+    std::vector<int> newParents;
+    std::vector<double> genBound; // per generated node: norm of its real leaf ancestor (upper bound of its own norm)
+    DevTopo topo;
+    int fTotal = fRealN; // real + generated input nodes known to the device
+    ensure_input_topology(inp, st);
+    DeviceTree &fd = inp.dev;
     const double fMaxNorm = fd.topoMaxNorm;
     std::vector<double> fNodeNorm; // host enumeration of the legacy (odd K) path only
     if (!usePipe) {
@@ -549,31 +600,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         }
         tp_phase2 += now_ms() - tq;
         tq = now_ms();
-        if (bt.dirty) {
-            bt.d_info.reserve(DM, false, st);
-            bt.d_candOff.reserve(bt.candOff.size(), false, st);
-            bt.d_candTerm.reserve(std::max<size_t>(bt.candTerm.size(), 1), false, st);
-            bt.d_candMask.reserve(std::max<size_t>(bt.candMask.size(), 1), false, st);
-            MRX_CUDA(cudaMemcpyAsync(bt.d_info.p, bt.info.data(), sizeof(DepthInfo) * DM, cudaMemcpyHostToDevice, st));
-            MRX_CUDA(cudaMemcpyAsync(bt.d_candOff.p, bt.candOff.data(), sizeof(int) * bt.candOff.size(), cudaMemcpyHostToDevice, st));
-            if (!bt.candTerm.empty()) {
-                MRX_CUDA(cudaMemcpyAsync(bt.d_candTerm.p, bt.candTerm.data(), sizeof(int) * bt.candTerm.size(),
-                                         cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaMemcpyAsync(bt.d_candMask.p, bt.candMask.data(), sizeof(unsigned long long) * bt.candMask.size(),
-                                         cudaMemcpyHostToDevice, st));
-            }
-            if (usePipe) {
-                bt.d_offs.reserve(std::max<size_t>(bt.offs.size(), 1), false, st);
-                bt.d_offStart.reserve(DM, false, st);
-                bt.d_offCount.reserve(DM, false, st);
-                if (!bt.offs.empty())
-                    MRX_CUDA(cudaMemcpyAsync(bt.d_offs.p, bt.offs.data(), sizeof(OffEntry) * bt.offs.size(), cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaMemcpyAsync(bt.d_offStart.p, bt.offStart.data(), sizeof(int) * DM, cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaMemcpyAsync(bt.d_offCount.p, bt.offCount.data(), sizeof(int) * DM, cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaStreamSynchronize(st)); // host vectors may be reallocated by the next build()
-            }
-            bt.dirty = false;
-        }
+        upload_band_tables(bt, DM, usePipe, st);
         if (usePipe) {
             // ---- device enumeration of the operator band + generated input nodes (apply_enum.cu)
             // sharded apply: cyclic distribution of the work vector, rank r computes the items i = r, r + world, ...
@@ -1006,6 +1033,478 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     if (profile) std::fprintf(stderr, "[mrx] run_apply ms: post-loop %.2f\n", now_ms() - tLoopEnd);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Work-list pipeline with the refinement step on the device. Per iteration the host launches kernels and reads back
+// three small records (enumeration counters, tuple/unit counts, split result); it replays the split decisions into its
+// own topology AFTER it has launched the next iteration's contraction, i.e. while the device is busy. Nothing on the
+// host's critical path loops over nodes (except the one-off set-up of the first work vector).
+static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
+                           std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm) {
+    cudaStream_t st = stream();
+    const double tEnter = now_ms();
+    Operator &op = oper.op;
+    const int M = op.size(), DM = oper.dev.DM;
+    const bool deriv = derivDir >= 0;
+    const int world = comm_world(comm), rank = comm_rank(comm);
+    const char *uEnv = getenv("MRX_UNIT_TUPLES");
+    const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
+    const bool profile = getenv("MRX_PROFILE") != nullptr;
+    Tree<3> &g = out.host;
+    Tree<3> &f = inp.host;
+    const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
+    const int maxScale = g.mra.maxScale();
+    g.allocCoefs = false; // the output lives in HBM until somebody asks for it
+    out.hostCoefsValid = false;
+    out.devValid = true;
+    const double *filt = device_filters(g.k);
+    const int fRealN = f.nReal;
+
+    Scratch scr;
+    scr.counters.reserve(4, false, st);
+    MRX_CUDA(cudaMemsetAsync(scr.counters.p, 0, 4 * sizeof(unsigned long long), st));
+    BandTables &bt = get_band_tables(oper, prec, derivDir, st);
+    const std::vector<int> &bsf = bt.bsf;
+    cudaEvent_t ev0, ev1, ev2, ev3;
+    MRX_CUDA(cudaEventCreate(&ev0));
+    MRX_CUDA(cudaEventCreate(&ev1));
+    MRX_CUDA(cudaEventCreate(&ev2));
+    MRX_CUDA(cudaEventCreate(&ev3));
+    float kernel_ms = 0.f, contract_ms = 0.f;
+    long long tuplesTotal = 0;
+
+    ensure_input_topology(inp, st);
+    DeviceTree &fd = inp.dev;
+    const double fMaxNorm = fd.topoMaxNorm;
+    DevTopo topo;
+    int fTotal = fRealN; // real + generated input nodes known to the device
+    topo.reserve((size_t)fRealN + 4096, st);
+    MRX_CUDA(cudaMemcpyAsync(topo.child0.p, fd.topoChild0.p, sizeof(int) * fRealN, cudaMemcpyDeviceToDevice, st));
+    MRX_CUDA(cudaMemcpyAsync(topo.depth.p, fd.topoDepth.p, sizeof(int) * fRealN, cudaMemcpyDeviceToDevice, st));
+    MRX_CUDA(cudaMemcpyAsync(topo.bound.p, fd.topoBound.p, sizeof(double) * fRealN, cudaMemcpyDeviceToDevice, st));
+    MRX_CUDA(cudaMemsetAsync(topo.flag.p, 0, sizeof(int) * topo.flag.cap, st));
+
+    // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store
+    struct {
+        bool active = false;
+        int buf = 0, nG = 0, rows = 0;
+    } pend;
+    auto flush_pending = [&]() {
+        if (!pend.active) return;
+        // own push done -> tiny all-reduce: behind it every peer's push is done as well -> unpack
+        MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
+        comm_allreduce_sum(comm, reinterpret_cast<double *>(scr.counters.p + 2), 1, st);
+        launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)), scr.gslotsAll[pend.buf].p, pend.nG,
+                            world, pend.rows, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, st);
+        pend.active = false;
+    };
+
+    // ---- first work vector: from the host topology
+    int nG = (int)workVec.size();
+    int minDep = 1 << 30, maxDep = -(1 << 30);
+    {
+        std::vector<int4> gN(std::max(nG, 1));
+        std::vector<unsigned char> br(std::max(nG, 1), 0);
+        bool anyBranch = false;
+        for (int i = 0; i < nG; i++) {
+            const auto &nd = g.nodes[workVec[i]];
+            const int dep = nd.scale - op.operRoot;
+            gN[i] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
+            br[i] = g.isBranch(workVec[i]) ? 1 : 0;
+            anyBranch = anyBranch || br[i];
+            minDep = std::min(minDep, dep);
+            maxDep = std::max(maxDep, dep);
+            if (dep >= 0 && dep < DM && !bt.built[dep]) bt.build(op, dep, derivDir, bsf, DM);
+        }
+        scr.gAll[0].reserve(std::max(nG, 1), false, st);
+        scr.gslotsAll[0].reserve(std::max(nG, 1), false, st);
+        scr.isBranch.reserve(std::max(nG, 1), false, st);
+        if (nG > 0) {
+            MRX_CUDA(cudaMemcpyAsync(scr.gAll[0].p, gN.data(), sizeof(int4) * nG, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(scr.gslotsAll[0].p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+            if (anyBranch) MRX_CUDA(cudaMemcpyAsync(scr.isBranch.p, br.data(), nG, cudaMemcpyHostToDevice, st));
+        }
+        scr.hasBranchFlags = anyBranch;
+        MRX_CUDA(cudaStreamSynchronize(st)); // gN / br are locals
+    }
+    upload_band_tables(bt, DM, true, st);
+    // split_check's scale factors as the host's pow() gives them; TreeBuilder state
+    {
+        const int nS = g.mra.maxDepth + 3;
+        std::vector<double> sf(nS);
+        for (int d = 0; d < nS; d++) {
+            const double expo = 0.5 * 1.0 * (g.mra.rootScale + d + 1);
+            sf[d] = std::pow(2.0, -expo);
+        }
+        scr.scaleFac.reserve(nS, false, st);
+        scr.state.reserve(4, false, st);
+        scr.splitRes.reserve(1, false, st);
+        MRX_CUDA(cudaMemcpyAsync(scr.scaleFac.p, sf.data(), sizeof(double) * nS, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemsetAsync(scr.state.p, 0, 4 * sizeof(double), st));
+        MRX_CUDA(cudaMemsetAsync(scr.splitRes.p, 0, sizeof(SplitResult), st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+    }
+    auto prep_local = [&](int cur, int slotBuf, int nGgiven) {
+        const int cap = (nGgiven >= 0) ? nGgiven : 8 * nG; // upper bound of the next work vector
+        const int capL = (cap + world - 1) / world + 1;
+        scr.gNodes.reserve(capL, false, st);
+        scr.gslots.reserve(capL, false, st);
+        scr.chunkOff.reserve(capL + 1, false, st);
+        PrepParams PP{};
+        PP.nG = nGgiven;
+        PP.world = world;
+        PP.rank = rank;
+        PP.gNodesAll = scr.gAll[cur].p;
+        PP.slotsAll = scr.gslotsAll[slotBuf].p;
+        PP.offCount = bt.d_offCount.p;
+        PP.depthInfo = bt.d_info.p;
+        PP.DM = DM;
+        PP.gNodesLoc = scr.gNodes.p;
+        PP.slotsLoc = scr.gslots.p;
+        PP.chunkOffLoc = scr.chunkOff.p;
+        PP.res = scr.splitRes.p;
+        launch_prep_local(PP, st);
+    };
+    SplitResult res{};
+    prep_local(0, 0, nG);
+    MRX_CUDA(cudaMemcpyAsync(&res, scr.splitRes.p, sizeof(res), cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+
+    // host replay of the split decisions (deferred: runs while the device contracts the next iteration)
+    struct Replay {
+        std::vector<unsigned char> flags;
+        int slotBase;
+    };
+    std::vector<Replay> replay; // one per finished iteration, processed in order
+    size_t replayed = 0;
+    std::vector<int> hostVec = workVec; // host work vector of iteration `replayed`
+    auto replay_pending = [&]() {
+        for (; replayed < replay.size(); replayed++) {
+            const Replay &R = replay[replayed];
+            std::vector<int> next;
+            int expect = R.slotBase;
+            for (size_t i = 0; i < hostVec.size(); i++) {
+                g.nodes[hostVec[i]].flags |= FlagHasCoefs;
+                if (i < R.flags.size() && R.flags[i]) {
+                    const int c0 = g.createChildren(hostVec[i], false);
+                    if (c0 != expect) MRX_ABORT("apply: host replay of the device split decisions lost its slot order");
+                    expect += 8;
+                    for (int c = 0; c < 8; c++) next.push_back(c0 + c);
+                }
+            }
+            hostVec.swap(next);
+        }
+    };
+
+    int nRealDev = g.nReal; // slots of the output tree as the device sees them (the host topology lags by one iteration)
+    int iter = 0, cur = 0;
+    double tp_gen = 0, tp_wait = 0, tp_split = 0, tp_replay = 0;
+    const double tLoop = now_ms();
+    while (nG > 0) {
+        double tq = now_ms();
+        const int b = iter % kCommStageBufs;
+        const int nL = res.nLoc, nChunks = res.nChunksLoc;
+        const long long nbrCap = res.nbrCapLoc;
+        const int rowsPerRank = (nG + world - 1) / world;
+        if (nbrCap >= (1ll << 31) || (long long)nChunks * 32 >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
+        double gThrs = g.squareNorm; // ConvolutionCalculator.cpp:241-248
+        if (gThrs > 0.0) gThrs = prec * 1.0 * std::sqrt(gThrs / static_cast<double>(M));
+        const bool screenOn = !deriv && gThrs >= 0.0;
+        // ---- band enumeration + generated input nodes (apply_enum.cu)
+        scr.gdesc.reserve(std::max(nL, 1), false, st);
+        scr.nbr.reserve(std::max<long long>(nbrCap, 1), false, st);
+        scr.pending.reserve(std::max<long long>(nbrCap, 1), false, st);
+        scr.ecnt.reserve(1, false, st);
+        scr.pNode.reserve(std::max<size_t>((size_t)nChunks * 32, 1), false, st);
+        scr.chunkPacked.reserve(std::max(nChunks, 1), false, st);
+        scr.chunkScan.reserve(std::max(nChunks, 1), false, st);
+        scr.tileTotal.reserve(nChunks / 2048 + 2, false, st);
+        scr.tileBase.reserve(nChunks / 2048 + 3, false, st);
+        MRX_CUDA(cudaMemsetAsync(scr.ecnt.p, 0, sizeof(EnumCounters), st));
+        EnumParams E{};
+        E.gNodes = scr.gNodes.p;
+        E.gSlots = scr.gslots.p;
+        E.nG = nL;
+        E.chunkOff = scr.chunkOff.p;
+        E.nChunks = nChunks;
+        E.pNode = scr.pNode.p;
+        E.chunkPacked = scr.chunkPacked.p;
+        E.chunkScan = scr.chunkScan.p;
+        E.tileTotal = scr.tileTotal.p;
+        E.tileBase = scr.tileBase.p;
+        E.depthShift = op.operRoot - f.mra.rootScale;
+        E.offStart = bt.d_offStart.p;
+        E.offCount = bt.d_offCount.p;
+        E.offs = bt.d_offs.p;
+        E.depthInfo = bt.d_info.p;
+        E.candOff = bt.d_candOff.p;
+        E.DM = DM;
+        E.fChild0 = topo.child0.p;
+        E.fDepth = topo.depth.p;
+        E.fBound = topo.bound.p;
+        E.fFlag = topo.flag.p;
+        for (int x = 0; x < 3; x++) {
+            E.corner[x] = f.mra.corner[x];
+            E.nboxes[x] = f.mra.nboxes[x];
+        }
+        E.gThrs = gThrs;
+        E.fMaxNorm = fMaxNorm;
+        E.screenOn = screenOn ? 1 : 0;
+        E.gdesc = scr.gdesc.p;
+        E.nbr = scr.nbr.p;
+        E.pending = scr.pending.p;
+        E.cnt = scr.ecnt.p;
+        launch_enum(E, st);
+        EnumCounters ec;
+        MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        const int nNbr = ec.nNbr;
+        const long long nCand = (long long)ec.nCand;
+        if (nCand >= (1ll << 31)) MRX_ABORT("apply: candidate space of one iteration exceeds 2^31");
+        const int nPending = ec.nPending;
+        while (nPending > 0) { // generated input nodes, one round per missing level
+            scr.newParents.reserve(nPending, false, st);
+            scr.genItems.reserve((size_t)2 * nPending, false, st);
+            E.newParents = scr.newParents.p;
+            E.genItems = scr.genItems.p;
+            MRX_CUDA(cudaMemsetAsync(&scr.ecnt.p->nUnresolved, 0, 2 * sizeof(int), st)); // nUnresolved, nNewParents
+            launch_enum_resolve(E, nPending, st);
+            MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
+            MRX_CUDA(cudaStreamSynchronize(st));
+            if (ec.nUnresolved == 0) break;
+            const int nNew = ec.nNewParents;
+            topo.reserve((size_t)fTotal + 8 * (size_t)nNew, st);
+            E.fChild0 = topo.child0.p;
+            E.fDepth = topo.depth.p;
+            E.fBound = topo.bound.p;
+            E.fFlag = topo.flag.p;
+            inp.dev.genCoefs.reserve((size_t)(fTotal - fRealN + 8 * nNew) * Kd, true, st);
+            inp.dev.genNorms.reserve((size_t)(fTotal - fRealN + 8 * nNew), true, st);
+            launch_enum_create(E, nNew, fTotal, st);
+            launch_gen_children(inp.dev.coefs.p, inp.dev.genCoefs.p, inp.dev.genNorms.p, fRealN, scr.genItems.p, nNew, K, filt, st);
+            fTotal += 8 * nNew;
+            S.gen_nodes += 8 * (long long)nNew;
+            inp.dev.nGen = fTotal - fRealN;
+        }
+        tp_gen += now_ms() - tq;
+        tq = now_ms();
+        // ---- device storage for the output nodes of this iteration
+        out.dev.coefs.reserve((size_t)nRealDev * ncoef, true, st);
+        out.dev.norms.reserve((size_t)nRealDev * 8, true, st);
+        out.dev.nNodes = nRealDev;
+
+        ApplyParams P{};
+        P.fReal = inp.dev.coefs.p;
+        P.fGen = inp.dev.genCoefs.p;
+        P.fNorms = inp.dev.norms.p;
+        P.fGenNorms = inp.dev.genNorms.p;
+        P.nRealF = fRealN;
+        P.gCoefs = out.dev.coefs.p;
+        P.gdesc = scr.gdesc.p; // node-level descriptors: balancing happens on the device
+        P.partials = nullptr;
+        P.nbr = scr.nbr.p;
+        P.mats = oper.dev.mats.p;
+        P.onorms = oper.dev.norms.p;
+        P.nodeBase = oper.dev.nodeBase.p;
+        P.bsf = oper.dev.bsf.p;
+        P.bsfSep = reinterpret_cast<const int4 *>(oper.dev.bw.p);
+        P.depthInfo = bt.d_info.p;
+        P.candOff = bt.d_candOff.p;
+        P.candTerm = bt.d_candTerm.p;
+        P.candMask = bt.d_candMask.p;
+        P.M = M;
+        P.DM = DM;
+        P.K = K;
+        P.gThrs = gThrs;
+        P.counters = scr.counters.p;
+        P.derivDir = derivDir;
+        P.identIdx = oper.dev.identIdx;
+
+        MRX_CUDA(cudaEventRecord(ev0, st));
+        scr.masks.reserve(std::max<long long>(nCand, 1), false, st);
+        scr.cnt64.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
+        scr.segOff.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
+        scr.blockCnt.reserve((size_t)nL * 8 + 8, false, st);
+        scr.blockTupOff.reserve((size_t)nL * 8 + 9, false, st);
+        scr.blockUnitOff.reserve((size_t)nL * 8 + 9, false, st);
+        DevBuf<double> &normsBuf = scr.normsW[world > 1 ? b : 0];
+        normsBuf.reserve((size_t)world * rowsPerRank * 8 + 8, false, st);
+        scr.header.reserve(1, false, st);
+        scr.queue.reserve(1, false, st);
+        PipeBuffers B{};
+        B.masks = scr.masks.p;
+        B.cnt64 = scr.cnt64.p;
+        B.segOff = scr.segOff.p;
+        B.blockCnt = scr.blockCnt.p;
+        B.blockTupOff = scr.blockTupOff.p;
+        B.blockUnitOff = scr.blockUnitOff.p;
+        B.header = scr.header.p;
+        B.queue = scr.queue.p;
+        launch_pipe_screen(P, B, nNbr, st);
+        launch_pipe_scan(P, B, nL, unitTuples, st);
+        PipeHeader hdr;
+        MRX_CUDA(cudaMemcpyAsync(&hdr, scr.header.p, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        if (hdr.totalTuples >= (1ull << 32)) MRX_ABORT("apply: tuple list of one iteration exceeds 2^32 records");
+        scr.tuples.reserve(std::max<size_t>((size_t)hdr.totalTuples, 1), false, st);
+        scr.units2.reserve(std::max<size_t>((size_t)hdr.nUnits, 1), false, st);
+        scr.partials.reserve(std::max<size_t>((size_t)hdr.nUnits * Kd, 1), false, st);
+        B.tuples = scr.tuples.p;
+        B.units = scr.units2.p;
+        B.partials = scr.partials.p;
+        launch_pipe_fill(P, B, nNbr, nL, st);
+        MRX_CUDA(cudaEventRecord(ev2, st));
+        launch_pipe_contract(P, B, hdr.nUnits, st);
+        MRX_CUDA(cudaEventRecord(ev3, st));
+        // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
+        double *normsMine = normsBuf.p + (size_t)rank * rowsPerRank * 8;
+        if (world == 1) {
+            launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
+            MRX_CUDA(cudaEventRecord(ev1, st));
+        } else {
+            // ---- exchange over NVLink. Output blocks: the reduce kernel writes this rank's rows of a rank-major staging
+            //      buffer; copy engines push them into every peer's HBM (CUDA IPC mapping) on a second stream while
+            //      the next iteration already runs, and the whole iteration is unpacked into the node store one
+            //      iteration later. Norms (8 doubles per node, the input of the split decision that every rank takes
+            //      identically) go through one in-place ncclAllGather, which is also the only cross-rank
+            //      synchronisation: a rank enters it only after its previous push has completed, so whoever leaves it
+            //      knows that the previous iteration's rows of all peers have landed.
+            const size_t rowBytes = (size_t)ncoef * sizeof(double);
+            const size_t segBytes = (size_t)rowsPerRank * rowBytes;
+            if ((size_t)world * segBytes > comm_stage_bytes(comm)) {
+                flush_pending();
+                comm_stage_reserve(comm, (size_t)world * segBytes, st);
+            }
+            const bool push = comm_peer_push_enabled(comm);
+            double *stageB = reinterpret_cast<double *>(comm_stage(comm, b));
+            launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st,
+                               reinterpret_cast<double *>(comm_stage(comm, b) + (size_t)rank * segBytes));
+            MRX_CUDA(cudaEventRecord(ev1, st));
+            if (push) {
+                MRX_CUDA(cudaEventRecord(comm_ev_reduced(comm, b), st));
+                comm_push(comm, b, (size_t)rank * segBytes, (size_t)nL * rowBytes);
+                if (pend.active) MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
+                comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
+                if (pend.active)
+                    launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)),
+                                        scr.gslotsAll[pend.buf].p, pend.nG, world, pend.rows, ncoef, scr.normsW[pend.buf].p,
+                                        out.dev.norms.p, st);
+                pend.active = true;
+                pend.buf = b;
+                pend.nG = nG;
+                pend.rows = rowsPerRank;
+            } else {
+                comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
+                comm_allgather(comm, stageB, segBytes, st);
+                launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, normsBuf.p,
+                                    out.dev.norms.p, st);
+            }
+        }
+        // ---- the device is busy for a while: replay earlier split decisions into the host topology, build the band
+        //      tables of the depths the next work vector can hold
+        double tr = now_ms();
+        replay_pending();
+        const bool doSplit = !deriv && !(iter >= maxIter && maxIter >= 0);
+        if (doSplit) {
+            for (int dep = std::max(minDep + 1, 0); dep <= maxDep + 1 && dep < DM; dep++)
+                if (!bt.built[dep]) bt.build(op, dep, derivDir, bsf, DM);
+            upload_band_tables(bt, DM, true, st); // synchronises only when a depth is new for this (operator, prec)
+        }
+        tp_replay += now_ms() - tr;
+        // ---- TreeBuilder bookkeeping, split decisions and the next work vector on the device (apply_split.cu)
+        const int nb = (iter + 1) % kCommStageBufs;
+        scr.gAll[cur ^ 1].reserve((size_t)8 * nG, false, st);
+        scr.gslotsAll[nb].reserve((size_t)8 * nG, false, st);
+        scr.flags.reserve(nG, false, st);
+        SplitParams SP{};
+        SP.normRows = normsBuf.p;
+        SP.nG = nG;
+        SP.world = world;
+        SP.rows = rowsPerRank;
+        SP.gNodesAll = scr.gAll[cur].p;
+        SP.isBranch = (iter == 0 && scr.hasBranchFlags) ? scr.isBranch.p : nullptr;
+        SP.operRoot = op.operRoot;
+        SP.rootScale = g.mra.rootScale;
+        SP.maxScale = maxScale;
+        SP.scaleFac = scr.scaleFac.p;
+        SP.prec = prec;
+        SP.absPrec = absPrec ? 1 : 0;
+        SP.iter = iter;
+        SP.doSplit = doSplit ? 1 : 0;
+        SP.slotBase = nRealDev;
+        SP.state = scr.state.p;
+        SP.gNodesNext = scr.gAll[cur ^ 1].p;
+        SP.slotsNext = scr.gslotsAll[nb].p;
+        SP.flags = scr.flags.p;
+        SP.res = scr.splitRes.p;
+        launch_split(SP, st);
+        prep_local(cur ^ 1, nb, -1);
+        Replay R;
+        R.flags.resize(nG);
+        R.slotBase = nRealDev;
+        MRX_CUDA(cudaMemcpyAsync(&res, scr.splitRes.p, sizeof(res), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaMemcpyAsync(R.flags.data(), scr.flags.p, nG, cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        tp_wait += now_ms() - tq;
+        tq = now_ms();
+        if (!doSplit) std::fill(R.flags.begin(), R.flags.end(), 0);
+        replay.push_back(std::move(R));
+        float ms = 0.f, msc = 0.f;
+        MRX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        MRX_CUDA(cudaEventElapsedTime(&msc, ev2, ev3));
+        kernel_ms += ms;
+        contract_ms += msc;
+        tuplesTotal += (long long)hdr.totalTuples;
+        if (profile)
+            std::fprintf(stderr, "[mrx] iter %d nG %d nbr %d cand %lld tuples %llu kernels %.3f ms (contract %.3f ms, %.2f TF/s) split %d\n", iter,
+                         nG, nNbr, nCand, hdr.totalTuples, ms, msc,
+                         msc > 0 ? hdr.totalTuples * 6.0 * K * K * K * K / (msc * 1e-3) / 1e12 : 0.0, res.nSplit);
+        S.g_nodes += nG;
+        g.squareNorm = res.squareNorm; // TreeBuilder.cpp:56-66
+        nRealDev += res.nNext;
+        nG = res.nNext;
+        minDep += 1;
+        maxDep += 1;
+        cur ^= 1;
+        iter++;
+        tp_split += now_ms() - tq;
+    }
+    if (world > 1) flush_pending();
+    replay_pending();
+    if (g.nReal != nRealDev) MRX_ABORT("apply: host topology and device node store disagree");
+    const double tLoopEnd = now_ms();
+    if (profile) {
+        std::fprintf(stderr, "[mrx] run_apply_pipe ms: pre-loop %.2f loop %.2f\n", tLoop - tEnter, tLoopEnd - tLoop);
+        std::fprintf(stderr, "[mrx] host phases ms: enum+gen %.2f screen..split (device wait) %.2f of which replay/tables %.2f, bookkeeping %.2f\n",
+                     tp_gen, tp_wait, tp_replay, tp_split);
+    }
+    S.iterations = iter;
+    S.ms_kernel = kernel_ms;
+    S.ms_contract = contract_ms;
+    S.f_applied = tuplesTotal;
+    S.f_applied_rank = S.f_applied;
+    if (world > 1) {
+        double h[2] = {(double)S.f_applied, (double)S.gen_nodes};
+        double *dsum = reinterpret_cast<double *>(scr.counters.p + 2);
+        MRX_CUDA(cudaMemcpyAsync(dsum, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        comm_allreduce_sum(comm, dsum, 2, st);
+        MRX_CUDA(cudaMemcpyAsync(h, dsum, sizeof(h), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        S.f_applied = (long long)(h[0] + 0.5);
+        S.gen_nodes = (long long)(h[1] + 0.5);
+    }
+    out.dev.nNodes = g.nReal;
+    MRX_CUDA(cudaEventDestroy(ev0));
+    MRX_CUDA(cudaEventDestroy(ev1));
+    MRX_CUDA(cudaEventDestroy(ev2));
+    MRX_CUDA(cudaEventDestroy(ev3));
+}
+
+static bool use_pipeline(const mrx_tree &out) {
+    const char *legacy = getenv("MRX_LEGACY");
+    return pipe_supports_order(out.host.K) && !(legacy && legacy[0] == '1');
+}
+
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
                   mrx_apply_stats *stats, const mrx_comm *comm) {
     require_device("device_apply");
@@ -1021,7 +1520,8 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     double tb = now_ms();
     std::vector<int> workVec;
     out.host.nodeTable(workVec); // getInitialWorkVector: ALL nodes of `out` (ConvolutionCalculator.cpp:400-405)
-    run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
+    if (use_pipeline(out)) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
+    else run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
     S.ms_build = now_ms() - tb;
 
     // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)
@@ -1093,7 +1593,8 @@ void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int d
     out.dev.coefs.reserve((size_t)g.nReal * g.ncoef, false, st);
     out.dev.norms.reserve((size_t)g.nReal * 8, false, st);
     MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p, 0, sizeof(double) * (size_t)g.nReal * g.ncoef, st));
-    run_apply(-1.0, out, oper, inp, 0, false, dir, workVec, S);
+    if (use_pipeline(out)) run_apply_pipe(-1.0, out, oper, inp, 0, false, dir, workVec, S, nullptr);
+    else run_apply(-1.0, out, oper, inp, 0, false, dir, workVec, S);
     S.ms_build = now_ms() - tb;
     double tp = now_ms();
     op.clearBandWidths();

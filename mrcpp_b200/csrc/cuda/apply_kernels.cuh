@@ -157,4 +157,43 @@ void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *g
 void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
                          const double *normRows, double *gNorms, cudaStream_t st);
 
+// ---- refinement step on the device (apply_split.cu) ------------------------------------------------------
+struct SplitResult {
+    double squareNorm, sNorm, wNorm; // TreeBuilder bookkeeping after this iteration
+    int nSplit, nNext;               // nodes that split; size of the next work vector (8 nSplit)
+    int nLoc, nChunksLoc;            // prep_local: this rank's items and probe chunks of the (next) work vector
+    long long nbrCapLoc;             // upper bound of its neighbour list
+};
+struct SplitParams {
+    const double *normRows; // component norms of the iteration, rank-major rows of 8 (item i = row (i % world) * rows + i / world)
+    int nG, world, rows;
+    const int4 *gNodesAll;          // [nG] (operator depth, lx, ly, lz) in work-vector order
+    const unsigned char *isBranch;  // [nG] or nullptr (no item is a branch node)
+    int operRoot, rootScale, maxScale;
+    const double *scaleFac;         // [depth] 2^{-(scale+1)/2} as the host's std::pow gives it (split_check)
+    double prec;
+    int absPrec, iter, doSplit;
+    int slotBase;                   // slot of the first child created by this iteration
+    double *state;                  // [3] sNorm, wNorm, squareNorm carried across iterations
+    int4 *gNodesNext;               // [8 nSplit] next work vector
+    int *slotsNext;
+    unsigned char *flags;           // [nG] split decisions (host replays them into its topology)
+    SplitResult *res;
+};
+struct PrepParams {
+    int nG;                  // >= 0: given by the host; < 0: read res->nNext (written by split_kernel just before)
+    int world, rank;
+    const int4 *gNodesAll;
+    const int *slotsAll;
+    const int *offCount;     // [DM] reachable offsets per depth (band tables)
+    const DepthInfo *depthInfo;
+    int DM;
+    int4 *gNodesLoc;         // this rank's items (i = rank + j world)
+    int *slotsLoc;
+    int *chunkOffLoc;        // [nLoc+1]
+    SplitResult *res;
+};
+void launch_split(const SplitParams &S, cudaStream_t st);
+void launch_prep_local(const PrepParams &P, cudaStream_t st);
+
 } // namespace mrx

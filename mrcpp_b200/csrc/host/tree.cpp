@@ -276,7 +276,7 @@ template <int D> double Tree<D>::waveletNorm(int n) const {
     double w = 0.0;
     for (int i = 1; i < tdim; i++) {
         double norm_i = cnorm[(size_t)n * tdim + i];
-        if (norm_i >= 0.0) w += norm_i * norm_i;
+        if (norm_i >= 0.0) w = std::fma(norm_i, norm_i, w); // explicit: the device restates this sum (apply_split.cu)
         else w = -1.0;
     }
     return w;
