@@ -91,6 +91,8 @@ struct Scratch {
     DevBuf<unsigned> blockTupOff;
     DevBuf<int> blockUnitOff;
     DevBuf<PipeHeader> header;
+    DevBuf<unsigned long long> pTileTotal, pTileBaseTup;
+    DevBuf<int> pTileBaseUnit;
     DevBuf<TupleRec> tuples;
     DevBuf<UnitDesc> units2;
     DevBuf<int> queue;
@@ -833,7 +835,13 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             B.blockCnt = scr.blockCnt.p;
             B.blockTupOff = scr.blockTupOff.p;
             B.blockUnitOff = scr.blockUnitOff.p;
-            B.header = scr.header.p;
+            scr.pTileTotal.reserve((size_t)nL * 8 / 2048 + 2, false, st);
+        scr.pTileBaseTup.reserve((size_t)nL * 8 / 2048 + 2, false, st);
+        scr.pTileBaseUnit.reserve((size_t)nL * 8 / 2048 + 2, false, st);
+        B.tileTotal = scr.pTileTotal.p;
+        B.tileBaseTup = scr.pTileBaseTup.p;
+        B.tileBaseUnit = scr.pTileBaseUnit.p;
+        B.header = scr.header.p;
             B.queue = scr.queue.p;
             scM.~SlowCall();
             scM.on = false;
@@ -1338,6 +1346,12 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         B.blockCnt = scr.blockCnt.p;
         B.blockTupOff = scr.blockTupOff.p;
         B.blockUnitOff = scr.blockUnitOff.p;
+        scr.pTileTotal.reserve((size_t)nL * 8 / 2048 + 2, false, st);
+        scr.pTileBaseTup.reserve((size_t)nL * 8 / 2048 + 2, false, st);
+        scr.pTileBaseUnit.reserve((size_t)nL * 8 / 2048 + 2, false, st);
+        B.tileTotal = scr.pTileTotal.p;
+        B.tileBaseTup = scr.pTileBaseTup.p;
+        B.tileBaseUnit = scr.pTileBaseUnit.p;
         B.header = scr.header.p;
         B.queue = scr.queue.p;
         launch_pipe_screen(P, B, nNbr, st);

@@ -170,7 +170,7 @@ __device__ unsigned long long block_excl_scan(unsigned long long v, unsigned lon
     if (lane == 31) sm[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long s = sm[lane];
+        unsigned long long s = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0ull;
         unsigned long long si = s;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -187,36 +187,63 @@ __device__ unsigned long long block_excl_scan(unsigned long long v, unsigned lon
     return res;
 }
 
-__global__ void __launch_bounds__(1024) pipe_blockscan_kernel(PipeBuffers B, int nBlocks, int unitHint) {
+// Offsets of the output blocks in the tuple list and in the unit list. Two levels: tiles of kBlockTile blocks are scanned
+// by one CTA each (coalesced), one CTA scans the tile totals and writes the header; pipe_units_kernel adds the tile bases.
+// Unit size: fixed, so that the summation order of a block does not depend on how much other work the launch holds
+// (results are bit-identical for any number of ranks sharing the work vector).
+constexpr int kBlockTile = 2048; // 256 threads x 8 blocks
+
+__global__ void __launch_bounds__(256) pipe_blockscan_tiles_kernel(PipeBuffers B, int nBlocks, int U) {
+    __shared__ unsigned long long sm[33];
+    const int base = blockIdx.x * kBlockTile + threadIdx.x * 8;
+    // low 40 bits: tuples, high 24 bits: units of the tile (a tile holds < 2^24 units and < 2^40 tuples)
+    unsigned long long v[8], local = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned long long c = (base + i < nBlocks) ? (unsigned long long)B.blockCnt[base + i] : 0ull;
+        v[i] = c | (((c + U - 1) / U) << 40);
+        local += v[i];
+    }
+    unsigned long long total;
+    unsigned long long run = block_excl_scan(local, sm, total);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (base + i < nBlocks) {
+            B.blockTupOff[base + i] = (unsigned)(run & ((1ull << 40) - 1));
+            B.blockUnitOff[base + i] = (int)(run >> 40);
+        }
+        run += v[i];
+    }
+    if (threadIdx.x == 0) B.tileTotal[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) pipe_blockscan_top_kernel(PipeBuffers B, int nBlocks, int nTiles, int U) {
     __shared__ unsigned long long sm[33];
     const int tid = threadIdx.x;
-    const int per = (nBlocks + 1023) / 1024;
-    const int b0 = min(tid * per, nBlocks), b1 = min(b0 + per, nBlocks);
-    unsigned long long local = 0;
-    for (int b = b0; b < b1; b++) local += (unsigned long long)B.blockCnt[b];
-    unsigned long long total;
-    unsigned long long off = block_excl_scan(local, sm, total);
+    const int per = (nTiles + 1023) / 1024;
+    const int b0 = min(tid * per, nTiles), b1 = min(b0 + per, nTiles);
+    unsigned long long locT = 0, locU = 0;
     for (int b = b0; b < b1; b++) {
-        B.blockTupOff[b] = (unsigned)off;
-        off += (unsigned long long)B.blockCnt[b];
+        const unsigned long long t = B.tileTotal[b];
+        locT += t & ((1ull << 40) - 1);
+        locU += t >> 40;
     }
-    // unit size: fixed, so that the summation order of a block does not depend on how much other work the launch
-    // holds (results are bit-identical for any number of ranks sharing the work vector)
-    const long long U = unitHint;
-    local = 0;
-    for (int b = b0; b < b1; b++) local += (unsigned long long)((B.blockCnt[b] + U - 1) / U);
-    unsigned long long totalUnits;
-    off = block_excl_scan(local, sm, totalUnits);
+    unsigned long long totT, totU;
+    unsigned long long runT = block_excl_scan(locT, sm, totT);
+    unsigned long long runU = block_excl_scan(locU, sm, totU);
     for (int b = b0; b < b1; b++) {
-        B.blockUnitOff[b] = (int)off;
-        off += (unsigned long long)((B.blockCnt[b] + U - 1) / U);
+        const unsigned long long t = B.tileTotal[b];
+        B.tileBaseTup[b] = runT;
+        B.tileBaseUnit[b] = (int)runU;
+        runT += t & ((1ull << 40) - 1);
+        runU += t >> 40;
     }
     if (tid == 0) {
-        B.blockTupOff[nBlocks] = (unsigned)total;
-        B.blockUnitOff[nBlocks] = (int)totalUnits;
-        B.header->totalTuples = total;
-        B.header->nUnits = (int)totalUnits;
-        B.header->U = (int)U;
+        B.blockTupOff[nBlocks] = (unsigned)totT;
+        B.blockUnitOff[nBlocks] = (int)totU;
+        B.header->totalTuples = totT;
+        B.header->nUnits = (int)totU;
+        B.header->U = U;
     }
 }
 
@@ -226,8 +253,14 @@ __global__ void __launch_bounds__(256) pipe_units_kernel(PipeBuffers B, int nBlo
     if (blk >= nBlocks) return;
     const int U = B.header->U;
     const int cnt = B.blockCnt[blk];
-    const unsigned t0 = B.blockTupOff[blk];
-    const int u0 = B.blockUnitOff[blk];
+    // tile-local offsets -> global offsets (each entry is read and rewritten by its own warp only)
+    const unsigned t0 = B.blockTupOff[blk] + (unsigned)B.tileBaseTup[blk / kBlockTile];
+    const int u0 = B.blockUnitOff[blk] + B.tileBaseUnit[blk / kBlockTile];
+    __syncwarp();
+    if (lane == 0) {
+        B.blockTupOff[blk] = t0;
+        B.blockUnitOff[blk] = u0;
+    }
     const int nu = (cnt + U - 1) / U;
     for (int u = lane; u < nu; u += 32) {
         UnitDesc d;
@@ -658,10 +691,15 @@ void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cu
 
 void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st) {
     const int nBlocks = nG * 8;
-    if (nBlocks > 0) pipe_segscan_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(P, B, nBlocks);
-    pipe_blockscan_kernel<<<1, 1024, 0, st>>>(B, nBlocks, unitHint);
+    const int nTiles = (nBlocks + kBlockTile - 1) / kBlockTile;
+    if (nBlocks > 0) {
+        pipe_segscan_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(P, B, nBlocks);
+        pipe_blockscan_tiles_kernel<<<nTiles, 256, 0, st>>>(B, nBlocks, unitHint);
+        launch_counter() += 2;
+    }
+    pipe_blockscan_top_kernel<<<1, 1024, 0, st>>>(B, nBlocks, nTiles, unitHint);
     MRX_CUDA(cudaGetLastError());
-    launch_counter() += 2;
+    launch_counter()++;
 }
 
 void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st) {
