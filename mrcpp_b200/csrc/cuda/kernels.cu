@@ -269,6 +269,213 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Even orders K = 4, 6, 8, 10, 12: two-scale transform on the FP64 tensor cores, one CTA (8 warps) per node.
+// A pass contracts dimension p together with bit p of the block index: with the 2K x 2K two-scale matrix
+//   F2[(b, t)][(gbit, j)] = F[2 gbit + b](t, j)                      (math_utils::apply_filter, math_utils.cpp:175-194)
+// it is the GEMM  out[(gbit, j)][col] = sum_(b,t) F2[(b,t)][(gbit,j)] in[(b,t)][col]  over the 4 K^2 columns (the two other
+// indices x the two other block bits). Treating the four K x K filter blocks as ONE 2K x 2K operand removes most of the tile
+// padding: M = 2K rows in tiles of 8 (K = 12: 100 %, 10: 83 %, 6: 75 % useful), inner dimension 2K = K/2 steps of 4, exact.
+// The node lives in shared memory for the three passes, which run IN PLACE (a column's outputs only replace that column's
+// inputs, and a warp owns whole columns); the last pass writes its D fragments straight to global memory.
+// Shared layout: element (blk, i0, i1, i2) at SB blk + i0 + S1 i1 + S2 i2 with S1 = 12 (mod 16), S2 = 4 or 12 (mod 16),
+// SB = 2 (mod 16): with the column tiles chosen below (an index pair x two block bits) the fragment loads of all three
+// passes and the fragment stores of passes 0 and 1 are free of bank conflicts.
+constexpr int next_mod16(int x, int m) { return x + ((m - x % 16) + 16) % 16; }
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+template <int K> struct TLayout {
+    static constexpr int K2 = K * K, Kd = K2 * K;
+    static constexpr int S1 = (K == 4) ? 4 : 12;
+    static constexpr int S2 = cmin(next_mod16((K - 1) * S1 + K, 4), next_mod16((K - 1) * S1 + K, 12));
+    static constexpr int SB = next_mod16((K - 1) * S2 + (K - 1) * S1 + K, 2);
+    static constexpr int MT = (2 * K + 7) / 8, KS = K / 2, NT = K2 / 2;
+    static constexpr size_t bytes = (size_t)8 * SB * sizeof(double);
+};
+
+// MODE 0: TopDown; 1: BottomUp; 2: generated children (+ norms); 3: in-node compression
+template <int K, int MODE>
+__global__ void __launch_bounds__(256) transformK_kernel(double *__restrict__ coefs, const double *__restrict__ realCoefs,
+                                                         double *__restrict__ genCoefs, double *__restrict__ genNorms, int nReal,
+                                                         const int *__restrict__ pairs, const double *__restrict__ filters, int overwrite,
+                                                         double *__restrict__ norms) {
+    using L = TLayout<K>;
+    constexpr int K2 = L::K2, Kd = L::Kd, ncoef = 8 * Kd, S1 = L::S1, S2 = L::S2, SB = L::SB, MT = L::MT, KS = L::KS, NT = L::NT;
+    extern __shared__ __align__(16) double smK[];
+    __shared__ double sN[8][8];
+    const int parent = pairs[2 * blockIdx.x];
+    const int child0 = pairs[2 * blockIdx.x + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    // ---- filter fragments: A[row = (gbit, j)][kc = (b, t)] = F[2 gbit + b](t, j)
+    const double *F = filters + (size_t)((MODE == 1 || MODE == 3) ? 0 : 1) * 4 * K2;
+    double a[MT][KS];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int row = 8 * mt + r, kc = 4 * s + q;
+            a[mt][s] = (row < 2 * K) ? F[(2 * (row / K) + kc / K) * K2 + (kc % K) * K + row % K] : 0.0;
+        }
+    // ---- stage the node: 16-byte coalesced loads into the padded layout
+    for (int e = tid; e < 4 * Kd; e += 256) {
+        const int blk = e / (Kd / 2), rem = 2 * (e - blk * (Kd / 2));
+        const int i0 = rem % K, i1 = (rem / K) % K, i2 = rem / K2;
+        double2 v;
+        if (MODE == 0 || MODE == 3) {
+            v = *reinterpret_cast<const double2 *>(coefs + (size_t)parent * ncoef + (size_t)blk * Kd + rem);
+        } else if (MODE == 1) {
+            v = *reinterpret_cast<const double2 *>(coefs + (size_t)(child0 + blk) * ncoef + rem);
+        } else {
+            if (parent < nReal) v = *reinterpret_cast<const double2 *>(realCoefs + (size_t)parent * ncoef + (size_t)blk * Kd + rem);
+            else v = (blk == 0) ? *reinterpret_cast<const double2 *>(genCoefs + (size_t)(parent - nReal) * Kd + rem) : make_double2(0.0, 0.0);
+        }
+        *reinterpret_cast<double2 *>(smK + SB * blk + i0 + S1 * i1 + S2 * i2) = v;
+    }
+    __syncthreads();
+    // ---- pass 0: contract i0 / block bit 0. Tile = (i1 pair, fixed i2) x (bit 1, bit 2); column c = bit1 + 2 bit2 + 4 e1
+    for (int tile = warp; tile < NT; tile += 8) {
+        const int pa = tile % (K / 2), i2 = tile / (K / 2);
+        const int cb = S1 * (2 * pa + (r >> 2)) + S2 * i2 + SB * (2 * (r & 1) + 4 * ((r >> 1) & 1));
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int kc = 4 * s + q;
+            bf[s] = smK[cb + kc % K + SB * (kc / K)];
+        }
+        // D columns 2q, 2q+1: bit1 = 0 / 1, bit2 = q & 1, e1 = q >> 1
+        const int ob = S1 * (2 * pa + (q >> 1)) + S2 * i2 + SB * (4 * (q & 1));
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; s++) dmma884(d0, d1, a[mt][s], bf[s]);
+            const int row = 8 * mt + r;
+            if (row < 2 * K) {
+                const int o = ob + row % K + SB * (row / K);
+                smK[o] = d0;
+                smK[o + 2 * SB] = d1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- pass 1: contract i1 / block bit 1. Tile = (i0 pair, fixed i2) x (bit 0, bit 2); column c = e0 + 2 bit0 + 4 bit2
+    for (int tile = warp; tile < NT; tile += 8) {
+        const int pa = tile % (K / 2), i2 = tile / (K / 2);
+        const int cb = 2 * pa + (r & 1) + S2 * i2 + SB * (((r >> 1) & 1) + 4 * (r >> 2));
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int kc = 4 * s + q;
+            bf[s] = smK[cb + S1 * (kc % K) + 2 * SB * (kc / K)];
+        }
+        const int ob = 2 * pa + S2 * i2 + SB * ((q & 1) + 4 * (q >> 1)); // columns 2q, 2q+1 = the i0 pair
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; s++) dmma884(d0, d1, a[mt][s], bf[s]);
+            const int row = 8 * mt + r;
+            if (row < 2 * K) *reinterpret_cast<double2 *>(smK + ob + S1 * (row % K) + 2 * SB * (row / K)) = make_double2(d0, d1);
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: contract i2 / block bit 2, results to global. Tile = (i0 pair, fixed i1) x (bit 0, bit 1)
+    double n2a = 0.0, n2b = 0.0; // square norm contributions to the blocks gt = q (gbit 0) and q + 4 (gbit 1)
+    for (int tile = warp; tile < NT; tile += 8) {
+        const int pa = tile % (K / 2), i1 = tile / (K / 2);
+        const int cb = 2 * pa + (r & 1) + S1 * i1 + SB * (((r >> 1) & 1) + 2 * (r >> 2));
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int kc = 4 * s + q;
+            bf[s] = smK[cb + S2 * (kc % K) + 4 * SB * (kc / K)];
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; s++) dmma884(d0, d1, a[mt][s], bf[s]);
+            const int row = 8 * mt + r;
+            if (row < 2 * K) {
+                const int gbit = row / K, j = row % K;
+                const int gt = q + 4 * gbit; // bit0 = q & 1, bit1 = q >> 1
+                const int elem = 2 * pa + K * i1 + K2 * j;
+                double *dst;
+                if (MODE == 0) dst = coefs + (size_t)(child0 + gt) * ncoef + elem;
+                else if (MODE == 2) dst = genCoefs + (size_t)(child0 - nReal + gt) * Kd + elem;
+                else dst = coefs + (size_t)parent * ncoef + (size_t)gt * Kd + elem;
+                if (MODE == 0 && !overwrite) {
+                    const double2 o = *reinterpret_cast<const double2 *>(dst);
+                    d0 += o.x;
+                    d1 += o.y;
+                }
+                *reinterpret_cast<double2 *>(dst) = make_double2(d0, d1);
+                const double c2 = fma(d1, d1, d0 * d0);
+                if (gbit) n2b += c2;
+                else n2a += c2;
+            }
+        }
+    }
+    // ---- norms of the eight blocks written (fixed reduction shape: deterministic)
+    if (norms != nullptr || MODE == 2) {
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            double v = g ? n2b : n2a;
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (r == 0) sN[warp][q + 4 * g] = v;
+        }
+        __syncthreads();
+        if (tid < 8) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) v += sN[w][tid];
+            const double nrm = sqrt(v);
+            if (MODE == 2) genNorms[child0 - nReal + tid] = nrm;
+            else if (MODE == 0) norms[(size_t)(child0 + tid) * 8] = nrm;
+            else norms[(size_t)parent * 8 + tid] = nrm;
+        }
+    }
+    if (MODE == 0 && overwrite) {
+        // giveChildrenCoefs(overwrite=true) zeroes the children first (MWNode.cpp:317-319)
+        for (int o = tid; o < 8 * 7 * Kd / 2; o += 256) {
+            const int c = o / (7 * Kd / 2), rem = o - c * (7 * Kd / 2);
+            reinterpret_cast<double2 *>(coefs + (size_t)(child0 + c) * ncoef + Kd)[rem] = make_double2(0.0, 0.0);
+        }
+    }
+}
+
+template <int K, int MODE>
+void launch_transformK(double *coefs, const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *pairs, int cnt,
+                       const double *filters, int overwrite, double *norms, cudaStream_t st) {
+    static bool conf = false;
+    if (!conf) {
+        MRX_CUDA(cudaFuncSetAttribute(transformK_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TLayout<K>::bytes));
+        conf = true;
+    }
+    transformK_kernel<K, MODE><<<cnt, 256, TLayout<K>::bytes, st>>>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, filters, overwrite, norms);
+}
+
+// even orders served by transformK_kernel (K = 8 keeps its register-chained kernel unless MRX_TK8 is set)
+bool transformK_supports(int K) {
+    static const bool k8 = getenv("MRX_TK8") != nullptr;
+    return K == 4 || K == 6 || K == 10 || K == 12 || (K == 8 && k8);
+}
+
+template <int MODE>
+void dispatch_transformK(int K, double *coefs, const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *pairs,
+                         int cnt, const double *filters, int overwrite, double *norms, cudaStream_t st) {
+    switch (K) {
+    case 4: launch_transformK<4, MODE>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st); break;
+    case 6: launch_transformK<6, MODE>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st); break;
+    case 8: launch_transformK<8, MODE>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st); break;
+    case 10: launch_transformK<10, MODE>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st); break;
+    case 12: launch_transformK<12, MODE>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st); break;
+    default: MRX_ABORT("transformK: unsupported order");
+    }
+}
+
 __global__ void __launch_bounds__(256) norms_kernel(const double *__restrict__ coefs, double *__restrict__ norms,
                                                     const int *__restrict__ slots, int Kd, double *__restrict__ normsW) {
     int node = slots ? slots[blockIdx.x] : blockIdx.x;
@@ -351,11 +558,18 @@ void launch_norms(const double *coefs, double *norms, const int *slots, int n, i
     launch_counter()++;
 }
 
-bool transform_fuses_norms(int K) { return K == 8; }
+bool transform_fuses_norms(int K) { return K == 8 || transformK_supports(K); }
 
 void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *filters,
                       cudaStream_t st, double *norms) {
     if (cnt <= 0) return;
+    if (transformK_supports(K)) {
+        if (down) dispatch_transformK<0>(K, coefs, nullptr, nullptr, nullptr, 0, pairs, cnt, filters, overwrite ? 1 : 0, norms, st);
+        else dispatch_transformK<1>(K, coefs, nullptr, nullptr, nullptr, 0, pairs, cnt, filters, 1, norms, st);
+        MRX_CUDA(cudaGetLastError());
+        launch_counter()++;
+        return;
+    }
     if (K == 8) {
         constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
         static bool conf = false;
@@ -386,6 +600,12 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
 
 void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st, double *norms) {
     if (cnt <= 0) return;
+    if (transformK_supports(K)) {
+        dispatch_transformK<3>(K, coefs, nullptr, nullptr, nullptr, 0, pairs, cnt, filters, 1, norms, st);
+        MRX_CUDA(cudaGetLastError());
+        launch_counter()++;
+        return;
+    }
     if (K == 8) {
         constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
         static bool conf = false;
@@ -407,6 +627,12 @@ void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, cons
 void launch_gen_children(const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *items, int cnt,
                          int K, const double *filters, cudaStream_t st) {
     if (cnt <= 0) return;
+    if (transformK_supports(K) || K == 8) {
+        dispatch_transformK<2>(K, nullptr, realCoefs, genCoefs, genNorms, nReal, items, cnt, filters, 1, nullptr, st);
+        MRX_CUDA(cudaGetLastError());
+        launch_counter()++;
+        return;
+    }
     int padOn;
     size_t bytes = transform_smem(K, padOn);
     set_smem_attr<2>(bytes);

@@ -1,5 +1,6 @@
-"""C2: mwTransform(TopDown) + mwTransform(BottomUp) sweep over a projected Gaussian tree, k = 5/7/9."""
-import math, sys, time, os
+"""C2: filter kernels of mwTransform(TopDown, overwrite) / mwTransform(BottomUp) over a projected multi-centre
+Gaussian tree, k = 3..11: level launches only, CUDA events (mrx_bench_mw_transform)."""
+import ctypes as C, math, sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
@@ -7,9 +8,10 @@ import mrcpp_b200 as mw
 from mrcpp_b200 import _lib
 _lib.init()
 L = _lib.load()
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-for k in (5, 7, 9):
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+orders = [int(a) for a in sys.argv[3:]] or [3, 5, 7, 9, 11]
+for k in orders:
     prec = 1e-6
     mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
     rng = np.random.default_rng(42)
@@ -18,17 +20,14 @@ for k in (5, 7, 9):
         beta = 10.0 ** rng.uniform(1, 3)
         func.append(mw.GaussFunc(beta, (beta / math.pi) ** 1.5 / n, tuple(rng.uniform(-8, 8, 3))))
     f = mw.FunctionTree(mra)
-    mw.project(prec, f, func)
-    A = f.to_arrays()
-    nb = int((A["child0"] >= 0).sum())
+    mw.project(prec, f, func, device=True)
     K = k + 1
-    f.sync_device()
-    for kind, name in ((mw.TopDown, "TopDown"), (mw.BottomUp, "BottomUp")):
-        f.mwTransform(kind)
-        L.mrx_timer_start()
-        for r in range(reps):
-            f.mwTransform(kind)
-        ms = L.mrx_timer_stop_ms() / reps
-        gb = nb * 128 * K ** 3 / 1e9
-        print(f"k={k} {name}: nodes {len(A['scale'])} branch {nb}  {ms:.3f} ms/pass  {nb/ms/1e3:.2f} Mnodes/s  {gb/ms*1e3:.0f} GB/s algorithmic  "
-              f"{nb*96*K**4/ms/1e9:.2f} TFLOP/s", flush=True)
+    nb = C.c_int(0)
+    for kind, name in ((0, "TopDown(overwrite)"), (1, "BottomUp")):
+        L.mrx_bench_mw_transform(f._h, kind, 2, C.byref(nb))
+        ms = L.mrx_bench_mw_transform(f._h, kind, reps, C.byref(nb))
+        gb = nb.value * 128 * K ** 3 / 1e9
+        real = gb * (4.5 if kind == 0 else 1.0)  # TopDown(overwrite) also zeroes 7 wavelet blocks of every child
+        print(f"k={k} {name}: nodes {f.getNNodes()} parents {nb.value}  {ms:.3f} ms/pass  {nb.value/ms/1e3:.2f} Mnodes/s  "
+              f"{gb/ms*1e3:.0f} GB/s algorithmic ({real/ms*1e3:.0f} GB/s moved)  {nb.value*96*K**4/ms/1e9:.2f} TFLOP/s", flush=True)
+    del f
