@@ -8,8 +8,9 @@ with a fresh output tree each step.
 
   value  output nodes/s (calcNode invocations over all refinement iterations / device time), inputs
          resident in HBM when the timed region starts.
-  e2e    same metric through the C-ABI with HOST buffers: the input tree is uploaded and the result
-         tree downloaded inside the timed region.
+  e2e    same metric through the C-ABI with HOST buffers: the input tree starts in pinned host memory (the apply
+         gathers the nodes it reads over PCIe, h2d_bytes_per_step is what actually crossed) and the result tree is
+         downloaded inside the timed region.
   roofline  dominant kernel = the contraction kernel (apply_dmma8_kernel): algorithmic flops =
          surviving tuples x 6 (k+1)^4, divided by the kernel's CUDA-event time; peak = FP64 tensor
          (DMMA) rate measured in this run (MEASURED_PEAKS.json has no FP64 entry).
@@ -284,7 +285,7 @@ def main():
         st, ms, nb_out = one_step(True)
         e2e_ms += ms
         e2e_nodes += st.g_nodes
-        h2d = ft.nbytes()
+        h2d = st.h2d_bytes  # counted by the library: coefficient blocks gathered from host memory + norms + topology
         d2h = nb_out
     barrier()
 

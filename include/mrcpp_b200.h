@@ -42,6 +42,7 @@ typedef struct mrx_apply_stats {
     double ms_download;    /* device->host copy of the result                                           */
     long long kernel_launches; /* CUDA kernels launched by this call                                    */
     long long f_applied_rank;  /* sharded apply: tuples contracted by THIS rank (f_applied = sum over ranks) */
+    long long h2d_bytes;       /* input-tree bytes this call moved host -> device (0 if the input was resident)     */
 } mrx_apply_stats;
 
 /* ---- library / device ------------------------------------------------------------------------ */

@@ -26,6 +26,7 @@ class ApplyStats(C.Structure):
         ("ms_download", C.c_double),
         ("kernel_launches", C.c_longlong),
         ("f_applied_rank", C.c_longlong),
+        ("h2d_bytes", C.c_longlong),
     ]
 
     def as_dict(self):

@@ -184,6 +184,7 @@ void mrx_tree_clear(mrx_tree *tree) {
     tree->dev.nNodes = 0;
     tree->dev.nGen = 0;
     tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
 }
 long long mrx_tree_bytes(const mrx_tree *tree) { return (long long)tree->host.nReal * tree->host.ncoef * 8; }
 
@@ -241,6 +242,7 @@ int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp) {
     out->devValid = false;
     out->dev.nNodes = 0;
     out->dev.topoNodes = -1;
+    out->dev.partial = false;
     return 0;
 }
 
@@ -262,6 +264,7 @@ int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double
     tree->hostCoefsValid = true;
     tree->devValid = false;
     tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
     // project.cpp:96-97: out.mwTransform(BottomUp); out.calcSquareNorm() -- on the device
     if (finalize) {
         mrx_mw_transform(tree, MRX_BOTTOM_UP, 1);
@@ -476,5 +479,6 @@ void mrx_tree_host_modified(mrx_tree *tree) {
     tree->devValid = false;
     tree->dev.nNodes = 0;
     tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
 }
 }

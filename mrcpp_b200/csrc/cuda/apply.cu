@@ -111,6 +111,9 @@ struct Scratch {
     bool hasBranchFlags = false;
     DevBuf<double> scaleFac, state;
     DevBuf<SplitResult> splitRes;
+    // lazy residency of the input tree
+    DevBuf<int> fetchList, fetchCnt;
+    DevBuf<unsigned long long> fetchTotal;
 };
 
 /// input-tree topology on the device for the band enumeration: real nodes + generated nodes in one slot space
@@ -1081,6 +1084,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     float kernel_ms = 0.f, contract_ms = 0.f;
     long long tuplesTotal = 0;
 
+    if (inp.dev.topoNodes != fRealN) S.h2d_bytes += 16ll * fRealN; // child pointer, depth, norm bound per node
     ensure_input_topology(inp, st);
     DeviceTree &fd = inp.dev;
     const double fMaxNorm = fd.topoMaxNorm;
@@ -1092,6 +1096,13 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     MRX_CUDA(cudaMemcpyAsync(topo.bound.p, fd.topoBound.p, sizeof(double) * fRealN, cudaMemcpyDeviceToDevice, st));
     MRX_CUDA(cudaMemsetAsync(topo.flag.p, 0, sizeof(int) * topo.flag.cap, st));
 
+    // input tree in pinned host memory (DeviceTree::partial): nodes are gathered over PCIe when the apply first reads them
+    const bool lazy = inp.dev.partial;
+    if (lazy) {
+        scr.fetchCnt.reserve(2, false, st);
+        scr.fetchTotal.reserve(1, false, st);
+        MRX_CUDA(cudaMemsetAsync(scr.fetchTotal.p, 0, sizeof(unsigned long long), st));
+    }
     // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store
     struct {
         bool active = false;
@@ -1289,6 +1300,12 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
             inp.dev.genCoefs.reserve((size_t)(fTotal - fRealN + 8 * nNew) * Kd, true, st);
             inp.dev.genNorms.reserve((size_t)(fTotal - fRealN + 8 * nNew), true, st);
             launch_enum_create(E, nNew, fTotal, st);
+            if (lazy) { // real leaves that get generated children are read by the generation kernel
+                scr.fetchList.reserve(std::max(nNew, 1), false, st);
+                MRX_CUDA(cudaMemsetAsync(scr.fetchCnt.p, 0, sizeof(int), st));
+                launch_fetch_mark(scr.newParents.p, nNew, fRealN, inp.dev.resident.p, scr.fetchList.p, scr.fetchCnt.p, st);
+                launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, scr.fetchCnt.p, ncoef, scr.fetchTotal.p, st);
+            }
             launch_gen_children(inp.dev.coefs.p, inp.dev.genCoefs.p, inp.dev.genNorms.p, fRealN, scr.genItems.p, nNew, K, filt, st);
             fTotal += 8 * nNew;
             S.gen_nodes += 8 * (long long)nNew;
@@ -1366,7 +1383,15 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         B.tuples = scr.tuples.p;
         B.units = scr.units2.p;
         B.partials = scr.partials.p;
+        if (lazy) {
+            scr.fetchList.reserve(std::max(nNbr, 1), false, st);
+            MRX_CUDA(cudaMemsetAsync(scr.fetchCnt.p, 0, sizeof(int), st));
+            B.resident = inp.dev.resident.p;
+            B.fetchList = scr.fetchList.p;
+            B.fetchCnt = scr.fetchCnt.p;
+        }
         launch_pipe_fill(P, B, nNbr, nL, st);
+        if (lazy) launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, scr.fetchCnt.p, ncoef, scr.fetchTotal.p, st);
         MRX_CUDA(cudaEventRecord(ev2, st));
         launch_pipe_contract(P, B, hdr.nUnits, st);
         MRX_CUDA(cudaEventRecord(ev3, st));
@@ -1497,6 +1522,12 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     S.ms_contract = contract_ms;
     S.f_applied = tuplesTotal;
     S.f_applied_rank = S.f_applied;
+    if (lazy) {
+        unsigned long long fetched = 0;
+        MRX_CUDA(cudaMemcpyAsync(&fetched, scr.fetchTotal.p, sizeof(fetched), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        S.h2d_bytes += (long long)fetched * ncoef * (long long)sizeof(double);
+    }
     if (world > 1) {
         double h[2] = {(double)S.f_applied, (double)S.gen_nodes};
         double *dsum = reinterpret_cast<double *>(scr.counters.p + 2);
@@ -1525,8 +1556,18 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     mrx_apply_stats S{};
     long long launches0 = launch_counter();
     double t0 = now_ms();
-    // ---- residency: input tree + operator tables in HBM
-    if (!inp.devValid) tree_upload(inp);
+    // ---- residency: input tree + operator tables in HBM. A tree whose coefficients sit in pinned host memory is not copied
+    //      as a whole: the apply gathers the nodes it reads (DeviceTree::partial); MRX_EAGER_UPLOAD=1 forces the full copy
+    if (!inp.devValid) {
+        const long long n8 = (long long)inp.host.nReal * 8 * (long long)sizeof(double);
+        if (use_pipeline(out) && inp.hostCoefsValid && inp.host.coefsPinned() && !getenv("MRX_EAGER_UPLOAD")) {
+            if (!inp.dev.partial) S.h2d_bytes += n8; // norms
+            tree_lazy_begin(inp);
+        } else {
+            tree_upload(inp);
+            S.h2d_bytes += n8 + (long long)inp.host.nReal * inp.host.ncoef * (long long)sizeof(double);
+        }
+    }
     oper_upload(oper);
     oper.op.calcBandWidths(prec);
     S.ms_upload = now_ms() - t0;
@@ -1560,7 +1601,10 @@ void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int d
     mrx_apply_stats S{};
     long long launches0 = launch_counter();
     double t0 = now_ms();
-    if (!inp.devValid) tree_upload(inp);
+    if (!inp.devValid) {
+        if (use_pipeline(out) && inp.hostCoefsValid && inp.host.coefsPinned() && !getenv("MRX_EAGER_UPLOAD")) tree_lazy_begin(inp);
+        else tree_upload(inp);
+    }
     oper_upload(oper);
     Operator &op = oper.op;
     op.calcBandWidths(1.0); // fixed 0 or 1 for derivatives (apply.cpp:389)

@@ -263,7 +263,44 @@ __global__ void __launch_bounds__(256) create_kernel(EnumParams E, int nNew, int
     E.genItems[2 * r + 1] = c0;
 }
 
+// ---- lazy residency of the input tree (engine.hpp DeviceTree::partial): nodes the apply is about to read are gathered from
+//      the pinned host chunks by the device itself; only they cross PCIe
+__global__ void __launch_bounds__(256) fetch_mark_kernel(const int *__restrict__ list, int n, int nRealF, int *__restrict__ resident,
+                                                         int *__restrict__ fetchList, int *__restrict__ fetchCnt) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int node = list[i];
+    if (node < nRealF && atomicExch(&resident[node], 1) == 0) fetchList[atomicAdd(fetchCnt, 1)] = node;
+}
+
+__global__ void __launch_bounds__(256) fetch_nodes_kernel(double *__restrict__ coefs, const double *const *__restrict__ chunkTab,
+                                                          const int *__restrict__ list, const int *__restrict__ cnt, int ncoef,
+                                                          unsigned long long *__restrict__ total) {
+    const int n = *cnt;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int slot = list[i];
+        const double2 *src = reinterpret_cast<const double2 *>(chunkTab[slot >> 6] + (size_t)(slot & 63) * ncoef);
+        double2 *dst = reinterpret_cast<double2 *>(coefs + (size_t)slot * ncoef);
+        for (int e = threadIdx.x; e < ncoef / 2; e += 256) dst[e] = src[e];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total += (unsigned long long)n;
+}
+
 } // namespace
+
+void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *fetchList, int *fetchCnt, cudaStream_t st) {
+    if (n <= 0) return;
+    fetch_mark_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, n, nRealF, resident, fetchList, fetchCnt);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *cnt, int ncoef, unsigned long long *total,
+                        cudaStream_t st) {
+    fetch_nodes_kernel<<<1184, 256, 0, st>>>(coefs, chunkTab, list, cnt, ncoef, total);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
 
 void launch_enum(const EnumParams &E, cudaStream_t st) {
     if (E.nG <= 0) return;

@@ -112,6 +112,11 @@ struct EnumParams {
 void launch_enum(const EnumParams &E, cudaStream_t st);
 void launch_enum_resolve(const EnumParams &E, int nPending, cudaStream_t st);
 void launch_enum_create(const EnumParams &E, int nNew, int firstSlot, cudaStream_t st);
+/// lazy residency: flag the real nodes of `list` that are not in HBM yet and queue them; gather the queued nodes from the
+/// pinned host chunks (64 nodes each) into the node store; *total accumulates the number of nodes fetched
+void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *fetchList, int *fetchCnt, cudaStream_t st);
+void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *cnt, int ncoef, unsigned long long *total,
+                        cudaStream_t st);
 
 // ---- work-list pipeline (apply_pipeline.cu): screen -> scan -> fill -> contract -> reduce -------------------
 /// one surviving (g, f, ft, gt, term) tuple: indices of the source block and of the three 1-D operator blocks
@@ -144,6 +149,10 @@ struct PipeBuffers {
     UnitDesc *units;
     double *partials; // [nUnits][K^3]
     int *queue;       // dynamic unit counter of the contraction kernel
+    // lazy residency of the input tree (nullptr: everything is resident): pipe_fill queues the nodes the tuples read
+    int *resident;
+    int *fetchList;
+    int *fetchCnt;
 };
 bool pipe_supports_order(int K); // orders with a work-list contraction kernel (K = k + 1)
 int pipe_contract_warps(); // persistent warps of the contraction kernel on this device

@@ -288,12 +288,14 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
     unsigned pos1 = B.blockTupOff[nb.g * 8 + 4 + (lane >> 3)] + (unsigned)B.segOff[(size_t)w * 64 + 32 + lane];
     const int fbase = (nb.fslot < P.nRealF) ? nb.fslot * 8 : P.nRealF * 8 + (nb.fslot - P.nRealF);
     const bool gen = nb.fslot >= P.nRealF;
+    bool anyPass = false;
     for (int base = 0; base < nc; base += 32) {
         const int c = base + lane;
         unsigned long long pass = 0ull;
         int oi0 = 0, oi1 = 0, oi2 = 0;
         if (c < nc) {
             pass = B.masks[(size_t)nb.candBase + c];
+            anyPass = anyPass || (pass != 0ull);
             if (pass) {
                 const int nbase = P.nodeBase[(size_t)P.candTerm[e0 + c] * P.DM + g.depth];
                 oi0 = (nbase + d[0]) * 4;
@@ -330,6 +332,11 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
                 else pos1 += __popc(bal);
             }
         }
+    }
+    // lazy residency: the contraction will read this input node; queue it if it is not in HBM yet
+    if (B.resident != nullptr && !gen) {
+        const bool any = __any_sync(0xffffffffu, anyPass);
+        if (any && lane == 0 && atomicExch(&B.resident[nb.fslot], 1) == 0) B.fetchList[atomicAdd(B.fetchCnt, 1)] = nb.fslot;
     }
 }
 

@@ -52,7 +52,29 @@ void tree_upload(mrx_tree &t) {
     t.dev.nNodes = n;
     t.dev.nGen = 0;
     t.dev.topoNodes = -1;
+    t.dev.partial = false;
     t.devValid = true;
+}
+
+void tree_lazy_begin(mrx_tree &t) {
+    require_device("tree_lazy_begin");
+    if (t.dev.partial) return; // keep what earlier applies already fetched
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    const int n = h.nReal;
+    t.dev.coefs.reserve((size_t)n * h.ncoef, false, st);
+    t.dev.norms.reserve((size_t)n * 8, false, st);
+    t.dev.resident.reserve(std::max(n, 1), false, st);
+    const auto &chunks = h.coefChunks();
+    t.dev.chunkTab.reserve(std::max<size_t>(chunks.size(), 1), false, st);
+    MRX_CUDA(cudaMemcpyAsync(t.dev.norms.p, h.cnorm.data(), sizeof(double) * (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaMemsetAsync(t.dev.resident.p, 0, sizeof(int) * std::max(n, 1), st));
+    MRX_CUDA(cudaMemcpyAsync(t.dev.chunkTab.p, chunks.data(), sizeof(double *) * chunks.size(), cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    t.dev.nNodes = n;
+    t.dev.nGen = 0;
+    t.dev.partial = true;
+    t.devValid = false;
 }
 
 void tree_download(mrx_tree &t) {
@@ -81,6 +103,9 @@ void tree_drop_device(mrx_tree &t) {
     t.dev.topoDepth.release();
     t.dev.topoBound.release();
     t.dev.topoNodes = -1;
+    t.dev.resident.release();
+    t.dev.chunkTab.release();
+    t.dev.partial = false;
     t.dev.nNodes = 0;
     t.dev.nGen = 0;
     t.devValid = false;

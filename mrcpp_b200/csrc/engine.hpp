@@ -61,6 +61,13 @@ struct DeviceTree {
     DevBuf<double> topoBound;
     int topoNodes = -1;
     double topoMaxNorm = 0.0;
+    // lazy residency of an apply INPUT whose coefficients live in pinned host memory: storage for every node is
+    // allocated, but only the nodes the apply actually reads are fetched over PCIe (by a gather kernel reading the host
+    // chunks directly); resident[n] = 1 once node n is in HBM. `partial` trees are not devValid: every other consumer
+    // completes the upload first (tree_upload).
+    DevBuf<int> resident;
+    DevBuf<const double *> chunkTab; // host chunk base pointers (64 nodes each), device-readable
+    bool partial = false;
 };
 
 struct DeviceOper {
@@ -103,6 +110,7 @@ long long &launch_counter();
 
 // device_tree.cu
 void tree_upload(mrx_tree &t);
+void tree_lazy_begin(mrx_tree &t); // norms + bookkeeping on the device, coefficient blocks fetched on demand by the apply
 void tree_download(mrx_tree &t);
 void tree_drop_device(mrx_tree &t);
 /// whole-tree transform (+ norms of every node). timedReps > 0: the level kernels are run timedReps times between two

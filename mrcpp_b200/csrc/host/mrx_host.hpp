@@ -197,6 +197,11 @@ public:
     void copyGridFrom(const Tree<D> &other); // copy_grid (grid.cpp:150-166)
     bool allocCoefs = true;       // false: new nodes get no host coefficient storage (device-resident)
     void ensureCoefStorage();     // allocate host storage for all nodes (before a download)
+    /// host coefficient chunks (64 nodes each) for device-side gathers; pinned (device-readable) unless the tree was
+    /// created before a CUDA device was selected
+    const std::vector<double *> &coefChunks() const { return chunks_; }
+    bool coefsPinned() const;
+    static constexpr int chunkNodes = 64;
 
     void zeroCoefs(int n);
     void calcNorms(int n);                  // MWNode.cpp:609-616 (+ OperatorNode.cpp:56-80 when operNorms)

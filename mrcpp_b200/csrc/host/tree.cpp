@@ -61,6 +61,8 @@ Tree<D>::Tree(const MRA<D> &m)
     nReal = nRoots;
 }
 
+template <int D> bool Tree<D>::coefsPinned() const { return alloc_ != default_chunk_alloc; }
+
 template <int D> int Tree<D>::allocNodes(int count) {
     int s = (int)nodes.size();
     nodes.resize(s + count);

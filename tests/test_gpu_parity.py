@@ -89,6 +89,40 @@ def test_device_projection(gpu, k, n, prec):
     assert_same_tree(ga, gb)
 
 
+@pytest.mark.parametrize("k,prec", [(7, 1e-5), (5, 1e-4)])
+def test_apply_input_in_host_memory(gpu, k, prec):
+    """Input tree in (pinned) host memory, as a reference-side binding hands it over: the apply gathers only the nodes it
+    reads (lazy residency) and must give bit-identical results to the apply on a fully resident input; a second apply on
+    the partially resident tree and a whole-tree operation afterwards (which completes the upload) stay correct."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(5, 31)
+    P = mw.PoissonOperator(mra, prec)
+    f = mw.FunctionTree(mra)
+    mw.project(prec, f, func)
+    ref = mw.FunctionTree(mra)
+    s0 = mw.apply(prec, ref, P, f)
+    assert s0.h2d_bytes == 0
+    R = ref.to_arrays()
+    f.drop_device()                       # host copy is the only copy now
+    g = mw.FunctionTree(mra)
+    s1 = mw.apply(prec, g, P, f)
+    G = g.to_arrays()
+    assert s1.f_applied == s0.f_applied
+    assert np.array_equal(G["transl"], R["transl"]) and np.array_equal(G["coefs"], R["coefs"])
+    assert 0 < s1.h2d_bytes < f.nbytes()   # only part of the input crossed PCIe
+    g2 = mw.FunctionTree(mra)
+    s2 = mw.apply(prec, g2, P, f)          # partially resident input: nothing (or little) left to fetch
+    assert np.array_equal(g2.to_arrays()["coefs"], R["coefs"]) and s2.h2d_bytes <= s1.h2d_bytes
+    D = mw.ABGVOperator(mra, 0.5, 0.5)
+    d1, d2 = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.apply(None, d1, D, f, dir=1)        # derivative apply on the partially resident tree
+    before = mw.dot(f, f)                  # whole-tree consumer: completes the upload
+    mw.apply(None, d2, D, f, dir=1)
+    assert np.array_equal(d1.to_arrays()["coefs"], d2.to_arrays()["coefs"])
+    assert abs(before - f.getSquareNorm()) <= 1e-12 * f.getSquareNorm()
+
+
 @pytest.mark.parametrize("k", [5, 7])
 def test_top_down_roundtrip(gpu, k):
     """mwTransform(TopDown) then (BottomUp) on the device: TopDown(overwrite) parity vs oracle and the
