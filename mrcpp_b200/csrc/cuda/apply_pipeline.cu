@@ -622,6 +622,118 @@ template <int K> __global__ void __launch_bounds__(256, 1) pipe_contract_pad_ker
     }
 }
 
+// The same padded-DMMA contraction with a CTA of four warps working on ONE unit: the n-tiles (columns) of every stage are
+// dealt out to the warps, the stage outputs live in CTA-shared memory. A unit then needs 2 K CP doubles of shared memory per
+// CTA instead of per warp, so 5-7 CTAs (20-28 warps) fit on an SM instead of 8 warps, and the DMMA latency is hidden by
+// other warps instead of by instruction-level parallelism alone. Summation order per output element is unchanged (tuples in
+// list order), so results are bit-identical to the warp-private kernel.
+template <int K, bool DENSE, bool ACC, int NTW>
+__device__ __forceinline__ void dmma_stage_coop(const double *__restrict__ in, const double *__restrict__ op, double *__restrict__ out,
+                                                double (&acc)[NTW][PadDims<K>::MT][2], int rr, int q, int warp) {
+    using D = PadDims<K>;
+    double a[D::MT][D::KS];
+#pragma unroll
+    for (int mt = 0; mt < D::MT; mt++)
+#pragma unroll
+        for (int s = 0; s < D::KS; s++) {
+            const int c = rr + 8 * mt, t = q + 4 * s;
+            a[mt][s] = (c < K && t < K) ? __ldg(op + t + K * c) : 0.0;
+        }
+#pragma unroll
+    for (int i = 0; i < NTW; i++) {
+        const int n0 = warp + 4 * i;
+        if (n0 < D::NT) {
+            const int r = 8 * n0 + rr;
+            const int rowAddr = DENSE ? K * r : K * (r % K) + D::CP * (r / K);
+            double b[D::KS];
+#pragma unroll
+            for (int s = 0; s < D::KS; s++) {
+                const int t = q + 4 * s;
+                b[s] = (r < D::K2 && t < K) ? in[rowAddr + t] : 0.0;
+            }
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) {
+                double d0 = 0.0, d1 = 0.0;
+                if (ACC) {
+                    d0 = acc[i][mt][0];
+                    d1 = acc[i][mt][1];
+                }
+#pragma unroll
+                for (int s = 0; s < D::KS; s++) dmma884(d0, d1, a[mt][s], b[s]);
+                if (ACC) {
+                    acc[i][mt][0] = d0;
+                    acc[i][mt][1] = d1;
+                } else {
+                    const int c = rr + 8 * mt, col = 8 * n0 + 2 * q;
+                    if (c < K && col < D::K2) *reinterpret_cast<double2 *>(out + col + D::CP * c) = make_double2(d0, d1);
+                }
+            }
+        }
+    }
+}
+
+template <int K> __global__ void __launch_bounds__(128) pipe_contract_coop_kernel(ApplyParams P, PipeBuffers B, int nUnits) {
+    using D = PadDims<K>;
+    constexpr int NTW = (D::NT + 3) / 4;
+    extern __shared__ __align__(16) double scratch[];
+    __shared__ int sUnit;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = lane >> 2, q = lane & 3;
+    double *S1 = scratch;
+    double *S2 = S1 + K * D::CP;
+    const long long nReal8 = (long long)P.nRealF * 8;
+    const int4 *recs = reinterpret_cast<const int4 *>(B.tuples);
+    for (;;) {
+        if (threadIdx.x == 0) sUnit = atomicAdd(B.queue, 1);
+        __syncthreads();
+        const int u = sUnit;
+        __syncthreads();
+        if (u >= nUnits) break;
+        const UnitDesc ud = B.units[u];
+        double acc[NTW][D::MT][2];
+#pragma unroll
+        for (int i = 0; i < NTW; i++)
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) acc[i][mt][0] = acc[i][mt][1] = 0.0;
+        for (int t = 0; t < ud.cnt; t++) {
+            const int4 rec = __ldg(recs + ud.t0 + t);
+            const double *fblk = (rec.x < nReal8) ? P.fReal + (size_t)rec.x * D::Kd : P.fGen + (size_t)(rec.x - nReal8) * D::Kd;
+            dmma_stage_coop<K, true, false, NTW>(fblk, P.mats + (size_t)rec.y * D::K2, S1, acc, rr, q, warp);
+            __syncthreads();
+            dmma_stage_coop<K, false, false, NTW>(S1, P.mats + (size_t)rec.z * D::K2, S2, acc, rr, q, warp);
+            __syncthreads();
+            dmma_stage_coop<K, false, true, NTW>(S2, P.mats + (size_t)rec.w * D::K2, nullptr, acc, rr, q, warp);
+            __syncthreads(); // the next tuple's second stage overwrites S2
+        }
+        double *pb = B.partials + (size_t)u * D::Kd;
+#pragma unroll
+        for (int i = 0; i < NTW; i++) {
+            const int n0 = warp + 4 * i;
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) {
+                const int c = rr + 8 * mt, col = 8 * n0 + 2 * q;
+                if (n0 < D::NT && c < K && col < D::K2)
+                    *reinterpret_cast<double2 *>(pb + col + D::K2 * c) = make_double2(acc[i][mt][0], acc[i][mt][1]);
+            }
+        }
+    }
+}
+
+template <int K> void launch_contract_coop(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
+    using D = PadDims<K>;
+    static int grid = 0;
+    const size_t bytes = (size_t)2 * K * D::CP * sizeof(double);
+    if (!grid) {
+        int dev = 0, sms = 0, perSm = 0;
+        MRX_CUDA(cudaGetDevice(&dev));
+        MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_coop_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pipe_contract_coop_kernel<K>, 128, bytes));
+        grid = sms * std::max(perSm, 1);
+    }
+    pipe_contract_coop_kernel<K><<<std::min(grid, nUnits), 128, bytes, st>>>(P, B, nUnits);
+}
+
 // ------------------------------------------------------------------------------------------------ reduce
 // stageRows != nullptr (sharded apply): the block goes to row (blk >> 3) of the rank's segment of the exchange staging buffer
 // instead of the node store; the whole iteration is unpacked into the node store after the peers' rows have arrived
@@ -776,6 +888,7 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
     if (nUnits <= 0) return;
     MRX_CUDA(cudaMemsetAsync(B.queue, 0, sizeof(int), st));
     static const bool useFma = getenv("MRX_FMA") != nullptr; // development switch: FMA instead of padded-DMMA contraction
+    static const bool warpPrivate = getenv("MRX_PAD_WARP") != nullptr; // development switch: one warp per unit instead of one CTA
     if (P.K == 8) {
         const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
         pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
@@ -783,13 +896,16 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
         launch_contract_fma<4>(P, B, nUnits, st);
     } else if (P.K == 6) {
         if (useFma) launch_contract_fma<6>(P, B, nUnits, st);
-        else launch_contract_pad<6>(P, B, nUnits, st);
+        else if (warpPrivate) launch_contract_pad<6>(P, B, nUnits, st);
+        else launch_contract_coop<6>(P, B, nUnits, st);
     } else if (P.K == 10) {
         if (useFma) launch_contract_fma<10>(P, B, nUnits, st);
-        else launch_contract_pad<10>(P, B, nUnits, st);
+        else if (warpPrivate) launch_contract_pad<10>(P, B, nUnits, st);
+        else launch_contract_coop<10>(P, B, nUnits, st);
     } else if (P.K == 12) {
         if (useFma) launch_contract_fma<12>(P, B, nUnits, st);
-        else launch_contract_pad<12>(P, B, nUnits, st);
+        else if (warpPrivate) launch_contract_pad<12>(P, B, nUnits, st);
+        else launch_contract_coop<12>(P, B, nUnits, st);
     } else {
         MRX_ABORT("pipeline contraction: unsupported order");
     }

@@ -102,7 +102,7 @@ def test_apply_input_in_host_memory(gpu, k, prec):
     mw.project(prec, f, func)
     ref = mw.FunctionTree(mra)
     s0 = mw.apply(prec, ref, P, f)
-    assert s0.h2d_bytes == 0
+    assert s0.h2d_bytes <= 16 * f.getNNodes()  # resident input: at most the band-walk topology (16 B per node) is uploaded
     R = ref.to_arrays()
     f.drop_device()                       # host copy is the only copy now
     g = mw.FunctionTree(mra)
