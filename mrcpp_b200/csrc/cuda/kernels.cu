@@ -116,12 +116,16 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
 // Warp w = (g0, f2) runs passes 0 and 1 register-to-register (D fragment -> B fragment under sigma) for
 // its four input blocks (f0, f1), writes P1(g0, g1, f2) into a padded shared tile, and after one barrier
 // warp w = (g0, g1) contracts z for g2 = 0, 1 out of the tiles. 768 DMMA.8x8x4 per node = 96 K^4 flop.
-constexpr int kT8Si = 18, kT8Sm = 152, kT8Doubles = 8 * kT8Sm; // same padded tile as the apply kernel
+// padded tile of the z pass: element (m1 = r, i2 = j, m0 pair) at 2 q + kT8Si j + kT8Sm r. kT8Si / 2 = 5 (mod 8) and
+// kT8Sm / 2 = 4 (mod 8) keep the 16-byte stores of a quarter warp and both 16-byte fragment reads of the z pass on eight
+// distinct bank groups with only 2 pad doubles per row of 8 (704 doubles per tile instead of 1216).
+constexpr int kT8Si = 10, kT8Sm = 88, kT8Doubles = 8 * kT8Sm;
+constexpr size_t kT8Bytes = (size_t)8 * kT8Doubles * sizeof(double); // 45 KB: the TMA-staged node (32 KB) aliases the tiles
 
 template <int MODE> // 0: TopDown (parent 8 blocks -> children scaling, = or +=); 1: BottomUp (children scaling -> parent); 3: in-node compression
 __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ coefs, const int *__restrict__ pairs,
                                                          const double *__restrict__ filters, int overwrite, double *__restrict__ norms) {
-    extern __shared__ __align__(128) double tiles8[]; // 8 padded tiles (kT8Doubles each) + the TMA-staged node (8 x 512)
+    extern __shared__ __align__(128) double tiles8[]; // 8 padded tiles (kT8Doubles each); the TMA-staged node (8 x 512) lives in the same bytes until its fragments are in registers
     constexpr int Kd = 512, ncoef = 8 * Kd;
     const int parent = pairs[2 * blockIdx.x];
     const int child0 = pairs[2 * blockIdx.x + 1];
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
     }
     // ---- the node's 8 source blocks (32 KB) are staged by the TMA engine: one bulk copy for a parent node (contiguous),
     //      eight 4 KB copies for the scaling blocks of the children; all bytes in flight at once
-    double *inbuf = tiles8 + 8 * kT8Doubles;
+    double *inbuf = tiles8;
     __shared__ __align__(8) uint64_t bar;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
                 bf[b][j][1] = blk[bo + 4 + 64 * j];
             }
         }
+        __syncthreads(); // every warp holds its source fragments: the staging bytes become the tiles
         double p0[2][8][2];
 #pragma unroll
         for (int f1 = 0; f1 < 2; f1++) {
@@ -571,7 +576,7 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
         return;
     }
     if (K == 8) {
-        constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
+        constexpr size_t bytes8 = kT8Bytes;
         static bool conf = false;
         if (!conf) {
             MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
@@ -607,7 +612,7 @@ void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, cons
         return;
     }
     if (K == 8) {
-        constexpr size_t bytes8 = (size_t)(8 * kT8Doubles + 8 * 512) * sizeof(double);
+        constexpr size_t bytes8 = kT8Bytes;
         static bool conf = false;
         if (!conf) {
             MRX_CUDA(cudaFuncSetAttribute(transform8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes8));
