@@ -25,7 +25,8 @@ import os as _os
 if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
     # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores
     _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
-_os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout; bench prints exactly one JSON line
+if _os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    _os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; bench prints exactly one JSON line
 import argparse
 import json
 import math
@@ -242,8 +243,8 @@ def main():
         out = mw.FunctionTree(mra)
         L.mrx_timer_start()
         st = mw.apply(prec, out, P, ft, comm=comm)
-        if e2e:
-            out.sync_host()  # result back in host memory
+        if e2e and rank == 0:
+            out.sync_host()  # result back in host memory (every rank holds the identical tree in HBM; rank 0 reads it back)
         ms = L.mrx_timer_stop_ms()
         nbytes_out = out.nbytes()
         del out
@@ -286,7 +287,7 @@ def main():
         e2e_ms += ms
         e2e_nodes += st.g_nodes
         h2d = st.h2d_bytes  # counted by the library: coefficient blocks gathered from host memory + norms + topology
-        d2h = nb_out
+        d2h = nb_out if rank == 0 else 0
     barrier()
 
     if world > 1:
