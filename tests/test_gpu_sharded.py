@@ -33,12 +33,15 @@ def test_sharded_apply_world1(libs):
     assert np.array_equal(A["transl"], B["transl"]) and np.array_equal(A["coefs"], B["coefs"])
 
 
-def test_sharded_apply_two_ranks(libs):
+@pytest.mark.parametrize("args,env", [(["1e-5", "6"], {}), (["1e-5", "6"], {"MRX_NO_IPC": "1"}), (["1e-4", "4", "11"], {}), (["1e-4", "4", "5"], {})])
+def test_sharded_apply_two_ranks(libs, args, env):
+    """2 ranks: every rank must end with the bit-identical tree of a single-GPU apply (k = 7 with the peer-push and with
+    the NCCL coefficient exchange, k = 11 and k = 5 with the padded contraction kernels)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (covered by tools/shard_check.py under gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "shard_check.py"), "1e-5", "6"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29533", os.path.join(ROOT, "tools", "shard_check.py")] + args
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("same-topology True") == 2

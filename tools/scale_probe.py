@@ -21,7 +21,7 @@ if world > 1:
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
     comm = mw.Comm(rank, world, bcast)
-k = 7; prec = 1e-7
+k = int(os.environ.get("MRX_PROBE_K", "7")); prec = float(os.environ.get("MRX_PROBE_PREC", "1e-7"))
 mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
 P = mw.PoissonOperator(mra, prec)
 for n in [int(a) for a in sys.argv[1:]] or [100]:

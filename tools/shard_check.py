@@ -19,7 +19,8 @@ def bcast(b):
     return obj[0]
 
 comm = mw.Comm(rank, world, bcast)
-k = 7; prec = float(sys.argv[1]) if len(sys.argv) > 1 else 1e-5; n = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+prec = float(sys.argv[1]) if len(sys.argv) > 1 else 1e-5; n = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 7
 mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
 rng = np.random.default_rng(42)
 func = mw.GaussExp()
