@@ -1051,7 +1051,8 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
 // own topology AFTER it has launched the next iteration's contraction, i.e. while the device is busy. Nothing on the
 // host's critical path loops over nodes (except the one-off set-up of the first work vector).
 static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
-                           std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm) {
+                           std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm,
+                           std::vector<std::vector<int>> *branchPairs = nullptr) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
@@ -1208,6 +1209,12 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                     const int c0 = g.createChildren(hostVec[i], false);
                     if (c0 != expect) MRX_ABORT("apply: host replay of the device split decisions lost its slot order");
                     expect += 8;
+                    if (branchPairs) { // level lists of the closing transforms, for free while the device is busy
+                        const size_t d = (size_t)(g.nodes[hostVec[i]].scale - g.mra.rootScale);
+                        if (branchPairs->size() <= d) branchPairs->resize(d + 1);
+                        (*branchPairs)[d].push_back(hostVec[i]);
+                        (*branchPairs)[d].push_back(c0);
+                    }
                     for (int c = 0; c < 8; c++) next.push_back(c0 + c);
                 }
             }
@@ -1575,7 +1582,12 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     double tb = now_ms();
     std::vector<int> workVec;
     out.host.nodeTable(workVec); // getInitialWorkVector: ALL nodes of `out` (ConvolutionCalculator.cpp:400-405)
-    if (use_pipeline(out)) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
+    // an output tree that starts from bare roots gets all its branch nodes from this apply: their (parent, child0) pairs
+    // are collected per depth during the loop and handed to the closing transforms
+    std::vector<std::vector<int>> branchPairs;
+    const bool bareRoots = out.host.nReal == out.host.nRoots;
+    const bool pipe = use_pipeline(out);
+    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr);
     else run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
     S.ms_build = now_ms() - tb;
 
@@ -1583,7 +1595,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     double tp = now_ms();
     oper.op.clearBandWidths();
     const bool prof = getenv("MRX_PROFILE") != nullptr;
-    device_apply_post(out);
+    device_apply_post(out, (pipe && bareRoots) ? &branchPairs : nullptr);
     inp.host.deleteGenerated();
     inp.dev.nGen = 0;
     S.ms_post = now_ms() - tp;

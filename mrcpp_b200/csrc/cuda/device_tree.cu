@@ -161,18 +161,42 @@ static int build_level_pairs(const Tree<3> &h, std::vector<int> &levelOff, std::
 /// (scaling norm of every child on the way down, all eight norms of every parent on the way up) no separate pass over the
 /// tree is needed: wavelet norms of the leaves are those of the apply itself. The tree norm is the sum of the end-node
 /// square norms in slot order (the reference sums the same terms in end-node-table order).
-void device_apply_post(mrx_tree &t) {
+// pinned bounce buffer for small device->host results (a pageable destination is staged by the driver at a fraction of
+// the PCIe rate)
+static double *pinned_scratch(size_t doubles) {
+    static double *buf = nullptr;
+    static size_t cap = 0;
+    if (doubles > cap) {
+        if (buf) cudaFreeHost(buf);
+        cap = std::max(doubles, 2 * cap);
+        MRX_CUDA(cudaMallocHost(&buf, cap * sizeof(double)));
+    }
+    return buf;
+}
+
+void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth) {
     require_device("device_apply_post");
     Tree<3> &h = t.host;
     cudaStream_t st = stream();
     const int n = h.nReal;
     std::vector<int> levelOff, flat;
-    const int nPairs = build_level_pairs(h, levelOff, flat);
+    int nPairs = 0;
+    if (pairsByDepth) { // collected by the apply while it replayed the split decisions (already grouped by depth)
+        levelOff.assign(1, 0);
+        for (const auto &lv : *pairsByDepth) {
+            flat.insert(flat.end(), lv.begin(), lv.end());
+            levelOff.push_back((int)flat.size() / 2);
+        }
+        if (levelOff.size() == 1) levelOff.push_back(0);
+        nPairs = (int)flat.size() / 2;
+    } else {
+        nPairs = build_level_pairs(h, levelOff, flat);
+    }
     const int nLevels = (int)levelOff.size() - 1;
     const bool fused = transform_fuses_norms(h.K);
     t.dev.topoNodes = -1;
+    DevBuf<int> pairs;
     if (nPairs > 0) {
-        DevBuf<int> pairs;
         pairs.reserve(flat.size(), false, st);
         MRX_CUDA(cudaMemcpyAsync(pairs.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
         const double *filt = device_filters(h.k);
@@ -186,18 +210,21 @@ void device_apply_post(mrx_tree &t) {
             if (cnt > 0) launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st, nrm);
         }
         if (!fused) launch_norms(t.dev.coefs.p, t.dev.norms.p, nullptr, n, h.Kd, st);
-        MRX_CUDA(cudaMemcpyAsync(h.cnorm.data(), t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaStreamSynchronize(st)); // also keeps `pairs` alive until the launches have consumed it
-    } else {
-        MRX_CUDA(cudaMemcpyAsync(h.cnorm.data(), t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaStreamSynchronize(st));
     }
+    double *bounce = pinned_scratch((size_t)n * 8);
+    MRX_CUDA(cudaMemcpyAsync(bounce, t.dev.norms.p, sizeof(double) * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st)); // also keeps `pairs` alive until the launches have consumed it
     t.devValid = true;
     t.hostCoefsValid = false;
     double tot = 0.0;
+    double *cn = h.cnorm.data();
     for (int i = 0; i < n; i++) {
         double sq = 0.0;
-        for (int c = 0; c < 8; c++) sq += h.cnorm[(size_t)i * 8 + c] * h.cnorm[(size_t)i * 8 + c];
+        for (int c = 0; c < 8; c++) {
+            const double v = bounce[(size_t)i * 8 + c];
+            cn[(size_t)i * 8 + c] = v;
+            sq += v * v;
+        }
         h.sqn[i] = sq;
         if (h.nodes[i].flags & FlagEnd) tot += sq;
     }

@@ -117,7 +117,9 @@ void tree_drop_device(mrx_tree &t);
 /// CUDA events (measurement of the filter kernels alone; TopDown with overwrite and BottomUp are idempotent)
 void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = true, int timedReps = 0, double *timedMs = nullptr,
                          int *branchNodes = nullptr);
-void device_apply_post(mrx_tree &t); // TopDown(+=), BottomUp, norms, square norm: the closing passes of mrcpp::apply
+/// TopDown(+=), BottomUp, norms, square norm: the closing passes of mrcpp::apply. pairsByDepth (optional): (parent, child0)
+/// pairs per depth of ALL branch nodes, if the caller already has them
+void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth = nullptr);
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
 double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
