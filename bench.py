@@ -25,8 +25,9 @@ import os as _os
 if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
     # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores
     _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
-if _os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    _os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; bench prints exactly one JSON line
+# bench prints exactly one JSON line on stdout: if the environment turns NCCL logging on (NCCL_DEBUG=VERSION/WARN print a
+# version banner), send it to stderr
+_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import argparse
 import json
 import math

@@ -2,7 +2,6 @@
 import math, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")
 import numpy as np
 import torch
 import torch.distributed as dist
