@@ -1,22 +1,23 @@
-// mrcpp::apply on the GPU: host-driven refinement loop + device kernels.
+// mrcpp::apply on the GPU: drivers of the operator application.
 //
 // Reference control flow replaced (file:line relative to the MRCPP tree):
 //   apply<3,double>(prec,out,oper,inp,maxIter,absPrec)       src/treebuilders/apply.cpp:68-93
+//   apply(out, DerivativeOperator, inp, dir)                  src/treebuilders/apply.cpp:379-412
 //   TreeBuilder::build                                        src/treebuilders/TreeBuilder.cpp:38-86
 //   ConvolutionCalculator::{initBandSizes,makeOperBand,calcNode,applyOperComp,applyOperator,
 //                           tensorApplyOperComp}              src/treebuilders/ConvolutionCalculator.cpp:105-382
 //   WaveletAdaptor::splitNode / tree_utils::split_check       src/treebuilders/WaveletAdaptor.h:51-54, tree_utils.cpp:47-65
 //   TreeAdaptor::splitNodeVector                              src/treebuilders/TreeAdaptor.h:41-54
 //
-// Division of labour. The host keeps only topology (which node exists where) and the scalar
-// bookkeeping whose summation order defines the reference's thresholds (sNorm/wNorm in work-vector
-// order, split decisions). Everything that touches coefficients runs on the device:
-//   1. generated input nodes are materialised level by level (kernels.cu, MODE 2);
-//   2. one CTA per output node screens every (input node, term) pair with the reference's exact
-//      predicate (integer band tests + the FP64 norm product in the reference's operation order) and
-//      contracts the surviving (ft, gt, term) tuples; warp w owns output component gt = w, so the
-//      accumulation order is fixed and no atomics are needed;
-//   3. component norms come back (8 doubles per node) for the split decision.
+// run_apply_pipe (orders with a work-list contraction kernel, K = 4, 6, 8, 10, 12; one or many GPUs): per refinement
+//   iteration  enumerate band (apply_enum.cu) -> screen / scan / fill / contract / reduce (apply_pipeline.cu) ->
+//   [norm all-gather + peer push of the coefficient rows (comm.cu)] -> bookkeeping + split + next work vector
+//   (apply_split.cu). The device owns the work vector; the host reads back three small records per iteration and replays
+//   the split flags into its topology while the device contracts the next iteration.
+// run_apply_legacy (other orders, MRX_LEGACY=1): band enumeration and refinement loop on the host, one CTA per output
+//   node (apply_kernels.cu).
+// device_apply / device_apply_derivative: residency of the input (whole upload or lazy gathers), the loop, the closing
+//   TopDown(+=) / BottomUp passes (device_tree.cu), cleanup of generated nodes.
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -342,19 +343,17 @@ static void ensure_input_topology(mrx_tree &inp, cudaStream_t st) {
     }
 }
 
-static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
-                      std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm = nullptr) {
+// ---------------------------------------------------------------------------------------------------------------------
+// First-generation path, kept for the orders the work-list pipeline does not cover (odd K = even polynomial order) and as
+// a development cross-check (MRX_LEGACY=1): band enumeration and the refinement loop on the host, one CTA per output
+// node (apply_kernels.cu). Single GPU only.
+static void run_apply_legacy(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
+                             std::vector<int> workVec, mrx_apply_stats &S) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
-    const char *legacy = getenv("MRX_LEGACY");
-    const bool usePipe = pipe_supports_order(out.host.K) && !(legacy && legacy[0] == '1');
-    const int world = comm_world(comm), rank = comm_rank(comm);
-    const char *uEnv = getenv("MRX_UNIT_TUPLES");
-    const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
-    if (world > 1 && !usePipe) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11 convolution operators) only");
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -370,13 +369,10 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     BandTables &bt = get_band_tables(oper, prec, derivDir, st);
     const std::vector<int> &bsf = bt.bsf;
 
-    cudaEvent_t ev0, ev1, ev2, ev3;
+    cudaEvent_t ev0, ev1;
     MRX_CUDA(cudaEventCreate(&ev0));
     MRX_CUDA(cudaEventCreate(&ev1));
-    MRX_CUDA(cudaEventCreate(&ev2));
-    MRX_CUDA(cudaEventCreate(&ev3));
-    float kernel_ms = 0.f, contract_ms = 0.f;
-    long long tuplesTotal = 0, iterTuples = 0;
+    float kernel_ms = 0.f;
 
     double sNorm = 0.0, wNorm = 0.0;
     int iter = 0;
@@ -385,41 +381,13 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
     std::vector<NbrEntry> nbr;
     std::vector<int> newParents;
     std::vector<double> genBound; // per generated node: norm of its real leaf ancestor (upper bound of its own norm)
-    DevTopo topo;
-    int fTotal = fRealN; // real + generated input nodes known to the device
     ensure_input_topology(inp, st);
     DeviceTree &fd = inp.dev;
     const double fMaxNorm = fd.topoMaxNorm;
     std::vector<double> fNodeNorm; // host enumeration of the legacy (odd K) path only
-    if (!usePipe) {
-        fNodeNorm.resize(fRealN);
-        for (int n = 0; n < fRealN; n++) fNodeNorm[n] = std::sqrt(f.sqn[n]);
-    }
-    if (usePipe) {
-        topo.reserve((size_t)fRealN + 4096, st);
-        MRX_CUDA(cudaMemcpyAsync(topo.child0.p, fd.topoChild0.p, sizeof(int) * fRealN, cudaMemcpyDeviceToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(topo.depth.p, fd.topoDepth.p, sizeof(int) * fRealN, cudaMemcpyDeviceToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(topo.bound.p, fd.topoBound.p, sizeof(double) * fRealN, cudaMemcpyDeviceToDevice, st));
-        MRX_CUDA(cudaMemsetAsync(topo.flag.p, 0, sizeof(int) * topo.flag.cap, st));
-    }
-    // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store
-    struct {
-        bool active = false;
-        int buf = 0, nG = 0, rows = 0;
-    } pend;
-    auto flush_pending = [&]() {
-        if (!pend.active) return;
-        // own push done -> tiny all-reduce: behind it every peer's push is done as well -> unpack
-        MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
-        scr.counters.reserve(4, false, st);
-        comm_allreduce_sum(comm, reinterpret_cast<double *>(scr.counters.p + 2), 1, st);
-        launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)), scr.gslotsAll[pend.buf].p, pend.nG,
-                            world, pend.rows, out.host.ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, st);
-        pend.active = false;
-    };
+    fNodeNorm.resize(fRealN);
+    for (int n = 0; n < fRealN; n++) fNodeNorm[n] = std::sqrt(f.sqn[n]);
     double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
-    double tg_prep = 0, tg_enum = 0, tg_resolve = 0;
-    int nResolveRounds = 0;
     const bool profile = getenv("MRX_PROFILE") != nullptr;
     const double tLoop = now_ms();
     while (!workVec.empty()) {
@@ -463,9 +431,7 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             int code;
             std::array<int, 3> l;
         };
-        const int nGH = usePipe ? 0 : nG; // the pipeline enumerates on the device (apply_enum.cu)
-        int nL = nG, rowsPerRank = nG;    // items of the work vector this rank computes / padded items per rank
-        std::vector<int> localSlots;
+        const int nGH = nG;
         std::vector<std::vector<Hit>> hits(nGH);
 #pragma omp parallel for schedule(dynamic, 16)
         for (int i = 0; i < nGH; i++) {
@@ -547,182 +513,63 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         std::vector<int> reduceItems; // (slot, firstPartial, nPartials)
         int nPartials = 0;
         if (nCand >= (1ll << 31)) MRX_ABORT("apply: candidate space of one iteration exceeds 2^31");
-        if (!usePipe) {
-            std::vector<long long> cost(nG, 0);
-            long long total = 0;
-            for (int i = 0; i < nG; i++) {
-                const GDesc &d = gdesc[i];
-                if (d.nbrCnt == 0) continue;
-                const int *coff = bt.candOff.data() + bt.info[d.depth].cubeOff;
-                long long c = 0;
-                for (int q = 0; q < d.nbrCnt; q++) {
-                    int code = nbr[d.nbrOff + q].code;
-                    c += coff[code + 1] - coff[code];
-                }
-                cost[i] = c;
-                total += c;
+        std::vector<long long> cost(nG, 0);
+        long long total = 0;
+        for (int i = 0; i < nG; i++) {
+            const GDesc &d = gdesc[i];
+            if (d.nbrCnt == 0) continue;
+            const int *coff = bt.candOff.data() + bt.info[d.depth].cubeOff;
+            long long c = 0;
+            for (int q = 0; q < d.nbrCnt; q++) {
+                int code = nbr[d.nbrOff + q].code;
+                c += coff[code + 1] - coff[code];
             }
-            const long long target = std::max<long long>(total / (148 * 4), 512);
-            for (int i = 0; i < nG; i++) {
-                const GDesc &d = gdesc[i];
-                int nChunks = (int)std::min<long long>((cost[i] + target - 1) / target, std::max(d.nbrCnt, 1));
-                if (nChunks <= 1) {
-                    units.push_back(d);
-                    unitCost.push_back(cost[i]);
-                    continue;
-                }
-                const int *coff = bt.candOff.data() + bt.info[d.depth].cubeOff;
-                reduceItems.push_back(d.slot);
-                reduceItems.push_back(nPartials);
-                int made = 0, q0 = 0;
-                long long acc = 0, done = 0;
-                for (int q = 0; q < d.nbrCnt; q++) {
-                    int code = nbr[d.nbrOff + q].code;
-                    acc += coff[code + 1] - coff[code];
-                    // close the chunk when its share of the remaining cost is reached
-                    long long want = (cost[i] - done + (nChunks - made) - 1) / (nChunks - made);
-                    if ((acc >= want && made < nChunks - 1) || q == d.nbrCnt - 1) {
-                        GDesc u = d;
-                        u.nbrOff = d.nbrOff + q0;
-                        u.nbrCnt = q - q0 + 1;
-                        u.partial = nPartials++;
-                        units.push_back(u);
-                        unitCost.push_back(acc);
-                        done += acc;
-                        acc = 0;
-                        q0 = q + 1;
-                        made++;
-                    }
-                }
-                reduceItems.push_back(made);
-            }
-            std::vector<int> order(units.size());
-            for (size_t u = 0; u < order.size(); u++) order[u] = (int)u;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return unitCost[a] > unitCost[b]; });
-            std::vector<GDesc> sorted(units.size());
-            for (size_t u = 0; u < order.size(); u++) sorted[u] = units[order[u]];
-            units.swap(sorted);
+            cost[i] = c;
+            total += c;
         }
+        const long long target = std::max<long long>(total / (148 * 4), 512);
+        for (int i = 0; i < nG; i++) {
+            const GDesc &d = gdesc[i];
+            int nChunks = (int)std::min<long long>((cost[i] + target - 1) / target, std::max(d.nbrCnt, 1));
+            if (nChunks <= 1) {
+                units.push_back(d);
+                unitCost.push_back(cost[i]);
+                continue;
+            }
+            const int *coff = bt.candOff.data() + bt.info[d.depth].cubeOff;
+            reduceItems.push_back(d.slot);
+            reduceItems.push_back(nPartials);
+            int made = 0, q0 = 0;
+            long long acc = 0, done = 0;
+            for (int q = 0; q < d.nbrCnt; q++) {
+                int code = nbr[d.nbrOff + q].code;
+                acc += coff[code + 1] - coff[code];
+                // close the chunk when its share of the remaining cost is reached
+                long long want = (cost[i] - done + (nChunks - made) - 1) / (nChunks - made);
+                if ((acc >= want && made < nChunks - 1) || q == d.nbrCnt - 1) {
+                    GDesc u = d;
+                    u.nbrOff = d.nbrOff + q0;
+                    u.nbrCnt = q - q0 + 1;
+                    u.partial = nPartials++;
+                    units.push_back(u);
+                    unitCost.push_back(acc);
+                    done += acc;
+                    acc = 0;
+                    q0 = q + 1;
+                    made++;
+                }
+            }
+            reduceItems.push_back(made);
+        }
+        std::vector<int> order(units.size());
+        for (size_t u = 0; u < order.size(); u++) order[u] = (int)u;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return unitCost[a] > unitCost[b]; });
+        std::vector<GDesc> sorted(units.size());
+        for (size_t u = 0; u < order.size(); u++) sorted[u] = units[order[u]];
+        units.swap(sorted);
         tp_phase2 += now_ms() - tq;
         tq = now_ms();
-        upload_band_tables(bt, DM, usePipe, st);
-        if (usePipe) {
-            // ---- device enumeration of the operator band + generated input nodes (apply_enum.cu)
-            // sharded apply: cyclic distribution of the work vector, rank r computes the items i = r, r + world, ...
-            // (siblings and spatial neighbours cost about the same, so the cyclic cut balances the tuple counts)
-            rowsPerRank = (nG + world - 1) / world;
-            nL = (nG + world - 1 - rank) / world;
-            std::vector<int4> gN(std::max(nL, 1));
-            localSlots.resize(std::max(nL, 1));
-            std::vector<int> chunkOff(nL + 1, 0);
-            long long nbrCap = 0, nChunksLL = 0;
-            for (int j = 0; j < nL; j++) {
-                const int i = rank + j * world;
-                const auto &nd = g.nodes[workVec[i]];
-                const int dep = nd.scale - op.operRoot;
-                gN[j] = make_int4(dep, nd.l[0], nd.l[1], nd.l[2]);
-                localSlots[j] = workVec[i];
-                chunkOff[j] = (int)nChunksLL;
-                // deeper than every operator tree, or no band at that depth: empty band (:146-151)
-                if (dep >= 0 && dep < DM && bt.built[dep] && bt.info[dep].W >= 0) {
-                    nbrCap += bt.offCount[dep];
-                    nChunksLL += (bt.offCount[dep] + 31) / 32;
-                }
-            }
-            chunkOff[nL] = (int)nChunksLL;
-            if (nChunksLL * 32 >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
-            const int nChunks = (int)nChunksLL;
-            if (nbrCap >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
-            scr.gNodes.reserve(std::max(nL, 1), false, st);
-            scr.gslots.reserve(std::max(nL, 1), false, st);
-            scr.gdesc.reserve(std::max(nL, 1), false, st);
-            scr.nbr.reserve(std::max<long long>(nbrCap, 1), false, st);
-            scr.pending.reserve(std::max<long long>(nbrCap, 1), false, st);
-            scr.ecnt.reserve(1, false, st);
-            scr.chunkOff.reserve(nL + 1, false, st);
-            scr.pNode.reserve(std::max<size_t>((size_t)nChunks * 32, 1), false, st);
-            scr.chunkPacked.reserve(std::max(nChunks, 1), false, st);
-            scr.chunkScan.reserve(std::max(nChunks, 1), false, st);
-            scr.tileTotal.reserve(nChunks / 2048 + 2, false, st);
-            scr.tileBase.reserve(nChunks / 2048 + 3, false, st);
-            MRX_CUDA(cudaMemcpyAsync(scr.chunkOff.p, chunkOff.data(), sizeof(int) * (nL + 1), cudaMemcpyHostToDevice, st));
-            if (nL > 0) {
-                MRX_CUDA(cudaMemcpyAsync(scr.gNodes.p, gN.data(), sizeof(int4) * nL, cudaMemcpyHostToDevice, st));
-                MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, localSlots.data(), sizeof(int) * nL, cudaMemcpyHostToDevice, st));
-            }
-            MRX_CUDA(cudaMemsetAsync(scr.ecnt.p, 0, sizeof(EnumCounters), st));
-            EnumParams E{};
-            E.gNodes = scr.gNodes.p;
-            E.gSlots = scr.gslots.p;
-            E.nG = nL;
-            E.chunkOff = scr.chunkOff.p;
-            E.nChunks = nChunks;
-            E.pNode = scr.pNode.p;
-            E.chunkPacked = scr.chunkPacked.p;
-            E.chunkScan = scr.chunkScan.p;
-            E.tileTotal = scr.tileTotal.p;
-            E.tileBase = scr.tileBase.p;
-            E.depthShift = op.operRoot - f.mra.rootScale;
-            E.offStart = bt.d_offStart.p;
-            E.offCount = bt.d_offCount.p;
-            E.offs = bt.d_offs.p;
-            E.depthInfo = bt.d_info.p;
-            E.candOff = bt.d_candOff.p;
-            E.DM = DM;
-            E.fChild0 = topo.child0.p;
-            E.fDepth = topo.depth.p;
-            E.fBound = topo.bound.p;
-            E.fFlag = topo.flag.p;
-            for (int x = 0; x < 3; x++) {
-                E.corner[x] = f.mra.corner[x];
-                E.nboxes[x] = f.mra.nboxes[x];
-            }
-            E.gThrs = gThrsIter;
-            E.fMaxNorm = fMaxNorm;
-            E.screenOn = screenOn ? 1 : 0;
-            E.gdesc = scr.gdesc.p;
-            E.nbr = scr.nbr.p;
-            E.pending = scr.pending.p;
-            E.cnt = scr.ecnt.p;
-            tg_prep += now_ms() - tq;
-            const double tE = now_ms();
-            launch_enum(E, st);
-            EnumCounters ec;
-            MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
-            MRX_CUDA(cudaStreamSynchronize(st));
-            tg_enum += now_ms() - tE;
-            const double tR = now_ms();
-            nNbr = ec.nNbr;
-            nCand = (long long)ec.nCand;
-            // generated input nodes, one round per missing level
-            const int nPending = ec.nPending;
-            while (nPending > 0) {
-                scr.newParents.reserve(nPending, false, st);
-                scr.genItems.reserve((size_t)2 * nPending, false, st);
-                E.newParents = scr.newParents.p;
-                E.genItems = scr.genItems.p;
-                MRX_CUDA(cudaMemsetAsync(&scr.ecnt.p->nUnresolved, 0, 2 * sizeof(int), st)); // nUnresolved, nNewParents
-                nResolveRounds++;
-                launch_enum_resolve(E, nPending, st);
-                MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
-                MRX_CUDA(cudaStreamSynchronize(st));
-                if (ec.nUnresolved == 0) break;
-                const int nNew = ec.nNewParents;
-                topo.reserve((size_t)fTotal + 8 * (size_t)nNew, st);
-                E.fChild0 = topo.child0.p;
-                E.fDepth = topo.depth.p;
-                E.fBound = topo.bound.p;
-                E.fFlag = topo.flag.p;
-                inp.dev.genCoefs.reserve((size_t)(fTotal - fRealN + 8 * nNew) * Kd, true, st);
-                inp.dev.genNorms.reserve((size_t)(fTotal - fRealN + 8 * nNew), true, st);
-                launch_enum_create(E, nNew, fTotal, st);
-                launch_gen_children(inp.dev.coefs.p, inp.dev.genCoefs.p, inp.dev.genNorms.p, fRealN, scr.genItems.p, nNew, K, filt, st);
-                fTotal += 8 * nNew;
-                S.gen_nodes += 8 * (long long)nNew;
-                inp.dev.nGen = fTotal - fRealN;
-            }
-            tg_resolve += now_ms() - tR;
-        }
+        upload_band_tables(bt, DM, false, st);
         // ---- generated input nodes: parents in creation order; a parent created this iteration must be
         //      filled before its own children -> waves
         if (!newParents.empty()) {
@@ -768,16 +615,14 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
             scr.reduceItems.reserve(reduceItems.size(), false, st);
             MRX_CUDA(cudaMemcpyAsync(scr.reduceItems.p, reduceItems.data(), sizeof(int) * reduceItems.size(), cudaMemcpyHostToDevice, st));
         }
-        if (!usePipe) {
-            scr.gdesc.reserve(nG, false, st);
-            scr.nbr.reserve(std::max<size_t>(nbr.size(), 1), false, st);
-            scr.gslots.reserve(nG, false, st);
-            MRX_CUDA(cudaMemcpyAsync(scr.gdesc.p, gdesc.data(), sizeof(GDesc) * nG, cudaMemcpyHostToDevice, st));
-            if (!nbr.empty())
-                MRX_CUDA(cudaMemcpyAsync(scr.nbr.p, nbr.data(), sizeof(NbrEntry) * nbr.size(), cudaMemcpyHostToDevice, st));
-            MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
-            nNbr = (int)nbr.size();
-        }
+        scr.gdesc.reserve(nG, false, st);
+        scr.nbr.reserve(std::max<size_t>(nbr.size(), 1), false, st);
+        scr.gslots.reserve(nG, false, st);
+        MRX_CUDA(cudaMemcpyAsync(scr.gdesc.p, gdesc.data(), sizeof(GDesc) * nG, cudaMemcpyHostToDevice, st));
+        if (!nbr.empty())
+            MRX_CUDA(cudaMemcpyAsync(scr.nbr.p, nbr.data(), sizeof(NbrEntry) * nbr.size(), cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(scr.gslots.p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
+        nNbr = (int)nbr.size();
 
         // gThrs (ConvolutionCalculator.cpp:241-248)
         double gThrs = g.squareNorm;
@@ -818,147 +663,31 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         tp_upload += now_ms() - tq;
         tq = now_ms();
         MRX_CUDA(cudaEventRecord(ev0, st));
-        if (usePipe) {
-            P.gdesc = scr.gdesc.p; // node-level descriptors: balancing happens on the device
-            SlowCall scM("reserve masks/counts", profile);
-            scr.masks.reserve(std::max<long long>(nCand, 1), false, st);
-            scr.cnt64.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
-            scr.segOff.reserve(std::max<size_t>((size_t)nNbr * 64, 1), false, st);
-            scr.blockCnt.reserve((size_t)nL * 8 + 8, false, st);
-            scr.blockTupOff.reserve((size_t)nL * 8 + 9, false, st);
-            scr.blockUnitOff.reserve((size_t)nL * 8 + 9, false, st);
-            DevBuf<double> &normsBuf = scr.normsW[world > 1 ? iter % kCommStageBufs : 0];
-            normsBuf.reserve((size_t)world * rowsPerRank * 8 + 8, false, st);
-            scr.header.reserve(1, false, st);
-            scr.queue.reserve(1, false, st);
-            PipeBuffers B{};
-            B.masks = scr.masks.p;
-            B.cnt64 = scr.cnt64.p;
-            B.segOff = scr.segOff.p;
-            B.blockCnt = scr.blockCnt.p;
-            B.blockTupOff = scr.blockTupOff.p;
-            B.blockUnitOff = scr.blockUnitOff.p;
-            scr.pTileTotal.reserve((size_t)nL * 8 / 2048 + 2, false, st);
-        scr.pTileBaseTup.reserve((size_t)nL * 8 / 2048 + 2, false, st);
-        scr.pTileBaseUnit.reserve((size_t)nL * 8 / 2048 + 2, false, st);
-        B.tileTotal = scr.pTileTotal.p;
-        B.tileBaseTup = scr.pTileBaseTup.p;
-        B.tileBaseUnit = scr.pTileBaseUnit.p;
-        B.header = scr.header.p;
-            B.queue = scr.queue.p;
-            scM.~SlowCall();
-            scM.on = false;
-            launch_pipe_screen(P, B, nNbr, st);
-            launch_pipe_scan(P, B, nL, unitTuples, st);
-            PipeHeader hdr;
-            {
-                SlowCall sc("header sync", profile);
-                MRX_CUDA(cudaMemcpyAsync(&hdr, scr.header.p, sizeof(hdr), cudaMemcpyDeviceToHost, st));
-                MRX_CUDA(cudaStreamSynchronize(st));
-            }
-            SlowCall scT("reserve tuples/units/partials", profile);
-            if (hdr.totalTuples >= (1ull << 32)) MRX_ABORT("apply: tuple list of one iteration exceeds 2^32 records");
-            scr.tuples.reserve(std::max<size_t>((size_t)hdr.totalTuples, 1), false, st);
-            scr.units2.reserve(std::max<size_t>((size_t)hdr.nUnits, 1), false, st);
-            scr.partials.reserve(std::max<size_t>((size_t)hdr.nUnits * Kd, 1), false, st);
-            B.tuples = scr.tuples.p;
-            B.units = scr.units2.p;
-            B.partials = scr.partials.p;
-            scT.~SlowCall();
-            scT.on = false;
-            launch_pipe_fill(P, B, nNbr, nL, st);
-            MRX_CUDA(cudaEventRecord(ev2, st));
-            launch_pipe_contract(P, B, hdr.nUnits, st);
-            MRX_CUDA(cudaEventRecord(ev3, st));
-            // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-            double *normsMine = normsBuf.p + (size_t)rank * rowsPerRank * 8;
-            if (world == 1) {
-                launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
-                MRX_CUDA(cudaEventRecord(ev1, st));
-            } else {
-                // ---- exchange over NVLink. Output blocks: the reduce kernel writes this rank's rows of a rank-major staging
-                //      buffer; copy engines push them into every peer's HBM (CUDA IPC mapping) on a second stream while
-                //      the next iteration already runs, and the whole iteration is unpacked into the node store one
-                //      iteration later. Norms (8 doubles per node, the input of the split decision that every rank takes
-                //      identically) go through one in-place ncclAllGather, which is also the only cross-rank
-                //      synchronisation: a rank enters it only after its previous push has completed, so whoever leaves it
-                //      knows that the previous iteration's rows of all peers have landed.
-                const int b = iter % kCommStageBufs;
-                const size_t rowBytes = (size_t)ncoef * sizeof(double);
-                const size_t segBytes = (size_t)rowsPerRank * rowBytes;
-                if ((size_t)world * segBytes > comm_stage_bytes(comm)) {
-                    flush_pending();
-                    comm_stage_reserve(comm, (size_t)world * segBytes, st);
-                }
-                const bool push = comm_peer_push_enabled(comm);
-                double *stageB = reinterpret_cast<double *>(comm_stage(comm, b));
-                launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st,
-                                   reinterpret_cast<double *>(comm_stage(comm, b) + (size_t)rank * segBytes));
-                MRX_CUDA(cudaEventRecord(ev1, st));
-                scr.gslotsAll[b].reserve(nG, false, st);
-                MRX_CUDA(cudaMemcpyAsync(scr.gslotsAll[b].p, workVec.data(), sizeof(int) * nG, cudaMemcpyHostToDevice, st));
-                if (push) {
-                    MRX_CUDA(cudaEventRecord(comm_ev_reduced(comm, b), st));
-                    comm_push(comm, b, (size_t)rank * segBytes, (size_t)nL * rowBytes);
-                    if (pend.active) MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
-                    comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
-                    if (pend.active)
-                        launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)),
-                                            scr.gslotsAll[pend.buf].p, pend.nG, world, pend.rows, ncoef, scr.normsW[pend.buf].p,
-                                            out.dev.norms.p, st);
-                    pend.active = true;
-                    pend.buf = b;
-                    pend.nG = nG;
-                    pend.rows = rowsPerRank;
-                } else {
-                    comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
-                    comm_allgather(comm, stageB, segBytes, st);
-                    launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, normsBuf.p,
-                                        out.dev.norms.p, st);
-                }
-            }
-            iterTuples = (long long)hdr.totalTuples;
-            tuplesTotal += iterTuples;
-        } else {
-            launch_apply(P, (int)units.size(), st);
-            if (nPartials > 0) launch_reduce_partials(out.dev.coefs.p, scr.partials.p, scr.reduceItems.p, (int)reduceItems.size() / 3, ncoef, st);
-            MRX_CUDA(cudaEventRecord(ev1, st));
-            // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-            launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
-        }
-        // norms back to the host: work-vector order (pipeline) or the covering slot range (legacy kernels)
+        launch_apply(P, (int)units.size(), st);
+        if (nPartials > 0) launch_reduce_partials(out.dev.coefs.p, scr.partials.p, scr.reduceItems.p, (int)reduceItems.size() / 3, ncoef, st);
+        MRX_CUDA(cudaEventRecord(ev1, st));
+        // calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
+        launch_norms(out.dev.coefs.p, out.dev.norms.p, scr.gslots.p, nG, Kd, st);
+        // norms back to the host: the slot range covering the work vector
         int lo = 0;
         std::vector<double> range;
-        if (usePipe) {
-            range.resize((size_t)world * rowsPerRank * 8);
-            MRX_CUDA(cudaMemcpyAsync(range.data(), scr.normsW[world > 1 ? iter % kCommStageBufs : 0].p, sizeof(double) * range.size(),
-                                     cudaMemcpyDeviceToHost, st));
-        } else {
-            lo = *std::min_element(workVec.begin(), workVec.end());
-            int hi = *std::max_element(workVec.begin(), workVec.end());
-            range.resize((size_t)(hi - lo + 1) * 8);
-            MRX_CUDA(cudaMemcpyAsync(range.data(), out.dev.norms.p + (size_t)lo * 8, sizeof(double) * range.size(),
-                                     cudaMemcpyDeviceToHost, st));
-        }
+        lo = *std::min_element(workVec.begin(), workVec.end());
+        int hi = *std::max_element(workVec.begin(), workVec.end());
+        range.resize((size_t)(hi - lo + 1) * 8);
+        MRX_CUDA(cudaMemcpyAsync(range.data(), out.dev.norms.p + (size_t)lo * 8, sizeof(double) * range.size(),
+                                 cudaMemcpyDeviceToHost, st));
         MRX_CUDA(cudaStreamSynchronize(st));
         tp_wait += now_ms() - tq;
         tq = now_ms();
-        float ms = 0.f, msc = 0.f;
+        float ms = 0.f;
         MRX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         kernel_ms += ms;
-        if (usePipe) {
-            MRX_CUDA(cudaEventElapsedTime(&msc, ev2, ev3));
-            contract_ms += msc;
-        }
-        if (profile)
-            std::fprintf(stderr, "[mrx] iter %d nG %d nbr %d cand %lld tuples %lld kernels %.3f ms (contract %.3f ms, %.2f TF/s)\n", iter, nG,
-                         nNbr, nCand, iterTuples, ms, msc, msc > 0 ? iterTuples * 6.0 * K * K * K * K / (msc * 1e-3) / 1e12 : 0.0);
+        if (profile) std::fprintf(stderr, "[mrx] iter %d nG %d nbr %d cand %lld kernels %.3f ms\n", iter, nG, nNbr, nCand, ms);
         for (int i = 0; i < nG; i++) {
             int n = workVec[i];
             double sq = 0.0;
             for (int c = 0; c < 8; c++) {
-                // pipeline: rank-major layout of the cyclic distribution (world == 1: plain work-vector order)
-                double v = usePipe ? range[((size_t)(i % world) * rowsPerRank + i / world) * 8 + c] : range[(size_t)(n - lo) * 8 + c];
+                double v = range[(size_t)(n - lo) * 8 + c];
                 g.cnorm[(size_t)n * 8 + c] = v;
                 sq += v * v;
             }
@@ -1009,38 +738,23 @@ static void run_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp,
         iter++;
         tp_host += now_ms() - tq;
     }
-    if (world > 1) flush_pending();
     const double tLoopEnd = now_ms();
     if (profile)
         std::fprintf(stderr, "[mrx] run_apply ms: pre-loop %.2f loop %.2f\n", tLoop - tEnter, tLoopEnd - tLoop);
-    if (profile)
-        std::fprintf(stderr, "[mrx] gen phase ms: prep %.2f enum+sync %.2f resolve %.2f (%d rounds)\n", tg_prep, tg_enum, tg_resolve, nResolveRounds);
     if (profile)
         std::fprintf(stderr, "[mrx] host phases ms: tables %.2f enum %.2f phase2 %.2f gen %.2f upload %.2f wait %.2f split %.2f\n", tp_tables,
                      tp_enum, tp_phase2, tp_gen, tp_upload, tp_wait, tp_host);
     S.iterations = iter;
     S.ms_kernel = kernel_ms;
-    S.ms_contract = usePipe ? contract_ms : kernel_ms;
+    S.ms_contract = kernel_ms;
     unsigned long long counters[4];
     MRX_CUDA(cudaMemcpyAsync(counters, scr.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
     MRX_CUDA(cudaStreamSynchronize(st));
-    S.f_applied = usePipe ? tuplesTotal : (long long)counters[0];
+    S.f_applied = (long long)counters[0];
     S.f_applied_rank = S.f_applied;
-    if (world > 1) {
-        double h[2] = {(double)S.f_applied, (double)S.gen_nodes};
-        double *dsum = reinterpret_cast<double *>(scr.counters.p + 2);
-        MRX_CUDA(cudaMemcpyAsync(dsum, h, sizeof(h), cudaMemcpyHostToDevice, st));
-        comm_allreduce_sum(comm, dsum, 2, st);
-        MRX_CUDA(cudaMemcpyAsync(h, dsum, sizeof(h), cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaStreamSynchronize(st));
-        S.f_applied = (long long)(h[0] + 0.5);
-        S.gen_nodes = (long long)(h[1] + 0.5);
-    }
     out.dev.nNodes = g.nReal;
     MRX_CUDA(cudaEventDestroy(ev0));
     MRX_CUDA(cudaEventDestroy(ev1));
-    MRX_CUDA(cudaEventDestroy(ev2));
-    MRX_CUDA(cudaEventDestroy(ev3));
     if (profile) std::fprintf(stderr, "[mrx] run_apply ms: post-loop %.2f\n", now_ms() - tLoopEnd);
 }
 
@@ -1588,7 +1302,10 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     const bool bareRoots = out.host.nReal == out.host.nRoots;
     const bool pipe = use_pipeline(out);
     if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr);
-    else run_apply(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm));
+    else {
+        if (comm_world(comm) > 1) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11) only");
+        run_apply_legacy(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);
+    }
     S.ms_build = now_ms() - tb;
 
     // ---- post: TopDown(+=), BottomUp, square norm, cleanup (apply.cpp:81-87)
@@ -1664,7 +1381,7 @@ void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int d
     out.dev.norms.reserve((size_t)g.nReal * 8, false, st);
     MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p, 0, sizeof(double) * (size_t)g.nReal * g.ncoef, st));
     if (use_pipeline(out)) run_apply_pipe(-1.0, out, oper, inp, 0, false, dir, workVec, S, nullptr);
-    else run_apply(-1.0, out, oper, inp, 0, false, dir, workVec, S);
+    else run_apply_legacy(-1.0, out, oper, inp, 0, false, dir, workVec, S);
     S.ms_build = now_ms() - tb;
     double tp = now_ms();
     op.clearBandWidths();

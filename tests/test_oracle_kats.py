@@ -226,3 +226,37 @@ def test_hot_path_aborts_without_device():
     r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode != 0 and "SURVIVED" not in r.stdout
     assert "no CPU fallback" in r.stderr
+
+
+def test_pruned_build_grid_equals_generic_loop(libs):
+    """build_grid of a Gaussian expansion: the pruned DFS (only nodes a term can split are visited) must create the same
+    nodes in the same slot order as the generic TreeBuilder loop over all end nodes (MRX_GRID_GENERIC=1, the restatement of
+    grid.cpp:78-123 + TreeBuilder.cpp:38-86 with AnalyticAdaptor.h:42-50)."""
+    import math
+    import os
+    import numpy as np
+    mw, _ = libs
+    from mrcpp_b200 import _lib
+    mra = mw.MultiResolutionAnalysis(5, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rng = np.random.default_rng(5)
+    func = mw.GaussExp()
+    for _ in range(25):
+        beta = 10.0 ** rng.uniform(0.5, 3)
+        func.append(mw.GaussFunc(beta, (beta / math.pi) ** 1.5 / 25, tuple(rng.uniform(-8, 8, 3))))
+    n, coef, alpha, pos, power = mw._gauss_arrays(func)
+
+    def grid():
+        t = mw.FunctionTree(mra)
+        # prec = 1e3: the projection itself never refines, the node set is the grid
+        _lib.load().mrx_project_gaussians(t._h, 1e3, n, mw._dp(coef), mw._dp(alpha), mw._dp(pos), mw._ip(power), 1, 0)
+        return t.to_arrays(coefs=False)
+
+    a = grid()
+    os.environ["MRX_GRID_GENERIC"] = "1"
+    try:
+        b = grid()
+    finally:
+        del os.environ["MRX_GRID_GENERIC"]
+    assert len(a["scale"]) > 1000
+    for key in ("scale", "transl", "parent", "child0"):
+        assert np.array_equal(a[key], b[key]), key
