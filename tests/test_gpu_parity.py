@@ -208,6 +208,31 @@ def test_apply_variants(gpu, k, prec, max_iter, abs_prec):
     assert_same_tree(gg, gc)
 
 
+def test_apply_refines_prebuilt_grid(gpu):
+    """`out` enters with a pre-built grid (apply.cpp:63-66 keeps it as the starting grid) and is refined further: the first
+    work vector holds branch and leaf nodes of mixed depths, only the leaves may split, children of several depths share the
+    later work vectors. Node set, tuple count and coefficients vs the oracle."""
+    mw, orc = gpu
+    prec, k = 1e-5, 7
+    mra = world(mw, k)
+    func = gaussians(4, 77, box=4.0, lo=1.0, hi=2.0)
+    P = mw.PoissonOperator(mra, prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, fg, func)
+    orc.project(prec, fc, func)
+    coarse = mw.FunctionTree(mra)
+    orc.apply(1e-2, coarse, P, fc)          # a shallow adaptive grid to start from
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.copy_grid(gg, coarse)
+    mw.copy_grid(gc, coarse)
+    assert gg.getNNodes() > 8
+    sg = mw.apply(prec, gg, P, fg)
+    sc = orc.apply(prec, gc, P, fc)
+    assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes and sg.iterations == sc.iters
+    assert gg.getNNodes() > coarse.getNNodes()
+    assert_same_tree(gg, gc)
+
+
 def test_multi_center_density(gpu):
     """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
     mw, orc = gpu
