@@ -221,7 +221,7 @@ def test_apply_refines_prebuilt_grid(gpu):
     mw.project(prec, fg, func)
     orc.project(prec, fc, func)
     coarse = mw.FunctionTree(mra)
-    orc.apply(1e-2, coarse, P, fc)          # a shallow adaptive grid to start from
+    orc.apply(prec, coarse, P, fc, maxIter=2)  # a shallow adaptive grid to start from (roots + two refinement levels)
     gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
     mw.copy_grid(gg, coarse)
     mw.copy_grid(gc, coarse)
