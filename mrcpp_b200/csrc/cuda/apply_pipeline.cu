@@ -71,9 +71,12 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
         for (int ft = 1; ft < 8; ft++) fn[ft] = 0.0;
     }
     unsigned long long fmask = 0ull; // (gt,ft) bits whose f component is not negligible (:254-255)
+    double fnMax = 0.0;
 #pragma unroll
-    for (int ft = 0; ft < 8; ft++)
+    for (int ft = 0; ft < 8; ft++) {
         if (!(fn[ft] < kMachineZero)) fmask |= 0x0101010101010101ull << ft;
+        fnMax = fmax(fnMax, fn[ft]);
+    }
     int d[3];
     decode_delta(nb.code, di.W, d);
     int cnt0 = 0, cnt1 = 0; // lane l counts bits l and l + 32
@@ -97,6 +100,21 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
                 // instead of 64 scattered table reads
                 const int4 s4 = P.bsfSep[(size_t)term * P.DM + g.depth];
                 const int sep[4] = {s4.x, s4.y, s4.z, s4.w};
+                // whole-candidate early-out: rounded products of non-negative numbers are monotone, so the same expression
+                // evaluated on the component-wise maxima bounds every (gt, ft) combination from above -- exact, no slack
+                {
+                    const double m0 = fmax(fmax(n0[0], n0[1]), fmax(n0[2], n0[3]));
+                    const double m1 = fmax(fmax(n1[0], n1[1]), fmax(n1[2], n1[3]));
+                    const double m2 = fmax(fmax(n2[0], n2[1]), fmax(n2[2], n2[3]));
+                    const int sm = max(max(sep[0], sep[1]), max(sep[2], sep[3]));
+                    double oMax = 1.0;
+                    oMax *= m0;
+                    oMax *= m1;
+                    oMax *= m2;
+                    const double tMax = (sm * sm * sm * 64) * fnMax;
+                    if (!(oMax * tMax > P.gThrs)) todo = 0ull;
+                }
+                if (todo)
 #pragma unroll
                 for (int gt = 0; gt < 8; gt++) {
 #pragma unroll
