@@ -25,9 +25,17 @@ import os as _os
 if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
     # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores
     _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
-# bench prints exactly one JSON line on stdout: if the environment turns NCCL logging on (NCCL_DEBUG=VERSION/WARN print a
-# version banner), send it to stderr
-_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# bench prints exactly ONE JSON line on stdout. Libraries write banners there (NCCL prints its version on communicator
+# creation on these boxes), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved
+# original descriptor.
+import sys as _sys
+_sys.stdout.flush()
+_REAL_STDOUT = _os.dup(1)
+_os.dup2(2, 1)
+
+
+def emit(line):
+    _os.write(_REAL_STDOUT, (line + "\n").encode())
 import argparse
 import json
 import math
@@ -154,7 +162,7 @@ def run_reference(args, rank, world):
                          "sample": f"{args.cpu_centers}-centre subset of the workload density, full adaptive apply"},
         "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_config(args, centers, sample=False):
@@ -338,7 +346,7 @@ def main():
         line["transforms"] = transforms_roofline(L, ft, K)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, mw, mra, P)
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
