@@ -9,7 +9,7 @@
 //   WaveletAdaptor::splitNode / tree_utils::split_check       src/treebuilders/WaveletAdaptor.h:51-54, tree_utils.cpp:47-65
 //   TreeAdaptor::splitNodeVector                              src/treebuilders/TreeAdaptor.h:41-54
 //
-// run_apply_pipe (orders with a work-list contraction kernel, K = 4, 6, 8, 10, 12; one or many GPUs): per refinement
+// run_apply_pipe (orders with a work-list contraction kernel, K = 4..12; one or many GPUs): per refinement
 //   iteration  enumerate band (apply_enum.cu) -> screen / scan / fill / contract / reduce (apply_pipeline.cu) ->
 //   [norm all-gather + peer push of the coefficient rows (comm.cu)] -> bookkeeping + split + next work vector
 //   (apply_split.cu). The device owns the work vector; the host reads back three small records per iteration and replays
@@ -344,7 +344,7 @@ static void ensure_input_topology(mrx_tree &inp, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// First-generation path, kept for the orders the work-list pipeline does not cover (odd K = even polynomial order) and as
+// First-generation path, kept for the orders the work-list pipeline does not cover (k < 3, k > 11) and as
 // a development cross-check (MRX_LEGACY=1): band enumeration and the refinement loop on the host, one CTA per output
 // node (apply_kernels.cu). Single GPU only.
 static void run_apply_legacy(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
@@ -384,7 +384,7 @@ static void run_apply_legacy(double prec, mrx_tree &out, mrx_oper &oper, mrx_tre
     ensure_input_topology(inp, st);
     DeviceTree &fd = inp.dev;
     const double fMaxNorm = fd.topoMaxNorm;
-    std::vector<double> fNodeNorm; // host enumeration of the legacy (odd K) path only
+    std::vector<double> fNodeNorm; // host enumeration
     fNodeNorm.resize(fRealN);
     for (int n = 0; n < fRealN; n++) fNodeNorm[n] = std::sqrt(f.sqn[n]);
     double tp_enum = 0, tp_phase2 = 0, tp_gen = 0, tp_upload = 0, tp_wait = 0, tp_host = 0, tp_tables = 0;
@@ -1303,7 +1303,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     const bool pipe = use_pipeline(out);
     if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr);
     else {
-        if (comm_world(comm) > 1) MRX_ABORT("sharded apply is implemented for the work-list pipeline (k = 3, 5, 7, 9, 11) only");
+        if (comm_world(comm) > 1) MRX_ABORT("sharded apply is implemented for the work-list pipeline (orders 3..11) only");
         run_apply_legacy(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);
     }
     S.ms_build = now_ms() - tb;

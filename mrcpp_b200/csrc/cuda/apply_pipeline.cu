@@ -730,8 +730,14 @@ template <int K> __global__ void __launch_bounds__(128) pipe_contract_coop_kerne
 #pragma unroll
             for (int mt = 0; mt < D::MT; mt++) {
                 const int c = rr + 8 * mt, col = 8 * n0 + 2 * q;
-                if (n0 < D::NT && c < K && col < D::K2)
-                    *reinterpret_cast<double2 *>(pb + col + D::K2 * c) = make_double2(acc[i][mt][0], acc[i][mt][1]);
+                if (n0 < D::NT && c < K && col < D::K2) {
+                    if (K & 1) { // odd K: rows of the dense block are not 16-byte aligned, K^2 is odd
+                        pb[col + D::K2 * c] = acc[i][mt][0];
+                        if (col + 1 < D::K2) pb[col + 1 + D::K2 * c] = acc[i][mt][1];
+                    } else {
+                        *reinterpret_cast<double2 *>(pb + col + D::K2 * c) = make_double2(acc[i][mt][0], acc[i][mt][1]);
+                    }
+                }
             }
         }
     }
@@ -763,9 +769,34 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const i
     if (blk >= nBlocks) return;
     const int u0 = B.blockUnitOff[blk], u1 = B.blockUnitOff[blk + 1];
     const int slot = gslots[blk >> 3], gt = blk & 7;
-    double2 *o = reinterpret_cast<double2 *>(stageRows ? stageRows + (size_t)blk * Kd : gCoefs + ((size_t)slot * 8 + gt) * Kd);
+    double *oS = stageRows ? stageRows + (size_t)blk * Kd : gCoefs + ((size_t)slot * 8 + gt) * Kd;
+    double2 *o = reinterpret_cast<double2 *>(oS);
     double n2 = 0.0;
-    // K is even on this path, so a block is a whole number of 16-byte pairs; 8 pairs per lane and trip
+    if (Kd & 1) {
+        // odd K: blocks are not 16-byte aligned; element-wise, 8 elements per lane and trip (same unit order)
+        for (int base = 0; base < Kd; base += 256) {
+            double s1[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) s1[i] = 0.0;
+            for (int u = u0; u < u1; u++) {
+                const double *p = B.partials + (size_t)u * Kd;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int e = base + i * 32 + lane;
+                    if (e < Kd) s1[i] += p[e];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int e = base + i * 32 + lane;
+                if (e < Kd) {
+                    oS[e] = s1[i];
+                    n2 = fma(s1[i], s1[i], n2);
+                }
+            }
+        }
+    } else
+    // even K: a block is a whole number of 16-byte pairs; 8 pairs per lane and trip
     for (int base = 0; base < Kd / 2; base += 256) {
         double2 s[8];
 #pragma unroll
@@ -900,7 +931,7 @@ template <int K> void launch_contract_pad(const ApplyParams &P, const PipeBuffer
     pipe_contract_pad_kernel<K><<<grid, 256, bytes, st>>>(P, B, nUnits, nWarps);
 }
 
-bool pipe_supports_order(int K) { return K == 4 || K == 6 || K == 8 || K == 10 || K == 12; }
+bool pipe_supports_order(int K) { return K >= 4 && K <= 12; }
 
 void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
     if (nUnits <= 0) return;
@@ -924,6 +955,14 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
         if (useFma) launch_contract_fma<12>(P, B, nUnits, st);
         else if (warpPrivate) launch_contract_pad<12>(P, B, nUnits, st);
         else launch_contract_coop<12>(P, B, nUnits, st);
+    } else if (P.K == 5) { // odd K (even polynomial orders): same padded-DMMA kernel, element-wise partial blocks
+        launch_contract_coop<5>(P, B, nUnits, st);
+    } else if (P.K == 7) {
+        launch_contract_coop<7>(P, B, nUnits, st);
+    } else if (P.K == 9) {
+        launch_contract_coop<9>(P, B, nUnits, st);
+    } else if (P.K == 11) {
+        launch_contract_coop<11>(P, B, nUnits, st);
     } else {
         MRX_ABORT("pipeline contraction: unsupported order");
     }

@@ -67,7 +67,7 @@ def test_bottom_up_and_norms(gpu, k):
     assert abs(a.getSquareNorm() - b.getSquareNorm()) <= 1e-13 * b.getSquareNorm()
 
 
-@pytest.mark.parametrize("k,n,prec", [(5, 3, 1e-4), (7, 6, 1e-5), (9, 2, 1e-4)])
+@pytest.mark.parametrize("k,n,prec", [(5, 3, 1e-4), (7, 6, 1e-5), (9, 2, 1e-4), (6, 2, 1e-4)])
 def test_device_projection(gpu, k, n, prec):
     """project with the quadrature, cvTransform, in-node compression and norms on the DEVICE vs the oracle
     projection: same node set; coefficients within 1e-12 of the node norm (device exp() and glibc exp() differ by <= 1 ulp);
@@ -145,7 +145,7 @@ def test_top_down_roundtrip(gpu, k):
     assert np.array_equal(before["transl"], after["transl"])
 
 
-@pytest.mark.parametrize("k,prec", [(5, 1e-3), (7, 1e-5), (9, 1e-4), (3, 1e-2), (11, 1e-4)])
+@pytest.mark.parametrize("k,prec", [(5, 1e-3), (7, 1e-5), (9, 1e-4), (3, 1e-2), (11, 1e-4), (4, 1e-3), (6, 1e-4), (8, 1e-4), (10, 1e-4)])
 def test_poisson_apply_adaptive(gpu, k, prec):
     """examples/poisson.cpp (C1): adaptive apply; node set, tuple count, coefficients, energy."""
     mw, orc = gpu
@@ -193,7 +193,7 @@ def test_poisson_apply_fixed_grid(gpu, k, prec):
 @pytest.mark.parametrize("k,prec,max_iter,abs_prec", [(7, 1e-4, 2, False), (7, 1e-4, -1, True), (5, 1e-3, 1, True), (4, 1e-3, -1, False)])
 def test_apply_variants(gpu, k, prec, max_iter, abs_prec):
     """maxIter-limited refinement (TreeBuilder.cpp:73), absolute precision (tree_utils.cpp:55-57) and an even order
-    (k = 4 -> K = 5 runs the generic one-CTA-per-node kernel with host-side band enumeration)."""
+    (k = 4 -> K = 5: odd K, element-wise partial blocks and the FMA transform kernels)."""
     mw, orc = gpu
     mra = world(mw, k)
     func = gaussians(3, 21, box=4.0, lo=1.0, hi=2.0)

@@ -33,10 +33,10 @@ def test_sharded_apply_world1(libs):
     assert np.array_equal(A["transl"], B["transl"]) and np.array_equal(A["coefs"], B["coefs"])
 
 
-@pytest.mark.parametrize("args,env", [(["1e-5", "6"], {}), (["1e-5", "6"], {"MRX_NO_IPC": "1"}), (["1e-4", "4", "11"], {}), (["1e-4", "4", "5"], {})])
+@pytest.mark.parametrize("args,env", [(["1e-5", "6"], {}), (["1e-5", "6"], {"MRX_NO_IPC": "1"}), (["1e-4", "4", "11"], {}), (["1e-4", "4", "5"], {}), (["1e-4", "4", "6"], {})])
 def test_sharded_apply_two_ranks(libs, args, env):
     """2 ranks: every rank must end with the bit-identical tree of a single-GPU apply (k = 7 with the peer-push and with
-    the NCCL coefficient exchange, k = 11 and k = 5 with the padded contraction kernels)."""
+    the NCCL coefficient exchange, k = 11, k = 5 and k = 6 (odd K) with the padded contraction kernels)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (covered by tools/shard_check.py under gpurun --gpus 2)")
