@@ -233,6 +233,32 @@ def test_apply_refines_prebuilt_grid(gpu):
     assert_same_tree(gg, gc)
 
 
+def test_identity_convolution_noncubic_world(gpu):
+    """The reference's identity-convolution case (tests/operators/identity_convolution.cpp, 3D): generic single-term Gaussian
+    kernel through ConvolutionOperator, k = 5, a 1 x 2 x 3 world at root scale 1 with corner (-1, 0, 1). GPU vs oracle."""
+    mw, orc = gpu
+    proj_prec, apply_prec, build_prec = 1e-3, 1e-3, 1e-4
+    mra = mw.MultiResolutionAnalysis(5, 1, (-1, 0, 1), (1, 2, 3), 25)
+    beta = 1.0e4
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (-0.2, 0.5, 1.0))
+    expo = math.sqrt(1.0 / (build_prec / 10.0))
+    I = mw.ConvolutionOperator(mra, [(expo / math.pi) ** 1.5], [expo], build_prec)
+    fg, fc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(proj_prec, fg, f)
+    orc.project(proj_prec, fc, f)
+    assert_same_tree(fg, fc)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(apply_prec, gg, I, fg)
+    sc = orc.apply(apply_prec, gc, I, fc)
+    assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
+    assert_same_tree(gg, gc)
+    assert gg.getNNodes() <= fg.getNNodes()
+    # device projection on the same world
+    fd = mw.FunctionTree(mra)
+    mw.project(proj_prec, fd, f, device=True)
+    assert_same_tree(fd, fc)
+
+
 def test_multi_center_density(gpu):
     """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
     mw, orc = gpu

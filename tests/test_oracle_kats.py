@@ -260,3 +260,43 @@ def test_pruned_build_grid_equals_generic_loop(libs):
     assert len(a["scale"]) > 1000
     for key in ("scale", "transl", "parent", "child0"):
         assert np.array_equal(a[key], b[key]), key
+
+
+def _integrate(tree_arrays, K, root_scale, n_roots):
+    """FunctionTree::integrate for the interpolating basis (FunctionNode.cpp integrateInterpolating): over the root nodes,
+    sum_i s_i prod_d sqrt(w_{i_d}) * 2^{-D n / 2}."""
+    import numpy as np
+    x, w = np.polynomial.legendre.leggauss(K)
+    sw = np.sqrt(w / 2.0)
+    w3 = np.einsum("i,j,k->kji", sw, sw, sw).reshape(-1)  # x index fastest
+    s = tree_arrays["coefs"][:n_roots, :K ** 3]
+    return float((s * w3).sum() * 2.0 ** (-3 * root_scale / 2.0))
+
+
+def test_identity_convolution_reference_case(libs):
+    """tests/operators/identity_convolution.cpp "Apply identity convolution operator" (3D): k = 5, world of 1 x 2 x 3 root boxes
+    at scale 1 with corner (-1, 0, 1), unit-charge Gaussian beta = 1e4 at (-0.2, 0.5, 1.0) (tests/factory_functions.h),
+    IdentityConvolution(build_prec 1e-4) = ConvolutionOperator of the single-term IdentityKernel<3>(prec / 10)
+    (src/operators/IdentityKernel.h, IdentityConvolution.cpp:38-52). The reference requires: output not deeper / larger than
+    the input, integrals equal within apply_prec. Also pins the generic-kernel ConvolutionOperator path and a non-cubic world
+    with a positive root scale."""
+    import math
+    import numpy as np
+    mw, orc = libs
+    k, K = 5, 6
+    proj_prec, apply_prec, build_prec = 1e-3, 1e-3, 1e-4
+    mra = mw.MultiResolutionAnalysis(k, 1, (-1, 0, 1), (1, 2, 3), 25)
+    beta = 1.0e4
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (-0.2, 0.5, 1.0))
+    expo = math.sqrt(1.0 / (build_prec / 10.0))
+    I = mw.ConvolutionOperator(mra, [(expo / math.pi) ** 1.5], [expo], build_prec)
+    assert I.size() == 1
+    ft, gt = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    orc.project(proj_prec, ft, f)
+    orc.apply(apply_prec, gt, I, ft)
+    F, G = ft.to_arrays(), gt.to_arrays()
+    assert G["scale"].max() <= F["scale"].max()
+    assert len(G["scale"]) <= len(F["scale"])
+    fi, gi = _integrate(F, K, 1, 6), _integrate(G, K, 1, 6)
+    assert abs(fi - 1.0) < 10 * proj_prec
+    assert abs(gi - fi) <= apply_prec * abs(fi)
