@@ -36,7 +36,15 @@ for rep in range(3):
     dist.barrier(); torch.cuda.synchronize(); t = time.time()
     s2 = mw.apply(prec, g, P, f, comm=comm)
     dt = time.time() - t
+# the same sharded apply with the input tree in pinned host memory: every rank gathers the nodes ITS items read
+f.drop_device()
+g2 = mw.FunctionTree(mra)
+dist.barrier()
+s3 = mw.apply(prec, g2, P, f, comm=comm)
 A, B = g.to_arrays(), ref.to_arrays()
+C2 = g2.to_arrays()
+assert np.array_equal(C2["transl"], B["transl"]) and np.array_equal(C2["coefs"], B["coefs"]), "sharded apply on a host-resident input differs"
+assert 0 < s3.h2d_bytes < f.nbytes() and s3.f_applied == s1.f_applied
 same = np.array_equal(A["scale"], B["scale"]) and np.array_equal(A["transl"], B["transl"])
 err = np.abs(A["coefs"] - B["coefs"]).max() if same else -1
 print(f"rank {rank}/{world}: nodes {len(A['scale'])} same-topology {same} max|dcoef| {err:.3e} tuples sharded {s2.f_applied} single {s1.f_applied} "
