@@ -1354,16 +1354,27 @@ void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int d
             for (int n : workVec) {
                 if (g.isBranch(n)) continue;
                 if (g.nodes[n].scale + 2 > maxScale) continue;
+                // CopyAdaptor::splitNode asks, for every child c of the node, dimension d and offset |b| <= bw[d], whether the input
+                // tree has a node at the child's index shifted by b along d. A node of scale + 1 exists iff its parent is a branch,
+                // so the 8 x 3 x (2 bw + 1) look-ups collapse to: is one of the input nodes at THIS scale with index l, or l shifted
+                // along d by j in [(2 l_d - bw) >> 1, (2 l_d + 1 + bw) >> 1], a branch node?
                 bool split = false;
                 const auto idx0 = g.nodes[n];
-                for (int c = 0; c < 8 && !split; c++)
-                    for (int d = 0; d < 3 && !split; d++)
-                        for (int b = -bw[d]; b <= bw[d] && !split; b++) {
-                            std::array<int, 3> l;
-                            for (int dd = 0; dd < 3; dd++) l[dd] = 2 * idx0.l[dd] + ((c >> dd) & 1);
-                            l[d] += b;
-                            if (f.findNode(idx0.scale + 1, l) >= 0) split = true;
-                        }
+                auto branch_at = [&](const std::array<int, 3> &l) {
+                    const int m = f.findNode(idx0.scale, l);
+                    return m >= 0 && f.isBranch(m) && f.nodes[m].child0 < f.nReal;
+                };
+                split = branch_at(idx0.l);
+                for (int d = 0; d < 3 && !split; d++) {
+                    if (bw[d] == 0) continue;
+                    const int lo = (2 * idx0.l[d] - bw[d]) >> 1, hi = (2 * idx0.l[d] + 1 + bw[d]) >> 1;
+                    for (int j = lo; j <= hi && !split; j++) {
+                        if (j == idx0.l[d]) continue;
+                        std::array<int, 3> l = idx0.l;
+                        l[d] = j;
+                        split = branch_at(l);
+                    }
+                }
                 if (split) {
                     int c0 = g.createChildren(n, false);
                     for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
