@@ -142,13 +142,15 @@ void comm_stage_reserve(mrx_comm *c, size_t bytes, cudaStream_t st) {
     if (c->stageBase) {
         for (int r = 0; r < W; r++)
             if (r != c->rank && c->peerBase[r]) cudaIpcCloseMemHandle(c->peerBase[r]);
+    }
+    // second barrier: every rank has unmapped the old peers' buffers BEFORE anybody frees its own (freeing memory that an
+    // importing process still has mapped is undefined)
+    check(a.AllReduce(c->ipcScratch, c->ipcScratch, 1, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce(barrier)");
+    MRX_CUDA(cudaStreamSynchronize(st));
+    if (c->stageBase) {
         MRX_CUDA(cudaFree(c->stageBase));
         c->stageBase = nullptr;
     }
-    // second barrier: every rank has unmapped the old peers before anybody frees/reallocates (cudaFree of memory still
-    // mapped elsewhere is legal but the new allocation must not alias a stale mapping)
-    check(a.AllReduce(c->ipcScratch, c->ipcScratch, 1, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce(barrier)");
-    MRX_CUDA(cudaStreamSynchronize(st));
     size_t nb = std::max(bytes + bytes / 2, (size_t)64 << 20);
     nb = (nb + 4095) / 4096 * 4096;
     MRX_CUDA(cudaMalloc(&c->stageBase, nb * mrx_comm::kStageBufs));
@@ -248,7 +250,9 @@ void mrx_comm_destroy(mrx_comm *c) {
         cudaDeviceSynchronize();
         for (int r = 0; r < c->world; r++)
             if (r != c->rank && r < (int)c->peerBase.size() && c->peerBase[r]) cudaIpcCloseMemHandle(c->peerBase[r]);
-        cudaFree(c->stageBase);
+        // destruction is not collective: a peer may still have this buffer mapped, and freeing exported memory before every
+        // importer has closed it is undefined -> an exported buffer is left to process teardown
+        if (!c->ipcOk) cudaFree(c->stageBase);
     }
     if (c->ipcScratch) cudaFree(c->ipcScratch);
     if (c->pushStream) cudaStreamDestroy(c->pushStream);
