@@ -141,7 +141,7 @@ struct PipeBuffers {
     int *blockCnt;             // [nG*8]
     unsigned *blockTupOff;     // [nG*8+1]
     int *blockUnitOff;         // [nG*8+1]
-    unsigned long long *tileTotal;   // [nTiles] block-scan tiles (2048 blocks): tuples | units << 40
+    unsigned long long *tileTotal;   // [nTiles] block-scan tiles (2048 blocks): tuples | units << 36
     unsigned long long *tileBaseTup; // [nTiles]
     int *tileBaseUnit;               // [nTiles]
     PipeHeader *header;

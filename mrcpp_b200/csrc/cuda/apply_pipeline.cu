@@ -210,16 +210,17 @@ __device__ unsigned long long block_excl_scan(unsigned long long v, unsigned lon
 // Unit size: fixed, so that the summation order of a block does not depend on how much other work the launch holds
 // (results are bit-identical for any number of ranks sharing the work vector).
 constexpr int kBlockTile = 2048; // 256 threads x 8 blocks
+constexpr int kTupBits = 36;      // packed tile sums: low 36 bits tuples (an iteration holds < 2^32), high 28 bits units
 
 __global__ void __launch_bounds__(256) pipe_blockscan_tiles_kernel(PipeBuffers B, int nBlocks, int U) {
     __shared__ unsigned long long sm[33];
     const int base = blockIdx.x * kBlockTile + threadIdx.x * 8;
-    // low 40 bits: tuples, high 24 bits: units of the tile (a tile holds < 2^24 units and < 2^40 tuples)
+    // low kTupBits bits: tuples, high bits: units of the tile (2048 blocks x <= 17 K units: far below 2^28)
     unsigned long long v[8], local = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const unsigned long long c = (base + i < nBlocks) ? (unsigned long long)B.blockCnt[base + i] : 0ull;
-        v[i] = c | (((c + U - 1) / U) << 40);
+        v[i] = c | (((c + U - 1) / U) << kTupBits);
         local += v[i];
     }
     unsigned long long total;
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(256) pipe_blockscan_tiles_kernel(PipeBuffers B
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if (base + i < nBlocks) {
-            B.blockTupOff[base + i] = (unsigned)(run & ((1ull << 40) - 1));
-            B.blockUnitOff[base + i] = (int)(run >> 40);
+            B.blockTupOff[base + i] = (unsigned)(run & ((1ull << kTupBits) - 1));
+            B.blockUnitOff[base + i] = (int)(run >> kTupBits);
         }
         run += v[i];
     }
@@ -243,8 +244,8 @@ __global__ void __launch_bounds__(1024) pipe_blockscan_top_kernel(PipeBuffers B,
     unsigned long long locT = 0, locU = 0;
     for (int b = b0; b < b1; b++) {
         const unsigned long long t = B.tileTotal[b];
-        locT += t & ((1ull << 40) - 1);
-        locU += t >> 40;
+        locT += t & ((1ull << kTupBits) - 1);
+        locU += t >> kTupBits;
     }
     unsigned long long totT, totU;
     unsigned long long runT = block_excl_scan(locT, sm, totT);
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(1024) pipe_blockscan_top_kernel(PipeBuffers B,
         const unsigned long long t = B.tileTotal[b];
         B.tileBaseTup[b] = runT;
         B.tileBaseUnit[b] = (int)runU;
-        runT += t & ((1ull << 40) - 1);
-        runU += t >> 40;
+        runT += t & ((1ull << kTupBits) - 1);
+        runU += t >> kTupBits;
     }
     if (tid == 0) {
         B.blockTupOff[nBlocks] = (unsigned)totT;
