@@ -133,11 +133,12 @@ def test_coulomb_self_energy_reference_fixture(libs):
     assert abs(en - ana) / ana < 1e-3
 
 
-def test_coulomb_self_energy_poisson_example(libs):
-    """examples/poisson.cpp at k=5/prec 1e-4 (fast variant): energy vs sqrt(2 beta/pi) within prec."""
+@pytest.mark.parametrize("k", [5, 4, 6])
+def test_coulomb_self_energy_poisson_example(libs, k):
+    """examples/poisson.cpp at prec 1e-4 (fast variant), odd and even orders: energy vs sqrt(2 beta/pi) within prec."""
     mw, orc = libs
     prec = 1e-4
-    mra = mw.MultiResolutionAnalysis(5, -4, (-1, -1, -1), (2, 2, 2), 25)
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
     beta = 100.0
     f = _gauss(beta, (math.pi / 3,) * 3)
     ft = mw.FunctionTree(mra)
