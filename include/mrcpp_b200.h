@@ -86,6 +86,12 @@ int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp);
 int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
                           const double *pos /*[n][3]*/, const int *power /*[n][3] or NULL*/, int build_grid, int finalize);
 
+/* project(prec, out, f) of an arbitrary function given as a callback (src/treebuilders/project.cpp:85-104,
+ * ProjectionCalculator.cpp:34-51): host quadrature, refinement by the wavelet norm from the tree's current grid.
+ * threads_ok != 0: the callback may be called from several OpenMP threads at once. finalize as above. */
+typedef double (*mrx_func3)(const double r[3], void *user);
+int mrx_project_function(mrx_tree *tree, double prec, mrx_func3 f, void *user, int threads_ok, int finalize);
+
 /* The same build_grid + project with the per-node quadrature on the device:
  * ProjectionCalculator::calcNode (src/treebuilders/ProjectionCalculator.cpp:34-51: function values at the expanded child
  * quadrature points, MWNode::cvTransform(Backward), MWNode::mwTransform(Compression), MWNode::calcNorms) runs as CUDA kernels

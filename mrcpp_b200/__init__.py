@@ -262,6 +262,16 @@ def project(prec, out, func, build_grid=True, finalize=True, device=False):
                                       1 if build_grid else 0, 1 if finalize else 0)
 
 
+_FUNC3 = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
+
+
+def project_function(prec, out, func, finalize=True):
+    """project(prec, out, f) of an arbitrary Python callable f(x, y, z) (src/treebuilders/project.cpp:85-104): host
+    quadrature through mrx_project_function; the callable is invoked from one thread."""
+    cb = _FUNC3(lambda r, _u: float(func(r[0], r[1], r[2])))
+    _lib.load().mrx_project_function(out._h, float(prec), C.cast(cb, C.c_void_p), None, 0, 1 if finalize else 0)
+
+
 def copy_grid(out, inp):
     """src/treebuilders/grid.cpp:150-166"""
     _lib.load().mrx_tree_copy_grid(out._h, inp._h)

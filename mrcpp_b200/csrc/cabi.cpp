@@ -1,5 +1,7 @@
 // C-ABI entry points (include/mrcpp_b200.h). Host-side object management lives here; every hot-path
 // call forwards to the CUDA engine and aborts when no device was selected (no CPU fallback).
+#include <omp.h>
+
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -266,6 +268,31 @@ int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double
     tree->dev.topoNodes = -1;
     tree->dev.partial = false;
     // project.cpp:96-97: out.mwTransform(BottomUp); out.calcSquareNorm() -- on the device
+    if (finalize) {
+        mrx_mw_transform(tree, MRX_BOTTOM_UP, 1);
+        mrx_calc_square_norm(tree);
+    }
+    return 0;
+}
+
+int mrx_project_function(mrx_tree *tree, double prec, mrx_func3 f, void *user, int threads_ok, int finalize) {
+    if (finalize) require_device("mrx_project_function (final BottomUp transform)");
+    if (!f) MRX_ABORT("mrx_project_function: null callback");
+    Tree<3> &h = tree->host;
+    // ProjectionCalculator::calcNode on the host (quadrature at the expanded child points); callbacks that are not thread safe
+    // (e.g. a host-language closure) are called from one thread only
+    if (threads_ok) {
+        project<3>(prec, h, [f, user](const double *r) { return f(r, user); }, -1, false, /*finalize=*/false);
+    } else {
+        const int saved = omp_get_max_threads();
+        omp_set_num_threads(1);
+        project<3>(prec, h, [f, user](const double *r) { return f(r, user); }, -1, false, /*finalize=*/false);
+        omp_set_num_threads(saved);
+    }
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
     if (finalize) {
         mrx_mw_transform(tree, MRX_BOTTOM_UP, 1);
         mrx_calc_square_norm(tree);

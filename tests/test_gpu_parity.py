@@ -259,6 +259,44 @@ def test_identity_convolution_noncubic_world(gpu):
     assert_same_tree(fd, fc)
 
 
+def test_hydrogen_fixed_point_helmholtz(gpu):
+    """The reference's Helmholtz apply case (tests/operators/helmholtz_operator.cpp): psi_1s = -1/(2 pi) H_1 [V psi_1s] on
+    [-32, 32]^3, k = 5, inputs projected through the callback projection, output refined from psi's grid. GPU vs oracle,
+    and the norm of the right-hand side is 1 within apply_prec."""
+    mw, orc = gpu
+    proj_prec, apply_prec, build_prec = 3.0e-3, 3.0e-2, 3.0e-3
+    mra = mw.MultiResolutionAnalysis(5, -5, (-1, -1, -1), (2, 2, 2), 25)
+    c = 1.0 / math.sqrt(math.pi)
+
+    def psi(x, y, z):
+        return c * math.exp(-math.sqrt(x * x + y * y + z * z))
+
+    def vpsi(x, y, z):
+        r = math.sqrt(x * x + y * y + z * z)
+        return -c * math.exp(-r) / r
+
+    pg, vg = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project_function(proj_prec, pg, psi)      # host quadrature + device BottomUp
+    mw.project_function(proj_prec, vg, vpsi)
+    pc, vc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    for t, f in ((pc, psi), (vc, vpsi)):
+        mw.project_function(proj_prec, t, f, finalize=False)
+        orc.mw_transform_up(t)
+        orc.calc_square_norm(t)
+    assert_same_tree(vg, vc)
+    H = mw.HelmholtzOperator(mra, 1.0, build_prec)
+    gg, gc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.copy_grid(gg, pg)
+    mw.copy_grid(gc, pc)
+    sg = mw.apply(apply_prec, gg, H, vg)
+    sc = orc.apply(apply_prec, gc, H, vc)
+    assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
+    assert_same_tree(gg, gc)
+    gg.rescale(-1.0 / (2.0 * math.pi))
+    assert abs(math.sqrt(gg.getSquareNorm()) - 1.0) < apply_prec
+    assert abs(mw.dot(gg, pg) - 1.0) < apply_prec
+
+
 def test_multi_center_density(gpu):
     """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
     mw, orc = gpu
