@@ -126,6 +126,11 @@ int mrx_oper_band_widths(mrx_oper *oper, double prec, int *band_max, int band_ma
 int mrx_oper_node(const mrx_oper *oper, int term, int depth, int transl, double *mats /*4*(k+1)^2*/, double *norms /*4*/);
 int mrx_oper_depth(const mrx_oper *oper, int term);
 int mrx_oper_max_transl(const mrx_oper *oper, int term, int depth);
+/* table introspection (tests): Gauss-Legendre roots / weights on [0, 1] (GaussQuadrature.cpp:157-193 through
+ * QuadratureCache.cpp:41-45) and the interpolating scaling functions phi_j of order k or their derivatives
+ * (InterpolatingBasis.cpp:62-84), which feed the projection and the ABGV operator construction */
+int mrx_quadrature(int n, double *roots, double *weights);
+double mrx_interp_scaling(int k, int j, double x, int derivative);
 /* PoissonKernel / HelmholtzKernel expansions (tests: size()==26 / 33 KATs) */
 int mrx_poisson_kernel(double epsilon, double r_min, double r_max, double *coef, double *expo, int cap);
 int mrx_helmholtz_kernel(double mu, double epsilon, double r_min, double r_max, double *coef, double *expo, int cap);

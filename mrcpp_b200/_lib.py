@@ -57,6 +57,8 @@ SIGNATURES = {
     "mrx_tree_copy_grid": (_I, [_P, _P]),
     "mrx_project_gaussians": (_I, [_P, _D, _I, _PD, _PD, _PD, _PI, _I, _I]),
     "mrx_project_gaussians_device": (_I, [_P, _D, _I, _PD, _PD, _PD, _PI, _I]),
+    "mrx_quadrature": (_I, [_I, _PD, _PD]),
+    "mrx_interp_scaling": (_D, [_I, _I, _D, _I]),
     "mrx_project_function": (_I, [_P, _D, C.c_void_p, _P, _I, _I]),
     "mrx_poisson_create": (_P, [_P, _D]),
     "mrx_helmholtz_create": (_P, [_P, _D, _D]),

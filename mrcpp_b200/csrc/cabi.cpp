@@ -395,6 +395,17 @@ int mrx_oper_node(const mrx_oper *oper, int term, int depth, int transl, double 
     if (norms) std::memcpy(norms, t.nodeNorms(depth, transl), sizeof(double) * 4);
     return 0;
 }
+int mrx_quadrature(int n, double *roots, double *weights) {
+    const Quadrature &q = quadrature(n);
+    for (int i = 0; i < n; i++) {
+        if (roots) roots[i] = q.roots[i];
+        if (weights) weights[i] = q.weights[i];
+    }
+    return n;
+}
+double mrx_interp_scaling(int k, int j, double x, int derivative) {
+    return derivative ? interp_scaling_deriv(k, j, x) : interp_scaling_eval(k, j, x);
+}
 int mrx_poisson_kernel(double epsilon, double r_min, double r_max, double *coef, double *expo, int cap) {
     GaussExp<1> k = poisson_kernel(epsilon, r_min, r_max);
     for (int i = 0; i < (int)k.size() && i < cap; i++) {

@@ -339,3 +339,39 @@ def test_hydrogen_1s_helmholtz_fixed_point(libs):
     # and it is the same function: overlap with psi close to 1 as well (psi_{n+1} = -1/(2 pi) H[V psi], so <psi|psi_{n+1}> > 0)
     overlap = -orc.dot(p1, p0) / (2.0 * math.pi)
     assert abs(overlap - 1.0) < apply_prec
+
+
+def test_quadrature_and_scaling_basis(libs):
+    """tests/core/scaling_basis.cpp (orthonormality of the interpolating scaling functions, orders 1, 6, 10) and the
+    Gauss-Legendre rule behind every projection (GaussQuadrature.cpp:157-193): roots / weights against numpy's, exactness for
+    polynomials up to degree 2n - 1, and phi_j(x_i) = delta_ij / sqrt(w_i) (InterpolatingBasis.cpp:62-84)."""
+    import ctypes as C
+    mw, _ = libs
+    from mrcpp_b200 import _lib
+    L = _lib.load()
+    for n in (2, 6, 8, 12, 24):
+        r, w = np.zeros(n), np.zeros(n)
+        assert L.mrx_quadrature(n, mw._dp(r), mw._dp(w)) == n
+        x, ww = np.polynomial.legendre.leggauss(n)
+        # the reference's Newton iteration stops at EPS = 3e-12 (GaussQuadrature.h:35) and takes the weights from the
+        # last-but-one iterate: ~1e-12 in the weights is the reference's own accuracy, restated as is
+        assert np.abs(r - 0.5 * (x + 1)).max() < 1e-14 and np.abs(w - 0.5 * ww).max() < 5e-12
+        for p in (0, 1, n, 2 * n - 1):
+            assert abs((w * r ** p).sum() - 1.0 / (p + 1)) < 5e-12
+    for k in (1, 6, 10):
+        K = k + 1
+        xq, wq = np.polynomial.legendre.leggauss(2 * K)
+        xq, wq = 0.5 * (xq + 1), 0.5 * wq
+        phi = np.array([[L.mrx_interp_scaling(k, j, float(x), 0) for x in xq] for j in range(K)])
+        gram = (phi * wq) @ phi.T
+        assert np.abs(gram - np.eye(K)).max() < 1e-11
+        r, w = np.zeros(K), np.zeros(K)
+        L.mrx_quadrature(K, mw._dp(r), mw._dp(w))
+        at_nodes = np.array([[L.mrx_interp_scaling(k, j, float(x), 0) for x in r] for j in range(K)])
+        assert np.abs(at_nodes - np.diag(1.0 / np.sqrt(w))).max() < 1e-10
+        # derivative consistent with a central difference
+        h = 1e-6
+        for j in (0, K - 1):
+            d = L.mrx_interp_scaling(k, j, 0.37, 1)
+            fd = (L.mrx_interp_scaling(k, j, 0.37 + h, 0) - L.mrx_interp_scaling(k, j, 0.37 - h, 0)) / (2 * h)
+            assert abs(d - fd) < 1e-5 * max(1.0, abs(d))
