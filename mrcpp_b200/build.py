@@ -82,7 +82,18 @@ def build_oracle(force=False):
     return ORACLE_LIB
 
 
+def build_ref(reference="/root/reference"):
+    """oracle/_ref: the reference's own sources compiled in place (oracle/build_ref.sh) -- only where the reference tree
+    exists (this container); the GPU box uses the prebuilt files that travel with the snapshot. Returns the driver library
+    path or None."""
+    out = os.path.join(ORACLE_DIR, "_ref", "libref_driver.so")
+    if os.path.isdir(os.path.join(reference, "src")):
+        subprocess.check_call(["bash", os.path.join(ORACLE_DIR, "build_ref.sh"), reference], stdout=sys.stderr)
+    return out if os.path.exists(out) else None
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_lib(force=force, verbose="-v" in sys.argv))
     print(build_oracle(force=force))
+    print(build_ref())

@@ -1,0 +1,121 @@
+// C interface to the REAL reference (MRCPP sources compiled in place into oracle/_ref/, see oracle/build_ref.sh) for the
+// tests: build trees and operators through the reference's own public API, run mrcpp::apply / project / mwTransform, and
+// export nodes keyed by (scale, translation). TEST INFRASTRUCTURE only. Everything computed here is computed by the
+// reference's code; the only foreign part is the dense linear-algebra stand-in for Eigen (oracle/eigen_shim).
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "MRCPP/Gaussians"
+#include "MRCPP/MWFunctions"
+#include "MRCPP/MWOperators"
+#include "MRCPP/Printer"
+#include "MRCPP/Timer"
+#include "treebuilders/apply.h"
+#include "treebuilders/grid.h"
+#include "treebuilders/project.h"
+#include "trees/FunctionTree.h"
+#include "trees/MWNode.h"
+#include "utils/tree_utils.h"
+
+using namespace mrcpp;
+
+namespace {
+struct RefTree {
+    FunctionTree<3, double> tree;
+    explicit RefTree(const MultiResolutionAnalysis<3> &mra) : tree(mra) {}
+};
+GaussExp<3> make_exp(int n, const double *coef, const double *alpha, const double *pos, const int *power) {
+    GaussExp<3> g;
+    for (int i = 0; i < n; i++) {
+        Coord<3> p{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+        std::array<int, 3> pw{0, 0, 0};
+        if (power)
+            for (int d = 0; d < 3; d++) pw[d] = power[3 * i + d];
+        GaussFunc<3> f(alpha[i], coef[i], p, pw);
+        g.append(f);
+    }
+    return g;
+}
+} // namespace
+
+extern "C" {
+
+void ref_init() {
+    static bool done = false;
+    if (!done) {
+        Printer::init(-1);
+        done = true;
+    }
+}
+
+void *ref_mra_create(int order, int root_scale, const int *corner, const int *nboxes, int max_depth) {
+    ref_init();
+    std::array<int, 3> c{corner[0], corner[1], corner[2]}, b{nboxes[0], nboxes[1], nboxes[2]};
+    BoundingBox<3> world(root_scale, c, b);
+    InterpolatingBasis basis(order);
+    return new MultiResolutionAnalysis<3>(world, basis, max_depth);
+}
+void ref_mra_destroy(void *m) { delete static_cast<MultiResolutionAnalysis<3> *>(m); }
+
+void *ref_tree_create(void *mra) { return new RefTree(*static_cast<MultiResolutionAnalysis<3> *>(mra)); }
+void ref_tree_destroy(void *t) { delete static_cast<RefTree *>(t); }
+int ref_tree_n_nodes(void *t) { return static_cast<RefTree *>(t)->tree.getNNodes(); }
+double ref_tree_square_norm(void *t) { return static_cast<RefTree *>(t)->tree.getSquareNorm(); }
+
+/// build_grid + project of a Gaussian expansion (src/treebuilders/grid.cpp:106-123, project.cpp:85-104)
+void ref_project_gaussians(void *t, double prec, int n, const double *coef, const double *alpha, const double *pos, const int *power,
+                           int do_build_grid) {
+    auto &tree = static_cast<RefTree *>(t)->tree;
+    GaussExp<3> g = make_exp(n, coef, alpha, pos, power);
+    if (do_build_grid) build_grid(tree, g);
+    project<3, double>(prec, tree, g);
+}
+
+void *ref_poisson_create(void *mra, double prec) { return new PoissonOperator(*static_cast<MultiResolutionAnalysis<3> *>(mra), prec); }
+void *ref_helmholtz_create(void *mra, double mu, double prec) {
+    return new HelmholtzOperator(*static_cast<MultiResolutionAnalysis<3> *>(mra), mu, prec);
+}
+void *ref_abgv_create(void *mra, double a, double b) { return new ABGVOperator<3>(*static_cast<MultiResolutionAnalysis<3> *>(mra), a, b); }
+int ref_oper_n_terms(void *o) { return static_cast<ConvolutionOperator<3> *>(o)->size(); }
+void ref_conv_destroy(void *o) { delete static_cast<ConvolutionOperator<3> *>(o); }
+void ref_deriv_destroy(void *o) { delete static_cast<DerivativeOperator<3> *>(o); }
+
+/// mrcpp::apply(prec, out, oper, inp, maxIter, absPrec) (src/treebuilders/apply.cpp:68-93); returns seconds
+double ref_apply(double prec, void *out, void *oper, void *inp, int max_iter, int abs_prec) {
+    Timer t;
+    apply(prec, static_cast<RefTree *>(out)->tree, *static_cast<ConvolutionOperator<3> *>(oper), static_cast<RefTree *>(inp)->tree, max_iter,
+          abs_prec != 0);
+    t.stop();
+    return t.elapsed();
+}
+/// mrcpp::apply(out, DerivativeOperator, inp, dir) (apply.cpp:379-412)
+void ref_apply_derivative(void *out, void *oper, void *inp, int dir) {
+    apply(static_cast<RefTree *>(out)->tree, *static_cast<DerivativeOperator<3> *>(oper), static_cast<RefTree *>(inp)->tree, dir);
+}
+double ref_dot(void *a, void *b) { return dot(static_cast<RefTree *>(a)->tree, static_cast<RefTree *>(b)->tree); }
+void ref_copy_grid(void *out, void *inp) { copy_grid(static_cast<RefTree *>(out)->tree, static_cast<RefTree *>(inp)->tree); }
+void ref_mw_transform(void *t, int type, int overwrite) { static_cast<RefTree *>(t)->tree.mwTransform(type, overwrite != 0); }
+
+/// every node (depth by depth, table order): scale, translation, is-branch flag, 8 (k+1)^3 coefficients, 8 component norms
+int ref_tree_export(void *t, int *scale, int *transl, int *branch, double *coefs, double *norms) {
+    auto &tree = static_cast<RefTree *>(t)->tree;
+    std::vector<MWNodeVector<3, double>> table;
+    tree_utils::make_node_table(tree, table);
+    int n = 0;
+    for (auto &level : table)
+        for (MWNode<3, double> *nd : level) {
+            if (scale) scale[n] = nd->getScale();
+            if (transl)
+                for (int d = 0; d < 3; d++) transl[3 * n + d] = nd->getNodeIndex()[d];
+            if (branch) branch[n] = nd->isBranchNode() ? 1 : 0;
+            if (coefs) std::memcpy(coefs + (size_t)n * nd->getNCoefs(), nd->getCoefs(), sizeof(double) * nd->getNCoefs());
+            if (norms)
+                for (int c = 0; c < 8; c++) norms[8 * n + c] = nd->getComponentNorm(c);
+            n++;
+        }
+    return n;
+}
+int ref_num_threads() { return mrcpp_get_num_threads(); }
+}

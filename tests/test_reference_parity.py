@@ -1,0 +1,129 @@
+"""The oracle against the REAL reference: MRCPP's own sources compiled in place (oracle/build_ref.sh -> oracle/_ref/, with the
+Eigen stand-in of oracle/eigen_shim for the dense products). Same inputs through both: the reference's project / apply /
+derivative apply / operator construction, and oracle/oracle.cpp on the shared host model. Bars: node sets identical,
+coefficients within 1e-12 of the node norm (observed 1e-15), tree norms to 1e-13, separation ranks equal.
+Skipped when oracle/_ref has not been built (it needs /root/reference at build time only)."""
+import math
+
+import numpy as np
+import pytest
+
+import ref_api as ref
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
+
+TOL = 1e-12
+
+
+def gaussians(mw, n, seed, box=4.0, lo=1.0, hi=2.0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        beta = 10.0 ** rng.uniform(lo, hi)
+        out.append(mw.GaussFunc(beta, (beta / math.pi) ** 1.5 / n, tuple(rng.uniform(-box, box, 3))))
+    return out
+
+
+def same_tree(R, O, tol=TOL):
+    ri, oi = ref.by_index(R), ref.by_index(O)
+    assert set(ri) == set(oi), (len(ri), len(oi))
+    nmax = max(np.linalg.norm(R["coefs"][i]) for i in ri.values())
+    worst = 0.0
+    for key, i in ri.items():
+        j = oi[key]
+        d = np.abs(R["coefs"][i] - O["coefs"][j]).max()
+        worst = max(worst, d / max(np.linalg.norm(R["coefs"][i]), 1e-3 * nmax + 1e-300))
+        assert (R["branch"][i] != 0) == (O["child0"][j] >= 0)
+    assert worst < tol, worst
+    return worst
+
+
+def expansion(mw, funcs):
+    g = mw.GaussExp()
+    for f in funcs:
+        g.append(f)
+    return g
+
+
+@pytest.mark.parametrize("k,prec,n", [(5, 1e-4, 1), (7, 1e-5, 1), (5, 1e-4, 5), (4, 1e-3, 3), (6, 1e-4, 2)])
+def test_poisson_apply_matches_reference(libs, k, prec, n):
+    mw, orc = libs
+    if n == 1:
+        beta = 100.0
+        funcs = [mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)]  # examples/poisson.cpp
+    else:
+        funcs = gaussians(mw, n, 17 + k)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    same_tree(rf.export(), of.to_arrays())
+    assert abs(rf.square_norm() - of.getSquareNorm()) <= 1e-13 * rf.square_norm()
+    RP, OP = ref.poisson(rm, prec), mw.PoissonOperator(om, prec)
+    assert ref.lib().ref_oper_n_terms(RP) == OP.size()
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, RP, rf)
+    st = orc.apply(prec, og, OP, of)
+    same_tree(rg.export(), og.to_arrays())
+    assert abs(rg.square_norm() - og.getSquareNorm()) <= 1e-13 * rg.square_norm()
+    assert abs(ref.dot(rg, rf) - orc.dot(og, of)) <= 1e-12 * abs(ref.dot(rg, rf))
+    assert st.nNodesOut == rg.n_nodes()
+    if n == 1:
+        assert abs(ref.dot(rg, rf) - math.sqrt(2 * 100.0 / math.pi)) / 7.978845608 < prec  # the reference's own check
+
+
+@pytest.mark.parametrize("max_iter,abs_prec", [(0, False), (2, False), (-1, True)])
+def test_apply_variants_match_reference(libs, max_iter, abs_prec):
+    """maxIter-limited and absolute-precision applies, and (maxIter = 0) the fixed-grid mode on a copied grid"""
+    mw, orc = libs
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 3, 5)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    RP, OP = ref.poisson(rm, prec), mw.PoissonOperator(om, prec)
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    if max_iter == 0:
+        ref.lib().ref_copy_grid(rg._h, rf._h)
+        mw.copy_grid(og, of)
+    ref.apply(prec, rg, RP, rf, max_iter, abs_prec)
+    orc.apply(prec, og, OP, of, max_iter, abs_prec)
+    same_tree(rg.export(), og.to_arrays())
+
+
+def test_helmholtz_apply_matches_reference(libs):
+    mw, orc = libs
+    k, prec, mu = 5, 1e-4, 1.0
+    funcs = gaussians(mw, 4, 3, box=3.0, lo=0.5, hi=1.5)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    RH, OH = ref.helmholtz(rm, mu, prec), mw.HelmholtzOperator(om, mu, prec)
+    assert ref.lib().ref_oper_n_terms(RH) == OH.size()
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, RH, rf)
+    orc.apply(prec, og, OH, of)
+    same_tree(rg.export(), og.to_arrays())
+
+
+@pytest.mark.parametrize("a,b", [(0.5, 0.5), (0.0, 0.0)])
+def test_abgv_derivative_matches_reference(libs, a, b):
+    mw, orc = libs
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 3, 9)
+    world = (k, -3, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    RD, OD = ref.abgv(rm, a, b), mw.ABGVOperator(om, a, b)
+    for d in range(3):
+        rg, og = ref.Tree(rm), mw.FunctionTree(om)
+        ref.apply_derivative(rg, RD, rf, d)
+        orc.apply_derivative(og, OD, of, d)
+        same_tree(rg.export(), og.to_arrays(), tol=1e-11)
