@@ -12,12 +12,14 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library; the product (mrcpp_b200/) never does.
 //
-// PARITY PINNING: the reference cannot be built in this image (Eigen 3.4.0 and Catch2 are
-// un-vendored dependencies, no network), so this oracle is pinned by the reference's own
-// known-answer tests instead (tests/test_oracle_kats.py): Poisson/Helmholtz kernel sizes and point
-// values, filter orthonormality, Coulomb self-energy of a Gaussian, band-width monotonicity,
-// derivative L2 error, projected-Gaussian integral/norm. At the 1e-12 coefficient level parity with
-// the real reference is UNPINNED (Eigen's summation order is unspecified anyway).
+// PARITY PINNING: (1) against the REAL reference: its own sources are compiled in place by oracle/build_ref.sh
+// (Eigen 3.4.0 is an un-vendored dependency and absent here, so the dense products go through the stand-in under
+// oracle/eigen_shim; everything else is the reference's code) and tests/test_reference_parity.py requires identical node
+// sets, equal separation ranks and coefficients within 1e-12 of the node norm (observed 1e-15) for Poisson / Helmholtz /
+// derivative applies and the projections feeding them; (2) against the reference's own known-answer tests
+// (tests/test_oracle_kats.py): Poisson/Helmholtz kernel sizes and point values, filter orthonormality, Coulomb
+// self-energy of a Gaussian, hydrogen 1s fixed point, identity convolution, band-width monotonicity, derivative L2 error,
+// projected-Gaussian integral/norm.
 //
 // It uses the product's host data model (mrcpp_b200/csrc/host: flat trees, tables, operator tables)
 // for inputs; the operator application and tree transforms below are written independently of the
