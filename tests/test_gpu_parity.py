@@ -330,6 +330,23 @@ def test_poisson_apply_vs_real_reference(gpu):
     assert abs(mw.dot(gg, fg) - ref.dot(rg, rf)) < 1e-11 * abs(ref.dot(rg, rf))
 
 
+def test_golden_vectors_of_the_real_reference(gpu):
+    """GPU path against tests/golden/poisson_ref.npz: outputs of the REAL reference (its own sources compiled in place,
+    tests/golden/make_golden_ref.py), compared node by node through (scale, translation). Needs nothing but the fixture."""
+    from test_reference_parity import check_against_golden_ref, golden_ref
+    mw, orc = gpu
+    gold = golden_ref()
+    k, prec, beta = int(gold["k"]), float(gold["prec"]), float(gold["beta"])
+    mra = world(mw, k)
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, tuple(gold["pos"]))
+    P = mw.PoissonOperator(mra, prec)
+    for device_projection in (False, True):
+        ft, gt = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        mw.project(prec, ft, f, device=device_projection)
+        mw.apply(prec, gt, P, ft)
+        check_against_golden_ref(mw, ft, gt, P, mw.dot(gt, ft))
+
+
 def test_multi_center_density(gpu):
     """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
     mw, orc = gpu
