@@ -45,7 +45,7 @@ def expansion(mw, funcs):
     return g
 
 
-@pytest.mark.parametrize("k,prec,n", [(5, 1e-4, 1), (7, 1e-5, 1), (5, 1e-4, 5), (4, 1e-3, 3), (6, 1e-4, 2)])
+@pytest.mark.parametrize("k,prec,n", [(5, 1e-4, 1), (7, 1e-5, 1), (5, 1e-4, 5), (4, 1e-3, 3), (6, 1e-4, 2), (9, 1e-4, 2), (11, 1e-3, 1), (3, 1e-2, 2)])
 @needs_ref
 def test_poisson_apply_matches_reference(libs, k, prec, n):
     mw, orc = libs
@@ -94,6 +94,26 @@ def test_apply_variants_match_reference(libs, max_iter, abs_prec):
     ref.apply(prec, rg, RP, rf, max_iter, abs_prec)
     orc.apply(prec, og, OP, of, max_iter, abs_prec)
     same_tree(rg.export(), og.to_arrays())
+
+
+@needs_ref
+@pytest.mark.parametrize("k", [5, 7])
+def test_mw_transforms_match_reference(libs, k):
+    """MWTree::mwTransform(TopDown, overwrite) then (BottomUp) of a projected tree: the reference's passes against the oracle's"""
+    mw, orc = libs
+    prec = 1e-4
+    funcs = gaussians(mw, 3, 21)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    ref.lib().ref_mw_transform(rf._h, 0, 1)  # TopDown, overwrite (api/constants.h: TopDown = 0, BottomUp = 1)
+    orc.mw_transform_down(of, True)
+    same_tree(rf.export(), of.to_arrays())
+    ref.lib().ref_mw_transform(rf._h, 1, 1)
+    orc.mw_transform_up(of)
+    same_tree(rf.export(), of.to_arrays())
 
 
 @needs_ref
