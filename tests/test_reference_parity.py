@@ -97,6 +97,30 @@ def test_apply_variants_match_reference(libs, max_iter, abs_prec):
 
 
 @needs_ref
+def test_bench_like_density_matches_reference(libs):
+    """the generator of bench.py (centres uniform in [-8, 8]^3, beta log-uniform in [10, 1000], seed 42) at the bench order
+    k = 7 on a 3-centre sample, prec 1e-6: generated input nodes, deep refinement, M = 89 terms"""
+    mw, orc = libs
+    k, prec = 7, 1e-6
+    funcs = gaussians(mw, 3, 42, box=8.0, lo=1.0, hi=3.0)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    same_tree(rf.export(), of.to_arrays())
+    RP, OP = ref.poisson(rm, prec), mw.PoissonOperator(om, prec)
+    assert ref.lib().ref_oper_n_terms(RP) == OP.size()
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, RP, rf)
+    st = orc.apply(prec, og, OP, of)
+    same_tree(rg.export(), og.to_arrays())
+    assert st.genUsed > 0
+    ana = sum(a.calc_coulomb_energy(b) for a in funcs for b in funcs)
+    assert abs(ref.dot(rg, rf) - ana) / ana < 10 * prec and abs(orc.dot(og, of) - ref.dot(rg, rf)) < 1e-12 * ana
+
+
+@needs_ref
 @pytest.mark.parametrize("k", [5, 7])
 def test_mw_transforms_match_reference(libs, k):
     """MWTree::mwTransform(TopDown, overwrite) then (BottomUp) of a projected tree: the reference's passes against the oracle's"""
