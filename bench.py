@@ -11,15 +11,18 @@ with a fresh output tree each step.
   e2e    same metric through the C-ABI with HOST buffers: the input tree starts in pinned host memory (the apply
          gathers the nodes it reads over PCIe, h2d_bytes_per_step is what actually crossed) and the result tree is
          downloaded inside the timed region.
-  roofline  dominant kernel = the contraction kernel (apply_dmma8_kernel): algorithmic flops =
+  roofline  dominant kernel = the contraction kernel (pipe_contract_kernel): algorithmic flops =
          surviving tuples x 6 (k+1)^4, divided by the kernel's CUDA-event time; peak = FP64 tensor
          (DMMA) rate measured in this run (MEASURED_PEAKS.json has no FP64 entry).
-  cpu_baseline  the CPU oracle (OpenMP restatement of the reference) on a bounded sample.
+  cpu_baseline  the CPU oracle (OpenMP restatement of the reference) on a bounded sample (16 of the 1000 centres).
+  --impl reference  the same sample through both CPU implementations: the oracle port and, where oracle/_ref exists, the
+         reference's own sources compiled in place; the line carries the faster of the two.
 
 N > 1 (torchrun): one process per GPU; ONE apply is sharded over the ranks: every refinement iteration's
-output-node list is cut into contiguous ranges (one per rank), input tree and operator are replicated,
-component norms and output coefficient blocks are all-gathered over NCCL/NVLink inside the library
-(mrx_apply_sharded). Same workload for every N -> strong scaling; time = max over ranks.
+output-node list is dealt out cyclically (item i -> rank i % N), input tree and operator are replicated, component norms
+are all-gathered over NCCL and the output coefficient blocks are pushed to the peers' HBM by the copy engines over NVLink
+(CUDA-IPC mappings; NCCL all-gather if IPC is unavailable) inside the library (mrx_apply_sharded). Same workload for every
+N -> strong scaling; time = max over ranks.
 """
 import os as _os
 if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
@@ -121,9 +124,10 @@ class ClockSampler:
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path. The real MRCPP cannot be built in this
-    image (Eigen 3.4.0 is an un-vendored dependency), so this arm times the oracle port (oracle/oracle.cpp: OpenMP
-    restatement, same loop structure and thresholds) on all host threads, on a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads, on a bounded sample of
+    the workload: the oracle port (oracle/oracle.cpp: OpenMP restatement, same loop structure and thresholds) and, where
+    oracle/_ref was built (oracle/build_ref.sh; the prebuilt files travel to the GPU box), the reference's own sources
+    compiled in place. The line reports the faster of the two."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -202,8 +206,9 @@ def workload_config(args, centers, sample=False):
             "operator": "PoissonOperator(prec)", "mode": "adaptive (maxIter=-1)",
             "l2_policy": "fresh output tree each step; input tree + operator tables exceed nothing: working set per step "
                          "is re-generated (generated input nodes, output coefficients) and an L2 flush buffer (256 MB) is written between steps",
-            "parallelism": "output-node list of every refinement iteration sharded over the ranks (contiguous ranges), input tree + "
-                           "operator replicated, NCCL all-gather of component norms and output coefficient blocks"}
+            "parallelism": "output-node list of every refinement iteration dealt out cyclically over the ranks, input tree + "
+                           "operator replicated, NCCL all-gather of component norms, output coefficient blocks pushed to the "
+                           "peers over NVLink (CUDA IPC, copy engines)"}
 
 
 def main():
@@ -215,7 +220,7 @@ def main():
     ap.add_argument("--order", type=int, default=7)
     ap.add_argument("--prec", type=float, default=1e-7)
     ap.add_argument("--centers", type=int, default=1000)
-    ap.add_argument("--cpu-centers", type=int, default=4)
+    ap.add_argument("--cpu-centers", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -359,7 +364,7 @@ def main():
             "fp64_tflops": flops / (tot_ms * 1e-3) / 1e12,
             "fp64_tflops_frac_of_dmma_peak": flops / (tot_ms * 1e-3) / 1e12 / (peak_dmma * world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
-                         "traffic": None, "kernel": "pipe_contract_kernel" if k == 7 else "apply_generic_kernel",
+                         "traffic": None, "kernel": "pipe_contract_kernel" if k == 7 else "pipe_contract_coop_kernel",
                          "peak_source": "FP64 DMMA m8n8k4 micro-benchmark measured in this run (no FP64 figure in "
                                         "MEASURED_PEAKS.json); DFMA peak %.1f TFLOP/s" % peak_dfma,
                          "kernel_share_of_step": contract_ms / tot_ms, "all_apply_kernels_share_of_step": kern_ms / tot_ms},

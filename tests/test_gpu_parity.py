@@ -297,56 +297,6 @@ def test_hydrogen_fixed_point_helmholtz(gpu):
     assert abs(mw.dot(gg, pg) - 1.0) < apply_prec
 
 
-def test_poisson_apply_vs_real_reference(gpu):
-    """examples/poisson.cpp (k = 7, prec 1e-5) on the GPU against the REAL reference (MRCPP's own sources compiled in place,
-    oracle/_ref, see tests/test_reference_parity.py): node set identical, coefficients within 1e-12 of the node norm.
-    Skipped where oracle/_ref was not built."""
-    import ref_api as ref
-    if not ref.available():
-        pytest.skip("oracle/_ref not built")
-    mw, orc = gpu
-    k, prec = 7, 1e-5
-    beta = 100.0
-    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)
-    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
-    try:
-        rm = ref.MRA(*world)
-    except OSError as e:  # the prebuilt library does not load on this box
-        pytest.skip(f"oracle/_ref does not load here: {e}")
-    rf, rg = ref.Tree(rm), ref.Tree(rm)
-    ref.project(prec, rf, [f])
-    ref.apply(prec, rg, ref.poisson(rm, prec), rf)
-    mra = mw.MultiResolutionAnalysis(*world)
-    fg, gg = mw.FunctionTree(mra), mw.FunctionTree(mra)
-    mw.project(prec, fg, f, device=True)
-    mw.apply(prec, gg, mw.PoissonOperator(mra, prec), fg)
-    for R, G in ((rf.export(), fg.to_arrays()), (rg.export(), gg.to_arrays())):
-        ri, gi = ref.by_index(R), ref.by_index(G)
-        assert set(ri) == set(gi)
-        nmax = max(np.linalg.norm(R["coefs"][i]) for i in ri.values())
-        worst = max(np.abs(R["coefs"][i] - G["coefs"][gi[key]]).max() / max(np.linalg.norm(R["coefs"][i]), 1e-3 * nmax)
-                    for key, i in ri.items())
-        assert worst < COEF_TOL, worst
-    assert abs(mw.dot(gg, fg) - ref.dot(rg, rf)) < 1e-11 * abs(ref.dot(rg, rf))
-
-
-def test_golden_vectors_of_the_real_reference(gpu):
-    """GPU path against tests/golden/poisson_ref.npz: outputs of the REAL reference (its own sources compiled in place,
-    tests/golden/make_golden_ref.py), compared node by node through (scale, translation). Needs nothing but the fixture."""
-    from test_reference_parity import check_against_golden_ref, golden_ref
-    mw, orc = gpu
-    gold = golden_ref()
-    k, prec, beta = int(gold["k"]), float(gold["prec"]), float(gold["beta"])
-    mra = world(mw, k)
-    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, tuple(gold["pos"]))
-    P = mw.PoissonOperator(mra, prec)
-    for device_projection in (False, True):
-        ft, gt = mw.FunctionTree(mra), mw.FunctionTree(mra)
-        mw.project(prec, ft, f, device=device_projection)
-        mw.apply(prec, gt, P, ft)
-        check_against_golden_ref(mw, ft, gt, P, mw.dot(gt, ft))
-
-
 def test_multi_center_density(gpu):
     """10 seeded Gaussians, k=7: adaptive parity + pairwise analytic Coulomb energy (SURVEY §8c KAT 3)."""
     mw, orc = gpu
