@@ -1,0 +1,656 @@
+// C++ host mirror of the MRCPP API for the B200 operator-application path, header-only, over the C ABI of
+// libmrcpp_b200.so (include/mrcpp_b200.h). Same names, argument meaning and error behaviour (print + abort) as the
+// reference classes it stands in for, so that a program written against MRCPP's public headers
+//
+//     #include "MRCPP/Gaussians"   #include "MRCPP/MWFunctions"   #include "MRCPP/MWOperators"
+//     #include "MRCPP/Printer"     #include "MRCPP/Timer"
+//
+// (e.g. the reference's examples/poisson.cpp and examples/projection.cpp, unmodified) compiles against -Iinclude and
+// links with -lmrcpp_b200. Only what the path needs is here: D = 3, T = double, interpolating basis, non-periodic worlds.
+// Anything else is a compile-time error (static_assert) or aborts with a message, never a silent CPU fallback: the
+// arithmetic of every call below runs in the library (CUDA); this file only holds handles and formats output.
+//
+// Reference interfaces mirrored (file:line under the MRCPP source tree):
+//   BoundingBox<D>               src/trees/BoundingBox.h:53-60
+//   InterpolatingBasis           src/core/InterpolatingBasis.h:43
+//   MultiResolutionAnalysis<D>   src/trees/MultiResolutionAnalysis.h:51-54
+//   GaussFunc<D>, GaussExp<D>    src/functions/GaussFunc.h:56, GaussExp.h:54-118
+//   FunctionTree<D, T>           src/trees/FunctionTree.h, MWTree.h:97-179
+//   ConvolutionOperator<D>, PoissonOperator, HelmholtzOperator, DerivativeOperator<D>, ABGVOperator<D>
+//                                src/operators/{ConvolutionOperator,PoissonOperator,HelmholtzOperator,ABGVOperator}.h
+//   build_grid, copy_grid, clear_grid   src/treebuilders/grid.h:35-43
+//   project                      src/treebuilders/project.h:33-34
+//   apply (convolution, derivative)     src/treebuilders/apply.h:41,49
+//   dot                          src/treebuilders/multiply.h
+//   Printer, print::*, Timer     src/utils/Printer.h:61-133, src/utils/Timer.h:42-50
+#pragma once
+
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../mrcpp_b200.h"
+
+namespace mrcpp {
+
+// ---- api/constants.h
+const double MachinePrec = 1.0e-15;
+const double MachineZero = 1.0e-14;
+const int MaxOrder = 41;
+const int MaxDepth = 30;
+const int MaxScale = 31;
+const int MinScale = -31;
+enum FuncType { Legendre, Interpol };
+enum Traverse { TopDown, BottomUp };
+const double pi = 3.1415926535897932384626433832795;
+const double root_pi = 1.7724538509055160273;
+
+template <int D> using Coord = std::array<double, D>;
+
+// ---- error convention: print + abort (src/utils/Printer.h:165-190)
+#define MRCPP_B200_ABORT(X)                                                                                                    \
+    {                                                                                                                          \
+        std::cerr << "Error: " << __FILE__ << ": " << __func__ << "(), line " << __LINE__ << ": " << X << std::endl;           \
+        std::abort();                                                                                                          \
+    }
+
+// ---- library / device selection -------------------------------------------------------------------------------------
+namespace b200 {
+/// Selects the CUDA device of this process (one process per GPU) and loads the filter tables. Called implicitly by the
+/// first object that needs the library: device = $MRCPP_B200_DEVICE if set, else 0 when a GPU is visible, else -1
+/// (host-only: construction helpers work, every hot-path call aborts). An MPI program calls init(local_rank) first.
+inline int &device_ref() {
+    static int dev = -2; // -2: not initialised
+    return dev;
+}
+inline void init(int device, const char *tables = nullptr) {
+    if (device_ref() != -2) {
+        if (device_ref() != device) MRCPP_B200_ABORT("library already initialised on device " << device_ref());
+        return;
+    }
+    if (tables == nullptr) tables = std::getenv("MRCPP_B200_TABLES"); // else: data/mwtables.bin next to the library
+    if (mrx_init(tables ? tables : "", device) != 0) MRCPP_B200_ABORT("mrx_init failed for device " << device);
+    device_ref() = device;
+}
+inline void ensure_init() {
+    if (device_ref() != -2) return;
+    int device = mrx_device_count() > 0 ? 0 : -1;
+    if (const char *env = std::getenv("MRCPP_B200_DEVICE")) device = std::atoi(env);
+    init(device);
+}
+} // namespace b200
+
+// ---- Timer (src/utils/Timer.h:42-50) -----------------------------------------------------------------------------------
+class Timer final {
+public:
+    explicit Timer(bool start_timer = true) {
+        if (start_timer) start();
+    }
+    void start() {
+        clock_start = now();
+        time_used = 0.0;
+        running = true;
+    }
+    void resume() {
+        if (running) std::cerr << "Warning: timer already running" << std::endl;
+        clock_start = now();
+        running = true;
+    }
+    void stop() {
+        if (!running) std::cerr << "Warning: timer not running" << std::endl;
+        time_used += diff(now(), clock_start);
+        running = false;
+    }
+    double elapsed() const { return running ? diff(now(), clock_start) : time_used; }
+
+private:
+    using timeT = std::chrono::time_point<std::chrono::high_resolution_clock>;
+    bool running{false};
+    double time_used{0.0};
+    timeT clock_start;
+    static timeT now() { return std::chrono::high_resolution_clock::now(); }
+    static double diff(timeT t2, timeT t1) { return std::chrono::duration<double>(t2 - t1).count(); }
+};
+
+// ---- BoundingBox / basis / MRA ----------------------------------------------------------------------------------------
+template <int D> class BoundingBox {
+public:
+    explicit BoundingBox(int n = 0, const std::array<int, D> &l = {}, const std::array<int, D> &nb = {},
+                         const std::array<double, D> &sf = {}, bool pbc = false)
+            : scale(n)
+            , corner(l)
+            , boxes(nb) {
+        for (int d = 0; d < D; d++) {
+            if (boxes[d] <= 0) boxes[d] = 1; // BoundingBox.cpp: zero means one box
+            if (sf[d] != 0.0 && sf[d] != 1.0) MRCPP_B200_ABORT("scaling factors are not supported on the B200 path");
+        }
+        if (pbc) MRCPP_B200_ABORT("periodic worlds are not supported on the B200 path");
+    }
+    int getScale() const { return scale; }
+    int size(int d) const { return boxes[d]; }
+    int size() const {
+        int n = 1;
+        for (int d = 0; d < D; d++) n *= boxes[d];
+        return n;
+    }
+    const std::array<int, D> &getCornerIndex() const { return corner; }
+    double getUnitLength(int) const { return std::pow(2.0, -scale); }
+    double getBoxLength(int d) const { return getUnitLength(d) * boxes[d]; }
+    double getLowerBound(int d) const { return getUnitLength(d) * corner[d]; }
+    double getUpperBound(int d) const { return getUnitLength(d) * (corner[d] + boxes[d]); }
+    bool isPeriodic() const { return false; }
+    bool operator==(const BoundingBox<D> &o) const { return scale == o.scale && corner == o.corner && boxes == o.boxes; }
+    bool operator!=(const BoundingBox<D> &o) const { return !(*this == o); }
+
+private:
+    int scale;
+    std::array<int, D> corner;
+    std::array<int, D> boxes;
+};
+
+class ScalingBasis {
+public:
+    ScalingBasis(int k, int t)
+            : type(t)
+            , order(k) {
+        if (order < 0) MRCPP_B200_ABORT("Invalid scaling order");
+    }
+    virtual ~ScalingBasis() = default;
+    int getScalingType() const { return type; }
+    int getScalingOrder() const { return order; }
+    int getQuadratureOrder() const { return order + 1; }
+
+protected:
+    const int type;
+    const int order;
+};
+
+class InterpolatingBasis final : public ScalingBasis {
+public:
+    InterpolatingBasis(int k)
+            : ScalingBasis(k, Interpol) {}
+};
+
+template <int D> class MultiResolutionAnalysis final {
+public:
+    MultiResolutionAnalysis(const BoundingBox<D> &bb, const ScalingBasis &sb, int depth = MaxDepth)
+            : world(bb)
+            , order(sb.getScalingOrder())
+            , maxDepth(depth) {
+        if (sb.getScalingType() != Interpol) MRCPP_B200_ABORT("only the interpolating basis is supported on the B200 path");
+        setup();
+    }
+    MultiResolutionAnalysis(const BoundingBox<D> &bb, int k, int depth = MaxDepth)
+            : world(bb)
+            , order(k)
+            , maxDepth(depth) {
+        setup();
+    }
+    int getOrder() const { return order; }
+    int getMaxDepth() const { return maxDepth; }
+    int getMaxScale() const { return world.getScale() + maxDepth; }
+    int getRootScale() const { return world.getScale(); }
+    const BoundingBox<D> &getWorldBox() const { return world; }
+    bool operator==(const MultiResolutionAnalysis<D> &o) const { return world == o.world && order == o.order && maxDepth == o.maxDepth; }
+    bool operator!=(const MultiResolutionAnalysis<D> &o) const { return !(*this == o); }
+    const mrx_mra *handle() const { return h.get(); }
+
+private:
+    BoundingBox<D> world;
+    int order;
+    int maxDepth;
+    std::shared_ptr<mrx_mra> h;
+    void setup() {
+        static_assert(D == 3, "the B200 path implements 3-dimensional trees only");
+        b200::ensure_init();
+        int c[3], nb[3];
+        for (int d = 0; d < 3; d++) {
+            c[d] = world.getCornerIndex()[d];
+            nb[d] = world.size(d);
+        }
+        h = std::shared_ptr<mrx_mra>(mrx_mra_create(order, world.getScale(), c, nb, maxDepth), mrx_mra_destroy);
+    }
+};
+
+// ---- analytic functions -----------------------------------------------------------------------------------------------
+template <int D, typename T = double> class RepresentableFunction {
+public:
+    virtual ~RepresentableFunction() = default;
+    virtual T evalf(const Coord<D> &r) const = 0;
+};
+
+template <int D> class Gaussian : public RepresentableFunction<D, double> {
+public:
+    Gaussian(double a, double c, const Coord<D> &r, const std::array<int, D> &p)
+            : coef(c)
+            , power(p)
+            , pos(r) {
+        alpha.fill(a);
+    }
+    double getCoef() const { return coef; }
+    const std::array<double, D> &getExp() const { return alpha; }
+    const std::array<int, D> &getPower() const { return power; }
+    const Coord<D> &getPos() const { return pos; }
+    void setCoef(double c) { coef = c; }
+    void setPos(const Coord<D> &r) { pos = r; }
+
+protected:
+    double coef;
+    std::array<int, D> power;
+    std::array<double, D> alpha;
+    Coord<D> pos;
+};
+
+/// coef * prod_d (x_d - pos_d)^pow_d * exp(-beta |x - pos|^2)   (src/functions/GaussFunc.cpp:47-66)
+template <int D> class GaussFunc : public Gaussian<D> {
+public:
+    GaussFunc(double beta, double alpha, const Coord<D> &pos = {}, const std::array<int, D> &pow = {})
+            : Gaussian<D>(beta, alpha, pos, pow) {}
+    double evalf(const Coord<D> &r) const override {
+        double q2 = 0.0, p2 = 1.0;
+        for (int d = 0; d < D; d++) {
+            const double q = r[d] - this->pos[d];
+            q2 += this->alpha[d] * q * q;
+            if (this->power[d] == 1) p2 *= q;
+            else if (this->power[d] != 0) p2 *= std::pow(q, this->power[d]);
+        }
+        return this->coef * p2 * std::exp(-q2);
+    }
+    /// src/functions/GaussFunc.cpp:210-237: sqrt(4 a / pi) F_0(a R^2), a = p q / (p + q); both Gaussians normalised to unit charge
+    double calcCoulombEnergy(const GaussFunc<D> &gf) const {
+        static_assert(D == 3, "calcCoulombEnergy: 3-dimensional Gaussians only (as in the reference)");
+        const double p = this->alpha[0], q = gf.alpha[0];
+        const double a = p * q / (p + q);
+        double R2 = 0.0;
+        for (int d = 0; d < D; d++) R2 += (this->pos[d] - gf.pos[d]) * (this->pos[d] - gf.pos[d]);
+        const double x = a * R2;
+        const double boys = x < 1.0e-14 ? 1.0 : 0.5 * std::sqrt(pi / x) * std::erf(std::sqrt(x));
+        return std::sqrt(4.0 * a / pi) * boys;
+    }
+};
+
+template <int D> class GaussExp : public RepresentableFunction<D, double> {
+public:
+    GaussExp(int nTerms = 0) { funcs.reserve(nTerms); }
+    double evalf(const Coord<D> &r) const override {
+        double v = 0.0;
+        for (const auto &f : funcs) v += f.evalf(r);
+        return v;
+    }
+    int size() const { return (int)funcs.size(); }
+    void append(const GaussFunc<D> &g) { funcs.push_back(g); }
+    void append(const GaussExp<D> &g) { funcs.insert(funcs.end(), g.funcs.begin(), g.funcs.end()); }
+    GaussFunc<D> &getFunc(int i) { return funcs[i]; }
+    const GaussFunc<D> &getFunc(int i) const { return funcs[i]; }
+
+private:
+    std::vector<GaussFunc<D>> funcs;
+};
+
+namespace b200 {
+/// flat arrays of a Gaussian expansion as the C ABI takes them
+template <int D> struct GaussArrays {
+    std::vector<double> coef, expo, pos;
+    std::vector<int> power;
+    void add(const GaussFunc<D> &g) {
+        for (int d = 1; d < D; d++)
+            if (g.getExp()[d] != g.getExp()[0]) MRCPP_B200_ABORT("anisotropic Gaussians are not supported on the B200 path");
+        coef.push_back(g.getCoef());
+        expo.push_back(g.getExp()[0]);
+        for (int d = 0; d < D; d++) {
+            pos.push_back(g.getPos()[d]);
+            power.push_back(g.getPower()[d]);
+        }
+    }
+    int size() const { return (int)coef.size(); }
+};
+/// Gaussian content of a RepresentableFunction, if it is one (GaussFunc or GaussExp)
+template <int D> bool gauss_arrays(const RepresentableFunction<D, double> &f, GaussArrays<D> &out) {
+    if (auto *g = dynamic_cast<const GaussFunc<D> *>(&f)) {
+        out.add(*g);
+        return true;
+    }
+    if (auto *e = dynamic_cast<const GaussExp<D> *>(&f)) {
+        for (int i = 0; i < e->size(); i++) out.add(e->getFunc(i));
+        return true;
+    }
+    return false;
+}
+} // namespace b200
+
+// ---- FunctionTree -----------------------------------------------------------------------------------------------------
+template <int D, typename T = double> class MWTree {
+public:
+    virtual ~MWTree() = default;
+    MWTree(const MWTree &) = delete;
+    MWTree &operator=(const MWTree &) = delete;
+
+    const MultiResolutionAnalysis<D> &getMRA() const { return MRA; }
+    int getOrder() const { return MRA.getOrder(); }
+    int getKp1() const { return MRA.getOrder() + 1; }
+    int getKp1_d() const {
+        int n = 1;
+        for (int d = 0; d < D; d++) n *= getKp1();
+        return n;
+    }
+    int getRootScale() const { return MRA.getRootScale(); }
+    double getSquareNorm() const { return mrx_tree_square_norm(h); }
+    void calcSquareNorm() { mrx_calc_square_norm(h); }
+    int getNNodes() const { return mrx_tree_n_nodes(h); }
+    int getNEndNodes() const { return mrx_tree_n_end_nodes(h); }
+    int getSizeNodes() const { return (int)(mrx_tree_bytes(h) / 1024); } // kB, MWTree.cpp:120-130
+    void mwTransform(int type, bool overwrite = true) { mrx_mw_transform(h, type == TopDown ? MRX_TOP_DOWN : MRX_BOTTOM_UP, overwrite ? 1 : 0); }
+    mrx_tree *handle() const { return h; }
+
+protected:
+    explicit MWTree(const MultiResolutionAnalysis<D> &mra)
+            : MRA(mra)
+            , h(mrx_tree_create(mra.handle())) {}
+    const MultiResolutionAnalysis<D> MRA;
+    mrx_tree *h;
+};
+
+template <int D, typename T = double> class FunctionTree final : public MWTree<D, T>, public RepresentableFunction<D, T> {
+    static_assert(D == 3 && std::is_same<T, double>::value, "the B200 path implements FunctionTree<3, double> only");
+
+public:
+    explicit FunctionTree(const MultiResolutionAnalysis<D> &mra)
+            : MWTree<D, T>(mra) {}
+    ~FunctionTree() override { mrx_tree_destroy(this->h); }
+    T integrate() const { return mrx_tree_integrate(this->h); }
+    void rescale(T c) { mrx_tree_rescale(this->h, c); }
+    void normalize() {
+        const double sq = this->getSquareNorm();
+        if (sq < 0.0) MRCPP_B200_ABORT("Normalizing uninitialized function");
+        rescale(1.0 / std::sqrt(sq));
+    }
+    void clear() { mrx_tree_clear(this->h); }
+    T evalf(const Coord<D> &) const override { MRCPP_B200_ABORT("FunctionTree::evalf is not on the B200 path"); }
+};
+
+// ---- operators ---------------------------------------------------------------------------------------------------------
+class MWOperatorBase {
+public:
+    virtual ~MWOperatorBase() {
+        if (h) mrx_oper_destroy(h);
+    }
+    MWOperatorBase(const MWOperatorBase &) = delete;
+    MWOperatorBase &operator=(const MWOperatorBase &) = delete;
+    int size() const { return mrx_oper_n_terms(h); } // separation rank (MWOperator::size)
+    mrx_oper *handle() const { return h; }
+
+protected:
+    MWOperatorBase() = default;
+    mrx_oper *h = nullptr;
+};
+
+template <int D> class ConvolutionOperator : public MWOperatorBase {
+    static_assert(D == 3, "the B200 path implements 3-dimensional operators only");
+
+public:
+    /// ConvolutionOperator(mra, kernel, prec): src/operators/ConvolutionOperator.cpp:50-62
+    ConvolutionOperator(const MultiResolutionAnalysis<D> &mra, GaussExp<1> &kernel, double prec)
+            : MRA(mra)
+            , buildPrec(prec) {
+        std::vector<double> c, e;
+        for (int i = 0; i < kernel.size(); i++) {
+            c.push_back(kernel.getFunc(i).getCoef());
+            e.push_back(kernel.getFunc(i).getExp()[0]);
+        }
+        h = mrx_convolution_create(mra.handle(), (int)c.size(), c.data(), e.data(), prec);
+    }
+    double getBuildPrec() const { return buildPrec; }
+    const MultiResolutionAnalysis<D> &getMRA() const { return MRA; }
+    bool isPeriodic() const { return false; }
+
+protected:
+    ConvolutionOperator(const MultiResolutionAnalysis<D> &mra, double prec)
+            : MRA(mra)
+            , buildPrec(prec) {}
+    const MultiResolutionAnalysis<D> MRA;
+    double buildPrec;
+};
+
+/// src/operators/PoissonOperator.cpp:40-55
+class PoissonOperator final : public ConvolutionOperator<3> {
+public:
+    PoissonOperator(const MultiResolutionAnalysis<3> &mra, double prec)
+            : ConvolutionOperator<3>(mra, prec) {
+        h = mrx_poisson_create(mra.handle(), prec);
+    }
+};
+
+/// src/operators/HelmholtzOperator.cpp:44-59
+class HelmholtzOperator final : public ConvolutionOperator<3> {
+public:
+    HelmholtzOperator(const MultiResolutionAnalysis<3> &mra, double m, double prec)
+            : ConvolutionOperator<3>(mra, prec)
+            , mu(m) {
+        h = mrx_helmholtz_create(mra.handle(), m, prec);
+    }
+    double getMu() const { return mu; }
+
+private:
+    double mu;
+};
+
+template <int D> class DerivativeOperator : public MWOperatorBase {
+    static_assert(D == 3, "the B200 path implements 3-dimensional operators only");
+
+public:
+    int getOrder() const { return order; }
+
+protected:
+    explicit DerivativeOperator(int ord)
+            : order(ord) {}
+    int order;
+};
+
+/// src/operators/ABGVOperator.cpp:46-74
+template <int D> class ABGVOperator final : public DerivativeOperator<D> {
+public:
+    ABGVOperator(const MultiResolutionAnalysis<D> &mra, double a, double b)
+            : DerivativeOperator<D>(1) {
+        this->h = mrx_abgv_create(mra.handle(), a, b);
+    }
+};
+
+// ---- tree builders -----------------------------------------------------------------------------------------------------
+/// build_grid(out, GaussExp | Gaussian): src/treebuilders/grid.cpp:78-123
+template <int D> void build_grid(FunctionTree<D> &out, const GaussExp<D> &inp, int maxIter = -1) {
+    b200::GaussArrays<D> a;
+    b200::gauss_arrays<D>(inp, a);
+    mrx_build_grid_gaussians(out.handle(), a.size(), a.coef.data(), a.expo.data(), a.pos.data(), a.power.data(), maxIter);
+}
+template <int D, typename T> void build_grid(FunctionTree<D, T> &out, const RepresentableFunction<D, T> &inp, int maxIter = -1) {
+    b200::GaussArrays<D> a;
+    if (!b200::gauss_arrays<D>(inp, a)) MRCPP_B200_ABORT("build_grid: only Gaussian functions know where they are visible on the B200 path");
+    mrx_build_grid_gaussians(out.handle(), a.size(), a.coef.data(), a.expo.data(), a.pos.data(), a.power.data(), maxIter);
+}
+/// copy_grid / clear_grid: src/treebuilders/grid.cpp:150-166, :180-186
+template <int D, typename T> void copy_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp) { mrx_tree_copy_grid(out.handle(), inp.handle()); }
+template <int D, typename T> void build_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp, int maxIter = -1) {
+    if (maxIter >= 0) MRCPP_B200_ABORT("build_grid(out, tree, maxIter >= 0) is not on the B200 path");
+    if (out.getNNodes() != out.getMRA().getWorldBox().size()) MRCPP_B200_ABORT("build_grid(out, tree): `out` must enter as empty roots on the B200 path");
+    mrx_tree_copy_grid(out.handle(), inp.handle());
+}
+
+namespace b200 {
+template <int D> double trampoline(const double r[3], void *user) {
+    const auto &f = *static_cast<const std::function<double(const Coord<D> &)> *>(user);
+    return f(Coord<D>{r[0], r[1], r[2]});
+}
+} // namespace b200
+
+/// project(prec, out, f): src/treebuilders/project.cpp:85-104. The callback may be invoked from several OpenMP threads at
+/// once, as in the reference (ProjectionCalculator runs inside TreeCalculator's parallel loop).
+template <int D, typename T = double>
+void project(double prec, FunctionTree<D, T> &out, std::function<T(const Coord<D> &r)> func, int maxIter = -1, bool absPrec = false) {
+    if (maxIter >= 0 || absPrec) MRCPP_B200_ABORT("project: maxIter / absPrec variants are not on the B200 path");
+    mrx_project_function(out.handle(), prec, &b200::trampoline<D>, &func, /*threads_ok=*/1, /*finalize=*/1);
+}
+/// Gaussian functions are projected on the device (quadrature, cvTransform, compression and norms as CUDA kernels); any other
+/// RepresentableFunction goes through the callback projection above.
+template <int D, typename T = double>
+void project(double prec, FunctionTree<D, T> &out, RepresentableFunction<D, T> &inp, int maxIter = -1, bool absPrec = false) {
+    if (maxIter >= 0 || absPrec) MRCPP_B200_ABORT("project: maxIter / absPrec variants are not on the B200 path");
+    b200::GaussArrays<D> a;
+    if (b200::gauss_arrays<D>(inp, a)) {
+        mrx_project_gaussians_device(out.handle(), prec, a.size(), a.coef.data(), a.expo.data(), a.pos.data(), a.power.data(),
+                                     /*build_grid=*/0);
+        return;
+    }
+    std::function<T(const Coord<D> &)> f = [&inp](const Coord<D> &r) { return inp.evalf(r); };
+    mrx_project_function(out.handle(), prec, &b200::trampoline<D>, &f, 1, 1);
+}
+
+namespace b200 {
+/// work counters of the last apply of this thread (OperatorStatistics, src/operators/OperatorStatistics.cpp:83-106)
+inline mrx_apply_stats &last_apply_stats() {
+    static thread_local mrx_apply_stats st{};
+    return st;
+}
+} // namespace b200
+
+/// mrcpp::apply(prec, out, oper, inp, maxIter, absPrec): src/treebuilders/apply.cpp:68-93
+template <int D, typename T>
+void apply(double prec, FunctionTree<D, T> &out, ConvolutionOperator<D> &oper, FunctionTree<D, T> &inp, int maxIter = -1, bool absPrec = false) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_apply(prec, out.handle(), oper.handle(), inp.handle(), maxIter, absPrec ? 1 : 0, &b200::last_apply_stats());
+}
+/// mrcpp::apply(out, DerivativeOperator, inp, dir): src/treebuilders/apply.cpp:379-412
+template <int D, typename T> void apply(FunctionTree<D, T> &out, DerivativeOperator<D> &oper, FunctionTree<D, T> &inp, int dir = -1) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_apply_derivative(out.handle(), oper.handle(), inp.handle(), dir, &b200::last_apply_stats());
+}
+/// mrcpp::dot(bra, ket): src/treebuilders/multiply.cpp:286-318
+template <int D, typename T> T dot(FunctionTree<D, T> &bra, FunctionTree<D, T> &ket) {
+    if (bra.getMRA() != ket.getMRA()) MRCPP_B200_ABORT("Trees not compatible");
+    return mrx_dot(bra.handle(), ket.handle());
+}
+
+// ---- Printer (src/utils/Printer.h:61-133) ------------------------------------------------------------------------------
+class Printer final {
+public:
+    static void init(int level = 0, int rank = 0, int size = 1, const char * /*file*/ = nullptr) {
+        state().level = level;
+        state().rank = rank;
+        state().size = size;
+        *state().out << std::scientific << std::setprecision(state().prec);
+    }
+    static void setScientific() { *state().out << std::scientific; }
+    static void setFixed() { *state().out << std::fixed; }
+    static int setWidth(int i) {
+        int old = state().width;
+        state().width = i;
+        return old;
+    }
+    static int setPrecision(int i) {
+        int old = state().prec;
+        state().prec = i;
+        *state().out << std::setprecision(i);
+        return old;
+    }
+    static int setPrintLevel(int i) {
+        int old = state().level;
+        state().level = i;
+        return old;
+    }
+    static int getWidth() { return state().width; }
+    static int getPrecision() { return state().prec; }
+    static int getPrintLevel() { return state().level; }
+    static void setOutputStream(std::ostream &o) { state().out = &o; }
+    static std::ostream &out() { return *state().out; }
+    static bool active(int level) { return level <= state().level && state().rank == 0; }
+
+private:
+    struct State {
+        int level = -1, width = 60, prec = 12, rank = 0, size = 1;
+        std::ostream *out = &std::cout;
+    };
+    static State &state() {
+        static State s;
+        return s;
+    }
+};
+
+namespace print {
+inline void separator(int level, const char &c, int newlines = 0) {
+    if (!Printer::active(level)) return;
+    Printer::out() << std::string(Printer::getWidth(), c) << std::endl;
+    for (int i = 0; i < newlines; i++) Printer::out() << std::endl;
+}
+inline void header(int level, const std::string &txt, int newlines = 0, const char &c = '=') {
+    if (!Printer::active(level)) return;
+    const int len = (int)txt.size();
+    separator(level, c);
+    Printer::out() << std::string(std::max(0, (Printer::getWidth() - len) / 2), ' ') << txt << std::endl;
+    separator(level, '-', newlines);
+}
+inline void footer(int level, const Timer &timer, int newlines = 0, const char &c = '=') {
+    if (!Printer::active(level)) return;
+    std::ostringstream o;
+    o << std::fixed << std::setprecision(5) << "Wall time: " << std::scientific << timer.elapsed() << " sec";
+    const int len = (int)o.str().size();
+    separator(level, '-');
+    Printer::out() << std::string(std::max(0, (Printer::getWidth() - len) / 2), ' ') << o.str() << std::endl;
+    separator(level, c, newlines);
+}
+inline void environment(int level) {
+    if (!Printer::active(level)) return;
+    b200::ensure_init();
+    separator(level, '-', 1);
+    Printer::out() << " MRCPP API on " << mrx_version() << std::endl;
+    Printer::out() << " CUDA devices visible : " << mrx_device_count() << std::endl;
+    Printer::out() << " device of this process: " << b200::device_ref() << (b200::device_ref() < 0 ? " (host only: hot-path calls abort)" : "") << std::endl;
+    Printer::out() << std::endl;
+    separator(level, '-', 1);
+}
+inline void memory(int level, const std::string &txt) {
+    if (!Printer::active(level)) return;
+    long pages = 0, rss = 0;
+    if (FILE *f = std::fopen("/proc/self/statm", "r")) {
+        if (std::fscanf(f, "%ld %ld", &pages, &rss) != 2) rss = 0;
+        std::fclose(f);
+    }
+    const double mb = rss * 4096.0 / (1024.0 * 1024.0);
+    std::ostringstream o;
+    o << " " << txt;
+    const int pad = std::max(1, Printer::getWidth() - (int)o.str().size() - 16);
+    Printer::out() << o.str() << std::string(pad, ' ') << std::fixed << std::setprecision(2) << std::setw(10) << mb << " (MB)" << std::scientific
+                   << std::setprecision(Printer::getPrecision()) << std::endl;
+}
+inline void value(int level, const std::string &txt, double v, const std::string &unit = "", int p = -1, bool sci = true) {
+    if (!Printer::active(level)) return;
+    if (p < 0) p = Printer::getPrecision();
+    std::ostringstream o;
+    o << " " << std::left << std::setw(30) << txt << std::right << std::setw(8) << unit << " ";
+    if (sci) o << std::scientific;
+    else o << std::fixed;
+    o << std::setprecision(p) << std::setw(std::max(p + 8, Printer::getWidth() - 41)) << v;
+    Printer::out() << o.str() << std::endl;
+}
+inline void time(int level, const std::string &txt, const Timer &timer) { value(level, txt, timer.elapsed(), "(sec)", 5); }
+inline void tree(int level, const std::string &txt, int n, int m, double t) {
+    if (!Printer::active(level)) return;
+    std::ostringstream o;
+    o << " " << std::left << std::setw(26) << txt << std::right << std::setw(8) << n << " nds " << std::setw(8) << m << " kB " << std::scientific
+      << std::setprecision(2) << std::setw(9) << t << " sec";
+    Printer::out() << o.str() << std::endl;
+}
+template <int D, typename T> void tree(int level, const std::string &txt, const MWTree<D, T> &tr, const Timer &timer) {
+    tree(level, txt, tr.getNNodes(), tr.getSizeNodes(), timer.elapsed());
+}
+} // namespace print
+
+} // namespace mrcpp

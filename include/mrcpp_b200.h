@@ -78,6 +78,14 @@ int mrx_tree_to_arrays(mrx_tree *tree, int *scale, int *transl, int *parent, int
 /* copy_grid (src/treebuilders/grid.cpp:150-166): give `out` the node structure of `inp`, no coefs */
 int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp);
 
+/* FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454, FunctionNode.cpp:128-157): integral of the function over
+ * the world, from the scaling blocks of the root nodes (read back from HBM if the host copy is not current) */
+double mrx_tree_integrate(mrx_tree *tree);
+/* build_grid(out, GaussExp) alone (src/treebuilders/grid.cpp:78-123): host only, leaves a grid without coefficients;
+ * max_iter < 0: no bound */
+int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, const double *alpha,
+                             const double *pos /*[n][3]*/, const int *power /*[n][3] or NULL*/, int max_iter);
+
 /* Host-side input generator: build_grid + project of a Gaussian expansion
  * (src/treebuilders/grid.cpp:78-123, project.cpp:85-104, ProjectionCalculator.cpp:34-51). The per-node
  * quadrature runs on the host; with finalize != 0 the closing mwTransform(BottomUp) + calcSquareNorm

@@ -109,6 +109,10 @@ class FunctionTree:
     def getSquareNorm(self):
         return _lib.load().mrx_tree_square_norm(self._h)
 
+    def integrate(self):
+        """FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454)"""
+        return _lib.load().mrx_tree_integrate(self._h)
+
     def clear(self):
         _lib.load().mrx_tree_clear(self._h)
 
@@ -248,6 +252,12 @@ def _gauss_arrays(func):
     pos = np.ascontiguousarray([g.pos for g in funcs], dtype=np.float64)
     power = np.ascontiguousarray([g.power for g in funcs], dtype=np.int32)
     return len(funcs), coef, alpha, pos, power
+
+
+def build_grid(out, func, maxIter=-1):
+    """build_grid(out, GaussFunc | GaussExp) alone (src/treebuilders/grid.cpp:78-123): host only"""
+    n, coef, alpha, pos, power = _gauss_arrays(func)
+    _lib.load().mrx_build_grid_gaussians(out._h, n, _dp(coef), _dp(alpha), _dp(pos), _ip(power), int(maxIter))
 
 
 def project(prec, out, func, build_grid=True, finalize=True, device=False):

@@ -248,6 +248,61 @@ int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp) {
     return 0;
 }
 
+// FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454) with FunctionNode::integrateInterpolating
+// (src/trees/FunctionNode.cpp:128-157): sum over the root nodes of 2^(-3 n / 2) * sum_ijk s_ijk sqrt(w_i w_j w_k). Only the
+// scaling blocks of the root nodes are needed: they are read back from HBM when the host copy is not current.
+double mrx_tree_integrate(mrx_tree *tree) {
+    Tree<3> &h = tree->host;
+    const int K = h.K, Kd = h.Kd;
+    std::vector<double> roots((size_t)h.nRoots * Kd, 0.0);
+    if (tree->hostCoefsValid) {
+        for (int r = 0; r < h.nRoots; r++)
+            if (h.nodes[r].flags & FlagHasCoefs) std::memcpy(roots.data() + (size_t)r * Kd, h.coef(r), sizeof(double) * Kd);
+    } else {
+        require_device("mrx_tree_integrate (root blocks live in HBM)");
+        if (!tree->devValid || tree->dev.nNodes < h.nRoots) MRX_ABORT("mrx_tree_integrate: no current copy of the coefficients");
+        if (cudaMemcpy2DAsync(roots.data(), sizeof(double) * Kd, tree->dev.coefs.p, sizeof(double) * h.ncoef, sizeof(double) * Kd,
+                              h.nRoots, cudaMemcpyDeviceToHost, g_stream) != cudaSuccess ||
+            cudaStreamSynchronize(g_stream) != cudaSuccess)
+            MRX_ABORT("mrx_tree_integrate: device->host copy of the root blocks failed");
+    }
+    const Quadrature &q = quadrature(K);
+    std::vector<double> sw(K);
+    for (int i = 0; i < K; i++) sw[i] = std::sqrt(q.weights[i]);
+    double result = 0.0;
+    for (int r = 0; r < h.nRoots; r++) {
+        const double *c = roots.data() + (size_t)r * Kd;
+        double sum = 0.0;
+        for (int z = 0; z < K; z++)
+            for (int y = 0; y < K; y++)
+                for (int x = 0; x < K; x++) sum += ((c[x + K * (y + K * z)] * sw[x]) * sw[y]) * sw[z];
+        result += std::pow(2.0, -(3 * h.nodes[r].scale) / 2.0) * sum;
+    }
+    return result;
+}
+
+// build_grid(out, GaussExp) alone (src/treebuilders/grid.cpp:78-123): refine the grid where the Gaussians are visible, no
+// coefficients. Host only.
+int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, const double *alpha, const double *pos,
+                             const int *power, int max_iter) {
+    GaussExp<3> gexp(n_gauss);
+    for (int i = 0; i < n_gauss; i++) {
+        gexp[i].coef = coef[i];
+        gexp[i].alpha = alpha[i];
+        for (int d = 0; d < 3; d++) {
+            gexp[i].pos[d] = pos[3 * i + d];
+            gexp[i].power[d] = power ? power[3 * i + d] : 0;
+        }
+    }
+    build_grid<3>(tree->host, gexp, max_iter);
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    tree->dev.nNodes = 0;
+    tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
+    return 0;
+}
+
 int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
                           const double *pos, const int *power, int do_build_grid, int finalize) {
     if (finalize) require_device("mrx_project_gaussians (final BottomUp transform)");

@@ -2,6 +2,8 @@
 // interpolating scaling functions, Hilbert-curve state tables.
 #include "mrx_host.hpp"
 
+#include <dlfcn.h>
+
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -31,7 +33,22 @@ void load_raw() {
         const char *env = std::getenv("MRX_TABLES");
         if (env) g_table_path = env;
     }
-    if (g_table_path.empty()) MRX_ABORT("table path not set (mrx_set_table_path / MRX_TABLES)");
+    if (g_table_path.empty()) {
+        // next to the library: <dir of libmrcpp_b200.so>/../data/mwtables.bin (the in-tree layout), like the reference falls
+        // back to its install directory (details::find_filters, src/utils/details.cpp:53-69)
+        Dl_info info;
+        if (dladdr(reinterpret_cast<const void *>(&set_table_path), &info) && info.dli_fname) {
+            std::string lib(info.dli_fname);
+            const size_t slash = lib.rfind('/');
+            const std::string dir = slash == std::string::npos ? std::string(".") : lib.substr(0, slash);
+            const std::string cand = dir + "/../data/mwtables.bin";
+            if (FILE *probe = std::fopen(cand.c_str(), "rb")) {
+                std::fclose(probe);
+                g_table_path = cand;
+            }
+        }
+    }
+    if (g_table_path.empty()) MRX_ABORT("table path not set (mrx_init / MRX_TABLES) and no data/mwtables.bin next to the library");
     FILE *f = std::fopen(g_table_path.c_str(), "rb");
     if (!f) MRX_ABORT("cannot open table file " + g_table_path);
     char magic[4];

@@ -63,6 +63,12 @@ void *ref_tree_create(void *mra) { return new RefTree(*static_cast<MultiResoluti
 void ref_tree_destroy(void *t) { delete static_cast<RefTree *>(t); }
 int ref_tree_n_nodes(void *t) { return static_cast<RefTree *>(t)->tree.getNNodes(); }
 double ref_tree_square_norm(void *t) { return static_cast<RefTree *>(t)->tree.getSquareNorm(); }
+double ref_tree_integrate(void *t) { return static_cast<RefTree *>(t)->tree.integrate(); }
+/// build_grid alone (src/treebuilders/grid.cpp:106-123)
+void ref_build_grid_gaussians(void *t, int n, const double *coef, const double *alpha, const double *pos, const int *power) {
+    GaussExp<3> g = make_exp(n, coef, alpha, pos, power);
+    build_grid(static_cast<RefTree *>(t)->tree, g);
+}
 
 /// build_grid + project of a Gaussian expansion (src/treebuilders/grid.cpp:106-123, project.cpp:85-104)
 void ref_project_gaussians(void *t, double prec, int n, const double *coef, const double *alpha, const double *pos, const int *power,

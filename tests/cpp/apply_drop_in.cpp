@@ -1,0 +1,112 @@
+// The hot path through the C++ MRCPP mirror (include/MRCPP/ over the C ABI), written the way a program is written against
+// MRCPP itself: Poisson apply (the case of the reference's examples/poisson.cpp and tests/operators/poisson_operator.cpp),
+// the hydrogen 1s fixed point of the Helmholtz operator (tests/operators/helmholtz_operator.cpp) and an ABGV derivative of a
+// Gaussian against the projection of its analytic derivative (tests/operators/derivative_operator.cpp pattern).
+// Prints "key value" lines; tests/test_zz_gpu_cpp_mirror.py checks them against the analytic answers and against the same
+// cases run through the Python mirror. Needs a CUDA device: without one the first projection aborts (no CPU fallback).
+#include "MRCPP/Gaussians"
+#include "MRCPP/MWFunctions"
+#include "MRCPP/MWOperators"
+#include "MRCPP/Printer"
+#include "MRCPP/Timer"
+
+constexpr int D = 3;
+
+static void poisson_case() {
+    const int order = 7;
+    const double prec = 1.0e-5;
+    mrcpp::BoundingBox<D> world(-4, std::array<int, D>{-1, -1, -1}, std::array<int, D>{2, 2, 2});
+    mrcpp::MultiResolutionAnalysis<D> MRA(world, mrcpp::InterpolatingBasis(order), 25);
+
+    const double beta = 100.0;
+    mrcpp::GaussFunc<D> rho(beta, std::pow(beta / mrcpp::pi, 1.5), mrcpp::Coord<D>{mrcpp::pi / 3.0, mrcpp::pi / 3.0, mrcpp::pi / 3.0});
+    mrcpp::PoissonOperator P(MRA, prec);
+
+    mrcpp::FunctionTree<D> f_tree(MRA);
+    mrcpp::build_grid(f_tree, rho);
+    mrcpp::project(prec, f_tree, rho);
+
+    mrcpp::Timer t;
+    mrcpp::FunctionTree<D> g_tree(MRA);
+    mrcpp::apply(prec, g_tree, P, f_tree);
+    t.stop();
+
+    const auto &st = mrcpp::b200::last_apply_stats();
+    std::printf("poisson_terms %d\n", P.size());
+    std::printf("poisson_f_nodes %d\npoisson_g_nodes %d\n", f_tree.getNNodes(), g_tree.getNNodes());
+    std::printf("poisson_f_integral %.17g\npoisson_f_sqnorm %.17g\n", f_tree.integrate(), f_tree.getSquareNorm());
+    std::printf("poisson_g_integral %.17g\npoisson_g_sqnorm %.17g\n", g_tree.integrate(), g_tree.getSquareNorm());
+    std::printf("poisson_energy %.17g\npoisson_analytic %.17g\n", mrcpp::dot(g_tree, f_tree), rho.calcCoulombEnergy(rho));
+    std::printf("poisson_tuples %lld\npoisson_calc_nodes %lld\npoisson_launches %lld\n", st.f_applied, st.g_nodes, st.kernel_launches);
+    mrcpp::print::tree(0, "g_tree", g_tree, t);
+
+    // fixed-grid variant: the same grid, maxIter = 0 (no refinement)
+    mrcpp::FunctionTree<D> h_tree(MRA);
+    mrcpp::copy_grid(h_tree, g_tree);
+    mrcpp::apply(prec, h_tree, P, f_tree, 0);
+    std::printf("poisson_fixed_grid_nodes %d\npoisson_fixed_grid_energy %.17g\n", h_tree.getNNodes(), mrcpp::dot(h_tree, f_tree));
+
+    // TopDown / BottomUp round trip leaves the norm where it was
+    g_tree.mwTransform(mrcpp::TopDown);
+    g_tree.mwTransform(mrcpp::BottomUp);
+    g_tree.calcSquareNorm();
+    std::printf("poisson_g_sqnorm_roundtrip %.17g\n", g_tree.getSquareNorm());
+}
+
+static void helmholtz_case() {
+    const double proj_prec = 3.0e-3, apply_prec = 3.0e-2, build_prec = 3.0e-3;
+    mrcpp::BoundingBox<D> world(-5, std::array<int, D>{-1, -1, -1}, std::array<int, D>{2, 2, 2});
+    mrcpp::MultiResolutionAnalysis<D> MRA(world, mrcpp::InterpolatingBasis(5), 25);
+    const double c = 1.0 / std::sqrt(mrcpp::pi);
+    auto psi = [c](const mrcpp::Coord<D> &r) -> double { return c * std::exp(-std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2])); };
+    auto vpsi = [c](const mrcpp::Coord<D> &r) -> double {
+        const double x = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        return -c * std::exp(-x) / x;
+    };
+    mrcpp::FunctionTree<D> psi_tree(MRA), vpsi_tree(MRA), out(MRA);
+    mrcpp::project<D, double>(proj_prec, psi_tree, psi);
+    mrcpp::project<D, double>(proj_prec, vpsi_tree, vpsi);
+    mrcpp::HelmholtzOperator H(MRA, 1.0, build_prec); // mu = sqrt(-2 E), E = -1/2
+    mrcpp::copy_grid(out, psi_tree);
+    mrcpp::apply(apply_prec, out, H, vpsi_tree);
+    out.rescale(-1.0 / (2.0 * mrcpp::pi));
+    std::printf("helmholtz_terms %d\nhelmholtz_psi_sqnorm %.17g\n", H.size(), psi_tree.getSquareNorm());
+    std::printf("helmholtz_out_norm %.17g\nhelmholtz_overlap %.17g\n", std::sqrt(out.getSquareNorm()), mrcpp::dot(out, psi_tree));
+}
+
+static void derivative_case() {
+    const int order = 7;
+    const double prec = 1.0e-5;
+    mrcpp::BoundingBox<D> world(-4, std::array<int, D>{-1, -1, -1}, std::array<int, D>{2, 2, 2});
+    mrcpp::MultiResolutionAnalysis<D> MRA(world, mrcpp::InterpolatingBasis(order), 25);
+    const double beta = 20.0, alpha = std::pow(beta / mrcpp::pi, 1.5);
+    const mrcpp::Coord<D> pos{0.3, -0.4, 0.5};
+    mrcpp::GaussFunc<D> f(beta, alpha, pos);
+    mrcpp::ABGVOperator<D> diff(MRA, 0.5, 0.5);
+    mrcpp::FunctionTree<D> f_tree(MRA);
+    mrcpp::build_grid(f_tree, f);
+    mrcpp::project(prec, f_tree, f);
+    for (int dir = 0; dir < D; dir++) {
+        // d/dx_dir of alpha exp(-beta |r - pos|^2) = -2 beta alpha (x_dir - pos_dir) exp(...)
+        std::array<int, D> power{0, 0, 0};
+        power[dir] = 1;
+        mrcpp::GaussFunc<D> df(beta, -2.0 * beta * alpha, pos, power);
+        mrcpp::FunctionTree<D> df_tree(MRA), dg_tree(MRA);
+        mrcpp::build_grid(df_tree, df);
+        mrcpp::project(prec, df_tree, df);
+        mrcpp::apply(dg_tree, diff, f_tree, dir);
+        const double gg = mrcpp::dot(dg_tree, dg_tree), gf = mrcpp::dot(dg_tree, df_tree), ff = mrcpp::dot(df_tree, df_tree);
+        std::printf("derivative_%d_nodes %d\nderivative_%d_sqnorm %.17g\nderivative_%d_rel_err %.17g\n", dir, dg_tree.getNNodes(), dir, gg, dir,
+                    std::sqrt(std::abs(gg - 2.0 * gf + ff) / ff));
+    }
+}
+
+int main(int argc, char **argv) {
+    mrcpp::Printer::init(argc > 1 ? std::atoi(argv[1]) : -1);
+    mrcpp::print::environment(0);
+    poisson_case();
+    helmholtz_case();
+    derivative_case();
+    std::printf("done 1\n");
+    return 0;
+}

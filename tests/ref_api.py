@@ -34,6 +34,7 @@ def lib():
             "ref_apply": (D, [D, P, P, P, I, I]), "ref_apply_derivative": (None, [P, P, P, I]), "ref_dot": (D, [P, P]),
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
+            "ref_tree_integrate": (D, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
             f = getattr(l, name)
@@ -69,6 +70,9 @@ class Tree:
     def square_norm(self):
         return lib().ref_tree_square_norm(self._h)
 
+    def integrate(self):
+        return lib().ref_tree_integrate(self._h)
+
     def export(self):
         """dict keyed like FunctionTree.to_arrays(), nodes in the reference's node-table order"""
         n = self.n_nodes()
@@ -86,6 +90,14 @@ def project(prec, tree, gauss_list, build_grid=True):
     pos = np.ascontiguousarray([g.pos for g in gauss_list], dtype=np.float64)
     power = np.ascontiguousarray([g.power for g in gauss_list], dtype=np.int32)
     lib().ref_project_gaussians(tree._h, float(prec), len(coef), _dp(coef), _dp(expo), _dp(pos), _ip(power), 1 if build_grid else 0)
+
+
+def build_grid(tree, gauss_list):
+    coef = np.array([g.coef for g in gauss_list], dtype=np.float64)
+    expo = np.array([g.beta for g in gauss_list], dtype=np.float64)
+    pos = np.ascontiguousarray([g.pos for g in gauss_list], dtype=np.float64)
+    power = np.ascontiguousarray([g.power for g in gauss_list], dtype=np.int32)
+    lib().ref_build_grid_gaussians(tree._h, len(coef), _dp(coef), _dp(expo), _dp(pos), _ip(power))
 
 
 def poisson(mra, prec):

@@ -1,0 +1,107 @@
+"""C++ host mirror of the MRCPP API (include/MRCPP/, header-only over the C ABI), CPU part: the reference's own example
+programs compile against it UNMODIFIED, host-side calls agree with the Python mirror of the same C ABI, a hot-path call
+without a device aborts like MSG_ABORT, and the program the GPU suite runs (tests/cpp/apply_drop_in.cpp) is checked here
+with the device entry points re-defined on top of the CPU oracle (tests/cpp/oracle_backend.cpp, test infrastructure)."""
+import math
+import os
+import signal
+
+import numpy as np
+import pytest
+
+import cpp_build as cb
+
+CPP = os.path.join(cb.ROOT, "tests", "cpp")
+REF_EXAMPLES = "/root/reference/examples"
+
+
+@pytest.fixture(scope="module")
+def bindir(libs, tmp_path_factory):
+    return str(tmp_path_factory.mktemp("cpp"))
+
+
+def test_host_api_matches_python_mirror(libs, bindir):
+    mw, orc = libs
+    exe = cb.compile_program([os.path.join(CPP, "host_api.cpp")], os.path.join(bindir, "host_api"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr
+    kv = cb.key_values(r.stdout)
+    assert (kv["order"], kv["root_scale"], kv["max_scale"], kv["lower"], kv["upper"]) == (7, -4, 21, -16.0, 16.0)
+    beta = 100.0
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)
+    g = mw.GaussFunc(50.0, (50.0 / math.pi) ** 1.5, (0.1, -0.2, 0.3))
+    assert abs(kv["self_energy"] - math.sqrt(2 * beta / math.pi)) < 1e-14 * kv["self_energy"]  # GaussFunc.cpp:210-237
+    assert abs(kv["pair_energy"] - f.calc_coulomb_energy(g)) < 1e-14
+    assert abs(kv["evalf"] - f.evalf((1.0, 1.1, 0.9))) < 1e-14 * abs(kv["evalf"])
+    assert kv["exp_size"] == 2 and abs(kv["exp_evalf"] - (f.evalf((0.2, -0.1, 0.4)) + g.evalf((0.2, -0.1, 0.4)))) < 1e-13
+    mra = mw.MultiResolutionAnalysis(7, -4, (-1, -1, -1), (2, 2, 2), 25)
+    assert kv["poisson_terms"] == mw.PoissonOperator(mra, 1e-5).size() == 73
+    assert kv["helmholtz_terms"] == mw.HelmholtzOperator(mra, 1.0, 1e-5).size()
+    t = mw.FunctionTree(mra)
+    mw.build_grid(t, f)
+    assert kv["root_nodes"] == 8 and kv["grid_nodes"] == t.getNNodes() and kv["grid_end_nodes"] == t.getNEndNodes()
+    t2 = mw.FunctionTree(mra)
+    e = mw.GaussExp()
+    e.append(f)
+    e.append(g)
+    mw.build_grid(t2, e)
+    assert kv["grid2_nodes"] == kv["copy_nodes"] == t2.getNNodes() and kv["cleared_nodes"] == 8
+    assert kv["square_norm_empty"] == -1.0 and kv["log_lines"] == 8
+
+
+def test_hot_path_call_without_device_aborts(libs, bindir):
+    """error behaviour of the reference (print + abort, Printer.h:165-169), and no CPU fallback behind the C++ mirror"""
+    exe = cb.compile_program([os.path.join(CPP, "apply_drop_in.cpp")], os.path.join(bindir, "apply_drop_in_nodev"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == -signal.SIGABRT
+    assert "no CPU fallback" in r.stderr and "poisson_energy" not in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("example", ["poisson", "projection"])
+def test_reference_examples_compile_unmodified(libs, bindir, example):
+    """examples/poisson.cpp and examples/projection.cpp of the reference, compiled where they lie against include/MRCPP/ and
+    linked with libmrcpp_b200.so; run without a device they print their header and abort at the first device call"""
+    exe = cb.compile_program([os.path.join(REF_EXAMPLES, example + ".cpp")], os.path.join(bindir, "ref_" + example))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == -signal.SIGABRT and "no CPU fallback" in r.stderr
+
+
+def test_drop_in_program_on_the_oracle_backend(libs, bindir):
+    """tests/cpp/apply_drop_in.cpp with the device entry points served by the CPU oracle: the reference's known answers, and
+    the same numbers as the Python mirror + oracle on the same case"""
+    mw, orc = libs
+    exe = cb.compile_program([os.path.join(CPP, "apply_drop_in.cpp"), os.path.join(CPP, "oracle_backend.cpp")],
+                             os.path.join(bindir, "apply_drop_in_cpu"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr
+    kv = cb.key_values(r.stdout)
+    assert kv["done"] == 1
+    check_drop_in_values(kv)
+    # the same Poisson case through the Python mirror and the oracle
+    k, prec, beta = 7, 1e-5, 100.0
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)
+    ft, gt = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    orc.project(prec, ft, f)
+    st = orc.apply(prec, gt, mw.PoissonOperator(mra, prec), ft)
+    assert kv["poisson_f_nodes"] == ft.getNNodes() and kv["poisson_g_nodes"] == gt.getNNodes()
+    assert kv["poisson_tuples"] == st.fApplied and kv["poisson_calc_nodes"] == st.gNodes
+    assert abs(kv["poisson_energy"] - orc.dot(gt, ft)) <= 1e-13 * abs(kv["poisson_energy"])
+    assert abs(kv["poisson_f_integral"] - ft.integrate()) <= 1e-14 and abs(kv["poisson_g_integral"] - gt.integrate()) <= 1e-10
+
+
+def check_drop_in_values(kv):
+    """known answers of tests/cpp/apply_drop_in.cpp (shared with the GPU test)"""
+    prec = 1e-5
+    assert kv["poisson_terms"] == 73
+    assert abs(kv["poisson_analytic"] - 7.978845608) < 1e-9
+    assert abs(kv["poisson_energy"] - kv["poisson_analytic"]) / kv["poisson_analytic"] < prec   # tests/operators/poisson_operator.cpp
+    assert abs(kv["poisson_f_integral"] - 1.0) < 1e-9
+    assert kv["poisson_fixed_grid_nodes"] == kv["poisson_g_nodes"]
+    assert abs(kv["poisson_fixed_grid_energy"] - kv["poisson_analytic"]) / kv["poisson_analytic"] < prec
+    assert kv["poisson_tuples"] > 1e5 and kv["poisson_calc_nodes"] >= kv["poisson_g_nodes"]
+    # tests/operators/helmholtz_operator.cpp: norm and overlap of the fixed point within apply_prec
+    assert abs(kv["helmholtz_out_norm"] - 1.0) < 3e-2 and abs(kv["helmholtz_overlap"] - 1.0) < 3e-2
+    for d in range(3):
+        assert kv[f"derivative_{d}_rel_err"] < 1e-4 and abs(kv[f"derivative_{d}_sqnorm"] - kv["derivative_0_sqnorm"]) < 1e-6

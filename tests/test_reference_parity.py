@@ -215,3 +215,28 @@ def test_oracle_matches_reference_golden_vectors(libs):
     orc.project(prec, ft, f)
     orc.apply(prec, gt, P, ft)
     check_against_golden_ref(mw, ft, gt, P, orc.dot(gt, ft))
+
+
+@needs_ref
+def test_integrate_and_build_grid_match_reference(libs):
+    """FunctionTree::integrate (FunctionTree.cpp:438-454) of a projected density and of the applied potential, and
+    build_grid alone (grid.cpp:106-123): the C-ABI's host entry points against the reference's"""
+    mw, orc = libs
+    k, prec = 7, 1e-5
+    funcs = gaussians(mw, 3, 33)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rb, ob = ref.Tree(rm), mw.FunctionTree(om)
+    ref.build_grid(rb, funcs)
+    mw.build_grid(ob, expansion(mw, funcs))
+    R, O = rb.export(), ob.to_arrays(coefs=False)
+    assert set(ref.by_index(R)) == set(ref.by_index(O)) and len(R["scale"]) > 8
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    assert abs(rf.integrate() - of.integrate()) <= 1e-14 * abs(rf.integrate())
+    assert abs(of.integrate() - 1.0) < 1e-6  # three normalised Gaussians / 3
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, ref.poisson(rm, prec), rf)
+    orc.apply(prec, og, mw.PoissonOperator(om, prec), of)
+    assert abs(rg.integrate() - og.integrate()) <= 1e-12 * abs(rg.integrate())

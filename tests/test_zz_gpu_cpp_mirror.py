@@ -1,0 +1,39 @@
+"""GPU test (-m gpu) of the C++ host mirror (include/MRCPP/): tests/cpp/apply_drop_in.cpp -- a program written against the
+MRCPP API names -- is compiled with g++, linked with libmrcpp_b200.so and run on the device; its numbers must reproduce the
+reference's known answers and the same cases run through the Python mirror (same C ABI, same kernels)."""
+import math
+import os
+
+import pytest
+
+import cpp_build as cb
+from test_cpp_mirror import check_drop_in_values
+
+pytestmark = pytest.mark.gpu
+
+
+def test_drop_in_program_on_the_device(libs, tmp_path):
+    mw, orc = libs
+    from mrcpp_b200 import _lib
+    if _lib.device() is None or _lib.device() < 0:
+        pytest.fail("no CUDA device visible: the product has no CPU fallback")
+    exe = cb.compile_program([os.path.join(cb.ROOT, "tests", "cpp", "apply_drop_in.cpp")], str(tmp_path / "apply_drop_in"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    kv = cb.key_values(r.stdout)
+    assert kv["done"] == 1
+    check_drop_in_values(kv)
+    assert kv["poisson_launches"] > 0  # CUDA kernels ran inside the apply
+    # same Poisson case through the Python mirror on the device
+    k, prec, beta = 7, 1e-5, 100.0
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    f = mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)
+    ft, gt = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(prec, ft, f, device=True)
+    st = mw.apply(prec, gt, mw.PoissonOperator(mra, prec), ft)
+    assert kv["poisson_f_nodes"] == ft.getNNodes() and kv["poisson_g_nodes"] == gt.getNNodes()
+    assert kv["poisson_tuples"] == st.f_applied and kv["poisson_calc_nodes"] == st.g_nodes
+    en = mw.dot(gt, ft)
+    assert abs(kv["poisson_energy"] - en) <= 1e-12 * abs(en)
+    assert abs(kv["poisson_g_sqnorm"] - gt.getSquareNorm()) <= 1e-12 * gt.getSquareNorm()
+    assert abs(kv["poisson_f_integral"] - ft.integrate()) <= 1e-13 and abs(kv["poisson_g_integral"] - gt.integrate()) <= 1e-9 * abs(gt.integrate())
