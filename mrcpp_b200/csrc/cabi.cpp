@@ -316,6 +316,8 @@ int mrx_project_gaussians(mrx_tree *tree, double prec, int n_gauss, const double
         }
     }
     Tree<3> &h = tree->host;
+    h.allocCoefs = true; // host quadrature writes host coefficient chunks
+    h.ensureCoefStorage();
     if (do_build_grid) build_grid<3>(h, gexp, -1);
     project_gaussians<3>(prec, h, gexp, -1, false, /*finalize=*/false);
     tree->hostCoefsValid = true;
@@ -334,6 +336,8 @@ int mrx_project_function(mrx_tree *tree, double prec, mrx_func3 f, void *user, i
     if (finalize) require_device("mrx_project_function (final BottomUp transform)");
     if (!f) MRX_ABORT("mrx_project_function: null callback");
     Tree<3> &h = tree->host;
+    h.allocCoefs = true; // host quadrature writes host coefficient chunks
+    h.ensureCoefStorage();
     // ProjectionCalculator::calcNode on the host (quadrature at the expanded child points); callbacks that are not thread safe
     // (e.g. a host-language closure) are called from one thread only
     if (threads_ok) {
