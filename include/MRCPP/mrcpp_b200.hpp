@@ -20,7 +20,9 @@
 //                                src/operators/{ConvolutionOperator,PoissonOperator,HelmholtzOperator,ABGVOperator}.h
 //   build_grid, copy_grid, clear_grid   src/treebuilders/grid.h:35-43
 //   project                      src/treebuilders/project.h:33-34
-//   apply (convolution, derivative)     src/treebuilders/apply.h:41,49
+//   apply (convolution, derivative), gradient, divergence   src/treebuilders/apply.h:41,49,51,55
+//   add (on a given grid)        src/treebuilders/add.h
+//   FunctionTreeVector           src/trees/FunctionTreeVector.h
 //   dot                          src/treebuilders/multiply.h
 //   Printer, print::*, Timer     src/utils/Printer.h:61-133, src/utils/Timer.h:42-50
 #pragma once
@@ -37,6 +39,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../mrcpp_b200.h"
@@ -378,6 +381,19 @@ public:
     T evalf(const Coord<D> &) const override { MRCPP_B200_ABORT("FunctionTree::evalf is not on the B200 path"); }
 };
 
+// ---- FunctionTreeVector (src/trees/FunctionTreeVector.h): (coefficient, tree) pairs, trees not owned ------------------
+template <int D, typename T = double> using CoefsFunctionTree = std::tuple<T, FunctionTree<D, T> *>;
+template <int D, typename T = double> using FunctionTreeVector = std::vector<CoefsFunctionTree<D, T>>;
+template <int D, typename T> T get_coef(const FunctionTreeVector<D, T> &fs, int i) { return std::get<0>(fs[i]); }
+template <int D, typename T> FunctionTree<D, T> &get_func(FunctionTreeVector<D, T> &fs, int i) { return *std::get<1>(fs[i]); }
+template <int D, typename T> const FunctionTree<D, T> &get_func(const FunctionTreeVector<D, T> &fs, int i) { return *std::get<1>(fs[i]); }
+/// clear(fs, dealloc): FunctionTreeVector.h -- optionally deletes the trees, then empties the vector
+template <int D, typename T> void clear(FunctionTreeVector<D, T> &fs, bool dealloc = false) {
+    if (dealloc)
+        for (auto &t : fs) delete std::get<1>(t);
+    fs.clear();
+}
+
 // ---- operators ---------------------------------------------------------------------------------------------------------
 class MWOperatorBase {
 public:
@@ -479,10 +495,17 @@ template <int D, typename T> void build_grid(FunctionTree<D, T> &out, const Repr
 }
 /// copy_grid / clear_grid: src/treebuilders/grid.cpp:150-166, :180-186
 template <int D, typename T> void copy_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp) { mrx_tree_copy_grid(out.handle(), inp.handle()); }
+/// build_grid(out, tree): extend the grid of `out` with the nodes of `inp` (src/treebuilders/grid.cpp:144-153)
 template <int D, typename T> void build_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp, int maxIter = -1) {
     if (maxIter >= 0) MRCPP_B200_ABORT("build_grid(out, tree, maxIter >= 0) is not on the B200 path");
-    if (out.getNNodes() != out.getMRA().getWorldBox().size()) MRCPP_B200_ABORT("build_grid(out, tree): `out` must enter as empty roots on the B200 path");
-    mrx_tree_copy_grid(out.handle(), inp.handle());
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_tree_build_grid_from(out.handle(), inp.handle());
+}
+
+/// build_grid(out, FunctionTreeVector): union with the grids of all inputs (src/treebuilders/grid.cpp:170-178)
+template <int D, typename T> void build_grid(FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp, int maxIter = -1) {
+    if (maxIter >= 0) MRCPP_B200_ABORT("build_grid(out, trees, maxIter >= 0) is not on the B200 path");
+    for (auto &t : inp) mrx_tree_build_grid_from(out.handle(), std::get<1>(t)->handle());
 }
 
 namespace b200 {
@@ -533,6 +556,56 @@ template <int D, typename T> void apply(FunctionTree<D, T> &out, DerivativeOpera
     if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
     mrx_apply_derivative(out.handle(), oper.handle(), inp.handle(), dir, &b200::last_apply_stats());
 }
+/// mrcpp::add(prec, out, inp, maxIter): src/treebuilders/add.cpp:41-70. On the B200 path the sum is computed on the grid `out`
+/// enters with (prec < 0 or maxIter = 0, the form mrcpp::divergence uses); the adaptive form aborts.
+template <int D, typename T>
+void add(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp, int maxIter = -1, bool absPrec = false, bool conjugate = false) {
+    (void)absPrec;
+    (void)conjugate;
+    if (prec >= 0.0 && maxIter != 0) MRCPP_B200_ABORT("adaptive add (prec > 0) is not on the B200 path: build_grid(out, inp) first, then add(-1.0, out, inp)");
+    std::vector<T> c;
+    std::vector<mrx_tree *> h;
+    for (auto &t : inp) {
+        if (out.getMRA() != std::get<1>(t)->getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+        c.push_back(std::get<0>(t));
+        h.push_back(std::get<1>(t)->handle());
+    }
+    mrx_tree_add(out.handle(), (int)h.size(), c.data(), h.data());
+}
+template <int D, typename T>
+void add(double prec, FunctionTree<D, T> &out, T a, FunctionTree<D, T> &inp_a, T b, FunctionTree<D, T> &inp_b, int maxIter = -1, bool absPrec = false,
+         bool conjugate = false) {
+    FunctionTreeVector<D, T> v;
+    v.push_back(std::make_tuple(a, &inp_a));
+    v.push_back(std::make_tuple(b, &inp_b));
+    add(prec, out, v, maxIter, absPrec, conjugate);
+}
+/// mrcpp::gradient(oper, inp): src/treebuilders/apply.cpp:444-452 (the caller owns the trees: clear(vec, true))
+template <int D, typename T> FunctionTreeVector<D, T> gradient(DerivativeOperator<D> &oper, FunctionTree<D, T> &inp) {
+    FunctionTreeVector<D, T> out;
+    for (int d = 0; d < D; d++) {
+        auto *grad_d = new FunctionTree<D, T>(inp.getMRA());
+        apply(*grad_d, oper, inp, d);
+        out.push_back(std::make_tuple(T(1.0), grad_d));
+    }
+    return out;
+}
+/// mrcpp::divergence(out, oper, inp): src/treebuilders/apply.cpp:514-530
+template <int D, typename T> void divergence(FunctionTree<D, T> &out, DerivativeOperator<D> &oper, FunctionTreeVector<D, T> &inp) {
+    if ((int)inp.size() != D) MRCPP_B200_ABORT("Dimension mismatch");
+    for (auto &t : inp)
+        if (out.getMRA() != std::get<1>(t)->getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    FunctionTreeVector<D, T> tmp_vec;
+    for (int d = 0; d < D; d++) {
+        auto *out_d = new FunctionTree<D, T>(get_func(inp, d).getMRA());
+        apply(*out_d, oper, get_func(inp, d), d);
+        tmp_vec.push_back(std::make_tuple(get_coef(inp, d), out_d));
+    }
+    build_grid(out, tmp_vec);
+    add(-1.0, out, tmp_vec, 0); // addition on the union grid
+    clear(tmp_vec, true);
+}
+
 /// mrcpp::dot(bra, ket): src/treebuilders/multiply.cpp:286-318
 template <int D, typename T> T dot(FunctionTree<D, T> &bra, FunctionTree<D, T> &ket) {
     if (bra.getMRA() != ket.getMRA()) MRCPP_B200_ABORT("Trees not compatible");

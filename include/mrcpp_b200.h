@@ -183,6 +183,14 @@ double mrx_dot(mrx_tree *bra, mrx_tree *ket);
 /* FunctionTree::rescale(c): src/trees/FunctionTree.cpp (coefficient-wise scaling) */
 int mrx_tree_rescale(mrx_tree *tree, double c);
 
+/* build_grid(out, inp) (src/treebuilders/grid.cpp:144-153): extend the grid of `out` with every node of `inp` (union of the
+ * two grids; coefficients of `out` are dropped). Host only. */
+int mrx_tree_build_grid_from(mrx_tree *out, const mrx_tree *inp);
+/* add(-1.0, out, {(coefs[i], inp[i])}, 0) (src/treebuilders/add.cpp:41-70, AdditionCalculator.h:42-66): sum of the inputs on
+ * the grid `out` enters with, no refinement -- the form mrcpp::divergence uses (apply.cpp:527-528). Inputs coarser than the
+ * grid contribute their generated (scaling-only) nodes, inputs finer than the grid are truncated, as in the reference. */
+int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp);
+
 /* residency control for measurement: host->device / device->host copies of a tree's coefficients */
 int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */
 int mrx_tree_sync_host(mrx_tree *tree);   /* download if the device copy is newer                    */

@@ -255,7 +255,11 @@ def _gauss_arrays(func):
 
 
 def build_grid(out, func, maxIter=-1):
-    """build_grid(out, GaussFunc | GaussExp) alone (src/treebuilders/grid.cpp:78-123): host only"""
+    """build_grid(out, GaussFunc | GaussExp) alone (src/treebuilders/grid.cpp:78-123), or build_grid(out, FunctionTree): extend
+    the grid of `out` with the nodes of another tree (grid.cpp:144-153). Host only."""
+    if isinstance(func, FunctionTree):
+        _lib.load().mrx_tree_build_grid_from(out._h, func._h)
+        return
     n, coef, alpha, pos, power = _gauss_arrays(func)
     _lib.load().mrx_build_grid_gaussians(out._h, n, _dp(coef), _dp(alpha), _dp(pos), _ip(power), int(maxIter))
 
@@ -348,6 +352,41 @@ def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None, comm=None):
     else:
         _lib.load().mrx_apply(float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, C.byref(st))
     return st
+
+
+def add(prec, out, inp, maxIter=-1):
+    """mrcpp::add(prec, out, FunctionTreeVector) (src/treebuilders/add.cpp:41-70) on the grid `out` enters with: inp = list of
+    (coef, tree). Only the non-refining form (prec < 0 or maxIter = 0) is on the device path."""
+    if prec >= 0 and maxIter != 0:
+        raise NotImplementedError("adaptive add (prec > 0) is not on the B200 path: build the grid first and call add(-1, ...)")
+    c = np.ascontiguousarray([float(ci) for ci, _ in inp], dtype=np.float64)
+    h = (C.c_void_p * len(inp))(*[t._h for _, t in inp])
+    _lib.load().mrx_tree_add(out._h, len(inp), _dp(c), h)
+
+
+def gradient(oper, inp):
+    """mrcpp::gradient(D, f) (src/treebuilders/apply.cpp:444-452): [(1.0, df/dx), (1.0, df/dy), (1.0, df/dz)]"""
+    out = []
+    for d in range(3):
+        g = FunctionTree(inp.mra)
+        apply(None, g, oper, inp, dir=d)
+        out.append((1.0, g))
+    return out
+
+
+def divergence(out, oper, inp):
+    """mrcpp::divergence(out, D, FunctionTreeVector) (src/treebuilders/apply.cpp:514-530): derivative of component d along d,
+    union grid, sum. inp = list of three (coef, tree)."""
+    if len(inp) != 3:
+        raise ValueError("Dimension mismatch")
+    parts = []
+    for d, (c, t) in enumerate(inp):
+        p = FunctionTree(t.mra)
+        apply(None, p, oper, t, dir=d)
+        parts.append((c, p))
+    for _, p in parts:
+        build_grid(out, p)
+    add(-1.0, out, parts, 0)
 
 
 def dot(bra, ket):

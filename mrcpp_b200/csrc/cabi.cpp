@@ -535,6 +535,26 @@ int mrx_tree_rescale(mrx_tree *tree, double c) {
     device_rescale(*tree, c);
     return 0;
 }
+int mrx_tree_build_grid_from(mrx_tree *out, const mrx_tree *inp) {
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    out->host.extendGridFrom(inp->host);
+    out->hostCoefsValid = true;
+    out->devValid = false;
+    out->dev.nNodes = 0;
+    out->dev.topoNodes = -1;
+    out->dev.partial = false;
+    return 0;
+}
+int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {
+    require_device("mrx_tree_add");
+    if (n <= 0) MRX_ABORT("mrx_tree_add: empty input vector");
+    for (int i = 0; i < n; i++) {
+        if (!(out->host.mra == inp[i]->host.mra)) MRX_ABORT("Incompatible MRA");
+        if (inp[i] == out) MRX_ABORT("mrx_tree_add: output tree among the inputs");
+    }
+    device_add(*out, n, coefs, inp);
+    return 0;
+}
 int mrx_tree_sync_device(mrx_tree *tree) {
     require_device("mrx_tree_sync_device");
     if (!tree->devValid) tree_upload(*tree);

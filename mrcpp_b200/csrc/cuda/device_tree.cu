@@ -317,6 +317,55 @@ double device_dot(mrx_tree &bra, mrx_tree &ket) {
     return s;
 }
 
+// add(prec < 0 | maxIter = 0, out, {(c_i, inp_i)}) on the grid `out` enters with (src/treebuilders/add.cpp:41-70,
+// AdditionCalculator.h:42-66), restated for the compressed representation: the sum is linear, so its wavelet blocks are the
+// sums of the inputs' wavelet blocks on the nodes they share with `out` (zero where an input is coarser: generated nodes
+// have no wavelet part), its root scaling blocks the sums of the root scaling blocks, and every other scaling block follows
+// from those by reconstruction -- one TopDown(+=) pass over the zero-initialised scaling blocks. That is what the reference's
+// per-end-node sum followed by BottomUp produces (its branch nodes are compress(children) = the same (s, w) sums).
+void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp) {
+    require_device("device_add");
+    Tree<3> &h = out.host;
+    cudaStream_t st = stream();
+    for (int i = 0; i < n; i++)
+        if (!inp[i]->devValid) tree_upload(*inp[i]);
+    out.dev.coefs.reserve((size_t)h.nReal * h.ncoef, false, st);
+    out.dev.norms.reserve((size_t)h.nReal * 8, false, st);
+    MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p, 0, sizeof(double) * (size_t)h.nReal * h.ncoef, st));
+    out.dev.nNodes = h.nReal;
+    out.dev.nGen = 0;
+    out.dev.topoNodes = -1;
+    out.dev.partial = false;
+    std::vector<std::vector<int>> pairs(n);
+    std::vector<DevBuf<int>> dpairs(n);
+    for (int i = 0; i < n; i++) {
+        const Tree<3> &b = inp[i]->host;
+        // nodes present in both trees, walked together from the roots
+        std::vector<std::pair<int, int>> stack;
+        for (int r = h.nRoots - 1; r >= 0; r--) stack.push_back({r, r});
+        while (!stack.empty()) {
+            auto pr = stack.back();
+            stack.pop_back();
+            pairs[i].push_back(pr.first);
+            pairs[i].push_back(pr.second);
+            const bool oB = h.isBranch(pr.first) && !h.isGen(h.nodes[pr.first].child0);
+            const bool iB = b.isBranch(pr.second) && !b.isGen(b.nodes[pr.second].child0);
+            if (oB && iB)
+                for (int k = 7; k >= 0; k--) stack.push_back({h.nodes[pr.first].child0 + k, b.nodes[pr.second].child0 + k});
+        }
+        const int np = (int)pairs[i].size() / 2;
+        dpairs[i].reserve(pairs[i].size(), false, st);
+        MRX_CUDA(cudaMemcpyAsync(dpairs[i].p, pairs[i].data(), sizeof(int) * pairs[i].size(), cudaMemcpyHostToDevice, st));
+        launch_axpy_nodes(out.dev.coefs.p, inp[i]->dev.coefs.p, dpairs[i].p, np, h.nRoots, h.Kd, c[i], st);
+    }
+    MRX_CUDA(cudaStreamSynchronize(st)); // the pair lists are host vectors read by the asynchronous copies above
+    for (int s = 0; s < h.nReal; s++) h.nodes[s].flags |= FlagHasCoefs;
+    out.devValid = true;
+    out.hostCoefsValid = false;
+    device_mw_transform(out, MRX_TOP_DOWN, /*overwrite=*/false); // + norms of every node
+    h.calcSquareNorm();
+}
+
 void device_rescale(mrx_tree &t, double c) {
     if (!t.devValid) tree_upload(t);
     cudaStream_t st = stream();

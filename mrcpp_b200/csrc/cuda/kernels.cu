@@ -534,6 +534,18 @@ __global__ void scale_kernel(double *x, size_t n, double c) {
     for (; i < n; i += stride) x[i] *= c;
 }
 
+// AdditionCalculator::calcNode (src/treebuilders/AdditionCalculator.h:42-66) for the nodes two trees share: out node o +=
+// c * in node i. Wavelet blocks always; the scaling block only on root nodes -- every other scaling block of the sum is
+// produced by the TopDown(+=) pass that follows (device_add), which also covers output nodes finer than the input tree.
+// One CTA per pair; pairs of one launch have distinct output nodes, so there is no race and the summation order over the
+// input trees is the launch order.
+__global__ void __launch_bounds__(256) axpy_nodes_kernel(double *out, const double *in, const int *pairs, int nRoots, int Kd, double c) {
+    const int o = pairs[2 * blockIdx.x], i = pairs[2 * blockIdx.x + 1];
+    double *po = out + (size_t)o * 8 * Kd;
+    const double *pi = in + (size_t)i * 8 * Kd;
+    for (int j = (o < nRoots ? 0 : Kd) + threadIdx.x; j < 8 * Kd; j += 256) po[j] = __dadd_rn(po[j], __dmul_rn(c, pi[j]));
+}
+
 size_t transform_smem(int K, int &padOn) {
     int K2 = K * K, Kd = K2 * K;
     padOn = 1;
@@ -657,6 +669,13 @@ void launch_reduce_partials(double *coefs, const double *partials, const int *it
 void launch_dot(const double *a, const double *b, const int *pairs, double *res, int np, int nRoots, int Kd, cudaStream_t st) {
     if (np <= 0) return;
     dot_kernel<<<np, 256, 0, st>>>(a, b, pairs, res, nRoots, Kd);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t st) {
+    if (np == 0) return;
+    axpy_nodes_kernel<<<np, 256, 0, st>>>(out, in, pairs, nRoots, Kd, c);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

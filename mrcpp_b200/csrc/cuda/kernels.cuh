@@ -45,5 +45,7 @@ void launch_reduce_partials(double *coefs, const double *partials, const int *it
 
 void launch_dot(const double *a, const double *b, const int *pairs, double *res, int np, int nRoots, int Kd, cudaStream_t st);
 void launch_scale(double *x, size_t n, double c, cudaStream_t st);
+/// out node pairs[2 p] += c * in node pairs[2 p + 1] (wavelet blocks; scaling block only where the out node is a root)
+void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t st);
 
 } // namespace mrx

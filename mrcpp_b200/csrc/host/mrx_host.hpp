@@ -195,6 +195,7 @@ public:
     int getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents, bool withCoefStorage = false);
     void clearToRoots();          // FunctionTree::clear
     void copyGridFrom(const Tree<D> &other); // copy_grid (grid.cpp:150-166)
+    void extendGridFrom(const Tree<D> &other); // build_grid(out, inp) (grid.cpp:144-153): union with the grid of `other`
     bool allocCoefs = true;       // false: new nodes get no host coefficient storage (device-resident)
     void ensureCoefStorage();     // allocate host storage for all nodes (before a download)
     /// host coefficient chunks (64 nodes each) for device-side gathers; pinned (device-readable) unless the tree was

@@ -127,6 +127,26 @@ template <int D> void Tree<D>::copyGridFrom(const Tree<D> &other) {
     }
 }
 
+// build_grid(out, inp) (src/treebuilders/grid.cpp:144-153): TreeBuilder loop with a CopyAdaptor -- the end nodes of this tree
+// split wherever `other` has real children at the same index, until every node of `other` is covered; nodes this tree
+// already has stay
+template <int D> void Tree<D>::extendGridFrom(const Tree<D> &other) {
+    std::vector<int> work, next;
+    endNodeTable(work);
+    while (!work.empty()) {
+        next.clear();
+        for (int n : work) {
+            if (isBranch(n)) continue;
+            const int m = other.findNode(nodes[n].scale, nodes[n].l);
+            if (m < 0 || !other.isBranch(m) || other.isGen(other.nodes[m].child0)) continue;
+            if (nodes[n].scale + 1 > mra.maxScale()) continue;
+            const int c0 = createChildren(n, false);
+            for (int c = 0; c < tdim; c++) next.push_back(c0 + c);
+        }
+        work.swap(next);
+    }
+}
+
 template <int D> int Tree<D>::nDepths() const {
     int md = 0;
     for (const auto &nd : nodes) md = std::max(md, nd.scale - mra.rootScale);

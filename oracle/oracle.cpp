@@ -670,6 +670,34 @@ void apply_derivative(Tree<3> &out, Operator &oper, Tree<3> &inp, int dir, Apply
     if (stats) *stats = st;
 }
 
+// add(prec < 0 | maxIter = 0, out, inp) on the grid `out` enters with (src/treebuilders/add.cpp:41-70): TreeBuilder runs the
+// AdditionCalculator (AdditionCalculator.h:42-66) over the END nodes of the grid (TreeCalculator.h:37) -- coefficients of
+// the input node at the same index, generated through getNode where the input tree is coarser -- then BottomUp, square norm
+// and cleanup of the generated nodes.
+void add(Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp) {
+    const FilterSet &fs = filter_set(out.k);
+    for (Tree<3> *t : inp)
+        if (!(t->mra == out.mra)) MRX_ABORT("Incompatible MRA");
+    std::vector<int> work;
+    out.endNodeTable(work);
+    for (int n : work) {
+        double *o = out.coef(n);
+        std::memset(o, 0, sizeof(double) * out.ncoef);
+        for (size_t i = 0; i < inp.size(); i++) {
+            Tree<3> &t = *inp[i];
+            const int m = get_node_gen(t, fs, out.nodes[n].scale, out.nodes[n].l, nullptr);
+            const double *x = t.coef(m);
+            const int nc = t.isGen(m) ? t.Kd : t.ncoef; // generated nodes hold the scaling block only (MWNode.cpp:644)
+            for (int j = 0; j < nc; j++) o[j] += c[i] * x[j];
+        }
+        out.nodes[n].flags |= FlagHasCoefs;
+        calc_norms(out, n);
+    }
+    mw_transform_up(out);
+    calc_square_norm(out);
+    for (Tree<3> *t : inp) t->deleteGenerated();
+}
+
 // <bra|ket> from compressed coefficients: scaling blocks of the roots + wavelet blocks of every node
 // present in both trees (mathematically equal to mrcpp::dot, multiply.cpp:286-318).
 double dot(const Tree<3> &bra, const Tree<3> &ket) {
@@ -740,4 +768,10 @@ void orc_mw_transform_down(void *tree, int overwrite) { orc::mw_transform_down(*
 void orc_mw_transform_up(void *tree) { orc::mw_transform_up(*static_cast<Tree<3> *>(tree)); }
 void orc_calc_square_norm(void *tree) { orc::calc_square_norm(*static_cast<Tree<3> *>(tree)); }
 double orc_dot(void *bra, void *ket) { return orc::dot(*static_cast<Tree<3> *>(bra), *static_cast<Tree<3> *>(ket)); }
+void orc_add(void *out, int n, const double *coefs, void **inp) {
+    std::vector<double> c(coefs, coefs + n);
+    std::vector<Tree<3> *> t(n);
+    for (int i = 0; i < n; i++) t[i] = static_cast<Tree<3> *>(inp[i]);
+    orc::add(*static_cast<Tree<3> *>(out), c, t);
+}
 }

@@ -12,6 +12,7 @@
 #include "MRCPP/MWOperators"
 #include "MRCPP/Printer"
 #include "MRCPP/Timer"
+#include "treebuilders/add.h"
 #include "treebuilders/apply.h"
 #include "treebuilders/grid.h"
 #include "treebuilders/project.h"
@@ -101,6 +102,20 @@ void ref_apply_derivative(void *out, void *oper, void *inp, int dir) {
     apply(static_cast<RefTree *>(out)->tree, *static_cast<DerivativeOperator<3> *>(oper), static_cast<RefTree *>(inp)->tree, dir);
 }
 double ref_dot(void *a, void *b) { return dot(static_cast<RefTree *>(a)->tree, static_cast<RefTree *>(b)->tree); }
+/// build_grid(out, inp): extend the grid of `out` with the nodes of `inp` (src/treebuilders/grid.cpp:144-153)
+void ref_build_grid_tree(void *out, void *inp) { build_grid(static_cast<RefTree *>(out)->tree, static_cast<RefTree *>(inp)->tree); }
+/// add(-1.0, out, {(c_i, inp_i)}, 0): addition on the grid `out` enters with (src/treebuilders/add.cpp:41-70)
+void ref_add(void *out, int n, const double *coefs, void **inp) {
+    FunctionTreeVector<3, double> vec;
+    for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
+    add(-1.0, static_cast<RefTree *>(out)->tree, vec, 0);
+}
+/// divergence(out, oper, {inp_x, inp_y, inp_z}) (src/treebuilders/apply.cpp:514-530)
+void ref_divergence(void *out, void *oper, void **inp) {
+    FunctionTreeVector<3, double> vec;
+    for (int d = 0; d < 3; d++) vec.push_back(std::make_tuple(1.0, &static_cast<RefTree *>(inp[d])->tree));
+    divergence(static_cast<RefTree *>(out)->tree, *static_cast<DerivativeOperator<3> *>(oper), vec);
+}
 void ref_copy_grid(void *out, void *inp) { copy_grid(static_cast<RefTree *>(out)->tree, static_cast<RefTree *>(inp)->tree); }
 void ref_mw_transform(void *t, int type, int overwrite) { static_cast<RefTree *>(t)->tree.mwTransform(type, overwrite != 0); }
 

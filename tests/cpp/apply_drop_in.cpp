@@ -101,12 +101,47 @@ static void derivative_case() {
     }
 }
 
+static void divergence_case() {
+    // gradient and divergence (apply.h:51,55): div grad f of a Gaussian against the projection of its analytic Laplacian
+    // (4 beta^2 r^2 - 6 beta) f, and <div grad f | f> = -|grad f|^2 (the ABGV operator with a = b = 1/2 is antisymmetric)
+    const int order = 7;
+    const double prec = 1.0e-5;
+    mrcpp::BoundingBox<D> world(-4, std::array<int, D>{-1, -1, -1}, std::array<int, D>{2, 2, 2});
+    mrcpp::MultiResolutionAnalysis<D> MRA(world, mrcpp::InterpolatingBasis(order), 25);
+    const double beta = 20.0, alpha = std::pow(beta / mrcpp::pi, 1.5);
+    const mrcpp::Coord<D> pos{0.3, -0.4, 0.5};
+    mrcpp::GaussFunc<D> f(beta, alpha, pos);
+    mrcpp::ABGVOperator<D> diff(MRA, 0.5, 0.5);
+    mrcpp::FunctionTree<D> f_tree(MRA), lap_tree(MRA), ana_tree(MRA), err_tree(MRA);
+    mrcpp::build_grid(f_tree, f);
+    mrcpp::project(prec, f_tree, f);
+    auto grad = mrcpp::gradient(diff, f_tree);
+    double grad_sq = 0.0;
+    for (int d = 0; d < D; d++) grad_sq += mrcpp::get_func(grad, d).getSquareNorm();
+    mrcpp::divergence(lap_tree, diff, grad);
+    mrcpp::clear(grad, true);
+    auto lap = [&](const mrcpp::Coord<D> &r) -> double {
+        double r2 = 0.0;
+        for (int d = 0; d < D; d++) r2 += (r[d] - pos[d]) * (r[d] - pos[d]);
+        return (4.0 * beta * beta * r2 - 6.0 * beta) * alpha * std::exp(-beta * r2);
+    };
+    mrcpp::copy_grid(ana_tree, lap_tree);
+    mrcpp::project<D, double>(-1.0, ana_tree, lap); // on the grid of the numerical result, no refinement
+    mrcpp::build_grid(err_tree, lap_tree);
+    mrcpp::add(-1.0, err_tree, 1.0, lap_tree, -1.0, ana_tree);
+    std::printf("divergence_nodes %d\ndivergence_grad_sqnorm %.17g\ndivergence_overlap %.17g\n", lap_tree.getNNodes(), grad_sq,
+                mrcpp::dot(lap_tree, f_tree));
+    std::printf("divergence_integral %.17g\ndivergence_sqnorm %.17g\ndivergence_rel_err %.17g\n", lap_tree.integrate(), lap_tree.getSquareNorm(),
+                std::sqrt(err_tree.getSquareNorm() / ana_tree.getSquareNorm()));
+}
+
 int main(int argc, char **argv) {
     mrcpp::Printer::init(argc > 1 ? std::atoi(argv[1]) : -1);
     mrcpp::print::environment(0);
     poisson_case();
     helmholtz_case();
     derivative_case();
+    divergence_case();
     std::printf("done 1\n");
     return 0;
 }

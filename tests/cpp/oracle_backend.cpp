@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/mrcpp_b200.h"
 #include "../../mrcpp_b200/csrc/host/mrx_host.hpp"
@@ -27,6 +28,7 @@ struct Oracle {
     void (*sqnorm)(void *);
     double (*dot)(void *, void *);
     void (*set_tables)(const char *);
+    void (*add)(void *, int, const double *, void **);
 };
 Oracle &oracle() {
     static Oracle o = [] {
@@ -44,6 +46,7 @@ Oracle &oracle() {
         r.sqnorm = reinterpret_cast<decltype(r.sqnorm)>(dlsym(h, "orc_calc_square_norm"));
         r.dot = reinterpret_cast<decltype(r.dot)>(dlsym(h, "orc_dot"));
         r.set_tables = reinterpret_cast<decltype(r.set_tables)>(dlsym(h, "orc_set_table_path"));
+        r.add = reinterpret_cast<decltype(r.add)>(dlsym(h, "orc_add"));
         if (const char *t = std::getenv("MRX_TABLES")) r.set_tables(t);
         return r;
     }();
@@ -104,6 +107,13 @@ int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, 
         stats->f_applied = st.fApplied;
         stats->n_nodes_out = st.nNodesOut;
     }
+    return 0;
+}
+int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {
+    std::vector<void *> h(n);
+    for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
+    oracle().add(mrx_tree_host_handle(out), n, coefs, h.data());
+    mrx_tree_host_modified(out);
     return 0;
 }
 double mrx_dot(mrx_tree *bra, mrx_tree *ket) { return oracle().dot(mrx_tree_host_handle(bra), mrx_tree_host_handle(ket)); }

@@ -37,6 +37,7 @@ def lib():
         o.orc_calc_square_norm.argtypes = [C.c_void_p]
         o.orc_dot.argtypes = [C.c_void_p, C.c_void_p]
         o.orc_dot.restype = C.c_double
+        o.orc_add.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
         o.orc_set_table_path(_plib.TABLES.encode())
         _o = o
     return _o
@@ -94,6 +95,29 @@ def dot(bra, ket):
     bra.sync_host()
     ket.sync_host()
     return lib().orc_dot(_th(bra), _th(ket))
+
+
+def add(out, coefs, trees):
+    """add(-1.0, out, {(c_i, tree_i)}, 0) on the grid `out` enters with (src/treebuilders/add.cpp:41-70)"""
+    for t in trees:
+        t.sync_host()
+    c = (C.c_double * len(trees))(*[float(x) for x in coefs])
+    h = (C.c_void_p * len(trees))(*[_th(t) for t in trees])
+    lib().orc_add(_th(out), len(trees), c, h)
+    _modified(out)
+
+
+def divergence(out, oper, trees):
+    """divergence(out, D, {f_x, f_y, f_z}) (src/treebuilders/apply.cpp:514-530): derivative apply per direction, union grid, sum"""
+    import mrcpp_b200 as mw
+    parts = []
+    for d, t in enumerate(trees):
+        p = mw.FunctionTree(out.mra)
+        apply_derivative(p, oper, t, d)
+        parts.append(p)
+    for p in parts:
+        mw.build_grid(out, p)
+    add(out, [1.0] * len(parts), parts)
 
 
 def project(prec, out, func, build_grid=True):

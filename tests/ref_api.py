@@ -34,7 +34,8 @@ def lib():
             "ref_apply": (D, [D, P, P, P, I, I]), "ref_apply_derivative": (None, [P, P, P, I]), "ref_dot": (D, [P, P]),
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
-            "ref_tree_integrate": (D, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
+            "ref_tree_integrate": (D, [P]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
+            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
             f = getattr(l, name)
@@ -122,6 +123,21 @@ def apply_derivative(out, oper, inp, d):
 
 def dot(a, b):
     return lib().ref_dot(a._h, b._h)
+
+
+def build_grid_tree(out, inp):
+    lib().ref_build_grid_tree(out._h, inp._h)
+
+
+def add(out, coefs, trees):
+    c = np.ascontiguousarray(coefs, dtype=np.float64)
+    h = (C.c_void_p * len(trees))(*[t._h for t in trees])
+    lib().ref_add(out._h, len(trees), _dp(c), h)
+
+
+def divergence(out, oper, trees):
+    h = (C.c_void_p * 3)(*[t._h for t in trees])
+    lib().ref_divergence(out._h, oper, h)
 
 
 def by_index(arrays):

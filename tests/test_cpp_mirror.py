@@ -105,3 +105,7 @@ def check_drop_in_values(kv):
     assert abs(kv["helmholtz_out_norm"] - 1.0) < 3e-2 and abs(kv["helmholtz_overlap"] - 1.0) < 3e-2
     for d in range(3):
         assert kv[f"derivative_{d}_rel_err"] < 1e-4 and abs(kv[f"derivative_{d}_sqnorm"] - kv["derivative_0_sqnorm"]) < 1e-6
+    # gradient / divergence / add: div grad f against the analytic Laplacian; <div grad f | f> = -|grad f|^2; integral 0
+    assert kv["divergence_rel_err"] < 1e-3 and abs(kv["divergence_integral"]) < 1e-8
+    assert abs(kv["divergence_overlap"] + kv["divergence_grad_sqnorm"]) < 1e-9 * kv["divergence_grad_sqnorm"]
+    assert abs(kv["divergence_grad_sqnorm"] - 3.0 * kv["derivative_0_sqnorm"]) < 1e-6

@@ -240,3 +240,91 @@ def test_integrate_and_build_grid_match_reference(libs):
     ref.apply(prec, rg, ref.poisson(rm, prec), rf)
     orc.apply(prec, og, mw.PoissonOperator(om, prec), of)
     assert abs(rg.integrate() - og.integrate()) <= 1e-12 * abs(rg.integrate())
+
+
+def _two_trees(mw, orc, k, prec):
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    fa, fb = gaussians(mw, 2, 71), gaussians(mw, 3, 72, box=2.0)
+    trees = []
+    for funcs in (fa, fb):
+        rt, ot = ref.Tree(rm), mw.FunctionTree(om)
+        ref.project(prec, rt, funcs)
+        orc.project(prec, ot, expansion(mw, funcs))
+        trees.append((rt, ot))
+    return rm, om, trees
+
+
+@needs_ref
+@pytest.mark.parametrize("grid", ["union", "roots", "first"])
+def test_add_matches_reference(libs, grid):
+    """add(-1.0, out, {(a, f), (b, g)}, 0) (add.cpp:41-70) on the union grid (build_grid(out, tree), grid.cpp:144-153), on bare
+    roots (inputs truncated) and on the grid of the first input only (second input partly coarser: generated nodes, partly
+    finer: truncated)"""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-4)
+    ro, oo = ref.Tree(rm), mw.FunctionTree(om)
+    if grid in ("union", "first"):
+        ref.build_grid_tree(ro, ra)
+        mw.build_grid(oo, oa)
+    if grid == "union":
+        ref.build_grid_tree(ro, rb)
+        mw.build_grid(oo, ob)
+    assert set(ref.by_index(ro.export())) == set(ref.by_index(oo.to_arrays(coefs=False)))
+    ref.add(ro, [0.5, -2.0], [ra, rb])
+    orc.add(oo, [0.5, -2.0], [oa, ob])
+    same_tree(ro.export(), oo.to_arrays())
+    assert abs(ro.square_norm() - oo.getSquareNorm()) <= 1e-13 * ro.square_norm()
+    assert oa.getNNodes() == ra.n_nodes()  # generated nodes cleaned up
+
+
+@needs_ref
+def test_divergence_matches_reference(libs):
+    """divergence(out, D, {f, g, f}) (apply.cpp:514-530): three derivative applies, union grid, sum"""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-4)
+    RD, OD = ref.abgv(rm, 0.5, 0.5), mw.ABGVOperator(om, 0.5, 0.5)
+    ro, oo = ref.Tree(rm), mw.FunctionTree(om)
+    ref.divergence(ro, RD, [ra, rb, ra])
+    orc.divergence(oo, OD, [oa, ob, oa])
+    same_tree(ro.export(), oo.to_arrays(), tol=1e-11)
+
+
+def test_add_as_wavelet_sum_plus_top_down(libs):
+    """the formulation the DEVICE add uses (device_add, csrc/cuda/device_tree.cu), carried out with the oracle's transforms:
+    wavelet blocks summed on the shared nodes, scaling blocks summed on the roots only, every other scaling block by one
+    TopDown(+=) pass -- must equal the reference algorithm (per-end-node sums with generated nodes, then BottomUp) as restated
+    by orc.add"""
+    mw, orc = libs
+    k, prec = 5, 1e-4
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    fa, fb = expansion(mw, gaussians(mw, 2, 71)), expansion(mw, gaussians(mw, 3, 72, box=2.0))
+    ta, tb = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    orc.project(prec, ta, fa)
+    orc.project(prec, tb, fb)
+    for grid in ("union", "first"):
+        want = mw.FunctionTree(mra)
+        mw.build_grid(want, ta)
+        if grid == "union":
+            mw.build_grid(want, tb)
+        got = mw.FunctionTree(mra)
+        mw.copy_grid(got, want)
+        orc.add(want, [0.5, -2.0], [ta, tb])
+        G = got.to_arrays()
+        Kd = (k + 1) ** 3
+        coefs = np.zeros_like(G["coefs"])
+        gi = ref.by_index(G)
+        for c, t in ((0.5, ta), (-2.0, tb)):
+            T = t.to_arrays()
+            for key, i in ref.by_index(T).items():
+                if key in gi:
+                    o = gi[key]
+                    lo = 0 if G["parent"][o] < 0 else Kd
+                    coefs[o, lo:] += c * T["coefs"][i, lo:]
+        got2 = mw.FunctionTree.from_arrays(mra, G["scale"], G["transl"], G["parent"], G["child0"], coefs)
+        orc.mw_transform_down(got2, overwrite=False)
+        W, H = want.to_arrays(), got2.to_arrays()
+        assert np.array_equal(W["transl"], H["transl"])
+        nrm = np.sqrt((W["coefs"] ** 2).sum(axis=1))
+        err = np.abs(W["coefs"] - H["coefs"]).max(axis=1)
+        assert (err / np.maximum(nrm, 1e-3 * nrm.max())).max() < 1e-13

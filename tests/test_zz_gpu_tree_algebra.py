@@ -1,0 +1,72 @@
+"""GPU parity tests (-m gpu) of the callers next to the derivative apply (src/treebuilders/apply.h:51-55,
+add.h, grid.h:37): add on a given grid, build_grid from trees, gradient, divergence, integrate -- the CUDA path through the
+C ABI against the CPU oracle (which tests/test_reference_parity.py pins against the real reference for the same calls)."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import assert_same_tree, gaussians, world
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(libs):
+    mw, orc = libs
+    from mrcpp_b200 import _lib
+    if _lib.device() is None or _lib.device() < 0:
+        pytest.fail("no CUDA device visible: the product has no CPU fallback")
+    return mw, orc
+
+
+def two_trees(mw, orc, k, prec):
+    mra = world(mw, k)
+    out = []
+    for n, seed, box in ((2, 71, 4.0), (3, 72, 2.0)):
+        func = gaussians(n, seed, box=box, lo=1.0, hi=2.0)
+        g, c = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        mw.project(prec, g, func)
+        orc.project(prec, c, func)
+        out.append((g, c))
+    return mra, out
+
+
+@pytest.mark.parametrize("k,grid", [(5, "union"), (7, "union"), (5, "roots"), (5, "first"), (4, "union")])
+def test_add_on_grid(gpu, k, grid):
+    """add(-1.0, out, {(a, f), (b, g)}, 0) (add.cpp:41-70): union grid, bare roots (inputs truncated), grid of the first
+    input (second input partly coarser -> generated nodes, partly finer -> truncated)"""
+    mw, orc = gpu
+    mra, ((ga, ca), (gb, cb)) = two_trees(mw, orc, k, 1e-4)
+    og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    for o, a, b in ((og, ga, gb), (oc, ca, cb)):
+        if grid in ("union", "first"):
+            mw.build_grid(o, a)
+        if grid == "union":
+            mw.build_grid(o, b)
+    mw.add(-1.0, og, [(0.5, ga), (-2.0, gb)], 0)
+    orc.add(oc, [0.5, -2.0], [ca, cb])
+    assert_same_tree(og, oc)
+    assert abs(og.getSquareNorm() - oc.getSquareNorm()) <= 1e-12 * oc.getSquareNorm()
+    assert abs(og.integrate() - oc.integrate()) <= 1e-12 * max(abs(oc.integrate()), 1.0)
+    # linear functional: <sum | f> = a <f | f> + b <g | f> on the union grid (nothing truncated)
+    if grid == "union":
+        want = 0.5 * mw.dot(ga, ga) - 2.0 * mw.dot(gb, ga)
+        assert abs(mw.dot(og, ga) - want) <= 1e-10 * abs(want)
+
+
+def test_gradient_and_divergence(gpu):
+    """gradient(D, f) and divergence(out, D, {f, g, f}) (apply.cpp:444-452, :514-530) vs the oracle; integrate() of device
+    resident trees (root blocks read back from HBM) vs the oracle's host trees"""
+    mw, orc = gpu
+    mra, ((ga, ca), (gb, cb)) = two_trees(mw, orc, 5, 1e-4)
+    D = mw.ABGVOperator(mra, 0.5, 0.5)
+    grad = mw.gradient(D, ga)
+    for d, (c, g) in enumerate(grad):
+        ref = mw.FunctionTree(mra)
+        orc.apply_derivative(ref, D, ca, d)
+        assert c == 1.0
+        assert_same_tree(g, ref)
+    og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.divergence(og, D, [(1.0, ga), (1.0, gb), (1.0, ga)])
+    orc.divergence(oc, D, [ca, cb, ca])
+    assert_same_tree(og, oc, tol=1e-11)
+    assert abs(ga.integrate() - ca.integrate()) <= 1e-13 and abs(og.integrate() - oc.integrate()) <= 1e-10
