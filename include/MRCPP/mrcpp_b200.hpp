@@ -378,7 +378,17 @@ public:
         rescale(1.0 / std::sqrt(sq));
     }
     void clear() { mrx_tree_clear(this->h); }
-    T evalf(const Coord<D> &) const override { MRCPP_B200_ABORT("FunctionTree::evalf is not on the B200 path"); }
+    /// FunctionTree::evalf / evalf_precise (src/trees/FunctionTree.cpp:374-436): values from the downloaded tree
+    T evalf(const Coord<D> &r) const override {
+        double v = 0.0;
+        mrx_tree_evalf(this->h, 1, r.data(), &v, 0);
+        return v;
+    }
+    T evalf_precise(const Coord<D> &r) {
+        double v = 0.0;
+        mrx_tree_evalf(this->h, 1, r.data(), &v, 1);
+        return v;
+    }
 };
 
 // ---- FunctionTreeVector (src/trees/FunctionTreeVector.h): (coefficient, tree) pairs, trees not owned ------------------

@@ -81,6 +81,10 @@ int mrx_tree_copy_grid(mrx_tree *out, const mrx_tree *inp);
 /* FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454, FunctionNode.cpp:128-157): integral of the function over
  * the world, from the scaling blocks of the root nodes (read back from HBM if the host copy is not current) */
 double mrx_tree_integrate(mrx_tree *tree);
+/* FunctionTree::evalf (precise == 0) / evalf_precise (precise != 0) at n_points points r[n][3] (src/trees/FunctionTree.cpp:
+ * 374-436): function values from the downloaded tree (host arithmetic; the tree is brought to the host first if its
+ * current copy is in HBM). Zero outside the world. */
+int mrx_tree_evalf(mrx_tree *tree, int n_points, const double *r /*[n][3]*/, double *values /*[n]*/, int precise);
 /* build_grid(out, GaussExp) alone (src/treebuilders/grid.cpp:78-123): host only, leaves a grid without coefficients;
  * max_iter < 0: no bound */
 int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, const double *alpha,

@@ -109,6 +109,13 @@ class FunctionTree:
     def getSquareNorm(self):
         return _lib.load().mrx_tree_square_norm(self._h)
 
+    def evalf(self, r, precise=False):
+        """FunctionTree::evalf / evalf_precise (src/trees/FunctionTree.cpp:374-436) at one point or an (n, 3) array of points"""
+        pts = np.ascontiguousarray(np.atleast_2d(np.asarray(r, dtype=np.float64)))
+        out = np.zeros(len(pts))
+        _lib.load().mrx_tree_evalf(self._h, len(pts), _dp(pts), _dp(out), 1 if precise else 0)
+        return float(out[0]) if np.ndim(r) == 1 else out
+
     def integrate(self):
         """FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454)"""
         return _lib.load().mrx_tree_integrate(self._h)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mrx_tree_to_arrays": (_I, [_P, _PI, _PI, _PI, _PI, _PD, _PD]),
     "mrx_tree_copy_grid": (_I, [_P, _P]),
     "mrx_tree_integrate": (_D, [_P]),
+    "mrx_tree_evalf": (_I, [_P, _I, _PD, _PD, _I]),
     "mrx_tree_build_grid_from": (_I, [_P, _P]),
     "mrx_tree_add": (_I, [_P, _I, _PD, C.POINTER(C.c_void_p)]),
     "mrx_build_grid_gaussians": (_I, [_P, _I, _PD, _PD, _PD, _PI, _I]),

@@ -281,6 +281,76 @@ double mrx_tree_integrate(mrx_tree *tree) {
     return result;
 }
 
+// FunctionTree::evalf / evalf_precise (src/trees/FunctionTree.cpp:374-436) with FunctionNode::evalScaling / evalf
+// (src/trees/FunctionNode.cpp:47-93): the end node that holds the point evaluates its scaling block (evalf), or -- precise -- the
+// scaling block of the child it generates from its full coefficients. Host arithmetic on the downloaded tree: reading values
+// back is a boundary operation, not part of the hot path.
+namespace {
+double eval_scaling(const Tree<3> &h, int n, const double r[3]) {
+    const int K = h.K;
+    const double nf = std::pow(2.0, h.nodes[n].scale);
+    double val[3][MaxOrder + 1];
+    for (int d = 0; d < 3; d++) {
+        const double x = r[d] * nf - static_cast<double>(h.nodes[n].l[d]);
+        for (int j = 0; j < K; j++) val[d][j] = (x < 0.0 || x > 1.0) ? 0.0 : interp_scaling_eval(h.k, j, x);
+    }
+    const double *c = h.coef(n);
+    double result = 0.0;
+    for (int z = 0; z < K; z++)
+        for (int y = 0; y < K; y++)
+            for (int x = 0; x < K; x++) result += ((c[x + K * (y + K * z)] * val[0][x]) * val[1][y]) * val[2][z];
+    return std::pow(2.0, (3 * h.nodes[n].scale) / 2.0) * result;
+}
+} // namespace
+
+int mrx_tree_evalf(mrx_tree *tree, int n_points, const double *r, double *values, int precise) {
+    if (!tree->hostCoefsValid) mrx_tree_sync_host(tree);
+    Tree<3> &h = tree->host;
+    const double unit = std::pow(2.0, -h.mra.rootScale);
+    for (int p = 0; p < n_points; p++) {
+        const double *x = r + 3 * (size_t)p;
+        // outside the world the function is zero (FunctionTree.cpp:386); root box as BoundingBox::getBoxIndex(Coord)
+        int n = 0, cells = 1;
+        bool outside = false;
+        for (int d = 0; d < 3; d++) {
+            if (x[d] < h.mra.lower(d) || x[d] >= h.mra.upper(d)) outside = true;
+            if (outside) break;
+            double iint;
+            std::modf((x[d] - h.mra.lower(d)) / unit, &iint);
+            n += cells * (int)iint;
+            cells *= h.mra.nboxes[d];
+        }
+        if (outside) {
+            values[p] = 0.0;
+            continue;
+        }
+        // MWNode::retrieveNodeOrEndNode(r): descend by MWNode::getChildIndex(r) (MWNode.cpp:804-815)
+        auto child_of = [&h](int node, const double *pt) {
+            const double sFac = std::pow(2.0, -h.nodes[node].scale);
+            int c = 0;
+            for (int d = 0; d < 3; d++)
+                if (pt[d] > sFac * (h.nodes[node].l[d] + 0.5)) c += 1 << d;
+            return c;
+        };
+        while (h.isBranch(n) && !h.isGen(h.nodes[n].child0)) n = h.nodes[n].child0 + child_of(n, x);
+        if (!(h.nodes[n].flags & FlagHasCoefs)) MRX_ABORT("Evaluating node without coefs");
+        if (!precise) {
+            values[p] = eval_scaling(h, n, x);
+        } else {
+            const int c = child_of(n, x);
+            std::array<int, 3> l;
+            for (int d = 0; d < 3; d++) l[d] = 2 * h.nodes[n].l[d] + ((c >> d) & 1);
+            const bool saved = h.allocCoefs; // trees born on the device create nodes without host storage
+            h.allocCoefs = true;
+            const int m = h.getNode(h.nodes[n].scale + 1, l); // generates the children from the node's full coefficients
+            values[p] = eval_scaling(h, m, x);
+            h.deleteGenerated();
+            h.allocCoefs = saved;
+        }
+    }
+    return 0;
+}
+
 // build_grid(out, GaussExp) alone (src/treebuilders/grid.cpp:78-123): refine the grid where the Gaussians are visible, no
 // coefficients. Host only.
 int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, const double *alpha, const double *pos,

@@ -64,6 +64,11 @@ void *ref_tree_create(void *mra) { return new RefTree(*static_cast<MultiResoluti
 void ref_tree_destroy(void *t) { delete static_cast<RefTree *>(t); }
 int ref_tree_n_nodes(void *t) { return static_cast<RefTree *>(t)->tree.getNNodes(); }
 double ref_tree_square_norm(void *t) { return static_cast<RefTree *>(t)->tree.getSquareNorm(); }
+double ref_tree_evalf(void *t, const double *r, int precise) {
+    Coord<3> x{r[0], r[1], r[2]};
+    auto &tree = static_cast<RefTree *>(t)->tree;
+    return precise ? tree.evalf_precise(x) : tree.evalf(x);
+}
 double ref_tree_integrate(void *t) { return static_cast<RefTree *>(t)->tree.integrate(); }
 /// build_grid alone (src/treebuilders/grid.cpp:106-123)
 void ref_build_grid_gaussians(void *t, int n, const double *coef, const double *alpha, const double *pos, const int *power) {

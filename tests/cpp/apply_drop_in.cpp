@@ -118,6 +118,14 @@ static void divergence_case() {
     auto grad = mrcpp::gradient(diff, f_tree);
     double grad_sq = 0.0;
     for (int d = 0; d < D; d++) grad_sq += mrcpp::get_func(grad, d).getSquareNorm();
+    // point values of the gradient against the analytic ones (tests/operators/derivative_operator.cpp:417-453 pattern)
+    const mrcpp::Coord<D> r{0.45, -0.3, 0.35};
+    double worst = 0.0;
+    for (int d = 0; d < D; d++) {
+        const double ana = -2.0 * beta * (r[d] - pos[d]) * f.evalf(r);
+        worst = std::max(worst, std::abs(mrcpp::get_func(grad, d).evalf_precise(r) - ana) / std::abs(ana));
+    }
+    std::printf("gradient_point_rel_err %.17g\nfunction_point_rel_err %.17g\n", worst, std::abs(f_tree.evalf_precise(r) - f.evalf(r)) / f.evalf(r));
     mrcpp::divergence(lap_tree, diff, grad);
     mrcpp::clear(grad, true);
     auto lap = [&](const mrcpp::Coord<D> &r) -> double {

@@ -34,7 +34,7 @@ def lib():
             "ref_apply": (D, [D, P, P, P, I, I]), "ref_apply_derivative": (None, [P, P, P, I]), "ref_dot": (D, [P, P]),
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
-            "ref_tree_integrate": (D, [P]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
+            "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
             "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
@@ -73,6 +73,10 @@ class Tree:
 
     def integrate(self):
         return lib().ref_tree_integrate(self._h)
+
+    def evalf(self, r, precise=False):
+        x = np.ascontiguousarray(r, dtype=np.float64)
+        return lib().ref_tree_evalf(self._h, _dp(x), 1 if precise else 0)
 
     def export(self):
         """dict keyed like FunctionTree.to_arrays(), nodes in the reference's node-table order"""

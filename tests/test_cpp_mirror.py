@@ -109,3 +109,4 @@ def check_drop_in_values(kv):
     assert kv["divergence_rel_err"] < 1e-3 and abs(kv["divergence_integral"]) < 1e-8
     assert abs(kv["divergence_overlap"] + kv["divergence_grad_sqnorm"]) < 1e-9 * kv["divergence_grad_sqnorm"]
     assert abs(kv["divergence_grad_sqnorm"] - 3.0 * kv["derivative_0_sqnorm"]) < 1e-6
+    assert kv["gradient_point_rel_err"] < 1e-3 and kv["function_point_rel_err"] < 1e-4  # derivative_operator.cpp:417-453

@@ -328,3 +328,32 @@ def test_add_as_wavelet_sum_plus_top_down(libs):
         nrm = np.sqrt((W["coefs"] ** 2).sum(axis=1))
         err = np.abs(W["coefs"] - H["coefs"]).max(axis=1)
         assert (err / np.maximum(nrm, 1e-3 * nrm.max())).max() < 1e-13
+
+
+@needs_ref
+def test_evalf_matches_reference(libs):
+    """FunctionTree::evalf and evalf_precise (FunctionTree.cpp:374-436) of a projected density and of the applied potential at
+    random points, points outside the world, and the analytic function values within the projection precision"""
+    mw, orc = libs
+    k, prec = 7, 1e-5
+    funcs = gaussians(mw, 3, 33)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, ref.poisson(rm, prec), rf)
+    orc.apply(prec, og, mw.PoissonOperator(om, prec), of)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(-4, 4, (40, 3)), np.array([f.pos for f in funcs]) + 0.01, rng.uniform(-16, 16, (10, 3)),
+                          [[17.0, 0.0, 0.0], [0.0, -16.5, 3.0], [16.0, 1.0, 1.0]]])
+    for rt, ot in ((rf, of), (rg, og)):
+        scale = max(abs(rt.evalf(p, True)) for p in pts)
+        for precise in (False, True):
+            got = ot.evalf(pts, precise)
+            want = np.array([rt.evalf(p, precise) for p in pts])
+            assert np.abs(got - want).max() <= 1e-11 * scale, (precise, np.abs(got - want).max(), scale)
+        assert ot.evalf((17.0, 0.0, 0.0)) == 0.0 and ot.getNNodes() == rt.n_nodes()
+    exact = np.array([sum(f.evalf(p) for f in funcs) for p in pts[:43]])
+    assert np.abs(of.evalf(pts[:43], True) - exact).max() < 50 * prec * np.abs(exact).max()
