@@ -16,7 +16,7 @@
 //   MultiResolutionAnalysis<D>   src/trees/MultiResolutionAnalysis.h:51-54
 //   GaussFunc<D>, GaussExp<D>    src/functions/GaussFunc.h:56, GaussExp.h:54-118
 //   FunctionTree<D, T>           src/trees/FunctionTree.h, MWTree.h:97-179
-//   ConvolutionOperator<D>, PoissonOperator, HelmholtzOperator, DerivativeOperator<D>, ABGVOperator<D>
+//   ConvolutionOperator<D>, PoissonOperator, HelmholtzOperator, DerivativeOperator<D>, ABGVOperator<D>, PHOperator<D>, BSOperator<D>
 //                                src/operators/{ConvolutionOperator,PoissonOperator,HelmholtzOperator,ABGVOperator}.h
 //   build_grid, copy_grid, clear_grid   src/treebuilders/grid.h:35-43
 //   project                      src/treebuilders/project.h:33-34
@@ -488,6 +488,24 @@ public:
     ABGVOperator(const MultiResolutionAnalysis<D> &mra, double a, double b)
             : DerivativeOperator<D>(1) {
         this->h = mrx_abgv_create(mra.handle(), a, b);
+    }
+};
+
+/// src/operators/PHOperator.cpp:40-69 (order 1 or 2)
+template <int D> class PHOperator final : public DerivativeOperator<D> {
+public:
+    PHOperator(const MultiResolutionAnalysis<D> &mra, int order)
+            : DerivativeOperator<D>(order) {
+        this->h = mrx_ph_create(mra.handle(), order);
+    }
+};
+
+/// src/operators/BSOperator.cpp:40-66 (order 1, 2 or 3)
+template <int D> class BSOperator final : public DerivativeOperator<D> {
+public:
+    BSOperator(const MultiResolutionAnalysis<D> &mra, int order)
+            : DerivativeOperator<D>(order) {
+        this->h = mrx_bs_create(mra.handle(), order);
     }
 };
 

@@ -122,6 +122,10 @@ mrx_oper *mrx_helmholtz_create(const mrx_mra *mra, double mu, double prec);
 mrx_oper *mrx_convolution_create(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec);
 /* ABGVOperator<3>(MRA, a, b): src/operators/ABGVOperator.cpp:46-74 */
 mrx_oper *mrx_abgv_create(const mrx_mra *mra, double a, double b);
+/* PHOperator<3>(MRA, order), order 1 or 2: src/operators/PHOperator.cpp:40-69 (Holoborodko smoothing derivative) */
+mrx_oper *mrx_ph_create(const mrx_mra *mra, int order);
+/* BSOperator<3>(MRA, order), order 1, 2 or 3: src/operators/BSOperator.cpp:40-66 (B-spline derivative) */
+mrx_oper *mrx_bs_create(const mrx_mra *mra, int order);
 /* Import operator trees built by the reference: per term the [depth][transl] node cache of
  * OperatorTree::setupOperNodeCache (src/trees/OperatorTree.cpp:200-238). max_transl[t][d] for d <
  * n_depth[t]; mats/norms hold, term after term, depth after depth, transl = -max..max, the node's four

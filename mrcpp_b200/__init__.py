@@ -238,6 +238,22 @@ class ABGVOperator(_Operator):
         super().__init__(mra, _lib.load().mrx_abgv_create(mra._h, float(a), float(b)))
 
 
+class PHOperator(_Operator):
+    """PHOperator<3>(MRA, order): src/operators/PHOperator.cpp:40-69"""
+
+    def __init__(self, mra, order):
+        super().__init__(mra, _lib.load().mrx_ph_create(mra._h, int(order)))
+        self.order = order
+
+
+class BSOperator(_Operator):
+    """BSOperator<3>(MRA, order): src/operators/BSOperator.cpp:40-66"""
+
+    def __init__(self, mra, order):
+        super().__init__(mra, _lib.load().mrx_bs_create(mra._h, int(order)))
+        self.order = order
+
+
 def poisson_kernel(epsilon, r_min, r_max):
     c = np.zeros(1000)
     e = np.zeros(1000)

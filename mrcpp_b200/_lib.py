@@ -69,6 +69,8 @@ SIGNATURES = {
     "mrx_helmholtz_create": (_P, [_P, _D, _D]),
     "mrx_convolution_create": (_P, [_P, _I, _PD, _PD, _D]),
     "mrx_abgv_create": (_P, [_P, _D, _D]),
+    "mrx_ph_create": (_P, [_P, _I]),
+    "mrx_bs_create": (_P, [_P, _I]),
     "mrx_oper_from_arrays": (_P, [_P, _I, _PI, _PI, _PD, _PD, _I, _I, _D]),
     "mrx_oper_destroy": (None, [_P]),
     "mrx_oper_n_terms": (_I, [_P]),

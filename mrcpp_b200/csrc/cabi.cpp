@@ -474,6 +474,16 @@ mrx_oper *mrx_abgv_create(const mrx_mra *mra, double a, double b) {
     o->op = build_abgv_operator(mra->m, a, b);
     return o;
 }
+mrx_oper *mrx_ph_create(const mrx_mra *mra, int order) {
+    auto *o = new mrx_oper;
+    o->op = build_ph_operator(mra->m, order);
+    return o;
+}
+mrx_oper *mrx_bs_create(const mrx_mra *mra, int order) {
+    auto *o = new mrx_oper;
+    o->op = build_bs_operator(mra->m, order);
+    return o;
+}
 mrx_oper *mrx_oper_from_arrays(const mrx_mra *mra, int n_terms, const int *n_depth, const int *max_transl, const double *mats,
                                const double *norms, int oper_root, int derivative_order, double build_prec) {
     auto *o = new mrx_oper;

@@ -65,6 +65,9 @@ struct CrossCorr {
     std::vector<double> L, R;
 };
 const CrossCorr &cross_corr(int k);
+/// S_{+1}, S_0, S_{-1} (three K x K row-major matrices) of the tabulated derivative operators: kind 4/5 = Holoborodko order
+/// 1/2 (PHCalculator.cpp:47-79), 6/7/8 = B-spline order 1/2/3 (BSCalculator.cpp:47-79)
+const std::vector<double> &derivative_table(int kind, int k);
 
 /// Gauss-Legendre points/weights on [0,1] (GaussQuadrature.cpp:157-193, QuadratureCache.cpp:41-45).
 struct Quadrature {
@@ -303,7 +306,11 @@ GaussExp<1> helmholtz_kernel(double mu, double epsilon, double r_min, double r_m
 Operator build_convolution_operator(const MRA<3> &mra, const GaussExp<1> &kernel, double k_prec, double o_prec);
 Operator build_poisson_operator(const MRA<3> &mra, double prec);                  // PoissonOperator.cpp:40-55
 Operator build_helmholtz_operator(const MRA<3> &mra, double mu, double prec);     // HelmholtzOperator.cpp:44-59
-Operator build_abgv_operator(const MRA<3> &mra, double a, double b);              // ABGVOperator.cpp:52-74
+Operator build_abgv_operator(const MRA<3> &mra, double a, double b);
+/// PHOperator<3>(mra, order) (PHOperator.cpp:40-69) / BSOperator<3>(mra, order) (BSOperator.cpp:40-66): bandwidth-1 derivative
+/// operators from tabulated matrices
+Operator build_ph_operator(const MRA<3> &mra, int order);
+Operator build_bs_operator(const MRA<3> &mra, int order);              // ABGVOperator.cpp:52-74
 
 double calc_min_distance(const MRA<3> &mra, double eps); // MultiResolutionAnalysis.h:65
 double calc_max_distance(const MRA<3> &mra);             // MultiResolutionAnalysis.cpp:208

@@ -354,6 +354,75 @@ Operator build_abgv_operator(const MRA<3> &mra, double a, double b) {
     return op;
 }
 
+// PHOperator / BSOperator: the operator nodes are three tabulated K x K matrices scaled by 2^(order (n + 1)), laid out by
+// PHCalculator::calcNode (PHCalculator.cpp:82-128) / BSCalculator::calcNode (BSCalculator.cpp:82-128, identical), compressed
+// in the node; tree built by the BandWidthAdaptor with bandwidth 1.
+static Operator build_tabulated_derivative(const MRA<3> &mra, int kind, int order, int oper_reach) {
+    const int oper_root = mra.rootScale;
+    const int bw = 1;
+    MRA<2> o_mra = operator_mra(mra, oper_root, oper_reach);
+    const int k = mra.order, K = k + 1;
+    const std::vector<double> &tab = derivative_table(kind, k);
+    const double *S_p1 = tab.data(), *S_0 = tab.data() + (size_t)K * K, *S_m1 = tab.data() + (size_t)2 * K * K;
+
+    Tree<2> o_tree(o_mra);
+    o_tree.operNorms = true;
+    o_tree.normPrec = MachineZero;
+    auto calc = [&](Tree<2> &t, int n) {
+        t.zeroCoefs(n);
+        const int np1 = t.nodes[n].scale + 1;
+        const int kp1_d = K * K;
+        const double two_np1 = std::pow(2.0, order * np1);
+        double *coefs = t.coef(n);
+        switch (t.nodes[n].l[1] - t.nodes[n].l[0]) {
+            case 1:
+                for (int idx = 0; idx < kp1_d; idx++) coefs[1 * kp1_d + idx] = two_np1 * S_p1[idx];
+                break;
+            case 0:
+                for (int idx = 0; idx < kp1_d; idx++) {
+                    coefs[0 * kp1_d + idx] = two_np1 * S_0[idx];
+                    coefs[1 * kp1_d + idx] = two_np1 * S_m1[idx];
+                    coefs[2 * kp1_d + idx] = two_np1 * S_p1[idx];
+                    coefs[3 * kp1_d + idx] = two_np1 * S_0[idx];
+                }
+                break;
+            case -1:
+                for (int idx = 0; idx < kp1_d; idx++) coefs[2 * kp1_d + idx] = two_np1 * S_m1[idx];
+                break;
+            default:
+                break;
+        }
+        t.mwTransformNode(n, Compression);
+        t.nodes[n].flags |= FlagHasCoefs;
+        t.calcNorms(n);
+    };
+    auto split = [bw](const Tree<2> &t, int n) {
+        int dl = std::abs(t.nodes[n].l[0] - t.nodes[n].l[1]);
+        return ((t.nodes[n].l[0] == 0) and (2 * dl <= bw)); // BandWidthAdaptor::splitNode (BandWidthAdaptor.h:46-51)
+    };
+    build_tree<2>(o_tree, calc, split, -1, false, false);
+    o_tree.calcSquareNorm();
+
+    Operator op;
+    op.k = k;
+    op.K = K;
+    op.operRoot = oper_root;
+    op.derivative = true;
+    op.order = order;
+    op.terms.push_back(flatten_oper_tree(o_tree));
+    return op;
+}
+
+Operator build_ph_operator(const MRA<3> &mra, int order) {
+    if (order < 1 || order > 2) MRX_ABORT("PHOperator: derivative order 1 or 2"); // PHCalculator.cpp:40-45
+    return build_tabulated_derivative(mra, 3 + order, order, /*oper_reach=*/-10);  // PHOperator.cpp:41
+}
+
+Operator build_bs_operator(const MRA<3> &mra, int order) {
+    if (order < 1 || order > 3) MRX_ABORT("BSOperator: derivative order 1, 2 or 3"); // BSCalculator.cpp:38-45
+    return build_tabulated_derivative(mra, 5 + order, order, /*oper_reach=*/1);    // BSOperator.cpp:41
+}
+
 // OperatorTree::calcBandWidth (OperatorTree.cpp:109-134) per term, then MWOperator::calcBandWidths
 // (MWOperator.cpp:78-108). prec < 0 means "use the operator's build precision".
 void Operator::calcBandWidths(double prec) {

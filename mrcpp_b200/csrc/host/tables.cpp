@@ -22,7 +22,7 @@ std::mutex g_mutex;
 
 struct RawTables {
     // kind -> order -> data
-    std::map<int, std::vector<double>> t[4];
+    std::map<int, std::vector<double>> t[9];
     bool loaded = false;
 };
 RawTables g_raw;
@@ -60,7 +60,7 @@ void load_raw() {
         if (std::fread(hdr, 4, 3, f) != 3) MRX_ABORT("truncated table file");
         std::vector<double> d(hdr[2]);
         if (std::fread(d.data(), 8, d.size(), f) != d.size()) MRX_ABORT("truncated table file");
-        if (hdr[0] < 0 || hdr[0] > 3) MRX_ABORT("bad table kind");
+        if (hdr[0] < 0 || hdr[0] > 8) MRX_ABORT("bad table kind");
         g_raw.t[hdr[0]][hdr[1]] = std::move(d);
     }
     std::fclose(f);
@@ -116,6 +116,16 @@ const FilterSet &filter_set(int k) {
     auto *p = fs.get();
     g_filters[k] = std::move(fs);
     return *p;
+}
+
+const std::vector<double> &derivative_table(int kind, int k) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    load_raw();
+    if (kind < 4 || kind > 8) MRX_ABORT("derivative_table: bad kind");
+    auto it = g_raw.t[kind].find(k);
+    if (it == g_raw.t[kind].end()) MRX_ABORT("Scaling order not supported");
+    if ((int)it->second.size() != 3 * (k + 1) * (k + 1)) MRX_ABORT("derivative_table: bad size");
+    return it->second;
 }
 
 const CrossCorr &cross_corr(int k) {

@@ -53,14 +53,29 @@ import os, struct, sys
 src, dst = sys.argv[1], sys.argv[2]
 os.makedirs(dst, exist_ok=True)
 names = {0: "I_H0_%d", 1: "I_G0_%d", 2: "I_c_left_%d", 3: "I_c_right_%d"}
+# tabulated derivative matrices: text files read sequentially from K = 2 up to the order asked for (PHCalculator.cpp:47-79)
+text = {4: "I_ph_deriv_1.txt", 5: "I_ph_deriv_2.txt", 6: "I_b-spline-deriv1.txt", 7: "I_b-spline-deriv2.txt", 8: "I_b-spline-deriv3.txt"}
+blocks = {kind: {} for kind in text}
 with open(src, "rb") as f:
     assert f.read(4) == b"MRXT"
     (n,) = struct.unpack("<i", f.read(4))
     for _ in range(n):
         kind, k, cnt = struct.unpack("<iii", f.read(12))
         data = f.read(8 * cnt)
+        if kind in text:
+            blocks[kind][k + 1] = struct.unpack("<%dd" % cnt, data)
+            continue
         with open(os.path.join(dst, names[kind] % k), "wb") as g:
             g.write(data)
+for kind, name in text.items():
+    with open(os.path.join(dst, name), "w") as g:
+        K = 2
+        while K in blocks[kind]:
+            g.write("%d\n" % K)
+            v = blocks[kind][K]
+            for i in range(3 * K):
+                g.write(" ".join("%.17e" % x for x in v[i * K:(i + 1) * K]) + " \n")
+            K += 1
 EOP
 rm -rf $OUT/include  # build-time symlinks into the reference tree: nothing that points outside the repo may travel
 echo "built $OUT/libmrcpp_ref.so $OUT/libref_driver.so $OUT/mwfilters"

@@ -121,6 +121,12 @@ void ref_divergence(void *out, void *oper, void **inp) {
     for (int d = 0; d < 3; d++) vec.push_back(std::make_tuple(1.0, &static_cast<RefTree *>(inp[d])->tree));
     divergence(static_cast<RefTree *>(out)->tree, *static_cast<DerivativeOperator<3> *>(oper), vec);
 }
+void *ref_ph_create(void *mra, int order) {
+    return static_cast<DerivativeOperator<3> *>(new PHOperator<3>(*static_cast<MultiResolutionAnalysis<3> *>(mra), order));
+}
+void *ref_bs_create(void *mra, int order) {
+    return static_cast<DerivativeOperator<3> *>(new BSOperator<3>(*static_cast<MultiResolutionAnalysis<3> *>(mra), order));
+}
 void ref_copy_grid(void *out, void *inp) { copy_grid(static_cast<RefTree *>(out)->tree, static_cast<RefTree *>(inp)->tree); }
 void ref_mw_transform(void *t, int type, int overwrite) { static_cast<RefTree *>(t)->tree.mwTransform(type, overwrite != 0); }
 

@@ -37,6 +37,9 @@ int main() {
     mrcpp::PoissonOperator P(MRA, 1.0e-5);
     mrcpp::HelmholtzOperator H(MRA, 1.0, 1.0e-5);
     mrcpp::ABGVOperator<D> Dx(MRA, 0.5, 0.5);
+    mrcpp::PHOperator<D> ph(MRA, 2);
+    mrcpp::BSOperator<D> bs(MRA, 3);
+    std::printf("ph_order %d\nbs_order %d\nph_terms %d\n", ph.getOrder(), bs.getOrder(), ph.size());
     std::printf("poisson_terms %d\nhelmholtz_terms %d\nhelmholtz_mu %.17g\nabgv_order %d\nbuild_prec %.17g\n", P.size(), H.size(), H.getMu(),
                 Dx.getOrder(), P.getBuildPrec());
 

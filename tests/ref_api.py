@@ -34,7 +34,7 @@ def lib():
             "ref_apply": (D, [D, P, P, P, I, I]), "ref_apply_derivative": (None, [P, P, P, I]), "ref_dot": (D, [P, P]),
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
-            "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
+            "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
             "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
@@ -115,6 +115,14 @@ def helmholtz(mra, mu, prec):
 
 def abgv(mra, a, b):
     return lib().ref_abgv_create(mra._h, float(a), float(b))
+
+
+def ph(mra, order):
+    return lib().ref_ph_create(mra._h, int(order))
+
+
+def bs(mra, order):
+    return lib().ref_bs_create(mra._h, int(order))
 
 
 def apply(prec, out, oper, inp, maxIter=-1, absPrec=False):

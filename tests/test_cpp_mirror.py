@@ -37,6 +37,7 @@ def test_host_api_matches_python_mirror(libs, bindir):
     mra = mw.MultiResolutionAnalysis(7, -4, (-1, -1, -1), (2, 2, 2), 25)
     assert kv["poisson_terms"] == mw.PoissonOperator(mra, 1e-5).size() == 73
     assert kv["helmholtz_terms"] == mw.HelmholtzOperator(mra, 1.0, 1e-5).size()
+    assert (kv["ph_order"], kv["bs_order"], kv["ph_terms"]) == (2, 3, 1)
     t = mw.FunctionTree(mra)
     mw.build_grid(t, f)
     assert kv["root_nodes"] == 8 and kv["grid_nodes"] == t.getNNodes() and kv["grid_end_nodes"] == t.getNEndNodes()

@@ -357,3 +357,34 @@ def test_evalf_matches_reference(libs):
         assert ot.evalf((17.0, 0.0, 0.0)) == 0.0 and ot.getNNodes() == rt.n_nodes()
     exact = np.array([sum(f.evalf(p) for f in funcs) for p in pts[:43]])
     assert np.abs(of.evalf(pts[:43], True) - exact).max() < 50 * prec * np.abs(exact).max()
+
+
+@needs_ref
+@pytest.mark.parametrize("family,order", [("ph", 1), ("ph", 2), ("bs", 1), ("bs", 2), ("bs", 3)])
+def test_ph_bs_derivative_matches_reference(libs, family, order):
+    """PHOperator / BSOperator (PHOperator.cpp:40-69, BSOperator.cpp:40-66; tabulated matrices of PHCalculator.cpp:47-128,
+    BSCalculator.cpp:47-128) through apply(out, D, inp, dir) in all directions, and for the first-order operators the
+    reference's own check: relative L2 error against the projected analytic derivative (tests/operators/derivative_operator.cpp)"""
+    mw, orc = libs
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 2, 9, box=2.0, lo=0.5, hi=1.5)
+    world = (k, -3, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    RD = ref.ph(rm, order) if family == "ph" else ref.bs(rm, order)
+    OD = mw.PHOperator(om, order) if family == "ph" else mw.BSOperator(om, order)
+    for d in range(3):
+        rg, og = ref.Tree(rm), mw.FunctionTree(om)
+        ref.apply_derivative(rg, RD, rf, d)
+        orc.apply_derivative(og, OD, of, d)
+        same_tree(rg.export(), og.to_arrays(), tol=1e-11)
+        if order == 1:
+            power = [0, 0, 0]
+            power[d] = 1
+            dfuncs = [mw.GaussFunc(f.beta, -2.0 * f.beta * f.coef, f.pos, tuple(power)) for f in funcs]
+            dt = mw.FunctionTree(om)
+            orc.project(prec, dt, expansion(mw, dfuncs))
+            gg, gd, dd = orc.dot(og, og), orc.dot(og, dt), orc.dot(dt, dt)
+            assert math.sqrt(abs(gg - 2 * gd + dd) / dd) < 1e-2

@@ -70,3 +70,18 @@ def test_gradient_and_divergence(gpu):
     orc.divergence(oc, D, [ca, cb, ca])
     assert_same_tree(og, oc, tol=1e-11)
     assert abs(ga.integrate() - ca.integrate()) <= 1e-13 and abs(og.integrate() - oc.integrate()) <= 1e-10
+
+
+@pytest.mark.parametrize("family,order", [("ph", 1), ("ph", 2), ("bs", 1), ("bs", 2), ("bs", 3)])
+def test_ph_bs_derivative(gpu, family, order):
+    """PHOperator / BSOperator (PHOperator.cpp:40-69, BSOperator.cpp:40-66) through apply(out, D, inp, dir): the device path
+    against the oracle (pinned against the real reference for the same operators in tests/test_reference_parity.py)"""
+    mw, orc = gpu
+    mra, ((ga, ca), _) = two_trees(mw, orc, 5, 1e-4)
+    D = mw.PHOperator(mra, order) if family == "ph" else mw.BSOperator(mra, order)
+    for d in range(3):
+        og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        sg = mw.apply(None, og, D, ga, dir=d)
+        sc = orc.apply_derivative(oc, D, ca, d)
+        assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
+        assert_same_tree(og, oc, tol=1e-11)
