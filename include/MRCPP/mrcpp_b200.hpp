@@ -584,13 +584,11 @@ template <int D, typename T> void apply(FunctionTree<D, T> &out, DerivativeOpera
     if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
     mrx_apply_derivative(out.handle(), oper.handle(), inp.handle(), dir, &b200::last_apply_stats());
 }
-/// mrcpp::add(prec, out, inp, maxIter): src/treebuilders/add.cpp:41-70. On the B200 path the sum is computed on the grid `out`
-/// enters with (prec < 0 or maxIter = 0, the form mrcpp::divergence uses); the adaptive form aborts.
+/// mrcpp::add(prec, out, inp, maxIter, absPrec): src/treebuilders/add.cpp:41-70, from the grid `out` enters with; prec < 0 or
+/// maxIter = 0: no refinement (the form mrcpp::divergence uses)
 template <int D, typename T>
 void add(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp, int maxIter = -1, bool absPrec = false, bool conjugate = false) {
-    (void)absPrec;
-    (void)conjugate;
-    if (prec >= 0.0 && maxIter != 0) MRCPP_B200_ABORT("adaptive add (prec > 0) is not on the B200 path: build_grid(out, inp) first, then add(-1.0, out, inp)");
+    (void)conjugate; // real trees
     std::vector<T> c;
     std::vector<mrx_tree *> h;
     for (auto &t : inp) {
@@ -598,7 +596,7 @@ void add(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp, in
         c.push_back(std::get<0>(t));
         h.push_back(std::get<1>(t)->handle());
     }
-    mrx_tree_add(out.handle(), (int)h.size(), c.data(), h.data());
+    mrx_tree_add_adaptive(prec, out.handle(), (int)h.size(), c.data(), h.data(), maxIter, absPrec ? 1 : 0);
 }
 template <int D, typename T>
 void add(double prec, FunctionTree<D, T> &out, T a, FunctionTree<D, T> &inp_a, T b, FunctionTree<D, T> &inp_b, int maxIter = -1, bool absPrec = false,

@@ -198,6 +198,10 @@ int mrx_tree_build_grid_from(mrx_tree *out, const mrx_tree *inp);
  * the grid `out` enters with, no refinement -- the form mrcpp::divergence uses (apply.cpp:527-528). Inputs coarser than the
  * grid contribute their generated (scaling-only) nodes, inputs finer than the grid are truncated, as in the reference. */
 int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp);
+/* add(prec, out, {(coefs[i], inp[i])}, max_iter, abs_prec) (add.cpp:41-70): the adaptive form -- starts from the grid `out`
+ * enters with (normally empty roots) and refines where the wavelet norm of the sum asks for it (TreeBuilder.cpp:38-86,
+ * WaveletAdaptor.h:51-54). prec < 0 or max_iter == 0: same as mrx_tree_add. */
+int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec);
 
 /* residency control for measurement: host->device / device->host copies of a tree's coefficients */
 int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */

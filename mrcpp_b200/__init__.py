@@ -377,14 +377,12 @@ def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None, comm=None):
     return st
 
 
-def add(prec, out, inp, maxIter=-1):
-    """mrcpp::add(prec, out, FunctionTreeVector) (src/treebuilders/add.cpp:41-70) on the grid `out` enters with: inp = list of
-    (coef, tree). Only the non-refining form (prec < 0 or maxIter = 0) is on the device path."""
-    if prec >= 0 and maxIter != 0:
-        raise NotImplementedError("adaptive add (prec > 0) is not on the B200 path: build the grid first and call add(-1, ...)")
+def add(prec, out, inp, maxIter=-1, absPrec=False):
+    """mrcpp::add(prec, out, FunctionTreeVector, maxIter, absPrec) (src/treebuilders/add.cpp:41-70) from the grid `out` enters
+    with: inp = list of (coef, tree). prec < 0 or maxIter = 0: no refinement."""
     c = np.ascontiguousarray([float(ci) for ci, _ in inp], dtype=np.float64)
     h = (C.c_void_p * len(inp))(*[t._h for _, t in inp])
-    _lib.load().mrx_tree_add(out._h, len(inp), _dp(c), h)
+    _lib.load().mrx_tree_add_adaptive(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0)
 
 
 def gradient(oper, inp):

@@ -323,7 +323,7 @@ double device_dot(mrx_tree &bra, mrx_tree &ket) {
 // have no wavelet part), its root scaling blocks the sums of the root scaling blocks, and every other scaling block follows
 // from those by reconstruction -- one TopDown(+=) pass over the zero-initialised scaling blocks. That is what the reference's
 // per-end-node sum followed by BottomUp produces (its branch nodes are compress(children) = the same (s, w) sums).
-void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp) {
+void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec) {
     require_device("device_add");
     Tree<3> &h = out.host;
     cudaStream_t st = stream();
@@ -363,6 +363,90 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp) {
     out.devValid = true;
     out.hostCoefsValid = false;
     device_mw_transform(out, MRX_TOP_DOWN, /*overwrite=*/false); // + norms of every node
+    // Refinement (prec > 0): the TreeBuilder loop (TreeBuilder.cpp:38-86) with the WaveletAdaptor (WaveletAdaptor.h:51-54), from
+    // the end nodes of the grid just computed. The (s, w) blocks of a new child are fixed by what is already there: its scaling
+    // block is the reconstruction of its parent (one transform launch over the split parents, which also zeroes the child's
+    // wavelet blocks), its wavelet blocks the sum of the wavelet blocks of the inputs that hold the node (axpy launches);
+    // norms of the new nodes come back to the host, which takes the split decisions like the projection does.
+    if (prec > 0.0 && maxIter != 0) {
+        const double *filt = device_filters(h.k);
+        const int maxScale = h.mra.maxScale();
+        h.allocCoefs = false; // new nodes are born in HBM
+        std::vector<int> work, next, parentPairs, slotPairs;
+        h.endNodeTable(work);
+        DevBuf<int> dParents, dSlots, dAxpy;
+        DevBuf<double> dNormsW;
+        std::vector<double> nrm;
+        double sNorm = 0.0, wNorm = 0.0;
+        int iter = 0;
+        while (!work.empty()) {
+            if (iter == 0) {
+                sNorm = 0.0;
+                for (int s : work) sNorm += h.scalingNorm(s);
+            }
+            for (int s : work) wNorm += h.waveletNorm(s);
+            if (sNorm < 0.0 or wNorm < 0.0) h.squareNorm = -1.0;
+            else h.squareNorm = sNorm + wNorm;
+            next.clear();
+            parentPairs.clear();
+            if (iter >= maxIter and maxIter >= 0) work.clear();
+            for (int s : work) {
+                if (h.isBranch(s)) continue;
+                if (h.nodes[s].scale + 2 > maxScale) continue;
+                if (split_check(h, s, prec, 1.0, absPrec)) {
+                    const int c0 = h.createChildren(s, false);
+                    parentPairs.push_back(s);
+                    parentPairs.push_back(c0);
+                    for (int k = 0; k < 8; k++) next.push_back(c0 + k);
+                }
+            }
+            if (next.empty()) break;
+            const int nW = (int)next.size(), nP = (int)parentPairs.size() / 2;
+            out.dev.coefs.reserve((size_t)h.nReal * h.ncoef, true, st);
+            out.dev.norms.reserve((size_t)h.nReal * 8, true, st);
+            dParents.reserve(parentPairs.size(), false, st);
+            MRX_CUDA(cudaMemcpyAsync(dParents.p, parentPairs.data(), sizeof(int) * parentPairs.size(), cudaMemcpyHostToDevice, st));
+            launch_transform(true, true, out.dev.coefs.p, dParents.p, nP, h.K, filt, st);
+            for (int i = 0; i < n; i++) {
+                const Tree<3> &b = inp[i]->host;
+                slotPairs.clear();
+                for (int s : next) {
+                    const int m = b.findNode(h.nodes[s].scale, h.nodes[s].l);
+                    if (m >= 0 && m < b.nReal) {
+                        slotPairs.push_back(s);
+                        slotPairs.push_back(m);
+                    }
+                }
+                if (slotPairs.empty()) continue;
+                MRX_CUDA(cudaStreamSynchronize(st)); // dAxpy and slotPairs are reused per input
+                dAxpy.reserve(slotPairs.size(), false, st);
+                MRX_CUDA(cudaMemcpyAsync(dAxpy.p, slotPairs.data(), sizeof(int) * slotPairs.size(), cudaMemcpyHostToDevice, st));
+                launch_axpy_nodes(out.dev.coefs.p, inp[i]->dev.coefs.p, dAxpy.p, (int)slotPairs.size() / 2, /*nRoots=*/0, h.Kd, c[i], st);
+            }
+            dSlots.reserve(nW, false, st);
+            dNormsW.reserve((size_t)nW * 8, false, st);
+            MRX_CUDA(cudaMemcpyAsync(dSlots.p, next.data(), sizeof(int) * nW, cudaMemcpyHostToDevice, st));
+            launch_norms(out.dev.coefs.p, out.dev.norms.p, dSlots.p, nW, h.Kd, st, dNormsW.p);
+            nrm.resize((size_t)nW * 8);
+            MRX_CUDA(cudaMemcpyAsync(nrm.data(), dNormsW.p, sizeof(double) * nrm.size(), cudaMemcpyDeviceToHost, st));
+            MRX_CUDA(cudaStreamSynchronize(st));
+            for (int i = 0; i < nW; i++) {
+                const int s = next[i];
+                double sq = 0.0;
+                for (int k = 0; k < 8; k++) {
+                    const double v = nrm[(size_t)i * 8 + k];
+                    h.cnorm[(size_t)s * 8 + k] = v;
+                    sq += v * v;
+                }
+                h.sqn[s] = sq;
+                h.nodes[s].flags |= FlagHasCoefs;
+            }
+            work.swap(next);
+            iter++;
+        }
+        out.dev.nNodes = h.nReal;
+        out.dev.topoNodes = -1;
+    }
     h.calcSquareNorm();
 }
 

@@ -123,7 +123,8 @@ void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsBy
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
 double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
-void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp); // add on the grid of `out` (add.cpp:41-70)
+/// add(prec, out, {(c_i, inp_i)}, maxIter, absPrec) from the grid of `out` (add.cpp:41-70); prec < 0 or maxIter = 0: no refinement
+void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec = -1.0, int maxIter = 0, bool absPrec = false);
 void oper_upload(mrx_oper &o);
 
 // project.cu

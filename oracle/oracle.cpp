@@ -670,28 +670,53 @@ void apply_derivative(Tree<3> &out, Operator &oper, Tree<3> &inp, int dir, Apply
     if (stats) *stats = st;
 }
 
-// add(prec < 0 | maxIter = 0, out, inp) on the grid `out` enters with (src/treebuilders/add.cpp:41-70): TreeBuilder runs the
-// AdditionCalculator (AdditionCalculator.h:42-66) over the END nodes of the grid (TreeCalculator.h:37) -- coefficients of
-// the input node at the same index, generated through getNode where the input tree is coarser -- then BottomUp, square norm
-// and cleanup of the generated nodes.
-void add(Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp) {
+// add(prec, out, inp, maxIter, absPrec) (src/treebuilders/add.cpp:41-70): TreeBuilder::build (TreeBuilder.cpp:38-86) runs the
+// AdditionCalculator (AdditionCalculator.h:42-66) over the END nodes of the grid `out` enters with (TreeCalculator.h:37) --
+// coefficients of the input node at the same index, generated through getNode where the input tree is coarser -- and the
+// WaveletAdaptor refines where the wavelet norm of the sum asks for it (prec < 0 or maxIter = 0: no refinement); then
+// BottomUp, square norm and cleanup of the generated nodes.
+void add(double prec, Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp, int maxIter, bool absPrec) {
     const FilterSet &fs = filter_set(out.k);
     for (Tree<3> *t : inp)
         if (!(t->mra == out.mra)) MRX_ABORT("Incompatible MRA");
+    const int maxScale = out.mra.maxScale();
     std::vector<int> work;
     out.endNodeTable(work);
-    for (int n : work) {
-        double *o = out.coef(n);
-        std::memset(o, 0, sizeof(double) * out.ncoef);
-        for (size_t i = 0; i < inp.size(); i++) {
-            Tree<3> &t = *inp[i];
-            const int m = get_node_gen(t, fs, out.nodes[n].scale, out.nodes[n].l, nullptr);
-            const double *x = t.coef(m);
-            const int nc = t.isGen(m) ? t.Kd : t.ncoef; // generated nodes hold the scaling block only (MWNode.cpp:644)
-            for (int j = 0; j < nc; j++) o[j] += c[i] * x[j];
+    double sNorm = 0.0, wNorm = 0.0;
+    int iter = 0;
+    while (!work.empty()) {
+        for (int n : work) {
+            double *o = out.coef(n);
+            std::memset(o, 0, sizeof(double) * out.ncoef);
+            for (size_t i = 0; i < inp.size(); i++) {
+                Tree<3> &t = *inp[i];
+                const int m = get_node_gen(t, fs, out.nodes[n].scale, out.nodes[n].l, nullptr);
+                const double *x = t.coef(m);
+                const int nc = t.isGen(m) ? t.Kd : t.ncoef; // generated nodes hold the scaling block only (MWNode.cpp:644)
+                for (int j = 0; j < nc; j++) o[j] += c[i] * x[j];
+            }
+            out.nodes[n].flags |= FlagHasCoefs;
+            calc_norms(out, n);
         }
-        out.nodes[n].flags |= FlagHasCoefs;
-        calc_norms(out, n);
+        if (iter == 0) {
+            sNorm = 0.0;
+            for (int n : work) sNorm += out.scalingNorm(n);
+        }
+        for (int n : work) wNorm += out.waveletNorm(n);
+        if (sNorm < 0.0 or wNorm < 0.0) out.squareNorm = -1.0;
+        else out.squareNorm = sNorm + wNorm;
+        std::vector<int> next;
+        if (iter >= maxIter and maxIter >= 0) work.clear();
+        for (int n : work) {
+            if (out.isBranch(n)) continue;
+            if (out.nodes[n].scale + 2 > maxScale) continue;
+            if (split_check(out, n, prec, 1.0, absPrec)) {
+                const int c0 = out.createChildren(n, false);
+                for (int k = 0; k < 8; k++) next.push_back(c0 + k);
+            }
+        }
+        work.swap(next);
+        iter++;
     }
     mw_transform_up(out);
     calc_square_norm(out);
@@ -768,10 +793,10 @@ void orc_mw_transform_down(void *tree, int overwrite) { orc::mw_transform_down(*
 void orc_mw_transform_up(void *tree) { orc::mw_transform_up(*static_cast<Tree<3> *>(tree)); }
 void orc_calc_square_norm(void *tree) { orc::calc_square_norm(*static_cast<Tree<3> *>(tree)); }
 double orc_dot(void *bra, void *ket) { return orc::dot(*static_cast<Tree<3> *>(bra), *static_cast<Tree<3> *>(ket)); }
-void orc_add(void *out, int n, const double *coefs, void **inp) {
+void orc_add(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
     std::vector<double> c(coefs, coefs + n);
     std::vector<Tree<3> *> t(n);
     for (int i = 0; i < n; i++) t[i] = static_cast<Tree<3> *>(inp[i]);
-    orc::add(*static_cast<Tree<3> *>(out), c, t);
+    orc::add(prec, *static_cast<Tree<3> *>(out), c, t, maxIter, absPrec != 0);
 }
 }

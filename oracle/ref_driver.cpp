@@ -115,6 +115,12 @@ void ref_add(void *out, int n, const double *coefs, void **inp) {
     for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
     add(-1.0, static_cast<RefTree *>(out)->tree, vec, 0);
 }
+/// add(prec, out, {(c_i, inp_i)}, maxIter, absPrec): the adaptive form
+void ref_add_adaptive(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
+    FunctionTreeVector<3, double> vec;
+    for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
+    add(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0);
+}
 /// divergence(out, oper, {inp_x, inp_y, inp_z}) (src/treebuilders/apply.cpp:514-530)
 void ref_divergence(void *out, void *oper, void **inp) {
     FunctionTreeVector<3, double> vec;

@@ -143,6 +143,32 @@ static void divergence_case() {
                 std::sqrt(err_tree.getSquareNorm() / ana_tree.getSquareNorm()));
 }
 
+static void addition_case() {
+    // adaptive sum of three projected Gaussians, g = f_1 - 2 f_2 + 3 f_3 (the case of the reference's examples/addition.cpp)
+    const int order = 5;
+    const double prec = 1.0e-4;
+    mrcpp::BoundingBox<D> world(-4, std::array<int, D>{-1, -1, -1}, std::array<int, D>{2, 2, 2});
+    mrcpp::MultiResolutionAnalysis<D> MRA(world, mrcpp::InterpolatingBasis(order), 25);
+    const double beta = 20.0, alpha = std::pow(beta / mrcpp::pi, 1.5);
+    mrcpp::GaussFunc<D> f1(beta, alpha, mrcpp::Coord<D>{0.0, 0.0, 0.1}), f2(beta, alpha, mrcpp::Coord<D>{0.0, 0.0, -0.1}),
+        f3(beta, alpha, mrcpp::Coord<D>{0.0, 0.0, 0.3});
+    mrcpp::FunctionTree<D> t1(MRA), t2(MRA), t3(MRA), g(MRA);
+    mrcpp::project(prec, t1, f1);
+    mrcpp::project(prec, t2, f2);
+    mrcpp::project(prec, t3, f3);
+    mrcpp::FunctionTreeVector<D> vec;
+    vec.push_back(std::make_tuple(1.0, &t1));
+    vec.push_back(std::make_tuple(-2.0, &t2));
+    vec.push_back(std::make_tuple(3.0, &t3));
+    mrcpp::add(prec, g, vec);
+    const mrcpp::Coord<D> r{0.1, -0.05, 0.2};
+    const double ana = f1.evalf(r) - 2.0 * f2.evalf(r) + 3.0 * f3.evalf(r);
+    std::printf("addition_nodes %d\naddition_integral %.17g\naddition_sqnorm %.17g\naddition_point_rel_err %.17g\n", g.getNNodes(), g.integrate(),
+                g.getSquareNorm(), std::abs(g.evalf_precise(r) - ana) / std::abs(ana));
+    std::printf("addition_overlap_1 %.17g\naddition_overlap_expected %.17g\n", mrcpp::dot(g, t1),
+                mrcpp::dot(t1, t1) - 2.0 * mrcpp::dot(t2, t1) + 3.0 * mrcpp::dot(t3, t1));
+}
+
 int main(int argc, char **argv) {
     mrcpp::Printer::init(argc > 1 ? std::atoi(argv[1]) : -1);
     mrcpp::print::environment(0);
@@ -150,6 +176,7 @@ int main(int argc, char **argv) {
     helmholtz_case();
     derivative_case();
     divergence_case();
+    addition_case();
     std::printf("done 1\n");
     return 0;
 }

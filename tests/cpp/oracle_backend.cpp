@@ -28,7 +28,7 @@ struct Oracle {
     void (*sqnorm)(void *);
     double (*dot)(void *, void *);
     void (*set_tables)(const char *);
-    void (*add)(void *, int, const double *, void **);
+    void (*add)(double, void *, int, const double *, void **, int, int);
 };
 Oracle &oracle() {
     static Oracle o = [] {
@@ -109,12 +109,15 @@ int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, 
     }
     return 0;
 }
-int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {
+int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {
     std::vector<void *> h(n);
     for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
-    oracle().add(mrx_tree_host_handle(out), n, coefs, h.data());
+    oracle().add(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec);
     mrx_tree_host_modified(out);
     return 0;
+}
+int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {
+    return mrx_tree_add_adaptive(-1.0, out, n, coefs, inp, 0, 0);
 }
 double mrx_dot(mrx_tree *bra, mrx_tree *ket) { return oracle().dot(mrx_tree_host_handle(bra), mrx_tree_host_handle(ket)); }
 int mrx_tree_rescale(mrx_tree *tree, double c) {

@@ -37,7 +37,7 @@ def lib():
         o.orc_calc_square_norm.argtypes = [C.c_void_p]
         o.orc_dot.argtypes = [C.c_void_p, C.c_void_p]
         o.orc_dot.restype = C.c_double
-        o.orc_add.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
+        o.orc_add.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int]
         o.orc_set_table_path(_plib.TABLES.encode())
         _o = o
     return _o
@@ -97,13 +97,14 @@ def dot(bra, ket):
     return lib().orc_dot(_th(bra), _th(ket))
 
 
-def add(out, coefs, trees):
-    """add(-1.0, out, {(c_i, tree_i)}, 0) on the grid `out` enters with (src/treebuilders/add.cpp:41-70)"""
+def add(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False):
+    """add(prec, out, {(c_i, tree_i)}, maxIter, absPrec) from the grid `out` enters with (src/treebuilders/add.cpp:41-70);
+    prec < 0: no refinement"""
     for t in trees:
         t.sync_host()
     c = (C.c_double * len(trees))(*[float(x) for x in coefs])
     h = (C.c_void_p * len(trees))(*[_th(t) for t in trees])
-    lib().orc_add(_th(out), len(trees), c, h)
+    lib().orc_add(float(prec), _th(out), len(trees), c, h, int(maxIter), 1 if absPrec else 0)
     _modified(out)
 
 

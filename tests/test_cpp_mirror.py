@@ -111,3 +111,6 @@ def check_drop_in_values(kv):
     assert abs(kv["divergence_overlap"] + kv["divergence_grad_sqnorm"]) < 1e-9 * kv["divergence_grad_sqnorm"]
     assert abs(kv["divergence_grad_sqnorm"] - 3.0 * kv["derivative_0_sqnorm"]) < 1e-6
     assert kv["gradient_point_rel_err"] < 1e-3 and kv["function_point_rel_err"] < 1e-4  # derivative_operator.cpp:417-453
+    # adaptive add (examples/addition.cpp): integral 1 - 2 + 3, point value, linearity of the overlap
+    assert kv["addition_nodes"] > 8 and abs(kv["addition_integral"] - 2.0) < 1e-6 and kv["addition_point_rel_err"] < 1e-2
+    assert abs(kv["addition_overlap_1"] - kv["addition_overlap_expected"]) < 1e-3 * abs(kv["addition_overlap_expected"])

@@ -388,3 +388,29 @@ def test_ph_bs_derivative_matches_reference(libs, family, order):
             orc.project(prec, dt, expansion(mw, dfuncs))
             gg, gd, dd = orc.dot(og, og), orc.dot(og, dt), orc.dot(dt, dt)
             assert math.sqrt(abs(gg - 2 * gd + dd) / dd) < 1e-2
+
+
+@needs_ref
+@pytest.mark.parametrize("prec,max_iter,abs_prec,start", [(1e-4, -1, False, "roots"), (1e-3, -1, True, "roots"), (1e-4, 2, False, "roots"),
+                                                           (1e-5, -1, False, "first")])
+def test_adaptive_add_matches_reference(libs, prec, max_iter, abs_prec, start):
+    """add(prec, out, {(a, f), (b, g)}, maxIter, absPrec) (add.cpp:41-70), the adaptive form of examples/addition.cpp: from empty
+    roots, with an iteration limit, with absolute precision, and refining a pre-built grid"""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-5)
+    ro, oo = ref.Tree(rm), mw.FunctionTree(om)
+    if start == "first":
+        ref.build_grid_tree(ro, ra)
+        mw.build_grid(oo, oa)
+    ref.add(ro, [1.0, -2.0], [ra, rb], prec=prec, maxIter=max_iter, absPrec=abs_prec)
+    orc.add(oo, [1.0, -2.0], [oa, ob], prec=prec, maxIter=max_iter, absPrec=abs_prec)
+    same_tree(ro.export(), oo.to_arrays())
+    assert oo.getNNodes() > 8 and abs(ro.square_norm() - oo.getSquareNorm()) <= 1e-13 * ro.square_norm()
+    assert abs(ro.integrate() - oo.integrate()) <= 1e-13 * max(1.0, abs(ro.integrate()))
+    # the values the adaptive loop leaves are those of the sum on its final grid (what the device formulation relies on)
+    fixed = mw.FunctionTree(om)
+    mw.copy_grid(fixed, oo)
+    orc.add(fixed, [1.0, -2.0], [oa, ob])
+    A, B = oo.to_arrays(), fixed.to_arrays()
+    nrm = np.sqrt((A["coefs"] ** 2).sum(axis=1))
+    assert (np.abs(A["coefs"] - B["coefs"]).max(axis=1) / np.maximum(nrm, 1e-3 * nrm.max())).max() < 1e-13

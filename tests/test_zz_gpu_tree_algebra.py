@@ -85,3 +85,27 @@ def test_ph_bs_derivative(gpu, family, order):
         sc = orc.apply_derivative(oc, D, ca, d)
         assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
         assert_same_tree(og, oc, tol=1e-11)
+
+
+@pytest.mark.parametrize("k,prec,max_iter,abs_prec,start", [(5, 1e-4, -1, False, "roots"), (7, 1e-5, -1, False, "roots"), (5, 1e-3, -1, True, "roots"),
+                                                             (5, 1e-4, 2, False, "roots"), (5, 1e-5, -1, False, "first"), (4, 1e-4, -1, False, "roots")])
+def test_adaptive_add(gpu, k, prec, max_iter, abs_prec, start):
+    """add(prec, out, {(a, f), (b, g)}, maxIter, absPrec) (add.cpp:41-70), the adaptive form: node set, coefficients, norm"""
+    mw, orc = gpu
+    mra, ((ga, ca), (gb, cb)) = two_trees(mw, orc, k, 1e-5)
+    og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    if start == "first":
+        mw.build_grid(og, ga)
+        mw.build_grid(oc, ca)
+    mw.add(prec, og, [(1.0, ga), (-2.0, gb)], max_iter, abs_prec)
+    orc.add(oc, [1.0, -2.0], [ca, cb], prec=prec, maxIter=max_iter, absPrec=abs_prec)
+    assert og.getNNodes() > 8
+    assert_same_tree(og, oc)
+    assert abs(og.getSquareNorm() - oc.getSquareNorm()) <= 1e-12 * oc.getSquareNorm()
+    # the sum is usable as an apply input like any other tree
+    P = mw.PoissonOperator(mra, 1e-3)
+    vg, vc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    sg = mw.apply(1e-3, vg, P, og)
+    sc = orc.apply(1e-3, vc, P, oc)
+    assert sg.f_applied == sc.fApplied
+    assert_same_tree(vg, vc)
