@@ -8,6 +8,7 @@
 //   tree_utils::mw_transform[_back]         src/utils/tree_utils.cpp:113-301
 //   mrcpp::apply (DerivativeOperator)       src/treebuilders/apply.cpp:379-412
 //   DerivativeCalculator                    src/treebuilders/DerivativeCalculator.cpp:115-275
+//   mrcpp::add + AdditionCalculator         src/treebuilders/add.cpp:41-70, AdditionCalculator.h:42-66
 // Same loop structure, same thresholds, same summation order for the norms that feed thresholds.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library; the product (mrcpp_b200/) never does.
@@ -16,7 +17,7 @@
 // (Eigen 3.4.0 is an un-vendored dependency and absent here, so the dense products go through the stand-in under
 // oracle/eigen_shim; everything else is the reference's code) and tests/test_reference_parity.py requires identical node
 // sets, equal separation ranks and coefficients within 1e-12 of the node norm (observed 1e-15) for Poisson / Helmholtz /
-// derivative applies and the projections feeding them; (2) against the reference's own known-answer tests
+// derivative (ABGV, PH, BS) applies, add (fixed grid and adaptive), divergence and the projections feeding them; (2) against the reference's own known-answer tests
 // (tests/test_oracle_kats.py): Poisson/Helmholtz kernel sizes and point values, filter orthonormality, Coulomb
 // self-energy of a Gaussian, hydrogen 1s fixed point, identity convolution, band-width monotonicity, derivative L2 error,
 // projected-Gaussian integral/norm.
