@@ -579,6 +579,39 @@ void apply(double prec, FunctionTree<D, T> &out, ConvolutionOperator<D> &oper, F
     if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
     mrx_apply(prec, out.handle(), oper.handle(), inp.handle(), maxIter, absPrec ? 1 : 0, &b200::last_apply_stats());
 }
+namespace b200 {
+/// One rank of a multi-GPU job (one process per GPU; the library creates the NCCL communicator). Rank 0 obtains the 128-byte
+/// id with Comm::unique_id(), the host program ships it to every rank (MPI_Bcast in an MRCPP/MPI program), every rank
+/// constructs its Comm. The reference has no equivalent inside one apply: it distributes whole trees over MPI ranks.
+class Comm final {
+public:
+    static std::array<char, 128> unique_id() {
+        std::array<char, 128> id{};
+        mrx_comm_unique_id(id.data());
+        return id;
+    }
+    Comm(int rank, int world, const std::array<char, 128> &id)
+            : h(mrx_comm_create(rank, world, id.data())) {}
+    ~Comm() { mrx_comm_destroy(h); }
+    Comm(const Comm &) = delete;
+    Comm &operator=(const Comm &) = delete;
+    int rank() const { return mrx_comm_rank(h); }
+    int size() const { return mrx_comm_size(h); }
+    const mrx_comm *handle() const { return h; }
+
+private:
+    mrx_comm *h;
+};
+} // namespace b200
+
+/// mrcpp::apply sharded over the GPUs of `comm` (collective: every rank calls it with identical arguments and ends with the
+/// complete, bit-identical output tree)
+template <int D, typename T>
+void apply(double prec, FunctionTree<D, T> &out, ConvolutionOperator<D> &oper, FunctionTree<D, T> &inp, const b200::Comm &comm, int maxIter = -1,
+           bool absPrec = false) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_apply_sharded(prec, out.handle(), oper.handle(), inp.handle(), maxIter, absPrec ? 1 : 0, comm.handle(), &b200::last_apply_stats());
+}
 /// mrcpp::apply(out, DerivativeOperator, inp, dir): src/treebuilders/apply.cpp:379-412
 template <int D, typename T> void apply(FunctionTree<D, T> &out, DerivativeOperator<D> &oper, FunctionTree<D, T> &inp, int dir = -1) {
     if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");

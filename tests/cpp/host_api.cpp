@@ -55,6 +55,12 @@ int main() {
     copy.clear();
     std::printf("cleared_nodes %d\n", copy.getNNodes());
 
+    // the sharded form of apply and its communicator wrapper are part of the mirror (instantiated here, run on multi-GPU boxes)
+    using ShardedApply = void (*)(double, mrcpp::FunctionTree<D> &, mrcpp::ConvolutionOperator<D> &, mrcpp::FunctionTree<D> &,
+                                  const mrcpp::b200::Comm &, int, bool);
+    ShardedApply sharded = &mrcpp::apply<D, double>;
+    std::printf("sharded_apply_present %d\n", sharded != nullptr ? 1 : 0);
+
     timer.stop();
     mrcpp::print::value(0, "elapsed", timer.elapsed(), "(sec)");
     mrcpp::print::tree(0, "grid", tree, timer);
