@@ -21,7 +21,7 @@
 //   build_grid, copy_grid, clear_grid   src/treebuilders/grid.h:35-43
 //   project                      src/treebuilders/project.h:33-34
 //   apply (convolution, derivative), gradient, divergence   src/treebuilders/apply.h:41,49,51,55
-//   add (on a given grid)        src/treebuilders/add.h
+//   add, multiply, square        src/treebuilders/add.h, multiply.h
 //   FunctionTreeVector           src/trees/FunctionTreeVector.h
 //   dot                          src/treebuilders/multiply.h
 //   Printer, print::*, Timer     src/utils/Printer.h:61-133, src/utils/Timer.h:42-50
@@ -639,6 +639,37 @@ void add(double prec, FunctionTree<D, T> &out, T a, FunctionTree<D, T> &inp_a, T
     v.push_back(std::make_tuple(b, &inp_b));
     add(prec, out, v, maxIter, absPrec, conjugate);
 }
+/// mrcpp::multiply(prec, out, inp, maxIter, absPrec, useMaxNorms, conjugate): src/treebuilders/multiply.cpp:104-136
+template <int D, typename T>
+void multiply(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp, int maxIter = -1, bool absPrec = false, bool useMaxNorms = false,
+              bool conjugate = false) {
+    (void)conjugate; // real trees
+    if (useMaxNorms) MRCPP_B200_ABORT("multiply: the MultiplicationAdaptor (useMaxNorms) is not on the B200 path");
+    std::vector<T> c;
+    std::vector<mrx_tree *> h;
+    for (auto &t : inp) {
+        if (out.getMRA() != std::get<1>(t)->getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+        c.push_back(std::get<0>(t));
+        h.push_back(std::get<1>(t)->handle());
+    }
+    mrx_tree_multiply(prec, out.handle(), (int)h.size(), c.data(), h.data(), maxIter, absPrec ? 1 : 0);
+}
+template <int D, typename T>
+void multiply(double prec, FunctionTree<D, T> &out, T c, FunctionTree<D, T> &inp_a, FunctionTree<D, T> &inp_b, int maxIter = -1, bool absPrec = false,
+              bool useMaxNorms = false, bool conjugate = false) {
+    FunctionTreeVector<D, T> v;
+    v.push_back(std::make_tuple(c, &inp_a));
+    v.push_back(std::make_tuple(T(1.0), &inp_b));
+    multiply(prec, out, v, maxIter, absPrec, useMaxNorms, conjugate);
+}
+/// mrcpp::square(prec, out, inp): src/treebuilders/multiply.cpp (out = inp * inp)
+template <int D, typename T> void square(double prec, FunctionTree<D, T> &out, FunctionTree<D, T> &inp, int maxIter = -1, bool absPrec = false) {
+    FunctionTreeVector<D, T> v;
+    v.push_back(std::make_tuple(T(1.0), &inp));
+    v.push_back(std::make_tuple(T(1.0), &inp));
+    multiply(prec, out, v, maxIter, absPrec);
+}
+
 /// mrcpp::gradient(oper, inp): src/treebuilders/apply.cpp:444-452 (the caller owns the trees: clear(vec, true))
 template <int D, typename T> FunctionTreeVector<D, T> gradient(DerivativeOperator<D> &oper, FunctionTree<D, T> &inp) {
     FunctionTreeVector<D, T> out;

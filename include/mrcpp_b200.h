@@ -203,6 +203,12 @@ int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp
  * WaveletAdaptor.h:51-54). prec < 0 or max_iter == 0: same as mrx_tree_add. */
 int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec);
 
+/* multiply(prec, out, {(coefs[i], inp[i])}, max_iter, abs_prec) (src/treebuilders/multiply.cpp:104-136 with
+ * MultiplicationCalculator.h:43-72 and the WaveletAdaptor, i.e. useMaxNorms = false): point-wise product of the inputs from the
+ * grid `out` enters with (normally empty roots), refined where the wavelet norm of the product asks for it; prec < 0 or
+ * max_iter == 0: no refinement. */
+int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec);
+
 /* residency control for measurement: host->device / device->host copies of a tree's coefficients */
 int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */
 int mrx_tree_sync_host(mrx_tree *tree);   /* download if the device copy is newer                    */

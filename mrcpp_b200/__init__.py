@@ -385,6 +385,14 @@ def add(prec, out, inp, maxIter=-1, absPrec=False):
     _lib.load().mrx_tree_add_adaptive(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0)
 
 
+def multiply(prec, out, inp, maxIter=-1, absPrec=False):
+    """mrcpp::multiply(prec, out, FunctionTreeVector, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136): inp = list of
+    (coef, tree); prec < 0 or maxIter = 0: no refinement of the grid `out` enters with"""
+    c = np.ascontiguousarray([float(ci) for ci, _ in inp], dtype=np.float64)
+    h = (C.c_void_p * len(inp))(*[t._h for _, t in inp])
+    _lib.load().mrx_tree_multiply(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0)
+
+
 def gradient(oper, inp):
     """mrcpp::gradient(D, f) (src/treebuilders/apply.cpp:444-452): [(1.0, df/dx), (1.0, df/dy), (1.0, df/dz)]"""
     out = []

@@ -635,6 +635,16 @@ int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs
     device_add(*out, n, coefs, inp, prec, max_iter, abs_prec != 0);
     return 0;
 }
+int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {
+    require_device("mrx_tree_multiply");
+    if (n <= 0) MRX_ABORT("mrx_tree_multiply: empty input vector");
+    for (int i = 0; i < n; i++) {
+        if (!(out->host.mra == inp[i]->host.mra)) MRX_ABORT("Incompatible MRA");
+        if (inp[i] == out) MRX_ABORT("mrx_tree_multiply: output tree among the inputs");
+    }
+    device_multiply(*out, n, coefs, inp, prec, max_iter, abs_prec != 0);
+    return 0;
+}
 int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {
     return mrx_tree_add_adaptive(-1.0, out, n, coefs, inp, 0, 0);
 }

@@ -365,8 +365,7 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, dou
     device_mw_transform(out, MRX_TOP_DOWN, /*overwrite=*/false); // + norms of every node
     // Refinement (prec > 0): the TreeBuilder loop (TreeBuilder.cpp:38-86) with the WaveletAdaptor (WaveletAdaptor.h:51-54), from
     // the end nodes of the grid just computed. The (s, w) blocks of a new child are fixed by what is already there: its scaling
-    // block is the reconstruction of its parent (one transform launch over the split parents, which also zeroes the child's
-    // wavelet blocks), its wavelet blocks the sum of the wavelet blocks of the inputs that hold the node (axpy launches);
+    // block is the reconstruction of its parent (one transform launch over the split parents, into zeroed storage), its wavelet blocks the sum of the wavelet blocks of the inputs that hold the node (axpy launches);
     // norms of the new nodes come back to the host, which takes the split decisions like the projection does.
     if (prec > 0.0 && maxIter != 0) {
         const double *filt = device_filters(h.k);
@@ -404,9 +403,11 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, dou
             const int nW = (int)next.size(), nP = (int)parentPairs.size() / 2;
             out.dev.coefs.reserve((size_t)h.nReal * h.ncoef, true, st);
             out.dev.norms.reserve((size_t)h.nReal * 8, true, st);
+            // the new children are the last nW slots: zero them, then children.scaling += reconstruct(parent)
+            MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p + (size_t)(h.nReal - nW) * h.ncoef, 0, sizeof(double) * (size_t)nW * h.ncoef, st));
             dParents.reserve(parentPairs.size(), false, st);
             MRX_CUDA(cudaMemcpyAsync(dParents.p, parentPairs.data(), sizeof(int) * parentPairs.size(), cudaMemcpyHostToDevice, st));
-            launch_transform(true, true, out.dev.coefs.p, dParents.p, nP, h.K, filt, st);
+            launch_transform(true, false, out.dev.coefs.p, dParents.p, nP, h.K, filt, st);
             for (int i = 0; i < n; i++) {
                 const Tree<3> &b = inp[i]->host;
                 slotPairs.clear();
@@ -447,6 +448,218 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, dou
         out.dev.nNodes = h.nReal;
         out.dev.topoNodes = -1;
     }
+    h.calcSquareNorm();
+}
+
+// multiply(prec, out, {(c_i, inp_i)}, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136, MultiplicationCalculator.h:43-72,
+// WaveletAdaptor): per END node of the output grid the inputs' nodes at the same index are reconstructed, taken to function
+// values at the children's quadrature points and multiplied; the product returns through cvTransform(Backward) and
+// mwTransform(Compression). Built from the existing transform kernels and one element-wise kernel:
+//  * side stores X_i: every input represented on the OUTPUT grid ((s, w) per output node; wavelet blocks where the input holds
+//    the node, scaling blocks by TopDown(+=) -- the formulation of device_add, so nothing is generated), extended as the grid
+//    refines;
+//  * per chunk of work nodes: gather X_i(n) into a scratch "parent" slot, children.scaling += reconstruct(parent) into eight
+//    zeroed scratch child slots (the in-node Reconstruction), values_kernel accumulates c_i * value_i into the product scratch
+//    and finally applies the Backward map, BottomUp of the scratch children gives the compressed product node, which is
+//    copied into the node store.
+void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec) {
+    require_device("device_multiply");
+    Tree<3> &h = out.host;
+    cudaStream_t st = stream();
+    const int K = h.K, Kd = h.Kd, ncoef = h.ncoef;
+    const double *filt = device_filters(h.k);
+    const int maxScale = h.mra.maxScale();
+    for (int i = 0; i < n; i++)
+        if (!inp[i]->devValid) tree_upload(*inp[i]);
+    std::vector<double> hcv(K), hsw(K);
+    {
+        const Quadrature &q = quadrature(K);
+        for (int j = 0; j < K; j++) {
+            hcv[j] = std::sqrt(1.0 / q.weights[j]); // InterpolatingBasis::calcCVMaps (InterpolatingBasis.cpp:115-124)
+            hsw[j] = std::sqrt(q.weights[j]);
+        }
+    }
+    DevBuf<double> dcv, dsw;
+    dcv.reserve(K, false, st);
+    dsw.reserve(K, false, st);
+    MRX_CUDA(cudaMemcpyAsync(dcv.p, hcv.data(), sizeof(double) * K, cudaMemcpyHostToDevice, st));
+    MRX_CUDA(cudaMemcpyAsync(dsw.p, hsw.data(), sizeof(double) * K, cudaMemcpyHostToDevice, st));
+
+    // output node store and the side stores, all zero
+    out.dev.coefs.reserve((size_t)h.nReal * ncoef, false, st);
+    out.dev.norms.reserve((size_t)h.nReal * 8, false, st);
+    MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p, 0, sizeof(double) * (size_t)h.nReal * ncoef, st));
+    out.dev.nNodes = h.nReal;
+    out.dev.nGen = 0;
+    out.dev.topoNodes = -1;
+    out.dev.partial = false;
+    std::vector<DevBuf<double>> X(n);
+    DevBuf<int> dA, dB;
+    std::vector<int> hostPairs;
+    {
+        std::vector<int> levelOff, flat;
+        const int nPairs = build_level_pairs(h, levelOff, flat);
+        const int nLevels = (int)levelOff.size() - 1;
+        if (nPairs > 0) {
+            dB.reserve(flat.size(), false, st);
+            MRX_CUDA(cudaMemcpyAsync(dB.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
+        }
+        for (int i = 0; i < n; i++) {
+            const Tree<3> &b = inp[i]->host;
+            X[i].reserve((size_t)h.nReal * ncoef, false, st);
+            MRX_CUDA(cudaMemsetAsync(X[i].p, 0, sizeof(double) * (size_t)h.nReal * ncoef, st));
+            hostPairs.clear();
+            std::vector<std::pair<int, int>> stack;
+            for (int r = h.nRoots - 1; r >= 0; r--) stack.push_back({r, r});
+            while (!stack.empty()) {
+                auto pr = stack.back();
+                stack.pop_back();
+                hostPairs.push_back(pr.first);
+                hostPairs.push_back(pr.second);
+                const bool oB = h.isBranch(pr.first) && !h.isGen(h.nodes[pr.first].child0);
+                const bool iB = b.isBranch(pr.second) && !b.isGen(b.nodes[pr.second].child0);
+                if (oB && iB)
+                    for (int k = 7; k >= 0; k--) stack.push_back({h.nodes[pr.first].child0 + k, b.nodes[pr.second].child0 + k});
+            }
+            MRX_CUDA(cudaStreamSynchronize(st)); // dA / hostPairs are reused per input
+            dA.reserve(hostPairs.size(), false, st);
+            MRX_CUDA(cudaMemcpyAsync(dA.p, hostPairs.data(), sizeof(int) * hostPairs.size(), cudaMemcpyHostToDevice, st));
+            launch_axpy_nodes(X[i].p, inp[i]->dev.coefs.p, dA.p, (int)hostPairs.size() / 2, h.nRoots, Kd, 1.0, st);
+            for (int d = 0; d < nLevels && nPairs > 0; d++) {
+                const int cnt = levelOff[d + 1] - levelOff[d];
+                if (cnt > 0) launch_transform(true, false, X[i].p, dB.p + 2 * (size_t)levelOff[d], cnt, K, filt, st);
+            }
+        }
+        MRX_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // scratch: per chunk node one "parent" slot and eight "child" slots, for the current input (S) and for the product (P)
+    const size_t slotBytes = sizeof(double) * (size_t)ncoef;
+    const int chunkCap = (int)std::max<size_t>(64, std::min<size_t>(16384, ((size_t)768 << 20) / (9 * slotBytes)));
+    DevBuf<double> S, P, dNormsW;
+    DevBuf<int> dGather, dKids, dScale, dSlots, dParents;
+    std::vector<int> work, next, parentPairs, gather, kids, scales;
+    std::vector<double> nrm;
+    h.endNodeTable(work);
+    h.allocCoefs = false; // new nodes are born in HBM
+    double sNorm = 0.0, wNorm = 0.0;
+    int iter = 0;
+    while (!work.empty()) {
+        const int nW = (int)work.size();
+        for (int w0 = 0; w0 < nW; w0 += chunkCap) {
+            const int nC = std::min(chunkCap, nW - w0);
+            S.reserve((size_t)9 * nC * ncoef, false, st);
+            P.reserve((size_t)9 * nC * ncoef, false, st);
+            gather.resize((size_t)2 * nC);
+            kids.resize((size_t)2 * nC);
+            scales.resize(nC);
+            for (int j = 0; j < nC; j++) {
+                gather[2 * (size_t)j] = j;                // scratch parent slot j <- node store slot
+                gather[2 * (size_t)j + 1] = work[w0 + j];
+                kids[2 * (size_t)j] = j;                  // scratch children of parent j: slots nC + 8 j .. + 7
+                kids[2 * (size_t)j + 1] = nC + 8 * j;
+                scales[j] = h.nodes[work[w0 + j]].scale;
+            }
+            dGather.reserve(gather.size(), false, st);
+            dKids.reserve(kids.size(), false, st);
+            dScale.reserve(nC, false, st);
+            MRX_CUDA(cudaMemcpyAsync(dGather.p, gather.data(), sizeof(int) * gather.size(), cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(dKids.p, kids.data(), sizeof(int) * kids.size(), cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemcpyAsync(dScale.p, scales.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaMemsetAsync(P.p, 0, slotBytes * 9 * nC, st));
+            for (int i = 0; i < n; i++) {
+                MRX_CUDA(cudaMemsetAsync(S.p, 0, slotBytes * 9 * nC, st));
+                launch_axpy_nodes(S.p, X[i].p, dGather.p, nC, /*nRoots: scaling block of every node*/ 0x7fffffff, Kd, 1.0, st);
+                launch_transform(true, false, S.p, dKids.p, nC, K, filt, st); // in-node Reconstruction into the scratch children
+                launch_product_values(P.p, S.p, dScale.p, nC, K, dcv.p, c[i], i == 0 ? 0 : 1, st);
+            }
+            launch_product_values(P.p, nullptr, dScale.p, nC, K, dsw.p, 1.0, 2, st); // cvTransform(Backward)
+            launch_transform(false, true, P.p, dKids.p, nC, K, filt, st);            // in-node Compression: parent slot j
+            // compressed product nodes into the (zeroed) node store slots: gather list reversed
+            for (int j = 0; j < nC; j++) std::swap(gather[2 * (size_t)j], gather[2 * (size_t)j + 1]);
+            MRX_CUDA(cudaStreamSynchronize(st)); // dGather is still read by the launches above
+            MRX_CUDA(cudaMemcpyAsync(dGather.p, gather.data(), sizeof(int) * gather.size(), cudaMemcpyHostToDevice, st));
+            launch_axpy_nodes(out.dev.coefs.p, P.p, dGather.p, nC, 0x7fffffff, Kd, 1.0, st);
+            MRX_CUDA(cudaStreamSynchronize(st));
+        }
+        // norms of the work nodes -> host bookkeeping (TreeBuilder.cpp:56-66)
+        dSlots.reserve(nW, false, st);
+        dNormsW.reserve((size_t)nW * 8, false, st);
+        MRX_CUDA(cudaMemcpyAsync(dSlots.p, work.data(), sizeof(int) * nW, cudaMemcpyHostToDevice, st));
+        launch_norms(out.dev.coefs.p, out.dev.norms.p, dSlots.p, nW, Kd, st, dNormsW.p);
+        nrm.resize((size_t)nW * 8);
+        MRX_CUDA(cudaMemcpyAsync(nrm.data(), dNormsW.p, sizeof(double) * nrm.size(), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < nW; i++) {
+            const int s = work[i];
+            double sq = 0.0;
+            for (int k = 0; k < 8; k++) {
+                const double v = nrm[(size_t)i * 8 + k];
+                h.cnorm[(size_t)s * 8 + k] = v;
+                sq += v * v;
+            }
+            h.sqn[s] = sq;
+            h.nodes[s].flags |= FlagHasCoefs;
+        }
+        if (iter == 0) {
+            sNorm = 0.0;
+            for (int s : work) sNorm += h.scalingNorm(s);
+        }
+        for (int s : work) wNorm += h.waveletNorm(s);
+        if (sNorm < 0.0 or wNorm < 0.0) h.squareNorm = -1.0;
+        else h.squareNorm = sNorm + wNorm;
+        next.clear();
+        parentPairs.clear();
+        if (iter >= maxIter and maxIter >= 0) work.clear();
+        for (int s : work) {
+            if (h.isBranch(s)) continue;
+            if (h.nodes[s].scale + 2 > maxScale) continue;
+            if (split_check(h, s, prec, 1.0, absPrec)) {
+                const int c0 = h.createChildren(s, false);
+                parentPairs.push_back(s);
+                parentPairs.push_back(c0);
+                for (int k = 0; k < 8; k++) next.push_back(c0 + k);
+            }
+        }
+        if (!next.empty()) {
+            // grow the node store and the side stores; new children are the last slots: zero, then X_i(child).s += reconstruct(X_i(parent)),
+            // and the wavelet blocks of the children the input holds
+            const int nNew = (int)next.size(), nP = (int)parentPairs.size() / 2;
+            out.dev.coefs.reserve((size_t)h.nReal * ncoef, true, st);
+            out.dev.norms.reserve((size_t)h.nReal * 8, true, st);
+            MRX_CUDA(cudaMemsetAsync(out.dev.coefs.p + (size_t)(h.nReal - nNew) * ncoef, 0, slotBytes * nNew, st));
+            dParents.reserve(parentPairs.size(), false, st);
+            MRX_CUDA(cudaMemcpyAsync(dParents.p, parentPairs.data(), sizeof(int) * parentPairs.size(), cudaMemcpyHostToDevice, st));
+            for (int i = 0; i < n; i++) {
+                const Tree<3> &b = inp[i]->host;
+                X[i].reserve((size_t)h.nReal * ncoef, true, st);
+                MRX_CUDA(cudaMemsetAsync(X[i].p + (size_t)(h.nReal - nNew) * ncoef, 0, slotBytes * nNew, st));
+                launch_transform(true, false, X[i].p, dParents.p, nP, K, filt, st);
+                hostPairs.clear();
+                for (int s : next) {
+                    const int m = b.findNode(h.nodes[s].scale, h.nodes[s].l);
+                    if (m >= 0 && m < b.nReal) {
+                        hostPairs.push_back(s);
+                        hostPairs.push_back(m);
+                    }
+                }
+                if (hostPairs.empty()) continue;
+                MRX_CUDA(cudaStreamSynchronize(st)); // dA / hostPairs are reused per input
+                dA.reserve(hostPairs.size(), false, st);
+                MRX_CUDA(cudaMemcpyAsync(dA.p, hostPairs.data(), sizeof(int) * hostPairs.size(), cudaMemcpyHostToDevice, st));
+                launch_axpy_nodes(X[i].p, inp[i]->dev.coefs.p, dA.p, (int)hostPairs.size() / 2, /*nRoots=*/0, Kd, 1.0, st);
+            }
+            MRX_CUDA(cudaStreamSynchronize(st));
+            out.dev.nNodes = h.nReal;
+        }
+        work.swap(next);
+        iter++;
+    }
+    for (int s = 0; s < h.nReal; s++) h.nodes[s].flags |= FlagHasCoefs;
+    out.dev.nNodes = h.nReal;
+    out.devValid = true;
+    out.hostCoefsValid = false;
+    device_mw_transform(out, MRX_BOTTOM_UP, true); // branch nodes of the grid + norms of every node (multiply.cpp:122-123)
     h.calcSquareNorm();
 }
 

@@ -546,6 +546,29 @@ __global__ void __launch_bounds__(256) axpy_nodes_kernel(double *out, const doub
     for (int j = (o < nRoots ? 0 : Kd) + threadIdx.x; j < 8 * Kd; j += 256) po[j] = __dadd_rn(po[j], __dmul_rn(c, pi[j]));
 }
 
+// MultiplicationCalculator::calcNode's element-wise part (MultiplicationCalculator.h:43-72) on scratch nodes: node j of the chunk
+// has its eight reconstructed scaling blocks in block 0 of the scratch slots nC + 8 j + t (t = child). map = cvMap (Forward:
+// sqrt(1 / w), InterpolatingBasis.cpp:115-124) or vcMap (Backward: sqrt(w)), applied along x, y, z like MWNode::cvTransform
+// (MWNode.cpp:448-490), with the factor 2^(+-3 (n + 1) / 2) of the children's scale.
+//   mode 0: P  = c * forward(S)      mode 1: P *= c * forward(S)      mode 2: P = backward(P)
+__global__ void __launch_bounds__(256) product_values_kernel(double *P, const double *S, const int *scale, int nC, int K, const double *map,
+                                                             double c, int mode) {
+    const int j = blockIdx.x >> 3, t = blockIdx.x & 7;
+    const int Kd = K * K * K;
+    const size_t off = ((size_t)(nC + 8 * j + t) * 8) * Kd; // block 0 of the child slot
+    const int np1 = scale[j] + 1;
+    const double two_fac = mode == 2 ? sqrt(1.0 / exp2((double)(3 * np1))) : sqrt(exp2((double)(3 * np1)));
+    for (int q = threadIdx.x; q < Kd; q += 256) {
+        const int x = q % K, y = (q / K) % K, z = q / (K * K);
+        if (mode == 2) {
+            P[off + q] = two_fac * (((P[off + q] * map[x]) * map[y]) * map[z]);
+        } else {
+            const double v = c * (two_fac * (((S[off + q] * map[x]) * map[y]) * map[z]));
+            P[off + q] = mode == 0 ? v : P[off + q] * v;
+        }
+    }
+}
+
 size_t transform_smem(int K, int &padOn) {
     int K2 = K * K, Kd = K2 * K;
     padOn = 1;
@@ -676,6 +699,14 @@ void launch_dot(const double *a, const double *b, const int *pairs, double *res,
 void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t st) {
     if (np == 0) return;
     axpy_nodes_kernel<<<np, 256, 0, st>>>(out, in, pairs, nRoots, Kd, c);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_product_values(double *P, const double *S, const int *scale, int nC, int K, const double *map, double c, int mode,
+                           cudaStream_t st) {
+    if (nC == 0) return;
+    product_values_kernel<<<8 * nC, 256, 0, st>>>(P, S, scale, nC, K, map, c, mode);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

@@ -48,4 +48,9 @@ void launch_scale(double *x, size_t n, double c, cudaStream_t st);
 /// out node pairs[2 p] += c * in node pairs[2 p + 1] (wavelet blocks; scaling block only where the out node is a root)
 void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t st);
 
+/// element-wise part of the multiplication on scratch nodes (chunk of nC nodes; children of node j in slots nC + 8 j + t):
+/// mode 0: P = c * forward(S), mode 1: P *= c * forward(S), mode 2: P = backward(P); map = sqrt(1 / w) or sqrt(w) per index
+void launch_product_values(double *P, const double *S, const int *scale, int nC, int K, const double *map, double c, int mode,
+                           cudaStream_t st);
+
 } // namespace mrx

@@ -724,6 +724,87 @@ void add(double prec, Tree<3> &out, const std::vector<double> &c, const std::vec
     for (Tree<3> *t : inp) t->deleteGenerated();
 }
 
+// MWNode::cvTransform(Forward) for the interpolating basis (MWNode.cpp:448-490, InterpolatingBasis.cpp:115-124): coefficients
+// of the children's scaling functions -> function values at the children's quadrature points; scaling factor 1
+static void cv_forward(Tree<3> &t, int n) {
+    const Quadrature &q = quadrature(t.K);
+    std::vector<double> cv(t.K);
+    for (int j = 0; j < t.K; j++) cv[j] = std::sqrt(1.0 / q.weights[j]);
+    const int np1 = t.nodes[n].scale + 1;
+    const double two_fac = std::sqrt(std::pow(2.0, 3 * np1));
+    double *c = t.coef(n);
+    for (int b = 0; b < 8; b++)
+        for (int idx = 0; idx < t.Kd; idx++) {
+            double v = c[(size_t)b * t.Kd + idx];
+            int rem = idx;
+            for (int d = 0; d < 3; d++) {
+                v = v * cv[rem % t.K];
+                rem /= t.K;
+            }
+            c[(size_t)b * t.Kd + idx] = two_fac * v;
+        }
+}
+
+// multiply(prec, out, inp, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136, useMaxNorms = false): TreeBuilder::build with
+// the MultiplicationCalculator (MultiplicationCalculator.h:43-72) -- per END node of the output grid, every input node at the
+// same index (generated where the input is coarser) is reconstructed in the node and taken to function values at the
+// children's quadrature points, the values are multiplied (with the coefficients), and the product goes back through
+// cvTransform(Backward) and mwTransform(Compression) -- refined by the WaveletAdaptor; then BottomUp, square norm, cleanup.
+void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp, int maxIter, bool absPrec) {
+    const FilterSet &fs = filter_set(out.k);
+    for (Tree<3> *t : inp)
+        if (!(t->mra == out.mra)) MRX_ABORT("Incompatible MRA");
+    const int maxScale = out.mra.maxScale();
+    std::vector<int> work;
+    out.endNodeTable(work);
+    std::vector<double> acc(out.ncoef);
+    double sNorm = 0.0, wNorm = 0.0;
+    int iter = 0;
+    while (!work.empty()) {
+        for (int n : work) {
+            std::fill(acc.begin(), acc.end(), 1.0);
+            double *o = out.coef(n);
+            for (size_t i = 0; i < inp.size(); i++) {
+                Tree<3> &t = *inp[i];
+                const int m = get_node_gen(t, fs, out.nodes[n].scale, out.nodes[n].l, nullptr);
+                // copy of the input node (generated nodes hold the scaling block only), transformed in the output node's storage
+                std::memset(o, 0, sizeof(double) * out.ncoef);
+                std::memcpy(o, t.coef(m), sizeof(double) * (t.isGen(m) ? t.Kd : t.ncoef));
+                out.mwTransformNode(n, Reconstruction);
+                cv_forward(out, n);
+                for (int j = 0; j < out.ncoef; j++) acc[j] *= c[i] * o[j];
+            }
+            std::memcpy(o, acc.data(), sizeof(double) * out.ncoef);
+            out.cvTransformBackward(n);
+            out.mwTransformNode(n, Compression);
+            out.nodes[n].flags |= FlagHasCoefs;
+            calc_norms(out, n);
+        }
+        if (iter == 0) {
+            sNorm = 0.0;
+            for (int n : work) sNorm += out.scalingNorm(n);
+        }
+        for (int n : work) wNorm += out.waveletNorm(n);
+        if (sNorm < 0.0 or wNorm < 0.0) out.squareNorm = -1.0;
+        else out.squareNorm = sNorm + wNorm;
+        std::vector<int> next;
+        if (iter >= maxIter and maxIter >= 0) work.clear();
+        for (int n : work) {
+            if (out.isBranch(n)) continue;
+            if (out.nodes[n].scale + 2 > maxScale) continue;
+            if (split_check(out, n, prec, 1.0, absPrec)) {
+                const int c0 = out.createChildren(n, false);
+                for (int k = 0; k < 8; k++) next.push_back(c0 + k);
+            }
+        }
+        work.swap(next);
+        iter++;
+    }
+    mw_transform_up(out);
+    calc_square_norm(out);
+    for (Tree<3> *t : inp) t->deleteGenerated();
+}
+
 // <bra|ket> from compressed coefficients: scaling blocks of the roots + wavelet blocks of every node
 // present in both trees (mathematically equal to mrcpp::dot, multiply.cpp:286-318).
 double dot(const Tree<3> &bra, const Tree<3> &ket) {
@@ -794,6 +875,12 @@ void orc_mw_transform_down(void *tree, int overwrite) { orc::mw_transform_down(*
 void orc_mw_transform_up(void *tree) { orc::mw_transform_up(*static_cast<Tree<3> *>(tree)); }
 void orc_calc_square_norm(void *tree) { orc::calc_square_norm(*static_cast<Tree<3> *>(tree)); }
 double orc_dot(void *bra, void *ket) { return orc::dot(*static_cast<Tree<3> *>(bra), *static_cast<Tree<3> *>(ket)); }
+void orc_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
+    std::vector<double> c(coefs, coefs + n);
+    std::vector<Tree<3> *> t(n);
+    for (int i = 0; i < n; i++) t[i] = static_cast<Tree<3> *>(inp[i]);
+    orc::multiply(prec, *static_cast<Tree<3> *>(out), c, t, maxIter, absPrec != 0);
+}
 void orc_add(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
     std::vector<double> c(coefs, coefs + n);
     std::vector<Tree<3> *> t(n);

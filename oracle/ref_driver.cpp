@@ -15,6 +15,7 @@
 #include "treebuilders/add.h"
 #include "treebuilders/apply.h"
 #include "treebuilders/grid.h"
+#include "treebuilders/multiply.h"
 #include "treebuilders/project.h"
 #include "trees/FunctionTree.h"
 #include "trees/MWNode.h"
@@ -120,6 +121,12 @@ void ref_add_adaptive(double prec, void *out, int n, const double *coefs, void *
     FunctionTreeVector<3, double> vec;
     for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
     add(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0);
+}
+/// multiply(prec, out, {(c_i, inp_i)}, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136)
+void ref_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
+    FunctionTreeVector<3, double> vec;
+    for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
+    multiply(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0);
 }
 /// divergence(out, oper, {inp_x, inp_y, inp_z}) (src/treebuilders/apply.cpp:514-530)
 void ref_divergence(void *out, void *oper, void **inp) {

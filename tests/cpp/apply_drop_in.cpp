@@ -169,6 +169,42 @@ static void addition_case() {
                 mrcpp::dot(t1, t1) - 2.0 * mrcpp::dot(t2, t1) + 3.0 * mrcpp::dot(t3, t1));
 }
 
+static void multiplication_case() {
+    // h = f * g of two projected Gaussians against the analytic product Gaussian (the case of the reference's
+    // examples/multiplication.cpp): exponent 2 beta at the midpoint, prefactor alpha^2 exp(-beta |d|^2 / 2)
+    const int order = 5;
+    const double prec = 1.0e-4;
+    mrcpp::BoundingBox<D> world(-4, std::array<int, D>{-1, -1, -1}, std::array<int, D>{2, 2, 2});
+    mrcpp::MultiResolutionAnalysis<D> MRA(world, mrcpp::InterpolatingBasis(order), 25);
+    const double beta = 20.0, alpha = std::pow(beta / mrcpp::pi, 1.5);
+    const mrcpp::Coord<D> f_pos{0.0, 0.0, 0.17}, g_pos{0.0, 0.0, -0.1};
+    mrcpp::GaussFunc<D> f(beta, alpha, f_pos), g(beta, alpha, g_pos);
+    double dist_2 = 0.0;
+    mrcpp::Coord<D> p_pos{};
+    for (int d = 0; d < D; d++) {
+        dist_2 += (f_pos[d] - g_pos[d]) * (f_pos[d] - g_pos[d]);
+        p_pos[d] = 0.5 * (f_pos[d] + g_pos[d]);
+    }
+    mrcpp::GaussFunc<D> prod(2.0 * beta, alpha * alpha * std::exp(-beta * 0.5 * dist_2), p_pos);
+    mrcpp::FunctionTree<D> f_tree(MRA), g_tree(MRA), h_tree(MRA), sq_tree(MRA), prod_tree(MRA), err_tree(MRA);
+    mrcpp::project(prec, f_tree, f);
+    mrcpp::project(prec, g_tree, g);
+    mrcpp::project(prec / 1000, prod_tree, prod);
+    mrcpp::multiply(prec, h_tree, 1.0, f_tree, g_tree);
+    mrcpp::square(prec, sq_tree, f_tree);
+    mrcpp::build_grid(err_tree, h_tree);
+    mrcpp::build_grid(err_tree, prod_tree);
+    mrcpp::add(-1.0, err_tree, 1.0, h_tree, -1.0, prod_tree);
+    const double ana_int = alpha * alpha * std::exp(-beta * 0.5 * dist_2) * std::pow(mrcpp::pi / (2.0 * beta), 1.5);
+    const mrcpp::Coord<D> r{0.05, -0.1, 0.1};
+    std::printf("multiplication_nodes %d\nmultiplication_integral %.17g\nmultiplication_integral_analytic %.17g\n", h_tree.getNNodes(),
+                h_tree.integrate(), ana_int);
+    std::printf("multiplication_rel_err %.17g\nmultiplication_point_rel_err %.17g\n", std::sqrt(err_tree.getSquareNorm() / prod_tree.getSquareNorm()),
+                std::abs(h_tree.evalf_precise(r) - prod.evalf(r)) / prod.evalf(r));
+    // <f | f> = integral of f^2
+    std::printf("square_integral %.17g\nsquare_expected %.17g\n", sq_tree.integrate(), mrcpp::dot(f_tree, f_tree));
+}
+
 int main(int argc, char **argv) {
     mrcpp::Printer::init(argc > 1 ? std::atoi(argv[1]) : -1);
     mrcpp::print::environment(0);
@@ -177,6 +213,7 @@ int main(int argc, char **argv) {
     derivative_case();
     divergence_case();
     addition_case();
+    multiplication_case();
     std::printf("done 1\n");
     return 0;
 }

@@ -29,6 +29,7 @@ struct Oracle {
     double (*dot)(void *, void *);
     void (*set_tables)(const char *);
     void (*add)(double, void *, int, const double *, void **, int, int);
+    void (*multiply)(double, void *, int, const double *, void **, int, int);
 };
 Oracle &oracle() {
     static Oracle o = [] {
@@ -47,6 +48,7 @@ Oracle &oracle() {
         r.dot = reinterpret_cast<decltype(r.dot)>(dlsym(h, "orc_dot"));
         r.set_tables = reinterpret_cast<decltype(r.set_tables)>(dlsym(h, "orc_set_table_path"));
         r.add = reinterpret_cast<decltype(r.add)>(dlsym(h, "orc_add"));
+        r.multiply = reinterpret_cast<decltype(r.multiply)>(dlsym(h, "orc_multiply"));
         if (const char *t = std::getenv("MRX_TABLES")) r.set_tables(t);
         return r;
     }();
@@ -113,6 +115,13 @@ int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs
     std::vector<void *> h(n);
     for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
     oracle().add(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec);
+    mrx_tree_host_modified(out);
+    return 0;
+}
+int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {
+    std::vector<void *> h(n);
+    for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
+    oracle().multiply(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec);
     mrx_tree_host_modified(out);
     return 0;
 }

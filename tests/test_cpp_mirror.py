@@ -114,3 +114,7 @@ def check_drop_in_values(kv):
     # adaptive add (examples/addition.cpp): integral 1 - 2 + 3, point value, linearity of the overlap
     assert kv["addition_nodes"] > 8 and abs(kv["addition_integral"] - 2.0) < 1e-6 and kv["addition_point_rel_err"] < 1e-2
     assert abs(kv["addition_overlap_1"] - kv["addition_overlap_expected"]) < 1e-3 * abs(kv["addition_overlap_expected"])
+    # multiply / square (examples/multiplication.cpp): product of two Gaussians against the analytic product Gaussian
+    assert kv["multiplication_nodes"] > 8 and kv["multiplication_rel_err"] < 1e-2 and kv["multiplication_point_rel_err"] < 1e-2
+    assert abs(kv["multiplication_integral"] - kv["multiplication_integral_analytic"]) < 1e-3 * kv["multiplication_integral_analytic"]
+    assert abs(kv["square_integral"] - kv["square_expected"]) < 1e-3 * kv["square_expected"]

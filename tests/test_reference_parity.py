@@ -24,7 +24,9 @@ def gaussians(mw, n, seed, box=4.0, lo=1.0, hi=2.0):
     return out
 
 
-def same_tree(R, O, tol=TOL):
+def same_tree(R, O, tol=TOL, floor=1e-3):
+    """node sets identical; coefficients within tol of the node norm, nodes whose norm is below floor x the largest node norm
+    measured against that floor"""
     ri, oi = ref.by_index(R), ref.by_index(O)
     assert set(ri) == set(oi), (len(ri), len(oi))
     nmax = max(np.linalg.norm(R["coefs"][i]) for i in ri.values())
@@ -32,7 +34,7 @@ def same_tree(R, O, tol=TOL):
     for key, i in ri.items():
         j = oi[key]
         d = np.abs(R["coefs"][i] - O["coefs"][j]).max()
-        worst = max(worst, d / max(np.linalg.norm(R["coefs"][i]), 1e-3 * nmax + 1e-300))
+        worst = max(worst, d / max(np.linalg.norm(R["coefs"][i]), floor * nmax + 1e-300))
         assert (R["branch"][i] != 0) == (O["child0"][j] >= 0)
     assert worst < tol, worst
     return worst
@@ -242,10 +244,10 @@ def test_integrate_and_build_grid_match_reference(libs):
     assert abs(rg.integrate() - og.integrate()) <= 1e-12 * abs(rg.integrate())
 
 
-def _two_trees(mw, orc, k, prec):
+def _two_trees(mw, orc, k, prec, box=(4.0, 2.0)):
     world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
     rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
-    fa, fb = gaussians(mw, 2, 71), gaussians(mw, 3, 72, box=2.0)
+    fa, fb = gaussians(mw, 2, 71, box=box[0]), gaussians(mw, 3, 72, box=box[1])
     trees = []
     for funcs in (fa, fb):
         rt, ot = ref.Tree(rm), mw.FunctionTree(om)
@@ -414,3 +416,95 @@ def test_adaptive_add_matches_reference(libs, prec, max_iter, abs_prec, start):
     A, B = oo.to_arrays(), fixed.to_arrays()
     nrm = np.sqrt((A["coefs"] ** 2).sum(axis=1))
     assert (np.abs(A["coefs"] - B["coefs"]).max(axis=1) / np.maximum(nrm, 1e-3 * nrm.max())).max() < 1e-13
+
+
+@needs_ref
+@pytest.mark.parametrize("prec,max_iter,abs_prec,start", [(1e-4, -1, False, "roots"), (1e-3, -1, True, "roots"), (1e-4, 2, False, "roots"),
+                                                           (-1.0, -1, False, "union")])
+def test_multiply_matches_reference(libs, prec, max_iter, abs_prec, start):
+    """multiply(prec, out, {(c, f), (1, g)}, maxIter, absPrec) (multiply.cpp:104-136, MultiplicationCalculator.h:43-72): adaptive
+    from empty roots (examples/multiplication.cpp), with an iteration limit, absolute precision, and on the union grid without
+    refinement"""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-5, box=(1.0, 1.0))   # overlapping functions: a product of O(1)
+    ro, oo = ref.Tree(rm), mw.FunctionTree(om)
+    if start == "union":
+        for t in (ra, rb):
+            ref.build_grid_tree(ro, t)
+        for t in (oa, ob):
+            mw.build_grid(oo, t)
+    ref.multiply(ro, [0.7, 1.0], [ra, rb], prec=prec, maxIter=max_iter, absPrec=abs_prec)
+    orc.multiply(oo, [0.7, 1.0], [oa, ob], prec=prec, maxIter=max_iter, absPrec=abs_prec)
+    # a product of function values carries the rounding of the LARGER factor into regions where the product itself is tiny
+    # (observed: 3e-11 of the largest node norm between the reference and the oracle, which differ only in summation order), so
+    # the coefficient bar is measured against the largest node norm here, not against each node's own norm
+    same_tree(ro.export(), oo.to_arrays(), tol=1e-10, floor=1.0)
+    assert oo.getNNodes() > 8 and abs(ro.square_norm() - oo.getSquareNorm()) <= 1e-11 * ro.square_norm()
+    assert abs(ro.integrate() - oo.integrate()) <= 1e-11 * max(1e-3, abs(ro.integrate()))
+    assert oa.getNNodes() == ra.n_nodes()
+
+
+def test_multiply_as_device_formulation(libs):
+    """the formulation the DEVICE multiply uses (device_multiply, csrc/cuda/device_tree.cu), carried out with numpy and the
+    oracle's transforms on a union grid: inputs represented on the output grid (add with a single input), in-node
+    reconstruction as a TopDown(+=) step into eight extra child nodes, element-wise product of the function values, Backward
+    map, in-node compression as a BottomUp step -- must equal the reference algorithm as restated by orc.multiply"""
+    mw, orc = libs
+    k, prec = 5, 1e-4
+    K, Kd = k + 1, (k + 1) ** 3
+    mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    ta, tb = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    orc.project(prec, ta, expansion(mw, gaussians(mw, 2, 71, box=1.0)))      # overlapping functions: a product of O(1)
+    orc.project(prec, tb, expansion(mw, gaussians(mw, 3, 72, box=1.0)))
+    want = mw.FunctionTree(mra)
+    mw.build_grid(want, ta)
+    mw.build_grid(want, tb)
+    grid = mw.FunctionTree(mra)
+    mw.copy_grid(grid, want)
+    cs = [0.7, 1.0]
+    orc.multiply(want, cs, [ta, tb])
+    G = grid.to_arrays(coefs=False)
+    n = len(G["scale"])
+    ends = [i for i in range(n) if G["child0"][i] < 0]
+    # extended grid: eight children under every end node (the scratch child slots of the device code)
+    scale, transl, parent, child0 = list(G["scale"]), [tuple(t) for t in G["transl"]], list(G["parent"]), list(G["child0"])
+    for e in ends:
+        child0[e] = len(scale)
+        for c in range(8):
+            scale.append(scale[e] + 1)
+            transl.append(tuple(2 * transl[e][d] + ((c >> d) & 1) for d in range(3)))
+            parent.append(e)
+            child0.append(-1)
+    N = len(scale)
+    w = np.zeros(K)
+    from mrcpp_b200 import _lib
+    import ctypes as C
+    _lib.load().mrx_quadrature(K, None, w.ctypes.data_as(C.POINTER(C.c_double)))
+    idx = np.arange(Kd)
+    fx, fy, fz = idx % K, (idx // K) % K, idx // (K * K)
+    prod = None
+    for c, t in zip(cs, (ta, tb)):
+        X = mw.FunctionTree(mra)
+        mw.copy_grid(X, grid)
+        orc.add(X, [1.0], [t])                       # the input on the output grid
+        coefs = np.zeros((N, 8 * Kd))
+        coefs[:n] = X.to_arrays()["coefs"]
+        coefs[8:n, :Kd] = 0.0                        # the whole-tree TopDown(+=) below regenerates every non-root scaling block
+        E = mw.FunctionTree.from_arrays(mra, np.array(scale, np.int32), np.array(transl, np.int32), np.array(parent, np.int32),
+                                        np.array(child0, np.int32), coefs)
+        orc.mw_transform_down(E, overwrite=False)    # children.scaling += reconstruct(parent)
+        S = E.to_arrays()["coefs"][n:, :Kd]
+        np1 = np.array(scale[n:])                    # children's scale = scale of the output node + 1
+        vals = c * (np.sqrt(2.0 ** (3 * np1))[:, None] * (((S * np.sqrt(1 / w)[fx]) * np.sqrt(1 / w)[fy]) * np.sqrt(1 / w)[fz]))
+        prod = vals if prod is None else prod * vals
+    back = np.sqrt(1.0 / 2.0 ** (3 * np.array(scale[n:])))[:, None] * (((prod * np.sqrt(w)[fx]) * np.sqrt(w)[fy]) * np.sqrt(w)[fz])
+    coefs = np.zeros((N, 8 * Kd))
+    coefs[n:, :Kd] = back
+    Pt = mw.FunctionTree.from_arrays(mra, np.array(scale, np.int32), np.array(transl, np.int32), np.array(parent, np.int32),
+                                     np.array(child0, np.int32), coefs)
+    orc.mw_transform_up(Pt)
+    got, W = Pt.to_arrays()["coefs"][:n], want.to_arrays()
+    assert np.array_equal(W["transl"], G["transl"])
+    nrm = np.sqrt((W["coefs"] ** 2).sum(axis=1))
+    assert nrm.max() > 1e-2
+    assert (np.abs(W["coefs"] - got).max(axis=1) / nrm.max()).max() < 1e-11

@@ -109,3 +109,35 @@ def test_adaptive_add(gpu, k, prec, max_iter, abs_prec, start):
     sc = orc.apply(1e-3, vc, P, oc)
     assert sg.f_applied == sc.fApplied
     assert_same_tree(vg, vc)
+
+
+@pytest.mark.parametrize("k,prec,max_iter,abs_prec,start", [(5, 1e-4, -1, False, "roots"), (7, 1e-5, -1, False, "roots"), (5, 1e-3, -1, True, "roots"),
+                                                             (5, 1e-4, 2, False, "roots"), (5, -1.0, -1, False, "union"), (4, 1e-4, -1, False, "roots")])
+def test_multiply(gpu, k, prec, max_iter, abs_prec, start):
+    """multiply(prec, out, {(c, f), (1, g)}, maxIter, absPrec) (multiply.cpp:104-136): node set identical; coefficients against
+    the largest node norm (a product carries the rounding of its larger factor into regions where it is tiny itself, see
+    tests/test_reference_parity.py::test_multiply_matches_reference)"""
+    mw, orc = gpu
+    mra = world(mw, k)
+    trees = []
+    for n, seed in ((2, 71), (3, 72)):
+        func = gaussians(n, seed, box=1.0, lo=1.0, hi=2.0)   # overlapping functions: a product of O(1)
+        g, c = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        mw.project(1e-5, g, func)
+        orc.project(1e-5, c, func)
+        trees.append((g, c))
+    (ga, ca), (gb, cb) = trees
+    og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    if start == "union":
+        for o, a, b in ((og, ga, gb), (oc, ca, cb)):
+            mw.build_grid(o, a)
+            mw.build_grid(o, b)
+    mw.multiply(prec, og, [(0.7, ga), (1.0, gb)], max_iter, abs_prec)
+    orc.multiply(oc, [0.7, 1.0], [ca, cb], prec=prec, maxIter=max_iter, absPrec=abs_prec)
+    A, B = og.to_arrays(), oc.to_arrays()
+    assert A["scale"].shape == B["scale"].shape and np.array_equal(A["transl"], B["transl"]) and np.array_equal(A["child0"], B["child0"])
+    nrm = np.sqrt((B["coefs"] ** 2).sum(axis=1))
+    assert og.getNNodes() > 8 and nrm.max() > 1e-2
+    assert (np.abs(A["coefs"] - B["coefs"]).max(axis=1) / nrm.max()).max() < 1e-10
+    assert abs(og.getSquareNorm() - oc.getSquareNorm()) <= 1e-10 * oc.getSquareNorm()
+    assert abs(og.integrate() - oc.integrate()) <= 1e-10 * max(abs(oc.integrate()), 1e-3)
