@@ -706,58 +706,83 @@ template <int D, typename T> T dot(FunctionTree<D, T> &bra, FunctionTree<D, T> &
 class Printer final {
 public:
     static void init(int level = 0, int rank = 0, int size = 1, const char * /*file*/ = nullptr) {
-        state().level = level;
-        state().rank = rank;
-        state().size = size;
-        *state().out << std::scientific << std::setprecision(state().prec);
+        printLevel = level;
+        printRank = rank;
+        printSize = size;
+        if (rank != 0) printLevel = -1; // only rank 0 prints to the screen (Printer.cpp: other ranks go to files)
+        *out << std::scientific << std::setprecision(printPrec);
     }
-    static void setScientific() { *state().out << std::scientific; }
-    static void setFixed() { *state().out << std::fixed; }
+    static void setScientific() { *out << std::scientific; }
+    static void setFixed() { *out << std::fixed; }
     static int setWidth(int i) {
-        int old = state().width;
-        state().width = i;
+        int old = printWidth;
+        printWidth = i;
         return old;
     }
     static int setPrecision(int i) {
-        int old = state().prec;
-        state().prec = i;
-        *state().out << std::setprecision(i);
+        int old = printPrec;
+        printPrec = i;
+        *out << std::setprecision(i);
         return old;
     }
     static int setPrintLevel(int i) {
-        int old = state().level;
-        state().level = i;
+        int old = printLevel;
+        printLevel = i;
         return old;
     }
-    static int getWidth() { return state().width; }
-    static int getPrecision() { return state().prec; }
-    static int getPrintLevel() { return state().level; }
-    static void setOutputStream(std::ostream &o) { state().out = &o; }
-    static std::ostream &out() { return *state().out; }
-    static bool active(int level) { return level <= state().level && state().rank == 0; }
+    static int getWidth() { return printWidth; }
+    static int getPrecision() { return printPrec; }
+    static int getPrintLevel() { return printLevel; }
+    static void setOutputStream(std::ostream &o) { out = &o; }
+    static bool active(int level) { return level <= printLevel; }
+
+    static inline std::ostream *out = &std::cout; // public like the reference's (the print macros below write to it)
 
 private:
-    struct State {
-        int level = -1, width = 60, prec = 12, rank = 0, size = 1;
-        std::ostream *out = &std::cout;
-    };
-    static State &state() {
-        static State s;
-        return s;
-    }
+    static inline int printWidth = 60;
+    static inline int printLevel = -1;
+    static inline int printPrec = 12;
+    static inline int printRank = 0;
+    static inline int printSize = 1;
 };
+
+// print macros of src/utils/Printer.h:138-190
+#define println(level, STR)                                                                                                    \
+    {                                                                                                                          \
+        if (level <= mrcpp::Printer::getPrintLevel()) *mrcpp::Printer::out << STR << std::endl;                                \
+    }
+#define printout(level, STR)                                                                                                   \
+    {                                                                                                                          \
+        if (level <= mrcpp::Printer::getPrintLevel()) *mrcpp::Printer::out << STR;                                             \
+    }
+#define MSG_INFO(STR)                                                                                                          \
+    { *mrcpp::Printer::out << "Info: " << __FILE__ << ": " << __func__ << "(), line " << __LINE__ << ": " << STR << std::endl; }
+#define MSG_WARN(STR)                                                                                                          \
+    { *mrcpp::Printer::out << "Warning: " << __func__ << "(), line " << __LINE__ << ": " << STR << std::endl; }
+#define MSG_ERROR(STR)                                                                                                         \
+    { *mrcpp::Printer::out << "Error: " << __func__ << "(), line " << __LINE__ << ": " << STR << std::endl; }
+#define MSG_ABORT(STR)                                                                                                         \
+    {                                                                                                                          \
+        *mrcpp::Printer::out << "Error: " << __FILE__ << ": " << __func__ << "(), line " << __LINE__ << ": " << STR << std::endl; \
+        abort();                                                                                                               \
+    }
+#define NOT_IMPLEMENTED_ABORT                                                                                                  \
+    {                                                                                                                          \
+        *mrcpp::Printer::out << "Error: Not implemented, " << __FILE__ ", " << __func__ << "(), line " << __LINE__ << std::endl; \
+        abort();                                                                                                               \
+    }
 
 namespace print {
 inline void separator(int level, const char &c, int newlines = 0) {
     if (!Printer::active(level)) return;
-    Printer::out() << std::string(Printer::getWidth(), c) << std::endl;
-    for (int i = 0; i < newlines; i++) Printer::out() << std::endl;
+    (*Printer::out) << std::string(Printer::getWidth(), c) << std::endl;
+    for (int i = 0; i < newlines; i++) (*Printer::out) << std::endl;
 }
 inline void header(int level, const std::string &txt, int newlines = 0, const char &c = '=') {
     if (!Printer::active(level)) return;
     const int len = (int)txt.size();
     separator(level, c);
-    Printer::out() << std::string(std::max(0, (Printer::getWidth() - len) / 2), ' ') << txt << std::endl;
+    (*Printer::out) << std::string(std::max(0, (Printer::getWidth() - len) / 2), ' ') << txt << std::endl;
     separator(level, '-', newlines);
 }
 inline void footer(int level, const Timer &timer, int newlines = 0, const char &c = '=') {
@@ -766,17 +791,17 @@ inline void footer(int level, const Timer &timer, int newlines = 0, const char &
     o << std::fixed << std::setprecision(5) << "Wall time: " << std::scientific << timer.elapsed() << " sec";
     const int len = (int)o.str().size();
     separator(level, '-');
-    Printer::out() << std::string(std::max(0, (Printer::getWidth() - len) / 2), ' ') << o.str() << std::endl;
+    (*Printer::out) << std::string(std::max(0, (Printer::getWidth() - len) / 2), ' ') << o.str() << std::endl;
     separator(level, c, newlines);
 }
 inline void environment(int level) {
     if (!Printer::active(level)) return;
     b200::ensure_init();
     separator(level, '-', 1);
-    Printer::out() << " MRCPP API on " << mrx_version() << std::endl;
-    Printer::out() << " CUDA devices visible : " << mrx_device_count() << std::endl;
-    Printer::out() << " device of this process: " << b200::device_ref() << (b200::device_ref() < 0 ? " (host only: hot-path calls abort)" : "") << std::endl;
-    Printer::out() << std::endl;
+    (*Printer::out) << " MRCPP API on " << mrx_version() << std::endl;
+    (*Printer::out) << " CUDA devices visible : " << mrx_device_count() << std::endl;
+    (*Printer::out) << " device of this process: " << b200::device_ref() << (b200::device_ref() < 0 ? " (host only: hot-path calls abort)" : "") << std::endl;
+    (*Printer::out) << std::endl;
     separator(level, '-', 1);
 }
 inline void memory(int level, const std::string &txt) {
@@ -790,7 +815,7 @@ inline void memory(int level, const std::string &txt) {
     std::ostringstream o;
     o << " " << txt;
     const int pad = std::max(1, Printer::getWidth() - (int)o.str().size() - 16);
-    Printer::out() << o.str() << std::string(pad, ' ') << std::fixed << std::setprecision(2) << std::setw(10) << mb << " (MB)" << std::scientific
+    (*Printer::out) << o.str() << std::string(pad, ' ') << std::fixed << std::setprecision(2) << std::setw(10) << mb << " (MB)" << std::scientific
                    << std::setprecision(Printer::getPrecision()) << std::endl;
 }
 inline void value(int level, const std::string &txt, double v, const std::string &unit = "", int p = -1, bool sci = true) {
@@ -801,7 +826,7 @@ inline void value(int level, const std::string &txt, double v, const std::string
     if (sci) o << std::scientific;
     else o << std::fixed;
     o << std::setprecision(p) << std::setw(std::max(p + 8, Printer::getWidth() - 41)) << v;
-    Printer::out() << o.str() << std::endl;
+    (*Printer::out) << o.str() << std::endl;
 }
 inline void time(int level, const std::string &txt, const Timer &timer) { value(level, txt, timer.elapsed(), "(sec)", 5); }
 inline void tree(int level, const std::string &txt, int n, int m, double t) {
@@ -809,7 +834,7 @@ inline void tree(int level, const std::string &txt, int n, int m, double t) {
     std::ostringstream o;
     o << " " << std::left << std::setw(26) << txt << std::right << std::setw(8) << n << " nds " << std::setw(8) << m << " kB " << std::scientific
       << std::setprecision(2) << std::setw(9) << t << " sec";
-    Printer::out() << o.str() << std::endl;
+    (*Printer::out) << o.str() << std::endl;
 }
 template <int D, typename T> void tree(int level, const std::string &txt, const MWTree<D, T> &tr, const Timer &timer) {
     tree(level, txt, tr.getNNodes(), tr.getSizeNodes(), timer.elapsed());

@@ -59,11 +59,12 @@ def test_hot_path_call_without_device_aborts(libs, bindir):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
-@pytest.mark.parametrize("example", ["poisson", "projection"])
+@pytest.mark.parametrize("example", ["poisson", "projection", "scf"])
 def test_reference_examples_compile_unmodified(libs, bindir, example):
-    """examples/poisson.cpp and examples/projection.cpp of the reference, compiled where they lie against include/MRCPP/ and
-    linked with libmrcpp_b200.so; run without a device they print their header and abort at the first device call"""
-    exe = cb.compile_program([os.path.join(REF_EXAMPLES, example + ".cpp")], os.path.join(bindir, "ref_" + example))
+    """examples/poisson.cpp, examples/projection.cpp and examples/scf.cpp of the reference, compiled where they lie against
+    include/MRCPP/ and linked with libmrcpp_b200.so; run without a device they print their header and abort at the first
+    device call"""
+    exe = cb.compile_program([os.path.join(REF_EXAMPLES, example + ".cpp")], os.path.join(bindir, "ref_" + example), werror=False)
     r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
     assert r.returncode == -signal.SIGABRT and "no CPU fallback" in r.stderr
 
@@ -90,6 +91,33 @@ def test_drop_in_program_on_the_oracle_backend(libs, bindir):
     assert kv["poisson_tuples"] == st.fApplied and kv["poisson_calc_nodes"] == st.gNodes
     assert abs(kv["poisson_energy"] - orc.dot(gt, ft)) <= 1e-13 * abs(kv["poisson_energy"])
     assert abs(kv["poisson_f_integral"] - ft.integrate()) <= 1e-14 and abs(kv["poisson_g_integral"] - gt.integrate()) <= 1e-10
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
+def test_reference_scf_example_on_the_oracle_backend(libs, bindir):
+    """the reference's examples/scf.cpp, UNMODIFIED, through the C++ mirror with the device entry points served by the CPU oracle:
+    the hydrogen SCF must converge to -0.5 Hartree (project, multiply, Helmholtz apply, rescale, add, dot, normalize)"""
+    exe = cb.compile_program([os.path.join(REF_EXAMPLES, "scf.cpp"), os.path.join(CPP, "oracle_backend.cpp")], os.path.join(bindir, "ref_scf_cpu"),
+                             werror=False)
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if "Eigenvalue" in ln]
+    assert line and abs(float(line[0].split()[-1]) + 0.5) < 1e-3
+
+
+def test_scf_program_on_the_oracle_backend(libs, bindir):
+    """tests/cpp/scf_hydrogen.cpp (the program the GPU suite runs on the device) on the oracle backend: converges to the exact
+    ground-state energy, the orbital integrates to 8 sqrt(pi)"""
+    exe = cb.compile_program([os.path.join(CPP, "scf_hydrogen.cpp"), os.path.join(CPP, "oracle_backend.cpp")], os.path.join(bindir, "scf_cpu"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr
+    check_scf_values(cb.key_values(r.stdout))
+
+
+def check_scf_values(kv):
+    assert kv["done"] == 1 and 3 <= kv["iterations"] <= 12
+    assert abs(kv["final_energy"] + 0.5) < 1e-4 and kv["final_update"] < 1e-3
+    assert abs(kv["orbital_norm"] - 1.0) < 1e-12 and abs(kv["orbital_integral"] - 8.0 * math.sqrt(math.pi)) < 0.05
 
 
 def check_drop_in_values(kv):

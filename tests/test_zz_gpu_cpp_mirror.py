@@ -7,7 +7,7 @@ import os
 import pytest
 
 import cpp_build as cb
-from test_cpp_mirror import check_drop_in_values
+from test_cpp_mirror import check_drop_in_values, check_scf_values
 
 pytestmark = pytest.mark.gpu
 
@@ -37,3 +37,25 @@ def test_drop_in_program_on_the_device(libs, tmp_path):
     assert abs(kv["poisson_energy"] - en) <= 1e-12 * abs(en)
     assert abs(kv["poisson_g_sqnorm"] - gt.getSquareNorm()) <= 1e-12 * gt.getSquareNorm()
     assert abs(kv["poisson_f_integral"] - ft.integrate()) <= 1e-13 and abs(kv["poisson_g_integral"] - gt.integrate()) <= 1e-9 * abs(gt.integrate())
+
+
+def test_scf_cycle_on_the_device(libs, tmp_path):
+    """tests/cpp/scf_hydrogen.cpp: a complete self-consistency loop on resident trees (projection, multiply, Helmholtz operator
+    construction + apply, rescale, add, dot, normalize) on the device; same energies as the run of the same program with the
+    device entry points served by the CPU oracle"""
+    src = os.path.join(cb.ROOT, "tests", "cpp", "scf_hydrogen.cpp")
+    exe = cb.compile_program([src], str(tmp_path / "scf_gpu"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    kv = cb.key_values(r.stdout)
+    check_scf_values(kv)
+    cpu = cb.compile_program([src, os.path.join(cb.ROOT, "tests", "cpp", "oracle_backend.cpp")], str(tmp_path / "scf_cpu"))
+    rc = cb.run_program(cpu, env={"MRCPP_B200_DEVICE": "-1"})
+    assert rc.returncode == 0, rc.stderr[-2000:]
+    kc = cb.key_values(rc.stdout)
+    assert kv["iterations"] == kc["iterations"]
+    # the two runs differ in rounding only (same algorithm, same thresholds); a borderline split decision may still fall
+    # differently over seven chained operations, so node counts are compared loosely and energies at 1e-6
+    for it in range(1, int(kv["iterations"]) + 1):
+        assert abs(kv[f"nodes_{it}"] - kc[f"nodes_{it}"]) <= 0.02 * kc[f"nodes_{it}"]
+        assert abs(kv[f"energy_{it}"] - kc[f"energy_{it}"]) < 1e-6
