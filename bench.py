@@ -25,9 +25,12 @@ are all-gathered over NCCL and the output coefficient blocks are pushed to the p
 N -> strong scaling; time = max over ranks.
 """
 import os as _os
+import sys as _sys0
 if int(_os.environ.get("WORLD_SIZE", "1")) > 1:
-    # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores
-    _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
+    # torchrun pins OMP_NUM_THREADS=1; the host-side input generator (projection) wants the rank's share of cores. The
+    # reference arm runs on rank 0 alone (the other ranks exit at once), so there it gets every core of the box.
+    _ref_arm = any(a == "reference" or a.endswith("=reference") for a in _sys0.argv)
+    _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // (1 if _ref_arm else int(_os.environ["WORLD_SIZE"]))))
 # bench prints exactly ONE JSON line on stdout. Libraries write banners there (NCCL prints its version on communicator
 # creation on these boxes), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved
 # original descriptor.
