@@ -383,7 +383,7 @@ def main():
         }
         line["roofline"]["traffic"] = ncu_traffic()
         line["transforms"] = transforms_roofline(L, ft, K)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only (all host cores free)
             line["cpu_baseline"] = cpu_baseline(args, mw, mra, P)
         emit(json.dumps(line))
     if world > 1:
