@@ -470,6 +470,18 @@ private:
     double mu;
 };
 
+/// IdentityConvolution(mra, prec): src/operators/IdentityConvolution.cpp:40-56 with IdentityKernel (IdentityKernel.h:40-47): one
+/// narrow normalised Gaussian, exponent sqrt(1 / (prec / 10))
+template <int D> class IdentityConvolution final : public ConvolutionOperator<D> {
+public:
+    IdentityConvolution(const MultiResolutionAnalysis<D> &mra, double prec)
+            : ConvolutionOperator<D>(mra, prec) {
+        const double expo = std::sqrt(1.0 / (prec / 10.0));
+        const double coef = std::pow(expo / pi, D / 2.0);
+        this->h = mrx_convolution_create(mra.handle(), 1, &coef, &expo, prec);
+    }
+};
+
 template <int D> class DerivativeOperator : public MWOperatorBase {
     static_assert(D == 3, "the B200 path implements 3-dimensional operators only");
 
@@ -523,6 +535,8 @@ template <int D, typename T> void build_grid(FunctionTree<D, T> &out, const Repr
 }
 /// copy_grid / clear_grid: src/treebuilders/grid.cpp:150-166, :180-186
 template <int D, typename T> void copy_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp) { mrx_tree_copy_grid(out.handle(), inp.handle()); }
+/// clear_grid(out): src/treebuilders/grid.cpp:180-186
+template <int D, typename T> void clear_grid(FunctionTree<D, T> &out) { mrx_tree_clear_grid(out.handle()); }
 /// build_grid(out, tree): extend the grid of `out` with the nodes of `inp` (src/treebuilders/grid.cpp:144-153)
 template <int D, typename T> void build_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp, int maxIter = -1) {
     if (maxIter >= 0) MRCPP_B200_ABORT("build_grid(out, tree, maxIter >= 0) is not on the B200 path");
@@ -638,6 +652,18 @@ void add(double prec, FunctionTree<D, T> &out, T a, FunctionTree<D, T> &inp_a, T
     v.push_back(std::make_tuple(a, &inp_a));
     v.push_back(std::make_tuple(b, &inp_b));
     add(prec, out, v, maxIter, absPrec, conjugate);
+}
+/// copy_func(out, inp): src/treebuilders/grid.cpp:204-208 -- the function `inp` on the grid `out` enters with
+template <int D, typename T> void copy_func(FunctionTree<D, T> &out, FunctionTree<D, T> &inp) {
+    FunctionTreeVector<D, T> v;
+    v.push_back(std::make_tuple(T(1.0), &inp));
+    add(-1.0, out, v);
+}
+/// mrcpp::apply(prec, out, oper, inp, precTrees, maxIter, absPrec): src/treebuilders/apply.cpp:214-251 -- the locally scaled
+/// precision is not built on the B200 path: aborts rather than silently ignoring the precision trees
+template <int D, typename T>
+void apply(double, FunctionTree<D, T> &, ConvolutionOperator<D> &, FunctionTree<D, T> &, FunctionTreeVector<D, T> &, int = -1, bool = false) {
+    MRCPP_B200_ABORT("apply with precTrees is not built on the B200 path");
 }
 /// mrcpp::multiply(prec, out, inp, maxIter, absPrec, useMaxNorms, conjugate): src/treebuilders/multiply.cpp:104-136
 template <int D, typename T>

@@ -191,6 +191,8 @@ double mrx_dot(mrx_tree *bra, mrx_tree *ket);
 /* FunctionTree::rescale(c): src/trees/FunctionTree.cpp (coefficient-wise scaling) */
 int mrx_tree_rescale(mrx_tree *tree, double c);
 
+/* clear_grid(out) (src/treebuilders/grid.cpp:180-186): keep the grid, drop coefficients and norms. Host only. */
+int mrx_tree_clear_grid(mrx_tree *tree);
 /* build_grid(out, inp) (src/treebuilders/grid.cpp:144-153): extend the grid of `out` with every node of `inp` (union of the
  * two grids; coefficients of `out` are dropped). Host only. */
 int mrx_tree_build_grid_from(mrx_tree *out, const mrx_tree *inp);

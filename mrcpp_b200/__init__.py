@@ -309,6 +309,16 @@ def project_function(prec, out, func, finalize=True):
     _lib.load().mrx_project_function(out._h, float(prec), C.cast(cb, C.c_void_p), None, 0, 1 if finalize else 0)
 
 
+def clear_grid(out):
+    """src/treebuilders/grid.cpp:180-186: keep the grid, drop the coefficients"""
+    _lib.load().mrx_tree_clear_grid(out._h)
+
+
+def copy_func(out, inp):
+    """src/treebuilders/grid.cpp:204-208: the function `inp` on the grid `out` enters with"""
+    add(-1.0, out, [(1.0, inp)])
+
+
 def copy_grid(out, inp):
     """src/treebuilders/grid.cpp:150-166"""
     _lib.load().mrx_tree_copy_grid(out._h, inp._h)

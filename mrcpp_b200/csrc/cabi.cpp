@@ -615,6 +615,24 @@ int mrx_tree_rescale(mrx_tree *tree, double c) {
     device_rescale(*tree, c);
     return 0;
 }
+// clear_grid(out) (src/treebuilders/grid.cpp:180-186): keep the grid, drop coefficients and norms
+int mrx_tree_clear_grid(mrx_tree *tree) {
+    Tree<3> &h = tree->host;
+    h.deleteGenerated();
+    for (int n = 0; n < h.nReal; n++) {
+        h.nodes[n].flags &= ~FlagHasCoefs;
+        for (int t = 0; t < 8; t++) h.cnorm[(size_t)n * 8 + t] = -1.0;
+        h.sqn[n] = -1.0;
+    }
+    h.squareNorm = -1.0;
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    tree->dev.nNodes = 0;
+    tree->dev.nGen = 0;
+    tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
+    return 0;
+}
 int mrx_tree_build_grid_from(mrx_tree *out, const mrx_tree *inp) {
     if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
     out->host.extendGridFrom(inp->host);

@@ -52,6 +52,10 @@ int main() {
     mrcpp::FunctionTree<D> copy(MRA);
     mrcpp::copy_grid(copy, grid);
     std::printf("copy_nodes %d\nsquare_norm_empty %.17g\n", copy.getNNodes(), copy.getSquareNorm());
+    mrcpp::clear_grid(copy);
+    std::printf("clear_grid_nodes %d\n", copy.getNNodes());
+    mrcpp::IdentityConvolution<D> I(MRA, 1.0e-4);
+    std::printf("identity_terms %d\n", I.size());
     copy.clear();
     std::printf("cleared_nodes %d\n", copy.getNNodes());
 

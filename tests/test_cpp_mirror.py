@@ -48,6 +48,7 @@ def test_host_api_matches_python_mirror(libs, bindir):
     mw.build_grid(t2, e)
     assert kv["grid2_nodes"] == kv["copy_nodes"] == t2.getNNodes() and kv["cleared_nodes"] == 8
     assert kv["square_norm_empty"] == -1.0 and kv["log_lines"] == 8
+    assert kv["clear_grid_nodes"] == kv["copy_nodes"] and kv["identity_terms"] == 1
 
 
 def test_hot_path_call_without_device_aborts(libs, bindir):
