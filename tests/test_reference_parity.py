@@ -508,3 +508,35 @@ def test_multiply_as_device_formulation(libs):
     nrm = np.sqrt((W["coefs"] ** 2).sum(axis=1))
     assert nrm.max() > 1e-2
     assert (np.abs(W["coefs"] - got).max(axis=1) / nrm.max()).max() < 1e-11
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["C4", "C5"])
+def test_config_shapes_match_reference(libs, case):
+    """the shapes of BASELINE configs C4 and C5 at sizes the CPU finishes in seconds: HelmholtzOperator mu = 1 at k = 9 on a
+    ring of six centres of a benzene-like orbital, and Poisson at k = 11, prec 1e-6 on two centres of the C5
+    generator (centres uniform in [-8, 8]^3, beta log-uniform in [10, 1000], seed 42)"""
+    mw, orc = libs
+    if case == "C4":
+        k, prec = 9, 1e-5
+        rng = np.random.default_rng(2024)
+        funcs = [mw.GaussFunc(1.5, float(rng.normal()), (2.64 * math.cos(math.pi / 3 * a), 2.64 * math.sin(math.pi / 3 * a), 0.0)) for a in range(6)]
+    else:
+        k, prec = 11, 1e-6
+        funcs = gaussians(mw, 2, 42, box=8.0, lo=1.0, hi=3.0)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    same_tree(rf.export(), of.to_arrays())
+    if case == "C4":
+        RO, OO = ref.helmholtz(rm, 1.0, prec), mw.HelmholtzOperator(om, 1.0, prec)
+    else:
+        RO, OO = ref.poisson(rm, prec), mw.PoissonOperator(om, prec)
+    assert ref.lib().ref_oper_n_terms(RO) == OO.size()
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, RO, rf)
+    orc.apply(prec, og, OO, of)
+    same_tree(rg.export(), og.to_arrays())
+    assert abs(ref.dot(rg, rf) - orc.dot(og, of)) <= 1e-12 * abs(ref.dot(rg, rf))
