@@ -2,7 +2,7 @@
 // MRCPP itself: Poisson apply (the case of the reference's examples/poisson.cpp and tests/operators/poisson_operator.cpp),
 // the hydrogen 1s fixed point of the Helmholtz operator (tests/operators/helmholtz_operator.cpp) and an ABGV derivative of a
 // Gaussian against the projection of its analytic derivative (tests/operators/derivative_operator.cpp pattern).
-// Prints "key value" lines; tests/test_zz_gpu_cpp_mirror.py checks them against the analytic answers and against the same
+// Prints "key value" lines; tests/test_zz3_gpu_cpp_mirror.py checks them against the analytic answers and against the same
 // cases run through the Python mirror. Needs a CUDA device: without one the first projection aborts (no CPU fallback).
 #include "MRCPP/Gaussians"
 #include "MRCPP/MWFunctions"
@@ -206,14 +206,20 @@ static void multiplication_case() {
 }
 
 int main(int argc, char **argv) {
+    // argv[1]: print level (default -1); argv[2]: "core" (the apply path), "algebra" (its callers) or "all" (default)
     mrcpp::Printer::init(argc > 1 ? std::atoi(argv[1]) : -1);
+    const std::string what = argc > 2 ? argv[2] : "all";
     mrcpp::print::environment(0);
-    poisson_case();
-    helmholtz_case();
-    derivative_case();
-    divergence_case();
-    addition_case();
-    multiplication_case();
+    if (what != "algebra") {
+        poisson_case();
+        helmholtz_case();
+        derivative_case();
+    }
+    if (what != "core") {
+        divergence_case();
+        addition_case();
+        multiplication_case();
+    }
     std::printf("done 1\n");
     return 0;
 }

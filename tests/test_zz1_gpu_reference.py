@@ -70,52 +70,3 @@ def test_golden_vectors_of_the_real_reference(gpu):
         mw.project(prec, ft, f, device=device_projection)
         mw.apply(prec, gt, P, ft)
         check_against_golden_ref(mw, ft, gt, P, mw.dot(gt, ft))
-
-
-def test_tree_algebra_vs_real_reference(gpu):
-    """add (adaptive), multiply and divergence on the device against the REAL reference (oracle/_ref): node sets identical;
-    coefficients within 1e-12 of the node norm for the linear operations, 1e-10 of the largest node norm for the product"""
-    import ref_api as ref
-    if not ref.available():
-        pytest.skip("oracle/_ref not built")
-    mw, orc = gpu
-    k, prec = 5, 1e-5
-    wd = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
-    try:
-        rm = ref.MRA(*wd)
-    except OSError as e:
-        pytest.skip(f"oracle/_ref does not load here: {e}")
-    mra = mw.MultiResolutionAnalysis(*wd)
-    rng = np.random.default_rng(3)
-    trees = []
-    for n in (2, 3):
-        funcs = [mw.GaussFunc(b, (b / math.pi) ** 1.5 / n, tuple(rng.uniform(-1, 1, 3))) for b in 10.0 ** rng.uniform(1, 2, n)]
-        rt, gt = ref.Tree(rm), mw.FunctionTree(mra)
-        ref.project(prec, rt, funcs)
-        e = mw.GaussExp()
-        for f in funcs:
-            e.append(f)
-        mw.project(prec, gt, e, device=True)
-        trees.append((rt, gt))
-    (ra, ga), (rb, gb) = trees
-
-    def compare(R, G, tol, floor):
-        ri, gi = ref.by_index(R), ref.by_index(G)
-        assert set(ri) == set(gi)
-        nmax = max(np.linalg.norm(R["coefs"][i]) for i in ri.values())
-        worst = max(np.abs(R["coefs"][i] - G["coefs"][gi[key]]).max() / max(np.linalg.norm(R["coefs"][i]), floor * nmax) for key, i in ri.items())
-        assert worst < tol, worst
-
-    ro, go = ref.Tree(rm), mw.FunctionTree(mra)
-    ref.add(ro, [1.0, -2.0], [ra, rb], prec=1e-4)
-    mw.add(1e-4, go, [(1.0, ga), (-2.0, gb)])
-    compare(ro.export(), go.to_arrays(), COEF_TOL, 1e-3)
-    ro, go = ref.Tree(rm), mw.FunctionTree(mra)
-    ref.multiply(ro, [0.7, 1.0], [ra, rb], prec=1e-4)
-    mw.multiply(1e-4, go, [(0.7, ga), (1.0, gb)])
-    compare(ro.export(), go.to_arrays(), 1e-10, 1.0)
-    RD, GD = ref.abgv(rm, 0.5, 0.5), mw.ABGVOperator(mra, 0.5, 0.5)
-    ro, go = ref.Tree(rm), mw.FunctionTree(mra)
-    ref.divergence(ro, RD, [ra, rb, ra])
-    mw.divergence(go, GD, [(1.0, ga), (1.0, gb), (1.0, ga)])
-    compare(ro.export(), go.to_arrays(), 1e-11, 1e-3)

@@ -1,10 +1,12 @@
 """GPU parity tests (-m gpu) of the callers next to the derivative apply (src/treebuilders/apply.h:51-55,
 add.h, grid.h:37): add on a given grid, build_grid from trees, gradient, divergence, integrate -- the CUDA path through the
 C ABI against the CPU oracle (which tests/test_reference_parity.py pins against the real reference for the same calls)."""
+import math
+
 import numpy as np
 import pytest
 
-from test_gpu_parity import assert_same_tree, gaussians, world
+from test_gpu_parity import COEF_TOL, assert_same_tree, gaussians, world
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +30,21 @@ def two_trees(mw, orc, k, prec):
         orc.project(prec, c, func)
         out.append((g, c))
     return mra, out
+
+
+@pytest.mark.parametrize("family,order", [("ph", 1), ("ph", 2), ("bs", 1), ("bs", 2), ("bs", 3)])
+def test_ph_bs_derivative(gpu, family, order):
+    """PHOperator / BSOperator (PHOperator.cpp:40-69, BSOperator.cpp:40-66) through apply(out, D, inp, dir): the device path
+    against the oracle (pinned against the real reference for the same operators in tests/test_reference_parity.py)"""
+    mw, orc = gpu
+    mra, ((ga, ca), _) = two_trees(mw, orc, 5, 1e-4)
+    D = mw.PHOperator(mra, order) if family == "ph" else mw.BSOperator(mra, order)
+    for d in range(3):
+        og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        sg = mw.apply(None, og, D, ga, dir=d)
+        sc = orc.apply_derivative(oc, D, ca, d)
+        assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
+        assert_same_tree(og, oc, tol=1e-11)
 
 
 @pytest.mark.parametrize("k,grid", [(5, "union"), (7, "union"), (5, "roots"), (5, "first"), (4, "union")])
@@ -70,21 +87,6 @@ def test_gradient_and_divergence(gpu):
     orc.divergence(oc, D, [ca, cb, ca])
     assert_same_tree(og, oc, tol=1e-11)
     assert abs(ga.integrate() - ca.integrate()) <= 1e-13 and abs(og.integrate() - oc.integrate()) <= 1e-10
-
-
-@pytest.mark.parametrize("family,order", [("ph", 1), ("ph", 2), ("bs", 1), ("bs", 2), ("bs", 3)])
-def test_ph_bs_derivative(gpu, family, order):
-    """PHOperator / BSOperator (PHOperator.cpp:40-69, BSOperator.cpp:40-66) through apply(out, D, inp, dir): the device path
-    against the oracle (pinned against the real reference for the same operators in tests/test_reference_parity.py)"""
-    mw, orc = gpu
-    mra, ((ga, ca), _) = two_trees(mw, orc, 5, 1e-4)
-    D = mw.PHOperator(mra, order) if family == "ph" else mw.BSOperator(mra, order)
-    for d in range(3):
-        og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
-        sg = mw.apply(None, og, D, ga, dir=d)
-        sc = orc.apply_derivative(oc, D, ca, d)
-        assert sg.f_applied == sc.fApplied and sg.g_nodes == sc.gNodes
-        assert_same_tree(og, oc, tol=1e-11)
 
 
 @pytest.mark.parametrize("k,prec,max_iter,abs_prec,start", [(5, 1e-4, -1, False, "roots"), (7, 1e-5, -1, False, "roots"), (5, 1e-3, -1, True, "roots"),
@@ -141,3 +143,52 @@ def test_multiply(gpu, k, prec, max_iter, abs_prec, start):
     assert (np.abs(A["coefs"] - B["coefs"]).max(axis=1) / nrm.max()).max() < 1e-10
     assert abs(og.getSquareNorm() - oc.getSquareNorm()) <= 1e-10 * oc.getSquareNorm()
     assert abs(og.integrate() - oc.integrate()) <= 1e-10 * max(abs(oc.integrate()), 1e-3)
+
+
+def test_tree_algebra_vs_real_reference(gpu):
+    """add (adaptive), multiply and divergence on the device against the REAL reference (oracle/_ref): node sets identical;
+    coefficients within 1e-12 of the node norm for the linear operations, 1e-10 of the largest node norm for the product"""
+    import ref_api as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    mw, orc = gpu
+    k, prec = 5, 1e-5
+    wd = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    try:
+        rm = ref.MRA(*wd)
+    except OSError as e:
+        pytest.skip(f"oracle/_ref does not load here: {e}")
+    mra = mw.MultiResolutionAnalysis(*wd)
+    rng = np.random.default_rng(3)
+    trees = []
+    for n in (2, 3):
+        funcs = [mw.GaussFunc(b, (b / math.pi) ** 1.5 / n, tuple(rng.uniform(-1, 1, 3))) for b in 10.0 ** rng.uniform(1, 2, n)]
+        rt, gt = ref.Tree(rm), mw.FunctionTree(mra)
+        ref.project(prec, rt, funcs)
+        e = mw.GaussExp()
+        for f in funcs:
+            e.append(f)
+        mw.project(prec, gt, e, device=True)
+        trees.append((rt, gt))
+    (ra, ga), (rb, gb) = trees
+
+    def compare(R, G, tol, floor):
+        ri, gi = ref.by_index(R), ref.by_index(G)
+        assert set(ri) == set(gi)
+        nmax = max(np.linalg.norm(R["coefs"][i]) for i in ri.values())
+        worst = max(np.abs(R["coefs"][i] - G["coefs"][gi[key]]).max() / max(np.linalg.norm(R["coefs"][i]), floor * nmax) for key, i in ri.items())
+        assert worst < tol, worst
+
+    ro, go = ref.Tree(rm), mw.FunctionTree(mra)
+    ref.add(ro, [1.0, -2.0], [ra, rb], prec=1e-4)
+    mw.add(1e-4, go, [(1.0, ga), (-2.0, gb)])
+    compare(ro.export(), go.to_arrays(), COEF_TOL, 1e-3)
+    ro, go = ref.Tree(rm), mw.FunctionTree(mra)
+    ref.multiply(ro, [0.7, 1.0], [ra, rb], prec=1e-4)
+    mw.multiply(1e-4, go, [(0.7, ga), (1.0, gb)])
+    compare(ro.export(), go.to_arrays(), 1e-10, 1.0)
+    RD, GD = ref.abgv(rm, 0.5, 0.5), mw.ABGVOperator(mra, 0.5, 0.5)
+    ro, go = ref.Tree(rm), mw.FunctionTree(mra)
+    ref.divergence(ro, RD, [ra, rb, ra])
+    mw.divergence(go, GD, [(1.0, ga), (1.0, gb), (1.0, ga)])
+    compare(ro.export(), go.to_arrays(), 1e-11, 1e-3)

@@ -12,17 +12,23 @@ from test_cpp_mirror import check_drop_in_values, check_scf_values
 pytestmark = pytest.mark.gpu
 
 
-def test_drop_in_program_on_the_device(libs, tmp_path):
-    mw, orc = libs
+def _run_drop_in(tmp_path, what):
     from mrcpp_b200 import _lib
     if _lib.device() is None or _lib.device() < 0:
         pytest.fail("no CUDA device visible: the product has no CPU fallback")
     exe = cb.compile_program([os.path.join(cb.ROOT, "tests", "cpp", "apply_drop_in.cpp")], str(tmp_path / "apply_drop_in"))
-    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "0"})
+    r = cb.run_program(exe, args=["-1", what], env={"MRCPP_B200_DEVICE": "0"})
     assert r.returncode == 0, r.stderr[-2000:]
     kv = cb.key_values(r.stdout)
     assert kv["done"] == 1
-    check_drop_in_values(kv)
+    check_drop_in_values(kv, what)
+    return kv
+
+
+def test_drop_in_core_on_the_device(libs, tmp_path):
+    """the apply path through the C++ mirror: Poisson apply, hydrogen fixed point of the Helmholtz operator, ABGV derivative"""
+    mw, orc = libs
+    kv = _run_drop_in(tmp_path, "core")
     assert kv["poisson_launches"] > 0  # CUDA kernels ran inside the apply
     # same Poisson case through the Python mirror on the device
     k, prec, beta = 7, 1e-5, 100.0
@@ -37,6 +43,12 @@ def test_drop_in_program_on_the_device(libs, tmp_path):
     assert abs(kv["poisson_energy"] - en) <= 1e-12 * abs(en)
     assert abs(kv["poisson_g_sqnorm"] - gt.getSquareNorm()) <= 1e-12 * gt.getSquareNorm()
     assert abs(kv["poisson_f_integral"] - ft.integrate()) <= 1e-13 and abs(kv["poisson_g_integral"] - gt.integrate()) <= 1e-9 * abs(gt.integrate())
+
+
+def test_drop_in_algebra_on_the_device(libs, tmp_path):
+    """the callers around the apply through the C++ mirror: gradient, divergence, add (fixed grid and adaptive), multiply,
+    square, evalf"""
+    _run_drop_in(tmp_path, "algebra")
 
 
 def test_scf_cycle_on_the_device(libs, tmp_path):

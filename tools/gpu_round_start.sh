@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round, in one gpurun invocation (saves box acquisitions):
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round_start.sh r02a'
-# 1. the whole GPU suite (the tests/test_zz_gpu_*.py files were written on the CPU only in round 1: their first device run),
+# 1. the whole GPU suite (the tests/test_zz*_gpu_*.py files were written on the CPU only in round 1: their first device run),
 # 2. both bench arms at N = 1, 3. the launch list of the bench command, 4. ncu --set full of the contraction kernel and of the
 # tree-algebra kernels. Everything lands under gpurun_out/<tag>_*; copy what is to be judged into profiles/.
 tag=${1:-rXX}
@@ -10,7 +10,7 @@ mkdir -p $out
 python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.txt 2>&1
 python -m pytest tests -m gpu -q -x --durations=15 > $out/${tag}_tests.txt 2>&1
 # second pass without -x over the files that were new in round 1, so that one failure does not hide the others
-python -m pytest tests/test_zz_gpu_reference.py tests/test_zz_gpu_cpp_mirror.py tests/test_zz_gpu_tree_algebra.py -m gpu -q > $out/${tag}_tests_zz.txt 2>&1
+python -m pytest tests/test_zz1_gpu_reference.py tests/test_zz3_gpu_cpp_mirror.py tests/test_zz2_gpu_tree_algebra.py -m gpu -q > $out/${tag}_tests_zz.txt 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.txt 2>&1
 python bench.py --impl reference > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
@@ -19,6 +19,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
 ncu --set full --clock-control none --import-source on -k regex:pipe_contract -s 20 -c 3 -o $out/${tag}_contract \
     python tools/scale_probe.py 1000 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:axpy_nodes|product_values|transform8|norms_kernel" -c 24 -o $out/${tag}_algebra \
-    python -m pytest tests/test_zz_gpu_tree_algebra.py -m gpu -q -k "multiply and 7" > /dev/null 2>&1
+    python -m pytest tests/test_zz2_gpu_tree_algebra.py -m gpu -q -k "multiply and 7" > /dev/null 2>&1
 tail -3 $out/${tag}_tests.txt $out/${tag}_tests_zz.txt $out/${tag}_smoke.txt
 cat $out/${tag}_bench_n1.json
