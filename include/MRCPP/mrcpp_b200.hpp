@@ -371,6 +371,13 @@ public:
             : MWTree<D, T>(mra) {}
     ~FunctionTree() override { mrx_tree_destroy(this->h); }
     T integrate() const { return mrx_tree_integrate(this->h); }
+    /// FunctionTree::add(c, inp): in place, on this tree's grid (src/trees/FunctionTree.cpp:687-706)
+    void add(T c, FunctionTree<D, T> &inp) {
+        if (this->getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+        mrx_tree_add_inplace(this->h, c, inp.handle());
+    }
+    int getNGenNodes() const { return 0; } // generated nodes never outlive the call that made them
+    void deleteGenerated() {}
     void rescale(T c) { mrx_tree_rescale(this->h, c); }
     void normalize() {
         const double sq = this->getSquareNorm();
@@ -535,6 +542,13 @@ template <int D, typename T> void build_grid(FunctionTree<D, T> &out, const Repr
 }
 /// copy_grid / clear_grid: src/treebuilders/grid.cpp:150-166, :180-186
 template <int D, typename T> void copy_grid(FunctionTree<D, T> &out, FunctionTree<D, T> &inp) { mrx_tree_copy_grid(out.handle(), inp.handle()); }
+/// refine_grid(out, prec, absPrec) / refine_grid(out, scales): src/treebuilders/grid.cpp:271-302; returns the number of new nodes
+template <int D, typename T> int refine_grid(FunctionTree<D, T> &out, double prec, bool absPrec = false) {
+    return mrx_tree_refine_grid(out.handle(), prec, absPrec ? 1 : 0, 0);
+}
+template <int D, typename T> int refine_grid(FunctionTree<D, T> &out, int scales) {
+    return scales > 0 ? mrx_tree_refine_grid(out.handle(), -1.0, 0, scales) : 0;
+}
 /// clear_grid(out): src/treebuilders/grid.cpp:180-186
 template <int D, typename T> void clear_grid(FunctionTree<D, T> &out) { mrx_tree_clear_grid(out.handle()); }
 /// build_grid(out, tree): extend the grid of `out` with the nodes of `inp` (src/treebuilders/grid.cpp:144-153)

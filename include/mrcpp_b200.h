@@ -205,6 +205,12 @@ int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp
  * WaveletAdaptor.h:51-54). prec < 0 or max_iter == 0: same as mrx_tree_add. */
 int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec);
 
+/* refine_grid(out, prec, absPrec) (scales <= 0) / refine_grid(out, scales) (scales > 0) (src/treebuilders/grid.cpp:271-302): one
+ * pass of TreeBuilder::split over the end nodes (scales passes splitting every end node); the new children receive the
+ * reconstruction of their parent. Returns the number of new nodes. A grid without coefficients is refined on the host only. */
+int mrx_tree_refine_grid(mrx_tree *tree, double prec, int abs_prec, int scales);
+/* FunctionTree::add(c, inp) in place on the grid of `tree` (src/trees/FunctionTree.cpp:687-706) */
+int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp);
 /* multiply(prec, out, {(coefs[i], inp[i])}, max_iter, abs_prec) (src/treebuilders/multiply.cpp:104-136 with
  * MultiplicationCalculator.h:43-72 and the WaveletAdaptor, i.e. useMaxNorms = false): point-wise product of the inputs from the
  * grid `out` enters with (normally empty roots), refined where the wavelet norm of the product asks for it; prec < 0 or

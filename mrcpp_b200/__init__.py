@@ -116,6 +116,10 @@ class FunctionTree:
         _lib.load().mrx_tree_evalf(self._h, len(pts), _dp(pts), _dp(out), 1 if precise else 0)
         return float(out[0]) if np.ndim(r) == 1 else out
 
+    def add(self, c, inp):
+        """FunctionTree::add(c, inp): in place, on this tree's grid (src/trees/FunctionTree.cpp:687-706)"""
+        _lib.load().mrx_tree_add_inplace(self._h, float(c), inp._h)
+
     def integrate(self):
         """FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454)"""
         return _lib.load().mrx_tree_integrate(self._h)
@@ -307,6 +311,12 @@ def project_function(prec, out, func, finalize=True):
     quadrature through mrx_project_function; the callable is invoked from one thread."""
     cb = _FUNC3(lambda r, _u: float(func(r[0], r[1], r[2])))
     _lib.load().mrx_project_function(out._h, float(prec), C.cast(cb, C.c_void_p), None, 0, 1 if finalize else 0)
+
+
+def refine_grid(out, prec=None, absPrec=False, scales=0):
+    """refine_grid(out, prec, absPrec) or refine_grid(out, scales=n) (src/treebuilders/grid.cpp:271-302); returns the number of
+    new nodes"""
+    return _lib.load().mrx_tree_refine_grid(out._h, float(-1.0 if prec is None else prec), 1 if absPrec else 0, int(scales))
 
 
 def clear_grid(out):

@@ -365,6 +365,7 @@ int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, co
         }
     }
     build_grid<3>(tree->host, gexp, max_iter);
+    tree->host.squareNorm = -1.0; // a bare grid from here on
     tree->hostCoefsValid = true;
     tree->devValid = false;
     tree->dev.nNodes = 0;
@@ -615,10 +616,10 @@ int mrx_tree_rescale(mrx_tree *tree, double c) {
     device_rescale(*tree, c);
     return 0;
 }
-// clear_grid(out) (src/treebuilders/grid.cpp:180-186): keep the grid, drop coefficients and norms
-int mrx_tree_clear_grid(mrx_tree *tree) {
+namespace {
+// the tree is a bare grid from here on: no coefficients, no norms, nothing on the device
+void mark_grid_only(mrx_tree *tree) {
     Tree<3> &h = tree->host;
-    h.deleteGenerated();
     for (int n = 0; n < h.nReal; n++) {
         h.nodes[n].flags &= ~FlagHasCoefs;
         for (int t = 0; t < 8; t++) h.cnorm[(size_t)n * 8 + t] = -1.0;
@@ -631,16 +632,19 @@ int mrx_tree_clear_grid(mrx_tree *tree) {
     tree->dev.nGen = 0;
     tree->dev.topoNodes = -1;
     tree->dev.partial = false;
+}
+} // namespace
+
+// clear_grid(out) (src/treebuilders/grid.cpp:180-186): keep the grid, drop coefficients and norms
+int mrx_tree_clear_grid(mrx_tree *tree) {
+    tree->host.deleteGenerated();
+    mark_grid_only(tree);
     return 0;
 }
 int mrx_tree_build_grid_from(mrx_tree *out, const mrx_tree *inp) {
     if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
     out->host.extendGridFrom(inp->host);
-    out->hostCoefsValid = true;
-    out->devValid = false;
-    out->dev.nNodes = 0;
-    out->dev.topoNodes = -1;
-    out->dev.partial = false;
+    mark_grid_only(out);
     return 0;
 }
 int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {
@@ -651,6 +655,16 @@ int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs
         if (inp[i] == out) MRX_ABORT("mrx_tree_add: output tree among the inputs");
     }
     device_add(*out, n, coefs, inp, prec, max_iter, abs_prec != 0);
+    return 0;
+}
+int mrx_tree_refine_grid(mrx_tree *tree, double prec, int abs_prec, int scales) {
+    return device_refine_grid(*tree, prec, abs_prec != 0, scales);
+}
+int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp) {
+    require_device("mrx_tree_add_inplace");
+    if (!(tree->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (tree == inp) MRX_ABORT("mrx_tree_add_inplace: a tree cannot be added to itself in place (use rescale)");
+    device_add_inplace(*tree, c, *inp);
     return 0;
 }
 int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {

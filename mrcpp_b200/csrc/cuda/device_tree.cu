@@ -663,6 +663,118 @@ void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp
     h.calcSquareNorm();
 }
 
+// refine_grid(out, prec, absPrec) / refine_grid(out, scales) (src/treebuilders/grid.cpp:271-302, TreeBuilder::split
+// TreeBuilder.cpp:106-131): the host takes the split decisions from the norms it already holds; the new children get their
+// coefficients by giveChildrenCoefs(overwrite) = reconstruction of the parent into zeroed storage. Returns the new nodes.
+int device_refine_grid(mrx_tree &t, double prec, bool absPrec, int scales) {
+    Tree<3> &h = t.host;
+    // a tree carries coefficients once something has computed its norm (projection, apply, add, ...); grids from build_grid /
+    // copy_grid / clear_grid have squareNorm = -1 and nothing on the device
+    const bool hasCoefs = t.devValid || h.squareNorm >= 0.0;
+    cudaStream_t st = nullptr;
+    const double *filt = nullptr;
+    if (hasCoefs) {
+        require_device("device_refine_grid");
+        st = stream();
+        filt = device_filters(h.k);
+        if (!t.devValid) tree_upload(t);
+        h.allocCoefs = false; // the new nodes are born in HBM
+    }
+    const int maxScale = h.mra.maxScale();
+    int nNew = 0;
+    std::vector<int> work, parentPairs, slots;
+    DevBuf<int> dParents, dSlots;
+    DevBuf<double> dNormsW;
+    std::vector<double> nrm;
+    for (int pass = 0; pass < std::max(scales, 1); pass++) {
+        h.endNodeTable(work);
+        parentPairs.clear();
+        slots.clear();
+        for (int n : work) {
+            if (h.isBranch(n)) continue;
+            if (h.nodes[n].scale + 2 > maxScale) continue;
+            if (scales > 0 || split_check(h, n, prec, 1.0, absPrec)) {
+                const int c0 = h.createChildren(n, false);
+                parentPairs.push_back(n);
+                parentPairs.push_back(c0);
+                for (int k = 0; k < 8; k++) slots.push_back(c0 + k);
+            }
+        }
+        const int nW = (int)slots.size();
+        nNew += nW;
+        if (nW == 0 || !hasCoefs) continue;
+        t.dev.coefs.reserve((size_t)h.nReal * h.ncoef, true, st);
+        t.dev.norms.reserve((size_t)h.nReal * 8, true, st);
+        MRX_CUDA(cudaMemsetAsync(t.dev.coefs.p + (size_t)(h.nReal - nW) * h.ncoef, 0, sizeof(double) * (size_t)nW * h.ncoef, st));
+        dParents.reserve(parentPairs.size(), false, st);
+        dSlots.reserve(nW, false, st);
+        dNormsW.reserve((size_t)nW * 8, false, st);
+        MRX_CUDA(cudaMemcpyAsync(dParents.p, parentPairs.data(), sizeof(int) * parentPairs.size(), cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(dSlots.p, slots.data(), sizeof(int) * nW, cudaMemcpyHostToDevice, st));
+        launch_transform(true, false, t.dev.coefs.p, dParents.p, (int)parentPairs.size() / 2, h.K, filt, st);
+        launch_norms(t.dev.coefs.p, t.dev.norms.p, dSlots.p, nW, h.Kd, st, dNormsW.p);
+        nrm.resize((size_t)nW * 8);
+        MRX_CUDA(cudaMemcpyAsync(nrm.data(), dNormsW.p, sizeof(double) * nrm.size(), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < nW; i++) {
+            const int s = slots[i];
+            double sq = 0.0;
+            for (int k = 0; k < 8; k++) {
+                const double v = nrm[(size_t)i * 8 + k];
+                h.cnorm[(size_t)s * 8 + k] = v;
+                sq += v * v;
+            }
+            h.sqn[s] = sq;
+            h.nodes[s].flags |= FlagHasCoefs;
+        }
+        t.dev.nNodes = h.nReal;
+        t.hostCoefsValid = false;
+    }
+    t.dev.topoNodes = -1;
+    if (!hasCoefs && nNew > 0) { // a grid without coefficients: nothing lives on the device
+        t.devValid = false;
+        t.dev.nNodes = 0;
+        t.dev.partial = false;
+    }
+    return nNew;
+}
+
+// FunctionTree::add(c, inp) in place (src/trees/FunctionTree.cpp:687-706), in the formulation of device_add: wavelet blocks of the
+// shared nodes and root scaling blocks += c * input; every other scaling block is regenerated by TopDown(+=) from zero (the
+// tree is consistent, so that reproduces its own part and adds the input's, including where the input is coarser).
+void device_add_inplace(mrx_tree &out, double c, mrx_tree &inp) {
+    require_device("device_add_inplace");
+    if (!out.devValid) tree_upload(out);
+    if (!inp.devValid) tree_upload(inp);
+    Tree<3> &h = out.host;
+    const Tree<3> &b = inp.host;
+    cudaStream_t st = stream();
+    std::vector<int> pairs;
+    std::vector<std::pair<int, int>> stack;
+    for (int r = h.nRoots - 1; r >= 0; r--) stack.push_back({r, r});
+    while (!stack.empty()) {
+        auto pr = stack.back();
+        stack.pop_back();
+        pairs.push_back(pr.first);
+        pairs.push_back(pr.second);
+        const bool oB = h.isBranch(pr.first) && !h.isGen(h.nodes[pr.first].child0);
+        const bool iB = b.isBranch(pr.second) && !b.isGen(b.nodes[pr.second].child0);
+        if (oB && iB)
+            for (int k = 7; k >= 0; k--) stack.push_back({h.nodes[pr.first].child0 + k, b.nodes[pr.second].child0 + k});
+    }
+    DevBuf<int> dpairs;
+    dpairs.reserve(pairs.size(), false, st);
+    MRX_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(int) * pairs.size(), cudaMemcpyHostToDevice, st));
+    launch_axpy_nodes(out.dev.coefs.p, inp.dev.coefs.p, dpairs.p, (int)pairs.size() / 2, h.nRoots, h.Kd, c, st);
+    if (h.nReal > h.nRoots)
+        MRX_CUDA(cudaMemset2DAsync(out.dev.coefs.p + (size_t)h.nRoots * h.ncoef, sizeof(double) * h.ncoef, 0, sizeof(double) * h.Kd,
+                                   (size_t)(h.nReal - h.nRoots), st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    out.hostCoefsValid = false;
+    device_mw_transform(out, MRX_TOP_DOWN, /*overwrite=*/false); // + norms of every node
+    h.calcSquareNorm();
+}
+
 void device_rescale(mrx_tree &t, double c) {
     if (!t.devValid) tree_upload(t);
     cudaStream_t st = stream();

@@ -125,6 +125,8 @@ double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
 /// add(prec, out, {(c_i, inp_i)}, maxIter, absPrec) from the grid of `out` (add.cpp:41-70); prec < 0 or maxIter = 0: no refinement
 void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec = -1.0, int maxIter = 0, bool absPrec = false);
+int device_refine_grid(mrx_tree &t, double prec, bool absPrec, int scales); // refine_grid (grid.cpp:271-302), returns the new nodes
+void device_add_inplace(mrx_tree &out, double c, mrx_tree &inp);           // FunctionTree::add(c, inp) (FunctionTree.cpp:687-706)
 /// multiply(prec, out, {(c_i, inp_i)}, maxIter, absPrec) from the grid of `out` (multiply.cpp:104-136)
 void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec);
 void oper_upload(mrx_oper &o);

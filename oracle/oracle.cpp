@@ -805,6 +805,50 @@ void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std
     for (Tree<3> *t : inp) t->deleteGenerated();
 }
 
+// refine_grid(out, prec, absPrec) / refine_grid(out, scales) (src/treebuilders/grid.cpp:271-302): TreeBuilder::split
+// (TreeBuilder.cpp:106-131) -- one pass over the end nodes with the WaveletAdaptor (or `scales` passes splitting every end
+// node), coefficients handed to the new children by giveChildrenCoefs. Returns the number of new nodes.
+int refine_grid(Tree<3> &out, double prec, bool absPrec, int scales) {
+    const FilterSet &fs = filter_set(out.k);
+    const int maxScale = out.mra.maxScale();
+    int nNew = 0;
+    for (int pass = 0; pass < std::max(scales, 1); pass++) {
+        std::vector<int> work;
+        out.endNodeTable(work);
+        for (int n : work) {
+            if (out.isBranch(n)) continue;
+            if (out.nodes[n].scale + 2 > maxScale) continue;
+            if (scales > 0 || split_check(out, n, prec, 1.0, absPrec)) {
+                out.createChildren(n, false);
+                nNew += 8;
+            }
+        }
+        for (int n : work)
+            if (out.isBranch(n) && (out.nodes[n].flags & FlagHasCoefs)) give_children_coefs(out, fs, n, true);
+    }
+    return nNew;
+}
+
+// FunctionTree::add(c, inp) (src/trees/FunctionTree.cpp:687-706): in place, on the grid of `out`: every END node gets
+// c * (input node at the same index, generated where the input is coarser), then BottomUp and the square norm
+void add_inplace(Tree<3> &out, double c, Tree<3> &inp) {
+    if (!(out.mra == inp.mra)) MRX_ABORT("Incompatible MRA");
+    const FilterSet &fs = filter_set(out.k);
+    std::vector<int> work;
+    out.endNodeTable(work);
+    for (int n : work) {
+        const int m = get_node_gen(inp, fs, out.nodes[n].scale, out.nodes[n].l, nullptr);
+        const double *x = inp.coef(m);
+        double *o = out.coef(n);
+        const int nc = inp.isGen(m) ? inp.Kd : inp.ncoef;
+        for (int j = 0; j < nc; j++) o[j] += c * x[j];
+        calc_norms(out, n);
+    }
+    mw_transform_up(out);
+    calc_square_norm(out);
+    inp.deleteGenerated();
+}
+
 // <bra|ket> from compressed coefficients: scaling blocks of the roots + wavelet blocks of every node
 // present in both trees (mathematically equal to mrcpp::dot, multiply.cpp:286-318).
 double dot(const Tree<3> &bra, const Tree<3> &ket) {
@@ -875,6 +919,10 @@ void orc_mw_transform_down(void *tree, int overwrite) { orc::mw_transform_down(*
 void orc_mw_transform_up(void *tree) { orc::mw_transform_up(*static_cast<Tree<3> *>(tree)); }
 void orc_calc_square_norm(void *tree) { orc::calc_square_norm(*static_cast<Tree<3> *>(tree)); }
 double orc_dot(void *bra, void *ket) { return orc::dot(*static_cast<Tree<3> *>(bra), *static_cast<Tree<3> *>(ket)); }
+int orc_refine_grid(void *tree, double prec, int absPrec, int scales) {
+    return orc::refine_grid(*static_cast<Tree<3> *>(tree), prec, absPrec != 0, scales);
+}
+void orc_add_inplace(void *out, double c, void *inp) { orc::add_inplace(*static_cast<Tree<3> *>(out), c, *static_cast<Tree<3> *>(inp)); }
 void orc_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
     std::vector<double> c(coefs, coefs + n);
     std::vector<Tree<3> *> t(n);

@@ -128,6 +128,12 @@ void ref_multiply(double prec, void *out, int n, const double *coefs, void **inp
     for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
     multiply(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0);
 }
+int ref_refine_grid(void *t, double prec, int absPrec, int scales) {
+    auto &tree = static_cast<RefTree *>(t)->tree;
+    return scales > 0 ? refine_grid(tree, scales) : refine_grid(tree, prec, absPrec != 0);
+}
+void ref_add_inplace(void *out, double c, void *inp) { static_cast<RefTree *>(out)->tree.add(c, static_cast<RefTree *>(inp)->tree); }
+void ref_clear_grid(void *t) { clear_grid(static_cast<RefTree *>(t)->tree); }
 /// divergence(out, oper, {inp_x, inp_y, inp_z}) (src/treebuilders/apply.cpp:514-530)
 void ref_divergence(void *out, void *oper, void **inp) {
     FunctionTreeVector<3, double> vec;

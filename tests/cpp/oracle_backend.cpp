@@ -30,6 +30,8 @@ struct Oracle {
     void (*set_tables)(const char *);
     void (*add)(double, void *, int, const double *, void **, int, int);
     void (*multiply)(double, void *, int, const double *, void **, int, int);
+    int (*refine_grid)(void *, double, int, int);
+    void (*add_inplace)(void *, double, void *);
 };
 Oracle &oracle() {
     static Oracle o = [] {
@@ -49,6 +51,8 @@ Oracle &oracle() {
         r.set_tables = reinterpret_cast<decltype(r.set_tables)>(dlsym(h, "orc_set_table_path"));
         r.add = reinterpret_cast<decltype(r.add)>(dlsym(h, "orc_add"));
         r.multiply = reinterpret_cast<decltype(r.multiply)>(dlsym(h, "orc_multiply"));
+        r.refine_grid = reinterpret_cast<decltype(r.refine_grid)>(dlsym(h, "orc_refine_grid"));
+        r.add_inplace = reinterpret_cast<decltype(r.add_inplace)>(dlsym(h, "orc_add_inplace"));
         if (const char *t = std::getenv("MRX_TABLES")) r.set_tables(t);
         return r;
     }();
@@ -116,6 +120,16 @@ int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs
     for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
     oracle().add(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec);
     mrx_tree_host_modified(out);
+    return 0;
+}
+int mrx_tree_refine_grid(mrx_tree *tree, double prec, int abs_prec, int scales) {
+    const int n = oracle().refine_grid(mrx_tree_host_handle(tree), prec, abs_prec, scales);
+    mrx_tree_host_modified(tree);
+    return n;
+}
+int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp) {
+    oracle().add_inplace(mrx_tree_host_handle(tree), c, mrx_tree_host_handle(inp));
+    mrx_tree_host_modified(tree);
     return 0;
 }
 int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {

@@ -37,6 +37,9 @@ def lib():
         o.orc_calc_square_norm.argtypes = [C.c_void_p]
         o.orc_dot.argtypes = [C.c_void_p, C.c_void_p]
         o.orc_dot.restype = C.c_double
+        o.orc_refine_grid.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+        o.orc_refine_grid.restype = C.c_int
+        o.orc_add_inplace.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         o.orc_multiply.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int]
         o.orc_add.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int]
         o.orc_set_table_path(_plib.TABLES.encode())
@@ -116,6 +119,22 @@ def multiply(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False):
     c = (C.c_double * len(trees))(*[float(x) for x in coefs])
     h = (C.c_void_p * len(trees))(*[_th(t) for t in trees])
     lib().orc_multiply(float(prec), _th(out), len(trees), c, h, int(maxIter), 1 if absPrec else 0)
+    _modified(out)
+
+
+def refine_grid(tree, prec=-1.0, absPrec=False, scales=0):
+    """refine_grid(out, prec, absPrec) / refine_grid(out, scales) (src/treebuilders/grid.cpp:271-302); returns the new nodes"""
+    tree.sync_host()
+    n = lib().orc_refine_grid(_th(tree), float(prec), 1 if absPrec else 0, int(scales))
+    _modified(tree)
+    return n
+
+
+def add_inplace(out, c, inp):
+    """FunctionTree::add(c, inp) (src/trees/FunctionTree.cpp:687-706)"""
+    out.sync_host()
+    inp.sync_host()
+    lib().orc_add_inplace(_th(out), float(c), _th(inp))
     _modified(out)
 
 

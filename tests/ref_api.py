@@ -35,7 +35,8 @@ def lib():
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
             "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
-            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
+            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_refine_grid": (I, [P, D, I, I]),
+            "ref_add_inplace": (None, [P, D, P]), "ref_clear_grid": (None, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
             f = getattr(l, name)
@@ -154,6 +155,14 @@ def multiply(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False):
     c = np.ascontiguousarray(coefs, dtype=np.float64)
     h = (C.c_void_p * len(trees))(*[t._h for t in trees])
     lib().ref_multiply(float(prec), out._h, len(trees), _dp(c), h, int(maxIter), 1 if absPrec else 0)
+
+
+def refine_grid(tree, prec=-1.0, absPrec=False, scales=0):
+    return lib().ref_refine_grid(tree._h, float(prec), 1 if absPrec else 0, int(scales))
+
+
+def add_inplace(out, c, inp):
+    lib().ref_add_inplace(out._h, float(c), inp._h)
 
 
 def divergence(out, oper, trees):

@@ -60,9 +60,9 @@ def test_hot_path_call_without_device_aborts(libs, bindir):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
-@pytest.mark.parametrize("example", ["poisson", "projection", "scf"])
+@pytest.mark.parametrize("example", ["poisson", "projection", "scf", "tree_cleaner"])
 def test_reference_examples_compile_unmodified(libs, bindir, example):
-    """examples/poisson.cpp, examples/projection.cpp and examples/scf.cpp of the reference, compiled where they lie against
+    """examples/poisson.cpp, projection.cpp, scf.cpp and tree_cleaner.cpp of the reference, compiled where they lie against
     include/MRCPP/ and linked with libmrcpp_b200.so; run without a device they print their header and abort at the first
     device call"""
     exe = cb.compile_program([os.path.join(REF_EXAMPLES, example + ".cpp")], os.path.join(bindir, "ref_" + example), werror=False)
@@ -104,6 +104,19 @@ def test_reference_scf_example_on_the_oracle_backend(libs, bindir):
     assert r.returncode == 0, r.stderr
     line = [ln for ln in r.stdout.splitlines() if "Eigenvalue" in ln]
     assert line and abs(float(line[0].split()[-1]) + 0.5) < 1e-3
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
+def test_reference_tree_cleaner_example_on_the_oracle_backend(libs, bindir):
+    """the reference's examples/tree_cleaner.cpp, UNMODIFIED (fixed-grid projection, refine_grid, clear_grid until nothing splits):
+    the converged function integrates to 1 and has the norm of the projected Gaussian"""
+    exe = cb.compile_program([os.path.join(REF_EXAMPLES, "tree_cleaner.cpp"), os.path.join(CPP, "oracle_backend.cpp")],
+                             os.path.join(bindir, "ref_tree_cleaner_cpu"), werror=False)
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr
+    vals = {ln.split()[0] + " " + ln.split()[1] if ln.split()[0] == "Square" else ln.split()[0]: float(ln.split()[-1])
+            for ln in r.stdout.splitlines() if ln.strip().startswith(("Integral", "Square norm"))}
+    assert abs(vals["Integral"] - 1.0) < 1e-6 and abs(vals["Square norm"] - (100.0 / (2 * math.pi)) ** 1.5) < 1e-3
 
 
 def test_scf_program_on_the_oracle_backend(libs, bindir):

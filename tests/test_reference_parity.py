@@ -540,3 +540,23 @@ def test_config_shapes_match_reference(libs, case):
     orc.apply(prec, og, OO, of)
     same_tree(rg.export(), og.to_arrays())
     assert abs(ref.dot(rg, rf) - orc.dot(og, of)) <= 1e-12 * abs(ref.dot(rg, rf))
+
+
+@needs_ref
+def test_refine_grid_and_inplace_add_match_reference(libs):
+    """refine_grid(out, prec) and refine_grid(out, scales) (grid.cpp:271-302: TreeBuilder::split with coefficients handed to the
+    children) and FunctionTree::add(c, inp) in place (FunctionTree.cpp:687-706)"""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-3)
+    n_r, n_o = ref.refine_grid(ra, prec=1e-5), orc.refine_grid(oa, prec=1e-5)
+    assert n_r == n_o and n_r > 0 and n_r % 8 == 0
+    same_tree(ra.export(), oa.to_arrays())
+    n_r, n_o = ref.refine_grid(rb, scales=1), orc.refine_grid(ob, scales=1)
+    assert n_r == n_o and n_r > 0
+    same_tree(rb.export(), ob.to_arrays())
+    assert abs(rb.square_norm() - ob.getSquareNorm()) <= 1e-13 * rb.square_norm()
+    ref.add_inplace(ra, -0.5, rb)
+    orc.add_inplace(oa, -0.5, ob)
+    same_tree(ra.export(), oa.to_arrays())
+    assert abs(ra.square_norm() - oa.getSquareNorm()) <= 1e-13 * ra.square_norm()
+    assert ob.getNNodes() == rb.n_nodes()

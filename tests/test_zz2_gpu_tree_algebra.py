@@ -70,6 +70,26 @@ def test_add_on_grid(gpu, k, grid):
         assert abs(mw.dot(og, ga) - want) <= 1e-10 * abs(want)
 
 
+def test_refine_grid_and_inplace_add(gpu):
+    """refine_grid(out, prec) / refine_grid(out, scales) (grid.cpp:271-302) and FunctionTree::add(c, inp) in place
+    (FunctionTree.cpp:687-706) on device-resident trees vs the oracle"""
+    mw, orc = gpu
+    mra, ((ga, ca), (gb, cb)) = two_trees(mw, orc, 5, 1e-3)
+    n_g, n_c = mw.refine_grid(ga, 1e-5), orc.refine_grid(ca, prec=1e-5)
+    assert n_g == n_c and n_g > 0
+    assert_same_tree(ga, ca)
+    n_g, n_c = mw.refine_grid(gb, scales=1), orc.refine_grid(cb, scales=1)
+    assert n_g == n_c and n_g > 0
+    assert_same_tree(gb, cb)
+    assert abs(mw.dot(gb, gb) - orc.dot(cb, cb)) <= 1e-12 * orc.dot(cb, cb)
+    ga.add(-0.5, gb)
+    orc.add_inplace(ca, -0.5, cb)
+    assert_same_tree(ga, ca)
+    assert abs(ga.getSquareNorm() - ca.getSquareNorm()) <= 1e-12 * ca.getSquareNorm()
+    grid = mw.FunctionTree(mra)            # a grid without coefficients is refined on the host
+    assert mw.refine_grid(grid, scales=2) == 64 + 512 and grid.getNNodes() == 8 + 64 + 512
+
+
 def test_gradient_and_divergence(gpu):
     """gradient(D, f) and divergence(out, D, {f, g, f}) (apply.cpp:444-452, :514-530) vs the oracle; integrate() of device
     resident trees (root blocks read back from HBM) vs the oracle's host trees"""
