@@ -684,7 +684,6 @@ template <int D, typename T>
 void multiply(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp, int maxIter = -1, bool absPrec = false, bool useMaxNorms = false,
               bool conjugate = false) {
     (void)conjugate; // real trees
-    if (useMaxNorms) MRCPP_B200_ABORT("multiply: the MultiplicationAdaptor (useMaxNorms) is not on the B200 path");
     std::vector<T> c;
     std::vector<mrx_tree *> h;
     for (auto &t : inp) {
@@ -692,7 +691,7 @@ void multiply(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &in
         c.push_back(std::get<0>(t));
         h.push_back(std::get<1>(t)->handle());
     }
-    mrx_tree_multiply(prec, out.handle(), (int)h.size(), c.data(), h.data(), maxIter, absPrec ? 1 : 0);
+    mrx_tree_multiply(prec, out.handle(), (int)h.size(), c.data(), h.data(), maxIter, absPrec ? 1 : 0, useMaxNorms ? 1 : 0);
 }
 template <int D, typename T>
 void multiply(double prec, FunctionTree<D, T> &out, T c, FunctionTree<D, T> &inp_a, FunctionTree<D, T> &inp_b, int maxIter = -1, bool absPrec = false,

@@ -211,11 +211,13 @@ int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs
 int mrx_tree_refine_grid(mrx_tree *tree, double prec, int abs_prec, int scales);
 /* FunctionTree::add(c, inp) in place on the grid of `tree` (src/trees/FunctionTree.cpp:687-706) */
 int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp);
-/* multiply(prec, out, {(coefs[i], inp[i])}, max_iter, abs_prec) (src/treebuilders/multiply.cpp:104-136 with
- * MultiplicationCalculator.h:43-72 and the WaveletAdaptor, i.e. useMaxNorms = false): point-wise product of the inputs from the
- * grid `out` enters with (normally empty roots), refined where the wavelet norm of the product asks for it; prec < 0 or
+/* multiply(prec, out, {(coefs[i], inp[i])}, max_iter, abs_prec, use_max_norms) (src/treebuilders/multiply.cpp:104-136 with
+ * MultiplicationCalculator.h:43-72): point-wise product of the inputs from the grid `out` enters with (normally empty roots),
+ * refined where the wavelet norm of the product asks for it (WaveletAdaptor) or, with use_max_norms != 0 and two inputs, where the
+ * largest scaling / wavelet norms of the inputs do (makeMaxSquareNorms + MultiplicationAdaptor.h:46-66); prec < 0 or
  * max_iter == 0: no refinement. */
-int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec);
+int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec,
+                      int use_max_norms);
 
 /* residency control for measurement: host->device / device->host copies of a tree's coefficients */
 int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */

@@ -405,12 +405,12 @@ def add(prec, out, inp, maxIter=-1, absPrec=False):
     _lib.load().mrx_tree_add_adaptive(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0)
 
 
-def multiply(prec, out, inp, maxIter=-1, absPrec=False):
-    """mrcpp::multiply(prec, out, FunctionTreeVector, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136): inp = list of
-    (coef, tree); prec < 0 or maxIter = 0: no refinement of the grid `out` enters with"""
+def multiply(prec, out, inp, maxIter=-1, absPrec=False, useMaxNorms=False):
+    """mrcpp::multiply(prec, out, FunctionTreeVector, maxIter, absPrec, useMaxNorms) (src/treebuilders/multiply.cpp:104-136): inp =
+    list of (coef, tree); prec < 0 or maxIter = 0: no refinement of the grid `out` enters with"""
     c = np.ascontiguousarray([float(ci) for ci, _ in inp], dtype=np.float64)
     h = (C.c_void_p * len(inp))(*[t._h for _, t in inp])
-    _lib.load().mrx_tree_multiply(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0)
+    _lib.load().mrx_tree_multiply(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0, 1 if useMaxNorms else 0)
 
 
 def gradient(oper, inp):

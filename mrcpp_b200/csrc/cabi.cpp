@@ -667,14 +667,15 @@ int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp) {
     device_add_inplace(*tree, c, *inp);
     return 0;
 }
-int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {
+int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec,
+                      int use_max_norms) {
     require_device("mrx_tree_multiply");
     if (n <= 0) MRX_ABORT("mrx_tree_multiply: empty input vector");
     for (int i = 0; i < n; i++) {
         if (!(out->host.mra == inp[i]->host.mra)) MRX_ABORT("Incompatible MRA");
         if (inp[i] == out) MRX_ABORT("mrx_tree_multiply: output tree among the inputs");
     }
-    device_multiply(*out, n, coefs, inp, prec, max_iter, abs_prec != 0);
+    device_multiply(*out, n, coefs, inp, prec, max_iter, abs_prec != 0, use_max_norms != 0);
     return 0;
 }
 int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {

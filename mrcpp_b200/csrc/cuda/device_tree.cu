@@ -462,8 +462,9 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, dou
 //    zeroed scratch child slots (the in-node Reconstruction), values_kernel accumulates c_i * value_i into the product scratch
 //    and finally applies the Backward map, BottomUp of the scratch children gives the compressed product node, which is
 //    copied into the node store.
-void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec) {
+void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec, bool useMaxNorms) {
     require_device("device_multiply");
+    if (useMaxNorms && n != 2) MRX_ABORT("Invalid tree vec size"); // MultiplicationAdaptor.h:47
     Tree<3> &h = out.host;
     cudaStream_t st = stream();
     const int K = h.K, Kd = h.Kd, ncoef = h.ncoef;
@@ -471,6 +472,25 @@ void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp
     const int maxScale = h.mra.maxScale();
     for (int i = 0; i < n; i++)
         if (!inp[i]->devValid) tree_upload(*inp[i]);
+    // MWTree::makeMaxSquareNorms (MWTree.cpp:536-543) for the MultiplicationAdaptor: per real input node the largest scaled square
+    // norm 2^(3 n) |node|^2 (and scaled wavelet norm) among the node and its descendants, from the norms the host holds
+    std::vector<std::vector<double>> maxS(n), maxW(n);
+    if (useMaxNorms)
+        for (int i = 0; i < n; i++) {
+            const Tree<3> &b = inp[i]->host;
+            maxS[i].assign(b.nReal, 0.0);
+            maxW[i].assign(b.nReal, 0.0);
+            for (int m = b.nReal - 1; m >= 0; m--) { // children have larger slots than their parent
+                const double f = std::pow(2.0, 3 * b.nodes[m].scale);
+                maxS[i][m] = f * b.sqn[m];
+                maxW[i][m] = f * b.waveletNorm(m);
+                if (b.isBranch(m) && b.nodes[m].child0 < b.nReal)
+                    for (int k = 0; k < 8; k++) {
+                        maxS[i][m] = std::max(maxS[i][m], maxS[i][b.nodes[m].child0 + k]);
+                        maxW[i][m] = std::max(maxW[i][m], maxW[i][b.nodes[m].child0 + k]);
+                    }
+            }
+        }
     std::vector<double> hcv(K), hsw(K);
     {
         const Quadrature &q = quadrature(K);
@@ -536,7 +556,7 @@ void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp
     // scratch: per chunk node one "parent" slot and eight "child" slots, for the current input (S) and for the product (P)
     const size_t slotBytes = sizeof(double) * (size_t)ncoef;
     const int chunkCap = (int)std::max<size_t>(64, std::min<size_t>(16384, ((size_t)768 << 20) / (9 * slotBytes)));
-    DevBuf<double> S, P, dNormsW;
+    DevBuf<double> S, P, dNormsW, xNorms;
     DevBuf<int> dGather, dKids, dScale, dSlots, dParents;
     std::vector<int> work, next, parentPairs, gather, kids, scales;
     std::vector<double> nrm;
@@ -608,13 +628,48 @@ void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp
         for (int s : work) wNorm += h.waveletNorm(s);
         if (sNorm < 0.0 or wNorm < 0.0) h.squareNorm = -1.0;
         else h.squareNorm = sNorm + wNorm;
+        // MultiplicationAdaptor (MultiplicationAdaptor.h:46-66): where an input is coarser than the work node, its generated node
+        // is the scaling block of the side store: scaled square norm from the device, no wavelet part, a leaf
+        std::vector<std::vector<double>> xScal(n);
+        if (useMaxNorms && !(iter >= maxIter and maxIter >= 0)) {
+            xNorms.reserve((size_t)h.nReal * 8, false, st);
+            for (int i = 0; i < n; i++) {
+                launch_norms(X[i].p, xNorms.p, dSlots.p, nW, Kd, st, dNormsW.p);
+                xScal[i].resize((size_t)nW * 8);
+                MRX_CUDA(cudaMemcpyAsync(xScal[i].data(), dNormsW.p, sizeof(double) * xScal[i].size(), cudaMemcpyDeviceToHost, st));
+                MRX_CUDA(cudaStreamSynchronize(st));
+            }
+        }
+        auto split_max_norms = [&](int w, int s) {
+            double S[2], W[2];
+            bool leaf[2];
+            for (int i = 0; i < 2; i++) {
+                const Tree<3> &b = inp[i]->host;
+                const int m = b.findNode(h.nodes[s].scale, h.nodes[s].l);
+                const double f = std::pow(2.0, 3 * h.nodes[s].scale);
+                if (m >= 0 && m < b.nReal) {
+                    const double own = f * b.sqn[m], ownW = f * b.waveletNorm(m);
+                    S[i] = std::sqrt(maxS[i][m] > 0.0 ? maxS[i][m] : own); // MWNode::getMaxSquareNorm (MWNode.h:84)
+                    W[i] = std::sqrt(maxW[i][m] > 0.0 ? maxW[i][m] : ownW);
+                    leaf[i] = !(b.isBranch(m) && b.nodes[m].child0 < b.nReal);
+                } else {
+                    const double v = xScal[i][(size_t)w * 8];
+                    S[i] = std::sqrt(f * (v * v));
+                    W[i] = 0.0;
+                    leaf[i] = true;
+                }
+            }
+            const double multNorm = W[0] * S[1] + W[1] * S[0] + W[0] * W[1];
+            return multNorm > prec and not(leaf[0] and leaf[1]);
+        };
         next.clear();
         parentPairs.clear();
         if (iter >= maxIter and maxIter >= 0) work.clear();
-        for (int s : work) {
+        for (int w = 0; w < (int)work.size(); w++) {
+            const int s = work[w];
             if (h.isBranch(s)) continue;
             if (h.nodes[s].scale + 2 > maxScale) continue;
-            if (split_check(h, s, prec, 1.0, absPrec)) {
+            if (useMaxNorms ? split_max_norms(w, s) : split_check(h, s, prec, 1.0, absPrec)) {
                 const int c0 = h.createChildren(s, false);
                 parentPairs.push_back(s);
                 parentPairs.push_back(c0);

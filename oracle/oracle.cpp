@@ -750,7 +750,49 @@ static void cv_forward(Tree<3> &t, int n) {
 // same index (generated where the input is coarser) is reconstructed in the node and taken to function values at the
 // children's quadrature points, the values are multiplied (with the coefficients), and the product goes back through
 // cvTransform(Backward) and mwTransform(Compression) -- refined by the WaveletAdaptor; then BottomUp, square norm, cleanup.
-void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp, int maxIter, bool absPrec) {
+// MWTree::makeMaxSquareNorms (MWTree.cpp:536-543, MWNode::setMaxSquareNorm MWNode.cpp:1257-1269): per real node the largest
+// scaled square norm 2^(3 n) |node|^2 (and scaled wavelet norm) among the node and its descendants
+static void max_square_norms(const Tree<3> &t, std::vector<double> &maxS, std::vector<double> &maxW) {
+    maxS.assign(t.nReal, 0.0);
+    maxW.assign(t.nReal, 0.0);
+    for (int n = t.nReal - 1; n >= 0; n--) { // children have larger slots than their parent
+        const double f = std::pow(2.0, 3 * t.nodes[n].scale);
+        maxS[n] = f * t.sqn[n];
+        maxW[n] = f * t.waveletNorm(n);
+        if (t.isBranch(n) && t.nodes[n].child0 < t.nReal)
+            for (int k = 0; k < 8; k++) {
+                maxS[n] = std::max(maxS[n], maxS[t.nodes[n].child0 + k]);
+                maxW[n] = std::max(maxW[n], maxW[t.nodes[n].child0 + k]);
+            }
+    }
+}
+
+void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp, int maxIter, bool absPrec,
+              bool useMaxNorms) {
+    std::vector<std::vector<double>> maxS(inp.size()), maxW(inp.size());
+    if (useMaxNorms) {
+        if (inp.size() != 2) MRX_ABORT("Invalid tree vec size"); // MultiplicationAdaptor.h:47
+        for (size_t i = 0; i < inp.size(); i++) max_square_norms(*inp[i], maxS[i], maxW[i]);
+    }
+    // MultiplicationAdaptor::splitNode (MultiplicationAdaptor.h:46-66): estimate of the wavelet part of the product from the
+    // largest scaling / wavelet norms of the two inputs at and below the node
+    auto split_max_norms = [&](int n) {
+        double S[2], W[2];
+        bool leaf[2];
+        for (int i = 0; i < 2; i++) {
+            Tree<3> &t = *inp[i];
+            const int m = get_node_gen(t, filter_set(out.k), out.nodes[n].scale, out.nodes[n].l, nullptr);
+            const double f = std::pow(2.0, 3 * t.nodes[m].scale);
+            const bool real = m < t.nReal;
+            // getMaxSquareNorm / getMaxWSquareNorm (MWNode.h:84-85): the stored maximum if positive, else the node's own scaled norm
+            const double own = f * t.sqn[m], ownW = f * t.waveletNorm(m);
+            S[i] = std::sqrt(real && maxS[i][m] > 0.0 ? maxS[i][m] : own);
+            W[i] = std::sqrt(real && maxW[i][m] > 0.0 ? maxW[i][m] : ownW);
+            leaf[i] = !t.isBranch(m);
+        }
+        const double multNorm = W[0] * S[1] + W[1] * S[0] + W[0] * W[1];
+        return multNorm > prec and not(leaf[0] and leaf[1]);
+    };
     const FilterSet &fs = filter_set(out.k);
     for (Tree<3> *t : inp)
         if (!(t->mra == out.mra)) MRX_ABORT("Incompatible MRA");
@@ -792,7 +834,7 @@ void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std
         for (int n : work) {
             if (out.isBranch(n)) continue;
             if (out.nodes[n].scale + 2 > maxScale) continue;
-            if (split_check(out, n, prec, 1.0, absPrec)) {
+            if (useMaxNorms ? split_max_norms(n) : split_check(out, n, prec, 1.0, absPrec)) {
                 const int c0 = out.createChildren(n, false);
                 for (int k = 0; k < 8; k++) next.push_back(c0 + k);
             }
@@ -923,11 +965,11 @@ int orc_refine_grid(void *tree, double prec, int absPrec, int scales) {
     return orc::refine_grid(*static_cast<Tree<3> *>(tree), prec, absPrec != 0, scales);
 }
 void orc_add_inplace(void *out, double c, void *inp) { orc::add_inplace(*static_cast<Tree<3> *>(out), c, *static_cast<Tree<3> *>(inp)); }
-void orc_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
+void orc_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec, int useMaxNorms) {
     std::vector<double> c(coefs, coefs + n);
     std::vector<Tree<3> *> t(n);
     for (int i = 0; i < n; i++) t[i] = static_cast<Tree<3> *>(inp[i]);
-    orc::multiply(prec, *static_cast<Tree<3> *>(out), c, t, maxIter, absPrec != 0);
+    orc::multiply(prec, *static_cast<Tree<3> *>(out), c, t, maxIter, absPrec != 0, useMaxNorms != 0);
 }
 void orc_add(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
     std::vector<double> c(coefs, coefs + n);

@@ -123,10 +123,10 @@ void ref_add_adaptive(double prec, void *out, int n, const double *coefs, void *
     add(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0);
 }
 /// multiply(prec, out, {(c_i, inp_i)}, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136)
-void ref_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec) {
+void ref_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec, int useMaxNorms) {
     FunctionTreeVector<3, double> vec;
     for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(coefs[i], &static_cast<RefTree *>(inp[i])->tree));
-    multiply(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0);
+    multiply(prec, static_cast<RefTree *>(out)->tree, vec, maxIter, absPrec != 0, useMaxNorms != 0);
 }
 int ref_refine_grid(void *t, double prec, int absPrec, int scales) {
     auto &tree = static_cast<RefTree *>(t)->tree;

@@ -29,7 +29,7 @@ struct Oracle {
     double (*dot)(void *, void *);
     void (*set_tables)(const char *);
     void (*add)(double, void *, int, const double *, void **, int, int);
-    void (*multiply)(double, void *, int, const double *, void **, int, int);
+    void (*multiply)(double, void *, int, const double *, void **, int, int, int);
     int (*refine_grid)(void *, double, int, int);
     void (*add_inplace)(void *, double, void *);
 };
@@ -132,10 +132,11 @@ int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp) {
     mrx_tree_host_modified(tree);
     return 0;
 }
-int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec) {
+int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec,
+                      int use_max_norms) {
     std::vector<void *> h(n);
     for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
-    oracle().multiply(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec);
+    oracle().multiply(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec, use_max_norms);
     mrx_tree_host_modified(out);
     return 0;
 }

@@ -40,7 +40,7 @@ def lib():
         o.orc_refine_grid.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
         o.orc_refine_grid.restype = C.c_int
         o.orc_add_inplace.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
-        o.orc_multiply.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        o.orc_multiply.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
         o.orc_add.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int]
         o.orc_set_table_path(_plib.TABLES.encode())
         _o = o
@@ -112,13 +112,13 @@ def add(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False):
     _modified(out)
 
 
-def multiply(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False):
-    """multiply(prec, out, {(c_i, tree_i)}, maxIter, absPrec) (src/treebuilders/multiply.cpp:104-136)"""
+def multiply(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False, useMaxNorms=False):
+    """multiply(prec, out, {(c_i, tree_i)}, maxIter, absPrec, useMaxNorms) (src/treebuilders/multiply.cpp:104-136)"""
     for t in trees:
         t.sync_host()
     c = (C.c_double * len(trees))(*[float(x) for x in coefs])
     h = (C.c_void_p * len(trees))(*[_th(t) for t in trees])
-    lib().orc_multiply(float(prec), _th(out), len(trees), c, h, int(maxIter), 1 if absPrec else 0)
+    lib().orc_multiply(float(prec), _th(out), len(trees), c, h, int(maxIter), 1 if absPrec else 0, 1 if useMaxNorms else 0)
     _modified(out)
 
 

@@ -35,7 +35,7 @@ def lib():
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
             "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
-            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_refine_grid": (I, [P, D, I, I]),
+            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]),
             "ref_add_inplace": (None, [P, D, P]), "ref_clear_grid": (None, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
@@ -151,10 +151,10 @@ def add(out, coefs, trees, prec=None, maxIter=-1, absPrec=False):
         lib().ref_add_adaptive(float(prec), out._h, len(trees), _dp(c), h, int(maxIter), 1 if absPrec else 0)
 
 
-def multiply(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False):
+def multiply(out, coefs, trees, prec=-1.0, maxIter=-1, absPrec=False, useMaxNorms=False):
     c = np.ascontiguousarray(coefs, dtype=np.float64)
     h = (C.c_void_p * len(trees))(*[t._h for t in trees])
-    lib().ref_multiply(float(prec), out._h, len(trees), _dp(c), h, int(maxIter), 1 if absPrec else 0)
+    lib().ref_multiply(float(prec), out._h, len(trees), _dp(c), h, int(maxIter), 1 if absPrec else 0, 1 if useMaxNorms else 0)
 
 
 def refine_grid(tree, prec=-1.0, absPrec=False, scales=0):

@@ -60,9 +60,9 @@ def test_hot_path_call_without_device_aborts(libs, bindir):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
-@pytest.mark.parametrize("example", ["poisson", "projection", "scf", "tree_cleaner"])
+@pytest.mark.parametrize("example", ["poisson", "projection", "scf", "tree_cleaner", "multiplication"])
 def test_reference_examples_compile_unmodified(libs, bindir, example):
-    """examples/poisson.cpp, projection.cpp, scf.cpp and tree_cleaner.cpp of the reference, compiled where they lie against
+    """examples/poisson.cpp, projection.cpp, scf.cpp, tree_cleaner.cpp and multiplication.cpp of the reference, compiled where they lie against
     include/MRCPP/ and linked with libmrcpp_b200.so; run without a device they print their header and abort at the first
     device call"""
     exe = cb.compile_program([os.path.join(REF_EXAMPLES, example + ".cpp")], os.path.join(bindir, "ref_" + example), werror=False)
@@ -117,6 +117,21 @@ def test_reference_tree_cleaner_example_on_the_oracle_backend(libs, bindir):
     vals = {ln.split()[0] + " " + ln.split()[1] if ln.split()[0] == "Square" else ln.split()[0]: float(ln.split()[-1])
             for ln in r.stdout.splitlines() if ln.strip().startswith(("Integral", "Square norm"))}
     assert abs(vals["Integral"] - 1.0) < 1e-6 and abs(vals["Square norm"] - (100.0 / (2 * math.pi)) ** 1.5) < 1e-3
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="needs the reference tree (build container only)")
+def test_reference_multiplication_example_on_the_oracle_backend(libs, bindir):
+    """the reference's examples/multiplication.cpp, UNMODIFIED (adaptive product with the WaveletAdaptor and with useMaxNorms,
+    in-place subtraction of the projected analytic product): integral of the analytic product Gaussian, errors at 1e-9"""
+    exe = cb.compile_program([os.path.join(REF_EXAMPLES, "multiplication.cpp"), os.path.join(CPP, "oracle_backend.cpp")],
+                             os.path.join(bindir, "ref_multiplication_cpu"), werror=False)
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr
+    vals = {" ".join(ln.split()[:-1]): float(ln.split()[-1]) for ln in r.stdout.splitlines() if "method" in ln}
+    beta, d2 = 20.0, 0.27 ** 2
+    ana = (beta / math.pi) ** 3 * math.exp(-beta * 0.5 * d2) * (math.pi / (2 * beta)) ** 1.5
+    for m in ("1", "2"):
+        assert abs(vals["Integral method " + m] - ana) < 1e-6 * ana and vals["Square norm error method " + m] < 1e-6
 
 
 def test_scf_program_on_the_oracle_backend(libs, bindir):

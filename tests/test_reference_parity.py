@@ -560,3 +560,21 @@ def test_refine_grid_and_inplace_add_match_reference(libs):
     same_tree(ra.export(), oa.to_arrays())
     assert abs(ra.square_norm() - oa.getSquareNorm()) <= 1e-13 * ra.square_norm()
     assert ob.getNNodes() == rb.n_nodes()
+
+
+@needs_ref
+@pytest.mark.parametrize("prec,start", [(1e-4, "roots"), (1e-2, "roots"), (1e-5, "first")])
+def test_multiply_max_norms_matches_reference(libs, prec, start):
+    """multiply(prec, out, {f, g}, -1, true, useMaxNorms = true) (multiply.cpp:112-115): grid refined by the MultiplicationAdaptor
+    (MultiplicationAdaptor.h:46-66) from the largest scaling / wavelet norms of the inputs (makeMaxSquareNorms), as in the
+    second product of examples/multiplication.cpp"""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-5, box=(1.0, 1.0))
+    ro, oo = ref.Tree(rm), mw.FunctionTree(om)
+    if start == "first":
+        ref.build_grid_tree(ro, ra)
+        mw.build_grid(oo, oa)
+    ref.multiply(ro, [1.0, 1.0], [ra, rb], prec=prec, absPrec=True, useMaxNorms=True)
+    orc.multiply(oo, [1.0, 1.0], [oa, ob], prec=prec, absPrec=True, useMaxNorms=True)
+    same_tree(ro.export(), oo.to_arrays(), tol=1e-10, floor=1.0)
+    assert oo.getNNodes() > 8 and oa.getNNodes() == ra.n_nodes()

@@ -165,6 +165,32 @@ def test_multiply(gpu, k, prec, max_iter, abs_prec, start):
     assert abs(og.integrate() - oc.integrate()) <= 1e-10 * max(abs(oc.integrate()), 1e-3)
 
 
+@pytest.mark.parametrize("prec,start", [(1e-4, "roots"), (1e-5, "first")])
+def test_multiply_max_norms(gpu, prec, start):
+    """multiply(..., useMaxNorms = true) (multiply.cpp:112-115, MultiplicationAdaptor.h:46-66): the grid follows the largest scaling /
+    wavelet norms of the inputs; node set and coefficients vs the oracle"""
+    mw, orc = gpu
+    mra = world(mw, 5)
+    trees = []
+    for n, seed in ((2, 71), (3, 72)):
+        func = gaussians(n, seed, box=1.0, lo=1.0, hi=2.0)
+        g, c = mw.FunctionTree(mra), mw.FunctionTree(mra)
+        mw.project(1e-5, g, func)
+        orc.project(1e-5, c, func)
+        trees.append((g, c))
+    (ga, ca), (gb, cb) = trees
+    og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    if start == "first":
+        mw.build_grid(og, ga)
+        mw.build_grid(oc, ca)
+    mw.multiply(prec, og, [(1.0, ga), (1.0, gb)], -1, True, True)
+    orc.multiply(oc, [1.0, 1.0], [ca, cb], prec=prec, absPrec=True, useMaxNorms=True)
+    A, B = og.to_arrays(), oc.to_arrays()
+    assert A["scale"].shape == B["scale"].shape and np.array_equal(A["transl"], B["transl"]) and np.array_equal(A["child0"], B["child0"])
+    nrm = np.sqrt((B["coefs"] ** 2).sum(axis=1))
+    assert og.getNNodes() > 8 and (np.abs(A["coefs"] - B["coefs"]).max(axis=1) / nrm.max()).max() < 1e-10
+
+
 def test_tree_algebra_vs_real_reference(gpu):
     """add (adaptive), multiply and divergence on the device against the REAL reference (oracle/_ref): node sets identical;
     coefficients within 1e-12 of the node norm for the linear operations, 1e-10 of the largest node norm for the product"""
