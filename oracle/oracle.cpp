@@ -262,6 +262,7 @@ void calc_square_norm(Tree<3> &t) {
 // ConvolutionCalculator
 struct ConvCalc {
     double prec;
+    std::function<double(const Tree<3> &, int)> precFunc; // locally scaled precision (apply.cpp:222-234); empty: 1.0
     Operator *oper;
     Tree<3> *fTree;
     const FilterSet *fs;
@@ -410,7 +411,7 @@ struct ConvCalc {
         double gThrs = gTree.squareNorm;
         if (gThrs > 0.0) {
             auto nTerms = static_cast<double>(oper->size());
-            double precFac = 1.0;
+            const double precFac = precFunc ? precFunc(gTree, g) : 1.0; // ConvolutionCalculator.cpp:244
             gThrs = prec * precFac * std::sqrt(gThrs / nTerms);
         }
         const int M = oper->size();
@@ -461,7 +462,10 @@ struct ConvCalc {
 };
 
 // mrcpp::apply (apply.cpp:68-93) = calcBandWidths + TreeBuilder::build + TopDown(+=) + BottomUp + norm
-void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter, bool absPrec, ApplyStats *stats) {
+static void max_square_norms(const Tree<3> &t, std::vector<double> &maxS, std::vector<double> &maxW);
+
+void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter, bool absPrec, ApplyStats *stats,
+           const std::vector<Tree<3> *> *precTrees) {
     if (!(out.mra == inp.mra)) MRX_ABORT("Incompatible MRA");
     double t0 = now();
     ApplyStats st;
@@ -473,6 +477,32 @@ void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter,
     calc.fTree = &inp;
     calc.fs = &filter_set(inp.k);
     calc.initBandSizes();
+    // apply(prec, out, oper, inp, precTrees, ...) (apply.cpp:214-251): the precision is scaled per output node by
+    // 1 / max_i sqrt(maxSquareNorm of precTrees[i] at the node's index) -- makeMaxSquareNorms on every precision tree, getNode
+    // generating where the precision tree is coarser (a generated node answers with its own scaled square norm, MWNode.h:84)
+    std::vector<std::vector<double>> pMaxS, pMaxW;
+    std::function<double(const Tree<3> &, int)> precFunc;
+    if (precTrees) {
+        pMaxS.resize(precTrees->size());
+        pMaxW.resize(precTrees->size());
+        for (size_t i = 0; i < precTrees->size(); i++) max_square_norms(*(*precTrees)[i], pMaxS[i], pMaxW[i]);
+        precFunc = [&, precTrees](const Tree<3> &g, int n) {
+            double maxNorm = precTrees->empty() ? 1.0 : 0.0;
+            for (size_t i = 0; i < precTrees->size(); i++) {
+                Tree<3> &t = *(*precTrees)[i];
+                double v;
+#pragma omp critical(orc_prec_tree) // generation grows the node vectors of the precision tree
+                {
+                    const int m = get_node_gen(t, *calc.fs, g.nodes[n].scale, g.nodes[n].l, nullptr);
+                    const double own = std::pow(2.0, 3 * t.nodes[m].scale) * t.sqn[m];
+                    v = (m < t.nReal && pMaxS[i][m] > 0.0) ? pMaxS[i][m] : own;
+                }
+                maxNorm = std::max(maxNorm, std::sqrt(v));
+            }
+            return 1.0 / maxNorm;
+        };
+        calc.precFunc = precFunc;
+    }
 
     // TreeBuilder::build (TreeBuilder.cpp:38-86); initial work vector = all nodes of `out` (:400-405)
     std::vector<int> workVec;
@@ -521,7 +551,7 @@ void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter,
             // TreeAdaptor::splitNodeVector (TreeAdaptor.h:41-54) + WaveletAdaptor::splitNode
             if (out.isBranch(n)) continue;
             if (out.nodes[n].scale + 2 > maxScale) continue;
-            if (split_check(out, n, prec, 1.0, absPrec)) {
+            if (split_check(out, n, prec * (precFunc ? precFunc(out, n) : 1.0), 1.0, absPrec)) { // WaveletAdaptor.h:51-54
                 int c0 = out.createChildren(n, false);
                 for (int c = 0; c < 8; c++) newVec.push_back(c0 + c);
             }
@@ -536,6 +566,8 @@ void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter,
     mw_transform_up(out);
     calc_square_norm(out);
     inp.deleteGenerated();
+    if (precTrees)
+        for (Tree<3> *t : *precTrees) t->deleteGenerated();
     st.t_post = now() - tp;
     st.nNodesOut = out.size();
     st.t_total = now() - t0;
@@ -949,7 +981,16 @@ static void copy_stats(const orc::ApplyStats &s, orc_stats *o) {
 void orc_apply(double prec, void *out, void *oper, void *inp, int maxIter, int absPrec, orc_stats *stats) {
     orc::ApplyStats st;
     orc::apply(prec, *static_cast<Tree<3> *>(out), *static_cast<Operator *>(oper), *static_cast<Tree<3> *>(inp), maxIter,
-               absPrec != 0, &st);
+               absPrec != 0, &st, nullptr);
+    copy_stats(st, stats);
+}
+void orc_apply_prec_trees(double prec, void *out, void *oper, void *inp, int nPrec, void **precTrees, int maxIter, int absPrec,
+                          orc_stats *stats) {
+    orc::ApplyStats st;
+    std::vector<Tree<3> *> pt(nPrec);
+    for (int i = 0; i < nPrec; i++) pt[i] = static_cast<Tree<3> *>(precTrees[i]);
+    orc::apply(prec, *static_cast<Tree<3> *>(out), *static_cast<Operator *>(oper), *static_cast<Tree<3> *>(inp), maxIter,
+               absPrec != 0, &st, &pt);
     copy_stats(st, stats);
 }
 void orc_apply_derivative(void *out, void *oper, void *inp, int dir, orc_stats *stats) {

@@ -104,6 +104,14 @@ double ref_apply(double prec, void *out, void *oper, void *inp, int max_iter, in
     return t.elapsed();
 }
 /// mrcpp::apply(out, DerivativeOperator, inp, dir) (apply.cpp:379-412)
+/// apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (src/treebuilders/apply.cpp:214-251)
+double ref_apply_prec_trees(double prec, void *out, void *oper, void *inp, int n, void **precTrees, int maxIter, int absPrec) {
+    FunctionTreeVector<3, double> vec;
+    for (int i = 0; i < n; i++) vec.push_back(std::make_tuple(1.0, &static_cast<RefTree *>(precTrees[i])->tree));
+    apply(prec, static_cast<RefTree *>(out)->tree, *static_cast<ConvolutionOperator<3> *>(oper), static_cast<RefTree *>(inp)->tree, vec, maxIter,
+          absPrec != 0);
+    return static_cast<RefTree *>(out)->tree.getSquareNorm();
+}
 void ref_apply_derivative(void *out, void *oper, void *inp, int dir) {
     apply(static_cast<RefTree *>(out)->tree, *static_cast<DerivativeOperator<3> *>(oper), static_cast<RefTree *>(inp)->tree, dir);
 }

@@ -31,6 +31,8 @@ def lib():
         o.orc_num_threads.restype = C.c_int
         o.orc_set_num_threads.argtypes = [C.c_int]
         o.orc_apply.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcStats)]
+        o.orc_apply_prec_trees.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                           C.POINTER(OrcStats)]
         o.orc_apply_derivative.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcStats)]
         o.orc_mw_transform_down.argtypes = [C.c_void_p, C.c_int]
         o.orc_mw_transform_up.argtypes = [C.c_void_p]
@@ -67,6 +69,19 @@ def apply(prec, out, oper, inp, maxIter=-1, absPrec=False):
     st = OrcStats()
     inp.sync_host()
     lib().orc_apply(prec, _th(out), _oh(oper), _th(inp), maxIter, 1 if absPrec else 0, C.byref(st))
+    _modified(out)
+    return st
+
+
+def apply_prec_trees(prec, out, oper, inp, prec_trees, maxIter=-1, absPrec=False):
+    """apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (src/treebuilders/apply.cpp:214-251): precision scaled per node by
+    the largest norms of the precision trees. Oracle only: the device path does not build this variant yet."""
+    st = OrcStats()
+    inp.sync_host()
+    for t in prec_trees:
+        t.sync_host()
+    h = (C.c_void_p * len(prec_trees))(*[_th(t) for t in prec_trees])
+    lib().orc_apply_prec_trees(prec, _th(out), _oh(oper), _th(inp), len(prec_trees), h, maxIter, 1 if absPrec else 0, C.byref(st))
     _modified(out)
     return st
 

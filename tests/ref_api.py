@@ -35,7 +35,7 @@ def lib():
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
             "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
-            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]),
+            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]), "ref_apply_prec_trees": (D, [D, P, P, P, I, C.POINTER(P), I, I]),
             "ref_add_inplace": (None, [P, D, P]), "ref_clear_grid": (None, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
@@ -128,6 +128,11 @@ def bs(mra, order):
 
 def apply(prec, out, oper, inp, maxIter=-1, absPrec=False):
     return lib().ref_apply(float(prec), out._h, oper, inp._h, int(maxIter), 1 if absPrec else 0)
+
+
+def apply_prec_trees(prec, out, oper, inp, prec_trees, maxIter=-1, absPrec=False):
+    h = (C.c_void_p * len(prec_trees))(*[t._h for t in prec_trees])
+    return lib().ref_apply_prec_trees(float(prec), out._h, oper, inp._h, len(prec_trees), h, int(maxIter), 1 if absPrec else 0)
 
 
 def apply_derivative(out, oper, inp, d):

@@ -578,3 +578,26 @@ def test_multiply_max_norms_matches_reference(libs, prec, start):
     orc.multiply(oo, [1.0, 1.0], [oa, ob], prec=prec, absPrec=True, useMaxNorms=True)
     same_tree(ro.export(), oo.to_arrays(), tol=1e-10, floor=1.0)
     assert oo.getNNodes() > 8 and oa.getNNodes() == ra.n_nodes()
+
+
+@needs_ref
+@pytest.mark.parametrize("which", ["input", "other", "both"])
+def test_apply_with_prec_trees_matches_reference(libs, which):
+    """apply(prec, out, oper, inp, precTrees, ...) (apply.cpp:214-251): precision scaled per output node by the largest norms of the
+    precision trees (makeMaxSquareNorms; generated nodes where a precision tree is coarser than the output grid). ORACLE ONLY --
+    the device path does not build this variant; the restatement is pinned here for the round that does."""
+    mw, orc = libs
+    rm, om, ((ra, oa), (rb, ob)) = _two_trees(mw, orc, 5, 1e-4, box=(2.0, 2.0))
+    RP, OP = ref.poisson(rm, 1e-4), mw.PoissonOperator(om, 1e-4)
+    rpt = {"input": [ra], "other": [rb], "both": [ra, rb]}[which]
+    opt = {"input": [oa], "other": [ob], "both": [oa, ob]}[which]
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply_prec_trees(1e-4, rg, RP, ra, rpt)
+    st = orc.apply_prec_trees(1e-4, og, OP, oa, opt)
+    same_tree(rg.export(), og.to_arrays())
+    assert abs(rg.square_norm() - og.getSquareNorm()) <= 1e-13 * rg.square_norm()
+    # the scaled precision changes the grid with respect to the plain apply
+    plain = mw.FunctionTree(om)
+    orc.apply(1e-4, plain, OP, oa)
+    assert plain.getNNodes() != og.getNNodes() and st.fApplied > 0
+    assert oa.getNNodes() == ra.n_nodes() and ob.getNNodes() == rb.n_nodes()
