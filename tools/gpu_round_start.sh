@@ -18,6 +18,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_under_ncu.json 2>/dev/null
 ncu --set full --clock-control none --import-source on -k regex:pipe_contract -s 20 -c 3 -o $out/${tag}_contract \
     python tools/scale_probe.py 1000 > /dev/null 2>&1
+python tools/prof_algebra.py 100 7 1e-6 > $out/${tag}_algebra.txt 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:axpy_nodes|product_values|transform8|norms_kernel" -c 24 -o $out/${tag}_algebra \
     python -m pytest tests/test_zz2_gpu_tree_algebra.py -m gpu -q -k "multiply and 7" > /dev/null 2>&1
 tail -3 $out/${tag}_tests.txt $out/${tag}_tests_zz.txt $out/${tag}_smoke.txt
