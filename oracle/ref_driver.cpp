@@ -70,6 +70,9 @@ double ref_tree_evalf(void *t, const double *r, int precise) {
     auto &tree = static_cast<RefTree *>(t)->tree;
     return precise ? tree.evalf_precise(x) : tree.evalf(x);
 }
+/// FunctionTree::saveTreeTXT / loadTreeTXT (src/trees/FunctionTree.cpp:240-372): the text interchange format
+void ref_tree_save_txt(void *t, const char *path) { static_cast<RefTree *>(t)->tree.saveTreeTXT(path); }
+void ref_tree_load_txt(void *t, const char *path) { static_cast<RefTree *>(t)->tree.loadTreeTXT(path); }
 double ref_tree_integrate(void *t) { return static_cast<RefTree *>(t)->tree.integrate(); }
 /// build_grid alone (src/treebuilders/grid.cpp:106-123)
 void ref_build_grid_gaussians(void *t, int n, const double *coef, const double *alpha, const double *pos, const int *power) {

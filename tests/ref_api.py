@@ -34,7 +34,7 @@ def lib():
             "ref_apply": (D, [D, P, P, P, I, I]), "ref_apply_derivative": (None, [P, P, P, I]), "ref_dot": (D, [P, P]),
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
-            "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
+            "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_save_txt": (None, [P, C.c_char_p]), "ref_tree_load_txt": (None, [P, C.c_char_p]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
             "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]), "ref_apply_prec_trees": (D, [D, P, P, P, I, C.POINTER(P), I, I]),
             "ref_add_inplace": (None, [P, D, P]), "ref_clear_grid": (None, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
@@ -74,6 +74,12 @@ class Tree:
 
     def integrate(self):
         return lib().ref_tree_integrate(self._h)
+
+    def save_txt(self, path):
+        lib().ref_tree_save_txt(self._h, str(path).encode())
+
+    def load_txt(self, path):
+        lib().ref_tree_load_txt(self._h, str(path).encode())
 
     def evalf(self, r, precise=False):
         x = np.ascontiguousarray(r, dtype=np.float64)

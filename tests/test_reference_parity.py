@@ -601,3 +601,36 @@ def test_apply_with_prec_trees_matches_reference(libs, which):
     orc.apply(1e-4, plain, OP, oa)
     assert plain.getNNodes() != og.getNNodes() and st.fApplied > 0
     assert oa.getNNodes() == ra.n_nodes() and ob.getNNodes() == rb.n_nodes()
+
+
+@needs_ref
+def test_text_tree_format_against_reference(libs, tmp_path):
+    """mrcpp_b200/treetxt.py against the reference's own FunctionTree::saveTreeTXT / loadTreeTXT (FunctionTree.cpp:240-372): the file
+    the reference writes holds the values our reader expects, and the file our writer produces is read back by the reference
+    into the tree it came from"""
+    mw, orc = libs
+    from mrcpp_b200 import treetxt
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 2, 11)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    theirs, ours = str(tmp_path / "ref.txt"), str(tmp_path / "ours.txt")
+    rf.save_txt(theirs)
+    treetxt.save_tree_txt(of, ours)
+    Kr, R = treetxt.load_tree_txt(theirs)
+    Ko, O = treetxt.load_tree_txt(ours)
+    assert Kr == Ko == k + 1 and set(R) == set(O)
+    peak = max(np.abs(v).max() for v in R.values())
+    assert max(np.abs(R[key] - O[key]).max() for key in R) < 1e-12 * peak
+    # the reference reads our file
+    back = ref.Tree(rm)
+    back.load_txt(ours)
+    B, A = back.export(), of.to_arrays()
+    bi, ai = ref.by_index(B), ref.by_index(A)
+    assert set(bi) == set(ai)
+    nmax = np.sqrt((A["coefs"] ** 2).sum(axis=1)).max()
+    assert max(np.abs(B["coefs"][i] - A["coefs"][ai[key]]).max() for key, i in bi.items()) < 1e-11 * nmax
+    assert abs(back.square_norm() - of.getSquareNorm()) < 1e-11 * of.getSquareNorm()
