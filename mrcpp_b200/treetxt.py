@@ -7,6 +7,9 @@ index order. Host-side numpy only (nothing here is on the hot path): it works fr
 
     save_tree_txt(tree, "f.txt")            # a file MRCPP's loadTreeTXT / MADNESS can read
     blocks = load_tree_txt("f.txt")         # {(scale, lx, ly, lz): values[K, K, K] (x index fastest, MRCPP order)}
+    k, rscale, arrays = tree_arrays_from_txt("f.txt")   # -> FunctionTree.from_arrays(mra, *arrays), then mwTransform(BottomUp)
+
+Pinned against the reference's own saveTreeTXT / loadTreeTXT in tests/test_reference_parity.py.
 """
 import os
 import struct
@@ -115,3 +118,65 @@ def load_tree_txt(fname):
         shift = int(round(2.0 ** scale * L))
         blocks[(scale, lm[0] - shift, lm[1] - shift, lm[2] - shift)] = vals[inv].reshape(K, K, K)
     return K, blocks
+
+
+def node_coefs_from_child_values(vals, k, scale):
+    """inverse of child_values: the 8 (s, d) blocks of a node at `scale` from the values at the quadrature points of its 8 children
+    (MWNode::cvTransform(Backward) then MWNode::mwTransform(Compression), MWNode.cpp:448-594)"""
+    K = k + 1
+    H0, G0, H1, G1 = _filters(k)
+    X = np.empty((2, 2, K, K))
+    X[0, 0], X[1, 0], X[0, 1], X[1, 1] = H0, G0, H1, G1
+    _, w = _quadrature(K)
+    sw = np.sqrt(w)
+    s = np.asarray(vals, dtype=np.float64).reshape(2, 2, 2, K, K, K)  # [bz, by, bx, jz, jy, jx]
+    s = s * (sw[:, None, None] * sw[None, :, None] * sw[None, None, :]) * 2.0 ** (-1.5 * (scale + 1))
+    # the two-scale filter matrix is orthogonal: compression is the transpose of the reconstruction of child_values
+    out = np.einsum("fhglmn,afil->ahgimn", s, X)    # z
+    out = np.einsum("ahgimn,bhjm->abgijn", out, X)  # y
+    out = np.einsum("abgijn,cgkn->abcijk", out, X)  # x -> [tz, ty, tx, iz, iy, ix]
+    return out.reshape(8 * K ** 3)
+
+
+def tree_arrays_from_txt(fname, corner=(-1, -1, -1), boxes=(2, 2, 2)):
+    """Arrays for FunctionTree.from_arrays (scale, transl, parent, child0, coefs in slot order) of the tree a saveTreeTXT file
+    describes: the end nodes are the parents of the eight-block groups of the file; branch nodes carry zeros and are filled by the
+    mwTransform(BottomUp) the caller runs afterwards, like FunctionTree::loadTreeTXT does (FunctionTree.cpp:240-305). Files
+    written by MRCPP itself (complete sibling groups)."""
+    K, blocks = load_tree_txt(fname)
+    k = K - 1
+    ends = {}
+    for (scale, lx, ly, lz), v in blocks.items():
+        key = (scale - 1, lx >> 1, ly >> 1, lz >> 1)
+        ends.setdefault(key, np.zeros((8, K, K, K)))[(lx & 1) | ((ly & 1) << 1) | ((lz & 1) << 2)] = v
+    rscale = min(key[0] for key in ends)
+    while any(not (corner[d] <= (key[1 + d] >> (key[0] - rscale)) < corner[d] + boxes[d]) for key in ends for d in range(3)):
+        rscale -= 1  # (only if the file has no end node at the root scale and the guess was too fine)
+    branches = set()
+    for (s, lx, ly, lz) in ends:
+        while s > rscale:
+            s, lx, ly, lz = s - 1, lx >> 1, ly >> 1, lz >> 1
+            branches.add((s, lx, ly, lz))
+    scale, transl, parent, child0 = [], [], [], []
+    for r in range(boxes[0] * boxes[1] * boxes[2]):  # roots in box order, x fastest
+        scale.append(rscale)
+        transl.append((corner[0] + r % boxes[0], corner[1] + (r // boxes[0]) % boxes[1], corner[2] + r // (boxes[0] * boxes[1])))
+        parent.append(-1)
+        child0.append(-1)
+    n = 0
+    while n < len(scale):  # children of every branch node, appended in creation order
+        key = (scale[n], *transl[n])
+        if key in branches:
+            child0[n] = len(scale)
+            for c in range(8):
+                scale.append(scale[n] + 1)
+                transl.append(tuple(2 * transl[n][d] + ((c >> d) & 1) for d in range(3)))
+                parent.append(n)
+                child0.append(-1)
+        n += 1
+    coefs = np.zeros((len(scale), 8 * K ** 3))
+    for i in range(len(scale)):
+        key = (scale[i], *transl[i])
+        if key in ends:
+            coefs[i] = node_coefs_from_child_values(ends[key], k, scale[i])
+    return k, rscale, (np.array(scale, np.int32), np.array(transl, np.int32), np.array(parent, np.int32), np.array(child0, np.int32), coefs)

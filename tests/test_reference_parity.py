@@ -634,3 +634,30 @@ def test_text_tree_format_against_reference(libs, tmp_path):
     nmax = np.sqrt((A["coefs"] ** 2).sum(axis=1)).max()
     assert max(np.abs(B["coefs"][i] - A["coefs"][ai[key]]).max() for key, i in bi.items()) < 1e-11 * nmax
     assert abs(back.square_norm() - of.getSquareNorm()) < 1e-11 * of.getSquareNorm()
+
+
+@needs_ref
+def test_tree_from_reference_text_file(libs, tmp_path):
+    """a file written by the reference's saveTreeTXT becomes a tree here (treetxt.tree_arrays_from_txt + BottomUp) with the node
+    set and coefficients of the tree the reference wrote it from; the applied potential of that tree equals the reference's"""
+    mw, orc = libs
+    from mrcpp_b200 import treetxt
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 2, 11)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf = ref.Tree(rm)
+    ref.project(prec, rf, funcs)
+    path = str(tmp_path / "ref.txt")
+    rf.save_txt(path)
+    kk, rscale, arrays = treetxt.tree_arrays_from_txt(path)
+    assert (kk, rscale) == (k, -4)
+    of = mw.FunctionTree.from_arrays(om, *arrays)
+    orc.mw_transform_up(of)
+    orc.calc_square_norm(of)
+    same_tree(rf.export(), of.to_arrays(), tol=1e-11)     # 14 significant digits in the file
+    RP, OP = ref.poisson(rm, prec), mw.PoissonOperator(om, prec)
+    rg, og = ref.Tree(rm), mw.FunctionTree(om)
+    ref.apply(prec, rg, RP, rf)
+    orc.apply(prec, og, OP, of)
+    same_tree(rg.export(), og.to_arrays(), tol=1e-10)
