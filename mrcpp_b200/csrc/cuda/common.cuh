@@ -17,6 +17,7 @@
         }                                                                                                \
     } while (0)
 
+#ifdef __CUDACC__ // device helpers: only where the CUDA compiler reads this header (the host drivers also build without it, for the CPU mock of tests/cpp/cuda_mock)
 namespace mrx {
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe (SASS: DMMA.8x8x4).
@@ -71,3 +72,4 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 }
 
 } // namespace mrx
+#endif // __CUDACC__

@@ -1,0 +1,168 @@
+// TEST INFRASTRUCTURE (see cuda_runtime.h in this directory): host stand-ins for the kernels the host drivers of
+// csrc/cuda/device_tree.cu launch, and for the engine entry points that live in other .cu files (apply, projection, sharding,
+// micro-benchmarks). The transform stand-ins use the CPU oracle's restatement of tree_utils::mw_transform(_back) (oracle.cpp is
+// included into this translation unit); apply and projection are served by the oracle as a whole. What is exercised for real
+// is the driver code: buffer sizes, slot arithmetic, pair lists, residency flags, the refinement loops of add / multiply /
+// refine_grid.
+#include "../../../oracle/oracle.cpp"
+
+#include "../../../mrcpp_b200/csrc/engine.hpp"
+#include "../../../mrcpp_b200/csrc/cuda/kernels.cuh"
+
+namespace mrx {
+
+void launch_norms(const double *coefs, double *norms, const int *slots, int n, int Kd, cudaStream_t, double *normsW) {
+    for (int i = 0; i < n; i++) {
+        const int node = slots ? slots[i] : i;
+        for (int w = 0; w < 8; w++) {
+            const double *b = coefs + ((size_t)node * 8 + w) * Kd;
+            double s = 0.0;
+            for (int e = 0; e < Kd; e++) s += b[e] * b[e];
+            norms[(size_t)node * 8 + w] = std::sqrt(s);
+            if (normsW) normsW[(size_t)i * 8 + w] = std::sqrt(s);
+        }
+    }
+    launch_counter()++;
+}
+
+bool transform_fuses_norms(int) { return false; }
+
+void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs, int cnt, int K, const double *, cudaStream_t, double *) {
+    const FilterSet &fs = filter_set(K - 1);
+    const int Kd = K * K * K, ncoef = 8 * Kd;
+    for (int p = 0; p < cnt; p++) {
+        double *parent = coefs + (size_t)pairs[2 * p] * ncoef;
+        double *child0 = coefs + (size_t)pairs[2 * p + 1] * ncoef;
+        if (down) {
+            if (overwrite) std::memset(child0, 0, sizeof(double) * 8 * ncoef); // giveChildrenCoefs(overwrite) zeroes the children
+            orc::mw_transform3(fs, K, parent, child0, false, ncoef, overwrite);
+        } else {
+            std::vector<double> in((size_t)8 * Kd);
+            for (int c = 0; c < 8; c++) std::memcpy(in.data() + (size_t)c * Kd, child0 + (size_t)c * ncoef, sizeof(double) * Kd);
+            orc::mw_transform_back3(fs, K, in.data(), parent, Kd);
+        }
+    }
+    launch_counter()++;
+}
+
+void launch_compress_nodes(double *, const int *, int, int, const double *, cudaStream_t, double *) { MRX_ABORT("mock: launch_compress_nodes"); }
+void launch_project_eval(double *, const int *, const int4 *, int, int, const GaussTable &, const double *, const double *, cudaStream_t) {
+    MRX_ABORT("mock: launch_project_eval");
+}
+void launch_gen_children(const double *, double *, double *, int, const int *, int, int, const double *, cudaStream_t) {
+    MRX_ABORT("mock: launch_gen_children");
+}
+void launch_reduce_partials(double *, const double *, const int *, int, int, cudaStream_t) { MRX_ABORT("mock: launch_reduce_partials"); }
+
+void launch_dot(const double *a, const double *b, const int *pairs, double *res, int np, int nRoots, int Kd, cudaStream_t) {
+    for (int p = 0; p < np; p++) {
+        const double *x = a + (size_t)pairs[2 * p] * 8 * Kd, *y = b + (size_t)pairs[2 * p + 1] * 8 * Kd;
+        double s = 0.0;
+        for (int j = (pairs[2 * p] < nRoots ? 0 : Kd); j < 8 * Kd; j++) s += x[j] * y[j]; // scaling blocks of the roots + every wavelet block
+        res[p] = s;
+    }
+    launch_counter()++;
+}
+
+void launch_scale(double *x, size_t n, double c, cudaStream_t) {
+    for (size_t i = 0; i < n; i++) x[i] *= c;
+    launch_counter()++;
+}
+
+void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t) {
+    for (int p = 0; p < np; p++) {
+        const int o = pairs[2 * p], i = pairs[2 * p + 1];
+        double *po = out + (size_t)o * 8 * Kd;
+        const double *pi = in + (size_t)i * 8 * Kd;
+        for (int j = (o < nRoots ? 0 : Kd); j < 8 * Kd; j++) po[j] += c * pi[j];
+    }
+    launch_counter()++;
+}
+
+void launch_product_values(double *P, const double *S, const int *scale, int nC, int K, const double *map, double c, int mode, cudaStream_t) {
+    const int Kd = K * K * K;
+    for (int j = 0; j < nC; j++)
+        for (int t = 0; t < 8; t++) {
+            const size_t off = ((size_t)(nC + 8 * j + t) * 8) * Kd;
+            const int np1 = scale[j] + 1;
+            const double two_fac = mode == 2 ? std::sqrt(1.0 / std::exp2((double)(3 * np1))) : std::sqrt(std::exp2((double)(3 * np1)));
+            for (int q = 0; q < Kd; q++) {
+                const int x = q % K, y = (q / K) % K, z = q / (K * K);
+                if (mode == 2) {
+                    P[off + q] = two_fac * (((P[off + q] * map[x]) * map[y]) * map[z]);
+                } else {
+                    const double v = c * (two_fac * (((S[off + q] * map[x]) * map[y]) * map[z]));
+                    P[off + q] = mode == 0 ? v : P[off + q] * v;
+                }
+            }
+        }
+    launch_counter()++;
+}
+
+// ---- engine entry points of the other .cu files, served by the oracle on the host copies
+static void to_host(mrx_tree &t) {
+    if (!t.hostCoefsValid) tree_download(t);
+}
+static void host_result(mrx_tree &t) { // the host copy is the current one, nothing valid on the "device"
+    t.hostCoefsValid = true;
+    t.devValid = false;
+    t.dev.nNodes = 0;
+    t.dev.nGen = 0;
+    t.dev.topoNodes = -1;
+    t.dev.partial = false;
+}
+static void host_storage(mrx_tree &t) {
+    t.host.allocCoefs = true;
+    t.host.ensureCoefStorage();
+}
+static void fill_stats(const orc::ApplyStats &st, mrx_apply_stats *stats) {
+    if (!stats) return;
+    std::memset(stats, 0, sizeof(*stats));
+    stats->g_nodes = st.gNodes;
+    stats->f_applied = st.fApplied;
+    stats->f_applied_rank = st.fApplied;
+    stats->gen_nodes = st.genUsed;
+    stats->iterations = st.iters;
+    stats->n_nodes_out = st.nNodesOut;
+}
+void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, mrx_apply_stats *stats, const mrx_comm *) {
+    to_host(inp);
+    host_storage(out);
+    orc::ApplyStats st;
+    orc::apply(prec, out.host, oper.op, inp.host, maxIter, absPrec, &st, nullptr);
+    host_result(out);
+    fill_stats(st, stats);
+}
+void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int dir, mrx_apply_stats *stats) {
+    to_host(inp);
+    host_storage(out);
+    orc::ApplyStats st;
+    orc::apply_derivative(out.host, oper.op, inp.host, dir, &st);
+    host_result(out);
+    fill_stats(st, stats);
+}
+void device_project_gaussians(mrx_tree &t, double prec, const GaussExp<3> &gexp, int maxIter, bool absPrec) {
+    host_storage(t);
+    project_gaussians<3>(prec, t.host, gexp, maxIter, absPrec, /*finalize=*/false);
+    orc::mw_transform_up(t.host);
+    orc::calc_square_norm(t.host);
+    host_result(t);
+}
+int comm_rank(const mrx_comm *) { return 0; }
+int comm_world(const mrx_comm *) { return 1; }
+
+} // namespace mrx
+
+extern "C" {
+int mrx_comm_unique_id(char *) { MRX_ABORT("mock: no communicator"); }
+mrx_comm *mrx_comm_create(int, int, const char *) { MRX_ABORT("mock: no communicator"); }
+void mrx_comm_destroy(mrx_comm *) {}
+int mrx_comm_rank(const mrx_comm *) { return 0; }
+int mrx_comm_size(const mrx_comm *) { return 1; }
+void mrx_shard_partition(const long long *, int, int, int *) { MRX_ABORT("mock: sharding"); }
+void mrx_shard_cyclic(int, int, int, int *, int *) { MRX_ABORT("mock: sharding"); }
+int mrx_shard_cyclic_row(int, int, int) { MRX_ABORT("mock: sharding"); }
+double mrx_bench_dmma_tflops(int) { return 0.0; }
+double mrx_bench_dfma_tflops(int) { return 0.0; }
+double mrx_bench_hbm_gbs(long long, int) { return 0.0; }
+}

@@ -36,3 +36,34 @@ def key_values(stdout):
             except ValueError:
                 pass
     return out
+
+
+MOCK_DIR = os.path.join(ROOT, "tests", "_mock")
+MOCK_LIB = os.path.join(MOCK_DIR, "libmrcpp_b200_mock.so")
+
+
+def build_mock_lib():
+    """libmrcpp_b200_mock.so: the product's HOST code (C ABI, host data model, the host drivers of csrc/cuda/device_tree.cu)
+    compiled with g++ against the host-memory CUDA stand-in of tests/cpp/cuda_mock, kernels replaced by host functions. TEST
+    INFRASTRUCTURE: lets the driver logic of the tree algebra run where no GPU exists."""
+    csrc = os.path.join(ROOT, "mrcpp_b200", "csrc")
+    mock = os.path.join(ROOT, "tests", "cpp", "cuda_mock")
+    srcs = [os.path.join(csrc, "cabi.cpp"), os.path.join(csrc, "host", "tables.cpp"), os.path.join(csrc, "host", "tree.cpp"),
+            os.path.join(csrc, "host", "operators.cpp"), os.path.join(csrc, "cuda", "device_tree.cu"), os.path.join(mock, "mock_kernels.cpp")]
+    deps = srcs + [os.path.join(mock, "cuda_runtime.h"), os.path.join(csrc, "engine.hpp"), os.path.join(csrc, "host", "mrx_host.hpp"),
+                   os.path.join(ROOT, "oracle", "oracle.cpp"), os.path.join(ROOT, "include", "mrcpp_b200.h")]
+    if os.path.exists(MOCK_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(MOCK_LIB) for d in deps):
+        return MOCK_LIB
+    os.makedirs(MOCK_DIR, exist_ok=True)
+    objs, procs = [], []
+    for src in srcs:
+        obj = os.path.join(MOCK_DIR, os.path.basename(src) + ".o")
+        objs.append(obj)
+        cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-w", "-I" + mock, "-x", "c++", "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        assert p.returncode == 0, f"{src}:\n{out}"
+    r = subprocess.run(["g++", "-shared", "-fopenmp", "-o", MOCK_LIB] + objs + ["-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return MOCK_LIB
