@@ -69,33 +69,40 @@ void launch_scale(double *x, size_t n, double c, cudaStream_t) {
     launch_counter()++;
 }
 
+// The element-wise kernels of the tree algebra are executed from their REAL source: cpp_build.build_mock_lib() cuts the two
+// __global__ functions out of csrc/cuda/kernels.cu into extracted_kernels.inc; with blockIdx / threadIdx as plain variables the
+// launchers below run them block by block, thread by thread (no cross-thread communication in either kernel).
+namespace simt {
+struct Idx {
+    int x = 0, y = 0, z = 0;
+};
+static Idx blockIdx, threadIdx;
+#define __global__
+#define __launch_bounds__(...)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+using std::exp2;
+using std::sqrt;
+#include "extracted_kernels.inc"
+#undef __global__
+#undef __launch_bounds__
+template <typename F> void run(int blocks, int threads, F kernel) {
+    for (int b = 0; b < blocks; b++)
+        for (int t = 0; t < threads; t++) {
+            blockIdx.x = b;
+            threadIdx.x = t;
+            kernel();
+        }
+}
+} // namespace simt
+
 void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t) {
-    for (int p = 0; p < np; p++) {
-        const int o = pairs[2 * p], i = pairs[2 * p + 1];
-        double *po = out + (size_t)o * 8 * Kd;
-        const double *pi = in + (size_t)i * 8 * Kd;
-        for (int j = (o < nRoots ? 0 : Kd); j < 8 * Kd; j++) po[j] += c * pi[j];
-    }
+    simt::run(np, 256, [&] { simt::axpy_nodes_kernel(out, in, pairs, nRoots, Kd, c); });
     launch_counter()++;
 }
 
 void launch_product_values(double *P, const double *S, const int *scale, int nC, int K, const double *map, double c, int mode, cudaStream_t) {
-    const int Kd = K * K * K;
-    for (int j = 0; j < nC; j++)
-        for (int t = 0; t < 8; t++) {
-            const size_t off = ((size_t)(nC + 8 * j + t) * 8) * Kd;
-            const int np1 = scale[j] + 1;
-            const double two_fac = mode == 2 ? std::sqrt(1.0 / std::exp2((double)(3 * np1))) : std::sqrt(std::exp2((double)(3 * np1)));
-            for (int q = 0; q < Kd; q++) {
-                const int x = q % K, y = (q / K) % K, z = q / (K * K);
-                if (mode == 2) {
-                    P[off + q] = two_fac * (((P[off + q] * map[x]) * map[y]) * map[z]);
-                } else {
-                    const double v = c * (two_fac * (((S[off + q] * map[x]) * map[y]) * map[z]));
-                    P[off + q] = mode == 0 ? v : P[off + q] * v;
-                }
-            }
-        }
+    simt::run(8 * nC, 256, [&] { simt::product_values_kernel(P, S, scale, nC, K, map, c, mode); });
     launch_counter()++;
 }
 

@@ -50,16 +50,24 @@ def build_mock_lib():
     mock = os.path.join(ROOT, "tests", "cpp", "cuda_mock")
     srcs = [os.path.join(csrc, "cabi.cpp"), os.path.join(csrc, "host", "tables.cpp"), os.path.join(csrc, "host", "tree.cpp"),
             os.path.join(csrc, "host", "operators.cpp"), os.path.join(csrc, "cuda", "device_tree.cu"), os.path.join(mock, "mock_kernels.cpp")]
-    deps = srcs + [os.path.join(mock, "cuda_runtime.h"), os.path.join(csrc, "engine.hpp"), os.path.join(csrc, "host", "mrx_host.hpp"),
+    deps = srcs + [os.path.join(csrc, "cuda", "kernels.cu"), os.path.join(mock, "cuda_runtime.h"), os.path.join(csrc, "engine.hpp"), os.path.join(csrc, "host", "mrx_host.hpp"),
                    os.path.join(ROOT, "oracle", "oracle.cpp"), os.path.join(ROOT, "include", "mrcpp_b200.h")]
     if os.path.exists(MOCK_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(MOCK_LIB) for d in deps):
         return MOCK_LIB
     os.makedirs(MOCK_DIR, exist_ok=True)
+    # the element-wise kernels of the tree algebra have no cross-thread communication: their SOURCE is cut out of kernels.cu and
+    # compiled for the host, where mock_kernels.cpp runs it block by block, thread by thread (blockIdx / threadIdx as variables)
+    ksrc = open(os.path.join(csrc, "cuda", "kernels.cu")).read()
+    with open(os.path.join(MOCK_DIR, "extracted_kernels.inc"), "w") as f:
+        for name in ("axpy_nodes_kernel", "product_values_kernel"):
+            start = ksrc.index("__global__ void __launch_bounds__(256) " + name)
+            end = ksrc.index("\n}\n", start) + 3
+            f.write(ksrc[start:end] + "\n")
     objs, procs = [], []
     for src in srcs:
         obj = os.path.join(MOCK_DIR, os.path.basename(src) + ".o")
         objs.append(obj)
-        cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-w", "-I" + mock, "-x", "c++", "-c", src, "-o", obj]
+        cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-w", "-I" + mock, "-I" + MOCK_DIR, "-x", "c++", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
