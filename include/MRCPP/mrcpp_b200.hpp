@@ -709,6 +709,23 @@ template <int D, typename T> void square(double prec, FunctionTree<D, T> &out, F
     multiply(prec, out, v, maxIter, absPrec);
 }
 
+/// mrcpp::dot(prec, out, inp_a, inp_b, maxIter, absPrec): src/treebuilders/multiply.cpp:253-271 -- out = sum_d a_d b_d f_d g_d, every
+/// product on the grid of `out` refined with the MultiplicationAdaptor (useMaxNorms), the sum on the union of the product grids
+template <int D, typename T>
+void dot(double prec, FunctionTree<D, T> &out, FunctionTreeVector<D, T> &inp_a, FunctionTreeVector<D, T> &inp_b, int maxIter = -1, bool absPrec = false) {
+    if (inp_a.size() != inp_b.size()) MRCPP_B200_ABORT("Input length mismatch");
+    FunctionTreeVector<D, T> tmp_vec;
+    for (size_t d = 0; d < inp_a.size(); d++) {
+        auto *out_d = new FunctionTree<D, T>(out.getMRA());
+        build_grid(*out_d, out);
+        multiply(prec, *out_d, T(1.0), get_func(inp_a, (int)d), get_func(inp_b, (int)d), maxIter, absPrec, true);
+        tmp_vec.push_back(std::make_tuple(get_coef(inp_a, (int)d) * get_coef(inp_b, (int)d), out_d));
+    }
+    build_grid(out, tmp_vec);
+    add(-1.0, out, tmp_vec, 0);
+    clear(tmp_vec, true);
+}
+
 /// mrcpp::gradient(oper, inp): src/treebuilders/apply.cpp:444-452 (the caller owns the trees: clear(vec, true))
 template <int D, typename T> FunctionTreeVector<D, T> gradient(DerivativeOperator<D> &oper, FunctionTree<D, T> &inp) {
     FunctionTreeVector<D, T> out;

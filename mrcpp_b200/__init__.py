@@ -413,6 +413,21 @@ def multiply(prec, out, inp, maxIter=-1, absPrec=False, useMaxNorms=False):
     _lib.load().mrx_tree_multiply(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0, 1 if useMaxNorms else 0)
 
 
+def dot_vectors(prec, out, inp_a, inp_b, maxIter=-1, absPrec=False):
+    """mrcpp::dot(prec, out, FunctionTreeVector, FunctionTreeVector) (src/treebuilders/multiply.cpp:253-271): out = sum_d a_d b_d f_d g_d"""
+    if len(inp_a) != len(inp_b):
+        raise ValueError("Input length mismatch")
+    parts = []
+    for (ca, ta), (cb, tb) in zip(inp_a, inp_b):
+        p = FunctionTree(out.mra)
+        build_grid(p, out)
+        multiply(prec, p, [(1.0, ta), (1.0, tb)], maxIter, absPrec, True)
+        parts.append((ca * cb, p))
+    for _, p in parts:
+        build_grid(out, p)
+    add(-1.0, out, parts, 0)
+
+
 def gradient(oper, inp):
     """mrcpp::gradient(D, f) (src/treebuilders/apply.cpp:444-452): [(1.0, df/dx), (1.0, df/dy), (1.0, df/dz)]"""
     out = []

@@ -203,6 +203,15 @@ static void multiplication_case() {
                 std::abs(h_tree.evalf_precise(r) - prod.evalf(r)) / prod.evalf(r));
     // <f | f> = integral of f^2
     std::printf("square_integral %.17g\nsquare_expected %.17g\n", sq_tree.integrate(), mrcpp::dot(f_tree, f_tree));
+    // dot of two tree vectors (multiply.cpp:253-271): 2 f g - f f, integrated
+    mrcpp::FunctionTreeVector<D> va, vb;
+    va.push_back(std::make_tuple(2.0, &f_tree));
+    vb.push_back(std::make_tuple(1.0, &g_tree));
+    va.push_back(std::make_tuple(-1.0, &f_tree));
+    vb.push_back(std::make_tuple(1.0, &f_tree));
+    mrcpp::FunctionTree<D> dot_tree(MRA);
+    mrcpp::dot(prec, dot_tree, va, vb);
+    std::printf("dot_vectors_integral %.17g\ndot_vectors_expected %.17g\n", dot_tree.integrate(), 2.0 * mrcpp::dot(f_tree, g_tree) - mrcpp::dot(f_tree, f_tree));
 }
 
 int main(int argc, char **argv) {

@@ -176,5 +176,6 @@ def check_drop_in_values(kv, what="all"):
         assert kv["multiplication_nodes"] > 8 and kv["multiplication_rel_err"] < 1e-2 and kv["multiplication_point_rel_err"] < 1e-2
         assert abs(kv["multiplication_integral"] - kv["multiplication_integral_analytic"]) < 1e-3 * kv["multiplication_integral_analytic"]
         assert abs(kv["square_integral"] - kv["square_expected"]) < 1e-3 * kv["square_expected"]
+        assert abs(kv["dot_vectors_integral"] - kv["dot_vectors_expected"]) < 1e-3 * abs(kv["dot_vectors_expected"])
     if what == "all":
         assert abs(kv["divergence_grad_sqnorm"] - 3.0 * kv["derivative_0_sqnorm"]) < 1e-6
