@@ -25,6 +25,7 @@ namespace mrx {
 
 namespace {
 
+#ifdef __CUDACC__ // the kernel and its launcher: CUDA compiler only (the driver below also builds for the CPU mock of tests/cpp/cuda_mock)
 // One CTA per work node. Phase 1: ordered list of the terms that are not identically zero on the node's box
 // (exp(-q2) underflows to exactly 0 for q2 > 746 in IEEE double, GaussFunc::evalf returns 0.0 * coef * p2 there: leaving
 // such a term out of the sum changes nothing; same test as the host generator, tree.cpp project_gaussians).
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(256) project_eval_kernel(double *__restrict__ 
     }
 }
 
+#endif // __CUDACC__
+
 struct QuadDev {
     double *roots = nullptr, *sqrtw = nullptr;
 };
@@ -126,6 +129,7 @@ const QuadDev &device_quadrature(int K) {
 
 } // namespace
 
+#ifdef __CUDACC__
 void launch_project_eval(double *coefs, const int *slots, const int4 *nodeInfo, int cnt, int K, const GaussTable &g, const double *roots,
                          const double *sqrtw, cudaStream_t st) {
     if (cnt <= 0) return;
@@ -134,6 +138,7 @@ void launch_project_eval(double *coefs, const int *slots, const int4 *nodeInfo, 
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }
+#endif // __CUDACC__
 
 /// project(prec, out, GaussExp) with the tree resident in HBM (the host holds topology + norms only)
 void device_project_gaussians(mrx_tree &t, double prec, const GaussExp<3> &gexp, int maxIter, bool absPrec) {
@@ -171,6 +176,7 @@ void device_project_gaussians(mrx_tree &t, double prec, const GaussExp<3> &gexp,
         MRX_CUDA(cudaMemcpyAsync(dw.p, hw.data(), sizeof(int) * 3 * nGauss, cudaMemcpyHostToDevice, st));
     }
     GaussTable G{dc.p, da.p, dp.p, dw.p, nGauss};
+#ifdef __CUDACC__
     if (nGauss * (int)sizeof(int) > 48 * 1024) {
         static int configured = 0;
         if (nGauss > configured) {
@@ -178,6 +184,8 @@ void device_project_gaussians(mrx_tree &t, double prec, const GaussExp<3> &gexp,
             configured = nGauss;
         }
     }
+#endif
+
     const QuadDev &Q = device_quadrature(K);
     const double *filt = device_filters(h.k);
 

@@ -45,9 +45,47 @@ void launch_transform(bool down, bool overwrite, double *coefs, const int *pairs
     launch_counter()++;
 }
 
-void launch_compress_nodes(double *, const int *, int, int, const double *, cudaStream_t, double *) { MRX_ABORT("mock: launch_compress_nodes"); }
-void launch_project_eval(double *, const int *, const int4 *, int, int, const GaussTable &, const double *, const double *, cudaStream_t) {
-    MRX_ABORT("mock: launch_project_eval");
+// in-node compression MWNode::mwTransform(Compression): the node's 8 blocks hold its children's scaling coefficients
+void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *, cudaStream_t, double *) {
+    const FilterSet &fs = filter_set(K - 1);
+    const int Kd = K * K * K;
+    for (int p = 0; p < cnt; p++) {
+        double *node = coefs + (size_t)pairs[2 * p] * 8 * Kd;
+        std::vector<double> in(node, node + (size_t)8 * Kd);
+        orc::mw_transform_back3(fs, K, in.data(), node, Kd);
+    }
+    launch_counter()++;
+}
+// ProjectionCalculator::calcNode up to cvTransform(Backward): values of the expansion at the expanded child quadrature points,
+// times sqrt(w) per dimension and 2^(-3 (n + 1) / 2)  (what project_eval_kernel computes)
+void launch_project_eval(double *coefs, const int *slots, const int4 *nodeInfo, int cnt, int K, const GaussTable &G, const double *roots,
+                         const double *sqrtw, cudaStream_t) {
+    const int Kd = K * K * K;
+    for (int b = 0; b < cnt; b++) {
+        const int scale = nodeInfo[b].x, l[3] = {nodeInfo[b].y, nodeInfo[b].z, nodeInfo[b].w};
+        const double sFac = std::ldexp(1.0, -(scale + 1)), two_fac = std::sqrt(1.0 / std::ldexp(1.0, 3 * (scale + 1)));
+        double *out = coefs + (size_t)slots[b] * 8 * Kd;
+        for (int o = 0; o < 8 * Kd; o++) {
+            const int tt = o / Kd, idx = o % Kd;
+            const int j[3] = {idx % K, (idx / K) % K, idx / (K * K)};
+            double r[3];
+            for (int d = 0; d < 3; d++) r[d] = sFac * (roots[j[d]] + 2.0 * l[d] + (((tt >> d) & 1) ? 1.0 : 0.0));
+            double s = 0.0;
+            for (int g = 0; g < G.n; g++) {
+                double q2 = 0.0, p2 = 1.0;
+                for (int d = 0; d < 3; d++) {
+                    const double q = r[d] - G.pos[3 * g + d];
+                    q2 += G.alpha[g] * q * q;
+                    const int pw = G.power[3 * g + d];
+                    if (pw == 1) p2 *= q;
+                    else if (pw != 0) p2 *= std::pow(q, (double)pw);
+                }
+                s += (q2 > 746.0) ? 0.0 * G.coef[g] * p2 : G.coef[g] * p2 * std::exp(-q2);
+            }
+            out[o] = two_fac * (((s * sqrtw[j[0]]) * sqrtw[j[1]]) * sqrtw[j[2]]);
+        }
+    }
+    launch_counter()++;
 }
 void launch_gen_children(const double *, double *, double *, int, const int *, int, int, const double *, cudaStream_t) {
     MRX_ABORT("mock: launch_gen_children");
@@ -147,13 +185,6 @@ void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int d
     orc::apply_derivative(out.host, oper.op, inp.host, dir, &st);
     host_result(out);
     fill_stats(st, stats);
-}
-void device_project_gaussians(mrx_tree &t, double prec, const GaussExp<3> &gexp, int maxIter, bool absPrec) {
-    host_storage(t);
-    project_gaussians<3>(prec, t.host, gexp, maxIter, absPrec, /*finalize=*/false);
-    orc::mw_transform_up(t.host);
-    orc::calc_square_norm(t.host);
-    host_result(t);
 }
 int comm_rank(const mrx_comm *) { return 0; }
 int comm_world(const mrx_comm *) { return 1; }

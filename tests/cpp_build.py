@@ -49,7 +49,7 @@ def build_mock_lib():
     csrc = os.path.join(ROOT, "mrcpp_b200", "csrc")
     mock = os.path.join(ROOT, "tests", "cpp", "cuda_mock")
     srcs = [os.path.join(csrc, "cabi.cpp"), os.path.join(csrc, "host", "tables.cpp"), os.path.join(csrc, "host", "tree.cpp"),
-            os.path.join(csrc, "host", "operators.cpp"), os.path.join(csrc, "cuda", "device_tree.cu"), os.path.join(mock, "mock_kernels.cpp")]
+            os.path.join(csrc, "host", "operators.cpp"), os.path.join(csrc, "cuda", "device_tree.cu"), os.path.join(csrc, "cuda", "project.cu"), os.path.join(mock, "mock_kernels.cpp")]
     deps = srcs + [os.path.join(csrc, "cuda", "kernels.cu"), os.path.join(mock, "cuda_runtime.h"), os.path.join(csrc, "engine.hpp"), os.path.join(csrc, "host", "mrx_host.hpp"),
                    os.path.join(ROOT, "oracle", "oracle.cpp"), os.path.join(ROOT, "include", "mrcpp_b200.h")]
     if os.path.exists(MOCK_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(MOCK_LIB) for d in deps):

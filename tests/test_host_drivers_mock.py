@@ -27,7 +27,19 @@ def test_tree_algebra_gpu_tests_on_the_mock(mock_lib):
     assert " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout
 
 
-@pytest.mark.parametrize("program,args", [("apply_drop_in.cpp", ["-1", "algebra"]), ("scf_hydrogen.cpp", [])])
+def test_projection_and_transform_gpu_tests_on_the_mock(mock_lib):
+    """the device projection driver (csrc/cuda/project.cu: refinement loop, pre-built grids), whole-tree transforms, upload /
+    download, dot: the cases of the GPU suite that do not depend on the apply kernels' own counters"""
+    env = dict(os.environ, MRX_LIB_PATH=mock_lib)
+    files = [os.path.join(cb.ROOT, "tests", f) for f in ("test_gpu_parity.py", "test_zz1_gpu_reference.py")]
+    r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-k",
+                        "device_projection or identity or golden or vs_real_reference or bottom_up or top_down or hydrogen"],
+                       capture_output=True, text=True, env=env, cwd=cb.ROOT, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+@pytest.mark.parametrize("program,args", [("apply_drop_in.cpp", ["-1", "all"]), ("scf_hydrogen.cpp", [])])
 def test_cpp_programs_on_the_mock(mock_lib, tmp_path, program, args):
     """the C++ programs of the GPU suite linked with the mock library: C++ mirror -> C ABI -> real host drivers -> host kernels"""
     from test_cpp_mirror import check_drop_in_values, check_scf_values
@@ -42,4 +54,4 @@ def test_cpp_programs_on_the_mock(mock_lib, tmp_path, program, args):
     if program.startswith("scf"):
         check_scf_values(kv)
     else:
-        check_drop_in_values(kv, "algebra")
+        check_drop_in_values(kv, "all")
