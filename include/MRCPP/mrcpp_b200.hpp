@@ -376,6 +376,9 @@ public:
         if (this->getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
         mrx_tree_add_inplace(this->h, c, inp.handle());
     }
+    /// FunctionTree::saveTreeTXT / loadTreeTXT (src/trees/FunctionTree.cpp:240-372): the text interchange format
+    void saveTreeTXT(const std::string &file) { mrx_tree_save_txt(this->h, file.c_str()); }
+    void loadTreeTXT(const std::string &file) { mrx_tree_load_txt(this->h, file.c_str()); }
     int getNGenNodes() const { return 0; } // generated nodes never outlive the call that made them
     void deleteGenerated() {}
     void rescale(T c) { mrx_tree_rescale(this->h, c); }

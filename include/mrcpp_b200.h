@@ -85,6 +85,11 @@ double mrx_tree_integrate(mrx_tree *tree);
  * 374-436): function values from the downloaded tree (host arithmetic; the tree is brought to the host first if its
  * current copy is in HBM). Zero outside the world. */
 int mrx_tree_evalf(mrx_tree *tree, int n_points, const double *r /*[n][3]*/, double *values /*[n]*/, int precise);
+/* FunctionTree::saveTreeTXT / loadTreeTXT (src/trees/FunctionTree.cpp:240-372): the reference's text interchange format (function
+ * values at the quadrature points of the children of every end node, MADNESS conventions). Host arithmetic. load replaces the
+ * content of `tree` (same MRA) by the tree of the file; files with complete sibling groups, as saveTreeTXT writes them. */
+int mrx_tree_save_txt(mrx_tree *tree, const char *path);
+int mrx_tree_load_txt(mrx_tree *tree, const char *path);
 /* build_grid(out, GaussExp) alone (src/treebuilders/grid.cpp:78-123): host only, leaves a grid without coefficients;
  * max_iter < 0: no bound */
 int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, const double *alpha,

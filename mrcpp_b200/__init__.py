@@ -120,6 +120,14 @@ class FunctionTree:
         """FunctionTree::add(c, inp): in place, on this tree's grid (src/trees/FunctionTree.cpp:687-706)"""
         _lib.load().mrx_tree_add_inplace(self._h, float(c), inp._h)
 
+    def saveTreeTXT(self, path):
+        """FunctionTree::saveTreeTXT (src/trees/FunctionTree.cpp:306-372)"""
+        _lib.load().mrx_tree_save_txt(self._h, str(path).encode())
+
+    def loadTreeTXT(self, path):
+        """FunctionTree::loadTreeTXT (src/trees/FunctionTree.cpp:240-305), files written by saveTreeTXT"""
+        _lib.load().mrx_tree_load_txt(self._h, str(path).encode())
+
     def integrate(self):
         """FunctionTree::integrate (src/trees/FunctionTree.cpp:438-454)"""
         return _lib.load().mrx_tree_integrate(self._h)

@@ -57,6 +57,8 @@ SIGNATURES = {
     "mrx_tree_to_arrays": (_I, [_P, _PI, _PI, _PI, _PI, _PD, _PD]),
     "mrx_tree_copy_grid": (_I, [_P, _P]),
     "mrx_tree_integrate": (_D, [_P]),
+    "mrx_tree_save_txt": (_I, [_P, C.c_char_p]),
+    "mrx_tree_load_txt": (_I, [_P, C.c_char_p]),
     "mrx_tree_evalf": (_I, [_P, _I, _PD, _PD, _I]),
     "mrx_tree_build_grid_from": (_I, [_P, _P]),
     "mrx_tree_clear_grid": (_I, [_P]),

@@ -351,6 +351,142 @@ int mrx_tree_evalf(mrx_tree *tree, int n_points, const double *r, double *values
     return 0;
 }
 
+// ---- text interchange: FunctionTree::saveTreeTXT / loadTreeTXT (src/trees/FunctionTree.cpp:240-372). Host arithmetic on the
+// downloaded tree. The file holds, per end node, the function values at the quadrature points of its eight children
+// (mwTransform(Reconstruction) + cvTransform(Forward)), child by child, with MADNESS conventions: level counted from the box
+// [-L, L]^3, translations from 0, index order z fastest and descending.
+namespace {
+void cv_map_node(Tree<3> &h, int n, bool forward) { // MWNode::cvTransform for the interpolating basis (MWNode.cpp:448-490)
+    const int K = h.K;
+    const Quadrature &q = quadrature(K);
+    std::vector<double> m(K);
+    for (int j = 0; j < K; j++) m[j] = forward ? std::sqrt(1.0 / q.weights[j]) : std::sqrt(q.weights[j]);
+    const double two = std::pow(2.0, 3 * (h.nodes[n].scale + 1));
+    const double two_fac = forward ? std::sqrt(two) : std::sqrt(1.0 / two);
+    double *c = h.coef(n);
+    for (int b = 0; b < 8; b++)
+        for (int idx = 0; idx < h.Kd; idx++) {
+            double v = c[(size_t)b * h.Kd + idx];
+            v = ((v * m[idx % K]) * m[(idx / K) % K]) * m[idx / (K * K)];
+            c[(size_t)b * h.Kd + idx] = two_fac * v;
+        }
+}
+} // namespace
+
+int mrx_tree_save_txt(mrx_tree *tree, const char *path) {
+    if (!tree->hostCoefsValid) mrx_tree_sync_host(tree);
+    Tree<3> &h = tree->host;
+    FILE *f = std::fopen(path, "w");
+    if (!f) MRX_ABORT(std::string("cannot open ") + path);
+    const int K = h.K, Kd = h.Kd, rscale = h.mra.rootScale;
+    double Lw = 1.0;
+    for (int i = 0; i > rscale; i--) Lw *= 2; // the world is assumed to be [-L, L]^3 with two root boxes per direction (FunctionTree.cpp:313)
+    std::fprintf(f, "3\n");
+    for (int d = 0; d < 3; d++) std::fprintf(f, "%.14g %.14g\n", -Lw, Lw);
+    std::vector<int> ends;
+    h.endNodeTable(ends);
+    std::fprintf(f, "%d\n%d\n", K, 8 * (int)ends.size());
+    std::vector<int> map; // MADNESS index order (FunctionTree.cpp:335-342)
+    for (int x = K - 1; x >= 0; x--)
+        for (int y = K - 1; y >= 0; y--)
+            for (int z = K - 1; z >= 0; z--) map.push_back(z * K * K + y * K + x);
+    const int L = (int)std::pow(2.0, -rscale);
+    std::vector<double> keep(h.ncoef);
+    for (int n : ends) {
+        std::memcpy(keep.data(), h.coef(n), sizeof(double) * h.ncoef);
+        h.mwTransformNode(n, Reconstruction);
+        cv_map_node(h, n, true);
+        const int s = h.nodes[n].scale;
+        for (int c = 0; c < 8; c++) {
+            std::fprintf(f, "%d ", s - rscale + 2);
+            for (int d = 0; d < 3; d++) std::fprintf(f, "%d ", (int)(2 * (h.nodes[n].l[d] + std::pow(2.0, s) * L)) + ((c >> d) & 1));
+            std::fprintf(f, "\n");
+            const double *v = h.coef(n) + (size_t)c * Kd;
+            for (int i = 0; i < Kd; i++) std::fprintf(f, "%.14g ", v[map[i]]);
+            std::fprintf(f, "\n");
+        }
+        std::memcpy(h.coef(n), keep.data(), sizeof(double) * h.ncoef); // the node keeps its coefficients
+    }
+    std::fclose(f);
+    return 0;
+}
+
+int mrx_tree_load_txt(mrx_tree *tree, const char *path) {
+    Tree<3> &h = tree->host;
+    FILE *f = std::fopen(path, "r");
+    if (!f) MRX_ABORT(std::string("cannot open ") + path);
+    int D = 0, K = 0, nblk = 0;
+    double lo = 0.0, hi = 0.0;
+    if (std::fscanf(f, "%d", &D) != 1 || D != 3) MRX_ABORT("load_txt: not a 3-D tree file");
+    for (int d = 0; d < 3; d++)
+        if (std::fscanf(f, "%lf %lf", &lo, &hi) != 2) MRX_ABORT("load_txt: bad header");
+    if (std::fscanf(f, "%d %d", &K, &nblk) != 2 || K != h.K) MRX_ABORT("load_txt: polynomial order of the file differs from the tree's");
+    const int rscale = h.mra.rootScale, Kd = h.Kd;
+    const int L = (int)std::pow(2.0, -rscale);
+    if (std::abs(hi - std::pow(2.0, -rscale)) > 1e-12 * hi && rscale < 0) MRX_ABORT("load_txt: world of the file differs from the tree's");
+    std::vector<int> map;
+    for (int x = K - 1; x >= 0; x--)
+        for (int y = K - 1; y >= 0; y--)
+            for (int z = K - 1; z >= 0; z--) map.push_back(z * K * K + y * K + x);
+    h.deleteGenerated();
+    h.clearToRoots();
+    h.allocCoefs = true;
+    h.ensureCoefStorage();
+    std::vector<double> vals(Kd);
+    std::vector<int> filled; // per node: how many of its eight child blocks the file has delivered
+    for (int b = 0; b < nblk; b++) {
+        int lev = 0, lm[3];
+        if (std::fscanf(f, "%d %d %d %d", &lev, &lm[0], &lm[1], &lm[2]) != 4) MRX_ABORT("load_txt: truncated file");
+        for (int i = 0; i < Kd; i++)
+            if (std::fscanf(f, "%lf", &vals[i]) != 1) MRX_ABORT("load_txt: truncated file");
+        const int cscale = lev + rscale - 1; // scale of the child the block belongs to
+        std::array<int, 3> lc, lp;
+        int c = 0;
+        for (int d = 0; d < 3; d++) {
+            lc[d] = lm[d] - (int)(std::pow(2.0, cscale) * L);
+            lp[d] = lc[d] >> 1;
+            c |= (lc[d] & 1) << d;
+        }
+        // the end node the block belongs to: created on the way down if the grid does not have it yet
+        int n = h.rootIndex(cscale - 1, lp);
+        if (n < 0) MRX_ABORT("load_txt: block outside the world");
+        while (h.nodes[n].scale < cscale - 1) {
+            if (h.nodes[n].child0 < 0) h.createChildren(n, false);
+            const int shift = cscale - 1 - h.nodes[n].scale - 1;
+            int k = 0;
+            for (int d = 0; d < 3; d++) k |= ((lp[d] >> shift) & 1) << d;
+            n = h.nodes[n].child0 + k;
+        }
+        if ((int)filled.size() < h.size()) filled.resize(h.size(), 0);
+        double *dst = h.coef(n) + (size_t)c * Kd;
+        for (int i = 0; i < Kd; i++) dst[map[i]] = vals[i];
+        filled[n]++;
+    }
+    std::fclose(f);
+    filled.resize(h.size(), 0);
+    for (int n = 0; n < h.size(); n++) {
+        if (h.isBranch(n)) {
+            if (filled[n] != 0) MRX_ABORT("load_txt: values for a node that also has finer nodes (not a file written by saveTreeTXT)");
+            continue;
+        }
+        if (filled[n] != 8) MRX_ABORT("load_txt: incomplete sibling group (not a file written by saveTreeTXT)");
+        cv_map_node(h, n, false);
+        h.mwTransformNode(n, Compression);
+        h.nodes[n].flags |= FlagHasCoefs;
+        h.calcNorms(n);
+    }
+    h.mwTransformUpSerial(); // branch nodes from their children (host: the file has just been parsed here)
+    for (int n = 0; n < h.size(); n++) h.nodes[n].flags |= FlagHasCoefs;
+    h.calcSquareNorm();
+    tree->hostCoefsValid = true;
+    tree->devValid = false;
+    tree->dev.nNodes = 0;
+    tree->dev.nGen = 0;
+    tree->dev.topoNodes = -1;
+    tree->dev.partial = false;
+    return 0;
+}
+
 // build_grid(out, GaussExp) alone (src/treebuilders/grid.cpp:78-123): refine the grid where the Gaussians are visible, no
 // coefficients. Host only.
 int mrx_build_grid_gaussians(mrx_tree *tree, int n_gauss, const double *coef, const double *alpha, const double *pos,

@@ -661,3 +661,38 @@ def test_tree_from_reference_text_file(libs, tmp_path):
     ref.apply(prec, rg, RP, rf)
     orc.apply(prec, og, OP, of)
     same_tree(rg.export(), og.to_arrays(), tol=1e-10)
+
+
+@needs_ref
+def test_native_text_io_against_reference(libs, tmp_path):
+    """mrx_tree_save_txt / mrx_tree_load_txt (the C ABI's own saveTreeTXT / loadTreeTXT) against the reference's: our file is read
+    by the reference into the tree it came from, the reference's file is read by us into the reference's tree, and our writer
+    and the numpy writer of mrcpp_b200/treetxt.py produce the same values"""
+    mw, orc = libs
+    from mrcpp_b200 import treetxt
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 2, 11)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf, of = ref.Tree(rm), mw.FunctionTree(om)
+    ref.project(prec, rf, funcs)
+    orc.project(prec, of, expansion(mw, funcs))
+    ours, theirs, numpy_file = str(tmp_path / "ours.txt"), str(tmp_path / "ref.txt"), str(tmp_path / "np.txt")
+    before = of.to_arrays()["coefs"].copy()
+    of.saveTreeTXT(ours)
+    assert np.array_equal(before, of.to_arrays()["coefs"])          # saving leaves the tree as it was
+    rf.save_txt(theirs)
+    treetxt.save_tree_txt(of, numpy_file)
+    _, A = treetxt.load_tree_txt(ours)
+    _, B = treetxt.load_tree_txt(numpy_file)
+    _, R = treetxt.load_tree_txt(theirs)
+    peak = max(np.abs(v).max() for v in R.values())
+    assert set(A) == set(B) == set(R)
+    assert max(np.abs(A[key] - B[key]).max() for key in A) < 1e-12 * peak and max(np.abs(A[key] - R[key]).max() for key in A) < 1e-12 * peak
+    back = ref.Tree(rm)
+    back.load_txt(ours)                                              # the reference reads our file
+    same_tree(back.export(), of.to_arrays(), tol=1e-11)
+    mine = mw.FunctionTree(om)
+    mine.loadTreeTXT(theirs)                                         # we read the reference's file
+    same_tree(rf.export(), mine.to_arrays(), tol=1e-11)
+    assert abs(mine.getSquareNorm() - rf.square_norm()) < 1e-11 * rf.square_norm() and abs(mine.integrate() - rf.integrate()) < 1e-11
