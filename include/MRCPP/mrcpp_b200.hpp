@@ -712,6 +712,11 @@ template <int D, typename T> void square(double prec, FunctionTree<D, T> &out, F
     multiply(prec, out, v, maxIter, absPrec);
 }
 
+/// mrcpp::power(prec, out, inp, p): src/treebuilders/multiply.cpp:211-234
+template <int D, typename T> void power(double prec, FunctionTree<D, T> &out, FunctionTree<D, T> &inp, double p, int maxIter = -1, bool absPrec = false) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_tree_power(prec, out.handle(), inp.handle(), p, maxIter, absPrec ? 1 : 0);
+}
 /// mrcpp::dot(prec, out, inp_a, inp_b, maxIter, absPrec): src/treebuilders/multiply.cpp:253-271 -- out = sum_d a_d b_d f_d g_d, every
 /// product on the grid of `out` refined with the MultiplicationAdaptor (useMaxNorms), the sum on the union of the product grids
 template <int D, typename T>

@@ -224,6 +224,10 @@ int mrx_tree_add_inplace(mrx_tree *tree, double c, mrx_tree *inp);
 int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp, int max_iter, int abs_prec,
                       int use_max_norms);
 
+/* power(prec, out, inp, p, max_iter, abs_prec) (src/treebuilders/multiply.cpp:211-234, PowerCalculator.h:43-58): the function
+ * values of `inp` raised to the power p, refined like multiply */
+int mrx_tree_power(double prec, mrx_tree *out, mrx_tree *inp, double p, int max_iter, int abs_prec);
+
 /* residency control for measurement: host->device / device->host copies of a tree's coefficients */
 int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */
 int mrx_tree_sync_host(mrx_tree *tree);   /* download if the device copy is newer                    */

@@ -421,6 +421,11 @@ def multiply(prec, out, inp, maxIter=-1, absPrec=False, useMaxNorms=False):
     _lib.load().mrx_tree_multiply(float(prec), out._h, len(inp), _dp(c), h, int(maxIter), 1 if absPrec else 0, 1 if useMaxNorms else 0)
 
 
+def power(prec, out, inp, p, maxIter=-1, absPrec=False):
+    """mrcpp::power(prec, out, inp, p) (src/treebuilders/multiply.cpp:211-234): function values of `inp` raised to the power p"""
+    _lib.load().mrx_tree_power(float(prec), out._h, inp._h, float(p), int(maxIter), 1 if absPrec else 0)
+
+
 def dot_vectors(prec, out, inp_a, inp_b, maxIter=-1, absPrec=False):
     """mrcpp::dot(prec, out, FunctionTreeVector, FunctionTreeVector) (src/treebuilders/multiply.cpp:253-271): out = sum_d a_d b_d f_d g_d"""
     if len(inp_a) != len(inp_b):

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mrx_tree_refine_grid": (_I, [_P, _D, _I, _I]),
     "mrx_tree_add_inplace": (_I, [_P, _D, _P]),
     "mrx_tree_multiply": (_I, [_D, _P, _I, _PD, C.POINTER(C.c_void_p), _I, _I, _I]),
+    "mrx_tree_power": (_I, [_D, _P, _P, _D, _I, _I]),
     "mrx_tree_add_adaptive": (_I, [_D, _P, _I, _PD, C.POINTER(C.c_void_p), _I, _I]),
     "mrx_build_grid_gaussians": (_I, [_P, _I, _PD, _PD, _PD, _PI, _I]),
     "mrx_project_gaussians": (_I, [_P, _D, _I, _PD, _PD, _PD, _PI, _I, _I]),

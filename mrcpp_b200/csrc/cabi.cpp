@@ -814,6 +814,15 @@ int mrx_tree_multiply(double prec, mrx_tree *out, int n, const double *coefs, mr
     device_multiply(*out, n, coefs, inp, prec, max_iter, abs_prec != 0, use_max_norms != 0);
     return 0;
 }
+int mrx_tree_power(double prec, mrx_tree *out, mrx_tree *inp, double p, int max_iter, int abs_prec) {
+    require_device("mrx_tree_power");
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (inp == out) MRX_ABORT("mrx_tree_power: output tree is the input");
+    const double one = 1.0;
+    mrx_tree *v[1] = {inp};
+    device_multiply(*out, 1, &one, v, prec, max_iter, abs_prec != 0, false, &p);
+    return 0;
+}
 int mrx_tree_add(mrx_tree *out, int n, const double *coefs, mrx_tree *const *inp) {
     return mrx_tree_add_adaptive(-1.0, out, n, coefs, inp, 0, 0);
 }

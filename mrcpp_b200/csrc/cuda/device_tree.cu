@@ -462,9 +462,11 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, dou
 //    zeroed scratch child slots (the in-node Reconstruction), values_kernel accumulates c_i * value_i into the product scratch
 //    and finally applies the Backward map, BottomUp of the scratch children gives the compressed product node, which is
 //    copied into the node store.
-void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec, bool useMaxNorms) {
+void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec, bool useMaxNorms,
+                     const double *power) {
     require_device("device_multiply");
     if (useMaxNorms && n != 2) MRX_ABORT("Invalid tree vec size"); // MultiplicationAdaptor.h:47
+    if (power && n != 1) MRX_ABORT("power: one input");             // power(prec, out, inp, p): multiply.cpp:211-234, PowerCalculator.h:43-58
     Tree<3> &h = out.host;
     cudaStream_t st = stream();
     const int K = h.K, Kd = h.Kd, ncoef = h.ncoef;
@@ -591,7 +593,8 @@ void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp
                 MRX_CUDA(cudaMemsetAsync(S.p, 0, slotBytes * 9 * nC, st));
                 launch_axpy_nodes(S.p, X[i].p, dGather.p, nC, /*nRoots: scaling block of every node*/ 0x7fffffff, Kd, 1.0, st);
                 launch_transform(true, false, S.p, dKids.p, nC, K, filt, st); // in-node Reconstruction into the scratch children
-                launch_product_values(P.p, S.p, dScale.p, nC, K, dcv.p, c[i], i == 0 ? 0 : 1, st);
+                if (power) launch_product_values(P.p, S.p, dScale.p, nC, K, dcv.p, *power, 3, st); // values ^ p
+                else launch_product_values(P.p, S.p, dScale.p, nC, K, dcv.p, c[i], i == 0 ? 0 : 1, st);
             }
             launch_product_values(P.p, nullptr, dScale.p, nC, K, dsw.p, 1.0, 2, st); // cvTransform(Backward)
             launch_transform(false, true, P.p, dKids.p, nC, K, filt, st);            // in-node Compression: parent slot j

@@ -550,7 +550,8 @@ __global__ void __launch_bounds__(256) axpy_nodes_kernel(double *out, const doub
 // has its eight reconstructed scaling blocks in block 0 of the scratch slots nC + 8 j + t (t = child). map = cvMap (Forward:
 // sqrt(1 / w), InterpolatingBasis.cpp:115-124) or vcMap (Backward: sqrt(w)), applied along x, y, z like MWNode::cvTransform
 // (MWNode.cpp:448-490), with the factor 2^(+-3 (n + 1) / 2) of the children's scale.
-//   mode 0: P  = c * forward(S)      mode 1: P *= c * forward(S)      mode 2: P = backward(P)
+//   mode 0: P  = c * forward(S)      mode 1: P *= c * forward(S)      mode 2: P = backward(P)      mode 3: P = forward(S) ^ c
+//   (mode 3: PowerCalculator.h:43-58)
 __global__ void __launch_bounds__(256) product_values_kernel(double *P, const double *S, const int *scale, int nC, int K, const double *map,
                                                              double c, int mode) {
     const int j = blockIdx.x >> 3, t = blockIdx.x & 7;
@@ -562,6 +563,8 @@ __global__ void __launch_bounds__(256) product_values_kernel(double *P, const do
         const int x = q % K, y = (q / K) % K, z = q / (K * K);
         if (mode == 2) {
             P[off + q] = two_fac * (((P[off + q] * map[x]) * map[y]) * map[z]);
+        } else if (mode == 3) {
+            P[off + q] = pow(two_fac * (((S[off + q] * map[x]) * map[y]) * map[z]), c);
         } else {
             const double v = c * (two_fac * (((S[off + q] * map[x]) * map[y]) * map[z]));
             P[off + q] = mode == 0 ? v : P[off + q] * v;

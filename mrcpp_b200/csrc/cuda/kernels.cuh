@@ -49,7 +49,8 @@ void launch_scale(double *x, size_t n, double c, cudaStream_t st);
 void launch_axpy_nodes(double *out, const double *in, const int *pairs, int np, int nRoots, int Kd, double c, cudaStream_t st);
 
 /// element-wise part of the multiplication on scratch nodes (chunk of nC nodes; children of node j in slots nC + 8 j + t):
-/// mode 0: P = c * forward(S), mode 1: P *= c * forward(S), mode 2: P = backward(P); map = sqrt(1 / w) or sqrt(w) per index
+/// mode 0: P = c * forward(S), mode 1: P *= c * forward(S), mode 2: P = backward(P), mode 3: P = forward(S) ^ c; map = sqrt(1 / w) or
+/// sqrt(w) per index
 void launch_product_values(double *P, const double *S, const int *scale, int nC, int K, const double *map, double c, int mode,
                            cudaStream_t st);
 

@@ -128,8 +128,9 @@ void device_add(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, dou
 int device_refine_grid(mrx_tree &t, double prec, bool absPrec, int scales); // refine_grid (grid.cpp:271-302), returns the new nodes
 void device_add_inplace(mrx_tree &out, double c, mrx_tree &inp);           // FunctionTree::add(c, inp) (FunctionTree.cpp:687-706)
 /// multiply(prec, out, {(c_i, inp_i)}, maxIter, absPrec) from the grid of `out` (multiply.cpp:104-136)
+/// power != nullptr: power(prec, out, inp[0], *power) (multiply.cpp:211-234): the values of the single input raised to *power
 void device_multiply(mrx_tree &out, int n, const double *c, mrx_tree *const *inp, double prec, int maxIter, bool absPrec,
-                     bool useMaxNorms = false);
+                     bool useMaxNorms = false, const double *power = nullptr);
 void oper_upload(mrx_oper &o);
 
 // project.cu

@@ -800,7 +800,7 @@ static void max_square_norms(const Tree<3> &t, std::vector<double> &maxS, std::v
 }
 
 void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std::vector<Tree<3> *> &inp, int maxIter, bool absPrec,
-              bool useMaxNorms) {
+              bool useMaxNorms, const double *power = nullptr) { // power: PowerCalculator (PowerCalculator.h:43-58), one input
     std::vector<std::vector<double>> maxS(inp.size()), maxW(inp.size());
     if (useMaxNorms) {
         if (inp.size() != 2) MRX_ABORT("Invalid tree vec size"); // MultiplicationAdaptor.h:47
@@ -846,7 +846,10 @@ void multiply(double prec, Tree<3> &out, const std::vector<double> &c, const std
                 std::memcpy(o, t.coef(m), sizeof(double) * (t.isGen(m) ? t.Kd : t.ncoef));
                 out.mwTransformNode(n, Reconstruction);
                 cv_forward(out, n);
-                for (int j = 0; j < out.ncoef; j++) acc[j] *= c[i] * o[j];
+                if (power)
+                    for (int j = 0; j < out.ncoef; j++) acc[j] = std::pow(o[j], *power);
+                else
+                    for (int j = 0; j < out.ncoef; j++) acc[j] *= c[i] * o[j];
             }
             std::memcpy(o, acc.data(), sizeof(double) * out.ncoef);
             out.cvTransformBackward(n);
@@ -1006,6 +1009,9 @@ int orc_refine_grid(void *tree, double prec, int absPrec, int scales) {
     return orc::refine_grid(*static_cast<Tree<3> *>(tree), prec, absPrec != 0, scales);
 }
 void orc_add_inplace(void *out, double c, void *inp) { orc::add_inplace(*static_cast<Tree<3> *>(out), c, *static_cast<Tree<3> *>(inp)); }
+void orc_power(double prec, void *out, void *inp, double p, int maxIter, int absPrec) {
+    orc::multiply(prec, *static_cast<Tree<3> *>(out), {1.0}, {static_cast<Tree<3> *>(inp)}, maxIter, absPrec != 0, false, &p);
+}
 void orc_multiply(double prec, void *out, int n, const double *coefs, void **inp, int maxIter, int absPrec, int useMaxNorms) {
     std::vector<double> c(coefs, coefs + n);
     std::vector<Tree<3> *> t(n);

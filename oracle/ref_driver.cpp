@@ -145,6 +145,9 @@ int ref_refine_grid(void *t, double prec, int absPrec, int scales) {
 }
 void ref_add_inplace(void *out, double c, void *inp) { static_cast<RefTree *>(out)->tree.add(c, static_cast<RefTree *>(inp)->tree); }
 void ref_clear_grid(void *t) { clear_grid(static_cast<RefTree *>(t)->tree); }
+void ref_power(double prec, void *out, void *inp, double p, int maxIter, int absPrec) {
+    power(prec, static_cast<RefTree *>(out)->tree, static_cast<RefTree *>(inp)->tree, p, maxIter, absPrec != 0);
+}
 /// divergence(out, oper, {inp_x, inp_y, inp_z}) (src/treebuilders/apply.cpp:514-530)
 void ref_divergence(void *out, void *oper, void **inp) {
     FunctionTreeVector<3, double> vec;

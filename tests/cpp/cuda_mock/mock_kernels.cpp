@@ -120,6 +120,7 @@ static Idx blockIdx, threadIdx;
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 using std::exp2;
+using std::pow;
 using std::sqrt;
 #include "extracted_kernels.inc"
 #undef __global__

@@ -31,6 +31,7 @@ struct Oracle {
     void (*add)(double, void *, int, const double *, void **, int, int);
     void (*multiply)(double, void *, int, const double *, void **, int, int, int);
     int (*refine_grid)(void *, double, int, int);
+    void (*power)(double, void *, void *, double, int, int);
     void (*add_inplace)(void *, double, void *);
 };
 Oracle &oracle() {
@@ -52,6 +53,7 @@ Oracle &oracle() {
         r.add = reinterpret_cast<decltype(r.add)>(dlsym(h, "orc_add"));
         r.multiply = reinterpret_cast<decltype(r.multiply)>(dlsym(h, "orc_multiply"));
         r.refine_grid = reinterpret_cast<decltype(r.refine_grid)>(dlsym(h, "orc_refine_grid"));
+        r.power = reinterpret_cast<decltype(r.power)>(dlsym(h, "orc_power"));
         r.add_inplace = reinterpret_cast<decltype(r.add_inplace)>(dlsym(h, "orc_add_inplace"));
         if (const char *t = std::getenv("MRX_TABLES")) r.set_tables(t);
         return r;
@@ -119,6 +121,11 @@ int mrx_tree_add_adaptive(double prec, mrx_tree *out, int n, const double *coefs
     std::vector<void *> h(n);
     for (int i = 0; i < n; i++) h[i] = mrx_tree_host_handle(inp[i]);
     oracle().add(prec, mrx_tree_host_handle(out), n, coefs, h.data(), max_iter, abs_prec);
+    mrx_tree_host_modified(out);
+    return 0;
+}
+int mrx_tree_power(double prec, mrx_tree *out, mrx_tree *inp, double p, int max_iter, int abs_prec) {
+    oracle().power(prec, mrx_tree_host_handle(out), mrx_tree_host_handle(inp), p, max_iter, abs_prec);
     mrx_tree_host_modified(out);
     return 0;
 }

@@ -42,6 +42,7 @@ def lib():
         o.orc_refine_grid.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
         o.orc_refine_grid.restype = C.c_int
         o.orc_add_inplace.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        o.orc_power.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int]
         o.orc_multiply.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
         o.orc_add.argtypes = [C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.c_int, C.c_int]
         o.orc_set_table_path(_plib.TABLES.encode())
@@ -150,6 +151,13 @@ def add_inplace(out, c, inp):
     out.sync_host()
     inp.sync_host()
     lib().orc_add_inplace(_th(out), float(c), _th(inp))
+    _modified(out)
+
+
+def power(out, inp, p, prec=-1.0, maxIter=-1, absPrec=False):
+    """power(prec, out, inp, p) (src/treebuilders/multiply.cpp:211-234)"""
+    inp.sync_host()
+    lib().orc_power(float(prec), _th(out), _th(inp), float(p), int(maxIter), 1 if absPrec else 0)
     _modified(out)
 
 

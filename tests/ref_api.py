@@ -35,7 +35,7 @@ def lib():
             "ref_copy_grid": (None, [P, P]), "ref_mw_transform": (None, [P, I, I]),
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
             "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_save_txt": (None, [P, C.c_char_p]), "ref_tree_load_txt": (None, [P, C.c_char_p]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
-            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]), "ref_apply_prec_trees": (D, [D, P, P, P, I, C.POINTER(P), I, I]),
+            "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]), "ref_power": (None, [D, P, P, D, I, I]), "ref_apply_prec_trees": (D, [D, P, P, P, I, C.POINTER(P), I, I]),
             "ref_add_inplace": (None, [P, D, P]), "ref_clear_grid": (None, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
@@ -174,6 +174,10 @@ def refine_grid(tree, prec=-1.0, absPrec=False, scales=0):
 
 def add_inplace(out, c, inp):
     lib().ref_add_inplace(out._h, float(c), inp._h)
+
+
+def power(out, inp, p, prec=-1.0, maxIter=-1, absPrec=False):
+    lib().ref_power(float(prec), out._h, inp._h, float(p), int(maxIter), 1 if absPrec else 0)
 
 
 def divergence(out, oper, trees):

@@ -696,3 +696,21 @@ def test_native_text_io_against_reference(libs, tmp_path):
     mine.loadTreeTXT(theirs)                                         # we read the reference's file
     same_tree(rf.export(), mine.to_arrays(), tol=1e-11)
     assert abs(mine.getSquareNorm() - rf.square_norm()) < 1e-11 * rf.square_norm() and abs(mine.integrate() - rf.integrate()) < 1e-11
+
+
+@needs_ref
+@pytest.mark.parametrize("p,prec", [(2.0, 1e-4), (3.0, 1e-3), (2.0, -1.0)])
+def test_power_matches_reference(libs, p, prec):
+    """power(prec, out, inp, p) (multiply.cpp:211-234, PowerCalculator.h:43-58): function values raised to the power p"""
+    mw, orc = libs
+    rm, om, ((ra, oa), _) = _two_trees(mw, orc, 5, 1e-5, box=(1.0, 1.0))
+    ro, oo = ref.Tree(rm), mw.FunctionTree(om)
+    if prec < 0:
+        ref.build_grid_tree(ro, ra)
+        mw.build_grid(oo, oa)
+    ref.power(ro, ra, p, prec=prec)
+    orc.power(oo, oa, p, prec=prec)
+    same_tree(ro.export(), oo.to_arrays(), tol=1e-10, floor=1.0)
+    assert oo.getNNodes() > 8 and oa.getNNodes() == ra.n_nodes()
+    if p == 2.0:   # the square: integral of f^2 = <f | f>
+        assert abs(oo.integrate() - orc.dot(oa, oa)) < 1e-2 * orc.dot(oa, oa)

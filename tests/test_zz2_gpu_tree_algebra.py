@@ -238,3 +238,21 @@ def test_tree_algebra_vs_real_reference(gpu):
     ref.divergence(ro, RD, [ra, rb, ra])
     mw.divergence(go, GD, [(1.0, ga), (1.0, gb), (1.0, ga)])
     compare(ro.export(), go.to_arrays(), 1e-11, 1e-3)
+
+
+@pytest.mark.parametrize("p,prec", [(2.0, 1e-4), (3.0, 1e-3)])
+def test_power(gpu, p, prec):
+    """power(prec, out, inp, p) (multiply.cpp:211-234): node set and coefficients (against the largest node norm) vs the oracle"""
+    mw, orc = gpu
+    mra = world(mw, 5)
+    func = gaussians(2, 71, box=1.0, lo=1.0, hi=2.0)
+    ga, ca = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.project(1e-5, ga, func)
+    orc.project(1e-5, ca, func)
+    og, oc = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.power(prec, og, ga, p)
+    orc.power(oc, ca, p, prec=prec)
+    A, B = og.to_arrays(), oc.to_arrays()
+    assert A["scale"].shape == B["scale"].shape and np.array_equal(A["transl"], B["transl"]) and np.array_equal(A["child0"], B["child0"])
+    nrm = np.sqrt((B["coefs"] ** 2).sum(axis=1))
+    assert og.getNNodes() > 8 and (np.abs(A["coefs"] - B["coefs"]).max(axis=1) / nrm.max()).max() < 1e-10
