@@ -18,6 +18,13 @@ with a fresh output tree each step.
   --impl reference  the same sample through both CPU implementations: the oracle port and, where oracle/_ref exists, the
          reference's own sources compiled in place; the line carries the faster of the two.
 
+--config selects the workload (default: the headline above): c1 = examples/poisson.cpp at the target precision (k=7, prec 1e-7,
+one Gaussian), c4 = HelmholtzOperator(mu=1) k=9 prec 1e-7 on 50 synthetic orbital trees (a step = the 50 applies of one SCF
+iteration, examples/scf.cpp:101-111), c5 = Poisson k=11 prec 1e-9 on 100 centres. --centers/--order/--prec override. The
+reference arm prints the workload it really times (`config.centers` = the CPU sample, `config.sample_of` = the GPU arm's
+workload); the GPU arm additionally times that same CPU-sample workload (`same_workload_as_reference_arm`) so that a ratio on
+identical inputs can be formed from the two lines.
+
 N > 1 (torchrun): one process per GPU; ONE apply is sharded over the ranks: every refinement iteration's
 output-node list is dealt out cyclically (item i -> rank i % N), input tree and operator are replicated, component norms
 are all-gathered over NCCL and the output coefficient blocks are pushed to the peers' HBM by the copy engines over NVLink
@@ -126,6 +133,41 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, %d ms period" % int(self.period * 1e3)}
 
 
+CONFIGS = {
+    # name: (order, prec, centres, cpu sample centres, operator)
+    "headline": (7, 1e-7, 1000, 16, "poisson"),
+    "c1": (7, 1e-7, 1, 1, "poisson"),
+    "c4": (9, 1e-7, 50, 1, "helmholtz"),
+    "c5": (11, 1e-9, 100, 4, "poisson"),
+}
+
+
+def benzene_orbital(mw, j):
+    """C4 input j: 12 benzene-like centres (6 at radius 2.64, 6 at 4.69 bohr, z = 0, 60 degrees apart),
+    exponents 1.5 / 0.8, coefficients N(0,1) with seed 2024 + j"""
+    rng = np.random.default_rng(2024 + j)
+    ge = mw.GaussExp()
+    for a in range(12):
+        r = 2.64 if a < 6 else 4.69
+        ang = math.pi / 3.0 * (a % 6)
+        ge.append(mw.GaussFunc(1.5 if a < 6 else 0.8, float(rng.normal()), (r * math.cos(ang), r * math.sin(ang), 0.0)))
+    return ge
+
+
+def workload_inputs(mw, args, centers):
+    """the Gaussian expansions of the workload: one density (Poisson configs) or `centers` orbital functions (c4)"""
+    if args.operator == "helmholtz":
+        return [benzene_orbital(mw, j) for j in range(centers)]
+    if args.config == "c1":
+        beta = 100.0
+        return [[mw.GaussFunc(beta, (beta / math.pi) ** 1.5, (math.pi / 3,) * 3)]]
+    return [density(mw, centers, 42)]
+
+
+def make_operator(mw, mra, args):
+    return mw.HelmholtzOperator(mra, 1.0, args.prec) if args.operator == "helmholtz" else mw.PoissonOperator(mra, args.prec)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on all host threads, on a bounded sample of
     the workload: the oracle port (oracle/oracle.cpp: OpenMP restatement, same loop structure and thresholds) and, where
@@ -142,26 +184,31 @@ def run_reference(args, rank, world):
     import oracle_api as orc
     k, prec = args.order, args.prec
     mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
-    P = mw.PoissonOperator(mra, prec)
-    func = density(mw, args.cpu_centers, 42)
-    ft = mw.FunctionTree(mra)
-    orc.project(prec, ft, func)
+    P = make_operator(mw, mra, args)
+    funcs = workload_inputs(mw, args, args.cpu_centers)
+    fts = []
+    for func in funcs:
+        ft = mw.FunctionTree(mra)
+        orc.project(prec, ft, func)
+        fts.append(ft)
+    func = funcs[0]
     times, nodes, tuples = [], 0, 0
     for it in range(args.warmup + args.steps):
-        gt = mw.FunctionTree(mra)
-        t0 = time.perf_counter()
-        st = orc.apply(prec, gt, P, ft)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-            nodes += st.gNodes
-            tuples += st.fApplied
+        for ft in fts:
+            gt = mw.FunctionTree(mra)
+            t0 = time.perf_counter()
+            st = orc.apply(prec, gt, P, ft)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+                nodes += st.gNodes
+                tuples += st.fApplied
     total = sum(times)
     value = nodes / total
     K = k + 1
     port_value = value
     cb = {"value": value, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
-          "sample": f"{args.cpu_centers}-centre subset of the workload density, full adaptive apply"}
+          "sample": sample_text(args) + ", full adaptive apply"}
     # the REAL reference, when its sources were compiled in place (oracle/_ref, Eigen replaced by the eager stand-in of
     # oracle/eigen_shim, which costs it temporaries real Eigen does not have): timed on the same sample; the line reports
     # the FASTER of the two CPU implementations so that the ratio against the GPU arm is the conservative one
@@ -171,7 +218,7 @@ def run_reference(args, rank, world):
             rm = ref.MRA(k, -4, (-1, -1, -1), (2, 2, 2), 25)
             rf = ref.Tree(rm)
             ref.project(prec, rf, list(func))
-            RP = ref.poisson(rm, prec)
+            RP = ref.helmholtz(rm, 1.0, prec) if args.operator == "helmholtz" else ref.poisson(rm, prec)
             rt, rn = [], 0
             for it in range(1 + min(args.steps, 2)):
                 rg = ref.Tree(rm)
@@ -192,10 +239,12 @@ def run_reference(args, rank, world):
         except Exception as e:  # noqa: BLE001
             cb["reference_in_place_error"] = repr(e)
     line = {
-        "impl": "reference", "metric": "poisson_apply_output_nodes_per_s", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "helmholtz_apply_output_nodes_per_s" if args.operator == "helmholtz" else "poisson_apply_output_nodes_per_s",
+        "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.centers),  # the GPU arm's workload; each step here is the bounded sample below
+        # the workload this arm REALLY times: the bounded CPU sample (config.sample_of names the GPU arm's full workload)
+        "config": workload_config(args, args.cpu_centers, sample=True),
         "fp64_tflops": tuples * 6 * K ** 4 / (nodes / value) / 1e12,
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,15 +252,36 @@ def run_reference(args, rank, world):
     emit(json.dumps(line))
 
 
+def workload_name(args, centers):
+    if args.operator == "helmholtz":
+        return f"helmholtz_apply_k{args.order}_prec{args.prec:g}_mu1_orbitals{centers}"
+    return f"poisson_apply_k{args.order}_prec{args.prec:g}_gauss{centers}"
+
+
+def sample_text(args):
+    if args.operator == "helmholtz":
+        return f"the first {args.cpu_centers} of the workload's {args.centers} orbital trees"
+    if args.cpu_centers == args.centers:
+        return "the whole workload"
+    return f"a {args.cpu_centers}-centre density of the workload's generator (same seed; the workload has {args.centers} centres)"
+
+
 def workload_config(args, centers, sample=False):
-    return {"workload": f"poisson_apply_k{args.order}_prec{args.prec:g}_gauss{centers}" + ("_cpu_sample" if sample else ""),
+    cfg = {"workload": workload_name(args, centers) + ("_cpu_sample" if sample and centers != args.centers else ""),
+           "config": args.config}
+    if sample and centers != args.centers:
+        cfg["sample_of"] = workload_name(args, args.centers)
+    cfg.update({
             "order": args.order, "prec": args.prec, "centers": centers, "world": "[-16,16]^3 root scale -4, max depth 25",
-            "operator": "PoissonOperator(prec)", "mode": "adaptive (maxIter=-1)",
+            "operator": "HelmholtzOperator(mu=1, prec)" if args.operator == "helmholtz" else "PoissonOperator(prec)",
+            "mode": "adaptive (maxIter=-1)",
             "l2_policy": "fresh output tree each step; input tree + operator tables exceed nothing: working set per step "
                          "is re-generated (generated input nodes, output coefficients) and an L2 flush buffer (256 MB) is written between steps",
             "parallelism": "output-node list of every refinement iteration dealt out cyclically over the ranks, input tree + "
                            "operator replicated, NCCL all-gather of component norms, output coefficient blocks pushed to the "
-                           "peers over NVLink (CUDA IPC, copy engines)"}
+                           "peers over NVLink (CUDA IPC, copy engines)" if args.operator != "helmholtz" else
+                           "independent orbital trees dealt out over the ranks (tree j -> rank j % N), no data-path collective"})
+    return cfg
 
 
 def main():
@@ -220,14 +290,21 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--order", type=int, default=7)
-    ap.add_argument("--prec", type=float, default=1e-7)
-    ap.add_argument("--centers", type=int, default=1000)
-    ap.add_argument("--cpu-centers", type=int, default=16)
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
+    ap.add_argument("--order", type=int, default=None)
+    ap.add_argument("--prec", type=float, default=None)
+    ap.add_argument("--centers", type=int, default=None)
+    ap.add_argument("--cpu-centers", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    order, prec, centers, cpu_centers, operator = CONFIGS[args.config]
+    args.order = order if args.order is None else args.order
+    args.prec = prec if args.prec is None else args.prec
+    args.centers = centers if args.centers is None else args.centers
+    args.cpu_centers = min(cpu_centers if args.cpu_centers is None else args.cpu_centers, args.centers)
+    args.operator = operator
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,21 +337,26 @@ def main():
     k, prec, K = args.order, args.prec, args.order + 1
     mra = mw.MultiResolutionAnalysis(k, -4, (-1, -1, -1), (2, 2, 2), 25)
     t0 = time.perf_counter()
-    P = mw.PoissonOperator(mra, prec)
+    P = make_operator(mw, mra, args)
     t_oper = time.perf_counter() - t0
-    func = density(mw, args.centers, 42)  # same density on every rank: the apply is sharded, not the data
+    by_tree = args.operator == "helmholtz"  # independent orbital trees: dealt out over the ranks, no exchange
+    funcs = workload_inputs(mw, args, args.centers)  # same inputs on every rank
     comm = None
-    if world > 1:
+    if world > 1 and not by_tree:
         def _bcast(b):
             obj = [b]
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
         comm = mw.Comm(rank, world, _bcast)
-    ft = mw.FunctionTree(mra)
+    mine = [j for j in range(len(funcs)) if (not by_tree) or j % world == rank]
     t0 = time.perf_counter()
-    mw.project(prec, ft, func, device=True)  # quadrature, transforms and norms on the GPU; the host keeps the topology
+    fts = []
+    for j in mine:
+        ft = mw.FunctionTree(mra)
+        mw.project(prec, ft, funcs[j], device=True)  # quadrature, transforms and norms on the GPU; the host keeps the topology
+        ft.sync_device()
+        fts.append(ft)
     t_proj = time.perf_counter() - t0
-    ft.sync_device()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -283,20 +365,51 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(e2e):
+    class Acc:
+        def __init__(self):
+            self.ms = 0.0
+            self.nodes = self.tuples = self.tuples_rank = self.launches = self.h2d = self.d2h = self.iters = 0
+            self.kern_ms = self.contract_ms = 0.0
+            self.phases = {"ms_build": 0.0, "ms_post": 0.0, "ms_upload": 0.0}
+            self.last = None
+
+    def one_step(e2e, acc=None, trees=None, oper=None):
+        """one pass of the hot path over the workload: one apply per input tree of this rank"""
+        trees = fts if trees is None else trees
+        oper = P if oper is None else oper
         flush.fill_(1)  # L2 flush between timed iterations (untimed: the timer runs on the library stream)
         torch.cuda.synchronize()
         if e2e:
-            ft.drop_device()  # input starts in (pinned) host memory
-        out = mw.FunctionTree(mra)
+            for ft in trees:
+                ft.drop_device()  # input starts in (pinned) host memory
+        step_h2d = step_d2h = 0
         L.mrx_timer_start()
-        st = mw.apply(prec, out, P, ft, comm=comm)
-        if e2e and rank == 0:
-            out.sync_host()  # result back in host memory (every rank holds the identical tree in HBM; rank 0 reads it back)
+        sts = []
+        for ft in trees:
+            out = mw.FunctionTree(mra)
+            st = mw.apply(prec, out, oper, ft, comm=comm)
+            if e2e and (rank == 0 or by_tree):
+                out.sync_host()  # result back in host memory (sharded apply: every rank holds the identical tree, rank 0 reads it back)
+                step_d2h += out.nbytes()
+            step_h2d += st.h2d_bytes  # counted by the library: coefficient blocks gathered from host memory + norms + topology
+            sts.append(st)
+            del out
         ms = L.mrx_timer_stop_ms()
-        nbytes_out = out.nbytes()
-        del out
-        return st, ms, nbytes_out
+        if acc is not None:
+            acc.ms += ms
+            for st in sts:
+                acc.nodes += st.g_nodes
+                acc.tuples += st.f_applied
+                acc.tuples_rank += st.f_applied_rank
+                acc.launches += st.kernel_launches
+                acc.iters += st.iterations
+                acc.kern_ms += st.ms_kernel
+                acc.contract_ms += st.ms_contract
+                for kk in acc.phases:
+                    acc.phases[kk] += getattr(st, kk)
+            acc.last = sts
+            acc.h2d, acc.d2h = step_h2d, step_d2h
+        return ms
 
     # ---- resident-input arm
     for _ in range(args.warmup):
@@ -304,85 +417,109 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    tot_ms = 0.0
-    nodes = tuples = launches = 0
-    kern_ms = 0.0
-    contract_ms = 0.0
-    phases = {"ms_build": 0.0, "ms_post": 0.0, "ms_upload": 0.0}
-    last = None
+    A = Acc()
     for _ in range(args.steps):
-        st, ms, _ = one_step(False)
-        tot_ms += ms
-        nodes += st.g_nodes
-        tuples += st.f_applied
-        launches += st.kernel_launches
-        kern_ms += st.ms_kernel
-        contract_ms += st.ms_contract
-        for kk in phases:
-            phases[kk] += getattr(st, kk)
-        last = st
+        one_step(False, A)
     barrier()
     clocks = sampler.stop()
 
     # ---- end-to-end arm (host buffers in, host buffers out)
     one_step(True)
     barrier()
-    e2e_ms = 0.0
-    e2e_nodes = 0
-    h2d = d2h = 0
+    E = Acc()
     for _ in range(args.steps):
-        st, ms, nb_out = one_step(True)
-        e2e_ms += ms
-        e2e_nodes += st.g_nodes
-        h2d = st.h2d_bytes  # counted by the library: coefficient blocks gathered from host memory + norms + topology
-        d2h = nb_out if rank == 0 else 0
+        one_step(True, E)
     barrier()
 
+    tot_ms, e2e_ms = A.ms, E.ms
+    nodes, tuples, launches, h2d, d2h = A.nodes, A.tuples, A.launches, E.h2d, E.d2h
+    e2e_nodes = E.nodes
     if world > 1:
         t = torch.tensor([tot_ms, e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_ms, e2e_ms = float(t[0]), float(t[1])
-        # output nodes and surviving tuples are whole-job counts already (every rank holds the full topology; the library
-        # sums the tuple counters over ranks); launches and copied bytes add up over ranks
-        c = torch.tensor([launches, h2d, d2h], dtype=torch.float64, device="cuda")
+        # sharded apply: output nodes and surviving tuples are whole-job counts already (every rank holds the full topology; the
+        # library sums the tuple counters over ranks). Trees dealt out over the ranks: the counts add up. Launches and copied
+        # bytes add up over ranks in both cases.
+        c = torch.tensor([launches, h2d, d2h, nodes if by_tree else 0, tuples if by_tree else 0, e2e_nodes if by_tree else 0],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        launches, h2d, d2h = (int(x) for x in c.tolist())
-        km = torch.tensor([kern_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(km, op=dist.ReduceOp.MAX)
-        kern_ms_max = float(km[0])
-    else:
-        kern_ms_max = kern_ms
+        launches, h2d, d2h = (int(x) for x in c.tolist()[:3])
+        if by_tree:
+            nodes, tuples, e2e_nodes = (int(x) for x in c.tolist()[3:])
 
     if rank == 0:
+        # FP64 tensor peak measured in this run, with its own clock record (MEASURED_PEAKS.json has no FP64 entry)
+        psamp = ClockSampler(local_rank, period_s=0.005)
+        psamp.start()
         peak_dmma = L.mrx_bench_dmma_tflops(20000)
         peak_dfma = L.mrx_bench_dfma_tflops(20000)
+        peak_clocks = psamp.stop()
         flops = tuples * 6.0 * K ** 4
         # rank 0's contraction kernel and the tuples rank 0 contracted
-        achieved = (last.f_applied_rank * 6.0 * K ** 4 * args.steps) / (contract_ms * 1e-3) / 1e12
+        achieved = (A.tuples_rank * 6.0 * K ** 4) / (A.contract_ms * 1e-3) / 1e12
+        kernel = "pipe_contract_kernel" if k == 7 else "pipe_contract_coop_kernel<%d>" % K
+        napply = len(A.last)
+        last = A.last[-1]
         line = {
-            "metric": "poisson_apply_output_nodes_per_s", "value": nodes / (tot_ms * 1e-3), "unit": "nodes/s",
+            "metric": "poisson_apply_output_nodes_per_s" if not by_tree else "helmholtz_apply_output_nodes_per_s",
+            "value": nodes / (tot_ms * 1e-3), "unit": "nodes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.centers),
             "fp64_tflops": flops / (tot_ms * 1e-3) / 1e12,
             "fp64_tflops_frac_of_dmma_peak": flops / (tot_ms * 1e-3) / 1e12 / (peak_dmma * world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
-                         "traffic": None, "kernel": "pipe_contract_kernel" if k == 7 else "pipe_contract_coop_kernel",
+                         "traffic": None, "kernel": kernel,
                          "peak_source": "FP64 DMMA m8n8k4 micro-benchmark measured in this run (no FP64 figure in "
                                         "MEASURED_PEAKS.json); DFMA peak %.1f TFLOP/s" % peak_dfma,
-                         "kernel_share_of_step": contract_ms / tot_ms, "all_apply_kernels_share_of_step": kern_ms / tot_ms},
+                         "peak_clocks": peak_clocks,
+                         "peak_arithmetic_limit": "148 SM x 128 flop/clk x sm_mhz",
+                         "kernel_share_of_step": A.contract_ms / A.ms, "all_apply_kernels_share_of_step": A.kern_ms / A.ms},
             "clocks": clocks,
             "e2e": {"value": e2e_nodes / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "detail": {"output_nodes_per_step": last.g_nodes, "final_tree_nodes": last.n_nodes_out, "iterations": last.iterations,
-                       "tuples_per_step": last.f_applied, "generated_input_nodes": last.gen_nodes, "input_tree_nodes": ft.getNNodes(),
-                       "separation_rank": P.size(), "ms_kernel_per_step": kern_ms / args.steps, "ms_contract_per_step": contract_ms / args.steps,
-                       "ms_build_per_step": phases["ms_build"] / args.steps, "ms_post_per_step": phases["ms_post"] / args.steps,
+            "detail": {"applies_per_step_this_rank": napply, "output_nodes_per_step": nodes // args.steps,
+                       "final_tree_nodes_last_apply": last.n_nodes_out, "iterations_last_apply": last.iterations,
+                       "tuples_per_step": tuples // args.steps, "generated_input_nodes_last_apply": last.gen_nodes,
+                       "input_tree_nodes": sum(ft.getNNodes() for ft in fts),
+                       "separation_rank": P.size(), "ms_kernel_per_step": A.kern_ms / args.steps,
+                       "ms_contract_per_step": A.contract_ms / args.steps,
+                       "ms_build_per_step": A.phases["ms_build"] / args.steps, "ms_post_per_step": A.phases["ms_post"] / args.steps,
+                       "ms_not_in_kernels_per_step": (A.ms - A.kern_ms) / args.steps,
                        "setup_s": {"operator": t_oper, "projection": t_proj}},
         }
-        line["roofline"]["traffic"] = ncu_traffic()
-        line["transforms"] = transforms_roofline(L, ft, K)
+        # achieved and traffic are both PER LAUNCH averages of the contraction kernel (one launch per refinement iteration)
+        line["roofline"]["launches_in_timed_region"] = A.iters
+        line["roofline"]["achieved_flop_per_launch"] = A.tuples_rank * 6.0 * K ** 4 / max(A.iters, 1)
+        line["roofline"]["traffic"], line["roofline"]["traffic_source"] = ncu_traffic(kernel, k, A.tuples_rank / max(A.iters, 1))
+        if world == 1 and args.config == "headline":
+            line["transforms"] = transforms_roofline(L, fts[0], K)
+        if world == 1 and args.cpu_centers != args.centers:
+            # the workload the reference arm times (bench.py --impl reference), on the GPU: a ratio on IDENTICAL inputs can be
+            # formed from this object and the reference arm's line. Small workload: launch- and latency-bound on a B200.
+            sfuncs = workload_inputs(mw, args, args.cpu_centers)
+            sft = []
+            for fn in sfuncs:
+                t_ = mw.FunctionTree(mra)
+                mw.project(prec, t_, fn, device=True)
+                t_.sync_device()
+                sft.append(t_)
+            for _ in range(3):
+                one_step(False, None, sft)
+            Sa, Se = Acc(), Acc()
+            for _ in range(args.steps):
+                one_step(False, Sa, sft)
+            one_step(True, None, sft)
+            for _ in range(args.steps):
+                one_step(True, Se, sft)
+            line["same_workload_as_reference_arm"] = {
+                "config": workload_config(args, args.cpu_centers, sample=True),
+                "value": Sa.nodes / (Sa.ms * 1e-3), "unit": "nodes/s", "ms_per_step": Sa.ms / args.steps,
+                "e2e_value": Se.nodes / (Se.ms * 1e-3), "e2e_ms_per_step": Se.ms / args.steps,
+                "output_nodes_per_step": Sa.nodes // args.steps, "tuples_per_step": Sa.tuples // args.steps}
+            del sft
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only (all host cores free)
             line["cpu_baseline"] = cpu_baseline(args, mw, mra, P)
         emit(json.dumps(line))
@@ -391,15 +528,24 @@ def main():
         dist.destroy_process_group()
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the contraction kernel from the committed ncu --set full capture
-    (profiles/traffic.json, written by tools/ncu_summary.py): bytes of the largest captured launch, or None"""
+def ncu_traffic(kernel, order, tuples_per_launch):
+    """DRAM traffic of the contraction kernel PER LAUNCH (dram__bytes_read.sum + dram__bytes_write.sum): the bytes-per-tuple figure
+    of the committed `ncu --set full` capture (profiles/traffic.json: kernel, order, captured tuples and bytes, source report,
+    commit) times the average tuples per launch of THIS run. Returned only when the capture is of the same kernel and order as
+    the run; otherwise (None, reason). It is a scaled capture, not a counter read in this run - the source says so."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f)
-    except Exception:  # noqa: BLE001
-        return None
+            t = json.load(f)
+        if not isinstance(t, dict):
+            return None, "profiles/traffic.json carries no kernel/order tag"
+        if t.get("kernel") != kernel.split("<")[0] or int(t.get("order", -1)) != order:
+            return None, "profiles/traffic.json is a capture of %s at k=%s, not of this run's kernel" % (t.get("kernel"), t.get("order"))
+        return float(t["bytes_per_tuple"]) * tuples_per_launch, (
+            "ncu --set full capture %s (commit %s): %.1f B/tuple x this run's average tuples per launch" %
+            (t.get("source"), t.get("commit"), float(t["bytes_per_tuple"])))
+    except Exception as e:  # noqa: BLE001
+        return None, "no capture (%r)" % (e,)
 
 
 def transforms_roofline(L, ft, K):
@@ -430,25 +576,33 @@ def transforms_roofline(L, ft, K):
 
 
 def cpu_baseline(args, mw, mra, P):
-    """oracle (kind: port) on a bounded sample: same operator, cpu_centers-centre density, all host threads"""
+    """oracle (kind: port) on a bounded sample: same operator, the CPU sample of the workload, all host threads"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from mrcpp_b200 import build
     build.build_oracle()
     import oracle_api as orc
-    func = density(mw, args.cpu_centers, 42)
-    ft = mw.FunctionTree(mra)
-    orc.project(args.prec, ft, func)
+    fts = []
+    for func in workload_inputs(mw, args, args.cpu_centers):
+        ft = mw.FunctionTree(mra)
+        orc.project(args.prec, ft, func)
+        fts.append(ft)
     # one untimed pass first: in this process host node storage is pinned (cudaMallocHost), and the first pass pays for
     # allocating it; the reference arm (bench.py --impl reference, no CUDA) has no such cost
-    orc.apply(args.prec, mw.FunctionTree(mra), P, ft)
-    gt = mw.FunctionTree(mra)
-    t0 = time.perf_counter()
-    st = orc.apply(args.prec, gt, P, ft)
-    dt = time.perf_counter() - t0
+    orc.apply(args.prec, mw.FunctionTree(mra), P, fts[0])
+    nodes = tuples = 0
+    dt = 0.0
+    for ft in fts:
+        gt = mw.FunctionTree(mra)
+        t0 = time.perf_counter()
+        st = orc.apply(args.prec, gt, P, ft)
+        dt += time.perf_counter() - t0
+        nodes += st.gNodes
+        tuples += st.fApplied
     K = args.order + 1
-    return {"value": st.gNodes / dt, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"{args.cpu_centers}-centre subset of the workload density, one full adaptive apply after one warm-up ({dt:.1f} s)",
-            "fp64_tflops": st.fApplied * 6 * K ** 4 / dt / 1e12, "output_nodes": st.gNodes}
+    return {"value": nodes / dt, "unit": "nodes/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": sample_text(args) + f", one full adaptive apply per tree after one warm-up ({dt:.1f} s)",
+            "config": workload_config(args, args.cpu_centers, sample=True),
+            "fp64_tflops": tuples * 6 * K ** 4 / dt / 1e12, "output_nodes": nodes}
 
 
 if __name__ == "__main__":

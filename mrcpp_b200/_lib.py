@@ -7,8 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# MRX_LIB_PATH: load another build of the same C ABI (the tests use it for the host-driver mock of tests/cpp/cuda_mock)
-LIB_PATH = os.environ.get("MRX_LIB_PATH") or os.path.join(_HERE, "lib", "libmrcpp_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", "libmrcpp_b200.so")  # the one library of the product; no switch, no fallback
 TABLES = os.path.join(_HERE, "data", "mwtables.bin")
 
 

@@ -21,3 +21,16 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("poisson_apply_k7_prec")
+    # the arm states the workload it REALLY times: the bounded CPU sample, and which full workload it is a sample of
+    assert d["config"]["centers"] == 1 and d["config"]["workload"].endswith("_cpu_sample")
+    assert d["config"]["sample_of"].endswith("_gauss1000")
+
+
+def test_reference_arm_config_c4_helmholtz_one_orbital():
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c4", "--steps", "1", "--warmup", "3",
+           "--prec", "1e-3", "--order", "5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][0])
+    assert d["metric"] == "helmholtz_apply_output_nodes_per_s" and d["config"]["config"] == "c4" and d["config"]["centers"] == 1
+    assert d["config"]["operator"].startswith("HelmholtzOperator")

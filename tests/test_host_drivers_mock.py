@@ -20,7 +20,7 @@ def mock_lib(libs):
 
 
 def test_tree_algebra_gpu_tests_on_the_mock(mock_lib):
-    env = dict(os.environ, MRX_LIB_PATH=mock_lib)
+    env = dict(os.environ, MRX_TEST_MOCK_LIB=mock_lib)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(cb.ROOT, "tests", "test_zz2_gpu_tree_algebra.py"), "-m", "gpu", "-x", "-q",
                         "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=cb.ROOT, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -30,7 +30,7 @@ def test_tree_algebra_gpu_tests_on_the_mock(mock_lib):
 def test_projection_and_transform_gpu_tests_on_the_mock(mock_lib):
     """the device projection driver (csrc/cuda/project.cu: refinement loop, pre-built grids), whole-tree transforms, upload /
     download, dot: the cases of the GPU suite that do not depend on the apply kernels' own counters"""
-    env = dict(os.environ, MRX_LIB_PATH=mock_lib)
+    env = dict(os.environ, MRX_TEST_MOCK_LIB=mock_lib)
     files = [os.path.join(cb.ROOT, "tests", f) for f in ("test_gpu_parity.py", "test_zz1_gpu_reference.py")]
     r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-k",
                         "device_projection or identity or golden or vs_real_reference or bottom_up or top_down or hydrogen"],
