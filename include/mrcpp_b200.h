@@ -26,6 +26,8 @@ typedef struct mrx_oper mrx_oper; /* ConvolutionOperator<3> / DerivativeOperator
 typedef struct mrx_comm mrx_comm; /* one rank of a multi-GPU job (NCCL communicator over NVLink)          */
 
 enum { MRX_TOP_DOWN = 0, MRX_BOTTOM_UP = 1 }; /* api/constants.h TopDown/BottomUp */
+enum { MRX_FORWARD = 0, MRX_BACKWARD = 1 };          /* api/constants.h:48 CV_Transform */
+enum { MRX_COMPRESSION = 0, MRX_RECONSTRUCTION = 1 }; /* api/constants.h:49 MW_Transform */
 
 /* counters of one apply; mirrors OperatorStatistics (src/operators/OperatorStatistics.cpp:83-106) */
 typedef struct mrx_apply_stats {
@@ -185,10 +187,26 @@ int mrx_shard_cyclic_row(int i, int n, int world);
  * calls it with identical arguments. stats->f_applied / gen_nodes are summed over ranks. */
 int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
                       const mrx_comm *comm, mrx_apply_stats *stats);
+/* mrcpp::apply(prec, out, oper, inp, precTrees, maxIter, absPrec): src/treebuilders/apply.cpp:214-251. The precision is scaled
+ * per output node by 1 / max_i sqrt(maxSquareNorm of prec_trees[i] at the node's index) (makeMaxSquareNorms, MWTree.cpp:536-543;
+ * where a precision tree is coarser than the output grid the generated node's own scaled norm, MWNode.h:84), in the screening
+ * threshold (ConvolutionCalculator.cpp:241-248) and in the split threshold (WaveletAdaptor.h:51-54). n_prec = 0: factor 1.
+ * comm == NULL: one GPU; otherwise sharded like mrx_apply_sharded (collective). */
+int mrx_apply_prec_trees(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int n_prec, mrx_tree *const *prec_trees,
+                         int max_iter, int abs_prec, const mrx_comm *comm, mrx_apply_stats *stats);
 /* mrcpp::apply(out, DerivativeOperator, inp, dir): src/treebuilders/apply.cpp:379-412 */
 int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, mrx_apply_stats *stats);
 /* MWTree::mwTransform(type, overwrite): src/trees/MWTree.cpp:143-216 (+ norms of touched nodes) */
 int mrx_mw_transform(mrx_tree *tree, int type, int overwrite);
+/* MWNode::mwTransform(kind): src/trees/MWNode.cpp:557-594 -- in-node compression / reconstruction of the listed nodes (slots in
+ * node-store order; n_nodes < 0: every node), in place on the resident node store; component norms are refreshed. */
+int mrx_node_mw_transform(mrx_tree *tree, int kind /* MRX_COMPRESSION | MRX_RECONSTRUCTION */, int n_nodes, const int *slots);
+/* MWNode::cvTransform(kind): src/trees/MWNode.cpp:448-490 -- scaling coefficients of the children (0/1 representation, i.e. after
+ * MRX_RECONSTRUCTION) <-> function values at the children's quadrature points, for the listed nodes, in place. */
+int mrx_node_cv_transform(mrx_tree *tree, int kind /* MRX_FORWARD | MRX_BACKWARD */, int n_nodes, const int *slots);
+/* measurement: cvTransform(Forward) then (Backward) over every node, `reps` times between CUDA events; returns ms per pass
+ * (algorithmic traffic 128 K^3 B per node and pass) */
+double mrx_bench_cv_transform(mrx_tree *tree, int reps);
 /* MWTree::calcSquareNorm: src/trees/MWTree.cpp:109-118 */
 double mrx_calc_square_norm(mrx_tree *tree);
 /* mrcpp::dot(bra, ket): src/treebuilders/multiply.cpp:286-318 */

@@ -19,6 +19,8 @@ from ._lib import ApplyStats
 
 TopDown = 0   # api/constants.h
 BottomUp = 1
+Forward, Backward = 0, 1             # CV_Transform
+Compression, Reconstruction = 0, 1   # MW_Transform
 
 
 def _ip(a):
@@ -137,6 +139,16 @@ class FunctionTree:
 
     def mwTransform(self, kind, overwrite=True):
         _lib.load().mrx_mw_transform(self._h, kind, 1 if overwrite else 0)
+
+    def nodeMwTransform(self, kind, slots=None):
+        """MWNode::mwTransform(kind) (src/trees/MWNode.cpp:557-594) of the listed nodes (None: every node), in place"""
+        a = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        _lib.load().mrx_node_mw_transform(self._h, int(kind), -1 if a is None else len(a), None if a is None else _ip(a))
+
+    def nodeCvTransform(self, kind, slots=None):
+        """MWNode::cvTransform(kind) (src/trees/MWNode.cpp:448-490) of the listed nodes (None: every node), in place"""
+        a = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        _lib.load().mrx_node_cv_transform(self._h, int(kind), -1 if a is None else len(a), None if a is None else _ip(a))
 
     def calcSquareNorm(self):
         return _lib.load().mrx_calc_square_norm(self._h)
@@ -390,13 +402,19 @@ def shard_cyclic_row(i, n, world):
     return _lib.load().mrx_shard_cyclic_row(int(i), int(n), int(world))
 
 
-def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None, comm=None):
+def apply(prec, out, oper, inp, maxIter=-1, absPrec=False, dir=None, comm=None, precTrees=None):
     """mrcpp::apply. ConvolutionOperator form: apply(prec, out, oper, inp, maxIter, absPrec)
-    (src/treebuilders/apply.cpp:68-93); derivative form: apply(None, out, D, inp, dir=d) (:379-412).
+    (src/treebuilders/apply.cpp:68-93); derivative form: apply(None, out, D, inp, dir=d) (:379-412);
+    precTrees=[trees]: apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (:214-251), precision scaled per output node
+    by the largest norms of the precision trees.
     comm: shard the apply over the ranks of a Comm (collective call). Returns the work counters
     (OperatorStatistics)."""
     st = ApplyStats()
-    if dir is not None:
+    if precTrees is not None:
+        h = (C.c_void_p * max(len(precTrees), 1))(*[t._h for t in precTrees])
+        _lib.load().mrx_apply_prec_trees(float(prec), out._h, oper._h, inp._h, len(precTrees), h, int(maxIter), 1 if absPrec else 0,
+                                         comm._h if comm is not None else None, C.byref(st))
+    elif dir is not None:
         _lib.load().mrx_apply_derivative(out._h, oper._h, inp._h, int(dir), C.byref(st))
     elif comm is not None:
         _lib.load().mrx_apply_sharded(float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, comm._h, C.byref(st))

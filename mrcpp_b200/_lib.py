@@ -90,6 +90,7 @@ SIGNATURES = {
     "mrx_helmholtz_kernel": (_I, [_D, _D, _D, _D, _PD, _PD, _I]),
     "mrx_apply": (_I, [_D, _P, _P, _P, _I, _I, C.POINTER(ApplyStats)]),
     "mrx_apply_sharded": (_I, [_D, _P, _P, _P, _I, _I, _P, C.POINTER(ApplyStats)]),
+    "mrx_apply_prec_trees": (_I, [_D, _P, _P, _P, _I, C.POINTER(C.c_void_p), _I, _I, _P, C.POINTER(ApplyStats)]),
     "mrx_comm_unique_id": (_I, [C.c_char_p]),
     "mrx_comm_create": (_P, [_I, _I, C.c_char_p]),
     "mrx_comm_destroy": (None, [_P]),
@@ -100,6 +101,9 @@ SIGNATURES = {
     "mrx_shard_cyclic_row": (_I, [_I, _I, _I]),
     "mrx_apply_derivative": (_I, [_P, _P, _P, _I, C.POINTER(ApplyStats)]),
     "mrx_mw_transform": (_I, [_P, _I, _I]),
+    "mrx_node_mw_transform": (_I, [_P, _I, _I, _PI]),
+    "mrx_node_cv_transform": (_I, [_P, _I, _I, _PI]),
+    "mrx_bench_cv_transform": (_D, [_P, _I]),
     "mrx_calc_square_norm": (_D, [_P]),
     "mrx_dot": (_D, [_P, _P]),
     "mrx_tree_rescale": (_I, [_P, _D]),

@@ -24,6 +24,7 @@ SOURCES = [
     "cuda/apply_pipeline.cu",
     "cuda/apply_enum.cu",
     "cuda/apply_split.cu",
+    "cuda/apply_prec.cu",
     "cuda/comm.cu",
     "cuda/microbench.cu",
 ]

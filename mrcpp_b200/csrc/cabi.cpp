@@ -707,6 +707,15 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
     device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats);
     return 0;
 }
+int mrx_apply_prec_trees(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int n_prec, mrx_tree *const *prec_trees, int max_iter,
+                         int abs_prec, const mrx_comm *comm, mrx_apply_stats *stats) {
+    require_device("mrx_apply_prec_trees");
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (oper->op.derivative) MRX_ABORT("mrx_apply_prec_trees: derivative operator passed to the convolution apply");
+    std::vector<mrx_tree *> pt(prec_trees, prec_trees + (n_prec > 0 ? n_prec : 0));
+    device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats, comm, &pt);
+    return 0;
+}
 double mrx_bench_mw_transform(mrx_tree *tree, int type, int reps, int *branch_nodes) {
     require_device("mrx_bench_mw_transform");
     double ms = 0.0;
@@ -735,6 +744,24 @@ int mrx_mw_transform(mrx_tree *tree, int type, int overwrite) {
     if (type != MRX_BOTTOM_UP && type != MRX_TOP_DOWN) MRX_ABORT("Invalid wavelet transform");
     device_mw_transform(*tree, type, overwrite != 0);
     return 0;
+}
+int mrx_node_mw_transform(mrx_tree *tree, int kind, int n_nodes, const int *slots) {
+    require_device("mrx_node_mw_transform");
+    if (kind != MRX_COMPRESSION && kind != MRX_RECONSTRUCTION) MRX_ABORT("Invalid operation");
+    device_node_transform(*tree, 0, kind == MRX_COMPRESSION ? 0 : 1, n_nodes, slots);
+    return 0;
+}
+int mrx_node_cv_transform(mrx_tree *tree, int kind, int n_nodes, const int *slots) {
+    require_device("mrx_node_cv_transform");
+    if (kind != MRX_FORWARD && kind != MRX_BACKWARD) MRX_ABORT("Invalid operation");
+    device_node_transform(*tree, 1, kind == MRX_FORWARD ? 0 : 1, n_nodes, slots);
+    return 0;
+}
+double mrx_bench_cv_transform(mrx_tree *tree, int reps) {
+    require_device("mrx_bench_cv_transform");
+    double ms = 0.0;
+    device_node_transform(*tree, 1, 0, -1, nullptr, reps > 0 ? reps : 1, &ms);
+    return ms;
 }
 double mrx_calc_square_norm(mrx_tree *tree) {
     require_device("mrx_calc_square_norm");

@@ -112,6 +112,10 @@ struct Scratch {
     bool hasBranchFlags = false;
     DevBuf<double> scaleFac, state;
     DevBuf<SplitResult> splitRes;
+    // locally scaled precision (apply with precTrees, apply_prec.cu)
+    DevBuf<double> precAll[2], precLoc; // factors of the whole work vector (current / next) and of this rank's share
+    DevBuf<PrecTreeDev> precTreeTab;
+    std::vector<std::unique_ptr<DevBuf<double>>> precVReal;
     // lazy residency of the input tree
     DevBuf<int> fetchList, fetchCnt;
     DevBuf<unsigned long long> fetchTotal;
@@ -766,7 +770,7 @@ static void run_apply_legacy(double prec, mrx_tree &out, mrx_oper &oper, mrx_tre
 // host's critical path loops over nodes (except the one-off set-up of the first work vector).
 static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
                            std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm,
-                           std::vector<std::vector<int>> *branchPairs = nullptr) {
+                           std::vector<std::vector<int>> *branchPairs = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
@@ -833,6 +837,51 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         pend.active = false;
     };
 
+    // ---- precision trees (apply.cpp:214-234): per real node the value getMaxSquareNorm() answers after makeMaxSquareNorms
+    //      (stored maximum over the node and its descendants if positive, else the node's own scaled square norm), computed from
+    //      the host's norms (children have larger slots than their parent) and uploaded; node stores and topologies resident
+    const bool usePrec = precTrees != nullptr;
+    PrecParams PR{};
+    if (usePrec) {
+        std::vector<PrecTreeDev> tab;
+        for (mrx_tree *pt : *precTrees) {
+            Tree<3> &t = pt->host;
+            if (!(t.mra == g.mra)) MRX_ABORT("Incompatible MRA");
+            ensure_input_topology(*pt, st);
+            std::vector<double> v(t.nReal);
+            for (int n = t.nReal - 1; n >= 0; n--) {
+                const double own = std::pow(2.0, 3 * t.nodes[n].scale) * t.sqn[n];
+                double mx = own;
+                if (t.isBranch(n) && t.nodes[n].child0 < t.nReal)
+                    for (int c = 0; c < 8; c++) mx = std::max(mx, v[t.nodes[n].child0 + c]);
+                v[n] = mx;
+            }
+            // getMaxSquareNorm (MWNode.h:84): a stored maximum that is not positive falls back to the node's own scaled norm,
+            // which is then 0 as well: v[n] as computed covers both cases
+            auto buf = std::make_unique<DevBuf<double>>();
+            buf->reserve(std::max(t.nReal, 1), false, st);
+            MRX_CUDA(cudaMemcpyAsync(buf->p, v.data(), sizeof(double) * t.nReal, cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaStreamSynchronize(st)); // v is a local
+            tab.push_back(PrecTreeDev{pt->dev.topoChild0.p, pt->dev.coefs.p, buf->p});
+            scr.precVReal.push_back(std::move(buf));
+        }
+        scr.precTreeTab.reserve(std::max<size_t>(tab.size(), 1), false, st);
+        if (!tab.empty()) {
+            MRX_CUDA(cudaMemcpyAsync(scr.precTreeTab.p, tab.data(), sizeof(PrecTreeDev) * tab.size(), cudaMemcpyHostToDevice, st));
+            MRX_CUDA(cudaStreamSynchronize(st));
+        }
+        PR.depthShift = op.operRoot - g.mra.rootScale;
+        PR.trees = scr.precTreeTab.p;
+        PR.nTrees = (int)tab.size();
+        for (int x = 0; x < 3; x++) {
+            PR.corner[x] = g.mra.corner[x];
+            PR.nboxes[x] = g.mra.nboxes[x];
+        }
+        PR.K = K;
+        PR.rootScale = g.mra.rootScale;
+        PR.filters = filt;
+    }
+
     // ---- first work vector: from the host topology
     int nG = (int)workVec.size();
     int minDep = 1 << 30, maxDep = -(1 << 30);
@@ -885,6 +934,18 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         scr.gslots.reserve(capL, false, st);
         scr.chunkOff.reserve(capL + 1, false, st);
         PrepParams PP{};
+        if (usePrec) {
+            // precision factors of the work vector in buffer `cur` (item count on the device when the vector was just built)
+            scr.precAll[cur].reserve(std::max(cap, 1), false, st);
+            scr.precLoc.reserve(capL, false, st);
+            PR.gNodesAll = scr.gAll[cur].p;
+            PR.nG = nGgiven;
+            PR.nGptr = (nGgiven >= 0) ? nullptr : &scr.splitRes.p->nNext;
+            PR.precFacAll = scr.precAll[cur].p;
+            launch_prec_factor(PR, cap, st);
+            PP.precAll = scr.precAll[cur].p;
+            PP.precLoc = scr.precLoc.p;
+        }
         PP.nG = nGgiven;
         PP.world = world;
         PP.rank = rank;
@@ -990,6 +1051,13 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         E.gThrs = gThrs;
         E.fMaxNorm = fMaxNorm;
         E.screenOn = screenOn ? 1 : 0;
+        // apply with precTrees: gThrs = prec * precFac(node) * sqrt(|g|^2 / M) (ConvolutionCalculator.cpp:241-248)
+        const double sqrtTerm = (g.squareNorm > 0.0) ? std::sqrt(g.squareNorm / static_cast<double>(M)) : g.squareNorm;
+        if (usePrec) {
+            E.precFac = scr.precLoc.p;
+            E.prec = prec;
+            E.sqrtTerm = sqrtTerm;
+        }
         E.gdesc = scr.gdesc.p;
         E.nbr = scr.nbr.p;
         E.pending = scr.pending.p;
@@ -1062,6 +1130,11 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         P.DM = DM;
         P.K = K;
         P.gThrs = gThrs;
+        if (usePrec) {
+            P.precFac = scr.precLoc.p;
+            P.prec = prec;
+            P.sqrtTerm = sqrtTerm;
+        }
         P.counters = scr.counters.p;
         P.derivDir = derivDir;
         P.identIdx = oper.dev.identIdx;
@@ -1188,6 +1261,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         SP.maxScale = maxScale;
         SP.scaleFac = scr.scaleFac.p;
         SP.prec = prec;
+        SP.precFacAll = usePrec ? scr.precAll[cur].p : nullptr;
         SP.absPrec = absPrec ? 1 : 0;
         SP.iter = iter;
         SP.doSplit = doSplit ? 1 : 0;
@@ -1272,11 +1346,21 @@ static bool use_pipeline(const mrx_tree &out) {
 }
 
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats, const mrx_comm *comm) {
+                  mrx_apply_stats *stats, const mrx_comm *comm, const std::vector<mrx_tree *> *precTrees) {
     require_device("device_apply");
     mrx_apply_stats S{};
     long long launches0 = launch_counter();
     double t0 = now_ms();
+    // precision trees (apply.cpp:214-251) are read node by node on the device: whole trees resident (the input tree itself is
+    // often one of them; it is then resident before its own residency decision below)
+    if (precTrees) {
+        if (!use_pipeline(out)) MRX_ABORT("apply with precision trees is implemented for the work-list pipeline (orders 3..11) only");
+        for (mrx_tree *pt : *precTrees)
+            if (!pt->devValid) {
+                tree_upload(*pt);
+                S.h2d_bytes += (long long)pt->host.nReal * (pt->host.ncoef + 8) * (long long)sizeof(double);
+            }
+    }
     // ---- residency: input tree + operator tables in HBM. A tree whose coefficients sit in pinned host memory is not copied
     //      as a whole: the apply gathers the nodes it reads (DeviceTree::partial); MRX_EAGER_UPLOAD=1 forces the full copy
     if (!inp.devValid) {
@@ -1301,7 +1385,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     std::vector<std::vector<int>> branchPairs;
     const bool bareRoots = out.host.nReal == out.host.nRoots;
     const bool pipe = use_pipeline(out);
-    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr);
+    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr, precTrees);
     else {
         if (comm_world(comm) > 1) MRX_ABORT("sharded apply is implemented for the work-list pipeline (orders 3..11) only");
         run_apply_legacy(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);

@@ -73,13 +73,15 @@ __global__ void __launch_bounds__(256) enum_probe_kernel(EnumParams E) {
             hi[x] = lo[x] + E.nboxes[x] * (1 << td) - 1;
         }
         const double slack = 1.0 + 1e-9;
+        // apply with precTrees: the node's own threshold (ConvolutionCalculator.cpp:244-245)
+        const double gThrs = E.precFac ? E.prec * E.precFac[j] * E.sqrtTerm : E.gThrs;
         const bool inb = lx >= lo[0] && lx <= hi[0] && ly >= lo[1] && ly <= hi[1] && lz >= lo[2] && lz <= hi[2];
-        if (inb && (!E.screenOn || oe.maxO * E.fMaxNorm * slack > E.gThrs)) {
+        if (inb && (!E.screenOn || oe.maxO * E.fMaxNorm * slack > gThrs)) {
             node = ((lx >> td) - E.corner[0]) + E.nboxes[0] * (((ly >> td) - E.corner[1]) + E.nboxes[1] * ((lz >> td) - E.corner[2]));
             node = descend(E.fChild0, node, nd, td, lx, ly, lz);
             // |f_ft| <= |node| for a real node; a generated node is an orthogonal projection of its real leaf
             // ancestor, so the ancestor's norm bounds it
-            if (!E.screenOn || !(oe.maxO * E.fBound[node] * slack <= E.gThrs)) {
+            if (!E.screenOn || !(oe.maxO * E.fBound[node] * slack <= gThrs)) {
                 hit = true;
                 const int *coff = E.candOff + E.depthInfo[dep].cubeOff;
                 nc = coff[oe.code + 1] - coff[oe.code];

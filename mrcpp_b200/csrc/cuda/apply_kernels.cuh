@@ -53,6 +53,10 @@ struct ApplyParams {
     const unsigned long long *candMask; // band-allowed (gt*8+ft) bits per candidate
     int M, DM, K;
     double gThrs;
+    // locally scaled precision (apply with precTrees, apply.cpp:214-251): gThrs of output node g = prec * precFac[g] * sqrtTerm
+    // (ConvolutionCalculator.cpp:241-248, same operation order) while the tree norm is known (sqrtTerm >= 0)
+    const double *precFac; // [nG local] or nullptr
+    double prec, sqrtTerm;
     unsigned long long *counters; // [0] tuples applied
     int derivDir;                 // -1 for convolution operators
     int identIdx;                 // operator block index of the K x K identity (derivative apply: dimensions != derivDir)
@@ -101,6 +105,8 @@ struct EnumParams {
     int corner[3], nboxes[3];
     double gThrs, fMaxNorm;
     int screenOn;
+    const double *precFac; // [nG] per-node precision factor (apply with precTrees) or nullptr: gThrs = prec * precFac * sqrtTerm
+    double prec, sqrtTerm;
     // outputs
     GDesc *gdesc;
     NbrEntry *nbr;
@@ -184,6 +190,7 @@ struct SplitParams {
     int operRoot, rootScale, maxScale;
     const double *scaleFac;         // [depth] 2^{-(scale+1)/2} as the host's std::pow gives it (split_check)
     double prec;
+    const double *precFacAll;       // [nG] per-node precision factor (apply with precTrees, WaveletAdaptor.h:51-54) or nullptr
     int absPrec, iter, doSplit;
     int slotBase;                   // slot of the first child created by this iteration
     double *state;                  // [3] sNorm, wNorm, squareNorm carried across iterations
@@ -202,10 +209,34 @@ struct PrepParams {
     int DM;
     int4 *gNodesLoc;         // this rank's items (i = rank + j world)
     int *slotsLoc;
+    const double *precAll;   // per-item precision factors of the whole work vector (or nullptr) ...
+    double *precLoc;         // ... and this rank's share
     int *chunkOffLoc;        // [nLoc+1]
     SplitResult *res;
 };
 void launch_split(const SplitParams &S, cudaStream_t st);
+
+// ---- locally scaled precision (apply_prec.cu) ---------------------------------------------------------------
+/// one precision tree on the device: real-node topology, node store, and per real node the value getMaxSquareNorm() answers
+/// (stored maximum over the node and its descendants if positive, else the node's own scaled square norm; MWNode.h:84)
+struct PrecTreeDev {
+    const int *child0;
+    const double *coefs;
+    const double *vReal;
+};
+struct PrecParams {
+    const int4 *gNodesAll; // (operator depth, lx, ly, lz) of the work vector
+    int nG;                // number of items, or ...
+    const int *nGptr;      // ... read from the device (next work vector, written by split_kernel) when not null
+    int depthShift;        // function-tree depth = operator depth + depthShift
+    const PrecTreeDev *trees;
+    int nTrees;
+    int corner[3], nboxes[3];
+    int K, rootScale;
+    const double *filters;
+    double *precFacAll;    // [nG] out: 1 / max_i sqrt(maxSquareNorm_i(idx))
+};
+void launch_prec_factor(const PrecParams &P, int gridCap, cudaStream_t st);
 void launch_prep_local(const PrepParams &P, cudaStream_t st);
 
 } // namespace mrx

@@ -79,6 +79,9 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
     }
     int d[3];
     decode_delta(nb.code, di.W, d);
+    // screening threshold of this output node: one value per apply iteration, or scaled per node (apply with precTrees):
+    // gThrs = prec * precFac * sqrt(|g|^2 / M) in the reference's operation order (ConvolutionCalculator.cpp:241-248)
+    const double gThrs = (P.precFac != nullptr && P.sqrtTerm >= 0.0) ? P.prec * P.precFac[nb.g] * P.sqrtTerm : P.gThrs;
     int cnt0 = 0, cnt1 = 0; // lane l counts bits l and l + 32
     for (int base = 0; base < nc; base += 32) {
         const int c = base + lane;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
                     oMax *= m1;
                     oMax *= m2;
                     const double tMax = (sm * sm * sm * 64) * fnMax;
-                    if (!(oMax * tMax > P.gThrs)) todo = 0ull;
+                    if (!(oMax * tMax > gThrs)) todo = 0ull;
                 }
                 if (todo)
 #pragma unroll
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(256) pipe_screen_kernel(ApplyParams P, PipeBuf
                                             sep[2 * ((gt >> 2) & 1) + ((ft >> 2) & 1)] * 64;
                             const double fThreshold = bsI * fn[ft];
                             const double upperBound = oNorm * fThreshold;
-                            if (upperBound > P.gThrs) pass |= 1ull << b;
+                            if (upperBound > gThrs) pass |= 1ull << b;
                         }
                     }
                 }

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(1024) split_kernel(SplitParams S) {
                     double w = 0.0;
 #pragma unroll
                     for (int c = 1; c < 8; c++) w = fma(n[c], n[c], w);
-                    const double thr = fmax(2.0 * 1.0e-15, S.prec * t_norm * S.scaleFac[scale - S.rootScale]);
+                    // WaveletAdaptor::splitNode: prec * precFac (1.0 without precision trees), then split_check's product
+                    const double precN = S.precFacAll ? S.prec * S.precFacAll[i] : S.prec;
+                    const double thr = fmax(2.0 * 1.0e-15, precN * t_norm * S.scaleFac[scale - S.rootScale]);
                     if (sqrt(w) > thr) flag = 1;
                 }
                 S.flags[i] = (unsigned char)flag;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(1024) prep_local_kernel(PrepParams P) {
             const int4 gn = P.gNodesAll[i];
             P.gNodesLoc[j] = gn;
             P.slotsLoc[j] = P.slotsAll[i];
+            if (P.precAll) P.precLoc[j] = P.precAll[i];
             const int dep = gn.x;
             // deeper than every operator tree, or no band at that depth: empty band (ConvolutionCalculator.cpp:146-151)
             if (dep >= 0 && dep < P.DM && P.depthInfo[dep].W >= 0) {

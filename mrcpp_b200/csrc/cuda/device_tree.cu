@@ -833,6 +833,68 @@ void device_add_inplace(mrx_tree &out, double c, mrx_tree &inp) {
     h.calcSquareNorm();
 }
 
+// MWNode::mwTransform(Compression | Reconstruction) (MWNode.cpp:557-594) and MWNode::cvTransform(Forward | Backward)
+// (MWNode.cpp:448-490) of a list of nodes (n < 0: every node), in place on the resident node store.
+// what: 0 = mwTransform (kind 0 Compression, 1 Reconstruction), 1 = cvTransform (kind 0 Forward, 1 Backward).
+// timedReps > 0 (cvTransform only): Forward then Backward, timedReps times between two CUDA events; *timedMs = ms per pass.
+void device_node_transform(mrx_tree &t, int what, int kind, int n, const int *slots, int timedReps, double *timedMs) {
+    require_device("device_node_transform");
+    if (!t.devValid) tree_upload(t);
+    Tree<3> &h = t.host;
+    cudaStream_t st = stream();
+    const int cnt = n < 0 ? h.nReal : n;
+    if (cnt == 0) return;
+    std::vector<int> items((size_t)2 * cnt);
+    for (int i = 0; i < cnt; i++) {
+        const int slot = n < 0 ? i : slots[i];
+        if (slot < 0 || slot >= h.nReal) MRX_ABORT("node transform: slot out of range");
+        items[2 * i] = slot;
+        items[2 * i + 1] = h.nodes[slot].scale;
+    }
+    DevBuf<int> dItems;
+    dItems.reserve(items.size(), false, st);
+    MRX_CUDA(cudaMemcpyAsync(dItems.p, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice, st));
+    if (what == 0) {
+        const double *filt = device_filters(h.k);
+        if (kind == 0) launch_compress_nodes(t.dev.coefs.p, dItems.p, cnt, h.K, filt, st, nullptr);
+        else launch_reconstruct_nodes(t.dev.coefs.p, dItems.p, cnt, h.K, filt, st);
+    } else {
+        const Quadrature &q = quadrature(h.K);
+        std::vector<double> m(2 * h.K);
+        for (int j = 0; j < h.K; j++) {
+            m[j] = std::sqrt(1.0 / q.weights[j]); // InterpolatingBasis::calcCVMaps (InterpolatingBasis.cpp:115-124)
+            m[h.K + j] = std::sqrt(q.weights[j]);
+        }
+        DevBuf<double> dMap;
+        dMap.reserve(m.size(), false, st);
+        MRX_CUDA(cudaMemcpyAsync(dMap.p, m.data(), sizeof(double) * m.size(), cudaMemcpyHostToDevice, st));
+        if (timedReps > 0) {
+            cudaEvent_t e0, e1;
+            MRX_CUDA(cudaEventCreate(&e0));
+            MRX_CUDA(cudaEventCreate(&e1));
+            MRX_CUDA(cudaEventRecord(e0, st));
+            for (int r = 0; r < timedReps; r++) {
+                launch_cv_transform(t.dev.coefs.p, dItems.p, cnt, h.K, dMap.p, false, st);
+                launch_cv_transform(t.dev.coefs.p, dItems.p, cnt, h.K, dMap.p + h.K, true, st);
+            }
+            MRX_CUDA(cudaEventRecord(e1, st));
+            MRX_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            MRX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (timedMs) *timedMs = ms / (2.0 * timedReps);
+            MRX_CUDA(cudaEventDestroy(e0));
+            MRX_CUDA(cudaEventDestroy(e1));
+        } else {
+            launch_cv_transform(t.dev.coefs.p, dItems.p, cnt, h.K, kind == 0 ? dMap.p : dMap.p + h.K, kind != 0, st);
+        }
+        MRX_CUDA(cudaStreamSynchronize(st)); // dMap / m
+    }
+    MRX_CUDA(cudaStreamSynchronize(st)); // items
+    t.hostCoefsValid = false;
+    t.dev.topoNodes = -1;
+    device_calc_norms_all(t);
+}
+
 void device_rescale(mrx_tree &t, double c) {
     if (!t.devValid) tree_upload(t);
     cudaStream_t st = stream();

@@ -21,6 +21,7 @@ constexpr int kTransformThreads = 256;
 // MODE 2: generated children of an input-tree node (scaling only, separate pool) + their norms;
 // MODE 3: in-node compression (MWNode::mwTransform(Compression), MWNode.cpp:557-594): the node's own 8 blocks hold the
 //         scaling blocks of its children (projection, ProjectionCalculator.cpp:34-51) and are replaced by (s, d).
+// MODE 4: in-node reconstruction (MWNode::mwTransform(Reconstruction)): (s, d) replaced by the children's scaling blocks.
 template <int MODE>
 __global__ void __launch_bounds__(kTransformThreads)
 transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoefs, double *__restrict__ genCoefs,
@@ -43,7 +44,7 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
     for (int o = tid; o < 8 * Kd; o += kTransformThreads) {
         int t = o / Kd, rem = o - t * Kd;
         double v;
-        if (MODE == 0 || MODE == 3) {
+        if (MODE == 0 || MODE == 3 || MODE == 4) {
             v = coefs[(size_t)parent * ncoef + o];
         } else if (MODE == 1) {
             v = coefs[(size_t)(child0 + t) * ncoef + rem];
@@ -75,7 +76,7 @@ transform_kernel(double *__restrict__ coefs, const double *__restrict__ realCoef
                 double *dst = coefs + (size_t)(child0 + gt) * ncoef + rem;
                 if (overwrite) *dst = acc;
                 else *dst += acc;
-            } else if (MODE == 1 || MODE == 3) {
+            } else if (MODE == 1 || MODE == 3 || MODE == 4) {
                 coefs[(size_t)parent * ncoef + o] = acc;
             } else {
                 genCoefs[(size_t)(child0 - nReal + gt) * Kd + rem] = acc;
@@ -572,6 +573,42 @@ __global__ void __launch_bounds__(256) product_values_kernel(double *P, const do
     }
 }
 
+// MWNode::cvTransform (MWNode.cpp:448-490) as a standalone pass over a list of nodes: the node's 8 blocks hold the scaling
+// coefficients of its children (0/1 representation, after mwTransform(Reconstruction)); Forward turns them into function values
+// at the children's quadrature points, Backward back. For the interpolating basis the coefficient-value map is diagonal
+// (InterpolatingBasis.cpp:115-124: sqrt(1 / w_j) forward, sqrt(w_j) backward), so the three apply_filter passes of the reference
+// reduce to ((c m[x]) m[y]) m[z] -- same operation order -- times 2^(+-3 (n + 1) / 2) of the children's scale.
+// Element-wise and HBM-bound: 8 K^3 doubles read and written per node (128 K^3 B), 16-byte accesses, one CTA per node.
+__global__ void __launch_bounds__(256) cv_transform_kernel(double *__restrict__ coefs, const int *__restrict__ items, int K,
+                                                           const double *__restrict__ map, int backward) {
+    __shared__ double sMap[16];
+    const int slot = items[2 * blockIdx.x], scale = items[2 * blockIdx.x + 1];
+    const int Kd = K * K * K, ncoef = 8 * Kd;
+    if (threadIdx.x < K) sMap[threadIdx.x] = map[threadIdx.x];
+    __syncthreads();
+    const int np1 = scale + 1;
+    const double two_fac = backward ? sqrt(1.0 / exp2((double)(3 * np1))) : sqrt(exp2((double)(3 * np1)));
+    double *c = coefs + (size_t)slot * ncoef;
+    if ((Kd & 1) == 0) {
+        double2 *c2 = reinterpret_cast<double2 *>(c);
+        for (int o = threadIdx.x; o < ncoef / 2; o += 256) {
+            const int q = (2 * o) % Kd; // K even: a pair never straddles a row
+            const int x = q % K, y = (q / K) % K, z = q / (K * K);
+            double2 v = c2[o];
+            const double myz0 = sMap[y], mz = sMap[z];
+            v.x = two_fac * (((v.x * sMap[x]) * myz0) * mz);
+            v.y = two_fac * (((v.y * sMap[x + 1]) * myz0) * mz);
+            c2[o] = v;
+        }
+    } else {
+        for (int o = threadIdx.x; o < ncoef; o += 256) {
+            const int q = o % Kd;
+            const int x = q % K, y = (q / K) % K, z = q / (K * K);
+            c[o] = two_fac * (((c[o] * sMap[x]) * sMap[y]) * sMap[z]);
+        }
+    }
+}
+
 size_t transform_smem(int K, int &padOn) {
     int K2 = K * K, Kd = K2 * K;
     padOn = 1;
@@ -663,6 +700,24 @@ void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, cons
         set_smem_attr<3>(bytes);
         transform_kernel<3><<<cnt, kTransformThreads, bytes, st>>>(coefs, nullptr, nullptr, nullptr, 0, pairs, K, padOn, filters, 1);
     }
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_reconstruct_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st) {
+    if (cnt <= 0) return;
+    int padOn;
+    size_t bytes = transform_smem(K, padOn);
+    set_smem_attr<4>(bytes);
+    transform_kernel<4><<<cnt, kTransformThreads, bytes, st>>>(coefs, nullptr, nullptr, nullptr, 0, pairs, K, padOn, filters, 1);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+void launch_cv_transform(double *coefs, const int *items, int cnt, int K, const double *map, bool backward, cudaStream_t st) {
+    if (cnt <= 0) return;
+    if (K > 16) MRX_ABORT("cvTransform: order too large");
+    cv_transform_kernel<<<cnt, 256, 0, st>>>(coefs, items, K, map, backward ? 1 : 0);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

@@ -24,6 +24,12 @@ bool transform_fuses_norms(int K);
 void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st,
                            double *norms = nullptr);
 
+/// in-node reconstruction MWNode::mwTransform(Reconstruction) of the nodes pairs[2 i] (pairs[2 i + 1] unused)
+void launch_reconstruct_nodes(double *coefs, const int *pairs, int cnt, int K, const double *filters, cudaStream_t st);
+/// MWNode::cvTransform(Forward | Backward) of the nodes items[2 i] (items[2 i + 1] = the node's scale); map = sqrt(1 / w) or
+/// sqrt(w) per quadrature index
+void launch_cv_transform(double *coefs, const int *items, int cnt, int K, const double *map, bool backward, cudaStream_t st);
+
 /// ProjectionCalculator::calcNode for a Gaussian expansion (project.cu): function values at the expanded child quadrature
 /// points of every work node, scaled to scaling coefficients (cvTransform Backward); nodeInfo = (scale, lx, ly, lz)
 struct GaussTable {

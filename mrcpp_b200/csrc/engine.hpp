@@ -121,6 +121,9 @@ void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = tru
 /// pairs per depth of ALL branch nodes, if the caller already has them
 void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth = nullptr);
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
+/// MWNode::mwTransform (what = 0: kind 0 Compression, 1 Reconstruction) / MWNode::cvTransform (what = 1: kind 0 Forward, 1 Backward)
+/// of the listed nodes (n < 0: every node) in place
+void device_node_transform(mrx_tree &t, int what, int kind, int n, const int *slots, int timedReps = 0, double *timedMs = nullptr);
 double device_dot(mrx_tree &bra, mrx_tree &ket);
 void device_rescale(mrx_tree &t, double c);
 /// add(prec, out, {(c_i, inp_i)}, maxIter, absPrec) from the grid of `out` (add.cpp:41-70); prec < 0 or maxIter = 0: no refinement
@@ -152,8 +155,10 @@ cudaEvent_t comm_ev_reduced(const mrx_comm *c, int buf);
 cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf);
 
 // apply.cu
+/// precTrees != nullptr: apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (apply.cpp:214-251), precision scaled per
+/// output node by the largest norms of the precision trees (an empty vector scales by 1)
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats, const mrx_comm *comm = nullptr);
+                  mrx_apply_stats *stats, const mrx_comm *comm = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr);
 void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int dir, mrx_apply_stats *stats);
 
 } // namespace mrx

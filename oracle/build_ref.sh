@@ -77,5 +77,16 @@ for kind, name in text.items():
                 g.write(" ".join("%.17e" % x for x in v[i * K:(i + 1) * K]) + " \n")
             K += 1
 EOP
+# the reference-side binding of INTEGRATION.md as a real program (tests/cpp/ref_binding.cpp: the reference's own FunctionTree /
+# ConvolutionOperator handed to the C ABI of libmrcpp_b200.so): one binary for the GPU box, one with the device entry points
+# served by the CPU oracle (tests/cpp/oracle_backend.cpp) for the CPU suite. Needs the product library (built first).
+PROD=$HERE/../mrcpp_b200/lib
+if [ -f $PROD/libmrcpp_b200.so ]; then
+  BFLAGS="$CXXFLAGS -I$HERE/../include -L$OUT -lmrcpp_ref -L$PROD -lmrcpp_b200 -ldl -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../../mrcpp_b200/lib"
+  if [ ! -f $OUT/ref_binding ] || [ $HERE/../tests/cpp/ref_binding.cpp -nt $OUT/ref_binding ] || [ $HERE/../include/mrcpp_b200.h -nt $OUT/ref_binding ]; then
+    g++ $HERE/../tests/cpp/ref_binding.cpp $BFLAGS -o $OUT/ref_binding
+    g++ -rdynamic $HERE/../tests/cpp/ref_binding.cpp $HERE/../tests/cpp/oracle_backend.cpp $BFLAGS -o $OUT/ref_binding_cpu
+  fi
+fi
 rm -rf $OUT/include  # build-time symlinks into the reference tree: nothing that points outside the repo may travel
 echo "built $OUT/libmrcpp_ref.so $OUT/libref_driver.so $OUT/mwfilters"

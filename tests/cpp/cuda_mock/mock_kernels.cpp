@@ -56,6 +56,31 @@ void launch_compress_nodes(double *coefs, const int *pairs, int cnt, int K, cons
     }
     launch_counter()++;
 }
+// in-node reconstruction MWNode::mwTransform(Reconstruction): (s, d) -> the children's scaling blocks, in place
+void launch_reconstruct_nodes(double *coefs, const int *pairs, int cnt, int K, const double *, cudaStream_t) {
+    const FilterSet &fs = filter_set(K - 1);
+    const int Kd = K * K * K;
+    for (int p = 0; p < cnt; p++) {
+        double *node = coefs + (size_t)pairs[2 * p] * 8 * Kd;
+        std::vector<double> in(node, node + (size_t)8 * Kd);
+        orc::mw_transform3(fs, K, in.data(), node, false, Kd, true);
+    }
+    launch_counter()++;
+}
+// MWNode::cvTransform for the interpolating basis: diagonal map per index and 2^(+-3 (n + 1) / 2)
+void launch_cv_transform(double *coefs, const int *items, int cnt, int K, const double *map, bool backward, cudaStream_t) {
+    const int Kd = K * K * K;
+    for (int p = 0; p < cnt; p++) {
+        double *c = coefs + (size_t)items[2 * p] * 8 * Kd;
+        const int np1 = items[2 * p + 1] + 1;
+        const double two_fac = backward ? std::sqrt(1.0 / std::exp2((double)(3 * np1))) : std::sqrt(std::exp2((double)(3 * np1)));
+        for (int o = 0; o < 8 * Kd; o++) {
+            const int q = o % Kd;
+            c[o] = two_fac * (((c[o] * map[q % K]) * map[(q / K) % K]) * map[q / (K * K)]);
+        }
+    }
+    launch_counter()++;
+}
 // ProjectionCalculator::calcNode up to cvTransform(Backward): values of the expansion at the expanded child quadrature points,
 // times sqrt(w) per dimension and 2^(-3 (n + 1) / 2)  (what project_eval_kernel computes)
 void launch_project_eval(double *coefs, const int *slots, const int4 *nodeInfo, int cnt, int K, const GaussTable &G, const double *roots,
@@ -171,11 +196,19 @@ static void fill_stats(const orc::ApplyStats &st, mrx_apply_stats *stats) {
     stats->iterations = st.iters;
     stats->n_nodes_out = st.nNodesOut;
 }
-void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, mrx_apply_stats *stats, const mrx_comm *) {
+void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, mrx_apply_stats *stats, const mrx_comm *,
+                  const std::vector<mrx_tree *> *precTrees) {
     to_host(inp);
     host_storage(out);
     orc::ApplyStats st;
-    orc::apply(prec, out.host, oper.op, inp.host, maxIter, absPrec, &st, nullptr);
+    std::vector<mrx::Tree<3> *> pt;
+    if (precTrees)
+        for (mrx_tree *t : *precTrees) {
+            to_host(*t);
+            host_storage(*t); // the oracle generates nodes (with coefficients) below the leaves of the precision trees
+            pt.push_back(&t->host);
+        }
+    orc::apply(prec, out.host, oper.op, inp.host, maxIter, absPrec, &st, precTrees ? &pt : nullptr);
     host_result(out);
     fill_stats(st, stats);
 }

@@ -1,0 +1,280 @@
+// The reference-side binding of INTEGRATION.md, made real: MRCPP's OWN classes (FunctionTree<3>, PoissonOperator / HelmholtzOperator,
+// NodeAllocator serial order, OperatorTree::getNode(n, l) -- compiled in place from the reference's sources into oracle/_ref,
+// see oracle/build_ref.sh) handed to the C ABI through mrx_tree_from_arrays + mrx_oper_from_arrays, mrx_apply on the device,
+// the result written back into a reference FunctionTree through the reference's public node API, and compared with the
+// reference's own mrcpp::apply on the same inputs. TEST INFRASTRUCTURE (built by oracle/build_ref.sh where /root/reference
+// exists; the binary travels to the GPU box): this is the code a maintainer would add to MRCPP, exercised end to end.
+//
+//   ref_binding [poisson|helmholtz] [order] [prec] [nGauss]   prints "key value" lines, exit code 0 when every check passes
+#include <mrcpp_b200.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "MRCPP/Gaussians"
+#include "MRCPP/MWFunctions"
+#include "MRCPP/MWOperators"
+#include "MRCPP/Printer"
+#include "treebuilders/apply.h"
+#include "treebuilders/grid.h"
+#include "treebuilders/project.h"
+#include "trees/FunctionNode.h"
+#include "trees/FunctionTree.h"
+#include "trees/MWNode.h"
+#include "trees/NodeAllocator.h"
+#include "trees/OperatorNode.h"
+#include "trees/OperatorTree.h"
+#include "trees/TreeIterator.h"
+
+using namespace mrcpp;
+
+namespace b200 {
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+mrx_mra *to_mra(const MultiResolutionAnalysis<3> &mra) {
+    const auto &w = mra.getWorldBox();
+    int corner[3], boxes[3];
+    for (int d = 0; d < 3; d++) {
+        corner[d] = w.getCornerIndex()[d];
+        boxes[d] = w.size(d);
+    }
+    return mrx_mra_create(mra.getOrder(), w.getScale(), corner, boxes, mra.getMaxDepth());
+}
+
+// Node order of the C ABI = NodeAllocator serial order: roots in box order, then the 8 children of every split node
+// contiguously (NodeAllocator.cpp:115-216). A tree built by TreeBuilder has dense serial indices 0..nNodes-1.
+mrx_tree *to_tree(const mrx_mra *m, FunctionTree<3, double> &t, size_t *bytes) {
+    auto &alloc = t.getNodeAllocator();
+    const int n = alloc.getNNodes(), nc = alloc.getNCoefs();
+    std::vector<int> scale(n), transl(3 * (size_t)n), parent(n), child0(n);
+    std::vector<double> coefs((size_t)n * nc, 0.0);
+    for (int i = 0; i < n; i++) {
+        MWNode<3, double> &nd = *alloc.getNode_p(i);
+        if (nd.getSerialIx() != i) {
+            std::fprintf(stderr, "ref_binding: serial indices are not dense\n");
+            std::exit(2);
+        }
+        scale[i] = nd.getScale();
+        for (int d = 0; d < 3; d++) transl[3 * (size_t)i + d] = nd.getNodeIndex()[d];
+        parent[i] = nd.isRootNode() ? -1 : nd.getMWParent().getSerialIx();
+        child0[i] = nd.isBranchNode() ? nd.getMWChild(0).getSerialIx() : -1;
+        if (nd.hasCoefs()) std::memcpy(coefs.data() + (size_t)i * nc, nd.getCoefs(), sizeof(double) * nc);
+    }
+    if (bytes) *bytes = coefs.size() * sizeof(double);
+    return mrx_tree_from_arrays(m, n, scale.data(), transl.data(), parent.data(), child0.data(), coefs.data());
+}
+
+// OperatorTree::getNode(depth, transl) is the [depth][transl] cache built by setupOperNodeCache (OperatorTree.cpp:200-238);
+// the largest translation per depth as OperatorTree::getMaxTranslations computes it (:182-192, protected there)
+mrx_oper *to_oper(const mrx_mra *m, ConvolutionOperator<3> &O, int order, double build_prec) {
+    std::vector<int> nDepth, maxTransl;
+    std::vector<double> mats, norms;
+    const int K = order + 1, K2 = K * K; // the operator MRA has the function order (MWOperator.cpp:110-129)
+    for (int i = 0; i < O.size(); i++) {
+        OperatorTree &ot = O.getComponent(i, 0);
+        const int nScales = ot.getDepth();
+        std::vector<int> mt(nScales, 0);
+        TreeIterator<2> it(ot);
+        while (it.next()) {
+            const int n = it.getNode().getDepth();
+            const NodeIndex<2> &l = it.getNode().getNodeIndex();
+            mt[n] = std::max(mt[n], std::max(std::abs(l[0]), std::abs(l[1])));
+        }
+        nDepth.push_back(nScales);
+        for (int n = 0; n < nScales; n++) {
+            maxTransl.push_back(mt[n]);
+            for (int l = -mt[n]; l <= mt[n]; l++) {
+                const OperatorNode &nd = ot.getNode(n, l);
+                mats.insert(mats.end(), nd.getCoefs(), nd.getCoefs() + 4 * K2);
+                for (int c = 0; c < 4; c++) norms.push_back(nd.getComponentNorm(c));
+            }
+        }
+    }
+    return mrx_oper_from_arrays(m, O.size(), nDepth.data(), maxTransl.data(), mats.data(), norms.data(), O.getOperatorRoot(),
+                                /*derivative_order=*/0, build_prec);
+}
+
+// result -> reference tree: createChildren in slot order reproduces the allocator order, then coefficients and norms
+void from_arrays(FunctionTree<3, double> &out, int n, const std::vector<int> &child0, const std::vector<double> &coefs, int nc) {
+    auto &alloc = out.getNodeAllocator();
+    for (int i = 0; i < n; i++) {
+        MWNode<3, double> &nd = *alloc.getNode_p(i);
+        if (child0[i] >= 0 && !nd.isBranchNode()) {
+            nd.createChildren(true);
+            if (nd.getMWChild(0).getSerialIx() != child0[i]) {
+                std::fprintf(stderr, "ref_binding: slot order of the result differs from the allocator order\n");
+                std::exit(2);
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        MWNode<3, double> &nd = *alloc.getNode_p(i);
+        std::memcpy(nd.getCoefs(), coefs.data() + (size_t)i * nc, sizeof(double) * nc);
+        nd.setHasCoefs();
+        nd.calcNorms();
+    }
+    out.resetEndNodeTable();
+    out.calcSquareNorm();
+}
+
+// mrcpp::apply(prec, out, oper, inp, maxIter, absPrec) through the C ABI. timings[0..4]: tree export, operator export, apply,
+// result import, total
+void apply(double prec, FunctionTree<3, double> &out, ConvolutionOperator<3> &oper, FunctionTree<3, double> &inp, int maxIter, bool absPrec,
+           mrx_apply_stats *st, double *timings, size_t *bytesIn, size_t *bytesOut) {
+    const double t0 = now();
+    mrx_mra *m = to_mra(inp.getMRA());
+    mrx_tree *f = to_tree(m, inp, bytesIn);
+    mrx_tree *g = to_tree(m, out, nullptr); // `out` brings its starting grid (bare roots normally)
+    const double t1 = now();
+    mrx_oper *P = to_oper(m, oper, inp.getMRA().getOrder(), oper.getBuildPrec());
+    const double t2 = now();
+    mrx_apply(prec, g, P, f, maxIter, absPrec ? 1 : 0, st);
+    const int n = mrx_tree_n_nodes(g), nc = out.getNodeAllocator().getNCoefs();
+    std::vector<int> scale(n), transl(3 * (size_t)n), parent(n), child0(n);
+    std::vector<double> coefs((size_t)n * nc);
+    mrx_tree_to_arrays(g, scale.data(), transl.data(), parent.data(), child0.data(), coefs.data(), nullptr);
+    const double t3 = now();
+    from_arrays(out, n, child0, coefs, nc);
+    const double t4 = now();
+    if (bytesOut) *bytesOut = coefs.size() * sizeof(double);
+    mrx_tree_destroy(f);
+    mrx_tree_destroy(g);
+    mrx_oper_destroy(P);
+    mrx_mra_destroy(m);
+    timings[0] = t1 - t0;
+    timings[1] = t2 - t1;
+    timings[2] = t3 - t2;
+    timings[3] = t4 - t3;
+    timings[4] = t4 - t0;
+}
+
+} // namespace b200
+
+int main(int argc, char **argv) {
+    const std::string kind = argc > 1 ? argv[1] : "poisson";
+    const int order = argc > 2 ? std::atoi(argv[2]) : 7;
+    const double prec = argc > 3 ? std::atof(argv[3]) : 1e-5;
+    const int nGauss = argc > 4 ? std::atoi(argv[4]) : 1;
+    Printer::init(-1);
+    const char *tables = std::getenv("MRX_TABLES");
+    const char *dev = std::getenv("MRCPP_B200_DEVICE");
+    if (!tables) {
+        std::fprintf(stderr, "ref_binding: set MRX_TABLES to mrcpp_b200/data/mwtables.bin\n");
+        return 2;
+    }
+    if (mrx_init(tables, dev ? std::atoi(dev) : 0) != 0) return 2;
+
+    // the world of examples/poisson.cpp
+    BoundingBox<3> world(-4, std::array<int, 3>{-1, -1, -1}, std::array<int, 3>{2, 2, 2});
+    InterpolatingBasis basis(order);
+    MultiResolutionAnalysis<3> MRA(world, basis, 25);
+
+    GaussExp<3> func;
+    if (nGauss == 1) {
+        const double beta = 100.0, alpha = std::pow(beta / pi, 1.5);
+        func.append(GaussFunc<3>(beta, alpha, Coord<3>{pi / 3.0, pi / 3.0, pi / 3.0}));
+    } else {
+        std::mt19937_64 rng(1234);
+        std::uniform_real_distribution<double> pos(-4.0, 4.0), ex(1.0, 2.0);
+        for (int i = 0; i < nGauss; i++) {
+            const double beta = std::pow(10.0, ex(rng));
+            func.append(GaussFunc<3>(beta, std::pow(beta / pi, 1.5) / nGauss, Coord<3>{pos(rng), pos(rng), pos(rng)}));
+        }
+    }
+    FunctionTree<3, double> f(MRA);
+    build_grid(f, func);
+    project<3, double>(prec, f, func);
+
+    ConvolutionOperator<3> *oper = nullptr;
+    if (kind == "helmholtz") oper = new HelmholtzOperator(MRA, 1.0, prec);
+    else oper = new PoissonOperator(MRA, prec);
+
+    // ---- the reference's own apply
+    FunctionTree<3, double> gRef(MRA);
+    double tr = b200::now();
+    mrcpp::apply<3, double>(prec, gRef, *oper, f);
+    tr = b200::now() - tr;
+
+    // ---- the same call through the binding
+    FunctionTree<3, double> gDev(MRA);
+    mrx_apply_stats st;
+    double tm[5];
+    size_t bytesIn = 0, bytesOut = 0;
+    b200::apply(prec, gDev, *oper, f, -1, false, &st, tm, &bytesIn, &bytesOut);
+    // second call: steady state (caches warm), what the e2e figure quotes
+    FunctionTree<3, double> gDev2(MRA);
+    double tm2[5];
+    b200::apply(prec, gDev2, *oper, f, -1, false, &st, tm2, &bytesIn, &bytesOut);
+
+    // ---- compare inside the reference: node sets through the allocator order, coefficients relative to the node norm
+    int bad = 0;
+    const int n = gRef.getNNodes();
+    std::printf("terms %d\n", oper->size());
+    std::printf("f_nodes %d\n", f.getNNodes());
+    std::printf("g_nodes_ref %d\n", n);
+    std::printf("g_nodes_b200 %d\n", gDev.getNNodes());
+    if (gDev.getNNodes() != n) bad++;
+    double worstFloored = 0.0, worstStrict = 0.0, nmax = 0.0;
+    int needFloor = 0;
+    if (!bad) {
+        auto &ar = gRef.getNodeAllocator();
+        const int nc = ar.getNCoefs();
+        std::vector<double> nrm(n), err(n);
+        for (int i = 0; i < n; i++) {
+            MWNode<3, double> &a = *ar.getNode_p(i);
+            // the same node in the other tree, by index (the reference's slot order depends on its OpenMP schedule only through
+            // the split order inside an iteration, which is work-vector order: it is the same, but do not rely on it)
+            MWNode<3, double> *b = gDev.findNode(a.getNodeIndex());
+            if (b == nullptr || b->isBranchNode() != a.isBranchNode()) {
+                bad++;
+                continue;
+            }
+            double s = 0.0, e = 0.0;
+            for (int j = 0; j < nc; j++) {
+                s += a.getCoefs()[j] * a.getCoefs()[j];
+                e = std::max(e, std::abs(a.getCoefs()[j] - b->getCoefs()[j]));
+            }
+            nrm[i] = std::sqrt(s);
+            err[i] = e;
+            nmax = std::max(nmax, nrm[i]);
+        }
+        for (int i = 0; i < n; i++) {
+            const double strict = err[i] / (nrm[i] > 0.0 ? nrm[i] : nmax);
+            worstStrict = std::max(worstStrict, strict);
+            if (strict > 1e-12) needFloor++;
+            worstFloored = std::max(worstFloored, err[i] / std::max(nrm[i], 1e-3 * nmax));
+        }
+    }
+    const double eRef = dot(gRef, f), eDev = dot(gDev, f);
+    std::printf("node_set_mismatches %d\n", bad);
+    std::printf("coef_err_floored %.3e\n", worstFloored);
+    std::printf("coef_err_strict %.3e\n", worstStrict);
+    std::printf("nodes_needing_floor %d\n", needFloor);
+    std::printf("energy_ref %.15e\n", eRef);
+    std::printf("energy_b200 %.15e\n", eDev);
+    std::printf("sqnorm_ref %.15e\n", gRef.getSquareNorm());
+    std::printf("sqnorm_b200 %.15e\n", gDev.getSquareNorm());
+    std::printf("tuples %lld\n", st.f_applied);
+    std::printf("calc_nodes %lld\n", st.g_nodes);
+    std::printf("seconds_reference_apply %.6f\n", tr);
+    std::printf("seconds_binding_total %.6f\n", tm2[4]);
+    std::printf("seconds_binding_tree_export %.6f\n", tm2[0]);
+    std::printf("seconds_binding_oper_export %.6f\n", tm2[1]);
+    std::printf("seconds_binding_apply_and_download %.6f\n", tm2[2]);
+    std::printf("seconds_binding_result_import %.6f\n", tm2[3]);
+    std::printf("seconds_binding_total_first_call %.6f\n", tm[4]);
+    std::printf("bytes_in %zu\n", bytesIn);
+    std::printf("bytes_out %zu\n", bytesOut);
+    const bool ok = bad == 0 && worstFloored < 1e-12 && std::abs(eRef - eDev) <= 1e-11 * std::abs(eRef) &&
+                    std::abs(gRef.getSquareNorm() - gDev.getSquareNorm()) <= 1e-12 * gRef.getSquareNorm();
+    std::printf("ok %d\n", ok ? 1 : 0);
+    delete oper;
+    return ok ? 0 : 1;
+}
