@@ -19,6 +19,7 @@
 // device_apply / device_apply_derivative: residency of the input (whole upload or lazy gathers), the loop, the closing
 //   TopDown(+=) / BottomUp passes (device_tree.cu), cleanup of generated nodes.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -73,6 +74,56 @@ void band_size_factors(const Operator &op, int DM, std::vector<int> &bsf, std::v
                 }
         }
     }
+}
+
+// Host mailbox of the refinement loop: three small records per iteration (enumeration counters, tuple / unit counts, split
+// result) are published by a one-thread kernel into pinned, mapped host memory and the host spins on a sequence flag -- a few
+// microseconds per read-back instead of a cudaMemcpyAsync + cudaStreamSynchronize round trip (MRX_NO_MAILBOX=1: the latter).
+struct Mailbox {
+    volatile unsigned flagEc, flagHdr, flagRes, pad;
+    EnumCounters ec;
+    PipeHeader hdr;
+    SplitResult res;
+};
+static Mailbox *mailbox() {
+    static Mailbox *mb = nullptr;
+    if (!mb) {
+        MRX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&mb), sizeof(Mailbox), cudaHostAllocMapped | cudaHostAllocPortable));
+        std::memset(const_cast<unsigned *>(&mb->flagEc), 0, sizeof(Mailbox));
+    }
+    return mb;
+}
+static unsigned &mailbox_seq() {
+    static unsigned seq = 0;
+    return seq;
+}
+template <typename T> static void *mailbox_dev(T *hostPtr) {
+    void *d = nullptr;
+    MRX_CUDA(cudaHostGetDevicePointer(&d, const_cast<void *>(static_cast<const volatile void *>(hostPtr)), 0));
+    return d;
+}
+// read a record back: mailbox (publish kernel + spin on the host flag) or plain copy + synchronise
+template <typename T> static void read_back(T *dst, const T *devSrc, T *mbSlot, volatile unsigned *mbFlag, bool useMailbox, cudaStream_t st) {
+    if (useMailbox) {
+        const unsigned seq = ++mailbox_seq();
+        launch_publish(devSrc, mailbox_dev(mbSlot), (int)(sizeof(T) / 4), static_cast<unsigned *>(mailbox_dev(mbFlag)), seq, st);
+        while (*mbFlag != seq) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        std::memcpy(dst, const_cast<const T *>(mbSlot), sizeof(T));
+    } else {
+        MRX_CUDA(cudaMemcpyAsync(dst, devSrc, sizeof(T), cudaMemcpyDeviceToHost, st));
+        MRX_CUDA(cudaStreamSynchronize(st));
+    }
+}
+
+// final node count of the last apply of this process: the next apply reserves its node store for that many nodes up front
+static size_t &nodeStoreHint() {
+    static size_t h = 0;
+    return h;
 }
 
 struct Scratch {
@@ -780,6 +831,8 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     const char *uEnv = getenv("MRX_UNIT_TUPLES");
     const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
     const bool profile = getenv("MRX_PROFILE") != nullptr;
+    const bool useMailbox = getenv("MRX_NO_MAILBOX") == nullptr;
+    Mailbox *mb = mailbox();
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -822,19 +875,41 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         scr.fetchTotal.reserve(1, false, st);
         MRX_CUDA(cudaMemsetAsync(scr.fetchTotal.p, 0, sizeof(unsigned long long), st));
     }
-    // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store
+    // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store. The unpack runs on a
+    // side stream beside the next iteration's kernels; whatever it reads or writes (ring slot `buf` of the staging buffer, the
+    // norm rows and the slot list; the node store) is protected by an event the main stream waits for before reusing it.
     struct {
         bool active = false;
         int buf = 0, nG = 0, rows = 0;
     } pend;
-    auto flush_pending = [&]() {
-        if (!pend.active) return;
-        // own push done -> tiny all-reduce: behind it every peer's push is done as well -> unpack
-        MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
-        comm_allreduce_sum(comm, reinterpret_cast<double *>(scr.counters.p + 2), 1, st);
+    bool unpackInFlight[kCommStageBufs] = {false, false, false};
+    cudaStream_t ust = (world > 1) ? comm_unpack_stream(comm) : nullptr;
+    auto wait_unpack = [&](int slot) { // main stream: the unpack that used ring slot `slot` has finished
+        if (world > 1 && unpackInFlight[slot]) {
+            MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_unpacked(comm, slot), 0));
+            unpackInFlight[slot] = false;
+        }
+    };
+    auto wait_all_unpacks = [&]() {
+        for (int x = 0; x < kCommStageBufs; x++) wait_unpack(x);
+    };
+    auto unpack_async = [&]() { // rows of `pend` have landed (the caller has ordered that on the main stream)
+        MRX_CUDA(cudaEventRecord(comm_ev_gathered(comm), st));
+        MRX_CUDA(cudaStreamWaitEvent(ust, comm_ev_gathered(comm), 0));
         launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)), scr.gslotsAll[pend.buf].p, pend.nG,
-                            world, pend.rows, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, st);
-        pend.active = false;
+                            world, pend.rows, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, ust);
+        MRX_CUDA(cudaEventRecord(comm_ev_unpacked(comm, pend.buf), ust));
+        unpackInFlight[pend.buf] = true;
+    };
+    auto flush_pending = [&]() {
+        if (pend.active) {
+            // own push done -> tiny all-reduce: behind it every peer's push is done as well -> unpack
+            MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
+            comm_allreduce_sum(comm, reinterpret_cast<double *>(scr.counters.p + 2), 1, st);
+            unpack_async();
+            pend.active = false;
+        }
+        wait_all_unpacks();
     };
 
     // ---- precision trees (apply.cpp:214-234): per real node the value getMaxSquareNorm() answers after makeMaxSquareNorms
@@ -962,13 +1037,32 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     };
     SplitResult res{};
     prep_local(0, 0, nG);
-    MRX_CUDA(cudaMemcpyAsync(&res, scr.splitRes.p, sizeof(res), cudaMemcpyDeviceToHost, st));
-    MRX_CUDA(cudaStreamSynchronize(st));
+    read_back(&res, scr.splitRes.p, &mb->res, &mb->flagRes, useMailbox, st);
 
     // host replay of the split decisions (deferred: runs while the device contracts the next iteration)
+    // split flags come down through a pinned arena with a truly asynchronous copy; the host reads them one iteration later,
+    // after it has seen a later mailbox flag (stream order: the copy has landed by then)
     struct Replay {
-        std::vector<unsigned char> flags;
+        size_t off;   // offset of the flags in the pinned arena
+        int n;        // items of the iteration
+        bool split;   // false: the iteration took no split decisions (all flags zero)
         int slotBase;
+    };
+    static unsigned char *flagArena = nullptr;
+    static size_t flagArenaCap = 0;
+    size_t flagArenaUsed = 0;
+    auto flag_arena_reserve = [&](size_t need) {
+        if (need <= flagArenaCap) return;
+        MRX_CUDA(cudaStreamSynchronize(st)); // copies into the old arena have landed; pending replays still read it: copy over
+        size_t ncap = std::max<size_t>(need * 2, (size_t)1 << 20);
+        unsigned char *np = nullptr;
+        MRX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&np), ncap, cudaHostAllocDefault));
+        if (flagArena) {
+            std::memcpy(np, flagArena, flagArenaUsed);
+            MRX_CUDA(cudaFreeHost(flagArena));
+        }
+        flagArena = np;
+        flagArenaCap = ncap;
     };
     std::vector<Replay> replay; // one per finished iteration, processed in order
     size_t replayed = 0;
@@ -976,11 +1070,12 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     auto replay_pending = [&]() {
         for (; replayed < replay.size(); replayed++) {
             const Replay &R = replay[replayed];
+            const unsigned char *rflags = flagArena + R.off;
             std::vector<int> next;
             int expect = R.slotBase;
             for (size_t i = 0; i < hostVec.size(); i++) {
                 g.nodes[hostVec[i]].flags |= FlagHasCoefs;
-                if (i < R.flags.size() && R.flags[i]) {
+                if (R.split && (int)i < R.n && rflags[i]) {
                     const int c0 = g.createChildren(hostVec[i], false);
                     if (c0 != expect) MRX_ABORT("apply: host replay of the device split decisions lost its slot order");
                     expect += 8;
@@ -1064,8 +1159,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         E.cnt = scr.ecnt.p;
         launch_enum(E, st);
         EnumCounters ec;
-        MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaStreamSynchronize(st));
+        read_back(&ec, scr.ecnt.p, &mb->ec, &mb->flagEc, useMailbox, st);
         const int nNbr = ec.nNbr;
         const long long nCand = (long long)ec.nCand;
         if (nCand >= (1ll << 31)) MRX_ABORT("apply: candidate space of one iteration exceeds 2^31");
@@ -1077,8 +1171,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
             E.genItems = scr.genItems.p;
             MRX_CUDA(cudaMemsetAsync(&scr.ecnt.p->nUnresolved, 0, 2 * sizeof(int), st)); // nUnresolved, nNewParents
             launch_enum_resolve(E, nPending, st);
-            MRX_CUDA(cudaMemcpyAsync(&ec, scr.ecnt.p, sizeof(ec), cudaMemcpyDeviceToHost, st));
-            MRX_CUDA(cudaStreamSynchronize(st));
+            read_back(&ec, scr.ecnt.p, &mb->ec, &mb->flagEc, useMailbox, st);
             if (ec.nUnresolved == 0) break;
             const int nNew = ec.nNewParents;
             topo.reserve((size_t)fTotal + 8 * (size_t)nNew, st);
@@ -1102,10 +1195,16 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         }
         tp_gen += now_ms() - tq;
         tq = now_ms();
-        // ---- device storage for the output nodes of this iteration
-        out.dev.coefs.reserve((size_t)nRealDev * ncoef, true, st);
-        out.dev.norms.reserve((size_t)nRealDev * 8, true, st);
+        // ---- device storage for the output nodes of this iteration (a growing store is copied: nothing may be writing it)
+        if ((size_t)nRealDev * ncoef > out.dev.coefs.cap || (size_t)nRealDev * 8 > out.dev.norms.cap) {
+            wait_all_unpacks();
+            // room for the whole tree if an earlier apply of this process told how large it gets: no copy, no regrowth
+            const size_t want = std::max<size_t>((size_t)nRealDev, std::min<size_t>(nodeStoreHint(), (size_t)64 * nRealDev + 4096));
+            out.dev.coefs.reserve(want * ncoef, true, st);
+            out.dev.norms.reserve(want * 8, true, st);
+        }
         out.dev.nNodes = nRealDev;
+        wait_unpack(b); // ring slot b (staging rows, norm rows) is written again by this iteration
 
         ApplyParams P{};
         P.fReal = inp.dev.coefs.p;
@@ -1168,8 +1267,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         launch_pipe_screen(P, B, nNbr, st);
         launch_pipe_scan(P, B, nL, unitTuples, st);
         PipeHeader hdr;
-        MRX_CUDA(cudaMemcpyAsync(&hdr, scr.header.p, sizeof(hdr), cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaStreamSynchronize(st));
+        read_back(&hdr, scr.header.p, &mb->hdr, &mb->flagHdr, useMailbox, st);
         if (hdr.totalTuples >= (1ull << 32)) MRX_ABORT("apply: tuple list of one iteration exceeds 2^32 records");
         scr.tuples.reserve(std::max<size_t>((size_t)hdr.totalTuples, 1), false, st);
         scr.units2.reserve(std::max<size_t>((size_t)hdr.nUnits, 1), false, st);
@@ -1218,10 +1316,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                 comm_push(comm, b, (size_t)rank * segBytes, (size_t)nL * rowBytes);
                 if (pend.active) MRX_CUDA(cudaStreamWaitEvent(st, comm_ev_pushed(comm, pend.buf), 0));
                 comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
-                if (pend.active)
-                    launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)),
-                                        scr.gslotsAll[pend.buf].p, pend.nG, world, pend.rows, ncoef, scr.normsW[pend.buf].p,
-                                        out.dev.norms.p, st);
+                if (pend.active) unpack_async(); // beside the next iteration's kernels
                 pend.active = true;
                 pend.buf = b;
                 pend.nG = nG;
@@ -1246,6 +1341,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         tp_replay += now_ms() - tr;
         // ---- TreeBuilder bookkeeping, split decisions and the next work vector on the device (apply_split.cu)
         const int nb = (iter + 1) % kCommStageBufs;
+        wait_unpack(nb); // the slot list of ring slot nb is rewritten by the split kernel
         scr.gAll[cur ^ 1].reserve((size_t)8 * nG, false, st);
         scr.gslotsAll[nb].reserve((size_t)8 * nG, false, st);
         scr.flags.reserve(nG, false, st);
@@ -1274,15 +1370,17 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         launch_split(SP, st);
         prep_local(cur ^ 1, nb, -1);
         Replay R;
-        R.flags.resize(nG);
+        flag_arena_reserve(flagArenaUsed + (size_t)nG);
+        R.off = flagArenaUsed;
+        R.n = nG;
+        R.split = doSplit;
         R.slotBase = nRealDev;
-        MRX_CUDA(cudaMemcpyAsync(&res, scr.splitRes.p, sizeof(res), cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaMemcpyAsync(R.flags.data(), scr.flags.p, nG, cudaMemcpyDeviceToHost, st));
-        MRX_CUDA(cudaStreamSynchronize(st));
+        flagArenaUsed += (size_t)nG;
+        if (doSplit) MRX_CUDA(cudaMemcpyAsync(flagArena + R.off, scr.flags.p, nG, cudaMemcpyDeviceToHost, st));
+        read_back(&res, scr.splitRes.p, &mb->res, &mb->flagRes, useMailbox, st);
         tp_wait += now_ms() - tq;
         tq = now_ms();
-        if (!doSplit) std::fill(R.flags.begin(), R.flags.end(), 0);
-        replay.push_back(std::move(R));
+        replay.push_back(R);
         float ms = 0.f, msc = 0.f;
         MRX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         MRX_CUDA(cudaEventElapsedTime(&msc, ev2, ev3));
@@ -1304,8 +1402,10 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         tp_split += now_ms() - tq;
     }
     if (world > 1) flush_pending();
+    MRX_CUDA(cudaStreamSynchronize(st)); // the last iteration's flags have landed; events are complete
     replay_pending();
     if (g.nReal != nRealDev) MRX_ABORT("apply: host topology and device node store disagree");
+    nodeStoreHint() = (size_t)nRealDev + (size_t)nRealDev / 8;
     const double tLoopEnd = now_ms();
     if (profile) {
         std::fprintf(stderr, "[mrx] run_apply_pipe ms: pre-loop %.2f loop %.2f\n", tLoop - tEnter, tLoopEnd - tLoop);

@@ -215,6 +215,10 @@ struct PrepParams {
     SplitResult *res;
 };
 void launch_split(const SplitParams &S, cudaStream_t st);
+/// host mailbox: copy `words` 32-bit words from device memory to (mapped, pinned) host memory, fence, then store `seq` into the
+/// host flag -- one tiny kernel at the end of a dependent chain, so that the host can spin on the flag instead of paying a
+/// cudaMemcpyAsync + cudaStreamSynchronize round trip per read-back
+void launch_publish(const void *src, void *hostDst, int words, unsigned *hostFlag, unsigned seq, cudaStream_t st);
 
 // ---- locally scaled precision (apply_prec.cu) ---------------------------------------------------------------
 /// one precision tree on the device: real-node topology, node store, and per real node the value getMaxSquareNorm() answers

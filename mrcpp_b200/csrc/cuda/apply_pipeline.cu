@@ -747,6 +747,139 @@ template <int K> __global__ void __launch_bounds__(128) pipe_contract_coop_kerne
     }
 }
 
+// Stage 1 stacked along M. Consecutive tuples of a unit are sorted by (input node, ft, term), so runs of tuples share their
+// SOURCE block and differ only in the operator: the first contraction of up to G such tuples is ONE GEMM
+//   [O_x^(1)^T; ...; O_x^(G)^T] (G K x K)  .  f (K x K^2)
+// whose G K rows fill whole 8-row tiles (K = 12, G = 2: 24 rows = 3 tiles instead of 2 x 2 padded ones; K = 10, G = 4: 40 rows =
+// 5 tiles instead of 4 x 2; K = 6, G = 4: 24 rows = 3 tiles instead of 4 x 1) and reads the source fragments once. Stages 2 and 3
+// then run per tuple as in pipe_contract_coop_kernel. Every output element is the same sequence of DMMA k-steps over the same
+// operands as in the unstacked kernel (padding contributes exact zeros), and tuples are accumulated in list order: results
+// are bit-identical to it.
+template <int K, int G> __global__ void __launch_bounds__(128) pipe_contract_stack_kernel(ApplyParams P, PipeBuffers B, int nUnits) {
+    using D = PadDims<K>;
+    constexpr int NTW = (D::NT + 3) / 4;
+    constexpr int GMT = (G * K + 7) / 8; // m-tiles of the stacked first stage
+    extern __shared__ __align__(16) double scratch[];
+    __shared__ int sUnit;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = lane >> 2, q = lane & 3;
+    double *S1 = scratch;                 // G stage-1 outputs, K * CP doubles each
+    double *S2 = S1 + G * K * D::CP;      // stage-2 output of the tuple in flight
+    const long long nReal8 = (long long)P.nRealF * 8;
+    const int4 *recs = reinterpret_cast<const int4 *>(B.tuples);
+    for (;;) {
+        if (threadIdx.x == 0) sUnit = atomicAdd(B.queue, 1);
+        __syncthreads();
+        const int u = sUnit;
+        __syncthreads();
+        if (u >= nUnits) break;
+        const UnitDesc ud = B.units[u];
+        double acc[NTW][D::MT][2];
+#pragma unroll
+        for (int i = 0; i < NTW; i++)
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) acc[i][mt][0] = acc[i][mt][1] = 0.0;
+        for (int t = 0; t < ud.cnt;) {
+            // ---- group: up to G consecutive tuples reading the same source block (uniform over the CTA)
+            int4 rec[G];
+            rec[0] = __ldg(recs + ud.t0 + t);
+            int g = 1;
+#pragma unroll
+            for (int i = 1; i < G; i++) {
+                rec[i] = rec[0];
+                if (g == i && t + i < ud.cnt) {
+                    const int4 r2 = __ldg(recs + ud.t0 + t + i);
+                    if (r2.x == rec[0].x) {
+                        rec[i] = r2;
+                        g = i + 1;
+                    }
+                }
+            }
+            const double *fblk = (rec[0].x < nReal8) ? P.fReal + (size_t)rec[0].x * D::Kd : P.fGen + (size_t)(rec[0].x - nReal8) * D::Kd;
+            // ---- stage 1, stacked: A[row = rr + 8 mt][t = q + 4 s] = O_x^(row / K)[t + K (row % K)]
+            {
+                double a[GMT][D::KS];
+#pragma unroll
+                for (int mt = 0; mt < GMT; mt++) {
+                    const int row = rr + 8 * mt, gi = row / K, c = row - gi * K;
+                    int oy = rec[0].y;
+#pragma unroll
+                    for (int i = 1; i < G; i++)
+                        if (gi == i) oy = rec[i].y;
+                    const double *op = P.mats + (size_t)oy * D::K2;
+#pragma unroll
+                    for (int s = 0; s < D::KS; s++) {
+                        const int tt = q + 4 * s;
+                        a[mt][s] = (gi < g && tt < K) ? __ldg(op + tt + K * c) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NTW; i++) {
+                    const int n0 = warp + 4 * i;
+                    if (n0 < D::NT) {
+                        const int r = 8 * n0 + rr;
+                        double b[D::KS];
+#pragma unroll
+                        for (int s = 0; s < D::KS; s++) {
+                            const int tt = q + 4 * s;
+                            b[s] = (r < D::K2 && tt < K) ? fblk[K * r + tt] : 0.0;
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < GMT; mt++) {
+                            if (8 * mt < g * K) {
+                                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                                for (int s = 0; s < D::KS; s++) dmma884(d0, d1, a[mt][s], b[s]);
+                                const int row = rr + 8 * mt, gi = row / K, c = row - gi * K, col = 8 * n0 + 2 * q;
+                                if (gi < g && col < D::K2)
+                                    *reinterpret_cast<double2 *>(S1 + (size_t)gi * K * D::CP + col + D::CP * c) = make_double2(d0, d1);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- stages 2 and 3 per tuple of the group, list order
+#pragma unroll
+            for (int gi = 0; gi < G; gi++) {
+                if (gi < g) {
+                    dmma_stage_coop<K, false, false, NTW>(S1 + (size_t)gi * K * D::CP, P.mats + (size_t)rec[gi].z * D::K2, S2, acc, rr, q, warp);
+                    __syncthreads();
+                    dmma_stage_coop<K, false, true, NTW>(S2, P.mats + (size_t)rec[gi].w * D::K2, nullptr, acc, rr, q, warp);
+                    __syncthreads(); // the next tuple's second stage overwrites S2; the next group's first stage overwrites S1
+                }
+            }
+            t += g;
+        }
+        double *pb = B.partials + (size_t)u * D::Kd;
+#pragma unroll
+        for (int i = 0; i < NTW; i++) {
+            const int n0 = warp + 4 * i;
+#pragma unroll
+            for (int mt = 0; mt < D::MT; mt++) {
+                const int c = rr + 8 * mt, col = 8 * n0 + 2 * q;
+                if (n0 < D::NT && c < K && col < D::K2) *reinterpret_cast<double2 *>(pb + col + D::K2 * c) = make_double2(acc[i][mt][0], acc[i][mt][1]);
+            }
+        }
+    }
+}
+
+template <int K, int G> void launch_contract_stack(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
+    using D = PadDims<K>;
+    static_assert((K & 1) == 0, "stacked contraction: even K only (16-byte aligned dense blocks)");
+    static int grid = 0;
+    const size_t bytes = (size_t)(G + 1) * K * D::CP * sizeof(double);
+    if (!grid) {
+        int dev = 0, sms = 0, perSm = 0;
+        MRX_CUDA(cudaGetDevice(&dev));
+        MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_stack_kernel<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pipe_contract_stack_kernel<K, G>, 128, bytes));
+        grid = sms * std::max(perSm, 1);
+    }
+    pipe_contract_stack_kernel<K, G><<<std::min(grid, nUnits), 128, bytes, st>>>(P, B, nUnits);
+}
+
 template <int K> void launch_contract_coop(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
     using D = PadDims<K>;
     static int grid = 0;
@@ -942,6 +1075,7 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
     MRX_CUDA(cudaMemsetAsync(B.queue, 0, sizeof(int), st));
     static const bool useFma = getenv("MRX_FMA") != nullptr; // development switch: FMA instead of padded-DMMA contraction
     static const bool warpPrivate = getenv("MRX_PAD_WARP") != nullptr; // development switch: one warp per unit instead of one CTA
+    static const bool noStack = getenv("MRX_NO_STACK") != nullptr;     // development switch: unstacked first stage
     if (P.K == 8) {
         const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
         pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
@@ -950,15 +1084,18 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
     } else if (P.K == 6) {
         if (useFma) launch_contract_fma<6>(P, B, nUnits, st);
         else if (warpPrivate) launch_contract_pad<6>(P, B, nUnits, st);
-        else launch_contract_coop<6>(P, B, nUnits, st);
+        else if (noStack) launch_contract_coop<6>(P, B, nUnits, st);
+        else launch_contract_stack<6, 4>(P, B, nUnits, st);
     } else if (P.K == 10) {
         if (useFma) launch_contract_fma<10>(P, B, nUnits, st);
         else if (warpPrivate) launch_contract_pad<10>(P, B, nUnits, st);
-        else launch_contract_coop<10>(P, B, nUnits, st);
+        else if (noStack) launch_contract_coop<10>(P, B, nUnits, st);
+        else launch_contract_stack<10, 4>(P, B, nUnits, st);
     } else if (P.K == 12) {
         if (useFma) launch_contract_fma<12>(P, B, nUnits, st);
         else if (warpPrivate) launch_contract_pad<12>(P, B, nUnits, st);
-        else launch_contract_coop<12>(P, B, nUnits, st);
+        else if (noStack) launch_contract_coop<12>(P, B, nUnits, st);
+        else launch_contract_stack<12, 2>(P, B, nUnits, st);
     } else if (P.K == 5) { // odd K (even polynomial orders): same padded-DMMA kernel, element-wise partial blocks
         launch_contract_coop<5>(P, B, nUnits, st);
     } else if (P.K == 7) {

@@ -48,33 +48,58 @@ __device__ __forceinline__ int cta_excl_scan_int(int v, int *sm, int &total) {
 
 // one CTA of 1024 threads
 __global__ void __launch_bounds__(1024) split_kernel(SplitParams S) {
-    __shared__ double sW[1024], sS[1024];
+    __shared__ double sW[2][1024], sS[2][1024];
     __shared__ int sm[33];
     __shared__ double shSq;
     const int tid = threadIdx.x;
     const int nG = S.nG;
-    // ---- norm bookkeeping in work-vector order
+    // ---- norm bookkeeping in work-vector order: ONE thread adds (the reference's summation order, TreeBuilder.cpp:56-66), the
+    //      other threads stage the next 1024 items meanwhile (double buffer), so only the dependent additions are serial
     double sNorm = S.state[0], wNorm = S.state[1];
     if (S.iter == 0) sNorm = 0.0;
-    for (int base = 0; base < nG; base += 1024) {
-        const int i = base + tid;
+    auto stage = [&](int buf, int i) {
         if (i < nG) {
             const double *n = S.normRows + ((size_t)(i % S.world) * S.rows + i / S.world) * 8;
             double w = 0.0;
 #pragma unroll
             for (int c = 1; c < 8; c++) w = fma(n[c], n[c], w); // MWNode::getWaveletNorm (squared), component order
-            sW[tid] = w;
-            sS[tid] = n[0] * n[0];
+            sW[buf][i & 1023] = w;
+            sS[buf][i & 1023] = n[0] * n[0];
         }
-        __syncthreads();
+    };
+    stage(0, tid); // chunk 0
+    const int nChunks = (nG + 1023) / 1024;
+    for (int c = 0; c < nChunks; c++) {
+        __syncthreads(); // chunk c is staged; thread 0 is done with chunk c - 1, whose buffer chunk c + 1 overwrites
+        const int buf = c & 1, base = c * 1024;
         if (tid == 0) {
             const int m = min(1024, nG - base);
-            if (S.iter == 0)
-                for (int k = 0; k < m; k++) sNorm += sS[k];
-            for (int k = 0; k < m; k++) wNorm += sW[k];
+            if (S.iter == 0) {
+                int k = 0;
+                for (; k + 8 <= m; k += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = sS[buf][k + q];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sNorm += v[q];
+                }
+                for (; k < m; k++) sNorm += sS[buf][k];
+            }
+            int k = 0;
+            for (; k + 8 <= m; k += 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = sW[buf][k + q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) wNorm += v[q];
+            }
+            for (; k < m; k++) wNorm += sW[buf][k];
+        } else if (c + 1 < nChunks) {
+            stage(buf ^ 1, base + 1024 + tid);
+            if (tid == 1) stage(buf ^ 1, base + 1024); // thread 0's item
         }
-        __syncthreads();
     }
+    __syncthreads();
     if (tid == 0) {
         const double sq = (sNorm < 0.0 || wNorm < 0.0) ? -1.0 : sNorm + wNorm;
         S.state[0] = sNorm;
@@ -178,7 +203,20 @@ __global__ void __launch_bounds__(1024) prep_local_kernel(PrepParams P) {
     }
 }
 
+__global__ void publish_kernel(const unsigned *__restrict__ src, volatile unsigned *hostDst, int words, volatile unsigned *hostFlag,
+                               unsigned seq) {
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < words; i++) hostDst[i] = src[i]; // a few words: one thread, one ordered sequence of stores
+    __threadfence_system();
+    *hostFlag = seq;
+}
+
 } // namespace
+
+void launch_publish(const void *src, void *hostDst, int words, unsigned *hostFlag, unsigned seq, cudaStream_t st) {
+    publish_kernel<<<1, 32, 0, st>>>(static_cast<const unsigned *>(src), static_cast<volatile unsigned *>(hostDst), words, hostFlag, seq);
+    MRX_CUDA(cudaGetLastError());
+}
 
 void launch_split(const SplitParams &S, cudaStream_t st) {
     split_kernel<<<1, 1024, 0, st>>>(S);

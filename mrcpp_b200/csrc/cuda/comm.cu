@@ -94,6 +94,9 @@ struct mrx_comm {
     std::vector<char *> peerBase;
     bool ipcTried = false, ipcOk = false;
     cudaStream_t pushStream = nullptr;
+    // unpacking of an iteration's rows into the node store runs on its own stream, beside the next iteration's kernels
+    cudaStream_t unpackStream = nullptr;
+    cudaEvent_t evGathered = nullptr, evUnpacked[kStageBufs] = {nullptr, nullptr, nullptr};
     cudaEvent_t evReduced[kStageBufs] = {nullptr, nullptr, nullptr}, evPushed[kStageBufs] = {nullptr, nullptr, nullptr};
     char *ipcScratch = nullptr; // device buffer for the handle all-gather
 };
@@ -215,6 +218,16 @@ void comm_push(mrx_comm *c, int buf, size_t off, size_t bytes) {
     }
     MRX_CUDA(cudaEventRecord(c->evPushed[buf], c->pushStream));
 }
+cudaStream_t comm_unpack_stream(mrx_comm *c) {
+    if (!c->unpackStream) {
+        MRX_CUDA(cudaStreamCreateWithFlags(&c->unpackStream, cudaStreamNonBlocking));
+        MRX_CUDA(cudaEventCreateWithFlags(&c->evGathered, cudaEventDisableTiming));
+        for (int b = 0; b < mrx_comm::kStageBufs; b++) MRX_CUDA(cudaEventCreateWithFlags(&c->evUnpacked[b], cudaEventDisableTiming));
+    }
+    return c->unpackStream;
+}
+cudaEvent_t comm_ev_gathered(const mrx_comm *c) { return c->evGathered; }
+cudaEvent_t comm_ev_unpacked(const mrx_comm *c, int buf) { return c->evUnpacked[buf]; }
 cudaEvent_t comm_ev_reduced(const mrx_comm *c, int buf) { return c->evReduced[buf]; }
 cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf) { return c->evPushed[buf]; }
 
@@ -256,6 +269,11 @@ void mrx_comm_destroy(mrx_comm *c) {
     }
     if (c->ipcScratch) cudaFree(c->ipcScratch);
     if (c->pushStream) cudaStreamDestroy(c->pushStream);
+    if (c->unpackStream) {
+        cudaStreamDestroy(c->unpackStream);
+        cudaEventDestroy(c->evGathered);
+        for (int b = 0; b < mrx_comm::kStageBufs; b++) cudaEventDestroy(c->evUnpacked[b]);
+    }
     for (int b = 0; b < mrx_comm::kStageBufs; b++) {
         if (c->evReduced[b]) cudaEventDestroy(c->evReduced[b]);
         if (c->evPushed[b]) cudaEventDestroy(c->evPushed[b]);

@@ -152,6 +152,9 @@ char *comm_stage(const mrx_comm *c, int buf);
 size_t comm_stage_bytes(const mrx_comm *c);
 void comm_push(mrx_comm *c, int buf, size_t off, size_t bytes);
 cudaEvent_t comm_ev_reduced(const mrx_comm *c, int buf);
+cudaStream_t comm_unpack_stream(mrx_comm *c); // side stream of the row unpack (created on first use, with its events)
+cudaEvent_t comm_ev_gathered(const mrx_comm *c);
+cudaEvent_t comm_ev_unpacked(const mrx_comm *c, int buf);
 cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf);
 
 // apply.cu
