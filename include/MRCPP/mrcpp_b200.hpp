@@ -6,7 +6,8 @@
 //     #include "MRCPP/Printer"     #include "MRCPP/Timer"
 //
 // (e.g. the reference's examples/poisson.cpp and examples/projection.cpp, unmodified) compiles against -Iinclude and
-// links with -lmrcpp_b200. Only what the path needs is here: D = 3, T = double, interpolating basis, non-periodic worlds.
+// links with -lmrcpp_b200. Only what the path needs is here: D = 3, T = double, interpolating basis; periodic worlds as the unit
+// cell [-1, 1]^3 without scaling factors.
 // Anything else is a compile-time error (static_assert) or aborts with a message, never a silent CPU fallback: the
 // arithmetic of every call below runs in the library (CUDA); this file only holds handles and formats output.
 //
@@ -132,12 +133,13 @@ public:
                          const std::array<double, D> &sf = {}, bool pbc = false)
             : scale(n)
             , corner(l)
-            , boxes(nb) {
+            , boxes(nb)
+            , periodic(pbc) {
         for (int d = 0; d < D; d++) {
             if (boxes[d] <= 0) boxes[d] = 1; // BoundingBox.cpp: zero means one box
             if (sf[d] != 0.0 && sf[d] != 1.0) MRCPP_B200_ABORT("scaling factors are not supported on the B200 path");
         }
-        if (pbc) MRCPP_B200_ABORT("periodic worlds are not supported on the B200 path");
+        // periodic worlds (BoundingBox.cpp:95-117): the unit cell [-1, 1]^D in box units; mrx_mra_set_periodic checks the shape
     }
     int getScale() const { return scale; }
     int size(int d) const { return boxes[d]; }
@@ -151,14 +153,17 @@ public:
     double getBoxLength(int d) const { return getUnitLength(d) * boxes[d]; }
     double getLowerBound(int d) const { return getUnitLength(d) * corner[d]; }
     double getUpperBound(int d) const { return getUnitLength(d) * (corner[d] + boxes[d]); }
-    bool isPeriodic() const { return false; }
-    bool operator==(const BoundingBox<D> &o) const { return scale == o.scale && corner == o.corner && boxes == o.boxes; }
+    bool isPeriodic() const { return periodic; }
+    bool operator==(const BoundingBox<D> &o) const {
+        return scale == o.scale && corner == o.corner && boxes == o.boxes && periodic == o.periodic;
+    }
     bool operator!=(const BoundingBox<D> &o) const { return !(*this == o); }
 
 private:
     int scale;
     std::array<int, D> corner;
     std::array<int, D> boxes;
+    bool periodic{false};
 };
 
 class ScalingBasis {
@@ -222,6 +227,7 @@ private:
             nb[d] = world.size(d);
         }
         h = std::shared_ptr<mrx_mra>(mrx_mra_create(order, world.getScale(), c, nb, maxDepth), mrx_mra_destroy);
+        if (world.isPeriodic()) mrx_mra_set_periodic(h.get(), 1);
     }
 };
 
@@ -464,6 +470,11 @@ public:
             : ConvolutionOperator<3>(mra, prec) {
         h = mrx_poisson_create(mra.handle(), prec);
     }
+    /// periodic worlds: src/operators/PoissonOperator.cpp:56-77
+    PoissonOperator(const MultiResolutionAnalysis<3> &mra, double prec, int root, int reach)
+            : ConvolutionOperator<3>(mra, prec) {
+        h = mrx_poisson_create_reach(mra.handle(), prec, root, reach);
+    }
 };
 
 /// src/operators/HelmholtzOperator.cpp:44-59
@@ -473,6 +484,12 @@ public:
             : ConvolutionOperator<3>(mra, prec)
             , mu(m) {
         h = mrx_helmholtz_create(mra.handle(), m, prec);
+    }
+    /// periodic worlds: src/operators/HelmholtzOperator.cpp:60-81
+    HelmholtzOperator(const MultiResolutionAnalysis<3> &mra, double m, double prec, int root, int reach)
+            : ConvolutionOperator<3>(mra, prec)
+            , mu(m) {
+        h = mrx_helmholtz_create_reach(mra.handle(), m, prec, root, reach);
     }
     double getMu() const { return mu; }
 
@@ -676,11 +693,30 @@ template <int D, typename T> void copy_func(FunctionTree<D, T> &out, FunctionTre
     v.push_back(std::make_tuple(T(1.0), &inp));
     add(-1.0, out, v);
 }
-/// mrcpp::apply(prec, out, oper, inp, precTrees, maxIter, absPrec): src/treebuilders/apply.cpp:214-251 -- the locally scaled
-/// precision is not built on the B200 path: aborts rather than silently ignoring the precision trees
+/// mrcpp::apply(prec, out, oper, inp, precTrees, maxIter, absPrec): src/treebuilders/apply.cpp:214-251 -- precision scaled per
+/// output node by the largest norms of the precision trees (the coefficients of the vector entries are not used, as in the reference)
 template <int D, typename T>
-void apply(double, FunctionTree<D, T> &, ConvolutionOperator<D> &, FunctionTree<D, T> &, FunctionTreeVector<D, T> &, int = -1, bool = false) {
-    MRCPP_B200_ABORT("apply with precTrees is not built on the B200 path");
+void apply(double prec, FunctionTree<D, T> &out, ConvolutionOperator<D> &oper, FunctionTree<D, T> &inp, FunctionTreeVector<D, T> &precTrees,
+           int maxIter = -1, bool absPrec = false) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    std::vector<mrx_tree *> h;
+    for (auto &t : precTrees) h.push_back(std::get<1>(t)->handle());
+    mrx_apply_prec_trees(prec, out.handle(), oper.handle(), inp.handle(), (int)h.size(), h.data(), maxIter, absPrec ? 1 : 0, nullptr,
+                         &b200::last_apply_stats());
+}
+/// mrcpp::apply_near_field / apply_far_field: src/treebuilders/apply.cpp:294-342 (periodic worlds: contributions from inside /
+/// outside the unit cell only)
+template <int D, typename T>
+void apply_near_field(double prec, FunctionTree<D, T> &out, ConvolutionOperator<D> &oper, FunctionTree<D, T> &inp, int maxIter = -1,
+                      bool absPrec = false) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_apply_unit_cell(1, prec, out.handle(), oper.handle(), inp.handle(), maxIter, absPrec ? 1 : 0, &b200::last_apply_stats());
+}
+template <int D, typename T>
+void apply_far_field(double prec, FunctionTree<D, T> &out, ConvolutionOperator<D> &oper, FunctionTree<D, T> &inp, int maxIter = -1,
+                     bool absPrec = false) {
+    if (out.getMRA() != inp.getMRA()) MRCPP_B200_ABORT("Incompatible MRA");
+    mrx_apply_unit_cell(0, prec, out.handle(), oper.handle(), inp.handle(), maxIter, absPrec ? 1 : 0, &b200::last_apply_stats());
 }
 /// mrcpp::multiply(prec, out, inp, maxIter, absPrec, useMaxNorms, conjugate): src/treebuilders/multiply.cpp:104-136
 template <int D, typename T>

@@ -59,6 +59,10 @@ const char *mrx_version(void);
 /* BoundingBox<3>(scale, corner, boxes) + InterpolatingBasis(order) + MultiResolutionAnalysis<3>(world,
  * basis, max_depth): src/trees/MultiResolutionAnalysis.cpp:69-77, examples/poisson.cpp:24-31 */
 mrx_mra *mrx_mra_create(int order, int root_scale, const int corner[3], const int nboxes[3], int max_depth);
+/* BoundingBox(n, l, nb, sf, pbc = true) (src/trees/BoundingBox.cpp:95-117): periodic world. The reference's periodic index
+ * arithmetic (src/utils/periodic_utils.cpp:35-85) works on the unit cell [-1, 1]^3 in box units, so the world must have root
+ * scale 0, corner (-1,-1,-1) and 2 x 2 x 2 root boxes (aborts otherwise); scaling factors are not supported (length unit = box). */
+int mrx_mra_set_periodic(mrx_mra *mra, int periodic);
 void mrx_mra_destroy(mrx_mra *mra);
 
 /* ---- function trees --------------------------------------------------------------------------- */
@@ -125,8 +129,21 @@ int mrx_project_gaussians_device(mrx_tree *tree, double prec, int n_gauss, const
 mrx_oper *mrx_poisson_create(const mrx_mra *mra, double prec);
 /* HelmholtzOperator(MRA, mu, prec): src/operators/HelmholtzOperator.cpp:44-59 */
 mrx_oper *mrx_helmholtz_create(const mrx_mra *mra, double mu, double prec);
+/* The Poisson / Helmholtz constructors keep the host tables of the last 16 operators built, keyed by every parameter they depend
+ * on (an SCF loop rebuilds the same operators every iteration, examples/scf.cpp:102); a repeated construction
+ * copies the tables (1-2 ms) instead of rebuilding them (30-200 ms). Counters of this process: */
+void mrx_oper_cache_stats(long long *hits, long long *misses);
 /* ConvolutionOperator<3>(MRA, GaussExp<1> kernel, prec): src/operators/ConvolutionOperator.cpp:50-62 */
 mrx_oper *mrx_convolution_create(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec);
+/* PoissonOperator(MRA, prec, root, reach) src/operators/PoissonOperator.cpp:56-77, HelmholtzOperator(MRA, mu, prec, root, reach)
+ * src/operators/HelmholtzOperator.cpp:60-81, ConvolutionOperator<3>(MRA, kernel, prec, root, reach)
+ * src/operators/ConvolutionOperator.cpp:63-76: operators for periodic worlds -- operator trees with reach + 1 root boxes
+ * (MWOperator::getOperatorMRA, MWOperator.cpp:110-129), kernel precision prec / 100, r_max stretched over the reach.
+ * The apply supports root == the world's root scale (0). */
+mrx_oper *mrx_poisson_create_reach(const mrx_mra *mra, double prec, int root, int reach);
+mrx_oper *mrx_helmholtz_create_reach(const mrx_mra *mra, double mu, double prec, int root, int reach);
+mrx_oper *mrx_convolution_create_reach(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec, int root,
+                                       int reach);
 /* ABGVOperator<3>(MRA, a, b): src/operators/ABGVOperator.cpp:46-74 */
 mrx_oper *mrx_abgv_create(const mrx_mra *mra, double a, double b);
 /* PHOperator<3>(MRA, order), order 1 or 2: src/operators/PHOperator.cpp:40-69 (Holoborodko smoothing derivative) */
@@ -187,6 +204,12 @@ int mrx_shard_cyclic_row(int i, int n, int world);
  * calls it with identical arguments. stats->f_applied / gen_nodes are summed over ranks. */
 int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
                       const mrx_comm *comm, mrx_apply_stats *stats);
+/* mrcpp::apply_near_field (inside = 1) / apply_far_field (inside = 0) = apply_on_unit_cell(inside, ...):
+ * src/treebuilders/apply.cpp:161-188, :294-342, ConvolutionCalculator::fillOperBand src/treebuilders/ConvolutionCalculator.cpp:191-218:
+ * on a periodic world, only the input nodes whose (unwrapped) index lies inside / outside the unit cell contribute. The plain
+ * mrx_apply on a periodic world is the sum of the two (band clipped to the operator's reach, ConvolutionCalculator.cpp:166-172). */
+int mrx_apply_unit_cell(int inside, double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
+                        mrx_apply_stats *stats);
 /* mrcpp::apply(prec, out, oper, inp, precTrees, maxIter, absPrec): src/treebuilders/apply.cpp:214-251. The precision is scaled
  * per output node by 1 / max_i sqrt(maxSquareNorm of prec_trees[i] at the node's index) (makeMaxSquareNorms, MWTree.cpp:536-543;
  * where a precision tree is coarser than the output grid the generated node's own scaled norm, MWNode.h:84), in the screening
@@ -204,6 +227,9 @@ int mrx_node_mw_transform(mrx_tree *tree, int kind /* MRX_COMPRESSION | MRX_RECO
 /* MWNode::cvTransform(kind): src/trees/MWNode.cpp:448-490 -- scaling coefficients of the children (0/1 representation, i.e. after
  * MRX_RECONSTRUCTION) <-> function values at the children's quadrature points, for the listed nodes, in place. */
 int mrx_node_cv_transform(mrx_tree *tree, int kind /* MRX_FORWARD | MRX_BACKWARD */, int n_nodes, const int *slots);
+/* project(prec, out, f) (src/treebuilders/project.cpp:85-104) of f(r) = sum_i amp[i] prod_d cos(pi kvec[3 i + d] r_d): a native
+ * callback for mrx_project_function (periodic test functions on the unit cell [-1, 1]^3) */
+int mrx_project_cosines(mrx_tree *tree, double prec, int n_terms, const double *amp, const double *kvec, int finalize);
 /* measurement: cvTransform(Forward) then (Backward) over every node, `reps` times between CUDA events; returns ms per pass
  * (algorithmic traffic 128 K^3 B per node and pass) */
 double mrx_bench_cv_transform(mrx_tree *tree, int reps);

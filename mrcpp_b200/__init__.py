@@ -34,12 +34,15 @@ def _dp(a):
 class MultiResolutionAnalysis:
     """BoundingBox<3> + InterpolatingBasis + max depth (src/trees/MultiResolutionAnalysis.h:49)."""
 
-    def __init__(self, order, root_scale=0, corner=(0, 0, 0), boxes=(1, 1, 1), max_depth=30):
+    def __init__(self, order, root_scale=0, corner=(0, 0, 0), boxes=(1, 1, 1), max_depth=30, periodic=False):
         _lib.init()
         self.order, self.root_scale, self.corner, self.boxes, self.max_depth = order, root_scale, tuple(corner), tuple(boxes), max_depth
+        self.periodic = bool(periodic)
         c = np.asarray(corner, dtype=np.int32)
         b = np.asarray(boxes, dtype=np.int32)
         self._h = _lib.load().mrx_mra_create(order, root_scale, _ip(c), _ip(b), max_depth)
+        if periodic:  # BoundingBox(..., pbc=True): unit cell [-1, 1]^3 (root scale 0, corner -1, 2 boxes per dimension)
+            _lib.load().mrx_mra_set_periodic(self._h, 1)
 
     @property
     def kp1(self):
@@ -228,20 +231,49 @@ class _Operator:
         return mats, norms
 
 
+def apply_near_field(prec, out, oper, inp, maxIter=-1, absPrec=False):
+    """mrcpp::apply_near_field (src/treebuilders/apply.cpp:318-342): periodic world, contributions from inside the unit cell only"""
+    st = ApplyStats()
+    _lib.load().mrx_apply_unit_cell(1, float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, C.byref(st))
+    return st
+
+
+def apply_far_field(prec, out, oper, inp, maxIter=-1, absPrec=False):
+    """mrcpp::apply_far_field (src/treebuilders/apply.cpp:272-316): periodic world, contributions from outside the unit cell only"""
+    st = ApplyStats()
+    _lib.load().mrx_apply_unit_cell(0, float(prec), out._h, oper._h, inp._h, int(maxIter), 1 if absPrec else 0, C.byref(st))
+    return st
+
+
+def project_cosines(prec, out, amp, kvec, finalize=True):
+    """project(prec, out, f) of f(r) = sum_i amp[i] prod_d cos(pi kvec[i][d] r_d) (host quadrature, native callback)"""
+    a = np.ascontiguousarray(amp, dtype=np.float64)
+    k = np.ascontiguousarray(kvec, dtype=np.float64).reshape(len(a), 3)
+    _lib.load().mrx_project_cosines(out._h, float(prec), len(a), _dp(a), _dp(k), 1 if finalize else 0)
+
+
 class PoissonOperator(_Operator):
     """src/operators/PoissonOperator.cpp:40-55"""
 
-    def __init__(self, mra, prec):
+    def __init__(self, mra, prec, root=None, reach=None):
+        """PoissonOperator(mra, prec) or, for periodic worlds, PoissonOperator(mra, prec, root, reach) (PoissonOperator.cpp:56-77)"""
         _lib.init()
-        super().__init__(mra, _lib.load().mrx_poisson_create(mra._h, float(prec)))
+        if root is None:
+            super().__init__(mra, _lib.load().mrx_poisson_create(mra._h, float(prec)))
+        else:
+            super().__init__(mra, _lib.load().mrx_poisson_create_reach(mra._h, float(prec), int(root), int(reach)))
 
 
 class HelmholtzOperator(_Operator):
     """src/operators/HelmholtzOperator.cpp:44-59"""
 
-    def __init__(self, mra, mu, prec):
+    def __init__(self, mra, mu, prec, root=None, reach=None):
+        """HelmholtzOperator(mra, mu, prec) or, for periodic worlds, (mra, mu, prec, root, reach) (HelmholtzOperator.cpp:60-81)"""
         _lib.init()
-        super().__init__(mra, _lib.load().mrx_helmholtz_create(mra._h, float(mu), float(prec)))
+        if root is None:
+            super().__init__(mra, _lib.load().mrx_helmholtz_create(mra._h, float(mu), float(prec)))
+        else:
+            super().__init__(mra, _lib.load().mrx_helmholtz_create_reach(mra._h, float(mu), float(prec), int(root), int(reach)))
 
 
 class ConvolutionOperator(_Operator):

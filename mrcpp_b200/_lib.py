@@ -45,6 +45,7 @@ SIGNATURES = {
     "mrx_device_count": (_I, []),
     "mrx_version": (C.c_char_p, []),
     "mrx_mra_create": (_P, [_I, _I, _PI, _PI, _I]),
+    "mrx_mra_set_periodic": (_I, [_P, _I]),
     "mrx_mra_destroy": (None, [_P]),
     "mrx_tree_create": (_P, [_P]),
     "mrx_tree_destroy": (None, [_P]),
@@ -76,6 +77,10 @@ SIGNATURES = {
     "mrx_poisson_create": (_P, [_P, _D]),
     "mrx_helmholtz_create": (_P, [_P, _D, _D]),
     "mrx_convolution_create": (_P, [_P, _I, _PD, _PD, _D]),
+    "mrx_poisson_create_reach": (_P, [_P, _D, _I, _I]),
+    "mrx_helmholtz_create_reach": (_P, [_P, _D, _D, _I, _I]),
+    "mrx_convolution_create_reach": (_P, [_P, _I, _PD, _PD, _D, _I, _I]),
+    "mrx_oper_cache_stats": (None, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "mrx_abgv_create": (_P, [_P, _D, _D]),
     "mrx_ph_create": (_P, [_P, _I]),
     "mrx_bs_create": (_P, [_P, _I]),
@@ -90,6 +95,8 @@ SIGNATURES = {
     "mrx_helmholtz_kernel": (_I, [_D, _D, _D, _D, _PD, _PD, _I]),
     "mrx_apply": (_I, [_D, _P, _P, _P, _I, _I, C.POINTER(ApplyStats)]),
     "mrx_apply_sharded": (_I, [_D, _P, _P, _P, _I, _I, _P, C.POINTER(ApplyStats)]),
+    "mrx_apply_unit_cell": (_I, [_I, _D, _P, _P, _P, _I, _I, C.POINTER(ApplyStats)]),
+    "mrx_project_cosines": (_I, [_P, _D, _I, _PD, _PD, _I]),
     "mrx_apply_prec_trees": (_I, [_D, _P, _P, _P, _I, C.POINTER(C.c_void_p), _I, _I, _P, C.POINTER(ApplyStats)]),
     "mrx_comm_unique_id": (_I, [C.c_char_p]),
     "mrx_comm_create": (_P, [_I, _I, C.c_char_p]),

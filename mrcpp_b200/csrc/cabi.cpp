@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <list>
 #include <map>
 #include <mutex>
 #include <string>
@@ -166,6 +167,16 @@ mrx_mra *mrx_mra_create(int order, int root_scale, const int corner[3], const in
     if (m->m.maxDepth > MaxDepth) MRX_ABORT("Beyond MaxDepth");
     if (m->m.maxScale() > MaxScale) MRX_ABORT("Beyond MaxScale");
     return m;
+}
+int mrx_mra_set_periodic(mrx_mra *mra, int periodic) {
+    // periodic_utils.cpp:35-85 works on the unit cell [-1, 1]^3 in box units: root scale 0, corner -1, two boxes per dimension
+    if (periodic) {
+        if (mra->m.rootScale != 0) MRX_ABORT("periodic world: root scale must be 0");
+        for (int d = 0; d < 3; d++)
+            if (mra->m.corner[d] != -1 || mra->m.nboxes[d] != 2) MRX_ABORT("periodic world: corner -1 and two boxes per dimension");
+    }
+    mra->m.periodic = periodic != 0;
+    return 0;
 }
 void mrx_mra_destroy(mrx_mra *mra) { delete mra; }
 
@@ -566,6 +577,27 @@ int mrx_project_function(mrx_tree *tree, double prec, mrx_func3 f, void *user, i
     return 0;
 }
 
+namespace {
+struct CosineSum {
+    int n;
+    const double *amp, *k; // f(r) = sum_i amp[i] prod_d cos(pi k[3 i + d] r_d)
+};
+double cosine_sum_eval(const double *r, void *user) {
+    const CosineSum *c = static_cast<const CosineSum *>(user);
+    double s = 0.0;
+    for (int i = 0; i < c->n; i++) {
+        double p = c->amp[i];
+        for (int d = 0; d < 3; d++) p *= std::cos(mrx::pi * c->k[3 * i + d] * r[d]);
+        s += p;
+    }
+    return s;
+}
+} // namespace
+int mrx_project_cosines(mrx_tree *tree, double prec, int n_terms, const double *amp, const double *kvec, int finalize) {
+    CosineSum c{n_terms, amp, kvec};
+    return mrx_project_function(tree, prec, cosine_sum_eval, &c, 1, finalize);
+}
+
 int mrx_project_gaussians_device(mrx_tree *tree, double prec, int n_gauss, const double *coef, const double *alpha,
                                  const double *pos, const int *power, int do_build_grid) {
     require_device("mrx_project_gaussians_device");
@@ -586,14 +618,72 @@ int mrx_project_gaussians_device(mrx_tree *tree, double prec, int n_gauss, const
 }
 
 // ---- operators
+} // extern "C"
+
+// ---- operator cache: an SCF loop constructs PoissonOperator / HelmholtzOperator(mu) objects again and again
+// (examples/scf.cpp:102); construction (kernel projection + cross correlation of every term, ConvolutionOperator.cpp:78-108)
+// costs 30-200 ms on the host, a copy of the finished tables 1-2 ms. The cache holds the HOST tables of the last operators built,
+// keyed by every parameter they depend on; a handle created from it owns its own copy (band widths are per-apply state of a
+// handle). MRX_OPER_CACHE=0 switches it off.
+namespace {
+struct OperCache {
+    std::mutex mu;
+    std::list<std::pair<std::string, std::shared_ptr<const Operator>>> lru;
+    long long hits = 0, misses = 0;
+};
+OperCache &oper_cache() {
+    static OperCache c;
+    return c;
+}
+std::string mra_key(const MRA<3> &m) {
+    char b[160];
+    std::snprintf(b, sizeof(b), "k%d n%d c%d,%d,%d b%d,%d,%d d%d p%d", m.order, m.rootScale, m.corner[0], m.corner[1], m.corner[2], m.nboxes[0],
+                  m.nboxes[1], m.nboxes[2], m.maxDepth, m.periodic ? 1 : 0);
+    return b;
+}
+template <typename F> Operator cached_operator(const std::string &key, F build) {
+    static const bool on = !(getenv("MRX_OPER_CACHE") && getenv("MRX_OPER_CACHE")[0] == '0');
+    OperCache &c = oper_cache();
+    if (on) {
+        std::lock_guard<std::mutex> lk(c.mu);
+        for (auto it = c.lru.begin(); it != c.lru.end(); ++it)
+            if (it->first == key) {
+                c.lru.splice(c.lru.begin(), c.lru, it);
+                c.hits++;
+                return *c.lru.front().second; // copy
+            }
+    }
+    Operator op = build();
+    if (on) {
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.misses++;
+        c.lru.emplace_front(key, std::make_shared<const Operator>(op));
+        while (c.lru.size() > 16) c.lru.pop_back();
+    }
+    return op;
+}
+std::string num_key(double v) {
+    char b[40];
+    std::snprintf(b, sizeof(b), " %.17g", v);
+    return b;
+}
+} // namespace
+
+extern "C" {
+void mrx_oper_cache_stats(long long *hits, long long *misses) {
+    OperCache &c = oper_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (hits) *hits = c.hits;
+    if (misses) *misses = c.misses;
+}
 mrx_oper *mrx_poisson_create(const mrx_mra *mra, double prec) {
     auto *o = new mrx_oper;
-    o->op = build_poisson_operator(mra->m, prec);
+    o->op = cached_operator("poisson " + mra_key(mra->m) + num_key(prec), [&] { return build_poisson_operator(mra->m, prec); });
     return o;
 }
 mrx_oper *mrx_helmholtz_create(const mrx_mra *mra, double mu, double prec) {
     auto *o = new mrx_oper;
-    o->op = build_helmholtz_operator(mra->m, mu, prec);
+    o->op = cached_operator("helmholtz " + mra_key(mra->m) + num_key(mu) + num_key(prec), [&] { return build_helmholtz_operator(mra->m, mu, prec); });
     return o;
 }
 mrx_oper *mrx_convolution_create(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec) {
@@ -604,6 +694,29 @@ mrx_oper *mrx_convolution_create(const mrx_mra *mra, int n_terms, const double *
     }
     auto *o = new mrx_oper;
     o->op = build_convolution_operator(mra->m, kernel, prec / 10.0, prec);
+    return o;
+}
+mrx_oper *mrx_poisson_create_reach(const mrx_mra *mra, double prec, int root, int reach) {
+    auto *o = new mrx_oper;
+    o->op = cached_operator("poisson_reach " + mra_key(mra->m) + num_key(prec) + num_key(root) + num_key(reach),
+                            [&] { return build_poisson_operator(mra->m, prec, root, reach); });
+    return o;
+}
+mrx_oper *mrx_helmholtz_create_reach(const mrx_mra *mra, double mu, double prec, int root, int reach) {
+    auto *o = new mrx_oper;
+    o->op = cached_operator("helmholtz_reach " + mra_key(mra->m) + num_key(mu) + num_key(prec) + num_key(root) + num_key(reach),
+                            [&] { return build_helmholtz_operator(mra->m, mu, prec, root, reach); });
+    return o;
+}
+mrx_oper *mrx_convolution_create_reach(const mrx_mra *mra, int n_terms, const double *coef, const double *expo, double prec, int root,
+                                       int reach) {
+    GaussExp<1> kernel(n_terms);
+    for (int i = 0; i < n_terms; i++) {
+        kernel[i].coef = coef[i];
+        kernel[i].alpha = expo[i];
+    }
+    auto *o = new mrx_oper;
+    o->op = build_convolution_operator(mra->m, kernel, prec / 100.0, prec, root, reach);
     return o;
 }
 mrx_oper *mrx_abgv_create(const mrx_mra *mra, double a, double b) {
@@ -705,6 +818,14 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
     if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
     if (oper->op.derivative) MRX_ABORT("mrx_apply: derivative operator passed to the convolution apply");
     device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats);
+    return 0;
+}
+int mrx_apply_unit_cell(int inside, double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
+                        mrx_apply_stats *stats) {
+    require_device("mrx_apply_unit_cell");
+    if (!(out->host.mra == inp->host.mra)) MRX_ABORT("Incompatible MRA");
+    if (oper->op.derivative) MRX_ABORT("mrx_apply_unit_cell: derivative operator passed to the convolution apply");
+    device_apply(prec, *out, *oper, *inp, max_iter, abs_prec != 0, stats, nullptr, nullptr, inside ? 1 : 2);
     return 0;
 }
 int mrx_apply_prec_trees(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int n_prec, mrx_tree *const *prec_trees, int max_iter,

@@ -821,7 +821,8 @@ static void run_apply_legacy(double prec, mrx_tree &out, mrx_oper &oper, mrx_tre
 // host's critical path loops over nodes (except the one-off set-up of the first work vector).
 static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
                            std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm,
-                           std::vector<std::vector<int>> *branchPairs = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr) {
+                           std::vector<std::vector<int>> *branchPairs = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr,
+                           int unitCell = 0) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
@@ -1146,6 +1147,9 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         E.gThrs = gThrs;
         E.fMaxNorm = fMaxNorm;
         E.screenOn = screenOn ? 1 : 0;
+        E.periodic = f.mra.periodic ? 1 : 0;
+        E.reach = op.operReach;
+        E.unitCell = unitCell;
         // apply with precTrees: gThrs = prec * precFac(node) * sqrt(|g|^2 / M) (ConvolutionCalculator.cpp:241-248)
         const double sqrtTerm = (g.squareNorm > 0.0) ? std::sqrt(g.squareNorm / static_cast<double>(M)) : g.squareNorm;
         if (usePrec) {
@@ -1446,8 +1450,17 @@ static bool use_pipeline(const mrx_tree &out) {
 }
 
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats, const mrx_comm *comm, const std::vector<mrx_tree *> *precTrees) {
+                  mrx_apply_stats *stats, const mrx_comm *comm, const std::vector<mrx_tree *> *precTrees, int unitCell) {
     require_device("device_apply");
+    if (out.host.mra.periodic) {
+        // apply on a periodic world: operator rooted at the world's root scale (no nodes above the root: touchParentNodes,
+        // ConvolutionCalculator.cpp:384-398, is the negative-scale variant this path does not build), with a reach
+        if (oper.op.operRoot != out.host.mra.rootScale) MRX_ABORT("periodic apply: operators rooted above the world are not supported");
+        if (oper.op.operReach < 0) MRX_ABORT("periodic apply: the operator was built without a reach (use the *_create_reach constructors)");
+        if (!use_pipeline(out)) MRX_ABORT("periodic apply is implemented for the work-list pipeline (orders 3..11) only");
+    } else if (unitCell != 0) {
+        MRX_ABORT("apply_near_field / apply_far_field need a periodic world");
+    }
     mrx_apply_stats S{};
     long long launches0 = launch_counter();
     double t0 = now_ms();
@@ -1485,7 +1498,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     std::vector<std::vector<int>> branchPairs;
     const bool bareRoots = out.host.nReal == out.host.nRoots;
     const bool pipe = use_pipeline(out);
-    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr, precTrees);
+    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr, precTrees, unitCell);
     else {
         if (comm_world(comm) > 1) MRX_ABORT("sharded apply is implemented for the work-list pipeline (orders 3..11) only");
         run_apply_legacy(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);

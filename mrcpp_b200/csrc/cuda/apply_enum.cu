@@ -49,6 +49,14 @@ __device__ __forceinline__ int find_node(const int *__restrict__ chunkOff, int n
 
 constexpr int kPendingBit = 1 << 30;
 
+// periodic::index_manipulation for scale >= 0 (periodic_utils.cpp:49-73): translation wrapped into [-2^n, 2^n)
+__device__ __forceinline__ int wrap_cell(int l, int scale) {
+    const int two_n = 1 << (scale + 1);
+    int t = l + (two_n >> 1);
+    t &= two_n - 1; // two_n is a power of two: the non-negative remainder
+    return t - (two_n >> 1);
+}
+
 // probe: one lane per (output node, reachable offset). Every pointer chase of the iteration is in flight at once (the
 // earlier warp-per-node loop serialised ~offCount / 32 dependent descents per node and was pure latency).
 __global__ void __launch_bounds__(256) enum_probe_kernel(EnumParams E) {
@@ -65,17 +73,30 @@ __global__ void __launch_bounds__(256) enum_probe_kernel(EnumParams E) {
     int node = 0, nd = 0, nc = 0;
     if (oi < o1) {
         const OffEntry oe = E.offs[oi];
-        const int lx = gn.y + oe.dx, ly = gn.z + oe.dy, lz = gn.w + oe.dz;
+        int lx = gn.y + oe.dx, ly = gn.z + oe.dy, lz = gn.w + oe.dz;
         int lo[3], hi[3];
 #pragma unroll
         for (int x = 0; x < 3; x++) {
             lo[x] = E.corner[x] * (1 << td);
             hi[x] = lo[x] + E.nboxes[x] * (1 << td) - 1;
+            if (E.periodic) { // `reach` cells around the world instead of the world (ConvolutionCalculator.cpp:169-171)
+                hi[x] = (lo[x] + E.nboxes[x] * (1 << td)) * E.reach - 1;
+                lo[x] = lo[x] * E.reach;
+            }
         }
         const double slack = 1.0 + 1e-9;
         // apply with precTrees: the node's own threshold (ConvolutionCalculator.cpp:244-245)
         const double gThrs = E.precFac ? E.prec * E.precFac[j] * E.sqrtTerm : E.gThrs;
-        const bool inb = lx >= lo[0] && lx <= hi[0] && ly >= lo[1] && ly <= hi[1] && lz >= lo[2] && lz <= hi[2];
+        bool inb = lx >= lo[0] && lx <= hi[0] && ly >= lo[1] && ly <= hi[1] && lz >= lo[2] && lz <= hi[2];
+        if (E.periodic) {
+            const int half = 1 << td; // unit cell [-2^n, 2^n) (periodic::in_unit_cell, periodic_utils.cpp:35-47)
+            const bool inCell = lx >= -half && lx < half && ly >= -half && ly < half && lz >= -half && lz < half;
+            if (E.unitCell == 1 && !inCell) inb = false;
+            if (E.unitCell == 2 && inCell) inb = false;
+            lx = wrap_cell(lx, td); // MWTree::getNode looks the wrapped index up (MWTree.cpp:341)
+            ly = wrap_cell(ly, td);
+            lz = wrap_cell(lz, td);
+        }
         if (inb && (!E.screenOn || oe.maxO * E.fMaxNorm * slack > gThrs)) {
             node = ((lx >> td) - E.corner[0]) + E.nboxes[0] * (((ly >> td) - E.corner[1]) + E.nboxes[1] * ((lz >> td) - E.corner[2]));
             node = descend(E.fChild0, node, nd, td, lx, ly, lz);
@@ -233,8 +254,13 @@ __global__ void __launch_bounds__(256) resolve_kernel(EnumParams E, int nPending
     NbrEntry e = E.nbr[idx];
     const int4 gn = E.gNodes[e.g];
     const int W = E.depthInfo[gn.x].W, cube = 2 * W + 1;
-    const int lx = gn.y + e.code % cube - W, ly = gn.z + (e.code / cube) % cube - W, lz = gn.w + e.code / (cube * cube) - W;
+    int lx = gn.y + e.code % cube - W, ly = gn.z + (e.code / cube) % cube - W, lz = gn.w + e.code / (cube * cube) - W;
     const int td = gn.x + E.depthShift;
+    if (E.periodic) {
+        lx = wrap_cell(lx, td);
+        ly = wrap_cell(ly, td);
+        lz = wrap_cell(lz, td);
+    }
     int nd = E.fDepth[e.fslot];
     const int node = descend(E.fChild0, e.fslot, nd, td, lx, ly, lz);
     E.nbr[idx].fslot = node;

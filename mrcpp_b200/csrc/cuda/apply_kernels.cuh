@@ -107,6 +107,11 @@ struct EnumParams {
     int screenOn;
     const double *precFac; // [nG] per-node precision factor (apply with precTrees) or nullptr: gThrs = prec * precFac * sqrtTerm
     double prec, sqrtTerm;
+    // periodic world (ConvolutionCalculator.cpp:166-172, :191-218; periodic_utils.cpp:35-73): the band is clipped to `reach`
+    // cells around the world, the input node is looked up at the index wrapped into the unit cell [-2^n, 2^n), the neighbour
+    // entry keeps the unwrapped offset (it selects the operator blocks). unitCell 1 / 2: keep only indices inside / outside
+    // the unit cell (apply_near_field / apply_far_field).
+    int periodic, reach, unitCell;
     // outputs
     GDesc *gdesc;
     NbrEntry *nbr;

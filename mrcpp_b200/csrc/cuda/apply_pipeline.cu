@@ -755,7 +755,7 @@ template <int K> __global__ void __launch_bounds__(128) pipe_contract_coop_kerne
 // then run per tuple as in pipe_contract_coop_kernel. Every output element is the same sequence of DMMA k-steps over the same
 // operands as in the unstacked kernel (padding contributes exact zeros), and tuples are accumulated in list order: results
 // are bit-identical to it.
-template <int K, int G> __global__ void __launch_bounds__(128) pipe_contract_stack_kernel(ApplyParams P, PipeBuffers B, int nUnits) {
+template <int K, int G, int MINB> __global__ void __launch_bounds__(128, MINB) pipe_contract_stack_kernel(ApplyParams P, PipeBuffers B, int nUnits) {
     using D = PadDims<K>;
     constexpr int NTW = (D::NT + 3) / 4;
     constexpr int GMT = (G * K + 7) / 8; // m-tiles of the stacked first stage
@@ -864,7 +864,7 @@ template <int K, int G> __global__ void __launch_bounds__(128) pipe_contract_sta
     }
 }
 
-template <int K, int G> void launch_contract_stack(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
+template <int K, int G, int MINB = 0> void launch_contract_stack(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
     using D = PadDims<K>;
     static_assert((K & 1) == 0, "stacked contraction: even K only (16-byte aligned dense blocks)");
     static int grid = 0;
@@ -873,11 +873,11 @@ template <int K, int G> void launch_contract_stack(const ApplyParams &P, const P
         int dev = 0, sms = 0, perSm = 0;
         MRX_CUDA(cudaGetDevice(&dev));
         MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_stack_kernel<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pipe_contract_stack_kernel<K, G>, 128, bytes));
+        MRX_CUDA(cudaFuncSetAttribute(pipe_contract_stack_kernel<K, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pipe_contract_stack_kernel<K, G, MINB>, 128, bytes));
         grid = sms * std::max(perSm, 1);
     }
-    pipe_contract_stack_kernel<K, G><<<std::min(grid, nUnits), 128, bytes, st>>>(P, B, nUnits);
+    pipe_contract_stack_kernel<K, G, MINB><<<std::min(grid, nUnits), 128, bytes, st>>>(P, B, nUnits);
 }
 
 template <int K> void launch_contract_coop(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
@@ -1090,7 +1090,13 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
         if (useFma) launch_contract_fma<10>(P, B, nUnits, st);
         else if (warpPrivate) launch_contract_pad<10>(P, B, nUnits, st);
         else if (noStack) launch_contract_coop<10>(P, B, nUnits, st);
-        else launch_contract_stack<10, 4>(P, B, nUnits, st);
+        else {
+            static const int variant = getenv("MRX_STACK_VARIANT") ? atoi(getenv("MRX_STACK_VARIANT")) : 0; // development switch
+            if (variant == 1) launch_contract_stack<10, 4, 5>(P, B, nUnits, st);
+            else if (variant == 2) launch_contract_stack<10, 2, 0>(P, B, nUnits, st);
+            else if (variant == 3) launch_contract_stack<10, 2, 6>(P, B, nUnits, st);
+            else launch_contract_stack<10, 4, 0>(P, B, nUnits, st);
+        }
     } else if (P.K == 12) {
         if (useFma) launch_contract_fma<12>(P, B, nUnits, st);
         else if (warpPrivate) launch_contract_pad<12>(P, B, nUnits, st);

@@ -160,8 +160,11 @@ cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf);
 // apply.cu
 /// precTrees != nullptr: apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (apply.cpp:214-251), precision scaled per
 /// output node by the largest norms of the precision trees (an empty vector scales by 1)
+/// unitCell: 0 plain apply; 1 / 2: apply_near_field / apply_far_field on a periodic world (apply.cpp:294-342): only the band
+/// entries inside / outside the unit cell contribute
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec,
-                  mrx_apply_stats *stats, const mrx_comm *comm = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr);
+                  mrx_apply_stats *stats, const mrx_comm *comm = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr,
+                  int unitCell = 0);
 void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int dir, mrx_apply_stats *stats);
 
 } // namespace mrx

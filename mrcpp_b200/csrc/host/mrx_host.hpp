@@ -87,6 +87,9 @@ template <int D> struct MRA {
     std::array<int, D> corner{};   // translation of the lower corner root box
     std::array<int, D> nboxes{};   // number of root boxes per dimension
     int maxDepth = MaxDepth;
+    // periodic world (BoundingBox(..., pbc = true), BoundingBox.cpp:95-117): the unit cell is [-1, 1]^D in box units, i.e. root
+    // scale 0, corner -1, two root boxes per dimension (periodic_utils.cpp:35-85 assumes exactly that)
+    bool periodic = false;
     int maxScale() const { return rootScale + maxDepth; }
     int nRoots() const {
         int n = 1;
@@ -97,7 +100,7 @@ template <int D> struct MRA {
     double upper(int d) const { return std::pow(2.0, -rootScale) * (corner[d] + nboxes[d]); }
     bool operator==(const MRA &o) const {
         return order == o.order && rootScale == o.rootScale && corner == o.corner && nboxes == o.nboxes &&
-               maxDepth == o.maxDepth;
+               maxDepth == o.maxDepth && periodic == o.periodic;
     }
 };
 
@@ -287,6 +290,7 @@ struct OperTerm {
 struct Operator {
     int k = 0, K = 0;
     int operRoot = 0;
+    int operReach = -10;   // MWOperator::oper_reach (MWOperator.h:75): >= 0 for operators built for a periodic world
     int order = 0;         // derivative order (0 for convolution operators)
     bool derivative = false;
     double buildPrec = 0.0;
@@ -303,9 +307,34 @@ GaussExp<1> poisson_kernel(double epsilon, double r_min, double r_max);
 GaussExp<1> helmholtz_kernel(double mu, double epsilon, double r_min, double r_max);
 
 /// ConvolutionOperator::initialize (ConvolutionOperator.cpp:78-108) for a 3-D MRA.
+/// root / reach: ConvolutionOperator(mra, kernel, prec, root, reach) (ConvolutionOperator.cpp:63-76); the defaults are those of
+/// ConvolutionOperator(mra): root = the world's root scale, reach = -10 (operator boxes = world boxes)
+Operator build_convolution_operator(const MRA<3> &mra, const GaussExp<1> &kernel, double k_prec, double o_prec, int oper_root,
+                                    int oper_reach);
 Operator build_convolution_operator(const MRA<3> &mra, const GaussExp<1> &kernel, double k_prec, double o_prec);
 Operator build_poisson_operator(const MRA<3> &mra, double prec);                  // PoissonOperator.cpp:40-55
 Operator build_helmholtz_operator(const MRA<3> &mra, double mu, double prec);     // HelmholtzOperator.cpp:44-59
+/// PoissonOperator(mra, prec, root, reach) PoissonOperator.cpp:56-77 / HelmholtzOperator(mra, mu, prec, root, reach)
+/// HelmholtzOperator.cpp:60-81: kernel precision prec / 100, r_max stretched over the reach (periodic worlds)
+Operator build_poisson_operator(const MRA<3> &mra, double prec, int oper_root, int oper_reach);
+Operator build_helmholtz_operator(const MRA<3> &mra, double mu, double prec, int oper_root, int oper_reach);
+/// periodic::index_manipulation (periodic_utils.cpp:49-73) for scale >= 0: translation wrapped into the unit cell [-2^n, 2^n)
+inline int periodic_wrap(int l, int scale) {
+    const int two_n = 1 << (scale + 1);
+    int t = l + two_n / 2;
+    if (t >= two_n) t = t % two_n;
+    if (t < 0) t = (t + 1) % two_n + two_n - 1;
+    return t - two_n / 2;
+}
+/// periodic::in_unit_cell (periodic_utils.cpp:35-47)
+inline bool periodic_in_unit_cell(const int l[3], int scale) {
+    const int two_n = 1 << (scale + 1);
+    for (int i = 0; i < 3; i++) {
+        const int t = l[i] + two_n / 2;
+        if (t >= two_n || t < 0) return false;
+    }
+    return true;
+}
 Operator build_abgv_operator(const MRA<3> &mra, double a, double b);
 /// PHOperator<3>(mra, order) (PHOperator.cpp:40-69) / BSOperator<3>(mra, order) (BSOperator.cpp:40-66): bandwidth-1 derivative
 /// operators from tabulated matrices

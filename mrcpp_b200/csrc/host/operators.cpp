@@ -207,11 +207,16 @@ MRA<1> kernel_mra(const MRA<3> &mra, int oper_root, int oper_reach) {
 
 Operator build_convolution_operator(const MRA<3> &mra, const GaussExp<1> &kernel, double k_prec, double o_prec) {
     // ConvolutionOperator(mra) -> MWOperator(mra, mra.getRootScale(), -10); initialize(); initOperExp()
-    const int oper_root = mra.rootScale, oper_reach = -10;
+    return build_convolution_operator(mra, kernel, k_prec, o_prec, mra.rootScale, -10);
+}
+
+Operator build_convolution_operator(const MRA<3> &mra, const GaussExp<1> &kernel, double k_prec, double o_prec, int oper_root,
+                                    int oper_reach) {
     Operator op;
     op.k = mra.order;
     op.K = mra.order + 1;
     op.operRoot = oper_root;
+    op.operReach = oper_reach;
     op.buildPrec = o_prec;
     op.terms.resize(kernel.size());
     MRA<1> k_mra = kernel_mra(mra, oper_root, oper_reach);
@@ -269,6 +274,31 @@ Operator build_helmholtz_operator(const MRA<3> &mra, double mu, double prec) {
     double r_max = calc_max_distance(mra);
     GaussExp<1> kernel = helmholtz_kernel(mu, k_prec, r_min, r_max);
     return build_convolution_operator(mra, kernel, k_prec, o_prec);
+}
+
+Operator build_poisson_operator(const MRA<3> &mra, double prec, int oper_root, int oper_reach) {
+    double o_prec = prec;
+    double k_prec = prec / 100.0;
+    double r_min = calc_min_distance(mra, k_prec);
+    double r_max = calc_max_distance(mra);
+    // Adjust r_max for periodic world (PoissonOperator.cpp:66-69)
+    const int rel_root = oper_root - mra.rootScale;
+    r_max *= std::pow(2.0, -rel_root);
+    r_max *= (2.0 * oper_reach) + 1.0;
+    GaussExp<1> kernel = poisson_kernel(k_prec, r_min, r_max);
+    return build_convolution_operator(mra, kernel, k_prec, o_prec, oper_root, oper_reach);
+}
+
+Operator build_helmholtz_operator(const MRA<3> &mra, double mu, double prec, int oper_root, int oper_reach) {
+    double o_prec = prec;
+    double k_prec = prec / 100.0;
+    double r_min = calc_min_distance(mra, k_prec);
+    double r_max = calc_max_distance(mra);
+    const int rel_root = oper_root - mra.rootScale;
+    r_max *= std::pow(2.0, -rel_root);
+    r_max *= (2.0 * oper_reach) + 1.0;
+    GaussExp<1> kernel = helmholtz_kernel(mu, k_prec, r_min, r_max);
+    return build_convolution_operator(mra, kernel, k_prec, o_prec, oper_root, oper_reach);
 }
 
 Operator build_abgv_operator(const MRA<3> &mra, double a, double b) {

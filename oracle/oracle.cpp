@@ -268,6 +268,8 @@ struct ConvCalc {
     const FilterSet *fs;
     std::vector<std::vector<int>> bandSizes; // [term][depth*65 + gt*8+ft]
     static constexpr int maxDepth = MaxDepth;
+    // apply_on_unit_cell / apply_near_field / apply_far_field (apply.cpp:161-188, :294-342): startManipulateOperator(inside)
+    bool manipulateOperator = false, onUnitcell = false;
 
     // initBandSizes / calcBandSizeFactor (ConvolutionCalculator.cpp:105-139), incl. the quirk that a
     // negative width does not stop the assignment at the end of the loop body
@@ -300,26 +302,43 @@ struct ConvCalc {
         }
     }
 
-    // makeOperBand / fillOperBand (ConvolutionCalculator.cpp:142-222), non-periodic
+    // makeOperBand / fillOperBand (ConvolutionCalculator.cpp:142-222). Periodic worlds: the band is clipped to `reach` cells
+    // around the world instead of to the world (:166-172) and keeps the UNWRAPPED indices (they give the operator translations);
+    // with a manipulated operator only the indices inside (near field) or outside (far field) the unit cell stay (:191-218).
     void band(const Tree<3> &gTree, int g, std::vector<std::array<int, 3>> &idx_band) const {
         idx_band.clear();
         int scale = gTree.nodes[g].scale;
         int o_depth = scale - oper->operRoot;
         int width = oper->getMaxBandWidth(o_depth);
         if (width < 0) return;
+        const bool periodic = gTree.mra.periodic;
+        const int reach = oper->operReach;
         int s[3], nbox[3];
         for (int i = 0; i < 3; i++) {
             int sI = gTree.nodes[g].l[i] - width, eI = gTree.nodes[g].l[i] + width;
             int nboxes = fTree->mra.nboxes[i] * (1 << o_depth);
             int c_i = fTree->mra.corner[i] * (1 << o_depth);
-            if (sI < c_i) sI = c_i;
-            if (eI > c_i + nboxes - 1) eI = c_i + nboxes - 1;
+            if (not periodic) {
+                if (sI < c_i) sI = c_i;
+                if (eI > c_i + nboxes - 1) eI = c_i + nboxes - 1;
+            } else {
+                if (sI < c_i * reach) sI = c_i * reach;
+                if (eI > (c_i + nboxes) * reach - 1) eI = (c_i + nboxes) * reach - 1;
+            }
             s[i] = sI;
             nbox[i] = eI - sI + 1;
         }
         for (int z = 0; z < nbox[2]; z++)
             for (int y = 0; y < nbox[1]; y++)
-                for (int x = 0; x < nbox[0]; x++) idx_band.push_back({s[0] + x, s[1] + y, s[2] + z});
+                for (int x = 0; x < nbox[0]; x++) {
+                    const int l[3] = {s[0] + x, s[1] + y, s[2] + z};
+                    if (manipulateOperator) {
+                        if (oper->operRoot != 0) MRX_ABORT("Cannot manipulate operators with non-zero operator scale");
+                        const bool in = periodic_in_unit_cell(l, scale);
+                        if (in != onUnitcell) continue;
+                    }
+                    idx_band.push_back({l[0], l[1], l[2]});
+                }
     }
 
     // tensorApplyOperComp (ConvolutionCalculator.cpp:333-382): three (kp1^2 x kp1)(kp1 x kp1) products,
@@ -465,8 +484,9 @@ struct ConvCalc {
 static void max_square_norms(const Tree<3> &t, std::vector<double> &maxS, std::vector<double> &maxW);
 
 void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter, bool absPrec, ApplyStats *stats,
-           const std::vector<Tree<3> *> *precTrees) {
+           const std::vector<Tree<3> *> *precTrees, int unitCell = 0) { // unitCell: 0 plain apply, 1 near field (inside), 2 far field
     if (!(out.mra == inp.mra)) MRX_ABORT("Incompatible MRA");
+    if (out.mra.periodic && oper.operRoot < out.mra.rootScale) MRX_ABORT("oracle: operators rooted above the world (negative scales) are not restated");
     double t0 = now();
     ApplyStats st;
     oper.calcBandWidths(prec);
@@ -476,6 +496,8 @@ void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter,
     calc.oper = &oper;
     calc.fTree = &inp;
     calc.fs = &filter_set(inp.k);
+    calc.manipulateOperator = unitCell != 0;
+    calc.onUnitcell = unitCell == 1;
     calc.initBandSizes();
     // apply(prec, out, oper, inp, precTrees, ...) (apply.cpp:214-251): the precision is scaled per output node by
     // 1 / max_i sqrt(maxSquareNorm of precTrees[i] at the node's index) -- makeMaxSquareNorms on every precision tree, getNode
@@ -522,8 +544,13 @@ void apply(double prec, Tree<3> &out, Operator &oper, Tree<3> &inp, int maxIter,
         for (int i = 0; i < nNodes; i++) {
             calc.band(out, workVec[i], idxs[i]);
             bands[i].resize(idxs[i].size());
-            for (size_t j = 0; j < idxs[i].size(); j++)
-                bands[i][j] = inp.getNodeTopo(out.nodes[workVec[i]].scale, idxs[i][j], &newParents, true);
+            for (size_t j = 0; j < idxs[i].size(); j++) {
+                std::array<int, 3> l = idxs[i][j];
+                // MWTree::getNode wraps the index into the unit cell of a periodic world (MWTree.cpp:341)
+                if (inp.mra.periodic)
+                    for (int d = 0; d < 3; d++) l[d] = periodic_wrap(l[d], out.nodes[workVec[i]].scale);
+                bands[i][j] = inp.getNodeTopo(out.nodes[workVec[i]].scale, l, &newParents, true);
+            }
         }
         fill_generated(inp, *calc.fs, newParents);
         st.genUsed += 8 * (long long)newParents.size();
@@ -985,6 +1012,13 @@ void orc_apply(double prec, void *out, void *oper, void *inp, int maxIter, int a
     orc::ApplyStats st;
     orc::apply(prec, *static_cast<Tree<3> *>(out), *static_cast<Operator *>(oper), *static_cast<Tree<3> *>(inp), maxIter,
                absPrec != 0, &st, nullptr);
+    copy_stats(st, stats);
+}
+// apply_near_field (inside = 1) / apply_far_field (inside = 0) on a periodic world (apply.cpp:294-342)
+void orc_apply_unit_cell(int inside, double prec, void *out, void *oper, void *inp, int maxIter, int absPrec, orc_stats *stats) {
+    orc::ApplyStats st;
+    orc::apply(prec, *static_cast<Tree<3> *>(out), *static_cast<Operator *>(oper), *static_cast<Tree<3> *>(inp), maxIter,
+               absPrec != 0, &st, nullptr, inside ? 1 : 2);
     copy_stats(st, stats);
 }
 void orc_apply_prec_trees(double prec, void *out, void *oper, void *inp, int nPrec, void **precTrees, int maxIter, int absPrec,

@@ -5,6 +5,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "MRCPP/Gaussians"
@@ -58,6 +59,44 @@ void *ref_mra_create(int order, int root_scale, const int *corner, const int *nb
     BoundingBox<3> world(root_scale, c, b);
     InterpolatingBasis basis(order);
     return new MultiResolutionAnalysis<3>(world, basis, max_depth);
+}
+/// periodic world (BoundingBox(n, l, nb, sf, pbc = true), src/trees/BoundingBox.cpp:95-117): unit cell [-1, 1]^3, scaling factor 1
+void *ref_mra_create_periodic(int order, int max_depth) {
+    ref_init();
+    std::array<int, 3> c{-1, -1, -1}, b{2, 2, 2};
+    std::array<double, 3> sf{1.0, 1.0, 1.0};
+    BoundingBox<3> world(0, c, b, sf, true);
+    InterpolatingBasis basis(order);
+    return new MultiResolutionAnalysis<3>(world, basis, max_depth);
+}
+/// project(prec, out, f) (src/treebuilders/project.cpp:85-104) of f(r) = sum_i amp[i] prod_d cos(pi k[3 i + d] r_d)
+void ref_project_cosines(void *t, double prec, int n, const double *amp, const double *k) {
+    auto &tree = static_cast<RefTree *>(t)->tree;
+    std::function<double(const Coord<3> &)> f = [n, amp, k](const Coord<3> &r) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) {
+            double p = amp[i];
+            for (int d = 0; d < 3; d++) p *= std::cos(pi * k[3 * i + d] * r[d]);
+            s += p;
+        }
+        return s;
+    };
+    project<3, double>(prec, tree, f);
+}
+/// operators for periodic worlds: PoissonOperator(mra, prec, root, reach) (PoissonOperator.cpp:56-77), HelmholtzOperator likewise
+void *ref_poisson_create_reach(void *mra, double prec, int root, int reach) {
+    return new PoissonOperator(*static_cast<MultiResolutionAnalysis<3> *>(mra), prec, root, reach);
+}
+void *ref_helmholtz_create_reach(void *mra, double mu, double prec, int root, int reach) {
+    return new HelmholtzOperator(*static_cast<MultiResolutionAnalysis<3> *>(mra), mu, prec, root, reach);
+}
+/// apply_near_field / apply_far_field (src/treebuilders/apply.cpp:294-342)
+void ref_apply_unit_cell(int inside, double prec, void *out, void *oper, void *inp, int max_iter, int abs_prec) {
+    auto &o = static_cast<RefTree *>(out)->tree;
+    auto &i = static_cast<RefTree *>(inp)->tree;
+    auto &P = *static_cast<ConvolutionOperator<3> *>(oper);
+    if (inside) apply_near_field<3, double>(prec, o, P, i, max_iter, abs_prec != 0);
+    else apply_far_field<3, double>(prec, o, P, i, max_iter, abs_prec != 0);
 }
 void ref_mra_destroy(void *m) { delete static_cast<MultiResolutionAnalysis<3> *>(m); }
 

@@ -197,7 +197,7 @@ static void fill_stats(const orc::ApplyStats &st, mrx_apply_stats *stats) {
     stats->n_nodes_out = st.nNodesOut;
 }
 void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, mrx_apply_stats *stats, const mrx_comm *,
-                  const std::vector<mrx_tree *> *precTrees) {
+                  const std::vector<mrx_tree *> *precTrees, int unitCell) {
     to_host(inp);
     host_storage(out);
     orc::ApplyStats st;
@@ -208,7 +208,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
             host_storage(*t); // the oracle generates nodes (with coefficients) below the leaves of the precision trees
             pt.push_back(&t->host);
         }
-    orc::apply(prec, out.host, oper.op, inp.host, maxIter, absPrec, &st, precTrees ? &pt : nullptr);
+    orc::apply(prec, out.host, oper.op, inp.host, maxIter, absPrec, &st, precTrees ? &pt : nullptr, unitCell);
     host_result(out);
     fill_stats(st, stats);
 }

@@ -33,6 +33,7 @@ def lib():
         o.orc_apply.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcStats)]
         o.orc_apply_prec_trees.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                            C.POINTER(OrcStats)]
+        o.orc_apply_unit_cell.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcStats)]
         o.orc_apply_derivative.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcStats)]
         o.orc_mw_transform_down.argtypes = [C.c_void_p, C.c_int]
         o.orc_mw_transform_up.argtypes = [C.c_void_p]
@@ -70,6 +71,15 @@ def apply(prec, out, oper, inp, maxIter=-1, absPrec=False):
     st = OrcStats()
     inp.sync_host()
     lib().orc_apply(prec, _th(out), _oh(oper), _th(inp), maxIter, 1 if absPrec else 0, C.byref(st))
+    _modified(out)
+    return st
+
+
+def apply_unit_cell(inside, prec, out, oper, inp, maxIter=-1, absPrec=False):
+    """apply_near_field (inside=True) / apply_far_field (inside=False) on a periodic world (src/treebuilders/apply.cpp:294-342)"""
+    st = OrcStats()
+    inp.sync_host()
+    lib().orc_apply_unit_cell(1 if inside else 0, prec, _th(out), _oh(oper), _th(inp), maxIter, 1 if absPrec else 0, C.byref(st))
     _modified(out)
     return st
 

@@ -36,6 +36,9 @@ def lib():
             "ref_tree_export": (I, [P, PI, PI, PI, PD, PD]), "ref_num_threads": (I, []),
             "ref_ph_create": (P, [P, I]), "ref_bs_create": (P, [P, I]), "ref_tree_integrate": (D, [P]), "ref_tree_save_txt": (None, [P, C.c_char_p]), "ref_tree_load_txt": (None, [P, C.c_char_p]), "ref_tree_evalf": (D, [P, PD, I]), "ref_build_grid_tree": (None, [P, P]), "ref_add": (None, [P, I, PD, C.POINTER(P)]),
             "ref_divergence": (None, [P, P, C.POINTER(P)]), "ref_add_adaptive": (None, [D, P, I, PD, C.POINTER(P), I, I]), "ref_multiply": (None, [D, P, I, PD, C.POINTER(P), I, I, I]), "ref_refine_grid": (I, [P, D, I, I]), "ref_power": (None, [D, P, P, D, I, I]), "ref_apply_prec_trees": (D, [D, P, P, P, I, C.POINTER(P), I, I]),
+            "ref_mra_create_periodic": (P, [I, I]), "ref_project_cosines": (None, [P, D, I, PD, PD]),
+            "ref_poisson_create_reach": (P, [P, D, I, I]), "ref_helmholtz_create_reach": (P, [P, D, D, I, I]),
+            "ref_apply_unit_cell": (None, [I, D, P, P, P, I, I]),
             "ref_add_inplace": (None, [P, D, P]), "ref_clear_grid": (None, [P]), "ref_build_grid_gaussians": (None, [P, I, PD, PD, PD, PI]),
         }
         for name, (res, args) in sig.items():
@@ -59,6 +62,14 @@ class MRA:
         b = np.ascontiguousarray(nboxes, dtype=np.int32)
         self.k = order
         self._h = lib().ref_mra_create(order, root_scale, _ip(c), _ip(b), max_depth)
+
+
+class PeriodicMRA(MRA):
+    """unit cell [-1, 1]^3 with periodic boundary conditions (BoundingBox(0, -1, 2, sf = 1, pbc = true))"""
+
+    def __init__(self, order, max_depth=25):
+        self.k = order
+        self._h = lib().ref_mra_create_periodic(order, max_depth)
 
 
 class Tree:
@@ -134,6 +145,24 @@ def bs(mra, order):
 
 def apply(prec, out, oper, inp, maxIter=-1, absPrec=False):
     return lib().ref_apply(float(prec), out._h, oper, inp._h, int(maxIter), 1 if absPrec else 0)
+
+
+def project_cosines(prec, tree, amp, kvec):
+    a = np.ascontiguousarray(amp, dtype=np.float64)
+    k = np.ascontiguousarray(kvec, dtype=np.float64).reshape(len(a), 3)
+    lib().ref_project_cosines(tree._h, float(prec), len(a), _dp(a), _dp(k))
+
+
+def poisson_reach(mra, prec, root, reach):
+    return lib().ref_poisson_create_reach(mra._h, float(prec), int(root), int(reach))
+
+
+def helmholtz_reach(mra, mu, prec, root, reach):
+    return lib().ref_helmholtz_create_reach(mra._h, float(mu), float(prec), int(root), int(reach))
+
+
+def apply_unit_cell(inside, prec, out, oper, inp, maxIter=-1, absPrec=False):
+    lib().ref_apply_unit_cell(1 if inside else 0, float(prec), out._h, oper, inp._h, int(maxIter), 1 if absPrec else 0)
 
 
 def apply_prec_trees(prec, out, oper, inp, prec_trees, maxIter=-1, absPrec=False):

@@ -43,8 +43,8 @@ def test_node_transform_and_prec_tree_gpu_tests_on_the_mock(mock_lib):
     """the drivers of the standalone node transforms (mrx_node_mw_transform / mrx_node_cv_transform) run for real; the apply with
     precision trees reaches the C ABI and the argument marshalling (its kernels are the B200's business)"""
     env = dict(os.environ, MRX_TEST_MOCK_LIB=mock_lib)
-    files = [os.path.join(cb.ROOT, "tests", f) for f in ("test_gpu_node_transforms.py", "test_gpu_prec_trees.py")]
-    r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"],
+    files = [os.path.join(cb.ROOT, "tests", f) for f in ("test_gpu_node_transforms.py", "test_gpu_prec_trees.py", "test_gpu_periodic.py")]
+    r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-k", "not needs_a_reach"],
                        capture_output=True, text=True, env=env, cwd=cb.ROOT, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout

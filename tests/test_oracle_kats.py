@@ -375,3 +375,34 @@ def test_quadrature_and_scaling_basis(libs):
             d = L.mrx_interp_scaling(k, j, 0.37, 1)
             fd = (L.mrx_interp_scaling(k, j, 0.37 + h, 0) - L.mrx_interp_scaling(k, j, 0.37 - h, 0)) / (2 * h)
             assert abs(d - fd) < 1e-5 * max(1.0, abs(d))
+
+
+def test_operator_cache_returns_identical_tables(libs):
+    """a repeated PoissonOperator / HelmholtzOperator construction is served from the cache of finished host
+    tables -- same separation rank, same band widths, bit-identical operator nodes -- and a different parameter misses"""
+    import ctypes as C
+    import time
+    mw, orc = libs
+    from mrcpp_b200 import _lib
+    L = _lib.load()
+    h0, m0 = C.c_longlong(0), C.c_longlong(0)
+    L.mrx_oper_cache_stats(C.byref(h0), C.byref(m0))
+    mra = mw.MultiResolutionAnalysis(5, -3, (-1, -1, -1), (2, 2, 2), 20)
+    t = time.perf_counter()
+    A = mw.HelmholtzOperator(mra, 0.83, 1e-4)
+    t_build = time.perf_counter() - t
+    t = time.perf_counter()
+    B = mw.HelmholtzOperator(mra, 0.83, 1e-4)
+    t_hit = time.perf_counter() - t
+    Cc = mw.HelmholtzOperator(mra, 0.84, 1e-4)
+    h1, m1 = C.c_longlong(0), C.c_longlong(0)
+    L.mrx_oper_cache_stats(C.byref(h1), C.byref(m1))
+    assert h1.value - h0.value == 1 and m1.value - m0.value == 2
+    assert A.size() == B.size() and np.array_equal(A.band_widths(1e-4), B.band_widths(1e-4))
+    for term in (0, A.size() // 2, A.size() - 1):
+        for depth in (0, 2):
+            ma, na = A.node(term, depth, 1)
+            mb, nb = B.node(term, depth, 1)
+            assert np.array_equal(ma, mb) and np.array_equal(na, nb)
+    assert t_hit < t_build
+    assert Cc.size() >= 1
