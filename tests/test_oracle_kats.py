@@ -399,10 +399,16 @@ def test_operator_cache_returns_identical_tables(libs):
     L.mrx_oper_cache_stats(C.byref(h1), C.byref(m1))
     assert h1.value - h0.value == 1 and m1.value - m0.value == 2
     assert A.size() == B.size() and np.array_equal(A.band_widths(1e-4), B.band_widths(1e-4))
-    for term in (0, A.size() // 2, A.size() - 1):
-        for depth in (0, 2):
-            ma, na = A.node(term, depth, 1)
-            mb, nb = B.node(term, depth, 1)
+    compared = 0
+    for term in range(A.size()):
+        for depth, transl in ((0, 0), (0, 1), (1, -1), (3, 2)):
+            try:
+                ma, na = A.node(term, depth, transl)
+            except IndexError:  # this term's operator tree has no such node
+                continue
+            mb, nb = B.node(term, depth, transl)
             assert np.array_equal(ma, mb) and np.array_equal(na, nb)
+            compared += 1
+    assert compared > A.size()
     assert t_hit < t_build
     assert Cc.size() >= 1
