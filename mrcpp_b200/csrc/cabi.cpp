@@ -390,8 +390,13 @@ int mrx_tree_save_txt(mrx_tree *tree, const char *path) {
     FILE *f = std::fopen(path, "w");
     if (!f) MRX_ABORT(std::string("cannot open ") + path);
     const int K = h.K, Kd = h.Kd, rscale = h.mra.rootScale;
+    // the format assumes the world [-L, L]^3 with two root boxes per direction (FunctionTree.cpp:313): any other world would be
+    // written with a wrong header and shifted translations -- refuse instead
+    for (int d = 0; d < 3; d++)
+        if (h.mra.corner[d] != -1 || h.mra.nboxes[d] != 2) MRX_ABORT("saveTreeTXT: the text format needs the world [-L, L]^3 (corner -1, 2 boxes per dimension)");
+    if (rscale > 0) MRX_ABORT("saveTreeTXT: the text format needs a root scale <= 0");
     double Lw = 1.0;
-    for (int i = 0; i > rscale; i--) Lw *= 2; // the world is assumed to be [-L, L]^3 with two root boxes per direction (FunctionTree.cpp:313)
+    for (int i = 0; i > rscale; i--) Lw *= 2;
     std::fprintf(f, "3\n");
     for (int d = 0; d < 3; d++) std::fprintf(f, "%.14g %.14g\n", -Lw, Lw);
     std::vector<int> ends;
@@ -427,14 +432,21 @@ int mrx_tree_load_txt(mrx_tree *tree, const char *path) {
     FILE *f = std::fopen(path, "r");
     if (!f) MRX_ABORT(std::string("cannot open ") + path);
     int D = 0, K = 0, nblk = 0;
-    double lo = 0.0, hi = 0.0;
     if (std::fscanf(f, "%d", &D) != 1 || D != 3) MRX_ABORT("load_txt: not a 3-D tree file");
-    for (int d = 0; d < 3; d++)
-        if (std::fscanf(f, "%lf %lf", &lo, &hi) != 2) MRX_ABORT("load_txt: bad header");
-    if (std::fscanf(f, "%d %d", &K, &nblk) != 2 || K != h.K) MRX_ABORT("load_txt: polynomial order of the file differs from the tree's");
     const int rscale = h.mra.rootScale, Kd = h.Kd;
+    // loadTreeTXT (FunctionTree.cpp:240-262) insists on the world [-L, L]^3 of THIS tree in all three dimensions, L = 2^(-root scale)
+    for (int d = 0; d < 3; d++)
+        if (h.mra.corner[d] != -1 || h.mra.nboxes[d] != 2) MRX_ABORT("loadTreeTXT: the text format needs the world [-L, L]^3 (corner -1, 2 boxes per dimension)");
+    if (rscale > 0) MRX_ABORT("loadTreeTXT: the text format needs a root scale <= 0");
+    double Lw = 1.0;
+    for (int i = 0; i > rscale; i--) Lw *= 2;
+    for (int d = 0; d < 3; d++) {
+        double lo = 0.0, hi = 0.0;
+        if (std::fscanf(f, "%lf %lf", &lo, &hi) != 2) MRX_ABORT("load_txt: bad header");
+        if (std::abs(lo + Lw) > 1e-12 * Lw || std::abs(hi - Lw) > 1e-12 * Lw) MRX_ABORT("load_txt: world of the file differs from the tree's");
+    }
+    if (std::fscanf(f, "%d %d", &K, &nblk) != 2 || K != h.K) MRX_ABORT("load_txt: polynomial order of the file differs from the tree's");
     const int L = (int)std::pow(2.0, -rscale);
-    if (std::abs(hi - std::pow(2.0, -rscale)) > 1e-12 * hi && rscale < 0) MRX_ABORT("load_txt: world of the file differs from the tree's");
     std::vector<int> map;
     for (int x = K - 1; x >= 0; x--)
         for (int y = K - 1; y >= 0; y--)
@@ -444,7 +456,7 @@ int mrx_tree_load_txt(mrx_tree *tree, const char *path) {
     h.allocCoefs = true;
     h.ensureCoefStorage();
     std::vector<double> vals(Kd);
-    std::vector<int> filled; // per node: how many of its eight child blocks the file has delivered
+    std::vector<unsigned char> fileMask; // per node: which of its eight child blocks the file has delivered
     for (int b = 0; b < nblk; b++) {
         int lev = 0, lm[3];
         if (std::fscanf(f, "%d %d %d %d", &lev, &lm[0], &lm[1], &lm[2]) != 4) MRX_ABORT("load_txt: truncated file");
@@ -458,36 +470,73 @@ int mrx_tree_load_txt(mrx_tree *tree, const char *path) {
             lp[d] = lc[d] >> 1;
             c |= (lc[d] & 1) << d;
         }
-        // the end node the block belongs to: created on the way down if the grid does not have it yet
+        // the node the block belongs to (parent of the block's box): created on the way down if the grid does not have it yet
         int n = h.rootIndex(cscale - 1, lp);
         if (n < 0) MRX_ABORT("load_txt: block outside the world");
         while (h.nodes[n].scale < cscale - 1) {
-            if (h.nodes[n].child0 < 0) h.createChildren(n, false);
+            if (h.nodes[n].child0 < 0) {
+                const int c0 = h.createChildren(n, false);
+                for (int q = 0; q < 8; q++) std::memset(h.coef(c0 + q), 0, sizeof(double) * h.ncoef);
+            }
             const int shift = cscale - 1 - h.nodes[n].scale - 1;
             int k = 0;
             for (int d = 0; d < 3; d++) k |= ((lp[d] >> shift) & 1) << d;
             n = h.nodes[n].child0 + k;
         }
-        if ((int)filled.size() < h.size()) filled.resize(h.size(), 0);
+        if ((int)fileMask.size() < h.size()) fileMask.resize(h.size(), 0);
+        if (fileMask[n] & (1u << c)) MRX_ABORT("load_txt: the same block twice");
         double *dst = h.coef(n) + (size_t)c * Kd;
         for (int i = 0; i < Kd; i++) dst[map[i]] = vals[i];
-        filled[n]++;
+        fileMask[n] |= (unsigned char)(1u << c);
     }
     std::fclose(f);
-    filled.resize(h.size(), 0);
-    for (int n = 0; n < h.size(); n++) {
-        if (h.isBranch(n)) {
-            if (filled[n] != 0) MRX_ABORT("load_txt: values for a node that also has finer nodes (not a file written by saveTreeTXT)");
+    fileMask.resize(h.size(), 0);
+    // quadrature-point values -> scaling coefficients of the children (cvTransform(Backward), FunctionTree.cpp:264-271); blocks the
+    // file did not deliver are zero and stay zero under the (diagonal) map
+    for (int n = 0; n < h.size(); n++)
+        if (fileMask[n]) cv_map_node(h, n, false);
+    // bottom-up (FunctionTree.cpp:273-303): a complete end node is compressed; a node with finer data below some of its children
+    // takes their scaling blocks, hands the blocks the file gave it directly to the children the file left undefined (scaling =
+    // the block, wavelets zero: they become end nodes), and is compressed itself -- the MADNESS convention allows sibling groups
+    // whose members end at different depths
+    std::vector<int> order(h.size());
+    for (int n = 0; n < h.size(); n++) order[n] = n;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h.nodes[a].scale > h.nodes[b].scale; });
+    std::vector<char> defined(h.size(), 0);
+    for (int n : order) {
+        if (!h.isBranch(n)) {
+            if (fileMask[n] == 0) continue; // an undefined child: its parent deals with it (or nothing refers to it: checked below)
+            if (fileMask[n] != 0xFF) MRX_ABORT("load_txt: incomplete sibling group at the finest level of a branch");
+            h.mwTransformNode(n, Compression);
+            h.nodes[n].flags |= FlagHasCoefs;
+            h.calcNorms(n);
+            defined[n] = 1;
             continue;
         }
-        if (filled[n] != 8) MRX_ABORT("load_txt: incomplete sibling group (not a file written by saveTreeTXT)");
-        cv_map_node(h, n, false);
+        const int c0 = h.nodes[n].child0;
+        for (int c = 0; c < 8; c++) {
+            double *blk = h.coef(n) + (size_t)c * Kd;
+            if (fileMask[n] & (1u << c)) {
+                // the file gave this child's values at this level: the child must not carry finer data
+                if (defined[c0 + c]) MRX_ABORT("load_txt: values for a box that also has finer boxes (not a tree file)");
+                double *cc = h.coef(c0 + c);
+                std::memcpy(cc, blk, sizeof(double) * Kd);
+                std::memset(cc + Kd, 0, sizeof(double) * (size_t)7 * Kd);
+                h.nodes[c0 + c].flags |= FlagHasCoefs;
+                h.calcNorms(c0 + c);
+                defined[c0 + c] = 1;
+            } else {
+                if (!defined[c0 + c]) MRX_ABORT("load_txt: incomplete sibling group (a box without values)");
+                std::memcpy(blk, h.coef(c0 + c), sizeof(double) * Kd); // the child's scaling block
+            }
+        }
         h.mwTransformNode(n, Compression);
         h.nodes[n].flags |= FlagHasCoefs;
         h.calcNorms(n);
+        defined[n] = 1;
     }
-    h.mwTransformUpSerial(); // branch nodes from their children (host: the file has just been parsed here)
-    for (int n = 0; n < h.size(); n++) h.nodes[n].flags |= FlagHasCoefs;
+    for (int n = 0; n < h.size(); n++)
+        if (!defined[n]) MRX_ABORT("load_txt: incomplete tree (a node without values)");
     h.calcSquareNorm();
     tree->hostCoefsValid = true;
     tree->devValid = false;

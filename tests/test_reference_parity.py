@@ -763,3 +763,56 @@ def test_periodic_apply_matches_reference(libs, kind, mode):
         # -lap u = 4 pi rho  ->  u = cos cos cos + 0.7 * 4 pi / (pi^2 (4 + 1 + 9)) cos(2 pi x) cos(pi y) cos(3 pi z)
         u0 = 1.0 + 0.7 * 4.0 * math.pi / (math.pi ** 2 * 14.0)
         assert abs(rg.evalf([0.0, 0.0, 0.0]) - u0) < 3e-2 * u0
+
+
+@needs_ref
+def test_text_file_with_mixed_sibling_group_matches_reference(libs, tmp_path):
+    """MADNESS-convention files may end the members of a sibling group at different depths; loadTreeTXT (FunctionTree.cpp:273-303)
+    fills the children the file leaves undefined from the parent's block and makes them end nodes. A file of that kind is derived
+    from a saveTreeTXT file (the 8 finest blocks of one end node replaced by ONE block at the end node's own level), read by the
+    reference and by mrx_tree_load_txt: node sets identical, coefficients equal to the file's precision; other worlds are refused."""
+    mw, orc = libs
+    k, prec = 5, 1e-4
+    funcs = gaussians(mw, 2, 11)
+    world = (k, -4, (-1, -1, -1), (2, 2, 2), 25)
+    rm, om = ref.MRA(*world), mw.MultiResolutionAnalysis(*world)
+    rf = ref.Tree(rm)
+    ref.project(prec, rf, funcs)
+    src = str(tmp_path / "ref.txt")
+    rf.save_txt(src)
+    lines = open(src).read().split("\n")
+    head, body = lines[:6], [ln for ln in lines[6:] if ln.strip()]
+    nblk = int(head[5])
+    blocks = [(tuple(int(x) for x in body[2 * i].split()), body[2 * i + 1]) for i in range(nblk)]
+    # the deepest end node: its 8 blocks share (level, l >> 1)
+    lev = max(b[0][0] for b in blocks)
+    key = next((b[0][0],) + tuple(x >> 1 for x in b[0][1:]) for b in blocks if b[0][0] == lev)
+    group = [b for b in blocks if (b[0][0],) + tuple(x >> 1 for x in b[0][1:]) == key]
+    assert len(group) == 8
+    rest = [b for b in blocks if b not in group]
+    vals = np.mean([[float(x) for x in b[1].split()] for b in group], axis=0)  # any values will do: both readers see the same file
+    merged = ((lev - 1,) + key[1:], " ".join("%.14g" % v for v in vals) + " ")
+    out = rest + [merged]
+    mixed = str(tmp_path / "mixed.txt")
+    with open(mixed, "w") as f:
+        f.write("\n".join(head[:5] + [str(len(out))]) + "\n")
+        for idx, v in out:
+            f.write(" ".join(str(x) for x in idx) + " \n" + v + "\n")
+    r2, o2 = ref.Tree(rm), mw.FunctionTree(om)
+    r2.load_txt(mixed)
+    o2.loadTreeTXT(mixed)
+    assert o2.getNNodes() == r2.n_nodes() == rf.n_nodes()
+    same_tree(r2.export(), o2.to_arrays(), tol=1e-11)
+    assert abs(r2.square_norm() - o2.getSquareNorm()) <= 1e-11 * r2.square_norm()
+    # a tree on another world refuses the file (all six bounds are checked, as in the reference)
+    import subprocess
+    import sys
+    import os
+    code = ("import mrcpp_b200 as mw\nfrom mrcpp_b200 import _lib\n_lib.load().mrx_init(_lib.TABLES.encode(), -1); _lib._device = -1\n"
+            f"m = mw.MultiResolutionAnalysis({k}, -3, (-1,-1,-1), (2,2,2), 25)\nmw.FunctionTree(m).loadTreeTXT({mixed!r})\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode != 0 and "world of the file differs" in r.stderr
+    code = code.replace("(-1,-1,-1), (2,2,2)", "(0,0,0), (1,1,1)").replace(", -3,", ", -4,")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode != 0 and "needs the world" in r.stderr
