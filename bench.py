@@ -562,16 +562,26 @@ def transforms_roofline(L, ft, K):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     out = {"hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
     nb = C.c_int(0)
-    for kind, name in ((0, "top_down"), (1, "bottom_up")):
+    # the += pass last: it accumulates into the tree (scratch by then)
+    for kind, name in ((0, "top_down"), (1, "bottom_up"), (2, "top_down_add")):
         L.mrx_bench_mw_transform(ft._h, kind, 2, C.byref(nb))
         ms = L.mrx_bench_mw_transform(ft._h, kind, 20, C.byref(nb))
-        gbs = nb.value * 128.0 * K ** 3 / (ms * 1e-3) / 1e9
-        # TopDown with overwrite also zeroes the 7 wavelet blocks of every child (MWNode.cpp:317-319): 576 K^3 B per parent
-        # really move, 4.5 x the algorithmic 128 K^3 B
+        per_parent = 192.0 if kind == 2 else 128.0  # += also reads the 8 scaling blocks it adds to
+        gbs = nb.value * per_parent * K ** 3 / (ms * 1e-3) / 1e9
+        # TopDown with overwrite also zeroes the 7 wavelet blocks of every child (MWNode.cpp:317-319, reference semantics: the
+        # children's wavelet coefficients are destroyed): 576 K^3 B per parent really move, 4.5 x the algorithmic 128 K^3 B
         moved = gbs * (4.5 if kind == 0 else 1.0)
         out[name] = {"ms_per_pass": ms, "parent_nodes": nb.value, "nodes_per_s": nb.value / (ms * 1e-3), "achieved_gbs": gbs,
                      "frac_of_hbm_peak": gbs / hbm, "moved_gbs": moved, "moved_frac_of_hbm_peak": moved / hbm,
+                     "algorithmic_bytes_per_parent": per_parent * K ** 3,
                      "fp64_tflops": nb.value * 96.0 * K ** 4 / (ms * 1e-3) / 1e12}
+    # MWNode::cvTransform (Forward then Backward over every node): element-wise, 128 K^3 B per node and pass
+    n_nodes = ft.getNNodes()
+    L.mrx_bench_cv_transform(ft._h, 2)
+    ms = L.mrx_bench_cv_transform(ft._h, 10)
+    gbs = n_nodes * 128.0 * K ** 3 / (ms * 1e-3) / 1e9
+    out["cv_transform"] = {"ms_per_pass": ms, "nodes": n_nodes, "nodes_per_s": n_nodes / (ms * 1e-3), "achieved_gbs": gbs,
+                           "frac_of_hbm_peak": gbs / hbm, "algorithmic_bytes_per_node": 128.0 * K ** 3}
     return out
 
 

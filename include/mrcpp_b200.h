@@ -293,9 +293,10 @@ double mrx_timer_stop_ms(void);
 double mrx_bench_dmma_tflops(int iters);
 double mrx_bench_dfma_tflops(int iters);
 double mrx_bench_hbm_gbs(long long bytes, int iters);
-/* filter kernels of MWTree::mwTransform alone: the level launches of one TopDown(overwrite) / BottomUp pass repeated
- * `reps` times between two CUDA events; returns ms per pass, *branch_nodes = parent nodes transformed per pass
- * (algorithmic traffic 128 (k+1)^3 bytes and 96 (k+1)^4 flop each) */
+/* filter kernels of MWTree::mwTransform alone: the level launches of one TopDown(overwrite) (type MRX_TOP_DOWN) / BottomUp
+ * (MRX_BOTTOM_UP) / TopDown(+=) (type 2: the mode mrcpp::apply closes with, apply.cpp:82; it accumulates, so the tree is scratch
+ * afterwards) pass repeated `reps` times between two CUDA events; returns ms per pass, *branch_nodes = parent nodes transformed
+ * per pass (algorithmic traffic 128 (k+1)^3 bytes -- 192 (k+1)^3 for += , which also reads the children -- and 96 (k+1)^4 flop each) */
 double mrx_bench_mw_transform(mrx_tree *tree, int type, int reps, int *branch_nodes);
 
 #ifdef __cplusplus

@@ -889,7 +889,8 @@ int mrx_apply_prec_trees(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *i
 double mrx_bench_mw_transform(mrx_tree *tree, int type, int reps, int *branch_nodes) {
     require_device("mrx_bench_mw_transform");
     double ms = 0.0;
-    device_mw_transform(*tree, type, true, true, reps > 0 ? reps : 1, &ms, branch_nodes);
+    // type 2: TopDown(+=), the mode mrcpp::apply closes with (apply.cpp:82); it accumulates, the tree is scratch afterwards
+    device_mw_transform(*tree, type == 2 ? MRX_TOP_DOWN : type, type != 2, true, reps > 0 ? reps : 1, &ms, branch_nodes);
     return ms;
 }
 int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec, const mrx_comm *comm,
