@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--centers", type=int, default=None)
     ap.add_argument("--cpu-centers", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (experiments only: the line then has e2e = null)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -423,13 +424,32 @@ def main():
     barrier()
     clocks = sampler.stop()
 
-    # ---- end-to-end arm (host buffers in, host buffers out)
-    one_step(True)
-    barrier()
+    # ---- end-to-end arm (host buffers in, host buffers out). Every rank keeps its copy of the input in pinned host memory: skipped
+    #      (e2e = null, with the reason) when the box does not have the memory for world x input tree
     E = Acc()
-    for _ in range(args.steps):
-        one_step(True, E)
-    barrier()
+    e2e_skip = None
+    if args.no_e2e:
+        e2e_skip = "--no-e2e"
+    else:
+        try:
+            import psutil
+            need = world * sum(ft.nbytes() for ft in fts) * 1.15
+            avail = psutil.virtual_memory().available
+            if need > avail:
+                e2e_skip = "host memory: %d ranks x %.1f GB of pinned input > %.1f GB available" % (world, need / world / 1.15 / 1e9, avail / 1e9)
+        except Exception:  # noqa: BLE001
+            pass
+    if world > 1:
+        flag = torch.tensor([1.0 if e2e_skip else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag[0]) > 0 and not e2e_skip:
+            e2e_skip = "skipped on another rank"
+    if not e2e_skip:
+        one_step(True)
+        barrier()
+        for _ in range(args.steps):
+            one_step(True, E)
+        barrier()
 
     tot_ms, e2e_ms = A.ms, E.ms
     nodes, tuples, launches, h2d, d2h = A.nodes, A.tuples, A.launches, E.h2d, E.d2h
@@ -477,8 +497,9 @@ def main():
                          "peak_arithmetic_limit": "148 SM x 128 flop/clk x sm_mhz",
                          "kernel_share_of_step": A.contract_ms / A.ms, "all_apply_kernels_share_of_step": A.kern_ms / A.ms},
             "clocks": clocks,
-            "e2e": {"value": e2e_nodes / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+            "e2e": ({"value": e2e_nodes / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d),
+                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps} if not e2e_skip else None),
+            "e2e_skipped": e2e_skip,
             "gpu_launches": int(launches),
             "detail": {"applies_per_step_this_rank": napply, "output_nodes_per_step": nodes // args.steps,
                        "final_tree_nodes_last_apply": last.n_nodes_out, "iterations_last_apply": last.iterations,
@@ -496,7 +517,7 @@ def main():
         line["roofline"]["traffic"], line["roofline"]["traffic_source"] = ncu_traffic(kernel, k, A.tuples_rank / max(A.iters, 1))
         if world == 1 and args.config == "headline":
             line["transforms"] = transforms_roofline(L, fts[0], K)
-        if world == 1 and args.cpu_centers != args.centers:
+        if world == 1 and args.cpu_centers != args.centers and not args.no_e2e:
             # the workload the reference arm times (bench.py --impl reference), on the GPU: a ratio on IDENTICAL inputs can be
             # formed from this object and the reference arm's line. Small workload: launch- and latency-bound on a B200.
             sfuncs = workload_inputs(mw, args, args.cpu_centers)

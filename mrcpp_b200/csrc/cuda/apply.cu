@@ -1187,7 +1187,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
             inp.dev.genNorms.reserve((size_t)(fTotal - fRealN + 8 * nNew), true, st);
             launch_enum_create(E, nNew, fTotal, st);
             if (lazy) { // real leaves that get generated children are read by the generation kernel
-                scr.fetchList.reserve(std::max(nNew, 1), false, st);
+                scr.fetchList.reserve((size_t)8 * std::max(nNew, 1), false, st);
                 MRX_CUDA(cudaMemsetAsync(scr.fetchCnt.p, 0, sizeof(int), st));
                 launch_fetch_mark(scr.newParents.p, nNew, fRealN, inp.dev.resident.p, scr.fetchList.p, scr.fetchCnt.p, st);
                 launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, scr.fetchCnt.p, ncoef, scr.fetchTotal.p, st);
@@ -1280,7 +1280,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         B.units = scr.units2.p;
         B.partials = scr.partials.p;
         if (lazy) {
-            scr.fetchList.reserve(std::max(nNbr, 1), false, st);
+            scr.fetchList.reserve((size_t)8 * std::max(nNbr, 1), false, st);
             MRX_CUDA(cudaMemsetAsync(scr.fetchCnt.p, 0, sizeof(int), st));
             B.resident = inp.dev.resident.p;
             B.fetchList = scr.fetchList.p;
@@ -1425,7 +1425,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         unsigned long long fetched = 0;
         MRX_CUDA(cudaMemcpyAsync(&fetched, scr.fetchTotal.p, sizeof(fetched), cudaMemcpyDeviceToHost, st));
         MRX_CUDA(cudaStreamSynchronize(st));
-        S.h2d_bytes += (long long)fetched * ncoef * (long long)sizeof(double);
+        S.h2d_bytes += (long long)fetched * Kd * (long long)sizeof(double); // coefficient blocks gathered
     }
     if (world > 1) {
         double h[2] = {(double)S.f_applied, (double)S.gen_nodes};

@@ -291,34 +291,44 @@ __global__ void __launch_bounds__(256) create_kernel(EnumParams E, int nNew, int
     E.genItems[2 * r + 1] = c0;
 }
 
-// ---- lazy residency of the input tree (engine.hpp DeviceTree::partial): nodes the apply is about to read are gathered from
-//      the pinned host chunks by the device itself; only they cross PCIe
+// ---- lazy residency of the input tree (engine.hpp DeviceTree::partial): the (node, block) pairs the apply is about to read
+//      are gathered from the pinned host chunks by the device itself; only they cross PCIe. resident[8 node + block].
 __global__ void __launch_bounds__(256) fetch_mark_kernel(const int *__restrict__ list, int n, int nRealF, int *__restrict__ resident,
                                                          int *__restrict__ fetchList, int *__restrict__ fetchCnt) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int node = list[i];
-    if (node < nRealF && atomicExch(&resident[node], 1) == 0) fetchList[atomicAdd(fetchCnt, 1)] = node;
+    if (i >= 8 * n) return;
+    const int node = list[i >> 3]; // generation reads all eight blocks of a real leaf
+    if (node < nRealF) {
+        const int blk = node * 8 + (i & 7);
+        if (atomicExch(&resident[blk], 1) == 0) fetchList[atomicAdd(fetchCnt, 1)] = blk;
+    }
 }
 
 __global__ void __launch_bounds__(256) fetch_nodes_kernel(double *__restrict__ coefs, const double *const *__restrict__ chunkTab,
                                                           const int *__restrict__ list, const int *__restrict__ cnt, int ncoef,
                                                           unsigned long long *__restrict__ total) {
     const int n = *cnt;
+    const int Kd = ncoef / 8;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int slot = list[i];
-        const double2 *src = reinterpret_cast<const double2 *>(chunkTab[slot >> 6] + (size_t)(slot & 63) * ncoef);
-        double2 *dst = reinterpret_cast<double2 *>(coefs + (size_t)slot * ncoef);
-        for (int e = threadIdx.x; e < ncoef / 2; e += 256) dst[e] = src[e];
+        const int blk = list[i], slot = blk >> 3, c = blk & 7;
+        const double *src = chunkTab[slot >> 6] + (size_t)(slot & 63) * ncoef + (size_t)c * Kd;
+        double *dst = coefs + (size_t)slot * ncoef + (size_t)c * Kd;
+        if ((Kd & 1) == 0) {
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 *d2 = reinterpret_cast<double2 *>(dst);
+            for (int e = threadIdx.x; e < Kd / 2; e += 256) d2[e] = s2[e];
+        } else {
+            for (int e = threadIdx.x; e < Kd; e += 256) dst[e] = src[e];
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *total += (unsigned long long)n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total += (unsigned long long)n; // blocks fetched
 }
 
 } // namespace
 
 void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *fetchList, int *fetchCnt, cudaStream_t st) {
     if (n <= 0) return;
-    fetch_mark_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, n, nRealF, resident, fetchList, fetchCnt);
+    fetch_mark_kernel<<<(8 * n + 255) / 256, 256, 0, st>>>(list, n, nRealF, resident, fetchList, fetchCnt);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

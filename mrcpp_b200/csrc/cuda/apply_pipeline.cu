@@ -310,14 +310,20 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
     unsigned pos1 = B.blockTupOff[nb.g * 8 + 4 + (lane >> 3)] + (unsigned)B.segOff[(size_t)w * 64 + 32 + lane];
     const int fbase = (nb.fslot < P.nRealF) ? nb.fslot * 8 : P.nRealF * 8 + (nb.fslot - P.nRealF);
     const bool gen = nb.fslot >= P.nRealF;
-    bool anyPass = false;
+    unsigned ftUsed = 0; // ft blocks of the input node that surviving tuples of this lane read
     for (int base = 0; base < nc; base += 32) {
         const int c = base + lane;
         unsigned long long pass = 0ull;
         int oi0 = 0, oi1 = 0, oi2 = 0;
         if (c < nc) {
             pass = B.masks[(size_t)nb.candBase + c];
-            anyPass = anyPass || (pass != 0ull);
+            {
+                unsigned long long m = pass; // fold the gt index away: bit ft of the low byte = some (gt, ft) survives
+                m |= m >> 32;
+                m |= m >> 16;
+                m |= m >> 8;
+                ftUsed |= (unsigned)(m & 0xFFull);
+            }
             if (pass) {
                 const int nbase = P.nodeBase[(size_t)P.candTerm[e0 + c] * P.DM + g.depth];
                 oi0 = (nbase + d[0]) * 4;
@@ -355,10 +361,14 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
             }
         }
     }
-    // lazy residency: the contraction will read this input node; queue it if it is not in HBM yet
+    // lazy residency, per coefficient BLOCK: the contraction will read these (input node, ft) blocks; queue the ones that are
+    // not in HBM yet (a smooth region contributes its scaling block and few wavelet blocks: whole nodes need not cross PCIe)
     if (B.resident != nullptr && !gen) {
-        const bool any = __any_sync(0xffffffffu, anyPass);
-        if (any && lane == 0 && atomicExch(&B.resident[nb.fslot], 1) == 0) B.fetchList[atomicAdd(B.fetchCnt, 1)] = nb.fslot;
+        const unsigned used = __reduce_or_sync(0xffffffffu, ftUsed);
+        if (lane < 8 && ((used >> lane) & 1u)) {
+            const int blk = nb.fslot * 8 + lane;
+            if (atomicExch(&B.resident[blk], 1) == 0) B.fetchList[atomicAdd(B.fetchCnt, 1)] = blk;
+        }
     }
 }
 

@@ -64,11 +64,11 @@ void tree_lazy_begin(mrx_tree &t) {
     const int n = h.nReal;
     t.dev.coefs.reserve((size_t)n * h.ncoef, false, st);
     t.dev.norms.reserve((size_t)n * 8, false, st);
-    t.dev.resident.reserve(std::max(n, 1), false, st);
+    t.dev.resident.reserve((size_t)8 * std::max(n, 1), false, st); // one flag per coefficient block
     const auto &chunks = h.coefChunks();
     t.dev.chunkTab.reserve(std::max<size_t>(chunks.size(), 1), false, st);
     MRX_CUDA(cudaMemcpyAsync(t.dev.norms.p, h.cnorm.data(), sizeof(double) * (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    MRX_CUDA(cudaMemsetAsync(t.dev.resident.p, 0, sizeof(int) * std::max(n, 1), st));
+    MRX_CUDA(cudaMemsetAsync(t.dev.resident.p, 0, sizeof(int) * (size_t)8 * std::max(n, 1), st));
     MRX_CUDA(cudaMemcpyAsync(t.dev.chunkTab.p, chunks.data(), sizeof(double *) * chunks.size(), cudaMemcpyHostToDevice, st));
     MRX_CUDA(cudaStreamSynchronize(st));
     t.dev.nNodes = n;
