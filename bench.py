@@ -388,6 +388,8 @@ def main():
         sts = []
         for ft in trees:
             out = mw.FunctionTree(mra)
+            if e2e and (comm is None or rank == 0):
+                out.set_host_mirror(True)  # the apply streams the result into host memory while it runs and returns with it there
             st = mw.apply(prec, out, oper, ft, comm=comm)
             if e2e and (rank == 0 or by_tree):
                 out.sync_host()  # result back in host memory (sharded apply: every rank holds the identical tree, rank 0 reads it back)

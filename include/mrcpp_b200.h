@@ -45,6 +45,7 @@ typedef struct mrx_apply_stats {
     long long kernel_launches; /* CUDA kernels launched by this call                                    */
     long long f_applied_rank;  /* sharded apply: tuples contracted by THIS rank (f_applied = sum over ranks) */
     long long h2d_bytes;       /* input-tree bytes this call moved host -> device (0 if the input was resident)     */
+    long long d2h_bytes;       /* result bytes this call left in host memory (output tree with a host mirror), else 0 */
 } mrx_apply_stats;
 
 /* ---- library / device ------------------------------------------------------------------------ */
@@ -275,6 +276,10 @@ int mrx_tree_power(double prec, mrx_tree *out, mrx_tree *inp, double p, int max_
 /* residency control for measurement: host->device / device->host copies of a tree's coefficients */
 int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer                        */
 int mrx_tree_sync_host(mrx_tree *tree);   /* download if the device copy is newer                    */
+/* keep the host copy of an apply OUTPUT current: mrx_apply then streams the result into the tree's pinned host chunks while it
+ * runs (copy engines, beside the next refinement iteration's kernels) and returns with the tree in host memory, so that a
+ * binding that reads coefficients on the host pays a fraction of the final download (one GPU; ignored by the sharded apply) */
+int mrx_tree_set_host_mirror(mrx_tree *tree, int on);
 int mrx_tree_drop_device(mrx_tree *tree); /* free the HBM copy (next use uploads again)              */
 long long mrx_tree_bytes(const mrx_tree *tree);
 

@@ -194,6 +194,10 @@ class FunctionTree:
     def sync_host(self):
         _lib.load().mrx_tree_sync_host(self._h)
 
+    def set_host_mirror(self, on=True):
+        """keep the host copy of this tree current when an apply writes it (result streamed down while the apply runs)"""
+        _lib.load().mrx_tree_set_host_mirror(self._h, 1 if on else 0)
+
     def drop_device(self):
         _lib.load().mrx_tree_drop_device(self._h)
 

@@ -27,6 +27,7 @@ class ApplyStats(C.Structure):
         ("kernel_launches", C.c_longlong),
         ("f_applied_rank", C.c_longlong),
         ("h2d_bytes", C.c_longlong),
+        ("d2h_bytes", C.c_longlong),
     ]
 
     def as_dict(self):
@@ -116,6 +117,7 @@ SIGNATURES = {
     "mrx_tree_rescale": (_I, [_P, _D]),
     "mrx_tree_sync_device": (_I, [_P]),
     "mrx_tree_sync_host": (_I, [_P]),
+    "mrx_tree_set_host_mirror": (_I, [_P, _I]),
     "mrx_tree_drop_device": (_I, [_P]),
     "mrx_tree_bytes": (C.c_longlong, [_P]),
     "mrx_tree_host_handle": (_P, [_P]),

@@ -1035,6 +1035,10 @@ int mrx_tree_sync_host(mrx_tree *tree) {
     tree_download(*tree);
     return 0;
 }
+int mrx_tree_set_host_mirror(mrx_tree *tree, int on) {
+    tree->hostMirror = on != 0;
+    return 0;
+}
 int mrx_tree_drop_device(mrx_tree *tree) {
     if (!tree->hostCoefsValid) mrx_tree_sync_host(tree);
     tree_drop_device(*tree);

@@ -120,6 +120,22 @@ template <typename T> static void read_back(T *dst, const T *devSrc, T *mbSlot, 
     }
 }
 
+// host mirror of an apply output (mrx_tree::hostMirror): copy-engine stream of the per-iteration downloads
+struct MirrorStream {
+    cudaStream_t dl = nullptr;
+    cudaEvent_t evReduced = nullptr, evCopied = nullptr;
+    bool pending = false; // copies enqueued since the last wait
+};
+static MirrorStream &mirror_stream() {
+    static MirrorStream m;
+    if (!m.dl) {
+        MRX_CUDA(cudaStreamCreateWithFlags(&m.dl, cudaStreamNonBlocking));
+        MRX_CUDA(cudaEventCreateWithFlags(&m.evReduced, cudaEventDisableTiming));
+        MRX_CUDA(cudaEventCreateWithFlags(&m.evCopied, cudaEventDisableTiming));
+    }
+    return m;
+}
+
 // final node count of the last apply of this process: the next apply reserves its node store for that many nodes up front
 static size_t &nodeStoreHint() {
     static size_t h = 0;
@@ -834,6 +850,9 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     const bool profile = getenv("MRX_PROFILE") != nullptr;
     const bool useMailbox = getenv("MRX_NO_MAILBOX") == nullptr;
     Mailbox *mb = mailbox();
+    // result streamed into the output tree's pinned host chunks while the loop runs (one GPU, convolution apply)
+    const bool mirror = out.hostMirror && derivDir < 0 && out.host.coefsPinned() && !getenv("MRX_NO_MIRROR_STREAM");
+    MirrorStream *ms_ = mirror ? &mirror_stream() : nullptr;
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -882,7 +901,38 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     struct {
         bool active = false;
         int buf = 0, nG = 0, rows = 0;
+        int slot0 = -1; // first slot of the iteration's (contiguous) nodes; -1: the first work vector (slots of the caller's grid)
     } pend;
+    // host mirror: wavelet blocks of the nodes of one iteration (final once the iteration is in the node store: the closing
+    // TopDown(+=) touches scaling blocks, BottomUp rewrites branch nodes only) as strided copies (7 K^3 of every 8 K^3 doubles)
+    // on the download stream, per 64-node host chunk; `after` = event on another stream the copies have to wait for
+    auto mirror_copy = [&](cudaEvent_t after, int slot0, int cnt, int storeNodes) {
+        out.host.ensureCoefStorageFor((size_t)storeNodes);
+        MRX_CUDA(cudaStreamWaitEvent(ms_->dl, after, 0));
+        auto copy_run = [&](int s0, int c) {
+            while (c > 0) {
+                const int inChunk = std::min(c, 64 - (s0 & 63));
+                MRX_CUDA(cudaMemcpy2DAsync(out.host.coef(s0) + out.host.Kd, (size_t)out.host.ncoef * sizeof(double),
+                                           out.dev.coefs.p + (size_t)s0 * out.host.ncoef + out.host.Kd, (size_t)out.host.ncoef * sizeof(double),
+                                           (size_t)7 * out.host.Kd * sizeof(double), (size_t)inChunk, cudaMemcpyDeviceToHost, ms_->dl));
+                s0 += inChunk;
+                c -= inChunk;
+            }
+        };
+        if (slot0 < 0) { // first work vector: runs of consecutive slots
+            size_t a = 0;
+            while (a < workVec.size()) {
+                size_t b2 = a + 1;
+                while (b2 < workVec.size() && workVec[b2] == workVec[b2 - 1] + 1) b2++;
+                copy_run(workVec[a], (int)(b2 - a));
+                a = b2;
+            }
+        } else {
+            copy_run(slot0, cnt);
+        }
+        MRX_CUDA(cudaEventRecord(ms_->evCopied, ms_->dl));
+        ms_->pending = true;
+    };
     bool unpackInFlight[kCommStageBufs] = {false, false, false};
     cudaStream_t ust = (world > 1) ? comm_unpack_stream(comm) : nullptr;
     auto wait_unpack = [&](int slot) { // main stream: the unpack that used ring slot `slot` has finished
@@ -901,6 +951,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                             world, pend.rows, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, ust);
         MRX_CUDA(cudaEventRecord(comm_ev_unpacked(comm, pend.buf), ust));
         unpackInFlight[pend.buf] = true;
+        if (mirror) mirror_copy(comm_ev_unpacked(comm, pend.buf), pend.slot0, pend.nG, out.dev.nNodes);
     };
     auto flush_pending = [&]() {
         if (pend.active) {
@@ -1202,6 +1253,10 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         // ---- device storage for the output nodes of this iteration (a growing store is copied: nothing may be writing it)
         if ((size_t)nRealDev * ncoef > out.dev.coefs.cap || (size_t)nRealDev * 8 > out.dev.norms.cap) {
             wait_all_unpacks();
+            if (mirror && ms_->pending) { // the download stream still reads the store that is about to be replaced
+                MRX_CUDA(cudaStreamWaitEvent(st, ms_->evCopied, 0));
+                ms_->pending = false;
+            }
             // room for the whole tree if an earlier apply of this process told how large it gets: no copy, no regrowth
             const size_t want = std::max<size_t>((size_t)nRealDev, std::min<size_t>(nodeStoreHint(), (size_t)64 * nRealDev + 4096));
             out.dev.coefs.reserve(want * ncoef, true, st);
@@ -1296,6 +1351,10 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         if (world == 1) {
             launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
             MRX_CUDA(cudaEventRecord(ev1, st));
+            if (mirror) {
+                MRX_CUDA(cudaEventRecord(ms_->evReduced, st));
+                mirror_copy(ms_->evReduced, iter == 0 ? -1 : nRealDev - nG, nG, nRealDev);
+            }
         } else {
             // ---- exchange over NVLink. Output blocks: the reduce kernel writes this rank's rows of a rank-major staging
             //      buffer; copy engines push them into every peer's HBM (CUDA IPC mapping) on a second stream while
@@ -1325,6 +1384,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                 pend.buf = b;
                 pend.nG = nG;
                 pend.rows = rowsPerRank;
+                pend.slot0 = (iter == 0) ? -1 : nRealDev - nG;
             } else {
                 comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
                 comm_allgather(comm, stageB, segBytes, st);
@@ -1510,6 +1570,32 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     oper.op.clearBandWidths();
     const bool prof = getenv("MRX_PROFILE") != nullptr;
     device_apply_post(out, (pipe && bareRoots) ? &branchPairs : nullptr);
+    if (pipe && out.hostMirror && out.host.coefsPinned() && !getenv("MRX_NO_MIRROR_STREAM")) {
+        // ---- host mirror: what the per-iteration copies could not take -- scaling blocks of every node, all blocks of the
+        //      branch nodes -- pushed by the SMs into the host chunks behind the streamed copies of the same nodes
+        cudaStream_t st = stream();
+        Tree<3> &g = out.host;
+        MirrorStream &M = mirror_stream();
+        g.ensureCoefStorageFor((size_t)g.nReal);
+        std::vector<int> items(g.nReal);
+        for (int n = 0; n < g.nReal; n++) items[n] = g.isBranch(n) ? (int)((unsigned)n | 0x80000000u) : n;
+        DevBuf<int> dItems;
+        dItems.reserve(std::max(g.nReal, 1), false, st);
+        const auto &chunks = g.coefChunks();
+        out.dev.chunkTab.reserve(std::max<size_t>(chunks.size(), 1), false, st);
+        MRX_CUDA(cudaMemcpyAsync(dItems.p, items.data(), sizeof(int) * g.nReal, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(out.dev.chunkTab.p, chunks.data(), sizeof(double *) * chunks.size(), cudaMemcpyHostToDevice, st));
+        if (M.pending) {
+            MRX_CUDA(cudaStreamWaitEvent(st, M.evCopied, 0));
+            M.pending = false;
+        }
+        launch_push_nodes(out.dev.coefs.p, const_cast<double *const *>(reinterpret_cast<const double *const *>(out.dev.chunkTab.p)), dItems.p,
+                          g.nReal, g.ncoef, st);
+        MRX_CUDA(cudaStreamSynchronize(st));
+        for (int n = 0; n < g.nReal; n++) g.nodes[n].flags |= FlagHasCoefs;
+        out.hostCoefsValid = true;
+        S.d2h_bytes = (long long)g.nReal * g.ncoef * (long long)sizeof(double);
+    }
     inp.host.deleteGenerated();
     inp.dev.nGen = 0;
     S.ms_post = now_ms() - tp;

@@ -17,6 +17,8 @@
 //   create   thread per flagged node: 8 generated children get slots, depth and norm bound; the (parent,
 //            child0) item list feeds transform_kernel<2> which fills their scaling coefficients.
 // resolve/create repeat until no entry is pending (one round per missing level).
+#include <algorithm>
+
 #include "../engine.hpp"
 #include "apply_kernels.cuh"
 #include "common.cuh"
@@ -324,7 +326,36 @@ __global__ void __launch_bounds__(256) fetch_nodes_kernel(double *__restrict__ c
     if (blockIdx.x == 0 && threadIdx.x == 0) *total += (unsigned long long)n; // blocks fetched
 }
 
+// host mirror of an apply output (mrx_tree_set_host_mirror): what the streamed per-iteration copies could not take yet -- the
+// scaling block of every node (final after the closing TopDown) and all blocks of the branch nodes (rewritten by BottomUp) --
+// written by the SMs straight into the pinned host chunks over PCIe
+__global__ void __launch_bounds__(256) push_nodes_kernel(const double *__restrict__ coefs, double *const *__restrict__ chunkTab,
+                                                         const int *__restrict__ items, int n, int ncoef) {
+    const int Kd = ncoef / 8;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int it = items[i];
+        const int slot = it & 0x7fffffff;
+        const int cnt = (it < 0) ? ncoef : Kd;
+        const double *src = coefs + (size_t)slot * ncoef;
+        double *dst = chunkTab[slot >> 6] + (size_t)(slot & 63) * ncoef;
+        if ((cnt & 1) == 0) {
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 *d2 = reinterpret_cast<double2 *>(dst);
+            for (int e = threadIdx.x; e < cnt / 2; e += 256) d2[e] = s2[e];
+        } else {
+            for (int e = threadIdx.x; e < cnt; e += 256) dst[e] = src[e];
+        }
+    }
+}
+
 } // namespace
+
+void launch_push_nodes(const double *coefs, double *const *chunkTab, const int *items, int n, int ncoef, cudaStream_t st) {
+    if (n <= 0) return;
+    push_nodes_kernel<<<std::min(n, 1184), 256, 0, st>>>(coefs, chunkTab, items, n, ncoef);
+    MRX_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
 
 void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *fetchList, int *fetchCnt, cudaStream_t st) {
     if (n <= 0) return;

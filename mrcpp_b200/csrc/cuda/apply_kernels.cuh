@@ -126,6 +126,9 @@ void launch_enum_create(const EnumParams &E, int nNew, int firstSlot, cudaStream
 /// lazy residency: flag the real nodes of `list` that are not in HBM yet and queue them; gather the queued nodes from the
 /// pinned host chunks (64 nodes each) into the node store; *total accumulates the number of nodes fetched
 void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *fetchList, int *fetchCnt, cudaStream_t st);
+/// host mirror of an apply output: blocks of the listed nodes from the node store straight into the pinned host chunks (64 nodes
+/// each). items[i] = slot, bit 31 set: all eight blocks (branch node), clear: the scaling block only
+void launch_push_nodes(const double *coefs, double *const *chunkTab, const int *items, int n, int ncoef, cudaStream_t st);
 void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *cnt, int ncoef, unsigned long long *total,
                         cudaStream_t st);
 

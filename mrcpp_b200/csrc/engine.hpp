@@ -91,6 +91,11 @@ struct mrx_tree {
     mrx::DeviceTree dev;
     bool hostCoefsValid = true; // host coefficient chunks hold the current values
     bool devValid = false;      // device copy holds the current values
+    // keep the host copy current: an apply writing this tree streams the result down while it runs (wavelet blocks of an
+    // iteration's nodes are final when the iteration is; copy engines move them beside the next iteration's kernels) and
+    // finishes the rest (scaling blocks, branch nodes) behind its closing passes, so that the tree is in host memory when the
+    // call returns (mrx_tree_set_host_mirror)
+    bool hostMirror = false;
     explicit mrx_tree(const mrx::MRA<3> &m)
             : host(m) {}
 };

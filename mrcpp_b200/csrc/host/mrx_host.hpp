@@ -204,6 +204,7 @@ public:
     void extendGridFrom(const Tree<D> &other); // build_grid(out, inp) (grid.cpp:144-153): union with the grid of `other`
     bool allocCoefs = true;       // false: new nodes get no host coefficient storage (device-resident)
     void ensureCoefStorage();     // allocate host storage for all nodes (before a download)
+    void ensureCoefStorageFor(size_t nSlots); // ... for the first nSlots slots, whether or not the topology holds them yet
     /// host coefficient chunks (64 nodes each) for device-side gathers; pinned (device-readable) unless the tree was
     /// created before a CUDA device was selected
     const std::vector<double *> &coefChunks() const { return chunks_; }

@@ -81,6 +81,11 @@ template <int D> void Tree<D>::ensureCoefStorage() {
     }
 }
 
+template <int D> void Tree<D>::ensureCoefStorageFor(size_t nSlots) {
+    size_t needChunks = (nSlots + chunkMask_) >> chunkShift_;
+    while (chunks_.size() < needChunks) chunks_.push_back(static_cast<double *>(alloc_((size_t)(chunkMask_ + 1) * ncoef * sizeof(double))));
+}
+
 template <int D>
 int Tree<D>::getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents, bool withCoefStorage) {
     int n = rootIndex(scale, l);

@@ -135,6 +135,7 @@ void apply(double prec, FunctionTree<3, double> &out, ConvolutionOperator<3> &op
     const double t1 = now();
     mrx_oper *P = to_oper(m, oper, inp.getMRA().getOrder(), oper.getBuildPrec());
     const double t2 = now();
+    mrx_tree_set_host_mirror(g, 1); // the result is wanted on the host: stream it down while the apply runs
     mrx_apply(prec, g, P, f, maxIter, absPrec ? 1 : 0, st);
     const int n = mrx_tree_n_nodes(g), nc = out.getNodeAllocator().getNCoefs();
     std::vector<int> scale(n), transl(3 * (size_t)n), parent(n), child0(n);

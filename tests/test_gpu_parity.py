@@ -485,3 +485,43 @@ def test_full_size_coulomb_energy(gpu):
     en = mw.dot(g1, f)
     assert abs(en - ana) / ana < 10 * prec
     assert f.getNNodes() > 40000 and s1.f_applied > 2e7  # really the full-size case
+
+
+@pytest.mark.parametrize("k,n,prec", [(7, 6, 1e-5), (5, 3, 1e-4), (9, 2, 1e-4)])
+def test_apply_with_host_mirror(gpu, k, n, prec):
+    """mrx_tree_set_host_mirror: the apply streams its result into the output tree's pinned host chunks while it runs (wavelet
+    blocks per refinement iteration on the copy engines, scaling blocks and branch nodes behind the closing passes). The host
+    copy must be bit-identical to a download after a plain apply -- on bare roots, on a pre-built grid (fixed-grid mode) and when
+    the same tree object is applied onto again -- and the block-granular lazy gather of a host-resident input must not change it."""
+    mw, orc = gpu
+    mra = world(mw, k)
+    func = gaussians(n, 77)
+    P = mw.PoissonOperator(mra, prec)
+    f = mw.FunctionTree(mra)
+    mw.project(prec, f, func, device=True)
+    ref = mw.FunctionTree(mra)
+    s0 = mw.apply(prec, ref, P, f)
+    R = ref.to_arrays()
+    g = mw.FunctionTree(mra)
+    g.set_host_mirror(True)
+    s1 = mw.apply(prec, g, P, f)
+    assert s1.d2h_bytes == g.nbytes() > 0 and s0.d2h_bytes == 0
+    G = g.to_arrays()  # no download left to do: the arrays come from the mirrored host chunks
+    assert np.array_equal(G["transl"], R["transl"]) and np.array_equal(G["coefs"], R["coefs"]) and np.array_equal(G["norms"], R["norms"])
+    # fixed-grid mode on a pre-built grid (arbitrary slots in the first work vector)
+    h0, h1 = mw.FunctionTree(mra), mw.FunctionTree(mra)
+    mw.copy_grid(h0, ref)
+    mw.copy_grid(h1, ref)
+    h1.set_host_mirror(True)
+    mw.apply(prec, h0, P, f, maxIter=0)
+    mw.apply(prec, h1, P, f, maxIter=0)
+    assert np.array_equal(h0.to_arrays()["coefs"], h1.to_arrays()["coefs"])
+    # host-resident input (block-granular gather) + mirrored output: the end-to-end path of bench.py
+    f.drop_device()
+    e = mw.FunctionTree(mra)
+    e.set_host_mirror(True)
+    s2 = mw.apply(prec, e, P, f)
+    assert 0 < s2.h2d_bytes < f.nbytes()
+    assert np.array_equal(e.to_arrays()["coefs"], R["coefs"])
+    # the mirrored tree is a valid input afterwards (host and device copies agree)
+    assert abs(mw.dot(e, e) - mw.dot(ref, ref)) <= 1e-13 * mw.dot(ref, ref)
