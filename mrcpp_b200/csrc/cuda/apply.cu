@@ -903,18 +903,20 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         int buf = 0, nG = 0, rows = 0;
         int slot0 = -1; // first slot of the iteration's (contiguous) nodes; -1: the first work vector (slots of the caller's grid)
     } pend;
-    // host mirror: wavelet blocks of the nodes of one iteration (final once the iteration is in the node store: the closing
-    // TopDown(+=) touches scaling blocks, BottomUp rewrites branch nodes only) as strided copies (7 K^3 of every 8 K^3 doubles)
-    // on the download stream, per 64-node host chunk; `after` = event on another stream the copies have to wait for
+    // host mirror: the nodes of one iteration, whose wavelet blocks are final once the iteration is in the node store (the closing
+    // TopDown(+=) touches scaling blocks, BottomUp rewrites branch nodes only), on the download stream, per 64-node host chunk;
+    // `after` = event on another stream the copies have to wait for
     auto mirror_copy = [&](cudaEvent_t after, int slot0, int cnt, int storeNodes) {
         out.host.ensureCoefStorageFor((size_t)storeNodes);
         MRX_CUDA(cudaStreamWaitEvent(ms_->dl, after, 0));
+        // whole nodes, contiguous per 64-node host chunk: one large DMA transfer each (strided 7-of-8-block copies cost a DMA
+        // descriptor per 28 KB row and ran at a third of the PCIe rate); the scaling block that travels with them is not final
+        // yet and is overwritten by the closing push
         auto copy_run = [&](int s0, int c) {
             while (c > 0) {
                 const int inChunk = std::min(c, 64 - (s0 & 63));
-                MRX_CUDA(cudaMemcpy2DAsync(out.host.coef(s0) + out.host.Kd, (size_t)out.host.ncoef * sizeof(double),
-                                           out.dev.coefs.p + (size_t)s0 * out.host.ncoef + out.host.Kd, (size_t)out.host.ncoef * sizeof(double),
-                                           (size_t)7 * out.host.Kd * sizeof(double), (size_t)inChunk, cudaMemcpyDeviceToHost, ms_->dl));
+                MRX_CUDA(cudaMemcpyAsync(out.host.coef(s0), out.dev.coefs.p + (size_t)s0 * out.host.ncoef,
+                                         (size_t)inChunk * out.host.ncoef * sizeof(double), cudaMemcpyDeviceToHost, ms_->dl));
                 s0 += inChunk;
                 c -= inChunk;
             }
@@ -1092,8 +1094,9 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     read_back(&res, scr.splitRes.p, &mb->res, &mb->flagRes, useMailbox, st);
 
     // host replay of the split decisions (deferred: runs while the device contracts the next iteration)
-    // split flags come down through a pinned arena with a truly asynchronous copy; the host reads them one iteration later,
-    // after it has seen a later mailbox flag (stream order: the copy has landed by then)
+    // split flags: split_kernel stores them straight into a pinned, mapped host arena (no copy-engine transfer in the loop: a small
+    // device-to-host copy would queue behind the megabytes a mirrored output streams down on the same DMA engine and stall the
+    // main stream); the host reads them one iteration later, after it has seen a later mailbox flag (the kernel has completed)
     struct Replay {
         size_t off;   // offset of the flags in the pinned arena
         int n;        // items of the iteration
@@ -1108,7 +1111,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         MRX_CUDA(cudaStreamSynchronize(st)); // copies into the old arena have landed; pending replays still read it: copy over
         size_t ncap = std::max<size_t>(need * 2, (size_t)1 << 20);
         unsigned char *np = nullptr;
-        MRX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&np), ncap, cudaHostAllocDefault));
+        MRX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&np), ncap, cudaHostAllocMapped | cudaHostAllocPortable));
         if (flagArena) {
             std::memcpy(np, flagArena, flagArenaUsed);
             MRX_CUDA(cudaFreeHost(flagArena));
@@ -1429,18 +1432,18 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         SP.state = scr.state.p;
         SP.gNodesNext = scr.gAll[cur ^ 1].p;
         SP.slotsNext = scr.gslotsAll[nb].p;
-        SP.flags = scr.flags.p;
+        // flags of this iteration: straight into the host arena (device pointer of the mapped allocation)
+        flag_arena_reserve(flagArenaUsed + (size_t)nG);
+        SP.flags = static_cast<unsigned char *>(mailbox_dev(flagArena)) + flagArenaUsed;
         SP.res = scr.splitRes.p;
         launch_split(SP, st);
         prep_local(cur ^ 1, nb, -1);
         Replay R;
-        flag_arena_reserve(flagArenaUsed + (size_t)nG);
         R.off = flagArenaUsed;
         R.n = nG;
         R.split = doSplit;
         R.slotBase = nRealDev;
         flagArenaUsed += (size_t)nG;
-        if (doSplit) MRX_CUDA(cudaMemcpyAsync(flagArena + R.off, scr.flags.p, nG, cudaMemcpyDeviceToHost, st));
         read_back(&res, scr.splitRes.p, &mb->res, &mb->flagRes, useMailbox, st);
         tp_wait += now_ms() - tq;
         tq = now_ms();
@@ -1585,6 +1588,15 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         out.dev.chunkTab.reserve(std::max<size_t>(chunks.size(), 1), false, st);
         MRX_CUDA(cudaMemcpyAsync(dItems.p, items.data(), sizeof(int) * g.nReal, cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaMemcpyAsync(out.dev.chunkTab.p, chunks.data(), sizeof(double *) * chunks.size(), cudaMemcpyHostToDevice, st));
+        double tm0 = now_ms();
+        if (prof) {
+            MRX_CUDA(cudaStreamSynchronize(st));
+            std::fprintf(stderr, "[mrx] mirror: closing passes drained after %.2f ms\n", now_ms() - tm0);
+            tm0 = now_ms();
+            MRX_CUDA(cudaStreamSynchronize(M.dl));
+            std::fprintf(stderr, "[mrx] mirror: streamed copies drained after another %.2f ms\n", now_ms() - tm0);
+            tm0 = now_ms();
+        }
         if (M.pending) {
             MRX_CUDA(cudaStreamWaitEvent(st, M.evCopied, 0));
             M.pending = false;
@@ -1592,6 +1604,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         launch_push_nodes(out.dev.coefs.p, const_cast<double *const *>(reinterpret_cast<const double *const *>(out.dev.chunkTab.p)), dItems.p,
                           g.nReal, g.ncoef, st);
         MRX_CUDA(cudaStreamSynchronize(st));
+        if (prof) std::fprintf(stderr, "[mrx] mirror: push of the remainder %.2f ms\n", now_ms() - tm0);
         for (int n = 0; n < g.nReal; n++) g.nodes[n].flags |= FlagHasCoefs;
         out.hostCoefsValid = true;
         S.d2h_bytes = (long long)g.nReal * g.ncoef * (long long)sizeof(double);

@@ -452,13 +452,213 @@ __global__ void __launch_bounds__(256) transformK_kernel(double *__restrict__ co
     }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The same kernel as a PERSISTENT CTA with the next node's blocks in flight while the current node is transformed: the staging
+// loads are cp.async (LDGSTS) copies into the second of two shared-memory buffers, committed before the three passes of the
+// current node start and waited for after they end. ncu of the one-node-per-CTA kernel (profiles/r02b_ncu_transform_kernels.txt)
+// showed neither roof near (K = 10: DMMA sub-pipe 38-45 %, DRAM 16-22 %, largest stall long scoreboard on the staging loads,
+// 2 CTAs per SM): load -> passes -> store were serial inside a CTA. Here the load of node i + 1 overlaps the passes of node i.
+// Used where two node buffers fit into shared memory (K <= 10); arithmetic and summation order are those of transformK_kernel.
+template <int K, int MODE, int NW>
+__global__ void __launch_bounds__(32 * NW) transformK_pipe_kernel(double *__restrict__ coefs, const double *__restrict__ realCoefs,
+                                                         double *__restrict__ genCoefs, double *__restrict__ genNorms, int nReal,
+                                                         const int *__restrict__ pairs, const double *__restrict__ filters, int overwrite,
+                                                         double *__restrict__ norms, int cnt) {
+    using L = TLayout<K>;
+    constexpr int K2 = L::K2, Kd = L::Kd, ncoef = 8 * Kd, S1 = L::S1, S2 = L::S2, SB = L::SB, MT = L::MT, KS = L::KS, NT = L::NT;
+    extern __shared__ __align__(16) double smAll[]; // two node buffers of 8 SB doubles
+    __shared__ double sN[NW][8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    // ---- filter fragments: A[row = (gbit, j)][kc = (b, t)] = F[2 gbit + b](t, j)
+    const double *F = filters + (size_t)((MODE == 1 || MODE == 3) ? 0 : 1) * 4 * K2;
+    double a[MT][KS];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int row = 8 * mt + r, kc = 4 * s + q;
+            a[mt][s] = (row < 2 * K) ? F[(2 * (row / K) + kc / K) * K2 + (kc % K) * K + row % K] : 0.0;
+        }
+    // ---- staging of one node into a buffer: 16-byte asynchronous copies into the padded layout
+    auto stage = [&](int item, double *buf) {
+        const int sp = pairs[2 * item], sc0 = pairs[2 * item + 1];
+        for (int e = tid; e < 4 * Kd; e += 32 * NW) {
+            const int blk = e / (Kd / 2), rem = 2 * (e - blk * (Kd / 2));
+            const int i0 = rem % K, i1 = (rem / K) % K, i2 = rem / K2;
+            double *dst = buf + SB * blk + i0 + S1 * i1 + S2 * i2;
+            const double *src = nullptr;
+            if (MODE == 0 || MODE == 3) {
+                src = coefs + (size_t)sp * ncoef + (size_t)blk * Kd + rem;
+            } else if (MODE == 1) {
+                src = coefs + (size_t)(sc0 + blk) * ncoef + rem;
+            } else {
+                if (sp < nReal) src = realCoefs + (size_t)sp * ncoef + (size_t)blk * Kd + rem;
+                else if (blk == 0) src = genCoefs + (size_t)(sp - nReal) * Kd + rem;
+            }
+            if (src) cp_async16(dst, src);
+            else *reinterpret_cast<double2 *>(dst) = make_double2(0.0, 0.0);
+        }
+    };
+    int item = blockIdx.x, nIt = 0;
+    if (item < cnt) stage(item, smAll);
+    cp_async_commit();
+    for (; item < cnt; item += gridDim.x, nIt++) {
+    double *smK = smAll + (size_t)(nIt & 1) * 8 * SB;
+    const int parent = pairs[2 * item];
+    const int child0 = pairs[2 * item + 1];
+    if (item + (int)gridDim.x < cnt) stage(item + gridDim.x, smAll + (size_t)((nIt + 1) & 1) * 8 * SB);
+    cp_async_commit();
+    cp_async_wait<1>(); // everything but the group just committed has landed: the current node is in its buffer
+    __syncthreads();
+    // ---- pass 0: contract i0 / block bit 0. Tile = (i1 pair, fixed i2) x (bit 1, bit 2); column c = bit1 + 2 bit2 + 4 e1
+    for (int tile = warp; tile < NT; tile += NW) {
+        const int pa = tile % (K / 2), i2 = tile / (K / 2);
+        const int cb = S1 * (2 * pa + (r >> 2)) + S2 * i2 + SB * (2 * (r & 1) + 4 * ((r >> 1) & 1));
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int kc = 4 * s + q;
+            bf[s] = smK[cb + kc % K + SB * (kc / K)];
+        }
+        // D columns 2q, 2q+1: bit1 = 0 / 1, bit2 = q & 1, e1 = q >> 1
+        const int ob = S1 * (2 * pa + (q >> 1)) + S2 * i2 + SB * (4 * (q & 1));
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; s++) dmma884(d0, d1, a[mt][s], bf[s]);
+            const int row = 8 * mt + r;
+            if (row < 2 * K) {
+                const int o = ob + row % K + SB * (row / K);
+                smK[o] = d0;
+                smK[o + 2 * SB] = d1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- pass 1: contract i1 / block bit 1. Tile = (i0 pair, fixed i2) x (bit 0, bit 2); column c = e0 + 2 bit0 + 4 bit2
+    for (int tile = warp; tile < NT; tile += NW) {
+        const int pa = tile % (K / 2), i2 = tile / (K / 2);
+        const int cb = 2 * pa + (r & 1) + S2 * i2 + SB * (((r >> 1) & 1) + 4 * (r >> 2));
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int kc = 4 * s + q;
+            bf[s] = smK[cb + S1 * (kc % K) + 2 * SB * (kc / K)];
+        }
+        const int ob = 2 * pa + S2 * i2 + SB * ((q & 1) + 4 * (q >> 1)); // columns 2q, 2q+1 = the i0 pair
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; s++) dmma884(d0, d1, a[mt][s], bf[s]);
+            const int row = 8 * mt + r;
+            if (row < 2 * K) *reinterpret_cast<double2 *>(smK + ob + S1 * (row % K) + 2 * SB * (row / K)) = make_double2(d0, d1);
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: contract i2 / block bit 2, results to global. Tile = (i0 pair, fixed i1) x (bit 0, bit 1)
+    double n2a = 0.0, n2b = 0.0; // square norm contributions to the blocks gt = q (gbit 0) and q + 4 (gbit 1)
+    for (int tile = warp; tile < NT; tile += NW) {
+        const int pa = tile % (K / 2), i1 = tile / (K / 2);
+        const int cb = 2 * pa + (r & 1) + S1 * i1 + SB * (((r >> 1) & 1) + 2 * (r >> 2));
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int kc = 4 * s + q;
+            bf[s] = smK[cb + S2 * (kc % K) + 4 * SB * (kc / K)];
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; s++) dmma884(d0, d1, a[mt][s], bf[s]);
+            const int row = 8 * mt + r;
+            if (row < 2 * K) {
+                const int gbit = row / K, j = row % K;
+                const int gt = q + 4 * gbit; // bit0 = q & 1, bit1 = q >> 1
+                const int elem = 2 * pa + K * i1 + K2 * j;
+                double *dst;
+                if (MODE == 0) dst = coefs + (size_t)(child0 + gt) * ncoef + elem;
+                else if (MODE == 2) dst = genCoefs + (size_t)(child0 - nReal + gt) * Kd + elem;
+                else dst = coefs + (size_t)parent * ncoef + (size_t)gt * Kd + elem;
+                if (MODE == 0 && !overwrite) {
+                    const double2 o = *reinterpret_cast<const double2 *>(dst);
+                    d0 += o.x;
+                    d1 += o.y;
+                }
+                *reinterpret_cast<double2 *>(dst) = make_double2(d0, d1);
+                const double c2 = fma(d1, d1, d0 * d0);
+                if (gbit) n2b += c2;
+                else n2a += c2;
+            }
+        }
+    }
+    // ---- norms of the eight blocks written (fixed reduction shape: deterministic)
+    if (norms != nullptr || MODE == 2) {
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            double v = g ? n2b : n2a;
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (r == 0) sN[warp][q + 4 * g] = v;
+        }
+        __syncthreads();
+        if (tid < 8) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) v += sN[w][tid];
+            const double nrm = sqrt(v);
+            if (MODE == 2) genNorms[child0 - nReal + tid] = nrm;
+            else if (MODE == 0) norms[(size_t)(child0 + tid) * 8] = nrm;
+            else norms[(size_t)parent * 8 + tid] = nrm;
+        }
+    }
+    if (MODE == 0 && overwrite) {
+        // giveChildrenCoefs(overwrite=true) zeroes the children first (MWNode.cpp:317-319)
+        for (int o = tid; o < 8 * 7 * Kd / 2; o += 32 * NW) {
+            const int c = o / (7 * Kd / 2), rem = o - c * (7 * Kd / 2);
+            reinterpret_cast<double2 *>(coefs + (size_t)(child0 + c) * ncoef + Kd)[rem] = make_double2(0.0, 0.0);
+        }
+    }
+    __syncthreads(); // this node's buffer is refilled by the staging of the node after next; sN is rewritten
+    } // nodes of this CTA
+}
+
 template <int K, int MODE>
 void launch_transformK(double *coefs, const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *pairs, int cnt,
                        const double *filters, int overwrite, double *norms, cudaStream_t st) {
+    // warps of the persistent variant: K = 6 has 18 column tiles per pass, dealt evenly to 9 warps; K = 10 measured faster with 8
+    // warps (7 rounds of tiles) than with 10 (5 exact rounds): 1.26 vs 1.32 ms per BottomUp pass on the C2 tree
+    constexpr int NW = (K == 6) ? 9 : 8;
     static bool conf = false;
+    static int pipeGrid = 0; // persistent, double-buffered variant where two node buffers fit (MRX_NO_TPIPE=1: one node per CTA)
     if (!conf) {
         MRX_CUDA(cudaFuncSetAttribute(transformK_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TLayout<K>::bytes));
+        if (2 * TLayout<K>::bytes <= 220 * 1024 && !getenv("MRX_NO_TPIPE")) {
+            int dev = 0, sms = 0, perSm = 0;
+            MRX_CUDA(cudaGetDevice(&dev));
+            MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            MRX_CUDA(cudaFuncSetAttribute(transformK_pipe_kernel<K, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TLayout<K>::bytes)));
+            MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, transformK_pipe_kernel<K, MODE, NW>, 32 * NW, 2 * TLayout<K>::bytes));
+            pipeGrid = sms * std::max(perSm, 1);
+        }
         conf = true;
+    }
+    // enough nodes per CTA for the prefetch to pay; TopDown(overwrite) at small K is dominated by zeroing the children's wavelet
+    // blocks, which a one-node CTA overlaps better with its neighbours on the SM
+    if (pipeGrid > 0 && cnt >= 2 * pipeGrid && !(MODE == 0 && overwrite && K < 10)) {
+        transformK_pipe_kernel<K, MODE, NW><<<pipeGrid, 32 * NW, 2 * TLayout<K>::bytes, st>>>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs,
+                                                                                            filters, overwrite, norms, cnt);
+        return;
     }
     transformK_kernel<K, MODE><<<cnt, 256, TLayout<K>::bytes, st>>>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, filters, overwrite, norms);
 }
