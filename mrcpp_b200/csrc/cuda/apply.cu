@@ -136,6 +136,26 @@ static MirrorStream &mirror_stream() {
     return m;
 }
 
+// closing TopDown(+=) folded into the refinement loop: the step parent level -> child level runs on a side stream as soon as the
+// children's own coefficients are in the node store (one GPU: after the reduce; sharded: after the unpack), beside the next
+// iteration's kernels, instead of level by level after the loop. Same kernel, same level order: bit-identical results.
+struct TopDownStream {
+    cudaStream_t td = nullptr;
+    cudaEvent_t evReady = nullptr, evDone = nullptr;
+    cudaEvent_t evBuf[3] = {nullptr, nullptr, nullptr}; // the step that read pair buffer x has finished
+    bool pending = false, bufBusy[3] = {false, false, false};
+};
+static TopDownStream &topdown_stream() {
+    static TopDownStream t;
+    if (!t.td) {
+        MRX_CUDA(cudaStreamCreateWithFlags(&t.td, cudaStreamNonBlocking));
+        MRX_CUDA(cudaEventCreateWithFlags(&t.evReady, cudaEventDisableTiming));
+        MRX_CUDA(cudaEventCreateWithFlags(&t.evDone, cudaEventDisableTiming));
+        for (int x = 0; x < 3; x++) MRX_CUDA(cudaEventCreateWithFlags(&t.evBuf[x], cudaEventDisableTiming));
+    }
+    return t;
+}
+
 // final node count of the last apply of this process: the next apply reserves its node store for that many nodes up front
 static size_t &nodeStoreHint() {
     static size_t h = 0;
@@ -180,6 +200,7 @@ struct Scratch {
     DevBuf<double> scaleFac, state;
     DevBuf<SplitResult> splitRes;
     // locally scaled precision (apply with precTrees, apply_prec.cu)
+    DevBuf<int> tdPairs[3];             // (parent, first child) of the nodes that split in an iteration: TopDown(+=) level lists
     DevBuf<double> precAll[2], precLoc; // factors of the whole work vector (current / next) and of this rank's share
     DevBuf<PrecTreeDev> precTreeTab;
     std::vector<std::unique_ptr<DevBuf<double>>> precVReal;
@@ -838,7 +859,7 @@ static void run_apply_legacy(double prec, mrx_tree &out, mrx_oper &oper, mrx_tre
 static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int maxIter, bool absPrec, int derivDir,
                            std::vector<int> workVec, mrx_apply_stats &S, mrx_comm *comm,
                            std::vector<std::vector<int>> *branchPairs = nullptr, const std::vector<mrx_tree *> *precTrees = nullptr,
-                           int unitCell = 0) {
+                           int unitCell = 0, bool *topDownFolded = nullptr) {
     cudaStream_t st = stream();
     const double tEnter = now_ms();
     Operator &op = oper.op;
@@ -853,6 +874,11 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     // result streamed into the output tree's pinned host chunks while the loop runs (one GPU, convolution apply)
     const bool mirror = out.hostMirror && derivDir < 0 && out.host.coefsPinned() && !getenv("MRX_NO_MIRROR_STREAM");
     MirrorStream *ms_ = mirror ? &mirror_stream() : nullptr;
+    // TopDown(+=) inside the loop: only when every branch node of the output comes from this apply's own splits (bare roots)
+    const bool fold = topDownFolded != nullptr && branchPairs != nullptr && derivDir < 0 && !getenv("MRX_NO_TDFOLD");
+    TopDownStream *td_ = fold ? &topdown_stream() : nullptr;
+    if (topDownFolded) *topDownFolded = fold;
+    int tdCount = 0, tdBuf = 0; // pairs of the step that becomes runnable when the CURRENT iteration's nodes are in the store
     Tree<3> &g = out.host;
     Tree<3> &f = inp.host;
     const int K = g.K, Kd = g.Kd, ncoef = g.ncoef;
@@ -902,6 +928,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         bool active = false;
         int buf = 0, nG = 0, rows = 0;
         int slot0 = -1; // first slot of the iteration's (contiguous) nodes; -1: the first work vector (slots of the caller's grid)
+        int tdCount = 0, tdBuf = 0; // TopDown(+=) step whose children are this iteration's nodes
     } pend;
     // host mirror: the nodes of one iteration, whose wavelet blocks are final once the iteration is in the node store (the closing
     // TopDown(+=) touches scaling blocks, BottomUp rewrites branch nodes only), on the download stream, per 64-node host chunk;
@@ -935,6 +962,19 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         MRX_CUDA(cudaEventRecord(ms_->evCopied, ms_->dl));
         ms_->pending = true;
     };
+    // TopDown(+=) step whose children are the nodes of the iteration that just reached the node store; `after` = the event that
+    // says so. The mirror copies of those nodes follow it on the download stream (their scaling blocks are final then).
+    auto topdown_step = [&](cudaEvent_t after, int cnt, int buf) {
+        if (cnt <= 0) return after;
+        MRX_CUDA(cudaStreamWaitEvent(td_->td, after, 0));
+        launch_transform(true, false, out.dev.coefs.p, scr.tdPairs[buf].p, cnt, K, filt, td_->td,
+                         transform_fuses_norms(K) ? out.dev.norms.p : nullptr);
+        MRX_CUDA(cudaEventRecord(td_->evDone, td_->td));
+        MRX_CUDA(cudaEventRecord(td_->evBuf[buf], td_->td));
+        td_->pending = true;
+        td_->bufBusy[buf] = true;
+        return td_->evDone;
+    };
     bool unpackInFlight[kCommStageBufs] = {false, false, false};
     cudaStream_t ust = (world > 1) ? comm_unpack_stream(comm) : nullptr;
     auto wait_unpack = [&](int slot) { // main stream: the unpack that used ring slot `slot` has finished
@@ -953,7 +993,9 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                             world, pend.rows, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, ust);
         MRX_CUDA(cudaEventRecord(comm_ev_unpacked(comm, pend.buf), ust));
         unpackInFlight[pend.buf] = true;
-        if (mirror) mirror_copy(comm_ev_unpacked(comm, pend.buf), pend.slot0, pend.nG, out.dev.nNodes);
+        cudaEvent_t ready = comm_ev_unpacked(comm, pend.buf);
+        if (fold) ready = topdown_step(ready, pend.tdCount, pend.tdBuf);
+        if (mirror) mirror_copy(ready, pend.slot0, pend.nG, out.dev.nNodes);
     };
     auto flush_pending = [&]() {
         if (pend.active) {
@@ -1256,6 +1298,10 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         // ---- device storage for the output nodes of this iteration (a growing store is copied: nothing may be writing it)
         if ((size_t)nRealDev * ncoef > out.dev.coefs.cap || (size_t)nRealDev * 8 > out.dev.norms.cap) {
             wait_all_unpacks();
+            if (fold && td_->pending) { // the TopDown stream still updates the store that is about to be replaced
+                MRX_CUDA(cudaStreamWaitEvent(st, td_->evDone, 0));
+                td_->pending = false;
+            }
             if (mirror && ms_->pending) { // the download stream still reads the store that is about to be replaced
                 MRX_CUDA(cudaStreamWaitEvent(st, ms_->evCopied, 0));
                 ms_->pending = false;
@@ -1354,9 +1400,11 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         if (world == 1) {
             launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
             MRX_CUDA(cudaEventRecord(ev1, st));
-            if (mirror) {
-                MRX_CUDA(cudaEventRecord(ms_->evReduced, st));
-                mirror_copy(ms_->evReduced, iter == 0 ? -1 : nRealDev - nG, nG, nRealDev);
+            if (fold || mirror) {
+                cudaEvent_t ready = fold ? td_->evReady : ms_->evReduced;
+                MRX_CUDA(cudaEventRecord(ready, st));
+                if (fold) ready = topdown_step(ready, tdCount, tdBuf);
+                if (mirror) mirror_copy(ready, iter == 0 ? -1 : nRealDev - nG, nG, nRealDev);
             }
         } else {
             // ---- exchange over NVLink. Output blocks: the reduce kernel writes this rank's rows of a rank-major staging
@@ -1388,11 +1436,19 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                 pend.nG = nG;
                 pend.rows = rowsPerRank;
                 pend.slot0 = (iter == 0) ? -1 : nRealDev - nG;
+                pend.tdCount = tdCount;
+                pend.tdBuf = tdBuf;
             } else {
                 comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
                 comm_allgather(comm, stageB, segBytes, st);
                 launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, normsBuf.p,
                                     out.dev.norms.p, st);
+                if (fold || mirror) { // this iteration's nodes are in the store: its TopDown step and mirror copies
+                    cudaEvent_t ready = fold ? td_->evReady : ms_->evReduced;
+                    MRX_CUDA(cudaEventRecord(ready, st));
+                    if (fold) ready = topdown_step(ready, tdCount, tdBuf);
+                    if (mirror) mirror_copy(ready, iter == 0 ? -1 : nRealDev - nG, nG, nRealDev);
+                }
             }
         }
         // ---- the device is busy for a while: replay earlier split decisions into the host topology, build the band
@@ -1432,6 +1488,16 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         SP.state = scr.state.p;
         SP.gNodesNext = scr.gAll[cur ^ 1].p;
         SP.slotsNext = scr.gslotsAll[nb].p;
+        if (fold) { // (parent, first child) pairs of the nodes that split now: the TopDown step of the NEXT iteration's nodes
+            const int x = (iter + 1) % 3;
+            if (td_->bufBusy[x]) { // the step that read this buffer three iterations ago (long finished; the wait is free)
+                MRX_CUDA(cudaStreamWaitEvent(st, td_->evBuf[x], 0));
+                td_->bufBusy[x] = false;
+            }
+            scr.tdPairs[x].reserve((size_t)2 * std::max(nG, 1), false, st);
+            SP.slotsCur = scr.gslotsAll[b].p;
+            SP.pairsNext = scr.tdPairs[x].p;
+        }
         // flags of this iteration: straight into the host arena (device pointer of the mapped allocation)
         flag_arena_reserve(flagArenaUsed + (size_t)nG);
         SP.flags = static_cast<unsigned char *>(mailbox_dev(flagArena)) + flagArenaUsed;
@@ -1459,6 +1525,8 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                          nG, nNbr, nCand, hdr.totalTuples, ms, msc,
                          msc > 0 ? hdr.totalTuples * 6.0 * K * K * K * K / (msc * 1e-3) / 1e12 : 0.0, res.nSplit);
         S.g_nodes += nG;
+        tdCount = res.nSplit; // pairs written by this iteration's split: runnable when the next iteration's nodes exist
+        tdBuf = (iter + 1) % 3;
         g.squareNorm = res.squareNorm; // TreeBuilder.cpp:56-66
         nRealDev += res.nNext;
         nG = res.nNext;
@@ -1469,6 +1537,12 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         tp_split += now_ms() - tq;
     }
     if (world > 1) flush_pending();
+    if (fold && td_->pending) { // the closing BottomUp (main stream) reads what the TopDown stream wrote
+        MRX_CUDA(cudaStreamWaitEvent(st, td_->evDone, 0));
+        td_->pending = false;
+    }
+    if (fold)
+        for (int x = 0; x < 3; x++) td_->bufBusy[x] = false;
     MRX_CUDA(cudaStreamSynchronize(st)); // the last iteration's flags have landed; events are complete
     replay_pending();
     if (g.nReal != nRealDev) MRX_ABORT("apply: host topology and device node store disagree");
@@ -1561,7 +1635,8 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     std::vector<std::vector<int>> branchPairs;
     const bool bareRoots = out.host.nReal == out.host.nRoots;
     const bool pipe = use_pipeline(out);
-    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr, precTrees, unitCell);
+    bool tdFolded = false;
+    if (pipe) run_apply_pipe(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S, const_cast<mrx_comm *>(comm), bareRoots ? &branchPairs : nullptr, precTrees, unitCell, &tdFolded);
     else {
         if (comm_world(comm) > 1) MRX_ABORT("sharded apply is implemented for the work-list pipeline (orders 3..11) only");
         run_apply_legacy(prec, out, oper, inp, maxIter, absPrec, -1, workVec, S);
@@ -1572,7 +1647,7 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
     double tp = now_ms();
     oper.op.clearBandWidths();
     const bool prof = getenv("MRX_PROFILE") != nullptr;
-    device_apply_post(out, (pipe && bareRoots) ? &branchPairs : nullptr);
+    device_apply_post(out, (pipe && bareRoots) ? &branchPairs : nullptr, pipe && bareRoots && tdFolded);
     if (pipe && out.hostMirror && out.host.coefsPinned() && !getenv("MRX_NO_MIRROR_STREAM")) {
         // ---- host mirror: what the per-iteration copies could not take -- scaling blocks of every node, all blocks of the
         //      branch nodes -- pushed by the SMs into the host chunks behind the streamed copies of the same nodes

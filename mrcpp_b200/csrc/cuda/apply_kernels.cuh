@@ -204,6 +204,9 @@ struct SplitParams {
     double *state;                  // [3] sNorm, wNorm, squareNorm carried across iterations
     int4 *gNodesNext;               // [8 nSplit] next work vector
     int *slotsNext;
+    const int *slotsCur;            // [nG] slots of this iteration's items (for the pair list) or nullptr
+    int *pairsNext;                 // [2 nSplit] (parent slot, first child slot) of the nodes that split: the level list of the
+                                    // closing TopDown(+=) step parent -> children, run as soon as the children exist (or nullptr)
     unsigned char *flags;           // [nG] split decisions (host replays them into its topology)
     SplitResult *res;
 };

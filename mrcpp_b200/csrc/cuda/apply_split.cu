@@ -141,6 +141,10 @@ __global__ void __launch_bounds__(1024) split_kernel(SplitParams S) {
             int total;
             const int pos = run + cta_excl_scan_int(flag, sm, total);
             if (flag) {
+                if (S.pairsNext) {
+                    S.pairsNext[2 * pos] = S.slotsCur[i];
+                    S.pairsNext[2 * pos + 1] = S.slotBase + 8 * pos;
+                }
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int q = 8 * pos + c;

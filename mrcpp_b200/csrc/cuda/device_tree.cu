@@ -174,7 +174,7 @@ static double *pinned_scratch(size_t doubles) {
     return buf;
 }
 
-void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth) {
+void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth, bool topDownDone) {
     require_device("device_apply_post");
     Tree<3> &h = t.host;
     cudaStream_t st = stream();
@@ -201,10 +201,11 @@ void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsBy
         MRX_CUDA(cudaMemcpyAsync(pairs.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
         const double *filt = device_filters(h.k);
         double *nrm = fused ? t.dev.norms.p : nullptr;
-        for (int d = 0; d < nLevels; d++) {
-            const int cnt = levelOff[d + 1] - levelOff[d];
-            if (cnt > 0) launch_transform(true, false, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st, nrm);
-        }
+        if (!topDownDone)
+            for (int d = 0; d < nLevels; d++) {
+                const int cnt = levelOff[d + 1] - levelOff[d];
+                if (cnt > 0) launch_transform(true, false, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st, nrm);
+            }
         for (int d = nLevels - 1; d >= 0; d--) {
             const int cnt = levelOff[d + 1] - levelOff[d];
             if (cnt > 0) launch_transform(false, true, t.dev.coefs.p, pairs.p + 2 * (size_t)levelOff[d], cnt, h.K, filt, st, nrm);

@@ -275,6 +275,12 @@ __global__ void __launch_bounds__(128) transform8_kernel(double *__restrict__ co
     }
 }
 
+// Tried and dropped (round 2, profiles/r02o_transform8_persistent_variant.txt): a PERSISTENT variant with its own 32 KB staging
+// buffer next to the tiles and the next node's bulk copy issued as soon as the source fragments are in registers. It needs 77 KB
+// of shared memory and 164 registers (the fragment tables stay live across the node loop), i.e. 2 CTAs = 8 warps per SM instead
+// of 5 x 4, and ran SLOWER: BottomUp 0.708 vs 0.648 ms per pass on the 256 K-node C2 tree, TopDown(+=) 1.09 vs 1.00 ms on the
+// bench tree. With five resident CTAs the hardware already overlaps the load of one node with the passes of another.
+
 // ------------------------------------------------------------------------------------------------
 // Even orders K = 4, 6, 8, 10, 12: two-scale transform on the FP64 tensor cores, one CTA (8 warps) per node.
 // A pass contracts dimension p together with bit p of the block index: with the 2K x 2K two-scale matrix

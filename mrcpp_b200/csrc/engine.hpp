@@ -124,7 +124,8 @@ void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = tru
                          int *branchNodes = nullptr);
 /// TopDown(+=), BottomUp, norms, square norm: the closing passes of mrcpp::apply. pairsByDepth (optional): (parent, child0)
 /// pairs per depth of ALL branch nodes, if the caller already has them
-void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth = nullptr);
+/// topDownDone: the TopDown(+=) steps were already run level by level inside the apply loop (apply.cu): BottomUp + norms only
+void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth = nullptr, bool topDownDone = false);
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
 /// MWNode::mwTransform (what = 0: kind 0 Compression, 1 Reconstruction) / MWNode::cvTransform (what = 1: kind 0 Forward, 1 Backward)
 /// of the listed nodes (n < 0: every node) in place
