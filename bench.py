@@ -388,10 +388,17 @@ def main():
         sts = []
         for ft in trees:
             out = mw.FunctionTree(mra)
-            if e2e and (comm is None or rank == 0):
+            shared = False
+            if e2e and comm is not None and shared_arena[0]:
+                # sharded apply: the result lands in host memory all ranks have mapped, every rank downloading its share of the
+                # chunks over its own PCIe link while the apply runs; the call returns with the whole tree there
+                shared = out.set_host_mirror(True, comm=comm)
+            elif e2e and (comm is None or rank == 0):
                 out.set_host_mirror(True)  # the apply streams the result into host memory while it runs and returns with it there
             st = mw.apply(prec, out, oper, ft, comm=comm)
-            if e2e and (rank == 0 or by_tree):
+            if e2e and shared:
+                step_d2h += st.d2h_bytes  # this rank's share (summed over ranks below)
+            elif e2e and (rank == 0 or by_tree):
                 out.sync_host()  # result back in host memory (sharded apply: every rank holds the identical tree, rank 0 reads it back)
                 step_d2h += out.nbytes()
             step_h2d += st.h2d_bytes  # counted by the library: coefficient blocks gathered from host memory + norms + topology
@@ -446,6 +453,11 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         if float(flag[0]) > 0 and not e2e_skip:
             e2e_skip = "skipped on another rank"
+    shared_arena = [False]
+    if not e2e_skip and comm is not None and not os.environ.get("MRX_BENCH_NO_SHARED_MIRROR"):
+        # host arena for the result of one apply (+ slack), mapped by every rank: N PCIe links carry the download instead of one
+        out_bytes = max(st.n_nodes_out for st in A.last) * 8 * 8 * (args.order + 1) ** 3
+        shared_arena[0] = comm.host_arena(int(out_bytes * 1.05) + (64 << 20))
     if not e2e_skip:
         one_step(True)
         barrier()
@@ -500,7 +512,10 @@ def main():
                          "kernel_share_of_step": A.contract_ms / A.ms, "all_apply_kernels_share_of_step": A.kern_ms / A.ms},
             "clocks": clocks,
             "e2e": ({"value": e2e_nodes / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d),
-                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps} if not e2e_skip else None),
+                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
+                     "result_download": ("every rank its chunks, into one host arena mapped by all ranks" if shared_arena[0]
+                                         else "rank 0" if world > 1 and not by_tree else "the rank that ran the apply")}
+                    if not e2e_skip else None),
             "e2e_skipped": e2e_skip,
             "gpu_launches": int(launches),
             "detail": {"applies_per_step_this_rank": napply, "output_nodes_per_step": nodes // args.steps,

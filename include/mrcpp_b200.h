@@ -193,6 +193,11 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
  * every rank calls mrx_comm_create. */
 int mrx_comm_unique_id(char *id128);
 mrx_comm *mrx_comm_create(int rank, int world, const char *id128);
+/* Collective, ranks of ONE node: a host arena of `bytes` that every rank maps and registers with CUDA (one anonymous
+ * shared-memory file), so that every GPU can write result nodes into the same host pages over its own PCIe link
+ * (mrx_tree_set_shared_host_mirror). Returns 0 when all ranks have it, 1 when shared mapping is not possible here (the
+ * host mirror of a sharded apply then stays on the calling rank's own link). */
+int mrx_comm_host_arena(mrx_comm *comm, long long bytes);
 void mrx_comm_destroy(mrx_comm *comm);
 int mrx_comm_rank(const mrx_comm *comm);
 int mrx_comm_size(const mrx_comm *comm);
@@ -278,8 +283,15 @@ int mrx_tree_sync_device(mrx_tree *tree); /* upload if the host copy is newer   
 int mrx_tree_sync_host(mrx_tree *tree);   /* download if the device copy is newer                    */
 /* keep the host copy of an apply OUTPUT current: mrx_apply then streams the result into the tree's pinned host chunks while it
  * runs (copy engines, beside the next refinement iteration's kernels) and returns with the tree in host memory, so that a
- * binding that reads coefficients on the host pays a fraction of the final download (one GPU; ignored by the sharded apply) */
+ * binding that reads coefficients on the host pays a fraction of the final download. In a sharded apply a rank with this
+ * flag downloads the whole (replicated) result over its own link. */
 int mrx_tree_set_host_mirror(mrx_tree *tree, int on);
+/* Sharded apply, collective by convention (every rank calls it on its output tree before mrx_apply_sharded): the tree's
+ * host chunks move into the communicator's shared host arena, every rank downloads the chunks it owns (chunk index modulo
+ * world size) while the apply runs, and the call returns on every rank with the complete tree in that (shared) host
+ * memory: N PCIe links carry the result instead of one. Returns 1 (and behaves like mrx_tree_set_host_mirror(tree, 1))
+ * when the communicator has no arena. The tree must not outlive the communicator. */
+int mrx_tree_set_shared_host_mirror(mrx_tree *tree, mrx_comm *comm);
 int mrx_tree_drop_device(mrx_tree *tree); /* free the HBM copy (next use uploads again)              */
 long long mrx_tree_bytes(const mrx_tree *tree);
 

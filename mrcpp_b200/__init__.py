@@ -194,9 +194,15 @@ class FunctionTree:
     def sync_host(self):
         _lib.load().mrx_tree_sync_host(self._h)
 
-    def set_host_mirror(self, on=True):
-        """keep the host copy of this tree current when an apply writes it (result streamed down while the apply runs)"""
+    def set_host_mirror(self, on=True, comm=None):
+        """keep the host copy of this tree current when an apply writes it (result streamed down while the apply runs).
+        With `comm` (every rank calls it; `comm.host_arena(nbytes)` first): the host chunks move into the ranks' shared host
+        arena and every rank downloads its share over its own PCIe link. Returns True when the shared path is in use."""
+        if comm is not None and on:
+            self._mirror_comm = comm  # the arena must outlive the tree
+            return _lib.load().mrx_tree_set_shared_host_mirror(self._h, comm._h) == 0
         _lib.load().mrx_tree_set_host_mirror(self._h, 1 if on else 0)
+        return False
 
     def drop_device(self):
         _lib.load().mrx_tree_drop_device(self._h)
@@ -409,6 +415,11 @@ class Comm:
         ident = bcast(bytes(buf.raw))
         self._h = L.mrx_comm_create(int(rank), int(world), C.create_string_buffer(ident, 128))
         self.rank, self.world = rank, world
+
+    def host_arena(self, nbytes):
+        """collective: host memory of `nbytes` mapped by all ranks of the node and registered with CUDA in each
+        (mrx_comm_host_arena); True when every rank has it"""
+        return _lib.load().mrx_comm_host_arena(self._h, int(nbytes)) == 0
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -118,6 +118,8 @@ SIGNATURES = {
     "mrx_tree_sync_device": (_I, [_P]),
     "mrx_tree_sync_host": (_I, [_P]),
     "mrx_tree_set_host_mirror": (_I, [_P, _I]),
+    "mrx_tree_set_shared_host_mirror": (_I, [_P, _P]),
+    "mrx_comm_host_arena": (_I, [_P, C.c_longlong]),
     "mrx_tree_drop_device": (_I, [_P]),
     "mrx_tree_bytes": (C.c_longlong, [_P]),
     "mrx_tree_host_handle": (_P, [_P]),

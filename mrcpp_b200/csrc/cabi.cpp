@@ -320,6 +320,16 @@ int mrx_tree_evalf(mrx_tree *tree, int n_points, const double *r, double *values
     const double unit = std::pow(2.0, -h.mra.rootScale);
     for (int p = 0; p < n_points; p++) {
         const double *x = r + 3 * (size_t)p;
+        double xw[3];
+        if (h.mra.periodic) { // periodic::coord_manipulation (periodic_utils.cpp:75-85): the point mapped into the unit cell
+            for (int d = 0; d < 3; d++) {
+                const double lo = h.mra.lower(d), len = h.mra.upper(d) - h.mra.lower(d);
+                double t = std::fmod(x[d] - lo, len);
+                if (t < 0.0) t += len;
+                xw[d] = lo + t;
+            }
+            x = xw;
+        }
         // outside the world the function is zero (FunctionTree.cpp:386); root box as BoundingBox::getBoxIndex(Coord)
         int n = 0, cells = 1;
         bool outside = false;
@@ -1037,6 +1047,15 @@ int mrx_tree_sync_host(mrx_tree *tree) {
 }
 int mrx_tree_set_host_mirror(mrx_tree *tree, int on) {
     tree->hostMirror = on != 0;
+    return 0;
+}
+int mrx_tree_set_shared_host_mirror(mrx_tree *tree, mrx_comm *comm) {
+    tree->hostMirror = true;
+    if (!comm_has_host_arena(comm)) return 1;
+    if (tree->mirrorComm == comm) return 0;
+    if (!tree->hostCoefsValid) mrx_tree_sync_host(tree);
+    tree->host.rebaseChunks(host_arena_alloc, host_arena_free);
+    tree->mirrorComm = comm;
     return 0;
 }
 int mrx_tree_drop_device(mrx_tree *tree) {

@@ -874,6 +874,8 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     // result streamed into the output tree's pinned host chunks while the loop runs (one GPU, convolution apply)
     const bool mirror = out.hostMirror && derivDir < 0 && out.host.coefsPinned() && !getenv("MRX_NO_MIRROR_STREAM");
     MirrorStream *ms_ = mirror ? &mirror_stream() : nullptr;
+    // shared mirror (mrx_tree_set_shared_host_mirror): host chunk c is downloaded by rank c % world over that rank's PCIe link
+    const int shareW = (mirror && out.mirrorComm && out.mirrorComm == comm) ? world : 1, shareR = rank;
     // TopDown(+=) inside the loop: only when every branch node of the output comes from this apply's own splits (bare roots)
     const bool fold = topDownFolded != nullptr && branchPairs != nullptr && derivDir < 0 && !getenv("MRX_NO_TDFOLD");
     TopDownStream *td_ = fold ? &topdown_stream() : nullptr;
@@ -942,8 +944,9 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         auto copy_run = [&](int s0, int c) {
             while (c > 0) {
                 const int inChunk = std::min(c, 64 - (s0 & 63));
-                MRX_CUDA(cudaMemcpyAsync(out.host.coef(s0), out.dev.coefs.p + (size_t)s0 * out.host.ncoef,
-                                         (size_t)inChunk * out.host.ncoef * sizeof(double), cudaMemcpyDeviceToHost, ms_->dl));
+                if (shareW == 1 || (s0 >> 6) % shareW == shareR)
+                    MRX_CUDA(cudaMemcpyAsync(out.host.coef(s0), out.dev.coefs.p + (size_t)s0 * out.host.ncoef,
+                                             (size_t)inChunk * out.host.ncoef * sizeof(double), cudaMemcpyDeviceToHost, ms_->dl));
                 s0 += inChunk;
                 c -= inChunk;
             }
@@ -1655,13 +1658,18 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         Tree<3> &g = out.host;
         MirrorStream &M = mirror_stream();
         g.ensureCoefStorageFor((size_t)g.nReal);
-        std::vector<int> items(g.nReal);
-        for (int n = 0; n < g.nReal; n++) items[n] = g.isBranch(n) ? (int)((unsigned)n | 0x80000000u) : n;
+        // shared mirror: every rank finishes the chunks it owns; a barrier at the end makes the whole tree visible to all
+        const int shareW = (out.mirrorComm && out.mirrorComm == comm) ? comm_world(comm) : 1, shareR = comm_rank(comm);
+        std::vector<int> items;
+        items.reserve(g.nReal / shareW + 64);
+        for (int n = 0; n < g.nReal; n++)
+            if (shareW == 1 || (n >> 6) % shareW == shareR) items.push_back(g.isBranch(n) ? (int)((unsigned)n | 0x80000000u) : n);
+        const int nItems = (int)items.size();
         DevBuf<int> dItems;
-        dItems.reserve(std::max(g.nReal, 1), false, st);
+        dItems.reserve(std::max(nItems, 1), false, st);
         const auto &chunks = g.coefChunks();
         out.dev.chunkTab.reserve(std::max<size_t>(chunks.size(), 1), false, st);
-        MRX_CUDA(cudaMemcpyAsync(dItems.p, items.data(), sizeof(int) * g.nReal, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(dItems.p, items.data(), sizeof(int) * nItems, cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaMemcpyAsync(out.dev.chunkTab.p, chunks.data(), sizeof(double *) * chunks.size(), cudaMemcpyHostToDevice, st));
         double tm0 = now_ms();
         if (prof) {
@@ -1677,12 +1685,18 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
             M.pending = false;
         }
         launch_push_nodes(out.dev.coefs.p, const_cast<double *const *>(reinterpret_cast<const double *const *>(out.dev.chunkTab.p)), dItems.p,
-                          g.nReal, g.ncoef, st);
+                          nItems, g.ncoef, st);
+        if (shareW > 1) { // the peers' pushes into the shared arena are ordered before this rank's return
+            DevBuf<double> bar;
+            bar.reserve(1, false, st);
+            MRX_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(double), st));
+            comm_allreduce_sum(comm, bar.p, 1, st);
+        }
         MRX_CUDA(cudaStreamSynchronize(st));
         if (prof) std::fprintf(stderr, "[mrx] mirror: push of the remainder %.2f ms\n", now_ms() - tm0);
         for (int n = 0; n < g.nReal; n++) g.nodes[n].flags |= FlagHasCoefs;
         out.hostCoefsValid = true;
-        S.d2h_bytes = (long long)g.nReal * g.ncoef * (long long)sizeof(double);
+        S.d2h_bytes = (long long)nItems * g.ncoef * (long long)sizeof(double); // what THIS rank's link carried
     }
     inp.host.deleteGenerated();
     inp.dev.nGen = 0;

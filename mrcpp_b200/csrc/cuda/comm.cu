@@ -3,8 +3,12 @@
 // NVLink. NCCL is loaded at run time (dlopen of libnccl.so.2: the copy the host framework already loaded,
 // else the system one), so the library has no link-time dependency and single-GPU users never touch it.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -99,6 +103,7 @@ struct mrx_comm {
     cudaEvent_t evGathered = nullptr, evUnpacked[kStageBufs] = {nullptr, nullptr, nullptr};
     cudaEvent_t evReduced[kStageBufs] = {nullptr, nullptr, nullptr}, evPushed[kStageBufs] = {nullptr, nullptr, nullptr};
     char *ipcScratch = nullptr; // device buffer for the handle all-gather
+    bool hostArena = false;     // this communicator's ranks share the process-wide host arena (mrx_comm_host_arena)
 };
 
 namespace mrx {
@@ -235,6 +240,107 @@ void comm_allreduce_sum(const mrx_comm *c, double *buf, size_t n, cudaStream_t s
     check(api().AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce");
 }
 
+// ---- host arena shared by the ranks of one node -------------------------------------------------------------------------
+// One anonymous shared-memory file (memfd: not bounded by the size of /dev/shm), created by rank 0 and mapped by every
+// rank through /proc/<pid>/fd/<fd>, then registered with CUDA in every process: each GPU can DMA into the SAME host pages
+// over its own PCIe link. Host chunks of an output tree with a shared mirror are carved from it in allocation order, which
+// is the same on every rank (SPMD), so chunk i of the tree has the same offset everywhere.
+namespace {
+struct HostArena {
+    char *base = nullptr;
+    size_t bytes = 0, used = 0;
+    int live = 0, fd = -1;
+} g_arena;
+} // namespace
+
+void *host_arena_alloc(size_t bytes) {
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    if (!g_arena.base || g_arena.used + bytes > g_arena.bytes)
+        MRX_ABORT("shared host arena exhausted (mrx_comm_host_arena: ask for more bytes)");
+    void *p = g_arena.base + g_arena.used;
+    g_arena.used += bytes;
+    g_arena.live++;
+    return p;
+}
+void host_arena_free(void *) {
+    if (--g_arena.live == 0) g_arena.used = 0; // bump allocator: space comes back when the last chunk is gone
+}
+bool comm_has_host_arena(const mrx_comm *c) { return c && c->hostArena && g_arena.base; }
+
+int comm_host_arena(mrx_comm *c, size_t bytes) {
+    NcclApi &a = api();
+    cudaStream_t st = stream();
+    bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    if (g_arena.base) {
+        if (g_arena.bytes >= bytes || g_arena.live > 0) {
+            c->hostArena = g_arena.bytes >= bytes;
+            return c->hostArena ? 0 : 1;
+        }
+        cudaHostUnregister(g_arena.base);
+        munmap(g_arena.base, g_arena.bytes);
+        if (g_arena.fd >= 0) close(g_arena.fd);
+        g_arena = HostArena{};
+    }
+    if (!c->ipcScratch) MRX_CUDA(cudaMalloc(&c->ipcScratch, (size_t)c->world * sizeof(cudaIpcMemHandle_t) + 64));
+    long long info[2] = {0, -1};
+    int ok = 1;
+    if (c->rank == 0) {
+        g_arena.fd = memfd_create("mrx_host_arena", 0);
+        if (g_arena.fd < 0 || ftruncate(g_arena.fd, (off_t)bytes) != 0) ok = 0;
+        info[0] = (long long)getpid();
+        info[1] = ok ? g_arena.fd : -1;
+    }
+    long long *dinfo = reinterpret_cast<long long *>(c->ipcScratch);
+    if (c->rank == 0) MRX_CUDA(cudaMemcpyAsync(dinfo, info, sizeof(info), cudaMemcpyHostToDevice, st));
+    check(a.Broadcast(dinfo, dinfo, sizeof(info), kNcclInt8, 0, c->comm, st), "ncclBroadcast(arena)");
+    MRX_CUDA(cudaMemcpyAsync(info, dinfo, sizeof(info), cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    if (info[1] < 0) ok = 0;
+    if (ok && c->rank != 0) {
+        char path[64];
+        std::snprintf(path, sizeof(path), "/proc/%lld/fd/%lld", info[0], info[1]);
+        g_arena.fd = open(path, O_RDWR);
+        if (g_arena.fd < 0) ok = 0;
+    }
+    void *p = MAP_FAILED;
+    if (ok) {
+        p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, g_arena.fd, 0);
+        if (p == MAP_FAILED) ok = 0;
+    }
+    if (ok) {
+        int dev = 0, same = 0;
+        MRX_CUDA(cudaGetDevice(&dev));
+        cudaDeviceGetAttribute(&same, cudaDevAttrCanUseHostPointerForRegisteredMem, dev);
+        if (!same || cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+            cudaGetLastError();
+            munmap(p, bytes);
+            ok = 0;
+        }
+    }
+    // all ranks or none
+    double flag = ok ? 1.0 : 0.0;
+    double *dflag = reinterpret_cast<double *>(c->ipcScratch + 32);
+    MRX_CUDA(cudaMemcpyAsync(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+    check(a.AllReduce(dflag, dflag, 1, kNcclFloat64, kNcclSum, c->comm, st), "ncclAllReduce(arena ok)");
+    MRX_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, st));
+    MRX_CUDA(cudaStreamSynchronize(st));
+    const bool all = flag > c->world - 0.5;
+    if (ok && !all) {
+        cudaHostUnregister(p);
+        munmap(p, bytes);
+    }
+    if (!all) {
+        if (g_arena.fd >= 0) close(g_arena.fd);
+        g_arena = HostArena{};
+        if (c->rank == 0) std::fprintf(stderr, "[mrx] shared host arena unavailable: the host mirror of a sharded apply stays on rank 0's PCIe link\n");
+        return 1;
+    }
+    g_arena.base = static_cast<char *>(p);
+    g_arena.bytes = bytes;
+    c->hostArena = true;
+    return 0;
+}
+
 } // namespace mrx
 
 extern "C" {
@@ -282,6 +388,11 @@ void mrx_comm_destroy(mrx_comm *c) {
     delete c;
 }
 
+int mrx_comm_host_arena(mrx_comm *c, long long bytes) {
+    mrx::require_device("mrx_comm_host_arena");
+    if (!c || c->world < 2 || bytes <= 0) return 1;
+    return mrx::comm_host_arena(c, (size_t)bytes);
+}
 int mrx_comm_rank(const mrx_comm *c) { return mrx::comm_rank(c); }
 int mrx_comm_size(const mrx_comm *c) { return mrx::comm_world(c); }
 

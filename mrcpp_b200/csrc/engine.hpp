@@ -96,6 +96,10 @@ struct mrx_tree {
     // finishes the rest (scaling blocks, branch nodes) behind its closing passes, so that the tree is in host memory when the
     // call returns (mrx_tree_set_host_mirror)
     bool hostMirror = false;
+    // sharded apply: the host chunks live in the host arena all ranks of `mirrorComm` have mapped (mrx_comm_host_arena); every
+    // rank downloads the chunks it owns (chunk index % world) over ITS PCIe link, and the call returns on every rank with the
+    // whole tree in that memory (mrx_tree_set_shared_host_mirror)
+    const mrx_comm *mirrorComm = nullptr;
     explicit mrx_tree(const mrx::MRA<3> &m)
             : host(m) {}
 };
@@ -162,6 +166,9 @@ cudaStream_t comm_unpack_stream(mrx_comm *c); // side stream of the row unpack (
 cudaEvent_t comm_ev_gathered(const mrx_comm *c);
 cudaEvent_t comm_ev_unpacked(const mrx_comm *c, int buf);
 cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf);
+bool comm_has_host_arena(const mrx_comm *c); // mrx_comm_host_arena succeeded on all ranks
+void *host_arena_alloc(size_t bytes);        // chunk allocator pair over the shared arena (Tree::rebaseChunks)
+void host_arena_free(void *p);
 
 // apply.cu
 /// precTrees != nullptr: apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (apply.cpp:214-251), precision scaled per

@@ -210,6 +210,8 @@ public:
     const std::vector<double *> &coefChunks() const { return chunks_; }
     bool coefsPinned() const;
     static constexpr int chunkNodes = 64;
+    /// move the coefficient chunks to another allocator (e.g. a host arena shared by the ranks of a sharded apply); contents kept
+    void rebaseChunks(void *(*alloc)(size_t), void (*free)(void *));
 
     void zeroCoefs(int n);
     void calcNorms(int n);                  // MWNode.cpp:609-616 (+ OperatorNode.cpp:56-80 when operNorms)

@@ -86,6 +86,18 @@ template <int D> void Tree<D>::ensureCoefStorageFor(size_t nSlots) {
     while (chunks_.size() < needChunks) chunks_.push_back(static_cast<double *>(alloc_((size_t)(chunkMask_ + 1) * ncoef * sizeof(double))));
 }
 
+template <int D> void Tree<D>::rebaseChunks(void *(*alloc)(size_t), void (*free)(void *)) {
+    const size_t bytes = (size_t)(chunkMask_ + 1) * ncoef * sizeof(double);
+    for (double *&c : chunks_) {
+        double *n = static_cast<double *>(alloc(bytes));
+        std::memcpy(n, c, bytes);
+        free_(c);
+        c = n;
+    }
+    alloc_ = alloc;
+    free_ = free;
+}
+
 template <int D>
 int Tree<D>::getNodeTopo(int scale, const std::array<int, D> &l, std::vector<int> *newParents, bool withCoefStorage) {
     int n = rootIndex(scale, l);

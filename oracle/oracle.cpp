@@ -475,6 +475,7 @@ struct ConvCalc {
                 }
             }
         }
+        gTree.nodes[g].flags |= FlagHasCoefs; // MWNode::zeroCoefs at the top of calcNode marks the node (MWNode.cpp: setHasCoefs)
         calc_norms(gTree, g);
         return applied;
     }

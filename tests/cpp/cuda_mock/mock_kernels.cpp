@@ -222,6 +222,9 @@ void device_apply_derivative(mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int d
 }
 int comm_rank(const mrx_comm *) { return 0; }
 int comm_world(const mrx_comm *) { return 1; }
+bool comm_has_host_arena(const mrx_comm *) { return false; }
+void *host_arena_alloc(size_t) { MRX_ABORT("mock: no communicator"); }
+void host_arena_free(void *) {}
 
 } // namespace mrx
 
@@ -229,6 +232,7 @@ extern "C" {
 int mrx_comm_unique_id(char *) { MRX_ABORT("mock: no communicator"); }
 mrx_comm *mrx_comm_create(int, int, const char *) { MRX_ABORT("mock: no communicator"); }
 void mrx_comm_destroy(mrx_comm *) {}
+int mrx_comm_host_arena(mrx_comm *, long long) { return 1; }
 int mrx_comm_rank(const mrx_comm *) { return 0; }
 int mrx_comm_size(const mrx_comm *) { return 1; }
 void mrx_shard_partition(const long long *, int, int, int *) { MRX_ABORT("mock: sharding"); }

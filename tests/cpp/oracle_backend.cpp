@@ -33,6 +33,8 @@ struct Oracle {
     int (*refine_grid)(void *, double, int, int);
     void (*power)(double, void *, void *, double, int, int);
     void (*add_inplace)(void *, double, void *);
+    void (*apply_unit_cell)(int, double, void *, void *, void *, int, int, orc_stats *);
+    void (*apply_prec_trees)(double, void *, void *, void *, int, void **, int, int, orc_stats *);
 };
 Oracle &oracle() {
     static Oracle o = [] {
@@ -55,6 +57,8 @@ Oracle &oracle() {
         r.refine_grid = reinterpret_cast<decltype(r.refine_grid)>(dlsym(h, "orc_refine_grid"));
         r.power = reinterpret_cast<decltype(r.power)>(dlsym(h, "orc_power"));
         r.add_inplace = reinterpret_cast<decltype(r.add_inplace)>(dlsym(h, "orc_add_inplace"));
+        r.apply_unit_cell = reinterpret_cast<decltype(r.apply_unit_cell)>(dlsym(h, "orc_apply_unit_cell"));
+        r.apply_prec_trees = reinterpret_cast<decltype(r.apply_prec_trees)>(dlsym(h, "orc_apply_prec_trees"));
         if (const char *t = std::getenv("MRX_TABLES")) r.set_tables(t);
         return r;
     }();
@@ -103,6 +107,34 @@ int mrx_apply(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max
         stats->iterations = st.iters;
         stats->n_nodes_out = st.nNodesOut;
     }
+    return 0;
+}
+static void copy_stats(const orc_stats &st, mrx_apply_stats *stats) {
+    if (!stats) return;
+    std::memset(stats, 0, sizeof(*stats));
+    stats->g_nodes = st.gNodes;
+    stats->f_applied = st.fApplied;
+    stats->gen_nodes = st.genUsed;
+    stats->iterations = st.iters;
+    stats->n_nodes_out = st.nNodesOut;
+}
+int mrx_apply_unit_cell(int inside, double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
+                        mrx_apply_stats *stats) {
+    orc_stats st{};
+    oracle().apply_unit_cell(inside, prec, mrx_tree_host_handle(out), mrx_oper_host_handle(oper), mrx_tree_host_handle(inp), max_iter, abs_prec, &st);
+    mrx_tree_host_modified(out);
+    copy_stats(st, stats);
+    return 0;
+}
+int mrx_apply_prec_trees(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int n_prec, mrx_tree *const *prec_trees, int max_iter,
+                         int abs_prec, const mrx_comm *, mrx_apply_stats *stats) {
+    orc_stats st{};
+    std::vector<void *> h(n_prec > 0 ? n_prec : 0);
+    for (int i = 0; i < n_prec; i++) h[i] = mrx_tree_host_handle(prec_trees[i]);
+    oracle().apply_prec_trees(prec, mrx_tree_host_handle(out), mrx_oper_host_handle(oper), mrx_tree_host_handle(inp), n_prec, h.data(), max_iter,
+                              abs_prec, &st);
+    mrx_tree_host_modified(out);
+    copy_stats(st, stats);
     return 0;
 }
 int mrx_apply_derivative(mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int dir, mrx_apply_stats *stats) {

@@ -179,3 +179,28 @@ def check_drop_in_values(kv, what="all"):
         assert abs(kv["dot_vectors_integral"] - kv["dot_vectors_expected"]) < 1e-3 * abs(kv["dot_vectors_expected"])
     if what == "all":
         assert abs(kv["divergence_grad_sqnorm"] - 3.0 * kv["derivative_0_sqnorm"]) < 1e-6
+
+
+def check_periodic_values(kv):
+    """numbers tests/cpp/periodic_drop_in.cpp prints: the periodic Poisson solution against the analytic one (the point
+    (1,0,0) is the image of (-1,0,0): evalf wraps as periodic::coord_manipulation does), near + far field = whole, the
+    Helmholtz apply, and the precision-tree apply"""
+    assert kv["periodic"] == 1 and kv["done"] == 1
+    assert kv["poisson_terms"] > 10 and kv["helmholtz_terms"] > 10
+    assert kv["source_nodes"] > 8 and kv["sol_nodes"] > 8
+    assert abs(kv["sol_diff_0_1"] - kv["exact_diff_0_1"]) < 2e-3
+    assert abs(kv["sol_diff_0_h"] - kv["exact_diff_0_h"]) < 2e-3
+    assert abs(kv["near_plus_far"] - kv["whole"]) < 1e-5 * abs(kv["whole"]) + 1e-6
+    assert kv["helmholtz_nodes"] >= 8 and kv["helmholtz_sqnorm"] > 0
+    assert kv["scaled_nodes"] >= 8 and abs(kv["scaled_diff_0_1"] - kv["exact_diff_0_1"]) < 2e-3
+
+
+def test_periodic_program_on_the_oracle_backend(libs, bindir):
+    """tests/cpp/periodic_drop_in.cpp (periodic BoundingBox, operators with root and reach, apply / apply_near_field /
+    apply_far_field, apply with precision trees -- the calls of the reference's periodic Poisson/Helmholtz tests) runs on CPU
+    with the device entry points served by the oracle"""
+    exe = cb.compile_program([os.path.join(CPP, "periodic_drop_in.cpp"), os.path.join(CPP, "oracle_backend.cpp")],
+                             os.path.join(bindir, "periodic_cpu"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "-1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    check_periodic_values(cb.key_values(r.stdout))

@@ -7,7 +7,7 @@ import os
 import pytest
 
 import cpp_build as cb
-from test_cpp_mirror import check_drop_in_values, check_scf_values
+from test_cpp_mirror import check_drop_in_values, check_periodic_values, check_scf_values
 
 pytestmark = pytest.mark.gpu
 
@@ -71,3 +71,22 @@ def test_scf_cycle_on_the_device(libs, tmp_path):
     for it in range(1, int(kv["iterations"]) + 1):
         assert abs(kv[f"nodes_{it}"] - kc[f"nodes_{it}"]) <= 0.02 * kc[f"nodes_{it}"]
         assert abs(kv[f"energy_{it}"] - kc[f"energy_{it}"]) < 1e-6
+
+
+def test_periodic_program_on_the_device(libs, tmp_path):
+    """tests/cpp/periodic_drop_in.cpp on the device: periodic operators with root and reach, near/far field and precision-tree
+    applies through the C++ mirror; node counts identical to the run served by the CPU oracle, values to rounding"""
+    src = os.path.join(cb.ROOT, "tests", "cpp", "periodic_drop_in.cpp")
+    exe = cb.compile_program([src], str(tmp_path / "periodic_gpu"))
+    r = cb.run_program(exe, env={"MRCPP_B200_DEVICE": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    kv = cb.key_values(r.stdout)
+    check_periodic_values(kv)
+    cpu = cb.compile_program([src, os.path.join(cb.ROOT, "tests", "cpp", "oracle_backend.cpp")], str(tmp_path / "periodic_cpu"))
+    rc = cb.run_program(cpu, env={"MRCPP_B200_DEVICE": "-1"})
+    assert rc.returncode == 0, rc.stderr[-2000:]
+    kc = cb.key_values(rc.stdout)
+    for key in ("source_nodes", "sol_nodes", "helmholtz_nodes", "scaled_nodes", "poisson_terms", "helmholtz_terms"):
+        assert kv[key] == kc[key], key
+    for key in ("sol_diff_0_1", "sol_diff_0_h", "near_plus_far", "whole", "helmholtz_sqnorm", "scaled_diff_0_1"):
+        assert abs(kv[key] - kc[key]) <= 1e-10 * max(1.0, abs(kc[key])), key

@@ -41,7 +41,26 @@ f.drop_device()
 g2 = mw.FunctionTree(mra)
 dist.barrier()
 s3 = mw.apply(prec, g2, P, f, comm=comm)
+# result into host memory shared by the ranks: every rank downloads its chunks, all see the whole tree when the call returns
 A, B = g.to_arrays(), ref.to_arrays()
+have_arena = comm.host_arena(int(ref.nbytes() * 1.1) + (64 << 20))
+if os.environ.get("MRX_EXPECT_ARENA"):
+    assert have_arena, "shared host arena expected on this box"
+for rep in range(2):  # second round: arena space of the first tree came back
+    g3 = mw.FunctionTree(mra)
+    shared = g3.set_host_mirror(True, comm=comm)
+    assert shared == have_arena
+    dist.barrier()
+    s4 = mw.apply(prec, g3, P, f, comm=comm)
+    g3.drop_device()  # what to_arrays reads now is the host copy
+    C3 = g3.to_arrays()
+    assert np.array_equal(C3["transl"], B["transl"]) and np.array_equal(C3["coefs"], B["coefs"]), "shared host mirror differs"
+    if shared:
+        t = torch.tensor([float(s4.d2h_bytes)], dtype=torch.float64, device="cuda"); dist.all_reduce(t)
+        assert int(t[0]) == g3.nbytes(), (int(t[0]), g3.nbytes())
+        assert 0 < s4.d2h_bytes < g3.nbytes()
+    del g3
+print(f"rank {rank}: shared host mirror {'on' if have_arena else 'unavailable'} ok", flush=True)
 C2 = g2.to_arrays()
 assert np.array_equal(C2["transl"], B["transl"]) and np.array_equal(C2["coefs"], B["coefs"]), "sharded apply on a host-resident input differs"
 assert 0 < s3.h2d_bytes < f.nbytes() and s3.f_applied == s1.f_applied
