@@ -518,6 +518,14 @@ def main():
                     if not e2e_skip else None),
             "e2e_skipped": e2e_skip,
             "gpu_launches": int(launches),
+            # where the step goes (rank 0's view). Sharded over the ranks: the contraction and the other work-list kernels
+            # (screen, scans, fill, reduce). Not sharded or latency-bound: band enumeration launches, the per-iteration norm
+            # exchange + split decisions + mailbox reads, and the closing passes every rank repeats on the whole tree
+            # (BottomUp, norms, topology to the host; the TopDown(+=) runs inside the loop on a side stream)
+            "breakdown_ms": {"contract": A.contract_ms / args.steps, "other_work_list_kernels": (A.kern_ms - A.contract_ms) / args.steps,
+                             "closing_passes_replicated": A.phases["ms_post"] / args.steps,
+                             "enumeration_exchange_split_host": (A.ms - A.kern_ms - A.phases["ms_post"]) / args.steps,
+                             "ms_replicated": (A.ms - A.kern_ms) / args.steps},
             "detail": {"applies_per_step_this_rank": napply, "output_nodes_per_step": nodes // args.steps,
                        "final_tree_nodes_last_apply": last.n_nodes_out, "iterations_last_apply": last.iterations,
                        "tuples_per_step": tuples // args.steps, "generated_input_nodes_last_apply": last.gen_nodes,

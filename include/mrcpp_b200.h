@@ -202,10 +202,12 @@ void mrx_comm_destroy(mrx_comm *comm);
 int mrx_comm_rank(const mrx_comm *comm);
 int mrx_comm_size(const mrx_comm *comm);
 void mrx_shard_partition(const long long *cost, int n, int world, int *begin /*[world+1]*/);
-/* the distribution mrx_apply_sharded uses: item i of an iteration's work vector is computed by rank i % world; exchange
- * buffers are rank-major with equal, padded segments: item i = row (i % world) * rows + i / world, rows = ceil(n / world) */
+/* the distribution mrx_apply_sharded uses: block-cyclic with blocks of B = mrx_shard_block() consecutive items: item i of an
+ * iteration's work vector is computed by rank (i / B) % world; exchange buffers are rank-major with equal, padded segments:
+ * item i = row ((i / B) % world) * rows + (i / (B world)) * B + i % B, rows = ceil(ceil(n / B) / world) * B */
 void mrx_shard_cyclic(int n, int world, int rank, int *count, int *rows);
 int mrx_shard_cyclic_row(int i, int n, int world);
+int mrx_shard_block(void);
 /* mrcpp::apply sharded over the ranks of `comm` (comm == NULL: same as mrx_apply). Collective: every rank
  * calls it with identical arguments. stats->f_applied / gen_nodes are summed over ranks. */
 int mrx_apply_sharded(double prec, mrx_tree *out, mrx_oper *oper, mrx_tree *inp, int max_iter, int abs_prec,
@@ -290,7 +292,9 @@ int mrx_tree_set_host_mirror(mrx_tree *tree, int on);
  * host chunks move into the communicator's shared host arena, every rank downloads the chunks it owns (chunk index modulo
  * world size) while the apply runs, and the call returns on every rank with the complete tree in that (shared) host
  * memory: N PCIe links carry the result instead of one. Returns 1 (and behaves like mrx_tree_set_host_mirror(tree, 1))
- * when the communicator has no arena. The tree must not outlive the communicator. */
+ * when the communicator has no arena. The host copy is ONE copy that all ranks see: every rank creates and frees its
+ * shared-mirror trees in the same order (the arena is a bump allocator; the apply aborts if the ranks disagree on where the
+ * tree lies), and the tree must not outlive the communicator. */
 int mrx_tree_set_shared_host_mirror(mrx_tree *tree, mrx_comm *comm);
 int mrx_tree_drop_device(mrx_tree *tree); /* free the HBM copy (next use uploads again)              */
 long long mrx_tree_bytes(const mrx_tree *tree);

@@ -444,6 +444,11 @@ def shard_cyclic(n, world, rank):
     return cnt.value, rows.value
 
 
+def shard_block():
+    """items dealt out together by the sharded apply's block-cyclic distribution (mrx_shard_block)"""
+    return _lib.load().mrx_shard_block()
+
+
 def shard_cyclic_row(i, n, world):
     """row of work-vector item i in the rank-major exchange buffers (mrx_shard_cyclic_row)"""
     return _lib.load().mrx_shard_cyclic_row(int(i), int(n), int(world))

@@ -107,6 +107,7 @@ SIGNATURES = {
     "mrx_shard_partition": (None, [C.POINTER(C.c_longlong), _I, _I, _PI]),
     "mrx_shard_cyclic": (None, [_I, _I, _I, _PI, _PI]),
     "mrx_shard_cyclic_row": (_I, [_I, _I, _I]),
+    "mrx_shard_block": (_I, []),
     "mrx_apply_derivative": (_I, [_P, _P, _P, _I, C.POINTER(ApplyStats)]),
     "mrx_mw_transform": (_I, [_P, _I, _I]),
     "mrx_node_mw_transform": (_I, [_P, _I, _I, _PI]),

@@ -414,21 +414,33 @@ static void ensure_input_topology(mrx_tree &inp, cudaStream_t st) {
     // per apply (generated nodes hang new children below real leaves while an apply runs)
     DeviceTree &fd = inp.dev;
     if (fd.topoNodes != fRealN) {
-        std::vector<int> hChild0(fRealN), hDepth(fRealN);
-        std::vector<double> fNodeNorm(fRealN);
+        // built straight into pinned staging memory on a few host threads: [bound: n doubles][child0: n ints][depth: n ints]
+        double *stage = pinned_stage((size_t)2 * fRealN + 2);
+        double *hBound = stage;
+        int *hChild0 = reinterpret_cast<int *>(stage + fRealN), *hDepth = hChild0 + fRealN;
+        std::vector<double> mxT(64, 0.0);
+        std::atomic<int> slot{0};
+        const int rootScale = f.mra.rootScale;
+        host_parallel((size_t)fRealN, [&](size_t a, size_t b) {
+            double m = 0.0;
+            for (size_t n = a; n < b; n++) {
+                const double v = std::sqrt(f.sqn[n]);
+                hBound[n] = v;
+                m = std::max(m, v);
+                const int c0 = f.nodes[n].child0;
+                hChild0[n] = (c0 >= 0 && c0 < fRealN) ? c0 : -1;
+                hDepth[n] = f.nodes[n].scale - rootScale;
+            }
+            mxT[slot.fetch_add(1) & 63] = m;
+        });
         double mx = 0.0;
-        for (int n = 0; n < fRealN; n++) {
-            fNodeNorm[n] = std::sqrt(f.sqn[n]);
-            mx = std::max(mx, fNodeNorm[n]);
-            hChild0[n] = (f.nodes[n].child0 >= 0 && f.nodes[n].child0 < fRealN) ? f.nodes[n].child0 : -1;
-            hDepth[n] = f.nodes[n].scale - f.mra.rootScale;
-        }
+        for (double v : mxT) mx = std::max(mx, v);
         fd.topoChild0.reserve(fRealN, false, st);
         fd.topoDepth.reserve(fRealN, false, st);
         fd.topoBound.reserve(fRealN, false, st);
-        MRX_CUDA(cudaMemcpyAsync(fd.topoChild0.p, hChild0.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(fd.topoDepth.p, hDepth.data(), sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
-        MRX_CUDA(cudaMemcpyAsync(fd.topoBound.p, fNodeNorm.data(), sizeof(double) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(fd.topoBound.p, hBound, sizeof(double) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(fd.topoChild0.p, hChild0, sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
+        MRX_CUDA(cudaMemcpyAsync(fd.topoDepth.p, hDepth, sizeof(int) * fRealN, cudaMemcpyHostToDevice, st));
         MRX_CUDA(cudaStreamSynchronize(st));
         fd.topoNodes = fRealN;
         fd.topoMaxNorm = mx;
@@ -866,6 +878,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     const int M = op.size(), DM = oper.dev.DM;
     const bool deriv = derivDir >= 0;
     const int world = comm_world(comm), rank = comm_rank(comm);
+    const int shardB = world > 1 ? shard_block() : 1;
     const char *uEnv = getenv("MRX_UNIT_TUPLES");
     const int unitTuples = uEnv ? std::max(8, atoi(uEnv)) : 64; // tuples per contraction work unit
     const bool profile = getenv("MRX_PROFILE") != nullptr;
@@ -993,7 +1006,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         MRX_CUDA(cudaEventRecord(comm_ev_gathered(comm), st));
         MRX_CUDA(cudaStreamWaitEvent(ust, comm_ev_gathered(comm), 0));
         launch_unpack_nodes(out.dev.coefs.p, reinterpret_cast<double *>(comm_stage(comm, pend.buf)), scr.gslotsAll[pend.buf].p, pend.nG,
-                            world, pend.rows, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, ust);
+                            world, pend.rows, shardB, ncoef, scr.normsW[pend.buf].p, out.dev.norms.p, ust);
         MRX_CUDA(cudaEventRecord(comm_ev_unpacked(comm, pend.buf), ust));
         unpackInFlight[pend.buf] = true;
         cudaEvent_t ready = comm_ev_unpacked(comm, pend.buf);
@@ -1103,7 +1116,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     }
     auto prep_local = [&](int cur, int slotBuf, int nGgiven) {
         const int cap = (nGgiven >= 0) ? nGgiven : 8 * nG; // upper bound of the next work vector
-        const int capL = (cap + world - 1) / world + 1;
+        const int capL = shard_rows(cap, world, shardB) + 1;
         scr.gNodes.reserve(capL, false, st);
         scr.gslots.reserve(capL, false, st);
         scr.chunkOff.reserve(capL + 1, false, st);
@@ -1123,6 +1136,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         PP.nG = nGgiven;
         PP.world = world;
         PP.rank = rank;
+        PP.shardB = shardB;
         PP.gNodesAll = scr.gAll[cur].p;
         PP.slotsAll = scr.gslotsAll[slotBuf].p;
         PP.offCount = bt.d_offCount.p;
@@ -1201,7 +1215,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         const int b = iter % kCommStageBufs;
         const int nL = res.nLoc, nChunks = res.nChunksLoc;
         const long long nbrCap = res.nbrCapLoc;
-        const int rowsPerRank = (nG + world - 1) / world;
+        const int rowsPerRank = shard_rows(nG, world, shardB);
         if (nbrCap >= (1ll << 31) || (long long)nChunks * 32 >= (1ll << 31)) MRX_ABORT("apply: band of one iteration exceeds 2^31 entries");
         double gThrs = g.squareNorm; // ConvolutionCalculator.cpp:241-248
         if (gThrs > 0.0) gThrs = prec * 1.0 * std::sqrt(gThrs / static_cast<double>(M));
@@ -1444,7 +1458,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
             } else {
                 comm_allgather(comm, normsBuf.p, (size_t)rowsPerRank * 8 * sizeof(double), st);
                 comm_allgather(comm, stageB, segBytes, st);
-                launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, ncoef, normsBuf.p,
+                launch_unpack_nodes(out.dev.coefs.p, stageB, scr.gslotsAll[b].p, nG, world, rowsPerRank, shardB, ncoef, normsBuf.p,
                                     out.dev.norms.p, st);
                 if (fold || mirror) { // this iteration's nodes are in the store: its TopDown step and mirror copies
                     cudaEvent_t ready = fold ? td_->evReady : ms_->evReduced;
@@ -1476,6 +1490,7 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         SP.nG = nG;
         SP.world = world;
         SP.rows = rowsPerRank;
+        SP.shardB = shardB;
         SP.gNodesAll = scr.gAll[cur].p;
         SP.isBranch = (iter == 0 && scr.hasBranchFlags) ? scr.isBranch.p : nullptr;
         SP.operRoot = op.operRoot;
@@ -1662,8 +1677,14 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         const int shareW = (out.mirrorComm && out.mirrorComm == comm) ? comm_world(comm) : 1, shareR = comm_rank(comm);
         std::vector<int> items;
         items.reserve(g.nReal / shareW + 64);
-        for (int n = 0; n < g.nReal; n++)
-            if (shareW == 1 || (n >> 6) % shareW == shareR) items.push_back(g.isBranch(n) ? (int)((unsigned)n | 0x80000000u) : n);
+        // TopDown(+=) folded into the loop: a leaf node was copied after the step that finished its scaling block, so only the
+        // branch nodes (rewritten by BottomUp) are left; otherwise the scaling block of every node has changed since its copy
+        const bool leavesDone = bareRoots && tdFolded;
+        for (int n = 0; n < g.nReal; n++) {
+            if (shareW > 1 && (n >> 6) % shareW != shareR) continue;
+            if (g.isBranch(n)) items.push_back((int)((unsigned)n | 0x80000000u));
+            else if (!leavesDone) items.push_back(n);
+        }
         const int nItems = (int)items.size();
         DevBuf<int> dItems;
         dItems.reserve(std::max(nItems, 1), false, st);
@@ -1686,17 +1707,29 @@ void device_apply(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree &inp, int
         }
         launch_push_nodes(out.dev.coefs.p, const_cast<double *const *>(reinterpret_cast<const double *const *>(out.dev.chunkTab.p)), dItems.p,
                           nItems, g.ncoef, st);
-        if (shareW > 1) { // the peers' pushes into the shared arena are ordered before this rank's return
-            DevBuf<double> bar;
-            bar.reserve(1, false, st);
-            MRX_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(double), st));
-            comm_allreduce_sum(comm, bar.p, 1, st);
+        std::vector<double> offs;
+        DevBuf<double> bar;
+        if (shareW > 1) {
+            // the peers' pushes into the shared arena are ordered before this rank's return; the same all-reduce carries every
+            // rank's arena offset of the tree's first chunk: the ranks must have placed the tree at the same spot
+            offs.assign(shareW, 0.0);
+            offs[shareR] = (double)host_arena_offset(chunks[0]);
+            bar.reserve(shareW, false, st);
+            MRX_CUDA(cudaMemcpyAsync(bar.p, offs.data(), sizeof(double) * shareW, cudaMemcpyHostToDevice, st));
+            comm_allreduce_sum(comm, bar.p, shareW, st);
+            MRX_CUDA(cudaMemcpyAsync(offs.data(), bar.p, sizeof(double) * shareW, cudaMemcpyDeviceToHost, st));
         }
         MRX_CUDA(cudaStreamSynchronize(st));
+        for (int r = 0; r < (int)offs.size(); r++)
+            if (offs[r] != offs[shareR])
+                MRX_ABORT("shared host mirror: the ranks placed the output tree at different arena offsets (every rank must create and "
+                          "free its shared-mirror trees in the same order)");
         if (prof) std::fprintf(stderr, "[mrx] mirror: push of the remainder %.2f ms\n", now_ms() - tm0);
         for (int n = 0; n < g.nReal; n++) g.nodes[n].flags |= FlagHasCoefs;
         out.hostCoefsValid = true;
-        S.d2h_bytes = (long long)nItems * g.ncoef * (long long)sizeof(double); // what THIS rank's link carried
+        long long mine = 0; // nodes THIS rank's link carried
+        for (int n = 0; n < g.nReal; n++) mine += (shareW == 1 || (n >> 6) % shareW == shareR) ? 1 : 0;
+        S.d2h_bytes = mine * g.ncoef * (long long)sizeof(double);
     }
     inp.host.deleteGenerated();
     inp.dev.nGen = 0;

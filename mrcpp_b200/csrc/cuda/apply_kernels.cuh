@@ -178,9 +178,25 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
 /// exchange staging buffer (row j = local node j) instead of the node store
 void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
                         cudaStream_t st, double *stageRows = nullptr);
-/// sharded apply: rank-major staging buffer (row r * rowsPerRank + j = work-vector item j * world + r) -> node store,
+// ---- distribution of a work vector over the ranks of a sharded apply: block-cyclic, blocks of B consecutive items (B = 1: plain
+//      cyclic). Consecutive items are siblings and spatial neighbours: they cost about the same (so dealing them out balances the
+//      tuple counts) and they read nearly the same input nodes (so keeping a few together lets a rank gather fewer of them from
+//      host memory). Item i -> rank (i / B) % world, local index (i / (B world)) B + i % B; rows = per-rank capacity.
+__host__ __device__ inline int shard_rows(int n, int world, int B) { return (((n + B - 1) / B + world - 1) / world) * B; }
+__host__ __device__ inline int shard_row(int i, int world, int rows, int B) {
+    const int q = i / B;
+    return (q % world) * rows + (q / world) * B + i % B;
+}
+__host__ __device__ inline int shard_count(int n, int world, int rank, int B) {
+    const int full = n / B, rem = n % B;
+    return ((full + world - 1 - rank) / world) * B + ((rem && full % world == rank) ? rem : 0);
+}
+__host__ __device__ inline int shard_item(int rank, int j, int world, int B) { return ((j / B) * world + rank) * B + j % B; }
+int shard_block(); // B of this process (MRX_SHARD_BLOCK; comm.cu)
+
+/// sharded apply: rank-major staging buffer (row shard_row(i) = work-vector item i) -> node store,
 /// coefficient blocks and (normRows, same layout, 8 per row) component norms
-void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
+void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int shardB, int ncoef,
                          const double *normRows, double *gNorms, cudaStream_t st);
 
 // ---- refinement step on the device (apply_split.cu) ------------------------------------------------------
@@ -191,8 +207,8 @@ struct SplitResult {
     long long nbrCapLoc;             // upper bound of its neighbour list
 };
 struct SplitParams {
-    const double *normRows; // component norms of the iteration, rank-major rows of 8 (item i = row (i % world) * rows + i / world)
-    int nG, world, rows;
+    const double *normRows; // component norms of the iteration, rank-major rows of 8 (item i = row shard_row(i, world, rows, shardB))
+    int nG, world, rows, shardB;
     const int4 *gNodesAll;          // [nG] (operator depth, lx, ly, lz) in work-vector order
     const unsigned char *isBranch;  // [nG] or nullptr (no item is a branch node)
     int operRoot, rootScale, maxScale;
@@ -212,13 +228,13 @@ struct SplitParams {
 };
 struct PrepParams {
     int nG;                  // >= 0: given by the host; < 0: read res->nNext (written by split_kernel just before)
-    int world, rank;
+    int world, rank, shardB;
     const int4 *gNodesAll;
     const int *slotsAll;
     const int *offCount;     // [DM] reachable offsets per depth (band tables)
     const DepthInfo *depthInfo;
     int DM;
-    int4 *gNodesLoc;         // this rank's items (i = rank + j world)
+    int4 *gNodesLoc;         // this rank's items (i = shard_item(rank, j, world, shardB))
     int *slotsLoc;
     const double *precAll;   // per-item precision factors of the whole work vector (or nullptr) ...
     double *precLoc;         // ... and this rank's share

@@ -980,12 +980,12 @@ __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const i
 }
 
 // sharded apply: one iteration's output nodes from the rank-major staging buffer (row r * rowsPerRank + j holds work-vector
-// item i = j * world + r, the cyclic distribution of the work vector) into the node store
+// item shard_item(r, j), the block-cyclic distribution of the work vector) into the node store
 __global__ void __launch_bounds__(256) unpack_nodes_kernel(double *__restrict__ coefs, const double *__restrict__ stage,
                                                            const int *__restrict__ gslotsAll, int nG, int world, int rowsPerRank,
-                                                           int ncoef, const double *__restrict__ normRows, double *__restrict__ gNorms) {
+                                                           int shardB, int ncoef, const double *__restrict__ normRows, double *__restrict__ gNorms) {
     const int r = blockIdx.x / rowsPerRank, j = blockIdx.x - r * rowsPerRank;
-    const int i = j * world + r;
+    const int i = shard_item(r, j, world, shardB);
     if (i >= nG) return;
     const int slot = gslotsAll[i];
     const double2 *src = reinterpret_cast<const double2 *>(stage + (size_t)blockIdx.x * ncoef);
@@ -1127,10 +1127,10 @@ void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits
     launch_counter()++;
 }
 
-void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int ncoef,
+void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAll, int nG, int world, int rowsPerRank, int shardB, int ncoef,
                          const double *normRows, double *gNorms, cudaStream_t st) {
     if (nG <= 0) return;
-    unpack_nodes_kernel<<<world * rowsPerRank, 256, 0, st>>>(coefs, stage, gslotsAll, nG, world, rowsPerRank, ncoef, normRows, gNorms);
+    unpack_nodes_kernel<<<world * rowsPerRank, 256, 0, st>>>(coefs, stage, gslotsAll, nG, world, rowsPerRank, shardB, ncoef, normRows, gNorms);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(1024) split_kernel(SplitParams S) {
     if (S.iter == 0) sNorm = 0.0;
     auto stage = [&](int buf, int i) {
         if (i < nG) {
-            const double *n = S.normRows + ((size_t)(i % S.world) * S.rows + i / S.world) * 8;
+            const double *n = S.normRows + (size_t)shard_row(i, S.world, S.rows, S.shardB) * 8;
             double w = 0.0;
 #pragma unroll
             for (int c = 1; c < 8; c++) w = fma(n[c], n[c], w); // MWNode::getWaveletNorm (squared), component order
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(1024) split_kernel(SplitParams S) {
                 const int scale = gn.x + S.operRoot;
                 const bool branch = S.isBranch ? (S.isBranch[i] != 0) : false;
                 if (!branch && scale + 2 <= S.maxScale && S.prec > 0.0) {
-                    const double *n = S.normRows + ((size_t)(i % S.world) * S.rows + i / S.world) * 8;
+                    const double *n = S.normRows + (size_t)shard_row(i, S.world, S.rows, S.shardB) * 8;
                     double w = 0.0;
 #pragma unroll
                     for (int c = 1; c < 8; c++) w = fma(n[c], n[c], w);
@@ -162,19 +162,19 @@ __global__ void __launch_bounds__(1024) split_kernel(SplitParams S) {
     }
 }
 
-// one CTA: the rank's share of a work vector (cyclic distribution) and the chunk table of its band enumeration
+// one CTA: the rank's share of a work vector (block-cyclic distribution) and the chunk table of its band enumeration
 __global__ void __launch_bounds__(1024) prep_local_kernel(PrepParams P) {
     __shared__ int sm[33];
     const int tid = threadIdx.x;
     const int nG = (P.nG >= 0) ? P.nG : P.res->nNext;
-    const int nL = (nG + P.world - 1 - P.rank) / P.world;
+    const int nL = shard_count(nG, P.world, P.rank, P.shardB);
     int run = 0;
     long long nbr = 0;
     for (int base = 0; base < nL; base += 1024) {
         const int j = base + tid;
         int cnt = 0;
         if (j < nL) {
-            const int i = P.rank + j * P.world;
+            const int i = shard_item(P.rank, j, P.world, P.shardB);
             const int4 gn = P.gNodesAll[i];
             P.gNodesLoc[j] = gn;
             P.slotsLoc[j] = P.slotsAll[i];

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../engine.hpp"
+#include "apply_kernels.cuh"
 #include "common.cuh"
 
 namespace mrx {
@@ -108,6 +109,14 @@ struct mrx_comm {
 
 namespace mrx {
 
+int shard_block() {
+    static const int B = [] {
+        const char *e = getenv("MRX_SHARD_BLOCK");
+        const int b = e ? atoi(e) : 1;
+        return b < 1 ? 1 : b;
+    }();
+    return B;
+}
 int comm_rank(const mrx_comm *c) { return c ? c->rank : 0; }
 int comm_world(const mrx_comm *c) { return c ? c->world : 1; }
 
@@ -266,6 +275,7 @@ void host_arena_free(void *) {
     if (--g_arena.live == 0) g_arena.used = 0; // bump allocator: space comes back when the last chunk is gone
 }
 bool comm_has_host_arena(const mrx_comm *c) { return c && c->hostArena && g_arena.base; }
+long long host_arena_offset(const void *p) { return (long long)(static_cast<const char *>(p) - g_arena.base); }
 
 int comm_host_arena(mrx_comm *c, size_t bytes) {
     NcclApi &a = api();
@@ -401,10 +411,15 @@ int mrx_comm_size(const mrx_comm *c) { return mrx::comm_world(c); }
  * padding to equal segments ((n + world - 1) / world). Item i lives in row (i % world) * rows + i / world of the rank-major
  * exchange buffers (norms and coefficient blocks). Pure host logic, shared with the CPU tests. */
 void mrx_shard_cyclic(int n, int world, int rank, int *count, int *rows) {
-    if (rows) *rows = (n + world - 1) / world;
-    if (count) *count = (n + world - 1 - rank) / world;
+    const int B = mrx::shard_block();
+    if (rows) *rows = mrx::shard_rows(n, world, B);
+    if (count) *count = mrx::shard_count(n, world, rank, B);
 }
-int mrx_shard_cyclic_row(int i, int n, int world) { return (i % world) * ((n + world - 1) / world) + i / world; }
+int mrx_shard_cyclic_row(int i, int n, int world) {
+    const int B = mrx::shard_block();
+    return mrx::shard_row(i, world, mrx::shard_rows(n, world, B), B);
+}
+int mrx_shard_block(void) { return mrx::shard_block(); }
 
 /* contiguous, order-preserving partition of n weighted items into `world` ranges: begin[r]..begin[r+1]
  * (the split of one refinement iteration's work vector; pure host logic, also used by the CPU tests) */

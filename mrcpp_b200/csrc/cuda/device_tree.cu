@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <thread>
+#include <vector>
 
 #include "../engine.hpp"
 #include "common.cuh"
@@ -32,6 +34,38 @@ const double *device_filters(int k) {
     MRX_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     cache[k] = d;
     return d;
+}
+
+double *pinned_stage(size_t doubles) {
+    static double *buf = nullptr;
+    static size_t cap = 0;
+    if (doubles > cap) {
+        if (buf) cudaFreeHost(buf);
+        cap = std::max(doubles, 2 * cap);
+        MRX_CUDA(cudaMallocHost(&buf, cap * sizeof(double)));
+    }
+    return buf;
+}
+
+void host_parallel(size_t n, const std::function<void(size_t, size_t)> &fn) {
+    static const unsigned maxT = [] {
+        const char *e = getenv("MRX_HOST_THREADS");
+        const int t = e ? atoi(e) : 4;
+        return (unsigned)std::max(1, std::min(t, (int)std::max(1u, std::thread::hardware_concurrency())));
+    }();
+    const unsigned T = (n < ((size_t)1 << 15)) ? 1u : maxT;
+    if (T == 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (n + T - 1) / T;
+    for (unsigned t = 1; t < T; t++) {
+        const size_t a = std::min(n, t * per), b = std::min(n, a + per);
+        if (a < b) th.emplace_back([&fn, a, b] { fn(a, b); });
+    }
+    fn(0, std::min(n, per));
+    for (auto &x : th) x.join();
 }
 
 void tree_upload(mrx_tree &t) {
@@ -67,7 +101,11 @@ void tree_lazy_begin(mrx_tree &t) {
     t.dev.resident.reserve((size_t)8 * std::max(n, 1), false, st); // one flag per coefficient block
     const auto &chunks = h.coefChunks();
     t.dev.chunkTab.reserve(std::max<size_t>(chunks.size(), 1), false, st);
-    MRX_CUDA(cudaMemcpyAsync(t.dev.norms.p, h.cnorm.data(), sizeof(double) * (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    // component norms: staged into pinned memory on a few threads, then one DMA transfer
+    double *stage = pinned_stage((size_t)n * 8);
+    const double *cn = h.cnorm.data();
+    host_parallel((size_t)n * 8, [&](size_t a, size_t b) { std::memcpy(stage + a, cn + a, (b - a) * sizeof(double)); });
+    MRX_CUDA(cudaMemcpyAsync(t.dev.norms.p, stage, sizeof(double) * (size_t)n * 8, cudaMemcpyHostToDevice, st));
     MRX_CUDA(cudaMemsetAsync(t.dev.resident.p, 0, sizeof(int) * (size_t)8 * std::max(n, 1), st));
     MRX_CUDA(cudaMemcpyAsync(t.dev.chunkTab.p, chunks.data(), sizeof(double *) * chunks.size(), cudaMemcpyHostToDevice, st));
     MRX_CUDA(cudaStreamSynchronize(st));

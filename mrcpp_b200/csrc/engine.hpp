@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -130,6 +131,11 @@ void device_mw_transform(mrx_tree &t, int type, bool overwrite, bool norms = tru
 /// pairs per depth of ALL branch nodes, if the caller already has them
 /// topDownDone: the TopDown(+=) steps were already run level by level inside the apply loop (apply.cu): BottomUp + norms only
 void device_apply_post(mrx_tree &t, const std::vector<std::vector<int>> *pairsByDepth = nullptr, bool topDownDone = false);
+/// pinned staging buffer for host->device uploads of host vectors (a pageable source is staged by the driver on one thread at a
+/// fraction of the PCIe rate); contents must be consumed (stream synchronised) before the next call
+double *pinned_stage(size_t doubles);
+/// fn(begin, end) over [0, n) on a few host threads (std::thread: independent of OMP_NUM_THREADS, which launchers set to 1)
+void host_parallel(size_t n, const std::function<void(size_t, size_t)> &fn);
 void device_calc_norms_all(mrx_tree &t);                         // norms of every node -> host cnorm/sqn
 /// MWNode::mwTransform (what = 0: kind 0 Compression, 1 Reconstruction) / MWNode::cvTransform (what = 1: kind 0 Forward, 1 Backward)
 /// of the listed nodes (n < 0: every node) in place
@@ -169,6 +175,7 @@ cudaEvent_t comm_ev_pushed(const mrx_comm *c, int buf);
 bool comm_has_host_arena(const mrx_comm *c); // mrx_comm_host_arena succeeded on all ranks
 void *host_arena_alloc(size_t bytes);        // chunk allocator pair over the shared arena (Tree::rebaseChunks)
 void host_arena_free(void *p);
+long long host_arena_offset(const void *p);  // of an arena chunk from the arena base (the same on every rank for the same chunk)
 
 // apply.cu
 /// precTrees != nullptr: apply(prec, out, oper, inp, precTrees, maxIter, absPrec) (apply.cpp:214-251), precision scaled per

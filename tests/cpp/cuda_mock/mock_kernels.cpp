@@ -225,6 +225,7 @@ int comm_world(const mrx_comm *) { return 1; }
 bool comm_has_host_arena(const mrx_comm *) { return false; }
 void *host_arena_alloc(size_t) { MRX_ABORT("mock: no communicator"); }
 void host_arena_free(void *) {}
+long long host_arena_offset(const void *) { return 0; }
 
 } // namespace mrx
 
@@ -238,6 +239,7 @@ int mrx_comm_size(const mrx_comm *) { return 1; }
 void mrx_shard_partition(const long long *, int, int, int *) { MRX_ABORT("mock: sharding"); }
 void mrx_shard_cyclic(int, int, int, int *, int *) { MRX_ABORT("mock: sharding"); }
 int mrx_shard_cyclic_row(int, int, int) { MRX_ABORT("mock: sharding"); }
+int mrx_shard_block(void) { return 1; }
 double mrx_bench_dmma_tflops(int) { return 0.0; }
 double mrx_bench_dfma_tflops(int) { return 0.0; }
 double mrx_bench_hbm_gbs(long long, int) { return 0.0; }

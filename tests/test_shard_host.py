@@ -28,18 +28,20 @@ def test_partition_properties(libs):
 
 def test_cyclic_distribution_properties(libs):
     mw, _ = libs
+    B = mw.shard_block()  # items dealt out together (MRX_SHARD_BLOCK)
+    assert B >= 1
     for n in (0, 1, 2, 7, 8, 9, 64, 1001):
         for world in (1, 2, 3, 4, 8):
             counts = [mw.shard_cyclic(n, world, r) for r in range(world)]
             rows = counts[0][1]
-            assert all(c[1] == rows for c in counts) and rows == (n + world - 1) // world
+            assert all(c[1] == rows for c in counts) and rows == -(-(-(-n // B)) // world) * B
             assert sum(c[0] for c in counts) == n                       # every item has exactly one owner
-            assert max(c[0] for c in counts) - min(c[0] for c in counts) <= 1  # balanced to within one item
+            assert max(c[0] for c in counts) - min(c[0] for c in counts) <= B  # balanced to within one block
             seen = set()
             for i in range(n):
                 row = mw.shard_cyclic_row(i, n, world)
                 r, j = divmod(row, rows)
-                assert r == i % world and j == i // world and j < counts[r][0]
+                assert r == (i // B) % world and j == (i // (B * world)) * B + i % B and j < counts[r][0]
                 seen.add(row)
             assert len(seen) == n                                       # rows are distinct: the unpack is a permutation
 
@@ -67,7 +69,10 @@ def _worker(rank, world, port, n, seed, q):
     # all-gather of equal segments completes it; the host reads item i at row (i % world) * rows + i / world
     cnt, rows = mw.shard_cyclic(n, world, rank)
     mine = torch.zeros(rows, 8, dtype=torch.float64)
-    mine[:cnt] = torch.from_numpy(truth[rank::world])
+    B = mw.shard_block()
+    owned = [i for i in range(n) if (i // B) % world == rank]  # in work-vector order = local order
+    assert len(owned) == cnt
+    mine[:cnt] = torch.from_numpy(truth[owned])
     segs = [torch.zeros(rows, 8, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(segs, mine)
     full = torch.cat(segs)
