@@ -103,3 +103,15 @@ def test_exchange_protocol_gloo_world2(libs):
         assert p.exitcode == 0
     assert all(ok and same for _, ok, same, _ in res)
     assert res[0][3] == res[1][3]
+
+
+def test_shared_host_mirror_without_an_arena_falls_back_to_the_rank_mirror(libs):
+    """mrx_tree_set_shared_host_mirror with no communicator / no arena: returns 1 and behaves like mrx_tree_set_host_mirror(tree, 1)
+    (the result of a sharded apply is then downloaded over the calling rank's link alone); host logic, no device needed"""
+    mw, _ = libs
+    from mrcpp_b200 import _lib
+    L = _lib.load()
+    mra = mw.MultiResolutionAnalysis(5, -2, (-1, -1, -1), (2, 2, 2), 20)
+    t = mw.FunctionTree(mra)
+    assert L.mrx_tree_set_shared_host_mirror(t._h, None) == 1
+    assert L.mrx_tree_set_host_mirror(t._h, 0) == 0
