@@ -156,6 +156,30 @@ static TopDownStream &topdown_stream() {
     return t;
 }
 
+// lazy residency of the input tree: a large iteration runs in node sub-ranges, and the gather of sub-range s + 1 (its own stream, one
+// CTA per SM: co-resident with the persistent contraction CTAs) runs BESIDE the contraction of sub-range s
+struct FetchStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t evFilled[kMaxSubRanges] = {}, evFetched[kMaxSubRanges] = {};
+    int grid = 0;
+};
+static FetchStream &fetch_stream() {
+    static FetchStream f;
+    if (!f.s) {
+        int least = 0, greatest = 0, dev = 0;
+        MRX_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        MRX_CUDA(cudaStreamCreateWithPriority(&f.s, cudaStreamNonBlocking, greatest));
+        for (int x = 0; x < kMaxSubRanges; x++) {
+            MRX_CUDA(cudaEventCreateWithFlags(&f.evFilled[x], cudaEventDisableTiming));
+            MRX_CUDA(cudaEventCreateWithFlags(&f.evFetched[x], cudaEventDisableTiming));
+        }
+        MRX_CUDA(cudaGetDevice(&dev));
+        MRX_CUDA(cudaDeviceGetAttribute(&f.grid, cudaDevAttrMultiProcessorCount, dev));
+        if (getenv("MRX_FETCH_GRID")) f.grid = std::max(1, atoi(getenv("MRX_FETCH_GRID"))); // development switch
+    }
+    return f;
+}
+
 // final node count of the last apply of this process: the next apply reserves its node store for that many nodes up front
 static size_t &nodeStoreHint() {
     static size_t h = 0;
@@ -205,7 +229,7 @@ struct Scratch {
     DevBuf<PrecTreeDev> precTreeTab;
     std::vector<std::unique_ptr<DevBuf<double>>> precVReal;
     // lazy residency of the input tree
-    DevBuf<int> fetchList, fetchCnt;
+    DevBuf<int> fetchList, fetchCnt, fetchSnap; // queue, its length, its length after each fill pass of a sub-range
     DevBuf<unsigned long long> fetchTotal;
 };
 
@@ -886,6 +910,9 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     Mailbox *mb = mailbox();
     // result streamed into the output tree's pinned host chunks while the loop runs (one GPU, convolution apply)
     const bool mirror = out.hostMirror && derivDir < 0 && out.host.coefsPinned() && !getenv("MRX_NO_MIRROR_STREAM");
+    // mirrored output, one GPU: iterations of at least 2 x subRangeMinTiles x 256 nodes run in up to subRangesMax sub-ranges
+    const int subRangesMax = getenv("MRX_SUB_RANGES") ? atoi(getenv("MRX_SUB_RANGES")) : 4;
+    const int subRangeMinTiles = getenv("MRX_SUB_MIN_TILES") ? std::max(1, atoi(getenv("MRX_SUB_MIN_TILES"))) : 4;
     MirrorStream *ms_ = mirror ? &mirror_stream() : nullptr;
     // shared mirror (mrx_tree_set_shared_host_mirror): host chunk c is downloaded by rank c % world over that rank's PCIe link
     const int shareW = (mirror && out.mirrorComm && out.mirrorComm == comm) ? world : 1, shareR = rank;
@@ -931,9 +958,14 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
 
     // input tree in pinned host memory (DeviceTree::partial): nodes are gathered over PCIe when the apply first reads them
     const bool lazy = inp.dev.partial;
+    // gather of sub-range s + 1 beside the contraction of sub-range s (k = 7 kernel: the one with unit sub-ranges)
+    const bool overlapFetch = lazy && K == 8 && !getenv("MRX_NO_FETCH_OVERLAP");
+    FetchStream *fs_ = overlapFetch ? &fetch_stream() : nullptr;
     if (lazy) {
-        scr.fetchCnt.reserve(2, false, st);
+        scr.fetchCnt.reserve(1, false, st);
+        scr.fetchSnap.reserve(kMaxSubRanges + 1, false, st);
         scr.fetchTotal.reserve(1, false, st);
+        MRX_CUDA(cudaMemsetAsync(scr.fetchSnap.p, 0, (kMaxSubRanges + 1) * sizeof(int), st));
         MRX_CUDA(cudaMemsetAsync(scr.fetchTotal.p, 0, sizeof(unsigned long long), st));
     }
     // sharded apply: the iteration whose rows are still travelling / not yet unpacked into the node store. The unpack runs on a
@@ -980,10 +1012,10 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
     };
     // TopDown(+=) step whose children are the nodes of the iteration that just reached the node store; `after` = the event that
     // says so. The mirror copies of those nodes follow it on the download stream (their scaling blocks are final then).
-    auto topdown_step = [&](cudaEvent_t after, int cnt, int buf) {
+    auto topdown_step = [&](cudaEvent_t after, int cnt, int buf, int pairOff = 0) {
         if (cnt <= 0) return after;
         MRX_CUDA(cudaStreamWaitEvent(td_->td, after, 0));
-        launch_transform(true, false, out.dev.coefs.p, scr.tdPairs[buf].p, cnt, K, filt, td_->td,
+        launch_transform(true, false, out.dev.coefs.p, scr.tdPairs[buf].p + 2 * (size_t)pairOff, cnt, K, filt, td_->td,
                          transform_fuses_norms(K) ? out.dev.norms.p : nullptr);
         MRX_CUDA(cudaEventRecord(td_->evDone, td_->td));
         MRX_CUDA(cudaEventRecord(td_->evBuf[buf], td_->td));
@@ -1303,7 +1335,8 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
                 scr.fetchList.reserve((size_t)8 * std::max(nNew, 1), false, st);
                 MRX_CUDA(cudaMemsetAsync(scr.fetchCnt.p, 0, sizeof(int), st));
                 launch_fetch_mark(scr.newParents.p, nNew, fRealN, inp.dev.resident.p, scr.fetchList.p, scr.fetchCnt.p, st);
-                launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, scr.fetchCnt.p, ncoef, scr.fetchTotal.p, st);
+                launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, nullptr, scr.fetchCnt.p, ncoef, scr.fetchTotal.p,
+                                   inp.dev.resident.p, st);
             }
             launch_gen_children(inp.dev.coefs.p, inp.dev.genCoefs.p, inp.dev.genNorms.p, fRealN, scr.genItems.p, nNew, K, filt, st);
             fTotal += 8 * nNew;
@@ -1389,6 +1422,28 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
         B.tileBaseUnit = scr.pTileBaseUnit.p;
         B.header = scr.header.p;
         B.queue = scr.queue.p;
+        // A large iteration runs in node sub-ranges (k = 7 kernel), boundaries on tiles of the block scan (256 nodes); same units,
+        // same unit order: bit-identical. Two uses. Host mirror on one GPU: contraction, reduce, TopDown step and download per
+        // sub-range, so that an iteration's first nodes travel while its last ones are still contracted (the two largest
+        // iterations come late: their download was the tail of the call). Input gathered from host memory: fill pass and gather
+        // per sub-range, the gather of sub-range s + 1 on its own stream beside the contraction of sub-range s; the first
+        // sub-range, whose gather nothing hides, is a small one. Work vectors after the first hold the children of the nodes
+        // that split, 8 per (parent, child0) pair.
+        const bool subMirror = mirror && world == 1 && K == 8;
+        int nSub = 1, subNode[kMaxSubRanges + 1] = {0};
+        if ((subMirror || overlapFetch) && iter > 0 && subRangesMax > 1) {
+            const int nTiles = (nL * 8 + kSubRangeBlocks - 1) / kSubRangeBlocks;
+            const int S = std::max(1, std::min(std::min(subRangesMax, kMaxSubRanges - 1), nTiles / subRangeMinTiles));
+            if (S > 1) {
+                const int first = overlapFetch ? std::max(1, nTiles / 16) : 0; // tiles of the small leading sub-range
+                nSub = 0;
+                if (first > 0) B.subTile[nSub++] = 0;
+                for (int x = 0; x < S; x++) B.subTile[nSub++] = first + (int)((long long)x * (nTiles - first) / S);
+                for (int x = 0; x < nSub; x++) subNode[x] = B.subTile[x] * (kSubRangeBlocks / 8);
+            }
+        }
+        subNode[nSub] = nL;
+        B.nSub = nSub;
         launch_pipe_screen(P, B, nNbr, st);
         launch_pipe_scan(P, B, nL, unitTuples, st);
         PipeHeader hdr;
@@ -1407,14 +1462,55 @@ static void run_apply_pipe(double prec, mrx_tree &out, mrx_oper &oper, mrx_tree 
             B.fetchList = scr.fetchList.p;
             B.fetchCnt = scr.fetchCnt.p;
         }
-        launch_pipe_fill(P, B, nNbr, nL, st);
-        if (lazy) launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, scr.fetchCnt.p, ncoef, scr.fetchTotal.p, st);
+        launch_pipe_units(B, nL, st);
+        const bool subFetch = overlapFetch && nSub > 1;
+        if (subFetch) {
+            // all fill passes up front (each leaves the queue length behind it in fetchSnap[x + 1]; fetchSnap[0] stays 0), the
+            // gathers behind them on the gather stream; the contraction of sub-range x below waits for gather x only
+            for (int x = 0; x < nSub; x++) {
+                B.fillLo = subNode[x];
+                B.fillHi = subNode[x + 1];
+                launch_pipe_fill(P, B, nNbr, st);
+                MRX_CUDA(cudaMemcpyAsync(scr.fetchSnap.p + x + 1, scr.fetchCnt.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                MRX_CUDA(cudaEventRecord(fs_->evFilled[x], st));
+                MRX_CUDA(cudaStreamWaitEvent(fs_->s, fs_->evFilled[x], 0));
+                launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, scr.fetchSnap.p + x, scr.fetchSnap.p + x + 1, ncoef,
+                                   scr.fetchTotal.p, inp.dev.resident.p, fs_->s, fs_->grid);
+                MRX_CUDA(cudaEventRecord(fs_->evFetched[x], fs_->s));
+            }
+        } else {
+            B.fillLo = 0;
+            B.fillHi = std::max(nL, 0) + 1;
+            launch_pipe_fill(P, B, nNbr, st);
+            if (lazy)
+                launch_fetch_nodes(inp.dev.coefs.p, inp.dev.chunkTab.p, scr.fetchList.p, nullptr, scr.fetchCnt.p, ncoef, scr.fetchTotal.p,
+                                   inp.dev.resident.p, st);
+        }
         MRX_CUDA(cudaEventRecord(ev2, st));
-        launch_pipe_contract(P, B, hdr.nUnits, st);
+        double *normsMine = normsBuf.p + (size_t)rank * rowsPerRank * 8;
+        if (nSub > 1) {
+            for (int x = 0; x < nSub; x++) {
+                if (subFetch) MRX_CUDA(cudaStreamWaitEvent(st, fs_->evFetched[x], 0));
+                const int uEnd = (x + 1 < nSub) ? hdr.subUnit[x + 1] : hdr.nUnits;
+                launch_pipe_contract(P, B, uEnd, st, hdr.subUnit[x]);
+                if (world > 1) continue; // sharded: one reduce into the staging rows below
+                launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, subNode[x + 1], st, nullptr, subNode[x]);
+                if (fold || mirror) {
+                    cudaEvent_t ready = fold ? td_->evReady : ms_->evReduced;
+                    MRX_CUDA(cudaEventRecord(ready, st));
+                    const int cntN = subNode[x + 1] - subNode[x];
+                    if (fold) ready = topdown_step(ready, std::min(tdCount - subNode[x] / 8, cntN / 8), tdBuf, subNode[x] / 8);
+                    if (mirror) mirror_copy(ready, nRealDev - nG + subNode[x], cntN, nRealDev);
+                }
+            }
+        } else {
+            launch_pipe_contract(P, B, hdr.nUnits, st);
+        }
         MRX_CUDA(cudaEventRecord(ev3, st));
         // partial sums in unit order + calcNorms of the output nodes (ConvolutionCalculator.cpp:270-272)
-        double *normsMine = normsBuf.p + (size_t)rank * rowsPerRank * 8;
-        if (world == 1) {
+        if (world == 1 && nSub > 1) {
+            MRX_CUDA(cudaEventRecord(ev1, st));
+        } else if (world == 1) {
             launch_pipe_reduce(P, B, scr.gslots.p, out.dev.norms.p, normsMine, nL, st);
             MRX_CUDA(cudaEventRecord(ev1, st));
             if (fold || mirror) {

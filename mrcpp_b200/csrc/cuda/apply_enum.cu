@@ -302,16 +302,21 @@ __global__ void __launch_bounds__(256) fetch_mark_kernel(const int *__restrict__
     const int node = list[i >> 3]; // generation reads all eight blocks of a real leaf
     if (node < nRealF) {
         const int blk = node * 8 + (i & 7);
-        if (atomicExch(&resident[blk], 1) == 0) fetchList[atomicAdd(fetchCnt, 1)] = blk;
+        if (atomicCAS(&resident[blk], 0, 1) == 0) fetchList[atomicAdd(fetchCnt, 1)] = blk;
     }
 }
 
+// resident[blk]: 0 not in HBM, 1 queued (pipe_fill / fetch_mark), 2 arrived (diagnostic: consumers are ordered behind the gather by
+// stream events). Entries [*begin, *end) of the queue: the gather of one node sub-range of an iteration runs on its own stream
+// beside the contraction of the sub-range before it (apply.cu), with one CTA per SM (30 registers: fits next to the three
+// persistent contraction CTAs of an SM; measured beside the contraction: 51 GB/s, profiles/r02w).
 __global__ void __launch_bounds__(256) fetch_nodes_kernel(double *__restrict__ coefs, const double *const *__restrict__ chunkTab,
-                                                          const int *__restrict__ list, const int *__restrict__ cnt, int ncoef,
-                                                          unsigned long long *__restrict__ total) {
-    const int n = *cnt;
+                                                          const int *__restrict__ list, const int *__restrict__ begin,
+                                                          const int *__restrict__ end, int ncoef, unsigned long long *__restrict__ total,
+                                                          int *__restrict__ resident) {
+    const int i0 = begin ? *begin : 0, n = *end;
     const int Kd = ncoef / 8;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    for (int i = i0 + blockIdx.x; i < n; i += gridDim.x) {
         const int blk = list[i], slot = blk >> 3, c = blk & 7;
         const double *src = chunkTab[slot >> 6] + (size_t)(slot & 63) * ncoef + (size_t)c * Kd;
         double *dst = coefs + (size_t)slot * ncoef + (size_t)c * Kd;
@@ -322,8 +327,9 @@ __global__ void __launch_bounds__(256) fetch_nodes_kernel(double *__restrict__ c
         } else {
             for (int e = threadIdx.x; e < Kd; e += 256) dst[e] = src[e];
         }
+        if (threadIdx.x == 0) resident[blk] = 2;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *total += (unsigned long long)n; // blocks fetched
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total += (unsigned long long)(n - i0); // blocks fetched
 }
 
 // host mirror of an apply output (mrx_tree_set_host_mirror): what the streamed per-iteration copies could not take yet -- the
@@ -364,9 +370,9 @@ void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *f
     launch_counter()++;
 }
 
-void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *cnt, int ncoef, unsigned long long *total,
-                        cudaStream_t st) {
-    fetch_nodes_kernel<<<1184, 256, 0, st>>>(coefs, chunkTab, list, cnt, ncoef, total);
+void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *begin, const int *end, int ncoef,
+                        unsigned long long *total, int *resident, cudaStream_t st, int grid) {
+    fetch_nodes_kernel<<<grid > 0 ? grid : 1184, 256, 0, st>>>(coefs, chunkTab, list, begin, end, ncoef, total, resident);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

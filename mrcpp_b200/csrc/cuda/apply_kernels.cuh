@@ -129,8 +129,10 @@ void launch_fetch_mark(const int *list, int n, int nRealF, int *resident, int *f
 /// host mirror of an apply output: blocks of the listed nodes from the node store straight into the pinned host chunks (64 nodes
 /// each). items[i] = slot, bit 31 set: all eight blocks (branch node), clear: the scaling block only
 void launch_push_nodes(const double *coefs, double *const *chunkTab, const int *items, int n, int ncoef, cudaStream_t st);
-void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *cnt, int ncoef, unsigned long long *total,
-                        cudaStream_t st);
+/// gathers queue entries [*begin, *end) (begin == nullptr: from 0); resident[blk] becomes 2 when block blk has arrived;
+/// grid > 0: that many CTAs (a gather that runs beside a contraction kernel: one CTA per SM is co-resident), 0: the default
+void launch_fetch_nodes(double *coefs, const double *const *chunkTab, const int *list, const int *begin, const int *end, int ncoef,
+                        unsigned long long *total, int *resident, cudaStream_t st, int grid = 0);
 
 // ---- work-list pipeline (apply_pipeline.cu): screen -> scan -> fill -> contract -> reduce -------------------
 /// one surviving (g, f, ft, gt, term) tuple: indices of the source block and of the three 1-D operator blocks
@@ -143,10 +145,13 @@ struct UnitDesc {
     unsigned t0; // first tuple in the iteration's tuple list
     int cnt;
 };
+constexpr int kMaxSubRanges = 8;
+constexpr int kSubRangeBlocks = 2048; // sub-range boundaries fall on tiles of the block scan (256 output nodes)
 struct PipeHeader {
     unsigned long long totalTuples;
     int nUnits;
     int U; // tuples per unit
+    int subUnit[kMaxSubRanges]; // first unit of sub-range s (s >= nSub: nUnits)
 };
 struct PipeBuffers {
     unsigned long long *masks; // [nCand] surviving (gt,ft) bits per candidate
@@ -167,17 +172,24 @@ struct PipeBuffers {
     int *resident;
     int *fetchList;
     int *fetchCnt;
+    int fillLo, fillHi; // pipe_fill pass: nodes [fillLo, fillHi) of the rank's items
+    // contraction / reduce / download of one iteration in nSub node sub-ranges: sub-range s starts at block tile subTile[s]
+    int nSub;
+    int subTile[kMaxSubRanges];
 };
 bool pipe_supports_order(int K); // orders with a work-list contraction kernel (K = k + 1)
 int pipe_contract_warps(); // persistent warps of the contraction kernel on this device
 void launch_pipe_screen(const ApplyParams &P, const PipeBuffers &B, int nNbr, cudaStream_t st);
 void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int unitHint, cudaStream_t st);
-void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st);
-void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st);
+void launch_pipe_units(const PipeBuffers &B, int nG, cudaStream_t st); // global block offsets + unit descriptors
+/// tuple records (and the gather queue of a lazily resident input) of the nodes [B.fillLo, B.fillHi)
+void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, cudaStream_t st);
+/// units [uBase, nUnits) of the iteration (uBase != 0: k = 7 kernel only)
+void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st, int uBase = 0);
 /// gslots / gNormsW: the rank's nodes in local order. stageRows != nullptr: output blocks go to the rank's rows of the
-/// exchange staging buffer (row j = local node j) instead of the node store
+/// exchange staging buffer (row j = local node j) instead of the node store; nodes [gBase, nG) of the rank's items
 void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
-                        cudaStream_t st, double *stageRows = nullptr);
+                        cudaStream_t st, double *stageRows = nullptr, int gBase = 0);
 // ---- distribution of a work vector over the ranks of a sharded apply: block-cyclic, blocks of B consecutive items (B = 1: plain
 //      cyclic). Consecutive items are siblings and spatial neighbours: they cost about the same (so dealing them out balances the
 //      tuple counts) and they read nearly the same input nodes (so keeping a few together lets a rank gather fewer of them from

@@ -213,6 +213,7 @@ __device__ unsigned long long block_excl_scan(unsigned long long v, unsigned lon
 // Unit size: fixed, so that the summation order of a block does not depend on how much other work the launch holds
 // (results are bit-identical for any number of ranks sharing the work vector).
 constexpr int kBlockTile = 2048; // 256 threads x 8 blocks
+static_assert(kBlockTile == kSubRangeBlocks, "sub-range boundaries are block-scan tiles");
 constexpr int kTupBits = 36;      // packed tile sums: low 36 bits tuples (an iteration holds < 2^32), high 28 bits units
 
 __global__ void __launch_bounds__(256) pipe_blockscan_tiles_kernel(PipeBuffers B, int nBlocks, int U) {
@@ -260,12 +261,17 @@ __global__ void __launch_bounds__(1024) pipe_blockscan_top_kernel(PipeBuffers B,
         runT += t & ((1ull << kTupBits) - 1);
         runU += t >> kTupBits;
     }
+    __syncthreads(); // tileBaseUnit is complete
     if (tid == 0) {
         B.blockTupOff[nBlocks] = (unsigned)totT;
         B.blockUnitOff[nBlocks] = (int)totU;
         B.header->totalTuples = totT;
         B.header->nUnits = (int)totU;
         B.header->U = U;
+        // contraction in sub-ranges (host mirror: an iteration's first nodes go down while its last ones are still contracted):
+        // first unit of the block tiles the host picked as boundaries
+        for (int s = 0; s < kMaxSubRanges; s++)
+            B.header->subUnit[s] = (s < B.nSub && B.subTile[s] < nTiles) ? B.tileBaseUnit[B.subTile[s]] : (int)totU;
     }
 }
 
@@ -298,6 +304,7 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= nNbr) return;
     const NbrEntry nb = P.nbr[w];
+    if (nb.g < B.fillLo || nb.g >= B.fillHi) return; // this pass fills (and queues the gather of) the nodes [fillLo, fillHi)
     const GDesc g = P.gdesc[nb.g];
     const DepthInfo di = P.depthInfo[g.depth];
     const int *coff = P.candOff + di.cubeOff;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(256) pipe_fill_kernel(ApplyParams P, PipeBuffe
         const unsigned used = __reduce_or_sync(0xffffffffu, ftUsed);
         if (lane < 8 && ((used >> lane) & 1u)) {
             const int blk = nb.fslot * 8 + lane;
-            if (atomicExch(&B.resident[blk], 1) == 0) B.fetchList[atomicAdd(B.fetchCnt, 1)] = blk;
+            if (atomicCAS(&B.resident[blk], 0, 1) == 0) B.fetchList[atomicAdd(B.fetchCnt, 1)] = blk;
         }
     }
 }
@@ -391,7 +398,7 @@ __device__ __forceinline__ OpFrag load_frags(const double *__restrict__ mats, co
     return f;
 }
 
-__global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_contract_kernel(ApplyParams P, PipeBuffers B, int nUnits) {
+__global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_contract_kernel(ApplyParams P, PipeBuffers B, int uBase, int nUnits) {
     extern __shared__ __align__(16) double tiles[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, q = lane & 3;
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kContractWarps * 32, kContractCtasPerSm) pipe_
 
     for (;;) {
         int u = 0;
-        if (lane == 0) u = atomicAdd(B.queue, 1);
+        if (lane == 0) u = uBase + atomicAdd(B.queue, 1); // units [uBase, nUnits) of the iteration
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= nUnits) break;
         const UnitDesc ud = B.units[u];
@@ -909,10 +916,10 @@ template <int K> void launch_contract_coop(const ApplyParams &P, const PipeBuffe
 // stageRows != nullptr (sharded apply): the block goes to row (blk >> 3) of the rank's segment of the exchange staging buffer
 // instead of the node store; the whole iteration is unpacked into the node store after the peers' rows have arrived
 __global__ void __launch_bounds__(256) pipe_reduce_kernel(PipeBuffers B, const int *__restrict__ gslots, double *__restrict__ gCoefs,
-                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int nBlocks, int Kd,
-                                                          double *__restrict__ stageRows) {
+                                                          double *__restrict__ gNorms, double *__restrict__ gNormsW, int blkBase, int nBlocks,
+                                                          int Kd, double *__restrict__ stageRows) {
     const int lane = threadIdx.x & 31;
-    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int blk = blkBase + blockIdx.x * 8 + (threadIdx.x >> 5); // blocks [blkBase, nBlocks) of the rank's items
     if (blk >= nBlocks) return;
     const int u0 = B.blockUnitOff[blk], u1 = B.blockUnitOff[blk + 1];
     const int slot = gslots[blk >> 3], gt = blk & 7;
@@ -1017,10 +1024,16 @@ void launch_pipe_scan(const ApplyParams &P, const PipeBuffers &B, int nG, int un
     launch_counter()++;
 }
 
-void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, int nG, cudaStream_t st) {
+void launch_pipe_units(const PipeBuffers &B, int nG, cudaStream_t st) {
     const int nBlocks = nG * 8;
-    if (nBlocks > 0) pipe_units_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, nBlocks);
-    launch_counter()++;
+    if (nBlocks > 0) {
+        pipe_units_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, nBlocks);
+        launch_counter()++;
+    }
+    MRX_CUDA(cudaGetLastError());
+}
+
+void launch_pipe_fill(const ApplyParams &P, const PipeBuffers &B, int nNbr, cudaStream_t st) {
     if (nNbr > 0) {
         pipe_fill_kernel<<<(nNbr + 7) / 8, 256, 0, st>>>(P, B, nNbr);
         launch_counter()++;
@@ -1080,15 +1093,16 @@ template <int K> void launch_contract_pad(const ApplyParams &P, const PipeBuffer
 
 bool pipe_supports_order(int K) { return K >= 4 && K <= 12; }
 
-void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st) {
-    if (nUnits <= 0) return;
+void launch_pipe_contract(const ApplyParams &P, const PipeBuffers &B, int nUnits, cudaStream_t st, int uBase) {
+    if (nUnits - uBase <= 0) return;
+    if (uBase != 0 && P.K != 8) MRX_ABORT("pipeline contraction: unit sub-ranges are implemented for the k = 7 kernel only");
     MRX_CUDA(cudaMemsetAsync(B.queue, 0, sizeof(int), st));
     static const bool useFma = getenv("MRX_FMA") != nullptr; // development switch: FMA instead of padded-DMMA contraction
     static const bool warpPrivate = getenv("MRX_PAD_WARP") != nullptr; // development switch: one warp per unit instead of one CTA
     static const bool noStack = getenv("MRX_NO_STACK") != nullptr;     // development switch: unstacked first stage
     if (P.K == 8) {
-        const int grid = std::min(pipe_contract_grid(), (nUnits + kContractWarps - 1) / kContractWarps);
-        pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, nUnits);
+        const int grid = std::min(pipe_contract_grid(), (nUnits - uBase + kContractWarps - 1) / kContractWarps);
+        pipe_contract_kernel<<<grid, kContractWarps * 32, kContractWarps * kTileDoubles * sizeof(double), st>>>(P, B, uBase, nUnits);
     } else if (P.K == 4) {
         launch_contract_fma<4>(P, B, nUnits, st);
     } else if (P.K == 6) {
@@ -1136,10 +1150,11 @@ void launch_unpack_nodes(double *coefs, const double *stage, const int *gslotsAl
 }
 
 void launch_pipe_reduce(const ApplyParams &P, const PipeBuffers &B, const int *gslots, double *gNorms, double *gNormsW, int nG,
-                        cudaStream_t st, double *stageRows) {
-    const int nBlocks = nG * 8;
-    if (nBlocks <= 0) return;
-    pipe_reduce_kernel<<<(nBlocks + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, nBlocks, P.K * P.K * P.K, stageRows);
+                        cudaStream_t st, double *stageRows, int gBase) {
+    const int nBlocks = nG * 8, blkBase = gBase * 8;
+    if (nBlocks - blkBase <= 0) return;
+    pipe_reduce_kernel<<<(nBlocks - blkBase + 7) / 8, 256, 0, st>>>(B, gslots, P.gCoefs, gNorms, gNormsW, blkBase, nBlocks, P.K * P.K * P.K,
+                                                                     stageRows);
     MRX_CUDA(cudaGetLastError());
     launch_counter()++;
 }

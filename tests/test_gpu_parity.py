@@ -487,6 +487,41 @@ def test_full_size_coulomb_energy(gpu):
     assert f.getNNodes() > 40000 and s1.f_applied > 2e7  # really the full-size case
 
 
+def test_end_to_end_path_sub_ranges_and_gather_beside_the_contraction(gpu, monkeypatch):
+    """The two overlaps of the end-to-end path at k = 7: (1) the gather of a host-resident input's blocks runs on its
+    own stream BESIDE the contraction kernel, which acquires each block's arrival flag before reading it; (2) with a mirrored
+    output a large iteration is contracted / reduced / sent down in node sub-ranges. Both must leave every bit of the result
+    as the plain apply on a resident input gives it, in every combination, and on the partially resident tree afterwards."""
+    mw, orc = gpu
+    k, prec = 7, 1e-6
+    mra = world(mw, k)
+    func = gaussians(40, 2026)
+    P = mw.PoissonOperator(mra, prec)
+    f = mw.FunctionTree(mra)
+    mw.project(prec, f, func, device=True)
+    ref = mw.FunctionTree(mra)
+    s0 = mw.apply(prec, ref, P, f)
+    R = ref.to_arrays()
+    f.to_arrays()  # host copy of the input
+    monkeypatch.setenv("MRX_SUB_MIN_TILES", "1")  # iterations of >= 512 nodes run in sub-ranges of >= 256 nodes
+    monkeypatch.setenv("MRX_SUB_RANGES", "8")
+    for overlap, subs in ((True, True), (False, True), (True, False)):
+        if overlap: monkeypatch.delenv("MRX_NO_FETCH_OVERLAP", raising=False)
+        else: monkeypatch.setenv("MRX_NO_FETCH_OVERLAP", "1")
+        monkeypatch.setenv("MRX_SUB_RANGES", "8" if subs else "1")
+        f.drop_device()
+        g = mw.FunctionTree(mra)
+        g.set_host_mirror(True)
+        s1 = mw.apply(prec, g, P, f)
+        assert s1.f_applied == s0.f_applied and 0 < s1.h2d_bytes < f.nbytes()
+        G = g.to_arrays()
+        assert np.array_equal(G["transl"], R["transl"]) and np.array_equal(G["coefs"], R["coefs"]) and np.array_equal(G["norms"], R["norms"])
+        g2 = mw.FunctionTree(mra)  # partially resident input, plain output
+        s2 = mw.apply(prec, g2, P, f)
+        assert s2.h2d_bytes <= s1.h2d_bytes and np.array_equal(g2.to_arrays()["coefs"], R["coefs"])
+    assert max(int(x) for x in np.bincount(R["scale"] - R["scale"].min())) >= 512  # the sub-range path did run
+
+
 @pytest.mark.parametrize("k,n,prec", [(7, 6, 1e-5), (5, 3, 1e-4), (9, 2, 1e-4)])
 def test_apply_with_host_mirror(gpu, k, n, prec):
     """mrx_tree_set_host_mirror: the apply streams its result into the output tree's pinned host chunks while it runs (wavelet

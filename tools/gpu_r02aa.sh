@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, GPU call aa (1 GPU): gather of sub-range s + 1 beside the contraction of sub-range s (plain contraction kernel; the
+# flag-waiting kernel of calls t-z is gone); tests, clean A/B of the end-to-end arm
+out=gpurun_out; tag=r02aa; mkdir -p $out
+python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "mirror or host_memory or end_to_end or full_size" > $out/${tag}_tests.txt 2>&1
+tail -3 $out/${tag}_tests.txt
+MRX_PROFILE=1 MRX_E2E_MIRROR_ONLY=1 MRX_E2E_KEEP=1 timeout 100 python tools/prof_e2e.py 1000 > $out/${tag}_e2e_default.txt 2>&1
+echo "default: $(grep 'mirror True\|partially' $out/${tag}_e2e_default.txt | tail -4 | tr '\n' ' ')"
+grep "iter [4-7] nG" $out/${tag}_e2e_default.txt | sed -n 9,12p | cut -c1-150
+grep "device_apply ms\|run_apply_pipe ms\|push of the" $out/${tag}_e2e_default.txt | sed -n 13,15p
+timeout 300 python bench.py --no-cpu-baseline > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+MRX_NO_FETCH_OVERLAP=1 timeout 300 python bench.py --no-cpu-baseline > $out/${tag}_bench_n1_nooverlap.json 2> $out/${tag}_bench_n1_nooverlap.err
+MRX_SUB_RANGES=7 MRX_SUB_MIN_TILES=2 timeout 300 python bench.py --no-cpu-baseline > $out/${tag}_bench_n1_sub7.json 2> $out/${tag}_bench_n1_sub7.err
+python -c "
+import json
+for f in ('','_nooverlap','_sub7'):
+    d=json.load(open('$out/${tag}_bench_n1'+f+'.json')); print(f, d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['frac'])
+"
