@@ -639,33 +639,57 @@ __global__ void __launch_bounds__(32 * NW) transformK_pipe_kernel(double *__rest
     } // nodes of this CTA
 }
 
-template <int K, int MODE>
-void launch_transformK(double *coefs, const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *pairs, int cnt,
-                       const double *filters, int overwrite, double *norms, cudaStream_t st) {
-    // warps of the persistent variant: K = 6 has 18 column tiles per pass, dealt evenly to 9 warps; K = 10 measured faster with 8
-    // warps (7 rounds of tiles) than with 10 (5 exact rounds): 1.26 vs 1.32 ms per BottomUp pass on the C2 tree
-    constexpr int NW = (K == 6) ? 9 : 8;
-    static bool conf = false;
-    static int pipeGrid = 0; // persistent, double-buffered variant where two node buffers fit (MRX_NO_TPIPE=1: one node per CTA)
-    if (!conf) {
-        MRX_CUDA(cudaFuncSetAttribute(transformK_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TLayout<K>::bytes));
+// persistent variant with NW warps per CTA: grid (0 where two node buffers do not fit or MRX_NO_TPIPE=1), configured once
+template <int K, int MODE, int NW> int transformK_pipe_grid() {
+    static int grid = -1;
+    if (grid < 0) {
+        grid = 0;
         if (2 * TLayout<K>::bytes <= 220 * 1024 && !getenv("MRX_NO_TPIPE")) {
             int dev = 0, sms = 0, perSm = 0;
             MRX_CUDA(cudaGetDevice(&dev));
             MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             MRX_CUDA(cudaFuncSetAttribute(transformK_pipe_kernel<K, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TLayout<K>::bytes)));
             MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, transformK_pipe_kernel<K, MODE, NW>, 32 * NW, 2 * TLayout<K>::bytes));
-            pipeGrid = sms * std::max(perSm, 1);
+            grid = sms * std::max(perSm, 1);
         }
-        conf = true;
     }
+    return grid;
+}
+
+template <int K, int MODE, int NW>
+bool try_transformK_pipe(double *coefs, const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *pairs, int cnt,
+                         const double *filters, int overwrite, double *norms, cudaStream_t st) {
+    const int pipeGrid = transformK_pipe_grid<K, MODE, NW>();
     // enough nodes per CTA for the prefetch to pay; TopDown(overwrite) at small K is dominated by zeroing the children's wavelet
     // blocks, which a one-node CTA overlaps better with its neighbours on the SM
     if (pipeGrid > 0 && cnt >= 2 * pipeGrid && !(MODE == 0 && overwrite && K < 10)) {
         transformK_pipe_kernel<K, MODE, NW><<<pipeGrid, 32 * NW, 2 * TLayout<K>::bytes, st>>>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs,
                                                                                             filters, overwrite, norms, cnt);
-        return;
+        return true;
     }
+    return false;
+}
+
+template <int K, int MODE>
+void launch_transformK(double *coefs, const double *realCoefs, double *genCoefs, double *genNorms, int nReal, const int *pairs, int cnt,
+                       const double *filters, int overwrite, double *norms, cudaStream_t st) {
+    // warps of the persistent variant: K = 6 has 18 column tiles per pass, dealt evenly to 9 warps; K = 10 measured faster with 8
+    // warps (7 rounds of tiles) than with 10 (5 exact rounds): 1.26 vs 1.32 ms per BottomUp pass on the C2 tree. ncu of the 8-warp
+    // CTA at K = 10 (profiles/r02ag_ncu_transformK_pipe.txt): DMMA sub-pipe 50 % active, DRAM 18-25 %, 2 warps per scheduler, largest
+    // stalls wait + math-pipe throttle: 16 warps per CTA at K = 10 (4 per scheduler): BottomUp 1.257 -> 1.185 ms; 17 warps (3 rounds of the 50 tiles) 1.231, 25 warps (2 exact rounds) 1.239 (profiles/r02ai). MRX_TPIPE_WARPS=8: the 8-warp CTA
+    constexpr int NW = (K == 6) ? 9 : 8;
+    static bool conf = false;
+    static int wide = 0;
+    if (!conf) {
+        MRX_CUDA(cudaFuncSetAttribute(transformK_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TLayout<K>::bytes));
+        wide = (K == 10) ? (getenv("MRX_TPIPE_WARPS") ? atoi(getenv("MRX_TPIPE_WARPS")) : 16) : 0;
+        conf = true;
+    }
+    constexpr int W16 = (K == 10) ? 16 : NW;
+    bool done;
+    if (K == 10 && wide == 16) done = try_transformK_pipe<K, MODE, W16>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st);
+    else done = try_transformK_pipe<K, MODE, NW>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, cnt, filters, overwrite, norms, st);
+    if (done) return;
     transformK_kernel<K, MODE><<<cnt, 256, TLayout<K>::bytes, st>>>(coefs, realCoefs, genCoefs, genNorms, nReal, pairs, filters, overwrite, norms);
 }
 
