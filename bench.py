@@ -565,6 +565,28 @@ def main():
                 "value": Sa.nodes / (Sa.ms * 1e-3), "unit": "nodes/s", "ms_per_step": Sa.ms / args.steps,
                 "e2e_value": Se.nodes / (Se.ms * 1e-3), "e2e_ms_per_step": Se.ms / args.steps,
                 "output_nodes_per_step": Sa.nodes // args.steps, "tuples_per_step": Sa.tuples // args.steps}
+            # ... and what a binding pays that converts PER CALL instead of keeping handles: the caller's arrays
+            # (pageable memory) -> mrx_tree_from_arrays (copy into pinned chunks) -> apply -> mrx_tree_to_arrays; host wall clock
+            try:
+                arrs = [t_.to_arrays() for t_ in sft]
+                tw = []
+                for _ in range(args.steps + 1):
+                    t0 = time.perf_counter()
+                    for a in arrs:
+                        fin = mw.FunctionTree.from_arrays(mra, a["scale"], a["transl"], a["parent"], a["child0"], a["coefs"])
+                        out = mw.FunctionTree(mra)
+                        out.set_host_mirror(True)
+                        mw.apply(prec, out, P, fin)
+                        res = out.to_arrays()
+                        del fin, out
+                    tw.append(time.perf_counter() - t0)
+                line["same_workload_as_reference_arm"]["from_caller_arrays"] = {
+                    "ms_per_step": 1e3 * sum(tw[1:]) / args.steps, "clock": "host wall clock (the copies are host work)",
+                    "input_bytes": int(sum(a["coefs"].nbytes for a in arrs)), "output_bytes": int(res["coefs"].nbytes),
+                    "path": "mrx_tree_from_arrays + mrx_apply (mirrored output) + mrx_tree_to_arrays, per call"}
+                del arrs, res
+            except Exception as e:  # noqa: BLE001
+                line["same_workload_as_reference_arm"]["from_caller_arrays"] = {"failed": repr(e)[:200]}
             del sft
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only (all host cores free)
             line["cpu_baseline"] = cpu_baseline(args, mw, mra, P)

@@ -488,10 +488,11 @@ def test_full_size_coulomb_energy(gpu):
 
 
 def test_end_to_end_path_sub_ranges_and_gather_beside_the_contraction(gpu, monkeypatch):
-    """The two overlaps of the end-to-end path at k = 7: (1) the gather of a host-resident input's blocks runs on its
-    own stream BESIDE the contraction kernel, which acquires each block's arrival flag before reading it; (2) with a mirrored
-    output a large iteration is contracted / reduced / sent down in node sub-ranges. Both must leave every bit of the result
-    as the plain apply on a resident input gives it, in every combination, and on the partially resident tree afterwards."""
+    """The two overlaps of the end-to-end path at k = 7: a large iteration runs in node sub-ranges; (1) with a
+    host-resident input the fill pass and the gather of its blocks are per sub-range, the gather of sub-range s + 1 on its own stream
+    beside the contraction of sub-range s; (2) with a mirrored output contraction / reduce / TopDown step / download are per
+    sub-range. Both must leave every bit of the result as the plain apply on a resident input gives it, in every combination,
+    and on the partially resident tree afterwards."""
     mw, orc = gpu
     k, prec = 7, 1e-6
     mra = world(mw, k)
