@@ -64,7 +64,7 @@ struct DeviceTree {
     double topoMaxNorm = 0.0;
     // lazy residency of an apply INPUT whose coefficients live in pinned host memory: storage for every node is
     // allocated, but only the nodes the apply actually reads are fetched over PCIe (by a gather kernel reading the host
-    // chunks directly); resident[8 n + c] = 1 once block c of node n is in HBM. `partial` trees are not devValid: every other consumer
+    // chunks directly); resident[8 n + c]: 0 block c of node n not in HBM, 1 queued for the gather, 2 arrived. `partial` trees are not devValid: every other consumer
     // completes the upload first (tree_upload).
     DevBuf<int> resident;
     DevBuf<const double *> chunkTab; // host chunk base pointers (64 nodes each), device-readable
