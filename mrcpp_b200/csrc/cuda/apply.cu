@@ -107,10 +107,22 @@ template <typename T> static void read_back(T *dst, const T *devSrc, T *mbSlot, 
     if (useMailbox) {
         const unsigned seq = ++mailbox_seq();
         launch_publish(devSrc, mailbox_dev(mbSlot), (int)(sizeof(T) / 4), static_cast<unsigned *>(mailbox_dev(mbFlag)), seq, st);
+        // the publish kernel sits at the end of a dependent chain: if a kernel before it faults, the flag never comes. The spin looks
+        // at the stream now and then and fails loudly instead of hanging the process
+        unsigned long long spins = 0;
+        const double tSpin = now_ms();
         while (*mbFlag != seq) {
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
+            if ((++spins & ((1ull << 22) - 1)) == 0) {
+                const cudaError_t e = cudaStreamQuery(st);
+                if (e != cudaSuccess && e != cudaErrorNotReady) {
+                    std::fprintf(stderr, "mrx abort: apply: the device reported '%s' while the host waited for a read-back\n", cudaGetErrorString(e));
+                    std::abort();
+                }
+                if (now_ms() - tSpin > 120000.0) MRX_ABORT("apply: a read-back did not arrive within two minutes");
+            }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         std::memcpy(dst, const_cast<const T *>(mbSlot), sizeof(T));
